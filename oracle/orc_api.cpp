@@ -1,0 +1,608 @@
+// ORACLE — test infrastructure only (see orc_math.hpp header). PARITY UNPINNED.
+//
+// orc_api.cpp — C entry points of the CPU oracle. The solver-level ones mirror include/smpc.h
+// one to one (orc_X has the signature of smpc_X without the device argument) so that tests drive the
+// oracle and the CUDA library with the same call sequence. The unit-level ones expose single
+// functions for finite-difference and known-answer checks.
+#include "orc_solver.hpp"
+#include <cstdio>
+#include <memory>
+#include <string>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+struct orc_ctx
+{
+  int batch;
+  std::vector<std::unique_ptr<Solver>> inst;
+};
+
+static thread_local std::string g_err;
+#define ORC_TRY try {
+#define ORC_CATCH                                                                                                      \
+  }                                                                                                                    \
+  catch (const std::exception & e)                                                                                     \
+  {                                                                                                                    \
+    g_err = e.what();                                                                                                  \
+    return SMPC_ERR_INVALID;                                                                                           \
+  }                                                                                                                    \
+  return SMPC_OK;
+
+static int check_range(orc_ctx * c, int first, int n)
+{
+  if (!c || first < 0 || n < 0 || first + n > c->batch)
+  {
+    g_err = "instance range out of bounds";
+    return SMPC_ERR_INVALID;
+  }
+  return 0;
+}
+
+extern "C" {
+
+const char * orc_last_error(void) { return g_err.c_str(); }
+
+void orc_default_solver_opts(smpc_solver_opts * o)
+{
+  o->tol = 1e-4;
+  o->mu_init = 1e-8;
+  o->max_iters = 1;
+  o->max_al_iters = 100;
+  o->prim_alpha = 0.1;
+  o->prim_beta = 0.9;
+  o->dual_alpha = 1.0;
+  o->dual_beta = 1.0;
+  o->mu_update_factor = 0.01;
+  o->mu_lower_bound = 1e-8;
+  o->inner_tol0 = 1.0;
+  o->prim_tol0 = 1.0;
+  o->reg_init = 1e-9;
+  o->reg_min = 1e-10;
+  o->reg_max = 1e9;
+  o->reg_inc_k = 10.0;
+  o->reg_inc_critical = 100.0;
+  o->reg_dec_k = 1.0 / 3.0;
+  o->ls_armijo_c1 = 1e-4;
+  o->ls_alpha_min = 1e-7;
+  o->ls_contraction = 0.5;
+  o->ls_avg_eta = 0.85;
+  o->ls_max_steps = 20;
+}
+
+int orc_problem_dims(const smpc_model_desc * m, const smpc_ocp_desc * o, int * nx, int * ndx, int * nu)
+{
+  ORC_TRY
+  smpc_ocp_desc oc = *o;
+  int fs = oc.force_size;
+  if (oc.kind == SMPC_OCP_KINODYNAMICS)
+  {
+    *nx = m->nq + m->nv;
+    *ndx = 2 * m->nv;
+    *nu = m->nv - 6 + fs * m->nfeet;
+  }
+  else if (oc.kind == SMPC_OCP_FULLDYNAMICS)
+  {
+    *nx = m->nq + m->nv;
+    *ndx = 2 * m->nv;
+    *nu = m->nv - 6;
+  }
+  else
+  {
+    *nx = *ndx = 9;
+    *nu = fs * m->nfeet;
+  }
+  ORC_CATCH
+}
+
+int orc_create(orc_ctx ** out, int batch, const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_solver_opts * opts)
+{
+  ORC_TRY
+  if (batch < 1)
+    throw std::runtime_error("batch must be >= 1");
+  auto c = new orc_ctx;
+  c->batch = batch;
+  for (int i = 0; i < batch; i++)
+    c->inst.emplace_back(new Solver(*model, *ocp, *opts));
+  *out = c;
+  ORC_CATCH
+}
+void orc_destroy(orc_ctx * c) { delete c; }
+
+int orc_set_slots(orc_ctx * c, int first, int n, const smpc_slot * slots)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    for (int t = 0; t < s.N; t++)
+      s.slots[t] = slots[(size_t)i * s.N + t];
+  }
+  return SMPC_OK;
+}
+int orc_set_slot(orc_ctx * c, int first, int n, int t, const smpc_slot * slots)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (t < 0 || t >= c->inst[0]->N)
+  {
+    g_err = "Stage index exceeds stage vector size";
+    return SMPC_ERR_INVALID;
+  }
+  for (int i = 0; i < n; i++)
+    c->inst[first + i]->slots[t] = slots[i];
+  return SMPC_OK;
+}
+int orc_set_foot_refs(orc_ctx * c, int first, int n, const double * foot_ref)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    const int nk = s.P.nk;
+    for (int t = 0; t < s.N; t++)
+      for (int f = 0; f < nk; f++)
+        memcpy(s.slots[t].foot_ref[f], foot_ref + (((size_t)i * s.N + t) * nk + f) * 12, 12 * sizeof(double));
+  }
+  return SMPC_OK;
+}
+int orc_set_terminal(orc_ctx * c, int first, int n, const smpc_terminal * term)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+    c->inst[first + i]->term = term[i];
+  return SMPC_OK;
+}
+int orc_cycle(orc_ctx * c, int first, int n, const smpc_slot * tail)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+    c->inst[first + i]->cycle(tail[i]);
+  return SMPC_OK;
+}
+int orc_set_warmstart(orc_ctx * c, int first, int n, const double * xs, const double * us)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    for (int t = 0; t <= s.N; t++)
+      s.xs[t].assign(xs + ((size_t)i * (s.N + 1) + t) * s.nx, xs + ((size_t)i * (s.N + 1) + t + 1) * s.nx);
+    for (int t = 0; t < s.N; t++)
+      s.us[t].assign(us + ((size_t)i * s.N + t) * s.nu, us + ((size_t)i * s.N + t + 1) * s.nu);
+  }
+  return SMPC_OK;
+}
+// reference src/mpc.cpp:201-207: xs.erase(begin); xs[0] = x0 (done by solve); xs.push_back(xs.back()); same for us
+int orc_shift_warmstart(orc_ctx * c, int first, int n)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    std::rotate(s.xs.begin(), s.xs.begin() + 1, s.xs.end());
+    s.xs[s.N] = s.xs[s.N - 1];
+    std::rotate(s.us.begin(), s.us.begin() + 1, s.us.end());
+    s.us[s.N - 1] = s.us[s.N - 2];
+  }
+  return SMPC_OK;
+}
+int orc_solve(orc_ctx * c, const double * x0, int max_iters)
+{
+  ORC_TRY
+  std::string err;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < c->batch; i++)
+  {
+    try
+    {
+      Solver & s = *c->inst[i];
+      s.run(x0 + (size_t)i * s.nx, max_iters);
+    }
+    catch (const std::exception & e)
+    {
+#pragma omp critical
+      err = e.what();
+    }
+  }
+  if (!err.empty())
+    throw std::runtime_error(err);
+  ORC_CATCH
+}
+int orc_get_results(orc_ctx * c, int first, int n, double * xs, double * us, double * Ks, double * ks)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    const int N = s.N, nx = s.nx, nu = s.nu, ndx = s.ndx;
+    if (xs)
+      for (int t = 0; t <= N; t++)
+        memcpy(xs + ((size_t)i * (N + 1) + t) * nx, s.xs[t].data(), nx * sizeof(double));
+    if (us)
+      for (int t = 0; t < N; t++)
+        memcpy(us + ((size_t)i * N + t) * nu, s.us[t].data(), nu * sizeof(double));
+    if ((Ks || ks) && (int)s.sol.size() == N + 1)
+      for (int t = 0; t < N; t++)
+      {
+        if (Ks)
+          memcpy(Ks + ((size_t)i * N + t) * nu * ndx, s.sol[t].K.d.data(), (size_t)nu * ndx * sizeof(double));
+        if (ks)
+          memcpy(ks + ((size_t)i * N + t) * nu, s.sol[t].k.data(), nu * sizeof(double));
+      }
+  }
+  return SMPC_OK;
+}
+int orc_get_head(orc_ctx * c, int first, int n, double * x1, double * u0, double * u1, double * K0)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    if (x1)
+      memcpy(x1 + (size_t)i * s.nx, s.xs[1].data(), s.nx * sizeof(double));
+    if (u0)
+      memcpy(u0 + (size_t)i * s.nu, s.us[0].data(), s.nu * sizeof(double));
+    if (u1)
+      memcpy(u1 + (size_t)i * s.nu, s.us[1].data(), s.nu * sizeof(double));
+    if (K0 && !s.sol.empty())
+      memcpy(K0 + (size_t)i * s.nu * s.ndx, s.sol[0].K.d.data(), (size_t)s.nu * s.ndx * sizeof(double));
+  }
+  return SMPC_OK;
+}
+int orc_get_info(orc_ctx * c, int first, int n, smpc_solve_info * info)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+    info[i] = c->inst[first + i]->info;
+  return SMPC_OK;
+}
+int orc_get_ncmax(orc_ctx * c) { return c->inst[0]->ncmax; }
+int orc_get_duals(orc_ctx * c, int first, int n, double * vs, double * lams)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    const int N = s.N;
+    if (vs)
+      for (int t = 0; t <= N; t++)
+        memcpy(vs + ((size_t)i * (N + 1) + t) * s.ncmax, s.vs[t].data(), s.ncmax * sizeof(double));
+    if (lams)
+      for (int t = 0; t <= N; t++)
+        memcpy(lams + ((size_t)i * (N + 1) + t) * s.ndx, s.lams[t].data(), s.ndx * sizeof(double));
+  }
+  return SMPC_OK;
+}
+int orc_get_xdot(orc_ctx * c, int first, int n, int t, double * xdot)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (t < 0 || t >= c->inst[0]->N)
+  {
+    g_err = "Stage index exceeds stage vector size";
+    return SMPC_ERR_INVALID;
+  }
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    memcpy(xdot + (size_t)i * s.ndx, s.xdots[t].data(), s.ndx * sizeof(double));
+  }
+  return SMPC_OK;
+}
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// ------------------------------- unit-level entry points -------------------------------------
+
+// LQ knot t of instance `inst` as assembled by the last solve: row-major dense blocks; any pointer may be NULL.
+// sizes: Q ndx*ndx, S ndx*nu, R nu*nu, q ndx, r nu, A ndx*ndx, B ndx*nu, f ndx, C ncmax*ndx, D ncmax*nu, d ncmax
+int orc_get_knot(
+  orc_ctx * c, int inst, int t, int * nc, double * Q, double * S, double * R, double * q, double * r, double * A, double * B,
+  double * f, double * C, double * D, double * d)
+{
+  if (check_range(c, inst, 1))
+    return SMPC_ERR_INVALID;
+  Solver & s = *c->inst[inst];
+  if (t < 0 || t > s.N || (int)s.knots.size() != s.N + 1)
+  {
+    g_err = "no LQ problem assembled / bad index";
+    return SMPC_ERR_INVALID;
+  }
+  const Knot & k = s.knots[t];
+  auto cp = [](double * dst, const std::vector<double> & v) {
+    if (dst && !v.empty())
+      memcpy(dst, v.data(), v.size() * sizeof(double));
+  };
+  if (nc)
+    *nc = k.nc;
+  cp(Q, k.Q.d);
+  cp(q, k.q);
+  cp(C, k.C.d);
+  cp(d, k.d);
+  if (t < s.N)
+  {
+    cp(S, k.S.d);
+    cp(R, k.R.d);
+    cp(r, k.r);
+    cp(A, k.A.d);
+    cp(B, k.B.d);
+    cp(f, k.f);
+    cp(D, k.D.d);
+  }
+  return SMPC_OK;
+}
+// value function / gains of node t from the last backward sweep
+int orc_get_stage_sol(orc_ctx * c, int inst, int t, double * P, double * p, double * K, double * k, double * Z, double * z)
+{
+  if (check_range(c, inst, 1))
+    return SMPC_ERR_INVALID;
+  Solver & s = *c->inst[inst];
+  if (t < 0 || t > s.N || (int)s.sol.size() != s.N + 1)
+  {
+    g_err = "no Riccati solution / bad index";
+    return SMPC_ERR_INVALID;
+  }
+  const StageSol & so = s.sol[t];
+  auto cp = [](double * dst, const std::vector<double> & v) {
+    if (dst && !v.empty())
+      memcpy(dst, v.data(), v.size() * sizeof(double));
+  };
+  cp(P, so.P.d);
+  cp(p, so.p);
+  cp(K, so.K.d);
+  cp(k, so.k);
+  cp(Z, so.Z.d);
+  cp(z, so.z);
+  return SMPC_OK;
+}
+// Newton step of the last iteration: dxs [N+1][ndx], dus [N][nu]
+int orc_get_step(orc_ctx * c, int inst, double * dxs, double * dus)
+{
+  if (check_range(c, inst, 1))
+    return SMPC_ERR_INVALID;
+  Solver & s = *c->inst[inst];
+  if ((int)s.dxs.size() != s.N + 1)
+  {
+    g_err = "no step computed";
+    return SMPC_ERR_INVALID;
+  }
+  for (int t = 0; t <= s.N; t++)
+    if (dxs)
+      memcpy(dxs + (size_t)t * s.ndx, s.dxs[t].data(), s.ndx * sizeof(double));
+  for (int t = 0; t < s.N; t++)
+    if (dus)
+      memcpy(dus + (size_t)t * s.nu, s.dus[t].data(), s.nu * sizeof(double));
+  return SMPC_OK;
+}
+
+// One stage evaluation (values, and derivatives if derivs != 0). Outputs (any may be NULL):
+// xnext nx, xdot ndx, cost 1, c ncmax, ctype ncmax, A ndx*ndx, B ndx*nu, lx ndx, lu nu, lxx, lxu, luu, Cx nc*ndx, Cu nc*nu
+int orc_stage_eval(
+  const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const double * x, const double * u,
+  int derivs, int * nc, double * xnext, double * xdot, double * cost, double * cval, int * ctype, double * A, double * B,
+  double * lx, double * lu, double * lxx, double * lxu, double * luu, double * Cx, double * Cu)
+{
+  ORC_TRY
+  Problem P(*model, *ocp);
+  StageEval e;
+  stage_eval(P, *slot, x, u, derivs != 0, e);
+  auto cp = [](double * dst, const std::vector<double> & v) {
+    if (dst && !v.empty())
+      memcpy(dst, v.data(), v.size() * sizeof(double));
+  };
+  if (nc)
+    *nc = e.nc;
+  cp(xnext, e.xnext);
+  cp(xdot, e.xdot);
+  if (cost)
+    *cost = e.cost;
+  cp(cval, e.c);
+  if (ctype)
+    for (int i = 0; i < e.nc; i++)
+      ctype[i] = e.ctype[i];
+  if (derivs)
+  {
+    cp(A, e.A.d);
+    cp(B, e.B.d);
+    cp(lx, e.lx);
+    cp(lu, e.lu);
+    cp(lxx, e.lxx.d);
+    cp(lxu, e.lxu.d);
+    cp(luu, e.luu.d);
+    cp(Cx, e.Cx.d);
+    cp(Cu, e.Cu.d);
+  }
+  ORC_CATCH
+}
+int orc_terminal_eval(
+  const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_terminal * term, const double * x, int derivs, int * nc,
+  double * cost, double * cval, double * lx, double * lxx, double * Cx)
+{
+  ORC_TRY
+  Problem P(*model, *ocp);
+  StageEval e;
+  terminal_eval(P, *term, x, derivs != 0, e);
+  if (nc)
+    *nc = e.nc;
+  if (cost)
+    *cost = e.cost;
+  if (cval && e.nc)
+    memcpy(cval, e.c.data(), e.nc * sizeof(double));
+  if (derivs)
+  {
+    if (lx)
+      memcpy(lx, e.lx.data(), e.lx.size() * sizeof(double));
+    if (lxx)
+      memcpy(lxx, e.lxx.d.data(), e.lxx.d.size() * sizeof(double));
+    if (Cx && e.nc)
+      memcpy(Cx, e.Cx.d.data(), e.Cx.d.size() * sizeof(double));
+  }
+  ORC_CATCH
+}
+
+// x (+) dx and x1 (-) x0 of the OCP's state space
+int orc_state_integrate(const smpc_model_desc * model, const smpc_ocp_desc * ocp, const double * x, const double * dx, double * xo)
+{
+  ORC_TRY
+  Problem P(*model, *ocp);
+  state_integrate(P, x, dx, xo);
+  ORC_CATCH
+}
+int orc_state_difference(const smpc_model_desc * model, const smpc_ocp_desc * ocp, const double * x0, const double * x1, double * d)
+{
+  ORC_TRY
+  Problem P(*model, *ocp);
+  state_difference(P, x0, x1, d);
+  ORC_CATCH
+}
+
+// Kinematics + centroidal quantities at (q, v, a): what RobotDataHandler::updateInternalData exposes
+// (reference src/robot-handler.cpp:114-127,142-149) plus the centroidal derivatives.
+// outputs (any may be NULL): foot_pose nfeet*12, footref_pose nfeet*12, base_pose 12, com 3, hg 6, hdg 6,
+// Ag 6*nv, dh_dq 6*nv, dhd_dq 6*nv, dhd_dv 6*nv, Jcom 3*nv
+int orc_kinematics(
+  const smpc_model_desc * model, const double * q, const double * v, const double * a, double * foot_pose,
+  double * footref_pose, double * base_pose, double * com, double * hg, double * hdg, double * Ag, double * dh_dq,
+  double * dhd_dq, double * dhd_dv, double * Jcom)
+{
+  ORC_TRY
+  Model m(*model);
+  Kin k;
+  centroidal_pass(m, q, v, a, true, k);
+  auto pose = [](double * dst, const SE3 & M) {
+    memcpy(dst, M.R, 9 * sizeof(double));
+    memcpy(dst + 9, M.p, 3 * sizeof(double));
+  };
+  for (int f = 0; f < m.nfeet; f++)
+  {
+    if (foot_pose)
+      pose(foot_pose + 12 * f, k.oMf[f]);
+    if (footref_pose)
+      pose(footref_pose + 12 * f, k.oMfref[f]);
+  }
+  if (base_pose)
+    pose(base_pose, k.oMbase);
+  if (com)
+    memcpy(com, k.com, sizeof(k.com));
+  if (hg)
+    memcpy(hg, k.hg, sizeof(k.hg));
+  if (hdg)
+    memcpy(hdg, k.hdg, sizeof(k.hdg));
+  auto cp = [](double * dst, const Mat & M) {
+    if (dst)
+      memcpy(dst, M.d.data(), M.d.size() * sizeof(double));
+  };
+  cp(Ag, k.Ag);
+  cp(dh_dq, k.dh_dq);
+  cp(dhd_dq, k.dhd_dq);
+  cp(dhd_dv, k.dhd_dv);
+  cp(Jcom, k.Jcom);
+  ORC_CATCH
+}
+
+// SE(3) helpers for known-answer tests
+void orc_exp6(const double * nu, double * pose12)
+{
+  SE3 M = exp6(nu);
+  memcpy(pose12, M.R, 9 * sizeof(double));
+  memcpy(pose12 + 9, M.p, 3 * sizeof(double));
+}
+void orc_log6(const double * pose12, double * nu)
+{
+  SE3 M;
+  memcpy(M.R, pose12, 9 * sizeof(double));
+  memcpy(M.p, pose12 + 9, 3 * sizeof(double));
+  log6(M, nu);
+}
+void orc_Jexp6(const double * nu, double * J) { Jexp6(nu, J); }
+void orc_Jlog6(const double * nu, double * J) { Jlog6(nu, J); }
+
+// Standalone proximal Riccati solve on caller-supplied dense knots (all stages share nc = ncs, terminal nc = nct).
+// Layout per stage: Q S R q r A B f C D d (row-major, sizes as in orc_get_knot with ncmax = ncs); terminal: Q q C d.
+// Outputs: K [N][nu][ndx], k [N][nu], P0 ndx*ndx, p0 ndx, dxs [N+1][ndx], dus [N][nu]
+int orc_riccati(
+  int N, int ndx, int nu, int ncs, int nct, double mudyn, double mueq, const double * stages, const double * terminal,
+  double * K, double * k, double * P0, double * p0, double * dxs_o, double * dus_o)
+{
+  ORC_TRY
+  std::vector<Knot> knots(N + 1);
+  const double * p = stages;
+  auto take = [&](Mat & M, int r, int c) {
+    M.resize(r, c);
+    memcpy(M.d.data(), p, sizeof(double) * r * c);
+    p += (size_t)r * c;
+  };
+  auto takev = [&](Vec & v, int n) {
+    v.assign(p, p + n);
+    p += n;
+  };
+  for (int t = 0; t < N; t++)
+  {
+    Knot & kn = knots[t];
+    kn.nc = ncs;
+    take(kn.Q, ndx, ndx);
+    take(kn.S, ndx, nu);
+    take(kn.R, nu, nu);
+    takev(kn.q, ndx);
+    takev(kn.r, nu);
+    take(kn.A, ndx, ndx);
+    take(kn.B, ndx, nu);
+    takev(kn.f, ndx);
+    take(kn.C, ncs, ndx);
+    take(kn.D, ncs, nu);
+    takev(kn.d, ncs);
+  }
+  p = terminal;
+  {
+    Knot & kn = knots[N];
+    kn.nc = nct;
+    take(kn.Q, ndx, ndx);
+    takev(kn.q, ndx);
+    take(kn.C, nct, ndx);
+    takev(kn.d, nct);
+  }
+  std::vector<StageSol> sol;
+  RiccatiStats st = riccati_backward(knots, ndx, nu, mudyn, mueq, sol);
+  std::vector<Vec> dxs, dus, vnew, lnew;
+  riccati_forward(knots, sol, ndx, nu, mudyn, dxs, dus, vnew, lnew);
+  for (int t = 0; t < N; t++)
+  {
+    if (K)
+      memcpy(K + (size_t)t * nu * ndx, sol[t].K.d.data(), sizeof(double) * nu * ndx);
+    if (k)
+      memcpy(k + (size_t)t * nu, sol[t].k.data(), sizeof(double) * nu);
+    if (dus_o)
+      memcpy(dus_o + (size_t)t * nu, dus[t].data(), sizeof(double) * nu);
+  }
+  for (int t = 0; t <= N; t++)
+    if (dxs_o)
+      memcpy(dxs_o + (size_t)t * ndx, dxs[t].data(), sizeof(double) * ndx);
+  if (P0)
+    memcpy(P0, sol[0].P.d.data(), sizeof(double) * ndx * ndx);
+  if (p0)
+    memcpy(p0, sol[0].p.data(), sizeof(double) * ndx);
+  if (!st.ok)
+    throw std::runtime_error("riccati: non-positive pivot");
+  ORC_CATCH
+}
+
+} // extern "C"

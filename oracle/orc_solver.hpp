@@ -1,0 +1,818 @@
+// ORACLE — test infrastructure only (see orc_math.hpp header). PARITY UNPINNED.
+//
+// orc_solver.hpp — the ProxDDP iteration that reference src/mpc.cpp:85,212 calls
+// (aligator::SolverProxDDPTpl<double>::run, [UPSTREAM] aligator 0.16.0, pixi.lock:11) restated from
+// the published algorithm (Jallet et al., "ProxDDP: Proximal Constrained Trajectory Optimization",
+// 2023; Jallet et al., "Parallel and Proximal Constrained LQ methods for Real-Time Nonlinear MPC",
+// RSS 2024) with the settings the reference selects (src/mpc.cpp:43-53): LINEAR rollout,
+// force_initial_condition, serial proximal Riccati, Gauss-Newton Hessians, nonmonotone linesearch.
+// Every constant that comes from upstream defaults is in smpc_solver_opts.
+//
+// The exact operation order of the Riccati recursion below is the CANONICAL order: the CUDA
+// kernels follow it term by term (ascending-k fused multiply-adds, structural zeros skipped) so
+// that the two agree to rounding.
+#pragma once
+#include "orc_ocp.hpp"
+#include <algorithm>
+
+namespace orc
+{
+
+  struct Knot
+  {
+    int nc = 0;
+    Mat Q, S, R, A, B, C, D;
+    Vec q, r, f, d;
+  };
+  struct StageSol
+  {
+    Mat K, Z, P, Pt; // du = k + K dx ; nu+ = z + Z dx ; cost-to-go ; P~ of the NEXT node
+    Vec k, z, p, pt;
+  };
+
+  // in-place Cholesky (lower) of an n x n row-major SPD matrix; returns false if a pivot is <= 0
+  inline bool chol_lower(Mat & M, int n)
+  {
+    for (int j = 0; j < n; j++)
+    {
+      double s = M(j, j);
+      for (int k = 0; k < j; k++)
+        s = std::fma(-M(j, k), M(j, k), s);
+      if (!(s > 0))
+        return false;
+      double l = std::sqrt(s);
+      M(j, j) = l;
+      double inv = 1.0 / l;
+      for (int i = j + 1; i < n; i++)
+      {
+        double t = M(i, j);
+        for (int k = 0; k < j; k++)
+          t = std::fma(-M(i, k), M(j, k), t);
+        M(i, j) = t * inv;
+      }
+    }
+    return true;
+  }
+  // X <- L^-1 X  (L lower n x n, X n x m), column by column
+  inline void solve_lower(const Mat & L, int n, Mat & X, int m)
+  {
+    for (int c = 0; c < m; c++)
+      for (int i = 0; i < n; i++)
+      {
+        double s = X(i, c);
+        for (int k = 0; k < i; k++)
+          s = std::fma(-L(i, k), X(k, c), s);
+        X(i, c) = s / L(i, i);
+      }
+  }
+  // X <- L^-T X
+  inline void solve_lower_T(const Mat & L, int n, Mat & X, int m)
+  {
+    for (int c = 0; c < m; c++)
+      for (int i = n - 1; i >= 0; i--)
+      {
+        double s = X(i, c);
+        for (int k = n - 1; k > i; k--)
+          s = std::fma(-L(k, i), X(k, c), s);
+        X(i, c) = s / L(i, i);
+      }
+  }
+
+  struct RiccatiStats
+  {
+    bool ok = true;
+  };
+
+  // Backward sweep of the proximal Riccati recursion (gar::ProximalRiccatiSolver::backward(mudyn, mueq)).
+  // knots[0..N-1] are stages, knots[N] the terminal node (Q,q,C,d only).
+  inline RiccatiStats riccati_backward(const std::vector<Knot> & knots, int ndx, int nu, double mudyn, double mueq, std::vector<StageSol> & sol)
+  {
+    RiccatiStats st;
+    const int N = (int)knots.size() - 1;
+    sol.resize(N + 1);
+    const double inv_mu = 1.0 / mueq;
+    // terminal: nu_N = (d + C dx)/mu ; P = Q + C^T Z ; p = q + C^T z
+    {
+      const Knot & kn = knots[N];
+      StageSol & s = sol[N];
+      const int nc = kn.nc;
+      s.Z.resize(nc, ndx);
+      s.z.assign(nc, 0);
+      for (int i = 0; i < nc; i++)
+      {
+        s.z[i] = kn.d[i] * inv_mu;
+        for (int j = 0; j < ndx; j++)
+          s.Z(i, j) = kn.C(i, j) * inv_mu;
+      }
+      s.P = kn.Q;
+      s.p = kn.q;
+      for (int a = 0; a < ndx; a++)
+      {
+        for (int b = 0; b < ndx; b++)
+        {
+          double acc = s.P(a, b);
+          for (int i = 0; i < nc; i++)
+            acc = std::fma(kn.C(i, a), s.Z(i, b), acc);
+          s.P(a, b) = acc;
+        }
+        double acc = s.p[a];
+        for (int i = 0; i < nc; i++)
+          acc = std::fma(kn.C(i, a), s.z[i], acc);
+        s.p[a] = acc;
+      }
+    }
+    for (int t = N - 1; t >= 0; t--)
+    {
+      const Knot & kn = knots[t];
+      const StageSol & nx = sol[t + 1];
+      StageSol & s = sol[t];
+      const int nc = kn.nc;
+      // 1. P~ = (I + mudyn P+)^-1 P+ , p~ = (I + mudyn P+)^-1 p+
+      s.Pt = nx.P;
+      s.pt = nx.p;
+      if (mudyn > 0)
+      {
+        Mat M(ndx, ndx);
+        for (int a = 0; a < ndx; a++)
+          for (int b = 0; b < ndx; b++)
+            M(a, b) = mudyn * nx.P(a, b) + (a == b ? 1.0 : 0.0);
+        if (!chol_lower(M, ndx))
+          st.ok = false;
+        Mat rhs(ndx, ndx + 1);
+        for (int a = 0; a < ndx; a++)
+        {
+          for (int b = 0; b < ndx; b++)
+            rhs(a, b) = nx.P(a, b);
+          rhs(a, ndx) = nx.p[a];
+        }
+        solve_lower(M, ndx, rhs, ndx + 1);
+        solve_lower_T(M, ndx, rhs, ndx + 1);
+        for (int a = 0; a < ndx; a++)
+        {
+          for (int b = 0; b < ndx; b++)
+            s.Pt(a, b) = rhs(a, b);
+          s.pt[a] = rhs(a, ndx);
+        }
+      }
+      // 2. w = P~ f + p~
+      Vec w(ndx);
+      for (int a = 0; a < ndx; a++)
+      {
+        double acc = s.pt[a];
+        for (int b = 0; b < ndx; b++)
+          acc = std::fma(s.Pt(a, b), kn.f[b], acc);
+        w[a] = acc;
+      }
+      // 3. PA = P~ A, PB = P~ B
+      Mat PA(ndx, ndx), PB(ndx, nu);
+      for (int a = 0; a < ndx; a++)
+      {
+        for (int b = 0; b < ndx; b++)
+        {
+          double acc = 0;
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(s.Pt(a, k), kn.A(k, b), acc);
+          PA(a, b) = acc;
+        }
+        for (int b = 0; b < nu; b++)
+        {
+          double acc = 0;
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(s.Pt(a, k), kn.B(k, b), acc);
+          PB(a, b) = acc;
+        }
+      }
+      // 4. Qh = Q + A^T PA ; Sh = S + A^T PB ; Rh = R + B^T PB ; qh = q + A^T w ; rh = r + B^T w
+      Mat Qh(ndx, ndx), Sh(ndx, nu), Rh(nu, nu);
+      Vec qh(ndx), rh(nu);
+      for (int a = 0; a < ndx; a++)
+      {
+        for (int b = 0; b < ndx; b++)
+        {
+          double acc = kn.Q(a, b);
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(kn.A(k, a), PA(k, b), acc);
+          Qh(a, b) = acc;
+        }
+        for (int b = 0; b < nu; b++)
+        {
+          double acc = kn.S(a, b);
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(kn.A(k, a), PB(k, b), acc);
+          Sh(a, b) = acc;
+        }
+        double acc = kn.q[a];
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(kn.A(k, a), w[k], acc);
+        qh[a] = acc;
+      }
+      for (int a = 0; a < nu; a++)
+      {
+        for (int b = 0; b < nu; b++)
+        {
+          double acc = kn.R(a, b);
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(kn.B(k, a), PB(k, b), acc);
+          Rh(a, b) = acc;
+        }
+        double acc = kn.r[a];
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(kn.B(k, a), w[k], acc);
+        rh[a] = acc;
+      }
+      // 5. quasi-definite KKT  [[Rh, D^T],[D, -mu I]] [u; nu] = -[[rh, Sh^T],[d, C]]  by block LDL^T:
+      //    Rh = L L^T ; Y = L^-1 [rh Sh^T] ; W = L^-1 D^T ; Sigma = mu I + W^T W = Ls Ls^T ;
+      //    nu = Sigma^-1 ([d C] - W^T Y) ; u = -L^-T (Y + W nu)
+      if (!chol_lower(Rh, nu))
+        st.ok = false;
+      Mat Y(nu, ndx + 1);
+      for (int a = 0; a < nu; a++)
+      {
+        Y(a, 0) = rh[a];
+        for (int b = 0; b < ndx; b++)
+          Y(a, 1 + b) = Sh(b, a);
+      }
+      solve_lower(Rh, nu, Y, ndx + 1);
+      Mat G(nc, ndx + 1); // multiplier gains: col 0 = z, cols 1.. = Z
+      if (nc > 0)
+      {
+        Mat W(nu, nc);
+        for (int a = 0; a < nu; a++)
+          for (int i = 0; i < nc; i++)
+            W(a, i) = kn.D(i, a);
+        solve_lower(Rh, nu, W, nc);
+        Mat Sg(nc, nc);
+        for (int i = 0; i < nc; i++)
+          for (int j = 0; j <= i; j++)
+          {
+            double acc = (i == j) ? mueq : 0.0;
+            for (int k = 0; k < nu; k++)
+              acc = std::fma(W(k, i), W(k, j), acc);
+            Sg(i, j) = acc;
+            Sg(j, i) = acc;
+          }
+        if (!chol_lower(Sg, nc))
+          st.ok = false;
+        for (int i = 0; i < nc; i++)
+          for (int c = 0; c < ndx + 1; c++)
+          {
+            double acc = (c == 0) ? kn.d[i] : kn.C(i, c - 1);
+            for (int k = 0; k < nu; k++)
+              acc = std::fma(-W(k, i), Y(k, c), acc);
+            G(i, c) = acc;
+          }
+        solve_lower(Sg, nc, G, ndx + 1);
+        solve_lower_T(Sg, nc, G, ndx + 1);
+        for (int a = 0; a < nu; a++)
+          for (int c = 0; c < ndx + 1; c++)
+          {
+            double acc = Y(a, c);
+            for (int i = 0; i < nc; i++)
+              acc = std::fma(W(a, i), G(i, c), acc);
+            Y(a, c) = acc;
+          }
+      }
+      solve_lower_T(Rh, nu, Y, ndx + 1);
+      s.K.resize(nu, ndx);
+      s.k.assign(nu, 0);
+      s.Z.resize(nc, ndx);
+      s.z.assign(nc, 0);
+      for (int a = 0; a < nu; a++)
+      {
+        s.k[a] = -Y(a, 0);
+        for (int b = 0; b < ndx; b++)
+          s.K(a, b) = -Y(a, 1 + b);
+      }
+      for (int i = 0; i < nc; i++)
+      {
+        s.z[i] = G(i, 0);
+        for (int b = 0; b < ndx; b++)
+          s.Z(i, b) = G(i, 1 + b);
+      }
+      // 6. P = Qh + Sh K + C^T Z (symmetrised) ; p = qh + Sh k + C^T z
+      s.P.resize(ndx, ndx);
+      s.p.assign(ndx, 0);
+      for (int a = 0; a < ndx; a++)
+      {
+        for (int b = 0; b < ndx; b++)
+        {
+          double acc = Qh(a, b);
+          for (int k = 0; k < nu; k++)
+            acc = std::fma(Sh(a, k), s.K(k, b), acc);
+          for (int i = 0; i < nc; i++)
+            acc = std::fma(kn.C(i, a), s.Z(i, b), acc);
+          s.P(a, b) = acc;
+        }
+        double acc = qh[a];
+        for (int k = 0; k < nu; k++)
+          acc = std::fma(Sh(a, k), s.k[k], acc);
+        for (int i = 0; i < nc; i++)
+          acc = std::fma(kn.C(i, a), s.z[i], acc);
+        s.p[a] = acc;
+      }
+      for (int a = 0; a < ndx; a++)
+        for (int b = 0; b < a; b++)
+        {
+          double m = 0.5 * (s.P(a, b) + s.P(b, a));
+          s.P(a, b) = m;
+          s.P(b, a) = m;
+        }
+    }
+    return st;
+  }
+
+  // Forward sweep: dx0 given (0 with force_initial_condition). Outputs steps dx, du and the TOTAL new
+  // multipliers nu+ (per stage, plus terminal) and lambda+ (lam[0] initial condition, lam[t+1] dynamics t).
+  inline void riccati_forward(
+    const std::vector<Knot> & knots, const std::vector<StageSol> & sol, int ndx, int nu, double mudyn, std::vector<Vec> & dxs,
+    std::vector<Vec> & dus, std::vector<Vec> & vnew, std::vector<Vec> & lnew)
+  {
+    const int N = (int)knots.size() - 1;
+    dxs.assign(N + 1, Vec(ndx, 0.0));
+    dus.assign(N, Vec(nu, 0.0));
+    vnew.resize(N + 1);
+    lnew.assign(N + 1, Vec(ndx, 0.0));
+    // lambda_0 = P_0 dx_0 + p_0
+    for (int a = 0; a < ndx; a++)
+    {
+      double acc = sol[0].p[a];
+      for (int b = 0; b < ndx; b++)
+        acc = std::fma(sol[0].P(a, b), dxs[0][b], acc);
+      lnew[0][a] = acc;
+    }
+    for (int t = 0; t < N; t++)
+    {
+      const Knot & kn = knots[t];
+      const StageSol & s = sol[t];
+      const Vec & dx = dxs[t];
+      for (int a = 0; a < nu; a++)
+      {
+        double acc = s.k[a];
+        for (int b = 0; b < ndx; b++)
+          acc = std::fma(s.K(a, b), dx[b], acc);
+        dus[t][a] = acc;
+      }
+      vnew[t].assign(kn.nc, 0.0);
+      for (int i = 0; i < kn.nc; i++)
+      {
+        double acc = s.z[i];
+        for (int b = 0; b < ndx; b++)
+          acc = std::fma(s.Z(i, b), dx[b], acc);
+        vnew[t][i] = acc;
+      }
+      Vec y(ndx);
+      for (int a = 0; a < ndx; a++)
+      {
+        double acc = kn.f[a];
+        for (int b = 0; b < ndx; b++)
+          acc = std::fma(kn.A(a, b), dx[b], acc);
+        for (int b = 0; b < nu; b++)
+          acc = std::fma(kn.B(a, b), dus[t][b], acc);
+        y[a] = acc;
+      }
+      for (int a = 0; a < ndx; a++)
+      {
+        double acc = s.pt[a];
+        for (int b = 0; b < ndx; b++)
+          acc = std::fma(s.Pt(a, b), y[b], acc);
+        lnew[t + 1][a] = acc;
+        dxs[t + 1][a] = y[a] - mudyn * acc;
+      }
+    }
+    const Knot & kn = knots[N];
+    vnew[N].assign(kn.nc, 0.0);
+    for (int i = 0; i < kn.nc; i++)
+    {
+      double acc = sol[N].z[i];
+      for (int b = 0; b < ndx; b++)
+        acc = std::fma(sol[N].Z(i, b), dxs[N][b], acc);
+      vnew[N][i] = acc;
+    }
+  }
+
+  // normal-cone projection of the shifted constraint value z (per row); returns projection, sets active
+  inline double ncone_proj(int type, double z, double lo, double hi, bool & active)
+  {
+    if (type == CSTR_EQ)
+    {
+      active = true;
+      return z;
+    }
+    if (type == CSTR_NEG)
+    {
+      active = z > 0;
+      return active ? z : 0.0;
+    }
+    // box
+    if (z < lo)
+    {
+      active = true;
+      return z - lo;
+    }
+    if (z > hi)
+    {
+      active = true;
+      return z - hi;
+    }
+    active = false;
+    return 0.0;
+  }
+
+  inline double inf_norm(const Vec & v)
+  {
+    double m = 0;
+    for (double e : v)
+      m = std::max(m, std::fabs(e));
+    return m;
+  }
+
+  struct Solver
+  {
+    Problem P;
+    smpc_solver_opts opt;
+    int N, nx, ndx, nu, ncmax;
+    // problem data
+    std::vector<smpc_slot> slots;
+    smpc_terminal term;
+    // iterate (persistent between solves: aligator results_ / workspace_)
+    std::vector<Vec> xs, us, vs, lams;
+    std::vector<Vec> prev_vs, prev_lams;
+    double mu, preg, inner_tol, prim_tol;
+    double ls_mov_avg = 0, ls_avg_weight = 0;
+    // last linearisation / solution
+    std::vector<StageEval> ev;
+    std::vector<Knot> knots;
+    std::vector<StageSol> sol;
+    std::vector<Vec> dxs, dus, vnew, lnew;
+    std::vector<Vec> xdots; // getStateDerivative
+    smpc_solve_info info;
+
+    Solver(const smpc_model_desc & md, const smpc_ocp_desc & od, const smpc_solver_opts & so) : P(md, od), opt(so)
+    {
+      N = P.N;
+      nx = P.nx;
+      ndx = P.ndx;
+      nu = P.nu;
+      ncmax = std::max(P.max_nc(), P.term_nc());
+      slots.resize(N);
+      for (auto & s : slots)
+        memset(&s, 0, sizeof(s));
+      memset(&term, 0, sizeof(term));
+      xs.assign(N + 1, Vec(nx, 0.0));
+      us.assign(N, Vec(nu, 0.0));
+      vs.assign(N + 1, Vec(ncmax, 0.0));
+      lams.assign(N + 1, Vec(ndx, 0.0));
+      prev_vs = vs;
+      prev_lams = lams;
+      xdots.assign(N, Vec(ndx, 0.0));
+      mu = opt.mu_init;
+      preg = opt.reg_init;
+      memset(&info, 0, sizeof(info));
+    }
+
+    // replaceStageCircular + cycleProblem: drop stage 0, append a new tail stage; duals follow.
+    void cycle(const smpc_slot & tail)
+    {
+      std::rotate(slots.begin(), slots.begin() + 1, slots.end());
+      slots[N - 1] = tail;
+      // stage multipliers rotate with their stage; the new tail stage starts from zero multipliers
+      std::rotate(vs.begin(), vs.begin() + 1, vs.begin() + N);
+      std::fill(vs[N - 1].begin(), vs[N - 1].end(), 0.0);
+      // co-states: lams[0] (initial condition) stays, lams[1..N] rotate left (wrap-around)
+      std::rotate(lams.begin() + 1, lams.begin() + 2, lams.end());
+    }
+
+    // values (and derivatives) of every node at (xs_, us_); fills ev
+    double evaluate(const std::vector<Vec> & xs_, const std::vector<Vec> & us_, bool derivs, std::vector<StageEval> & e)
+    {
+      e.resize(N + 1);
+      double cost = 0;
+      for (int t = 0; t < N; t++)
+      {
+        stage_eval(P, slots[t], xs_[t].data(), us_[t].data(), derivs, e[t]);
+        cost += e[t].cost;
+      }
+      terminal_eval(P, term, xs_[N].data(), derivs, e[N]);
+      cost += e[N].cost;
+      return cost;
+    }
+
+    // AL merit (LinesearchMode::PRIMAL):  cost + sum mu/2 |lam_e + e/mu|^2 + sum mu/2 |Pi_N(nu_e + c/mu)|^2
+    // also returns per-node lam_plus, nu_plus (scaled), slack e, and primal infeasibility.
+    struct Mults
+    {
+      std::vector<Vec> e;       // dynamics slack f(x,u) (-) x+
+      std::vector<Vec> lplus;   // lam_e + e/mu           (index t+1)
+      std::vector<Vec> vproj;   // Pi_N(c + mu nu_e)      (unscaled)
+      std::vector<std::vector<char>> active;
+      double merit = 0, prim_infeas = 0;
+    };
+    void multipliers(const std::vector<Vec> & xs_, const std::vector<StageEval> & e, double cost, Mults & m)
+    {
+      const double mud = mu, mue = mu;
+      m.e.assign(N, Vec(ndx, 0.0));
+      m.lplus.assign(N + 1, Vec(ndx, 0.0));
+      m.vproj.resize(N + 1);
+      m.active.resize(N + 1);
+      double pen = 0, pinf = 0;
+      for (int t = 0; t < N; t++)
+      {
+        state_difference(P, xs_[t + 1].data(), e[t].xnext.data(), m.e[t].data());
+        pinf = std::max(pinf, inf_norm(m.e[t]));
+        double sq = 0;
+        for (int a = 0; a < ndx; a++)
+        {
+          double lp = prev_lams[t + 1][a] + m.e[t][a] / mud;
+          m.lplus[t + 1][a] = lp;
+          sq += lp * lp;
+        }
+        pen += 0.5 * mud * sq;
+      }
+      for (int t = 0; t <= N; t++)
+      {
+        const int nc = e[t].nc;
+        m.vproj[t].assign(nc, 0.0);
+        m.active[t].assign(nc, 0);
+        double sq = 0;
+        for (int i = 0; i < nc; i++)
+        {
+          double z = e[t].c[i] + mue * prev_vs[t][i];
+          bool act;
+          double pr = ncone_proj(e[t].ctype[i], z, e[t].lo[i], e[t].hi[i], act);
+          m.vproj[t][i] = pr;
+          m.active[t][i] = act;
+          double vp = pr / mue;
+          sq += vp * vp;
+          // c - Pi_C(c + mu nu_e) = pr - mu nu_e
+          pinf = std::max(pinf, std::fabs(pr - mue * prev_vs[t][i]));
+        }
+        pen += 0.5 * mue * sq;
+      }
+      m.merit = cost + pen;
+      m.prim_infeas = pinf;
+    }
+
+    // LQ subproblem at the current iterate
+    void build_lq(const Mults & m)
+    {
+      knots.resize(N + 1);
+      for (int t = 0; t <= N; t++)
+      {
+        const StageEval & e = ev[t];
+        Knot & kn = knots[t];
+        const int nc = e.nc;
+        kn.nc = nc;
+        kn.Q = e.lxx;
+        kn.q = e.lx;
+        for (int a = 0; a < ndx; a++)
+          kn.Q(a, a) += preg;
+        kn.C.resize(nc, ndx);
+        kn.d.assign(nc, 0.0);
+        for (int i = 0; i < nc; i++)
+        {
+          kn.d[i] = m.vproj[t][i];
+          if (m.active[t][i])
+            for (int a = 0; a < ndx; a++)
+              kn.C(i, a) = e.Cx(i, a);
+        }
+        if (t == N)
+          break;
+        kn.S = e.lxu;
+        kn.R = e.luu;
+        kn.r = e.lu;
+        for (int a = 0; a < nu; a++)
+          kn.R(a, a) += preg;
+        kn.A = e.A;
+        kn.B = e.B;
+        kn.f.assign(ndx, 0.0);
+        for (int a = 0; a < ndx; a++)
+          kn.f[a] = m.e[t][a] + mu * prev_lams[t + 1][a];
+        kn.D.resize(nc, nu);
+        for (int i = 0; i < nc; i++)
+          if (m.active[t][i])
+            for (int a = 0; a < nu; a++)
+              kn.D(i, a) = e.Cu(i, a);
+      }
+    }
+
+    // Lagrangian gradient norms with multipliers (l, v); optionally the directional derivative along (dxs, dus)
+    double lagrangian_grad(const std::vector<Vec> & l, const std::vector<Vec> & v, double * dphi)
+    {
+      double dinf = 0, dd = 0;
+      for (int t = 0; t <= N; t++)
+      {
+        const StageEval & e = ev[t];
+        Vec Lx = e.lx;
+        for (int a = 0; a < ndx; a++)
+        {
+          double acc = Lx[a];
+          if (t < N)
+            for (int b = 0; b < ndx; b++)
+              acc += e.A(b, a) * l[t + 1][b];
+          for (int i = 0; i < e.nc; i++)
+            acc += e.Cx(i, a) * v[t][i];
+          acc -= l[t][a];
+          Lx[a] = acc;
+        }
+        if (t > 0) // dx_0 = 0 is imposed, its stationarity row defines lam_0
+          dinf = std::max(dinf, inf_norm(Lx));
+        if (dphi)
+          for (int a = 0; a < ndx; a++)
+            dd += Lx[a] * dxs[t][a];
+        if (t < N)
+        {
+          Vec Lu = e.lu;
+          for (int a = 0; a < nu; a++)
+          {
+            double acc = Lu[a];
+            for (int b = 0; b < ndx; b++)
+              acc += e.B(b, a) * l[t + 1][b];
+            for (int i = 0; i < e.nc; i++)
+              acc += e.Cu(i, a) * v[t][i];
+            Lu[a] = acc;
+          }
+          dinf = std::max(dinf, inf_norm(Lu));
+          if (dphi)
+            for (int a = 0; a < nu; a++)
+              dd += Lu[a] * dus[t][a];
+        }
+      }
+      if (dphi)
+        *dphi = dd;
+      return dinf;
+    }
+
+    // One call of SolverProxDDP::run (warm start in xs/us, duals persistent).
+    bool run(const double * x0, int max_iters)
+    {
+      xs[0].assign(x0, x0 + nx); // force_initial_condition_ (reference src/mpc.cpp:53)
+      mu = opt.mu_init;
+      prev_vs = vs;
+      prev_lams = lams;
+      auto tols_on_failure = [&]() {
+        prim_tol = opt.prim_tol0 * std::pow(mu, opt.prim_alpha);
+        inner_tol = opt.inner_tol0 * std::pow(mu, opt.dual_alpha);
+      };
+      tols_on_failure();
+      inner_tol = std::max(inner_tol, opt.tol);
+      prim_tol = std::max(prim_tol, opt.tol);
+      info.num_iters = 0;
+      info.al_iters = 0;
+      info.conv = 0;
+      info.ls_trials = 0;
+      info.alpha = 0;
+      info.flags = 0;
+      bool conv = false;
+      while (info.al_iters < opt.max_al_iters && info.num_iters < max_iters)
+      {
+        bool inner_conv = inner_loop(max_iters);
+        if (!inner_conv)
+        {
+          info.al_iters++;
+          break;
+        }
+        if (info.conv) // outer criterion met inside the inner loop
+        {
+          conv = true;
+          break;
+        }
+        if (info.prim_infeas <= prim_tol)
+        {
+          prim_tol = std::max(prim_tol * std::pow(mu, opt.prim_beta), opt.tol);
+          inner_tol = std::max(inner_tol * std::pow(mu, opt.dual_beta), opt.tol);
+          prev_vs = vs; // MultiplierUpdateMode::NEWTON
+          prev_lams = lams;
+          if (std::max(info.dual_infeas, info.prim_infeas) <= opt.tol)
+          {
+            conv = true;
+            break;
+          }
+        }
+        else
+        {
+          mu = std::max(mu * opt.mu_update_factor, opt.mu_lower_bound);
+          tols_on_failure();
+          inner_tol = std::max(inner_tol, opt.tol);
+          prim_tol = std::max(prim_tol, opt.tol);
+        }
+        info.al_iters++;
+      }
+      info.conv = conv;
+      info.mu = mu;
+      info.preg = preg;
+      return conv;
+    }
+
+    // returns true when the inner (fixed mu, fixed multiplier estimates) problem is solved
+    bool inner_loop(int max_iters)
+    {
+      for (; info.num_iters < max_iters;)
+      {
+        // linearise at the current iterate (values + derivatives), multipliers, merit
+        double cost = evaluate(xs, us, true, ev);
+        for (int t = 0; t < N; t++)
+          xdots[t] = ev[t].xdot;
+        Mults m;
+        multipliers(xs, ev, cost, m);
+        const double phi0 = m.merit;
+        info.traj_cost = cost;
+        info.merit = phi0;
+        build_lq(m);
+        info.prim_infeas = m.prim_infeas;
+        info.dual_infeas = lagrangian_grad(lams, vs, nullptr);
+        // inner criterion: stationarity + dual residuals mu (mult_plus - mult)
+        double inner_crit = info.dual_infeas;
+        for (int t = 0; t < N; t++)
+          for (int a = 0; a < ndx; a++)
+            inner_crit = std::max(inner_crit, std::fabs(mu * (m.lplus[t + 1][a] - lams[t + 1][a])));
+        for (int t = 0; t <= N; t++)
+          for (int i = 0; i < ev[t].nc; i++)
+            inner_crit = std::max(inner_crit, std::fabs(m.vproj[t][i] - mu * vs[t][i]));
+        if (std::max(info.prim_infeas, info.dual_infeas) <= opt.tol)
+        {
+          info.conv = 1;
+          return true;
+        }
+        // Newton step of the proximal subproblem
+        if (!riccati_backward(knots, ndx, nu, mu, mu, sol).ok)
+          info.flags |= 1;
+        riccati_forward(knots, sol, ndx, nu, mu, dxs, dus, vnew, lnew);
+        if (inner_crit <= inner_tol)
+          return true;
+        // directional derivative of the merit: gradient with the first-order multipliers lam_plus, nu_plus
+        std::vector<Vec> vplus(N + 1);
+        for (int t = 0; t <= N; t++)
+        {
+          vplus[t].assign(ev[t].nc, 0.0);
+          for (int i = 0; i < ev[t].nc; i++)
+            vplus[t][i] = m.vproj[t][i] / mu;
+        }
+        std::vector<Vec> lplus = m.lplus;
+        lplus[0].assign(ndx, 0.0);
+        double dphi0 = 0;
+        lagrangian_grad(lplus, vplus, &dphi0);
+        // nonmonotone (Zhang-Hager) backtracking linesearch on the merit, LINEAR rollout
+        ls_mov_avg = opt.ls_avg_eta * ls_avg_weight * ls_mov_avg + phi0;
+        ls_avg_weight = opt.ls_avg_eta * ls_avg_weight + 1.0;
+        ls_mov_avg /= ls_avg_weight;
+        double alpha = 1.0;
+        std::vector<Vec> txs(N + 1, Vec(nx)), tus(N, Vec(nu));
+        std::vector<StageEval> tev;
+        Mults tm;
+        double tcost = 0;
+        int trials = 0;
+        auto try_step = [&](double a) {
+          for (int t = 0; t <= N; t++)
+          {
+            Vec sdx(ndx);
+            for (int i = 0; i < ndx; i++)
+              sdx[i] = a * dxs[t][i];
+            state_integrate(P, xs[t].data(), sdx.data(), txs[t].data());
+          }
+          for (int t = 0; t < N; t++)
+            for (int i = 0; i < nu; i++)
+              tus[t][i] = us[t][i] + a * dus[t][i];
+          tcost = evaluate(txs, tus, false, tev);
+          multipliers(txs, tev, tcost, tm);
+          trials++;
+          return tm.merit;
+        };
+        double phi_new;
+        while (true)
+        {
+          phi_new = try_step(alpha);
+          if (phi_new <= ls_mov_avg + opt.ls_armijo_c1 * alpha * dphi0)
+            break;
+          if (alpha <= opt.ls_alpha_min || trials >= opt.ls_max_steps)
+            break;
+          alpha = std::max(alpha * opt.ls_contraction, opt.ls_alpha_min);
+        }
+        // accept
+        for (int t = 0; t <= N; t++)
+        {
+          xs[t] = txs[t];
+          for (int i = 0; i < ev[t].nc; i++)
+            vs[t][i] += alpha * (vnew[t][i] - vs[t][i]);
+          for (int a = 0; a < ndx; a++)
+            lams[t][a] += alpha * (lnew[t][a] - lams[t][a]);
+        }
+        for (int t = 0; t < N; t++)
+        {
+          us[t] = tus[t];
+          xdots[t] = tev[t].xdot;
+        }
+        info.traj_cost = tcost;
+        info.merit = phi_new;
+        info.alpha = alpha;
+        info.ls_trials = trials;
+        if (alpha <= opt.ls_alpha_min)
+          preg = std::min(preg * opt.reg_inc_k, opt.reg_max);
+        else
+          preg = std::max(preg * opt.reg_dec_k, opt.reg_min);
+        info.num_iters++;
+      }
+      return false;
+    }
+  };
+
+} // namespace orc
