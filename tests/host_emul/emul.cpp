@@ -1,0 +1,100 @@
+// TEST HARNESS — not part of the product. Compiles the per-knot / per-instance device routines of
+// simple-mpc_b200/csrc/*.cuh with g++ (par.cuh turns each parallel phase into a serial loop over the
+// thread index) so that kernel LOGIC can be debugged against the oracle on the GPU-less development
+// box. The shipped library (libsmpc_cuda.so) never contains or calls this code.
+#include "../../simple-mpc_b200/csrc/kino_knot.cuh"
+#include "../../simple-mpc_b200/csrc/riccati.cuh"
+#include "../../simple-mpc_b200/csrc/host_build.h"
+#include <memory>
+#include <vector>
+#include <string>
+
+using namespace smpc;
+static std::string g_err;
+typedef KinoCfg<13, 18, 4, 3> Go2Cfg;
+
+extern "C" {
+const char * emul_last_error() { return g_err.c_str(); }
+
+// one kinodynamics knot (Go2 sizes). knot buffer must hold KnotLayout(ndx,nu,ncmax).size doubles.
+int emul_kino_knot(
+  const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const smpc_terminal * term, int terminal,
+  int derivs, const double * x, const double * u, const double * xn, const double * vs, const double * prev_vs,
+  const double * lam_t, const double * lam_n, const double * prev_lam_n, double mu, double preg, double * knot, int * nc,
+  double * gx, double * gu, double * lplus, double * xdot, double * scalars /*8*/)
+{
+  try
+  {
+    auto M = std::make_unique<DevModel>();
+    auto O = std::make_unique<DevOcp>();
+    build_dev_model(*model, *M);
+    build_dev_ocp(*model, *ocp, *O);
+    if (model->njoints != 13 || model->nv != 18 || model->nfeet != 4 || O->fs != 3)
+      throw std::runtime_error("emul: only the Go2-sized kinodynamics instantiation is built");
+    KnotLayout L = make_knot_layout(O->ndx, O->nu, O->ncmax);
+    auto s = std::make_unique<KinoScratch<Go2Cfg>>();
+    memset(s.get(), 0, sizeof(*s));
+    KnotIO io;
+    memset(&io, 0, sizeof(io));
+    io.x = x, io.u = u, io.xn = xn;
+    io.slot = slot, io.term = term;
+    io.vs = vs, io.prev_vs = prev_vs, io.lam_t = lam_t, io.lam_n = lam_n, io.prev_lam_n = prev_lam_n;
+    io.mu = mu, io.preg = preg;
+    io.knot = knot, io.nc_out = nc, io.gx = gx, io.gu = gu, io.lplus_n = lplus, io.xdot = xdot;
+    KnotScalars sc;
+    memset(&sc, 0, sizeof(sc));
+    io.sc = &sc;
+    if (terminal)
+    {
+      if (derivs)
+        kino_terminal_knot<Go2Cfg, true>(*M, *O, L, io, *s);
+      else
+        kino_terminal_knot<Go2Cfg, false>(*M, *O, L, io, *s);
+    }
+    else
+    {
+      if (derivs)
+        kino_stage_knot<Go2Cfg, true>(*M, *O, L, io, *s);
+      else
+        kino_stage_knot<Go2Cfg, false>(*M, *O, L, io, *s);
+    }
+    memcpy(scalars, &sc, sizeof(sc));
+  }
+  catch (const std::exception & e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+
+int emul_knot_size(int ndx, int nu, int ncmax) { return make_knot_layout(ndx, nu, ncmax).size; }
+int emul_sol_size(int ndx, int nu, int ncmax) { return make_sol_layout(ndx, nu, ncmax).size; }
+void emul_knot_layout(int ndx, int nu, int ncmax, int * out /*12*/)
+{
+  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
+  int v[12] = {L.oQ, L.oS, L.oR, L.oq, L.or_, L.oA, L.oB, L.of, L.oC, L.oD, L.od, L.size};
+  memcpy(out, v, sizeof(v));
+}
+void emul_sol_layout(int ndx, int nu, int ncmax, int * out /*7*/)
+{
+  SolLayout L = make_sol_layout(ndx, nu, ncmax);
+  int v[7] = {L.oK, L.ok, L.oZ, L.oz, L.oPt, L.opt, L.size};
+  memcpy(out, v, sizeof(v));
+}
+
+// backward + forward Riccati sweep of one instance on dense knots in the device layout
+int emul_riccati(
+  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
+  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
+  double * dphi, int * flag)
+{
+  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
+  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
+  RicSmem RS = make_ric_smem(ndx, nu, ncmax);
+  std::vector<double> sm(RS.size + 8, 0.0), P0((size_t)ndx * (ndx + 1), 0.0), sm2(4 * ndx + nu + 80, 0.0);
+  riccati_backward_inst(L, SL, RS, N, knots, ncs, sol, mudyn, mueq, sm.data(), flag, P0.data());
+  riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
+  return 0;
+}
+}
