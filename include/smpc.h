@@ -218,6 +218,8 @@ int smpc_shift_warmstart(smpc_ctx *, int first, int n_inst);
 /* replaces: setInitState(x0) + solver_->run(...)          (reference src/mpc.cpp:209,212)
  * x0 [batch][nx]. Runs up to max_iters ProxDDP iterations for every instance. */
 int smpc_solve(smpc_ctx *, const double * x0, int max_iters);
+/* host -> device copy of the measured states only (x0 [batch][nx]); smpc_solve(ctx, NULL, n) then reuses them */
+int smpc_set_x0(smpc_ctx *, const double * x0);
 
 /* replaces: results_.xs / us / getCtrlFeedbacks()          (reference src/mpc.cpp:215-217)
  * any pointer may be NULL. xs [n][T+1][nx], us [n][T][nu], Ks [n][T][nu][ndx] (row-major, du = k + K dx),
@@ -241,6 +243,11 @@ int smpc_get_contact_forces(smpc_ctx *, int first, int n_inst, int t, double * f
 int smpc_last_solve_ms(smpc_ctx *, float * total_ms, float * riccati_ms);
 /* number of kernel launches issued by this context so far */
 int64_t smpc_launch_count(smpc_ctx *);
+
+/* test hooks: the dense LQ knot of (instance, t) from the last linearisation, in the device layout
+ * described by smpc_knot_layout: offsets {Q,S,R,q,r,A,B,f,C,D,d,size} in doubles, row-major blocks */
+int smpc_get_knot(smpc_ctx *, int inst, int t, int * nc, double * knot_out);
+int smpc_knot_layout(smpc_ctx *, int * out12);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,1120 @@
+// solver.cu — kernels, device-resident solver state and the C ABI (include/smpc.h) of libsmpc_cuda.
+//
+// One context = `batch` independent MPC instances that share a robot model, a problem recipe and the
+// solver options. One call of smpc_solve() is one SolverProxDDP::run per instance
+// (reference src/mpc.cpp:85,212), executed as rounds of
+//     linearize (CTA per knot)  ->  decide (CTA per instance)  ->  riccati backward (CTA per instance)
+//     ->  forward sweep (CTA per instance)  ->  { trial evaluation (CTA per knot) -> linesearch decide }*
+// on the context's stream. Per-instance control flow (convergence, BCL updates, step acceptance,
+// regularisation) lives on the device in InstState; the host only reads two counters per round.
+//
+// There is NO CPU fallback: every entry point that computes fails with SMPC_ERR_CUDA if the
+// CUDA runtime does.
+#include "kino_knot.cuh"
+#include "riccati.cuh"
+#include "host_build.h"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+using namespace smpc;
+
+namespace
+{
+  thread_local std::string g_err;
+
+  enum Phase
+  {
+    PH_DONE = 0,
+    PH_ACTIVE = 1,    // needs a linearisation
+    PH_NEED_STEP = 2, // linearised, Newton step wanted
+    PH_LS = 3         // step computed, linesearch pending
+  };
+
+  struct Dims
+  {
+    int B, N, nx, ndx, nu, ncmax, nk;
+  };
+
+  // device array pointers, passed by value to the kernels
+  struct Arrays
+  {
+    Dims dm;
+    KnotLayout L;
+    SolLayout SL;
+    RicSmem RS;
+    const DevModel * model;
+    const DevOcp * ocp;
+    smpc_solver_opts opt;
+    smpc_slot * slots;   // [B][N] ring buffer, head in InstState
+    smpc_terminal * term; // [B]
+    double *x0, *xs, *us, *vs, *lams, *prev_vs, *prev_lams, *txs, *tus;
+    double * knots;
+    int * ncs;
+    double *sol, *P0;
+    double *gx, *gu, *lplus;
+    double *dxs, *dus, *vnew, *lnew;
+    KnotScalars *sc, *sct;
+    double *xdot, *xdott;
+    InstState * inst;
+    int * counters; // [0] linesearch pending, [1] instances that need another round
+  };
+
+  __device__ __forceinline__ const smpc_slot & slot_at(const Arrays & A, const InstState & st, int b, int t)
+  {
+    return A.slots[(size_t)b * A.dm.N + (st.head + t) % A.dm.N];
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // kernels
+  // ------------------------------------------------------------------------------------------
+  __global__ void k_run_begin(Arrays A, int max_iters)
+  {
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    // force_initial_condition_: xs[0] = x0 (reference src/mpc.cpp:53)
+    for (int k = threadIdx.x; k < d.nx; k += blockDim.x)
+      A.xs[(size_t)b * (d.N + 1) * d.nx + k] = A.x0[(size_t)b * d.nx + k];
+    // prev multipliers <- current (start of run)
+    for (int k = threadIdx.x; k < (d.N + 1) * d.ncmax; k += blockDim.x)
+      A.prev_vs[(size_t)b * (d.N + 1) * d.ncmax + k] = A.vs[(size_t)b * (d.N + 1) * d.ncmax + k];
+    for (int k = threadIdx.x; k < (d.N + 1) * d.ndx; k += blockDim.x)
+      A.prev_lams[(size_t)b * (d.N + 1) * d.ndx + k] = A.lams[(size_t)b * (d.N + 1) * d.ndx + k];
+    if (threadIdx.x == 0)
+    {
+      const smpc_solver_opts & o = A.opt;
+      st.mu = o.mu_init;
+      st.prim_tol = fmax(o.prim_tol0 * pow(st.mu, o.prim_alpha), o.tol);
+      st.inner_tol = fmax(o.inner_tol0 * pow(st.mu, o.dual_alpha), o.tol);
+      st.num_iters = 0;
+      st.al_iters = 0;
+      st.conv = 0;
+      st.ls_trials = 0;
+      st.flags = 0;
+      st.alpha = 0;
+      st.max_iters = max_iters;
+      st.phase = (max_iters > 0 && o.max_al_iters > 0) ? PH_ACTIVE : PH_DONE;
+    }
+  }
+
+  template <class Cfg, bool TRIAL>
+  __global__ void __launch_bounds__(64) k_knots(Arrays A)
+  {
+    extern __shared__ double smem_raw[];
+    KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
+    const Dims & d = A.dm;
+    const int b = blockIdx.x / (d.N + 1);
+    const int t = blockIdx.x % (d.N + 1);
+    const InstState & st = A.inst[b];
+    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
+      return;
+    KnotIO io;
+    const size_t xb = (size_t)b * (d.N + 1);
+    io.x = A.xs + (xb + t) * d.nx;
+    io.u = (t < d.N) ? A.us + ((size_t)b * d.N + t) * d.nu : nullptr;
+    io.xn = (t < d.N) ? A.xs + (xb + t + 1) * d.nx : nullptr;
+    if (TRIAL)
+    {
+      io.dx = A.dxs + (xb + t) * d.ndx;
+      io.du = (t < d.N) ? A.dus + ((size_t)b * d.N + t) * d.nu : nullptr;
+      io.dxn = (t < d.N) ? A.dxs + (xb + t + 1) * d.ndx : nullptr;
+      io.alpha = st.alpha;
+      io.tx = A.txs + (xb + t) * d.nx;
+      io.tu = (t < d.N) ? A.tus + ((size_t)b * d.N + t) * d.nu : nullptr;
+    }
+    else
+    {
+      io.dx = io.du = io.dxn = nullptr;
+      io.alpha = 0;
+      io.tx = io.tu = nullptr;
+    }
+    io.slot = (t < d.N) ? &slot_at(A, st, b, t) : nullptr;
+    io.term = A.term + b;
+    io.vs = A.vs + (xb + t) * d.ncmax;
+    io.prev_vs = A.prev_vs + (xb + t) * d.ncmax;
+    io.lam_t = A.lams + (xb + t) * d.ndx;
+    io.lam_n = (t < d.N) ? A.lams + (xb + t + 1) * d.ndx : nullptr;
+    io.prev_lam_n = (t < d.N) ? A.prev_lams + (xb + t + 1) * d.ndx : nullptr;
+    io.mu = st.mu;
+    io.preg = st.preg;
+    io.knot = A.knots + (xb + t) * A.L.size;
+    io.nc_out = A.ncs + xb + t;
+    io.gx = A.gx + (xb + t) * d.ndx;
+    io.gu = (t < d.N) ? A.gu + ((size_t)b * d.N + t) * d.nu : nullptr;
+    io.lplus_n = (t < d.N) ? A.lplus + (xb + t + 1) * d.ndx : nullptr;
+    io.xdot = (t < d.N) ? (TRIAL ? A.xdott : A.xdot) + ((size_t)b * d.N + t) * d.ndx : nullptr;
+    io.sc = (TRIAL ? A.sct : A.sc) + xb + t;
+    int nc_dummy;
+    if (TRIAL)
+      io.nc_out = &nc_dummy;
+    if (t < d.N)
+      kino_stage_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, s);
+    else
+      kino_terminal_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, s);
+  }
+
+  // per-instance reductions and the ProxDDP control flow between linearisation and the Newton step
+  __global__ void k_decide(Arrays A)
+  {
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_ACTIVE)
+      return;
+    __shared__ int copy_prev;
+    if (threadIdx.x == 0)
+    {
+      const smpc_solver_opts & o = A.opt;
+      const KnotScalars * sc = A.sc + (size_t)b * (d.N + 1);
+      double cost = 0, pen = 0, pinf = 0, dinf = 0, crit = 0;
+      for (int t = 0; t <= d.N; t++)
+      {
+        cost += sc[t].cost;
+        pen += sc[t].pen;
+        pinf = fmax(pinf, sc[t].pinf);
+        if (t > 0)
+          dinf = fmax(dinf, sc[t].pad[0]);
+        if (t < d.N)
+          dinf = fmax(dinf, sc[t].pad[1]);
+        crit = fmax(crit, sc[t].crit);
+      }
+      const double inner_crit = fmax(dinf, crit);
+      st.cost0 = cost;
+      st.phi0 = cost + pen;
+      st.info.traj_cost = cost;
+      st.info.merit = cost + pen;
+      st.info.prim_infeas = pinf;
+      st.info.dual_infeas = dinf;
+      copy_prev = 0;
+      if (fmax(pinf, dinf) <= o.tol)
+      {
+        st.conv = 1;
+        st.phase = PH_DONE;
+      }
+      else if (inner_crit <= st.inner_tol)
+      {
+        // inner problem solved without a step: BCL outer update
+        if (pinf <= st.prim_tol)
+        {
+          st.prim_tol = fmax(st.prim_tol * pow(st.mu, o.prim_beta), o.tol);
+          st.inner_tol = fmax(st.inner_tol * pow(st.mu, o.dual_beta), o.tol);
+          copy_prev = 1; // MultiplierUpdateMode::NEWTON
+        }
+        else
+        {
+          st.mu = fmax(st.mu * o.mu_update_factor, o.mu_lower_bound);
+          st.prim_tol = fmax(o.prim_tol0 * pow(st.mu, o.prim_alpha), o.tol);
+          st.inner_tol = fmax(o.inner_tol0 * pow(st.mu, o.dual_alpha), o.tol);
+        }
+        st.al_iters++;
+        st.phase = (st.al_iters < o.max_al_iters) ? PH_ACTIVE : PH_DONE;
+      }
+      else
+        st.phase = PH_NEED_STEP;
+    }
+    __syncthreads();
+    if (copy_prev)
+    {
+      for (int k = threadIdx.x; k < (d.N + 1) * d.ncmax; k += blockDim.x)
+        A.prev_vs[(size_t)b * (d.N + 1) * d.ncmax + k] = A.vs[(size_t)b * (d.N + 1) * d.ncmax + k];
+      for (int k = threadIdx.x; k < (d.N + 1) * d.ndx; k += blockDim.x)
+        A.prev_lams[(size_t)b * (d.N + 1) * d.ndx + k] = A.lams[(size_t)b * (d.N + 1) * d.ndx + k];
+    }
+  }
+
+  __global__ void __launch_bounds__(128) k_riccati(Arrays A)
+  {
+    extern __shared__ double smem_raw[];
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    __shared__ int flag;
+    riccati_backward_inst(
+      A.L, A.SL, A.RS, d.N, A.knots + xb * A.L.size, A.ncs + xb, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
+      A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
+    if (threadIdx.x == 0 && flag)
+      st.flags |= 1;
+  }
+
+  __global__ void __launch_bounds__(64) k_forward(Arrays A)
+  {
+    __shared__ double sm[4 * SMPC_MAX_NDX + SMPC_MAX_NU + 72];
+    __shared__ double dphi;
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    riccati_forward_inst(
+      A.L, A.SL, d.N, A.knots + xb * A.L.size, A.ncs + xb, A.sol + xb * A.SL.size, A.P0 + (size_t)b * d.ndx * (d.ndx + 1),
+      st.mu, A.gx + xb * d.ndx, A.gu + (size_t)b * d.N * d.nu, A.lplus + xb * d.ndx, A.dxs + xb * d.ndx,
+      A.dus + (size_t)b * d.N * d.nu, A.vnew + xb * d.ncmax, A.lnew + xb * d.ndx, &dphi, sm);
+    if (threadIdx.x == 0)
+    {
+      const smpc_solver_opts & o = A.opt;
+      st.dphi0 = dphi;
+      // nonmonotone (Zhang-Hager) reference value
+      st.ls_mov_avg = o.ls_avg_eta * st.ls_avg_weight * st.ls_mov_avg + st.phi0;
+      st.ls_avg_weight = o.ls_avg_eta * st.ls_avg_weight + 1.0;
+      st.ls_mov_avg /= st.ls_avg_weight;
+      st.alpha = 1.0;
+      st.ls_trials = 0;
+      st.phase = PH_LS;
+    }
+  }
+
+  // reduce the trial merit, test the (nonmonotone) Armijo condition, accept or shrink the step
+  __global__ void k_ls_decide(Arrays A)
+  {
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_LS)
+    {
+      if (threadIdx.x == 0 && st.phase == PH_ACTIVE)
+        atomicAdd(A.counters + 1, 1);
+      return;
+    }
+    __shared__ int accept;
+    __shared__ double s_alpha;
+    if (threadIdx.x == 0)
+    {
+      const smpc_solver_opts & o = A.opt;
+      const KnotScalars * sc = A.sct + (size_t)b * (d.N + 1);
+      double cost = 0, pen = 0;
+      for (int t = 0; t <= d.N; t++)
+      {
+        cost += sc[t].cost;
+        pen += sc[t].pen;
+      }
+      const double phi = cost + pen;
+      st.ls_trials++;
+      const double alpha = st.alpha;
+      s_alpha = alpha;
+      const bool ok = phi <= st.ls_mov_avg + o.ls_armijo_c1 * alpha * st.dphi0;
+      if (ok || alpha <= o.ls_alpha_min || st.ls_trials >= o.ls_max_steps)
+      {
+        accept = 1;
+        st.info.traj_cost = cost;
+        st.info.merit = phi;
+        if (alpha <= o.ls_alpha_min)
+          st.preg = fmin(st.preg * o.reg_inc_k, o.reg_max);
+        else
+          st.preg = fmax(st.preg * o.reg_dec_k, o.reg_min);
+        st.num_iters++;
+        if (st.num_iters >= st.max_iters)
+        {
+          st.al_iters++;
+          st.phase = PH_DONE;
+        }
+        else
+        {
+          st.phase = PH_ACTIVE;
+          atomicAdd(A.counters + 1, 1);
+        }
+      }
+      else
+      {
+        accept = 0;
+        st.alpha = fmax(alpha * o.ls_contraction, o.ls_alpha_min);
+        atomicAdd(A.counters + 0, 1);
+      }
+    }
+    __syncthreads();
+    if (!accept)
+      return;
+    const double alpha = s_alpha;
+    const size_t xb = (size_t)b * (d.N + 1);
+    for (int k = threadIdx.x; k < (d.N + 1) * d.nx; k += blockDim.x)
+      A.xs[xb * d.nx + k] = A.txs[xb * d.nx + k];
+    for (int k = threadIdx.x; k < d.N * d.nu; k += blockDim.x)
+      A.us[(size_t)b * d.N * d.nu + k] = A.tus[(size_t)b * d.N * d.nu + k];
+    for (int k = threadIdx.x; k < d.N * d.ndx; k += blockDim.x)
+      A.xdot[(size_t)b * d.N * d.ndx + k] = A.xdott[(size_t)b * d.N * d.ndx + k];
+    for (int k = threadIdx.x; k < (d.N + 1) * d.ncmax; k += blockDim.x)
+    {
+      const int t = k / d.ncmax, i = k % d.ncmax;
+      if (i < A.ncs[xb + t])
+      {
+        const double v = A.vs[xb * d.ncmax + k];
+        A.vs[xb * d.ncmax + k] = v + alpha * (A.vnew[xb * d.ncmax + k] - v);
+      }
+    }
+    for (int k = threadIdx.x; k < (d.N + 1) * d.ndx; k += blockDim.x)
+    {
+      const double v = A.lams[xb * d.ndx + k];
+      A.lams[xb * d.ndx + k] = v + alpha * (A.lnew[xb * d.ndx + k] - v);
+    }
+  }
+
+  __global__ void k_finish(Arrays A)
+  {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= A.dm.B)
+      return;
+    InstState & st = A.inst[b];
+    st.info.num_iters = st.num_iters;
+    st.info.al_iters = st.al_iters;
+    st.info.conv = st.conv;
+    st.info.ls_trials = st.ls_trials;
+    st.info.flags = st.flags;
+    st.info.alpha = st.alpha;
+    st.info.mu = st.mu;
+    st.info.preg = st.preg;
+  }
+
+  // replaceStageCircular + cycleProblem (reference src/mpc.cpp:225-226): new tail slot, duals follow
+  __global__ void k_cycle(Arrays A, int first, const smpc_slot * tails)
+  {
+    const int b = first + blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    const size_t xb = (size_t)b * (d.N + 1);
+    // the slot at `head` is horizon position 0: overwrite it with the new tail, then advance head
+    {
+      const int * src = reinterpret_cast<const int *>(tails + blockIdx.x);
+      int * dst = reinterpret_cast<int *>(A.slots + (size_t)b * d.N + st.head);
+      for (int k = threadIdx.x; k < (int)(sizeof(smpc_slot) / sizeof(int)); k += blockDim.x)
+        dst[k] = src[k];
+    }
+    for (int i = threadIdx.x; i < d.ncmax; i += blockDim.x)
+    {
+      for (int t = 0; t + 1 < d.N; t++)
+        A.vs[(xb + t) * d.ncmax + i] = A.vs[(xb + t + 1) * d.ncmax + i];
+      A.vs[(xb + d.N - 1) * d.ncmax + i] = 0.0;
+    }
+    for (int i = threadIdx.x; i < d.ndx; i += blockDim.x)
+    {
+      const double first_l = A.lams[(xb + 1) * d.ndx + i];
+      for (int t = 1; t < d.N; t++)
+        A.lams[(xb + t) * d.ndx + i] = A.lams[(xb + t + 1) * d.ndx + i];
+      A.lams[(xb + d.N) * d.ndx + i] = first_l;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      st.head = (st.head + 1) % d.N;
+  }
+
+  // warm-start shift of reference src/mpc.cpp:201-207
+  __global__ void k_shift(Arrays A, int first)
+  {
+    const int b = first + blockIdx.x;
+    const Dims & d = A.dm;
+    const size_t xb = (size_t)b * (d.N + 1);
+    for (int i = threadIdx.x; i < d.nx; i += blockDim.x)
+      for (int t = 0; t < d.N; t++)
+        A.xs[(xb + t) * d.nx + i] = A.xs[(xb + t + 1) * d.nx + i];
+    for (int i = threadIdx.x; i < d.nu; i += blockDim.x)
+      for (int t = 0; t + 1 < d.N; t++)
+        A.us[((size_t)b * d.N + t) * d.nu + i] = A.us[((size_t)b * d.N + t + 1) * d.nu + i];
+  }
+
+  // slots arrive in horizon order; store them at ring positions
+  __global__ void k_store_slots(Arrays A, int first, const smpc_slot * src, int t_only)
+  {
+    const Dims & d = A.dm;
+    const int per = (t_only < 0) ? d.N : 1;
+    const int bi = blockIdx.x / per;
+    const int t = (t_only < 0) ? blockIdx.x % per : t_only;
+    const int b = first + bi;
+    const InstState & st = A.inst[b];
+    const int * s = reinterpret_cast<const int *>(src + blockIdx.x);
+    int * dst = reinterpret_cast<int *>(A.slots + (size_t)b * d.N + (st.head + t) % d.N);
+    for (int k = threadIdx.x; k < (int)(sizeof(smpc_slot) / sizeof(int)); k += blockDim.x)
+      dst[k] = s[k];
+  }
+  __global__ void k_store_foot_refs(Arrays A, int first, const double * src)
+  {
+    const Dims & d = A.dm;
+    const int bi = blockIdx.x / d.N, t = blockIdx.x % d.N;
+    const int b = first + bi;
+    const InstState & st = A.inst[b];
+    smpc_slot & sl = A.slots[(size_t)b * d.N + (st.head + t) % d.N];
+    for (int k = threadIdx.x; k < d.nk * 12; k += blockDim.x)
+      sl.foot_ref[k / 12][k % 12] = src[((size_t)blockIdx.x * d.nk) * 12 + k];
+  }
+  // gather rows of a strided device array into a dense staging buffer: dst[r][0..w) = src[r*stride + off .. + w)
+  __global__ void k_pack(const double * src, double * dst, size_t rows, int w, size_t stride, int off)
+  {
+    const size_t n = rows * (size_t)w;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+    {
+      const size_t r = e / w;
+      const int c = (int)(e % w);
+      dst[e] = src[r * stride + off + c];
+    }
+  }
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct smpc_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Arrays A;
+  DevModel hmodel;
+  DevOcp hocp;
+  std::vector<void *> allocs;
+  int * h_counters = nullptr; // pinned
+  void * staging = nullptr;   // device staging for host<->device conversions
+  size_t staging_bytes = 0;
+  void * h_staging = nullptr; // pinned host staging
+  size_t h_staging_bytes = 0;
+  cudaEvent_t ev0, ev1, evr0, evr1;
+  float last_ms = 0, last_ric_ms = 0;
+  int64_t launches = 0;
+  size_t knot_smem = 0, ric_smem = 0;
+  void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
+};
+
+#define CU(call)                                                                                                       \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e_ = (call);                                                                                           \
+    if (e_ != cudaSuccess)                                                                                             \
+    {                                                                                                                  \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                                      \
+      return SMPC_ERR_CUDA;                                                                                            \
+    }                                                                                                                  \
+  } while (0)
+
+namespace
+{
+  template <class Cfg>
+  void launch_knots_impl(smpc_ctx * c, bool trial)
+  {
+    const Dims & d = c->A.dm;
+    const int grid = d.B * (d.N + 1);
+    if (trial)
+      k_knots<Cfg, true><<<grid, 64, c->knot_smem, c->stream>>>(c->A);
+    else
+      k_knots<Cfg, false><<<grid, 64, c->knot_smem, c->stream>>>(c->A);
+    c->launches++;
+  }
+  template <class Cfg>
+  int setup_knots(smpc_ctx * c)
+  {
+    c->knot_smem = sizeof(KinoScratch<Cfg>);
+    CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    c->launch_knots = &launch_knots_impl<Cfg>;
+    return SMPC_OK;
+  }
+
+  template <class T>
+  int dev_alloc(smpc_ctx * c, T ** p, size_t n)
+  {
+    void * q = nullptr;
+    CU(cudaMalloc(&q, n * sizeof(T)));
+    CU(cudaMemsetAsync(q, 0, n * sizeof(T), c->stream));
+    c->allocs.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return SMPC_OK;
+  }
+  int ensure_staging(smpc_ctx * c, size_t bytes)
+  {
+    if (bytes > c->staging_bytes)
+    {
+      if (c->staging)
+        CU(cudaFree(c->staging));
+      CU(cudaMalloc(&c->staging, bytes));
+      c->staging_bytes = bytes;
+    }
+    if (bytes > c->h_staging_bytes)
+    {
+      if (c->h_staging)
+        CU(cudaFreeHost(c->h_staging));
+      CU(cudaMallocHost(&c->h_staging, bytes));
+      c->h_staging_bytes = bytes;
+    }
+    return SMPC_OK;
+  }
+  int check_range(smpc_ctx * c, int first, int n)
+  {
+    if (!c || first < 0 || n < 0 || first + n > c->A.dm.B)
+    {
+      g_err = "instance range out of bounds";
+      return SMPC_ERR_INVALID;
+    }
+    return 0;
+  }
+  // host -> device through the pinned staging buffer (async on the context stream, then safe to reuse after sync)
+  int h2d(smpc_ctx * c, void * dst, const void * src, size_t bytes)
+  {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return SMPC_OK;
+  }
+  int d2h(smpc_ctx * c, void * dst, const void * src, size_t bytes)
+  {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return SMPC_OK;
+  }
+} // namespace
+
+extern "C" {
+
+const char * smpc_last_error(void) { return g_err.c_str(); }
+
+void smpc_default_solver_opts(smpc_solver_opts * o)
+{
+  o->tol = 1e-4;
+  o->mu_init = 1e-8;
+  o->max_iters = 1;
+  o->max_al_iters = 100;
+  o->prim_alpha = 0.1;
+  o->prim_beta = 0.9;
+  o->dual_alpha = 1.0;
+  o->dual_beta = 1.0;
+  o->mu_update_factor = 0.01;
+  o->mu_lower_bound = 1e-8;
+  o->inner_tol0 = 1.0;
+  o->prim_tol0 = 1.0;
+  o->reg_init = 1e-9;
+  o->reg_min = 1e-10;
+  o->reg_max = 1e9;
+  o->reg_inc_k = 10.0;
+  o->reg_inc_critical = 100.0;
+  o->reg_dec_k = 1.0 / 3.0;
+  o->ls_armijo_c1 = 1e-4;
+  o->ls_alpha_min = 1e-7;
+  o->ls_contraction = 0.5;
+  o->ls_avg_eta = 0.85;
+  o->ls_max_steps = 20;
+}
+
+int smpc_problem_dims(const smpc_model_desc * m, const smpc_ocp_desc * o, int * nx, int * ndx, int * nu)
+{
+  if (!m || !o)
+  {
+    g_err = "null descriptor";
+    return SMPC_ERR_INVALID;
+  }
+  const int fs = o->force_size;
+  if (o->kind == SMPC_OCP_KINODYNAMICS)
+  {
+    *nx = m->nq + m->nv;
+    *ndx = 2 * m->nv;
+    *nu = m->nv - 6 + fs * m->nfeet;
+  }
+  else if (o->kind == SMPC_OCP_FULLDYNAMICS)
+  {
+    *nx = m->nq + m->nv;
+    *ndx = 2 * m->nv;
+    *nu = m->nv - 6;
+  }
+  else
+  {
+    *nx = *ndx = 9;
+    *nu = fs * m->nfeet;
+  }
+  return SMPC_OK;
+}
+
+int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_solver_opts * opts)
+{
+  if (!out || !model || !ocp || !opts || batch < 1)
+  {
+    g_err = "smpc_create: bad arguments";
+    return SMPC_ERR_INVALID;
+  }
+  smpc_ctx * c = new smpc_ctx;
+  try
+  {
+    build_dev_model(*model, c->hmodel);
+    build_dev_ocp(*model, *ocp, c->hocp);
+  }
+  catch (const std::exception & e)
+  {
+    g_err = e.what();
+    const bool unsup = g_err.find("CUDA") != std::string::npos || g_err.find("supported") != std::string::npos;
+    delete c;
+    return unsup ? SMPC_ERR_UNSUPPORTED : SMPC_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+  {
+    g_err = "no CUDA device: libsmpc_cuda has no CPU fallback";
+    delete c;
+    return SMPC_ERR_CUDA;
+  }
+  c->device = device;
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  Arrays & A = c->A;
+  const DevOcp & O = c->hocp;
+  A.dm = Dims{batch, O.N, O.nx, O.ndx, O.nu, O.ncmax, O.nk};
+  A.L = make_knot_layout(O.ndx, O.nu, O.ncmax);
+  A.SL = make_sol_layout(O.ndx, O.nu, O.ncmax);
+  A.RS = make_ric_smem(O.ndx, O.nu, O.ncmax);
+  A.opt = *opts;
+  // kernel instantiation for this (robot, problem) shape
+  int rc = SMPC_ERR_UNSUPPORTED;
+  if (O.kind == SMPC_OCP_KINODYNAMICS && model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3)
+    rc = setup_knots<KinoCfg<13, 18, 4, 3>>(c);
+  else
+    g_err = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics, 12-DoF quadruped, point feet)";
+  if (rc != SMPC_OK)
+  {
+    delete c;
+    return rc;
+  }
+  c->ric_smem = (size_t)A.RS.size * sizeof(double);
+  CU(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+  const Dims & d = A.dm;
+  const size_t B = d.B, N1 = d.N + 1;
+  DevModel * dmodel;
+  DevOcp * docp;
+#define AL(p, n)                                                                                                       \
+  if ((rc = dev_alloc(c, &(p), (n))) != SMPC_OK)                                                                       \
+  return rc
+  AL(dmodel, 1);
+  AL(docp, 1);
+  CU(cudaMemcpyAsync(dmodel, &c->hmodel, sizeof(DevModel), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(docp, &c->hocp, sizeof(DevOcp), cudaMemcpyHostToDevice, c->stream));
+  A.model = dmodel;
+  A.ocp = docp;
+  AL(A.slots, B * d.N);
+  AL(A.term, B);
+  AL(A.x0, B * d.nx);
+  AL(A.xs, B * N1 * d.nx);
+  AL(A.us, B * d.N * d.nu);
+  AL(A.txs, B * N1 * d.nx);
+  AL(A.tus, B * d.N * d.nu);
+  AL(A.vs, B * N1 * d.ncmax);
+  AL(A.prev_vs, B * N1 * d.ncmax);
+  AL(A.lams, B * N1 * d.ndx);
+  AL(A.prev_lams, B * N1 * d.ndx);
+  AL(A.knots, B * N1 * A.L.size);
+  AL(A.ncs, B * N1);
+  AL(A.sol, B * N1 * A.SL.size);
+  AL(A.P0, B * d.ndx * (d.ndx + 1));
+  AL(A.gx, B * N1 * d.ndx);
+  AL(A.gu, B * d.N * d.nu);
+  AL(A.lplus, B * N1 * d.ndx);
+  AL(A.dxs, B * N1 * d.ndx);
+  AL(A.dus, B * d.N * d.nu);
+  AL(A.vnew, B * N1 * d.ncmax);
+  AL(A.lnew, B * N1 * d.ndx);
+  AL(A.sc, B * N1);
+  AL(A.sct, B * N1);
+  AL(A.xdot, B * d.N * d.ndx);
+  AL(A.xdott, B * d.N * d.ndx);
+  AL(A.inst, B);
+  AL(A.counters, 4);
+#undef AL
+  // persistent solver scalars (aligator: set in setup())
+  {
+    std::vector<InstState> h(B);
+    memset(h.data(), 0, B * sizeof(InstState));
+    for (auto & s : h)
+    {
+      s.mu = opts->mu_init;
+      s.preg = opts->reg_init;
+    }
+    CU(cudaMemcpyAsync(A.inst, h.data(), B * sizeof(InstState), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  CU(cudaMallocHost(&c->h_counters, 4 * sizeof(int)));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreate(&c->evr0));
+  CU(cudaEventCreate(&c->evr1));
+  *out = c;
+  return SMPC_OK;
+}
+
+void smpc_destroy(smpc_ctx * c)
+{
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  for (void * p : c->allocs)
+    cudaFree(p);
+  if (c->staging)
+    cudaFree(c->staging);
+  if (c->h_staging)
+    cudaFreeHost(c->h_staging);
+  if (c->h_counters)
+    cudaFreeHost(c->h_counters);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->evr0);
+  cudaEventDestroy(c->evr1);
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int smpc_set_slots(smpc_ctx * c, int first, int n, const smpc_slot * slots)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * c->A.dm.N * sizeof(smpc_slot);
+  int rc;
+  if ((rc = ensure_staging(c, bytes)) != SMPC_OK)
+    return rc;
+  if ((rc = h2d(c, c->staging, slots, bytes)) != SMPC_OK)
+    return rc;
+  k_store_slots<<<n * c->A.dm.N, 128, 0, c->stream>>>(c->A, first, (const smpc_slot *)c->staging, -1);
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_set_slot(smpc_ctx * c, int first, int n, int t, const smpc_slot * slots)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (t < 0 || t >= c->A.dm.N)
+  {
+    g_err = "Stage index exceeds stage vector size";
+    return SMPC_ERR_INVALID;
+  }
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * sizeof(smpc_slot);
+  int rc;
+  if ((rc = ensure_staging(c, bytes)) != SMPC_OK)
+    return rc;
+  if ((rc = h2d(c, c->staging, slots, bytes)) != SMPC_OK)
+    return rc;
+  k_store_slots<<<n, 128, 0, c->stream>>>(c->A, first, (const smpc_slot *)c->staging, t);
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_set_foot_refs(smpc_ctx * c, int first, int n, const double * foot_ref)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  const size_t bytes = (size_t)n * d.N * d.nk * 12 * sizeof(double);
+  int rc;
+  if ((rc = ensure_staging(c, bytes)) != SMPC_OK)
+    return rc;
+  if ((rc = h2d(c, c->staging, foot_ref, bytes)) != SMPC_OK)
+    return rc;
+  k_store_foot_refs<<<n * d.N, 64, 0, c->stream>>>(c->A, first, (const double *)c->staging);
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_set_terminal(smpc_ctx * c, int first, int n, const smpc_terminal * term)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->A.term + first, term, (size_t)n * sizeof(smpc_terminal), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_cycle(smpc_ctx * c, int first, int n, const smpc_slot * new_tail)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * sizeof(smpc_slot);
+  int rc;
+  if ((rc = ensure_staging(c, bytes)) != SMPC_OK)
+    return rc;
+  if ((rc = h2d(c, c->staging, new_tail, bytes)) != SMPC_OK)
+    return rc;
+  k_cycle<<<n, 64, 0, c->stream>>>(c->A, first, (const smpc_slot *)c->staging);
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_set_warmstart(smpc_ctx * c, int first, int n, const double * xs, const double * us)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  if (xs)
+    CU(cudaMemcpyAsync(c->A.xs + (size_t)first * (d.N + 1) * d.nx, xs, (size_t)n * (d.N + 1) * d.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (us)
+    CU(cudaMemcpyAsync(c->A.us + (size_t)first * d.N * d.nu, us, (size_t)n * d.N * d.nu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_shift_warmstart(smpc_ctx * c, int first, int n)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  k_shift<<<n, 64, 0, c->stream>>>(c->A, first);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SMPC_OK;
+}
+
+int smpc_set_x0(smpc_ctx * c, const double * x0)
+{
+  if (!c || !x0)
+  {
+    g_err = "smpc_set_x0: null argument";
+    return SMPC_ERR_INVALID;
+  }
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  CU(cudaMemcpyAsync(c->A.x0, x0, (size_t)d.B * d.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return SMPC_OK;
+}
+
+int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
+{
+  if (!c)
+  {
+    g_err = "smpc_solve: null context";
+    return SMPC_ERR_INVALID;
+  }
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  if (x0)
+  {
+    int rc = smpc_set_x0(c, x0);
+    if (rc != SMPC_OK)
+      return rc;
+  }
+  cudaStream_t s = c->stream;
+  CU(cudaEventRecord(c->ev0, s));
+  k_run_begin<<<d.B, 128, 0, s>>>(c->A, max_iters);
+  c->launches++;
+  const int max_rounds = max_iters + c->A.opt.max_al_iters + 1;
+  bool timed_ric = false;
+  for (int round = 0; round < max_rounds; round++)
+  {
+    c->launch_knots(c, false);
+    k_decide<<<d.B, 64, 0, s>>>(c->A);
+    if (!timed_ric)
+      CU(cudaEventRecord(c->evr0, s));
+    k_riccati<<<d.B, 128, c->ric_smem, s>>>(c->A);
+    if (!timed_ric)
+      CU(cudaEventRecord(c->evr1, s));
+    timed_ric = true;
+    k_forward<<<d.B, 64, 0, s>>>(c->A);
+    c->launches += 3;
+    for (int trial = 0; trial <= c->A.opt.ls_max_steps + 1; trial++)
+    {
+      // counters: [0] instances whose linesearch needs another trial, [1] instances that need another round
+      // (both recounted by every k_ls_decide launch; the host reads the last one)
+      CU(cudaMemsetAsync(c->A.counters, 0, 2 * sizeof(int), s));
+      c->launch_knots(c, true);
+      k_ls_decide<<<d.B, 128, 0, s>>>(c->A);
+      c->launches++;
+      CU(cudaMemcpyAsync(c->h_counters, c->A.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      if (c->h_counters[0] == 0)
+        break;
+    }
+    if (c->h_counters[1] == 0)
+      break;
+  }
+  k_finish<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
+  c->launches++;
+  CU(cudaEventRecord(c->ev1, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaGetLastError());
+  CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  CU(cudaEventElapsedTime(&c->last_ric_ms, c->evr0, c->evr1));
+  return SMPC_OK;
+}
+
+static int pack_to_host(smpc_ctx * c, const double * src, size_t rows, int w, size_t stride, int off, double * dst_host)
+{
+  const size_t bytes = rows * (size_t)w * sizeof(double);
+  int rc;
+  if ((rc = ensure_staging(c, bytes)) != SMPC_OK)
+    return rc;
+  const size_t n = rows * (size_t)w;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 16)
+    grid = 148 * 16;
+  k_pack<<<grid, 256, 0, c->stream>>>(src, (double *)c->staging, rows, w, stride, off);
+  c->launches++;
+  CU(cudaMemcpyAsync(dst_host, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return SMPC_OK;
+}
+
+int smpc_get_results(smpc_ctx * c, int first, int n, double * xs, double * us, double * Ks, double * ks)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  const size_t N1 = d.N + 1;
+  int rc;
+  if (xs)
+    if ((rc = d2h(c, xs, c->A.xs + (size_t)first * N1 * d.nx, (size_t)n * N1 * d.nx * sizeof(double))) != SMPC_OK)
+      return rc;
+  if (us)
+    if ((rc = d2h(c, us, c->A.us + (size_t)first * d.N * d.nu, (size_t)n * d.N * d.nu * sizeof(double))) != SMPC_OK)
+      return rc;
+  // gains live in the per-stage solution records; rows t = 0..N-1 of each instance
+  for (int i = 0; i < n && (Ks || ks); i++)
+  {
+    const double * base = c->A.sol + ((size_t)(first + i) * N1) * c->A.SL.size;
+    if (Ks)
+    {
+      if ((rc = pack_to_host(c, base, d.N, d.nu * d.ndx, c->A.SL.size, c->A.SL.oK, Ks + (size_t)i * d.N * d.nu * d.ndx)) != SMPC_OK)
+        return rc;
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    if (ks)
+    {
+      if ((rc = pack_to_host(c, base, d.N, d.nu, c->A.SL.size, c->A.SL.ok, ks + (size_t)i * d.N * d.nu)) != SMPC_OK)
+        return rc;
+      CU(cudaStreamSynchronize(c->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
+int smpc_get_head(smpc_ctx * c, int first, int n, double * x1, double * u0, double * u1, double * K0)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  const size_t N1 = d.N + 1;
+  cudaStream_t s = c->stream;
+  if (x1)
+    CU(cudaMemcpy2DAsync(x1, d.nx * sizeof(double), c->A.xs + ((size_t)first * N1 + 1) * d.nx, N1 * d.nx * sizeof(double), d.nx * sizeof(double), n, cudaMemcpyDeviceToHost, s));
+  if (u0)
+    CU(cudaMemcpy2DAsync(u0, d.nu * sizeof(double), c->A.us + (size_t)first * d.N * d.nu, (size_t)d.N * d.nu * sizeof(double), d.nu * sizeof(double), n, cudaMemcpyDeviceToHost, s));
+  if (u1)
+    CU(cudaMemcpy2DAsync(u1, d.nu * sizeof(double), c->A.us + ((size_t)first * d.N + 1) * d.nu, (size_t)d.N * d.nu * sizeof(double), d.nu * sizeof(double), n, cudaMemcpyDeviceToHost, s));
+  if (K0)
+    CU(cudaMemcpy2DAsync(
+      K0, (size_t)d.nu * d.ndx * sizeof(double), c->A.sol + (size_t)first * N1 * c->A.SL.size + c->A.SL.oK,
+      N1 * c->A.SL.size * sizeof(double), (size_t)d.nu * d.ndx * sizeof(double), n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SMPC_OK;
+}
+
+int smpc_get_info(smpc_ctx * c, int first, int n, smpc_solve_info * info)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy2DAsync(
+    info, sizeof(smpc_solve_info), reinterpret_cast<const char *>(c->A.inst + first) + offsetof(InstState, info), sizeof(InstState),
+    sizeof(smpc_solve_info), n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
+int smpc_get_ncmax(smpc_ctx * c) { return c ? c->A.dm.ncmax : SMPC_ERR_INVALID; }
+
+int smpc_get_duals(smpc_ctx * c, int first, int n, double * vs, double * lams)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  const size_t N1 = d.N + 1;
+  int rc;
+  if (vs)
+    if ((rc = d2h(c, vs, c->A.vs + (size_t)first * N1 * d.ncmax, (size_t)n * N1 * d.ncmax * sizeof(double))) != SMPC_OK)
+      return rc;
+  if (lams)
+    if ((rc = d2h(c, lams, c->A.lams + (size_t)first * N1 * d.ndx, (size_t)n * N1 * d.ndx * sizeof(double))) != SMPC_OK)
+      return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
+int smpc_get_xdot(smpc_ctx * c, int first, int n, int t, double * xdot)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  const Dims & d = c->A.dm;
+  if (t < 0 || t >= d.N)
+  {
+    g_err = "Stage index exceeds stage vector size";
+    return SMPC_ERR_INVALID;
+  }
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy2DAsync(
+    xdot, d.ndx * sizeof(double), c->A.xdot + ((size_t)first * d.N + t) * d.ndx, (size_t)d.N * d.ndx * sizeof(double),
+    d.ndx * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
+int smpc_get_contact_forces(smpc_ctx * c, int first, int n, int t, double * forces)
+{
+  (void)first;
+  (void)n;
+  (void)t;
+  (void)forces;
+  if (!c)
+    return SMPC_ERR_INVALID;
+  // reference include/simple-mpc/mpc.hpp:174-178: only defined for the full-dynamics handler
+  g_err = "getContactForces is only available for full-dynamics problems";
+  return SMPC_ERR_UNSUPPORTED;
+}
+
+int smpc_last_solve_ms(smpc_ctx * c, float * total_ms, float * riccati_ms)
+{
+  if (!c)
+    return SMPC_ERR_INVALID;
+  if (total_ms)
+    *total_ms = c->last_ms;
+  if (riccati_ms)
+    *riccati_ms = c->last_ric_ms;
+  return SMPC_OK;
+}
+int64_t smpc_launch_count(smpc_ctx * c) { return c ? c->launches : 0; }
+
+// LQ knot t of instance `inst` as assembled by the last linearisation (test hook; device layout -> dense blocks)
+int smpc_get_knot(smpc_ctx * c, int inst, int t, int * nc, double * knot_out /* KnotLayout.size doubles */)
+{
+  if (check_range(c, inst, 1))
+    return SMPC_ERR_INVALID;
+  const Dims & d = c->A.dm;
+  if (t < 0 || t > d.N)
+  {
+    g_err = "bad knot index";
+    return SMPC_ERR_INVALID;
+  }
+  CU(cudaSetDevice(c->device));
+  const size_t k = (size_t)inst * (d.N + 1) + t;
+  CU(cudaMemcpyAsync(knot_out, c->A.knots + k * c->A.L.size, c->A.L.size * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (nc)
+    CU(cudaMemcpyAsync(nc, c->A.ncs + k, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_knot_layout(smpc_ctx * c, int * out /*12*/)
+{
+  if (!c)
+    return SMPC_ERR_INVALID;
+  const KnotLayout & L = c->A.L;
+  const int v[12] = {L.oQ, L.oS, L.oR, L.oq, L.or_, L.oA, L.oB, L.of, L.oC, L.oD, L.od, L.size};
+  memcpy(out, v, sizeof(v));
+  return SMPC_OK;
+}
+
+} // extern "C"

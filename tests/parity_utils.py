@@ -1,0 +1,228 @@
+"""Shared scenario + backend drivers for the parity tests, smoke() and bench.py.
+
+`Backend` drives either the CPU oracle (prefix "orc") or the CUDA library (prefix "smpc") through the
+same C-ABI call sequence that MPC::MPC / MPC::iterate perform (reference src/mpc.cpp:19-99,189-218):
+    create -> set_slots/set_terminal/set_warmstart -> solve(100)            (constructor)
+    per tick: cycle(new tail) -> [set_foot_refs] -> shift_warmstart -> solve(x, max_iters)
+"""
+import ctypes as C
+import numpy as np
+from smpc_ctypes import (Slot, Terminal, SolveInfo, SolverOpts, dbl_p, go2_like_model, go2_kino_ocp, standing_slot,
+                         fk_numpy, x_ref_of, total_mass, load_oracle, load_cuda)
+
+
+def P(a):
+    return a.ctypes.data_as(dbl_p)
+
+
+class Backend:
+    def __init__(self, lib, prefix, model, ocp_bundle, opts, batch, device=0):
+        self.lib, self.pre = lib, prefix
+        self.B = batch
+        self.model, self.ocpb = model, ocp_bundle
+        self.ctx = C.c_void_p()
+        nx, ndx, nu = C.c_int(), C.c_int(), C.c_int()
+        self._chk(self.f("problem_dims")(C.byref(model), C.byref(ocp_bundle.desc), C.byref(nx), C.byref(ndx), C.byref(nu)))
+        self.nx, self.ndx, self.nu = nx.value, ndx.value, nu.value
+        self.N = ocp_bundle.desc.horizon
+        if prefix == "smpc":
+            rc = lib.smpc_create(C.byref(self.ctx), device, batch, C.byref(model), C.byref(ocp_bundle.desc), C.byref(opts))
+        else:
+            rc = lib.orc_create(C.byref(self.ctx), batch, C.byref(model), C.byref(ocp_bundle.desc), C.byref(opts))
+        self._chk(rc)
+        self.ncmax = self.f("get_ncmax")(self.ctx)
+
+    def f(self, name):
+        return getattr(self.lib, self.pre + "_" + name)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("%s error %d: %s" % (self.pre, rc, self.f("last_error")().decode()))
+
+    def close(self):
+        if self.ctx:
+            self.f("destroy")(self.ctx)
+            self.ctx = None
+
+    def set_slots(self, slots):  # ctypes array [B*N]
+        self._chk(self.f("set_slots")(self.ctx, 0, self.B, slots))
+
+    def set_terminal(self, terms):
+        self._chk(self.f("set_terminal")(self.ctx, 0, self.B, terms))
+
+    def set_warmstart(self, xs, us):
+        self._chk(self.f("set_warmstart")(self.ctx, 0, self.B, P(xs), P(us)))
+
+    def cycle(self, tails):
+        self._chk(self.f("cycle")(self.ctx, 0, self.B, tails))
+
+    def set_foot_refs(self, refs):
+        self._chk(self.f("set_foot_refs")(self.ctx, 0, self.B, P(refs)))
+
+    def shift(self):
+        self._chk(self.f("shift_warmstart")(self.ctx, 0, self.B))
+
+    def solve(self, x0, max_iters):
+        x0 = np.ascontiguousarray(x0)
+        self._chk(self.f("solve")(self.ctx, P(x0), max_iters))
+
+    def results(self, gains=True):
+        B, N, nx, nu, ndx = self.B, self.N, self.nx, self.nu, self.ndx
+        xs = np.zeros((B, N + 1, nx))
+        us = np.zeros((B, N, nu))
+        Ks = np.zeros((B, N, nu, ndx)) if gains else None
+        ks = np.zeros((B, N, nu)) if gains else None
+        self._chk(self.f("get_results")(self.ctx, 0, B, P(xs), P(us), P(Ks) if gains else None, P(ks) if gains else None))
+        return xs, us, Ks, ks
+
+    def head(self):
+        B, nx, nu, ndx = self.B, self.nx, self.nu, self.ndx
+        x1, u0, u1, K0 = np.zeros((B, nx)), np.zeros((B, nu)), np.zeros((B, nu)), np.zeros((B, nu, ndx))
+        self._chk(self.f("get_head")(self.ctx, 0, B, P(x1), P(u0), P(u1), P(K0)))
+        return x1, u0, u1, K0
+
+    def info(self):
+        arr = (SolveInfo * self.B)()
+        self._chk(self.f("get_info")(self.ctx, 0, self.B, arr))
+        return arr
+
+    def duals(self):
+        vs = np.zeros((self.B, self.N + 1, self.ncmax))
+        lams = np.zeros((self.B, self.N + 1, self.ndx))
+        self._chk(self.f("get_duals")(self.ctx, 0, self.B, P(vs), P(lams)))
+        return vs, lams
+
+    def xdot(self, t):
+        out = np.zeros((self.B, self.ndx))
+        self._chk(self.f("get_xdot")(self.ctx, 0, self.B, t, P(out)))
+        return out
+
+
+class Go2Scenario:
+    """Config C1/C5 of SURVEY.md §8d on the synthetic go2-like robot: kinodynamics, T = 50, trot 10/30/10/30,
+    per-instance gait phase offset and state perturbation (numpy default_rng(seed), instance i = stream i)."""
+
+    GAIT = [0b1111] * 10 + [0b0110] * 30 + [0b1111] * 10 + [0b1001] * 30  # FL=bit0 FR=bit1 RL=bit2 RR=bit3
+
+    def __init__(self, batch, seed=0, T=50, **ocp_kw):
+        self.B, self.T = batch, T
+        self.model, self.limits = go2_like_model()
+        self.ocpb = go2_kino_ocp(self.model, self.limits, T=T, **ocp_kw)
+        self.nq, self.nv = self.model.nq, self.model.nv
+        self.nx, self.ndx, self.nu = self.nq + self.nv, 2 * self.nv, self.nv - 6 + 12
+        self.xref = x_ref_of(self.model)
+        self.feet = fk_numpy(self.model, self.xref[: self.nq])["feet"]
+        self.mass = total_mass(self.model)
+        rngs = [np.random.default_rng([seed, i]) for i in range(batch)]
+        self.phase = np.array([int(r.integers(0, 80)) for r in rngs])
+        self.noise = [r for r in rngs]
+        self.tick = 0
+
+    def gait_slot(self, k):
+        mask = self.GAIT[k % 80]
+        prev = self.GAIT[(k - 1) % 80]
+        land = mask & ~prev
+        nact = bin(mask).count("1")
+        return standing_slot(self.model, self.ocpb, self.feet, contact_mask=mask, land_mask=land,
+                             force_z=self.mass * 9.81 / max(nact, 1))
+
+    def initial_slots(self):
+        # createProblem: T all-feet-in-contact stages with Identity foot poses (reference src/ocp-handler.cpp:111-126)
+        ident = [(np.eye(3), np.zeros(3)) for _ in range(4)]
+        s = standing_slot(self.model, self.ocpb, ident)
+        return (Slot * (self.B * self.T))(*([s] * (self.B * self.T)))
+
+    def terminals(self):
+        t = Terminal()
+        t.x_ref[: self.nx] = self.xref
+        t.com_ref[:] = [0.0, 0.0, 0.3]
+        return (Terminal * self.B)(*([t] * self.B))
+
+    def warmstart(self):
+        s0 = standing_slot(self.model, self.ocpb, self.feet)
+        xs = np.tile(self.xref, (self.B, self.T + 1, 1)).copy()
+        us = np.tile(np.array(s0.u_ref[: self.nu]), (self.B, self.T, 1)).copy()
+        return xs, us
+
+    def x_start(self):
+        """perturbed initial states"""
+        xs = np.tile(self.xref, (self.B, 1))
+        for i, r in enumerate(self.noise):
+            xs[i, 7:19] += r.normal(size=12) * 0.02
+            xs[i, 0:3] += r.normal(size=3) * 0.01
+            xs[i, 19:] += r.normal(size=18) * 0.05
+        return xs
+
+    def tails(self, tick):
+        arr = (Slot * self.B)()
+        for i in range(self.B):
+            arr[i] = self.gait_slot(int(self.phase[i]) + tick)
+        return arr
+
+
+def relerr(a, b):
+    den = max(np.abs(b).max(), 1e-300)
+    return float(np.abs(a - b).max() / den)
+
+
+def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, **ocp_kw):
+    """Drive the oracle and the CUDA library through the same constructor solve + `ticks` MPC ticks and return
+    the worst normwise relative differences."""
+    orc, cu = load_oracle(), load_cuda()
+    sc = Go2Scenario(batch, seed, **ocp_kw)
+    opts_o, opts_c = SolverOpts(), SolverOpts()
+    orc.orc_default_solver_opts(C.byref(opts_o))
+    cu.smpc_default_solver_opts(C.byref(opts_c))
+    assert bytes(opts_o) == bytes(opts_c), "default solver options differ"
+    bo = Backend(orc, "orc", sc.model, sc.ocpb, opts_o, batch)
+    bc = Backend(cu, "smpc", sc.model, sc.ocpb, opts_c, batch)
+    worst = dict(xs=0.0, us=0.0, K=0.0, k=0.0, iters_equal=True, alphas_equal=True, prim=0.0, dual=0.0)
+    try:
+        for b in (bo, bc):
+            b.set_slots(sc.initial_slots())
+            b.set_terminal(sc.terminals())
+            xs, us = sc.warmstart()
+            b.set_warmstart(xs, us)
+        # constructor solve at the reference state (reference src/mpc.cpp:24-26,85); disturbances enter at the ticks
+        x = np.tile(sc.xref, (batch, 1))
+
+        def compare(tag):
+            xo, uo, Ko, ko = bo.results()
+            xc, uc, Kc, kc = bc.results()
+            io, ic = bo.info(), bc.info()
+            for i in range(batch):
+                worst["xs"] = max(worst["xs"], relerr(xc[i], xo[i]))
+                worst["us"] = max(worst["us"], relerr(uc[i], uo[i]))
+                worst["K"] = max(worst["K"], max(relerr(Kc[i, t], Ko[i, t]) for t in range(sc.T)))
+                worst["k"] = max(worst["k"], relerr(kc[i], ko[i]))
+                if io[i].num_iters != ic[i].num_iters or io[i].conv != ic[i].conv:
+                    worst["iters_equal"] = False
+                if io[i].alpha != ic[i].alpha or io[i].ls_trials != ic[i].ls_trials:
+                    worst["alphas_equal"] = False
+                worst["prim"] = max(worst["prim"], abs(io[i].prim_infeas - ic[i].prim_infeas) / max(abs(io[i].prim_infeas), 1e-300))
+                worst["dual"] = max(worst["dual"], abs(io[i].dual_infeas - ic[i].dual_infeas) / max(abs(io[i].dual_infeas), 1e-300))
+            if verbose:
+                print(tag, "iters", [(io[i].num_iters, ic[i].num_iters) for i in range(batch)], "alpha", [(io[i].alpha, ic[i].alpha) for i in range(batch)],
+                      {k: ("%.2e" % v if isinstance(v, float) else v) for k, v in worst.items()})
+            return xo
+
+        bo.solve(x, ctor_iters)
+        bc.solve(x, ctor_iters)
+        xo = compare("ctor")
+        for tick in range(ticks):
+            tails = sc.tails(tick)
+            # measured state: the oracle's predicted next state plus a small disturbance (same for both backends)
+            x = xo[:, 1, :].copy()
+            for i, r in enumerate(sc.noise):
+                x[i, 19:] += r.normal(size=18) * (0.05 if tick == 0 else 0.01)
+                if tick == 0:
+                    x[i, 7:19] += r.normal(size=12) * 0.02
+            for b in (bo, bc):
+                b.cycle(tails)
+                b.shift()
+                b.solve(x, 1)
+            xo = compare("tick %d" % tick)
+    finally:
+        bo.close()
+        bc.close()
+    return worst
