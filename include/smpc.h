@@ -208,6 +208,11 @@ int smpc_set_terminal(smpc_ctx *, int first, int n_inst, const smpc_terminal * t
 /* replaces: replaceStageCircular + cycleProblem           (reference src/mpc.cpp:225-226,246-247)
  * drops slot 0 of each instance, appends new_tail[i]; solver duals rotate with it. */
 int smpc_cycle(smpc_ctx *, int first, int n_inst, const smpc_slot * new_tail);
+/* replaces: MPC::generateCycleHorizon's table of pre-built stages   (reference src/mpc.cpp:101-187)
+ * the stages stay resident in HBM; smpc_cycle_ids appends table[ids[i]] to instance first+i, so a tick
+ * moves 4 bytes per instance over PCIe instead of one smpc_slot. */
+int smpc_upload_stage_table(smpc_ctx *, const smpc_slot * stages, int n);
+int smpc_cycle_ids(smpc_ctx *, int first, int n_inst, const int * ids);
 
 /* replaces: the warm-start arguments of run(problem, xs_, us_)   (reference src/mpc.cpp:201-207,212)
  * xs [n_inst][T+1][nx], us [n_inst][T][nu]. */
@@ -243,6 +248,13 @@ int smpc_get_contact_forces(smpc_ctx *, int first, int n_inst, int t, double * f
 int smpc_last_solve_ms(smpc_ctx *, float * total_ms, float * riccati_ms);
 /* number of kernel launches issued by this context so far */
 int64_t smpc_launch_count(smpc_ctx *);
+/* closed loop without a plant: x0 <- the predicted next state xs[1] of every instance (device to device) */
+int smpc_x0_from_prediction(smpc_ctx *);
+/* CUDA-event timer on the context's own stream (which = 0 start, 1 stop) and accumulated per-kernel device time */
+int smpc_timer_record(smpc_ctx *, int which);
+int smpc_timer_elapsed_ms(smpc_ctx *, float * ms);
+int smpc_timer_stats(smpc_ctx *, int reset, double * riccati_ms, int64_t * riccati_launches, double * solve_ms, int64_t * solves);
+int smpc_sync(smpc_ctx *);
 
 /* test hooks: the dense LQ knot of (instance, t) from the last linearisation, in the device layout
  * described by smpc_knot_layout: offsets {Q,S,R,q,r,A,B,f,C,D,d,size} in doubles, row-major blocks */

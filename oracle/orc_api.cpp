@@ -18,6 +18,7 @@ struct orc_ctx
 {
   int batch;
   std::vector<std::unique_ptr<Solver>> inst;
+  std::vector<smpc_slot> table;
 };
 
 static thread_local std::string g_err;
@@ -164,6 +165,31 @@ int orc_cycle(orc_ctx * c, int first, int n, const smpc_slot * tail)
     return SMPC_ERR_INVALID;
   for (int i = 0; i < n; i++)
     c->inst[first + i]->cycle(tail[i]);
+  return SMPC_OK;
+}
+int orc_upload_stage_table(orc_ctx * c, const smpc_slot * stages, int n)
+{
+  if (!c || !stages || n < 1)
+  {
+    g_err = "orc_upload_stage_table: bad arguments";
+    return SMPC_ERR_INVALID;
+  }
+  c->table.assign(stages, stages + n);
+  return SMPC_OK;
+}
+int orc_cycle_ids(orc_ctx * c, int first, int n, const int * ids)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    if (ids[i] < 0 || ids[i] >= (int)c->table.size())
+    {
+      g_err = "orc_cycle_ids: stage id out of range";
+      return SMPC_ERR_INVALID;
+    }
+    c->inst[first + i]->cycle(c->table[ids[i]]);
+  }
   return SMPC_OK;
 }
 int orc_set_warmstart(orc_ctx * c, int first, int n, const double * xs, const double * us)

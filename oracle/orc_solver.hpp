@@ -646,6 +646,10 @@ namespace orc
     bool run(const double * x0, int max_iters)
     {
       xs[0].assign(x0, x0 + nx); // force_initial_condition_ (reference src/mpc.cpp:53)
+      // the nonmonotone reference value belongs to one run: a stale average from the previous tick's
+      // (different) problem would reject every step whenever the merit jumps between ticks
+      ls_mov_avg = 0;
+      ls_avg_weight = 0;
       mu = opt.mu_init;
       prev_vs = vs;
       prev_lams = lams;

@@ -48,6 +48,8 @@ namespace
     const DevOcp * ocp;
     smpc_solver_opts opt;
     smpc_slot * slots;   // [B][N] ring buffer, head in InstState
+    smpc_slot * table;   // stage table (the cycle horizon of MPC::generateCycleHorizon), ntable entries
+    int ntable;
     smpc_terminal * term; // [B]
     double *x0, *xs, *us, *vs, *lams, *prev_vs, *prev_lams, *txs, *tus;
     double * knots;
@@ -94,6 +96,8 @@ namespace
       st.ls_trials = 0;
       st.flags = 0;
       st.alpha = 0;
+      st.ls_mov_avg = 0; // the nonmonotone reference value is per run (see oracle/orc_solver.hpp run())
+      st.ls_avg_weight = 0;
       st.max_iters = max_iters;
       st.phase = (max_iters > 0 && o.max_al_iters > 0) ? PH_ACTIVE : PH_DONE;
     }
@@ -370,7 +374,7 @@ namespace
   }
 
   // replaceStageCircular + cycleProblem (reference src/mpc.cpp:225-226): new tail slot, duals follow
-  __global__ void k_cycle(Arrays A, int first, const smpc_slot * tails)
+  __global__ void k_cycle(Arrays A, int first, const smpc_slot * tails, const int * ids)
   {
     const int b = first + blockIdx.x;
     const Dims & d = A.dm;
@@ -378,7 +382,7 @@ namespace
     const size_t xb = (size_t)b * (d.N + 1);
     // the slot at `head` is horizon position 0: overwrite it with the new tail, then advance head
     {
-      const int * src = reinterpret_cast<const int *>(tails + blockIdx.x);
+      const int * src = reinterpret_cast<const int *>(ids ? A.table + ids[blockIdx.x] : tails + blockIdx.x);
       int * dst = reinterpret_cast<int *>(A.slots + (size_t)b * d.N + st.head);
       for (int k = threadIdx.x; k < (int)(sizeof(smpc_slot) / sizeof(int)); k += blockDim.x)
         dst[k] = src[k];
@@ -470,6 +474,9 @@ struct smpc_ctx
   size_t h_staging_bytes = 0;
   cudaEvent_t ev0, ev1, evr0, evr1;
   float last_ms = 0, last_ric_ms = 0;
+  double acc_ric_ms = 0, acc_solve_ms = 0; // accumulated since smpc_timer_reset
+  int64_t acc_ric_launches = 0, acc_solves = 0;
+  cudaEvent_t evu0, evu1; // user timer on the context stream
   int64_t launches = 0;
   size_t knot_smem = 0, ric_smem = 0;
   void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
@@ -727,6 +734,8 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreate(&c->evr0));
   CU(cudaEventCreate(&c->evr1));
+  CU(cudaEventCreate(&c->evu0));
+  CU(cudaEventCreate(&c->evu1));
   *out = c;
   return SMPC_OK;
 }
@@ -750,6 +759,8 @@ void smpc_destroy(smpc_ctx * c)
   cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->evr0);
   cudaEventDestroy(c->evr1);
+  cudaEventDestroy(c->evu0);
+  cudaEventDestroy(c->evu1);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -837,8 +848,54 @@ int smpc_cycle(smpc_ctx * c, int first, int n, const smpc_slot * new_tail)
     return rc;
   if ((rc = h2d(c, c->staging, new_tail, bytes)) != SMPC_OK)
     return rc;
-  k_cycle<<<n, 64, 0, c->stream>>>(c->A, first, (const smpc_slot *)c->staging);
+  k_cycle<<<n, 64, 0, c->stream>>>(c->A, first, (const smpc_slot *)c->staging, nullptr);
   c->launches++;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+int smpc_upload_stage_table(smpc_ctx * c, const smpc_slot * stages, int n)
+{
+  if (!c || !stages || n < 1)
+  {
+    g_err = "smpc_upload_stage_table: bad arguments";
+    return SMPC_ERR_INVALID;
+  }
+  CU(cudaSetDevice(c->device));
+  smpc_slot * tbl = nullptr;
+  int rc = dev_alloc(c, &tbl, (size_t)n);
+  if (rc != SMPC_OK)
+    return rc;
+  CU(cudaMemcpyAsync(tbl, stages, (size_t)n * sizeof(smpc_slot), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->A.table = tbl;
+  c->A.ntable = n;
+  return SMPC_OK;
+}
+int smpc_cycle_ids(smpc_ctx * c, int first, int n, const int * ids)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (!c->A.table)
+  {
+    g_err = "smpc_cycle_ids: no stage table uploaded";
+    return SMPC_ERR_STATE;
+  }
+  for (int i = 0; i < n; i++)
+    if (ids[i] < 0 || ids[i] >= c->A.ntable)
+    {
+      g_err = "smpc_cycle_ids: stage id out of range";
+      return SMPC_ERR_INVALID;
+    }
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = ensure_staging(c, (size_t)n * sizeof(int))) != SMPC_OK)
+    return rc;
+  CU(cudaMemcpyAsync(c->staging, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  k_cycle<<<n, 64, 0, c->stream>>>(c->A, first, nullptr, (const int *)c->staging);
+  c->launches++;
+  // the staging buffer is reused by later calls: the copy above must have been consumed
   CU(cudaStreamSynchronize(c->stream));
   return SMPC_OK;
 }
@@ -937,6 +994,10 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   CU(cudaEventElapsedTime(&c->last_ric_ms, c->evr0, c->evr1));
+  c->acc_ric_ms += c->last_ric_ms;
+  c->acc_solve_ms += c->last_ms;
+  c->acc_ric_launches += 1;
+  c->acc_solves += 1;
   return SMPC_OK;
 }
 
@@ -1074,6 +1135,65 @@ int smpc_get_contact_forces(smpc_ctx * c, int first, int n, int t, double * forc
   // reference include/simple-mpc/mpc.hpp:174-178: only defined for the full-dynamics handler
   g_err = "getContactForces is only available for full-dynamics problems";
   return SMPC_ERR_UNSUPPORTED;
+}
+
+// x0 <- xs[1] of every instance (closed loop without a plant: the predicted next state is the measurement)
+int smpc_x0_from_prediction(smpc_ctx * c)
+{
+  if (!c)
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  CU(cudaMemcpy2DAsync(
+    c->A.x0, d.nx * sizeof(double), c->A.xs + d.nx, (size_t)(d.N + 1) * d.nx * sizeof(double), d.nx * sizeof(double), d.B,
+    cudaMemcpyDeviceToDevice, c->stream));
+  return SMPC_OK;
+}
+// device timer on the context's stream: which = 0 start, 1 stop
+int smpc_timer_record(smpc_ctx * c, int which)
+{
+  if (!c)
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(which ? c->evu1 : c->evu0, c->stream));
+  return SMPC_OK;
+}
+int smpc_timer_elapsed_ms(smpc_ctx * c, float * ms)
+{
+  if (!c || !ms)
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->evu1));
+  CU(cudaEventElapsedTime(ms, c->evu0, c->evu1));
+  return SMPC_OK;
+}
+// accumulated device time of the Riccati kernel / whole solves since the last reset
+int smpc_timer_stats(smpc_ctx * c, int reset, double * riccati_ms, int64_t * riccati_launches, double * solve_ms, int64_t * solves)
+{
+  if (!c)
+    return SMPC_ERR_INVALID;
+  if (riccati_ms)
+    *riccati_ms = c->acc_ric_ms;
+  if (riccati_launches)
+    *riccati_launches = c->acc_ric_launches;
+  if (solve_ms)
+    *solve_ms = c->acc_solve_ms;
+  if (solves)
+    *solves = c->acc_solves;
+  if (reset)
+  {
+    c->acc_ric_ms = c->acc_solve_ms = 0;
+    c->acc_ric_launches = c->acc_solves = 0;
+  }
+  return SMPC_OK;
+}
+int smpc_sync(smpc_ctx * c)
+{
+  if (!c)
+    return SMPC_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
 }
 
 int smpc_last_solve_ms(smpc_ctx * c, float * total_ms, float * riccati_ms)
