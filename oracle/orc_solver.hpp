@@ -62,7 +62,7 @@ namespace orc
         double s = X(i, c);
         for (int k = 0; k < i; k++)
           s = std::fma(-L(i, k), X(k, c), s);
-        X(i, c) = s / L(i, i);
+        X(i, c) = s * (1.0 / L(i, i)); // reciprocal pivot: the kernels keep 1/l, not l
       }
   }
   // X <- L^-T X
@@ -74,7 +74,7 @@ namespace orc
         double s = X(i, c);
         for (int k = n - 1; k > i; k--)
           s = std::fma(-L(k, i), X(k, c), s);
-        X(i, c) = s / L(i, i);
+        X(i, c) = s * (1.0 / L(i, i)); // reciprocal pivot: the kernels keep 1/l, not l
       }
   }
 

@@ -11,6 +11,7 @@
 // development box. That emulation is a TEST harness: it is not compiled into libsmpc_cuda.so, and
 // the product has no CPU path.
 #pragma once
+#define SMPC_SCHED_FENCE asm volatile("" ::: "memory");
 
 #ifdef __CUDACC__
 #define SMPC_DEV __device__ __forceinline__
@@ -23,8 +24,15 @@
 #define SMPC_END                                                                                                       \
   }                                                                                                                    \
   __syncthreads();
+// the one exception to "no registers across phases": a per-thread array that must survive barriers
+// (a matrix row kept in registers during a factorisation). Declared once, fetched inside each phase.
+#define SMPC_THREAD_ARRAY(name, n) double name##_reg[n];
+#define SMPC_THREAD_PTR(name, n, tid) (name##_reg)
 #else
 #include <cmath>
+#include <vector>
+#define SMPC_THREAD_ARRAY(name, n) std::vector<double> name##_all((size_t)SMPC_EMUL_NT * (n), 0.0);
+#define SMPC_THREAD_PTR(name, n, tid) (&name##_all[(size_t)(tid) * (n)])
 #ifndef SMPC_EMUL_NT
 #define SMPC_EMUL_NT 64
 #endif

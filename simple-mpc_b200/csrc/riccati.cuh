@@ -98,9 +98,9 @@ namespace smpc
     {
       SMPC_PAR(tid)
       {
-        const double lkk = L[k * ldl + k];
+        const double ilkk = 1.0 / L[k * ldl + k];
         for (int c = tid; c < m; c += SMPC_NT)
-          X[k * ldx + c] = X[k * ldx + c] / lkk;
+          X[k * ldx + c] = X[k * ldx + c] * ilkk;
       }
       SMPC_END
       SMPC_PAR(tid)
@@ -122,9 +122,9 @@ namespace smpc
     {
       SMPC_PAR(tid)
       {
-        const double lkk = L[k * ldl + k];
+        const double ilkk = 1.0 / L[k * ldl + k];
         for (int c = tid; c < m; c += SMPC_NT)
-          X[k * ldx + c] = X[k * ldx + c] / lkk;
+          X[k * ldx + c] = X[k * ldx + c] * ilkk;
       }
       SMPC_END
       SMPC_PAR(tid)

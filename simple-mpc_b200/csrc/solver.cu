@@ -12,6 +12,7 @@
 // CUDA runtime does.
 #include "kino_knot.cuh"
 #include "riccati.cuh"
+#include "riccati2.cuh"
 #include "host_build.h"
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -106,7 +107,7 @@ namespace
   template <class Cfg, bool TRIAL>
   __global__ void __launch_bounds__(64) k_knots(Arrays A)
   {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
     const Dims & d = A.dm;
     const int b = blockIdx.x / (d.N + 1);
@@ -230,7 +231,7 @@ namespace
 
   __global__ void __launch_bounds__(128) k_riccati(Arrays A)
   {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     const int b = blockIdx.x;
     const Dims & d = A.dm;
     InstState & st = A.inst[b];
@@ -240,6 +241,24 @@ namespace
     __shared__ int flag;
     riccati_backward_inst(
       A.L, A.SL, A.RS, d.N, A.knots + xb * A.L.size, A.ncs + xb, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
+      A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
+    if (threadIdx.x == 0 && flag)
+      st.flags |= 1;
+  }
+
+  template <int NDX, int NU, int NC>
+  __global__ void __launch_bounds__(128) k_riccati2(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    __shared__ int flag;
+    riccati2_backward_inst<NDX, NU, NC>(
+      A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
       st.flags |= 1;
@@ -480,6 +499,8 @@ struct smpc_ctx
   int64_t launches = 0;
   size_t knot_smem = 0, ric_smem = 0;
   void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
+  void (*launch_riccati)(smpc_ctx *) = nullptr;
+  const char * riccati_variant = "generic";
 };
 
 #define CU(call)                                                                                                       \
@@ -513,6 +534,25 @@ namespace
     CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
     CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
     c->launch_knots = &launch_knots_impl<Cfg>;
+    return SMPC_OK;
+  }
+
+  void launch_riccati_generic(smpc_ctx * c)
+  {
+    k_riccati<<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
+  }
+  template <int NDX, int NU, int NC>
+  void launch_riccati2_impl(smpc_ctx * c)
+  {
+    k_riccati2<NDX, NU, NC><<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
+  }
+  template <int NDX, int NU, int NC>
+  int setup_riccati2(smpc_ctx * c)
+  {
+    c->ric_smem = (size_t)Ric2<NDX, NU, NC>::SIZE * sizeof(double);
+    CU(cudaFuncSetAttribute(k_riccati2<NDX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    c->launch_riccati = &launch_riccati2_impl<NDX, NU, NC>;
+    c->riccati_variant = "specialised";
     return SMPC_OK;
   }
 
@@ -673,8 +713,22 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
     delete c;
     return rc;
   }
-  c->ric_smem = (size_t)A.RS.size * sizeof(double);
-  CU(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+  // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax)
+  if (O.ndx == 36 && O.nu == 24 && O.ncmax == 24)
+    rc = setup_riccati2<36, 24, 24>(c);
+  else if (O.ndx == 36 && O.nu == 24 && O.ncmax == 36)
+    rc = setup_riccati2<36, 24, 36>(c);
+  else
+  {
+    c->ric_smem = (size_t)A.RS.size * sizeof(double);
+    CU(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    c->launch_riccati = &launch_riccati_generic;
+  }
+  if (rc != SMPC_OK)
+  {
+    delete c;
+    return rc;
+  }
   const Dims & d = A.dm;
   const size_t B = d.B, N1 = d.N + 1;
   DevModel * dmodel;
@@ -965,7 +1019,7 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
     k_decide<<<d.B, 64, 0, s>>>(c->A);
     if (!timed_ric)
       CU(cudaEventRecord(c->evr0, s));
-    k_riccati<<<d.B, 128, c->ric_smem, s>>>(c->A);
+    c->launch_riccati(c);
     if (!timed_ric)
       CU(cudaEventRecord(c->evr1, s));
     timed_ric = true;
