@@ -16,6 +16,7 @@
 #include "host_build.h"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -105,7 +106,7 @@ namespace
   }
 
   template <class Cfg, bool TRIAL>
-  __global__ void __launch_bounds__(64) k_knots(Arrays A)
+  __global__ void __launch_bounds__(128) k_knots(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
     KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
@@ -246,8 +247,11 @@ namespace
       st.flags |= 1;
   }
 
+#ifndef SMPC_RIC_MINB
+#define SMPC_RIC_MINB 2
+#endif
   template <int NDX, int NU, int NC>
-  __global__ void __launch_bounds__(128) k_riccati2(Arrays A)
+  __global__ void __launch_bounds__(128, SMPC_RIC_MINB) k_riccati2(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
     const int b = blockIdx.x;
@@ -498,6 +502,7 @@ struct smpc_ctx
   cudaEvent_t evu0, evu1; // user timer on the context stream
   int64_t launches = 0;
   size_t knot_smem = 0, ric_smem = 0;
+  int knot_threads = 32;
   void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
   void (*launch_riccati)(smpc_ctx *) = nullptr;
   const char * riccati_variant = "generic";
@@ -522,15 +527,17 @@ namespace
     const Dims & d = c->A.dm;
     const int grid = d.B * (d.N + 1);
     if (trial)
-      k_knots<Cfg, true><<<grid, 64, c->knot_smem, c->stream>>>(c->A);
+      k_knots<Cfg, true><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
     else
-      k_knots<Cfg, false><<<grid, 64, c->knot_smem, c->stream>>>(c->A);
+      k_knots<Cfg, false><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
     c->launches++;
   }
   template <class Cfg>
   int setup_knots(smpc_ctx * c)
   {
     c->knot_smem = sizeof(KinoScratch<Cfg>);
+    if (const char * e = getenv("SMPC_KNOT_THREADS")) // tuning knob: 32, 64 or 128 threads per knot
+      c->knot_threads = atoi(e) == 64 ? 64 : (atoi(e) == 128 ? 128 : 32);
     CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
     CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
     c->launch_knots = &launch_knots_impl<Cfg>;
