@@ -280,7 +280,7 @@ def main():
                 "d2h_bytes_per_step": B * 8 * (sc.nx + 2 * sc.nu + sc.nu * sc.ndx), "ms_per_step": 1e3 * e2e_s / K},
         "gpu_launches": int(l1 - l0),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_riccati (proximal Riccati backward sweep, CTA per instance)",
+        "roofline": {"bound": "hbm", "kernel": "proximal Riccati backward sweep, CTA per instance, variant " + cu.smpc_riccati_variant(b.ctx).decode(),
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                      "traffic": None, "launch_ms": 1e3 * ric_avg_s,

@@ -248,6 +248,8 @@ int smpc_get_contact_forces(smpc_ctx *, int first, int n_inst, int t, double * f
 int smpc_last_solve_ms(smpc_ctx *, float * total_ms, float * riccati_ms);
 /* number of kernel launches issued by this context so far */
 int64_t smpc_launch_count(smpc_ctx *);
+/* which Riccati kernel this context launches ("tma-staged", "specialised", "generic") */
+const char * smpc_riccati_variant(smpc_ctx *);
 /* closed loop without a plant: x0 <- the predicted next state xs[1] of every instance (device to device) */
 int smpc_x0_from_prediction(smpc_ctx *);
 /* CUDA-event timer on the context's own stream (which = 0 start, 1 stop) and accumulated per-kernel device time */

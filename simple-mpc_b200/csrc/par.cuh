@@ -27,11 +27,13 @@
 // the one exception to "no registers across phases": a per-thread array that must survive barriers
 // (a matrix row kept in registers during a factorisation). Declared once, fetched inside each phase.
 #define SMPC_THREAD_ARRAY(name, n) double name##_reg[n];
+#define SMPC_THREAD_IARRAY(name, n) int name##_reg[n];
 #define SMPC_THREAD_PTR(name, n, tid) (name##_reg)
 #else
 #include <cmath>
 #include <vector>
 #define SMPC_THREAD_ARRAY(name, n) std::vector<double> name##_all((size_t)SMPC_EMUL_NT * (n), 0.0);
+#define SMPC_THREAD_IARRAY(name, n) std::vector<int> name##_all((size_t)SMPC_EMUL_NT * (n), 0);
 #define SMPC_THREAD_PTR(name, n, tid) (&name##_all[(size_t)(tid) * (n)])
 #ifndef SMPC_EMUL_NT
 #define SMPC_EMUL_NT 64

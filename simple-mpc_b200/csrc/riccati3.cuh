@@ -1,0 +1,792 @@
+// riccati3.cuh — proximal Riccati backward sweep, third layout (supersedes riccati2.cuh on the hot path).
+//
+// Same recursion and same per-element operation order as oracle/orc_solver.hpp (see riccati.cuh for the
+// algebra), so it stays bitwise equal to the oracle on identical knots. What changed against riccati2.cuh,
+// each item answering a line of profiles/r01a_ncu_summary.md:
+//   * stage data arrive by ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) of the whole dense
+//     knot (Q S R q r A B f C D d are contiguous in HBM) into shared memory, issued at the top of the stage
+//     and waited for after the factorisation of I + mu P, which does not need it. Nothing in the stage reads
+//     global memory inside a k-loop any more (C, D, d used to be read from HBM in the P update);
+//   * Q^, S^, R^, q^, r^ accumulate IN PLACE in the staged knot (no second copy of [Q S]);
+//   * factorisations are right-looking over ALL threads with the trailing matrix in registers: one barrier
+//     per column, the pivot's sqrt/reciprocal is the only serial part, and the column loop is a runtime loop
+//     (a fully unrolled factorisation made the kernel 600 KB of SASS and the sweep instruction-fetch bound);
+//     the scaled column is also written to the transposed (upper) slot, so the forward sweep reads L by rows
+//     (128-bit shared loads) exactly like the backward sweep;
+//   * every product that used strided one-output-per-thread loops (Sigma, G, Y + W G, P update) is register
+//     tiled or processes four outputs at a time, so no thread sits in one dependent FMA chain.
+//
+// Shared memory per CTA (doubles): KN knot copy · PP [NDX][NDX+1] = [p | P] · M (Cholesky of I + mu P, later
+// Sigma) · PAB = P~[A B] · YW [NU][NDX+1+NC] = [Y | W] · G [NC][NDX+1] · small vectors · the mbarrier.
+#pragma once
+#include "par.cuh"
+#include "dev_types.h"
+#include "riccati2.cuh" // ld2
+
+namespace smpc
+{
+
+  template <int NDX, int NU, int NC>
+  struct Ric3
+  {
+    static constexpr int LDP = NDX + 1;
+    static constexpr int NAB = NDX + NU;
+    static constexpr int NRY = NDX + 1 + NC;
+    // dense knot layout: must equal make_knot_layout(NDX, NU, NC) (checked by the host at create)
+    static constexpr int kQ = 0;
+    static constexpr int kS = kQ + NDX * NDX;
+    static constexpr int kR = kS + NDX * NU;
+    static constexpr int kq = kR + NU * NU;
+    static constexpr int kr = kq + NDX;
+    static constexpr int kA = kr + NU;
+    static constexpr int kB = kA + NDX * NDX;
+    static constexpr int kf = kB + NDX * NU;
+    static constexpr int kC = kf + NDX;
+    static constexpr int kD = kC + NC * NDX;
+    static constexpr int kd = kD + NC * NU;
+    static constexpr int KSIZE = (kd + NC + 1) & ~1;
+    // shared memory
+    static constexpr int oKN = 0;
+    static constexpr int oPP = oKN + KSIZE;
+    static constexpr int oM = (oPP + NDX * LDP + 1) & ~1;
+    static constexpr int szM = (NDX * NDX > NC * NC) ? NDX * NDX : NC * NC;
+    static constexpr int oPAB = oM + szM;
+    static constexpr int oYW = oPAB + NDX * NAB;
+    static constexpr int oG = (oYW + NU * NRY + 1) & ~1;
+    static constexpr int ow = (oG + NC * LDP + 1) & ~1;
+    static constexpr int oinvp = ow + NDX;
+    static constexpr int oinvr = oinvp + NDX;
+    static constexpr int oinvs = oinvr + NU;
+    static constexpr int ocol = oinvs + NC; // published pivot columns, double buffered
+    static constexpr int NMAX = (NDX > NC) ? (NDX > NU ? NDX : NU) : (NC > NU ? NC : NU);
+    static constexpr int obar = (ocol + 2 * (NMAX + 2) + 1) & ~1; // 8-byte mbarrier
+    static constexpr int oflag = obar + 2;
+    static constexpr int SIZE = oflag + 2;
+    static_assert((kA % 2) == 0 && (kB % 2) == 0 && (kC % 2) == 0 && (kQ % 2) == 0 && (kS % 2) == 0 && (kR % 2) == 0,
+                  "128-bit shared loads need even block offsets");
+    static_assert(NDX % 4 == 0 && NDX % 6 == 0 && NU % 4 == 0 && NU % 6 == 0, "4x6 tiles must divide the blocks");
+  };
+
+  // ---- bulk asynchronous global -> shared copy (TMA) -------------------------------------------------
+  // Device: cp.async.bulk completing on an mbarrier; CPU emulation harness: memcpy.
+  SMPC_DEV void bulk_init(void * bar)
+  {
+#ifdef __CUDACC__
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    (void)bar;
+#endif
+  }
+  // one thread: order earlier generic-proxy accesses of `dst` before the async-proxy write, arm, copy
+  SMPC_DEV void bulk_load(double * dst, const double * src, int ndoubles, void * bar)
+  {
+#ifdef __CUDACC__
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned bytes = (unsigned)ndoubles * 8u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+#else
+    for (int i = 0; i < ndoubles; i++)
+      dst[i] = src[i];
+    (void)bar;
+#endif
+  }
+  SMPC_DEV void bulk_wait(void * bar, unsigned parity)
+  {
+#ifdef __CUDACC__
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(b),
+      "r"(parity)
+      : "memory");
+#else
+    (void)bar;
+    (void)parity;
+#endif
+  }
+
+  // ---- right-looking Cholesky, trailing matrix in registers ----------------------------------------
+  // In: the LOWER triangle (with diagonal) of the N x N matrix M (ld LD). Out: L(i,j), i > j, in M[i][j] AND
+  // in the transposed slot M[j][i]; invd[j] = 1 / L(j,j).
+  // Ownership: thread t < N keeps diagonal entry (t,t); the N(N-1)/2 strictly-lower entries are dealt to the
+  // 128 threads (E = ceil(N(N-1)/256) each, folded-rectangle indexing); all stay in registers for the whole
+  // factorisation. Column step j is a runtime loop (a fully unrolled factorisation made the kernel 600 KB of
+  // SASS and the sweep instruction-fetch bound) of ONE phase:
+  //   - read the reciprocal pivot inv_j and the un-scaled column j from `col` (published in step j-1),
+  //   - diagonal owners: d(t) -= L(t,j)^2 ; every lane then forms 1/sqrt of its diagonal, lane j+1 publishes
+  //     it as inv_{j+1}: the only serial chain of a column (sqrt + reciprocal, 139 clocks on B200,
+  //     tools/microbench_fp64.cu) overlaps with the off-diagonal updates below, which do not depend on it,
+  //   - off-diagonal: m(i,k) -= L(i,j) L(k,j) for k > j (branch-free, predicated), entries of column j+1 are
+  //     published un-scaled.
+  // The factor is written once at the end: L(i,k) = m(i,k) inv_k. Per-entry update order is ascending j,
+  // the oracle's order, and every product is the oracle's product, so the factor is bitwise the oracle's.
+  template <int N, int LD>
+  SMPC_DEV void chol_reg(double * M, double * col /* [2][N+2] */, double * invd, int * bad)
+  {
+    static_assert(N % 2 == 0, "folded-rectangle indexing assumes an even order");
+    constexpr int NO = N * (N - 1) / 2, E = (NO + 127) / 128, RW = N - 1, CS = N + 2;
+    SMPC_THREAD_ARRAY(m, E + 1)
+    SMPC_THREAD_IARRAY(ik, 2 * E)
+    SMPC_PAR(tid)
+    {
+      double * m = SMPC_THREAD_PTR(m, E + 1, tid);
+      int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
+#pragma unroll
+      for (int q = 0; q < E; q++)
+      {
+        const int e = tid + SMPC_NT * q;
+        const int r = e / RW, c = e - r * RW;
+        // row r pairs with row N-1-r (r + N-1-r = N-1 entries); r = 0 is row N-1 alone
+        const int i = (r == 0) ? N - 1 : ((c < r) ? r : N - 1 - r);
+        const int k = (r == 0) ? c : ((c < r) ? c : c - r);
+        const bool valid = e < NO;
+        ik[2 * q] = valid ? i : 0; // a dead slot is (0,0): never above any column
+        ik[2 * q + 1] = valid ? k : 0;
+        m[q] = valid ? M[i * LD + k] : 0.0;
+        if (valid && k == 0)
+          col[i] = m[q];
+      }
+      m[E] = (tid < N) ? M[tid * LD + tid] : 1.0;
+      if (tid == 0)
+      {
+        const double d = m[E];
+        const double inv = 1.0 / sqrt(d);
+        col[N] = inv;
+        invd[0] = inv;
+        if (!(d > 0))
+          *bad = 1;
+      }
+    }
+    SMPC_END
+#pragma unroll 1
+    for (int j = 0; j < N; j++)
+    {
+      SMPC_PAR(tid)
+      {
+        double * m = SMPC_THREAD_PTR(m, E + 1, tid);
+        const int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
+        const double * cj = col + (j & 1) * CS;
+        double * cn = col + ((j + 1) & 1) * CS;
+        double ca[E], cb[E];
+#pragma unroll
+        for (int q = 0; q < E; q++)
+        {
+          ca[q] = cj[ik[2 * q]];
+          cb[q] = cj[ik[2 * q + 1]];
+        }
+        const double inv = cj[N];
+        {
+          const double lt = cj[tid < N ? tid : 0] * inv;
+          const double dn = fma(-lt, lt, m[E]);
+          if (tid > j && tid < N)
+            m[E] = dn;
+          const double d = m[E];
+          const double invn = 1.0 / sqrt(d);
+          if (tid == j + 1 && tid < N)
+          {
+            cn[N] = invn;
+            invd[j + 1] = invn;
+            if (!(d > 0))
+              *bad = 1;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < E; q++)
+        {
+          const int i = ik[2 * q], k = ik[2 * q + 1];
+          const double a = ca[q] * inv;
+          const double b = cb[q] * inv;
+          const double upd = fma(-a, b, m[q]);
+          if (k > j)
+            m[q] = upd;
+          if (k == j + 1)
+            cn[i] = upd;
+        }
+      }
+      SMPC_END
+    }
+    SMPC_PAR(tid)
+    {
+      const double * m = SMPC_THREAD_PTR(m, E + 1, tid);
+      const int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
+#pragma unroll
+      for (int q = 0; q < E; q++)
+      {
+        const int i = ik[2 * q], k = ik[2 * q + 1];
+        if (i > k)
+        {
+          const double lik = m[q] * invd[k];
+          M[i * LD + k] = lik;
+          M[k * LD + i] = lik;
+        }
+      }
+    }
+    SMPC_END
+  }
+
+  // x[i] -= row[i] * xk for i in [I0, I1): row is a shared-memory row of the factor (16-byte aligned when its
+  // element index is even); pairs of consecutive entries are fetched with one 128-bit load
+  template <int I0, int I1, int BASE>
+  SMPC_DEV void axpy_row(const double * __restrict__ Mrow, double xk, double * x)
+  {
+    // BASE = parity information: element index of Mrow[0] modulo 2 (compile time)
+    constexpr int first_even = ((BASE + I0) % 2 == 0) ? I0 : I0 + 1;
+    if (first_even > I0 && I0 < I1)
+      x[I0] = fma(-Mrow[I0], xk, x[I0]);
+#pragma unroll
+    for (int i = first_even; i + 1 < I1; i += 2)
+    {
+      double a, b;
+      ld2(Mrow + i, a, b);
+      x[i] = fma(-a, xk, x[i]);
+      x[i + 1] = fma(-b, xk, x[i + 1]);
+    }
+    constexpr int npairs = (I1 - first_even > 0) ? (I1 - first_even) / 2 : 0;
+    constexpr int last = first_even + 2 * npairs;
+    if (last < I1 && last >= first_even)
+      x[last] = fma(-Mrow[last], xk, x[last]);
+  }
+
+  template <int N, int LD, int K>
+  struct SweepFwd
+  {
+    static SMPC_DEV void run(const double * __restrict__ M, const double * __restrict__ invd, double * x)
+    {
+      x[K] = x[K] * invd[K];
+      axpy_row<K + 1, N, (K * LD) % 2>(M + K * LD, x[K], x); // upper slots of row K hold column K of L
+      SMPC_SCHED_FENCE
+      SweepFwd<N, LD, K + 1>::run(M, invd, x);
+    }
+  };
+  template <int N, int LD>
+  struct SweepFwd<N, LD, N>
+  {
+    static SMPC_DEV void run(const double *, const double *, double *) {}
+  };
+  template <int N, int LD, int K>
+  struct SweepBwd
+  {
+    static SMPC_DEV void run(const double * __restrict__ M, const double * __restrict__ invd, double * x)
+    {
+      x[K] = x[K] * invd[K];
+      axpy_row<0, K, (K * LD) % 2>(M + K * LD, x[K], x); // lower slots of row K hold row K of L
+      SMPC_SCHED_FENCE
+      SweepBwd<N, LD, K - 1>::run(M, invd, x);
+    }
+  };
+  template <int N, int LD>
+  struct SweepBwd<N, LD, -1>
+  {
+    static SMPC_DEV void run(const double *, const double *, double *) {}
+  };
+
+  // X <- L^-1 X (FWD) / X <- L^-T X (BWD) for the N x MC block X (ld LDX); factor from chol_rl (LD even).
+  // One thread per column, the column in registers, no barrier inside.
+  template <int N, int LD, int MC, int LDX, bool FWD, bool BWD>
+  SMPC_DEV void sweep_cols(const double * __restrict__ M, const double * __restrict__ invd, double * __restrict__ X)
+  {
+    static_assert(MC <= 128, "one thread per column");
+    static_assert(LD % 2 == 0, "factor rows must keep 16-byte alignment");
+    SMPC_PAR(tid)
+    const int c = tid;
+    if (c < MC)
+    {
+      double x[N];
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        x[i] = X[i * LDX + c];
+      if (FWD)
+        SweepFwd<N, LD, 0>::run(M, invd, x);
+      if (BWD)
+        SweepBwd<N, LD, N - 1>::run(M, invd, x);
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        X[i * LDX + c] = x[i];
+    }
+    SMPC_END
+  }
+
+  template <int NDX, int NU, int NC>
+  SMPC_DEV void riccati3_backward_inst(
+    const KnotLayout & L, const SolLayout & SL, int N, const double * __restrict__ knots, double * __restrict__ sol,
+    double mudyn, double mueq, double * sm, int * flag_out, double * P0out)
+  {
+    typedef Ric3<NDX, NU, NC> R;
+    constexpr int LDP = R::LDP, NAB = R::NAB, NRY = R::NRY;
+    double * KN = sm + R::oKN;
+    double * PP = sm + R::oPP; // [NDX][LDP]: col 0 = p, cols 1.. = P
+    double * Mb = sm + R::oM;
+    double * PAB = sm + R::oPAB;
+    double * YW = sm + R::oYW;
+    double * G = sm + R::oG;
+    double * w = sm + R::ow;
+    double * invp = sm + R::oinvp;
+    double * invr = sm + R::oinvr;
+    double * invs = sm + R::oinvs;
+    double * colb = sm + R::ocol;
+    void * bar = (void *)(sm + R::obar);
+    int * bad = (int *)(sm + R::oflag);
+    double * Qh = KN + R::kQ; // accumulate in place
+    double * Sh = KN + R::kS;
+    double * Rh = KN + R::kR;
+    double * qh = KN + R::kq;
+    double * rh = KN + R::kr;
+    const double * Ak = KN + R::kA;
+    const double * Bk = KN + R::kB;
+    const double * fk = KN + R::kf;
+    const double * Ck = KN + R::kC;
+    const double * Dk = KN + R::kD;
+    const double * dk = KN + R::kd;
+    double * Sg = Mb;
+    const double inv_mu = 1.0 / mueq;
+    unsigned parity = 0;
+
+    // ---- terminal node: Z = C/mu, z = d/mu ; P = Q + C^T Z ; p = q + C^T z ----
+    {
+      const double * kn = knots + (size_t)N * L.size;
+      double * so = sol + (size_t)N * SL.size;
+      SMPC_PAR(tid)
+      {
+        if (tid == 0)
+        {
+          *bad = 0;
+          bulk_init(bar);
+        }
+        for (int e = tid; e < NC * NDX; e += SMPC_NT)
+          so[SL.oZ + e] = kn[L.oC + e] * inv_mu;
+        for (int i = tid; i < NC; i += SMPC_NT)
+          so[SL.oz + i] = kn[L.od + i] * inv_mu;
+      }
+      SMPC_END
+      SMPC_PAR(tid)
+      for (int e = tid; e < NDX * LDP; e += SMPC_NT)
+      {
+        const int a = e / LDP, bb = e % LDP;
+        double acc;
+        if (bb == 0)
+        {
+          acc = kn[L.oq + a];
+          for (int i = 0; i < NC; i++)
+            acc = fma(kn[L.oC + i * NDX + a], so[SL.oz + i], acc);
+        }
+        else
+        {
+          acc = kn[L.oQ + a * NDX + (bb - 1)];
+          for (int i = 0; i < NC; i++)
+            acc = fma(kn[L.oC + i * NDX + a], so[SL.oZ + i * NDX + (bb - 1)], acc);
+        }
+        PP[e] = acc;
+      }
+      SMPC_END
+    }
+
+    for (int t = N - 1; t >= 0; t--)
+    {
+      const double * kn = knots + (size_t)t * L.size;
+      double * so = sol + (size_t)t * SL.size;
+      // ---- 0. start the copy of this stage's knot; M = I + mudyn P (lower) ----
+      SMPC_PAR(tid)
+      {
+        if (tid == 0)
+          bulk_load(KN, kn, R::KSIZE, bar);
+        if (mudyn > 0)
+          for (int e = tid; e < NDX * NDX; e += SMPC_NT)
+          {
+            const int a = e / NDX, b = e % NDX;
+            if (b <= a)
+              Mb[e] = mudyn * PP[a * LDP + 1 + b] + (a == b ? 1.0 : 0.0);
+          }
+      }
+      SMPC_END
+      // ---- 1. [p~ | P~] = (I + mudyn P)^-1 [p | P], in place ----
+      if (mudyn > 0)
+      {
+        chol_reg<NDX, NDX>(Mb, colb, invp, bad);
+        sweep_cols<NDX, NDX, LDP, LDP, true, false>(Mb, invp, PP);
+        sweep_cols<NDX, NDX, LDP, LDP, false, true>(Mb, invp, PP);
+      }
+      // ---- 2. knot landed ; P~ p~ out (for the forward sweep) ; w = P~ f + p~ ; PAB = P~ [A B] ----
+      SMPC_PAR(tid)
+      {
+        bulk_wait(bar, parity);
+        for (int e = tid; e < NDX * LDP; e += SMPC_NT)
+        {
+          const int a = e / LDP, bb = e % LDP;
+          if (bb == 0)
+            so[SL.opt + a] = PP[e];
+          else
+            so[SL.oPt + a * NDX + (bb - 1)] = PP[e];
+        }
+        constexpr int TR = NDX / 4, TCA = NDX / 6, TC = NAB / 6;
+        static_assert(TR * TC + NDX <= 128, "one tile per thread plus the w rows");
+        if (tid < TR * TC)
+        {
+          const int a0 = 4 * (tid / TC), tc = tid % TC;
+          const bool inA = tc < TCA;
+          const double * src = inA ? Ak + 6 * tc : Bk + 6 * (tc - TCA);
+          const int lds = inA ? NDX : NU;
+          double c[4][6];
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              c[r][q] = 0.0;
+#pragma unroll 4
+          for (int k = 0; k < NDX; k++)
+          {
+            double bv[6];
+            ld2(src + k * lds, bv[0], bv[1]);
+            ld2(src + k * lds + 2, bv[2], bv[3]);
+            ld2(src + k * lds + 4, bv[4], bv[5]);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+              const double pk = PP[(a0 + r) * LDP + 1 + k];
+#pragma unroll
+              for (int q = 0; q < 6; q++)
+                c[r][q] = fma(pk, bv[q], c[r][q]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              PAB[(a0 + r) * NAB + 6 * tc + q] = c[r][q];
+        }
+        else if (tid - TR * TC < NDX)
+        {
+          const int a = tid - TR * TC;
+          double acc = PP[a * LDP];
+          for (int b = 0; b < NDX; b++)
+            acc = fma(PP[a * LDP + 1 + b], fk[b], acc);
+          w[a] = acc;
+        }
+      }
+      SMPC_END
+      parity ^= 1u;
+      // ---- 3. [Qh | Sh] = [Q | S] + A^T PAB ; Rh = R + B^T PB ; qh = q + A^T w ; rh = r + B^T w (in place) ----
+      SMPC_PAR(tid)
+      {
+        constexpr int TR = NDX / 4, TCA = NDX / 6, TC = NAB / 6, TRU = NU / 4, TCU = NU / 6;
+        static_assert(TR * TC + TRU * TCU <= 128, "one tile per thread");
+        if (tid < TR * TC + TRU * TCU)
+        {
+          const bool isR = tid >= TR * TC;
+          const int tt = isR ? tid - TR * TC : tid;
+          // left operand: columns a0.. of A (Qh, Sh rows) or of B (Rh rows); right operand: columns b0.. of PAB
+          const int ar = isR ? 4 * (tt / TCU) : 4 * (tt / TC);
+          const int tc = isR ? tt % TCU : tt % TC;
+          const double * lhs = isR ? Bk + ar : Ak + ar;
+          const int ldl = isR ? NU : NDX;
+          const int b0 = isR ? NDX + 6 * tc : 6 * tc;
+          double * out;
+          int ldo;
+          if (isR)
+            out = Rh + ar * NU + 6 * tc, ldo = NU;
+          else if (tc < TCA)
+            out = Qh + ar * NDX + 6 * tc, ldo = NDX;
+          else
+            out = Sh + ar * NU + 6 * (tc - TCA), ldo = NU;
+          double c[4][6];
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              c[r][q] = out[r * ldo + q];
+#pragma unroll 4
+          for (int k = 0; k < NDX; k++)
+          {
+            double av[4], bv[6];
+            ld2(lhs + k * ldl, av[0], av[1]);
+            ld2(lhs + k * ldl + 2, av[2], av[3]);
+            ld2(PAB + k * NAB + b0, bv[0], bv[1]);
+            ld2(PAB + k * NAB + b0 + 2, bv[2], bv[3]);
+            ld2(PAB + k * NAB + b0 + 4, bv[4], bv[5]);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+              for (int q = 0; q < 6; q++)
+                c[r][q] = fma(av[r], bv[q], c[r][q]);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              out[r * ldo + q] = c[r][q];
+        }
+        if (tid < NAB)
+        {
+          const bool isq = tid < NDX;
+          const double * col = isq ? Ak + tid : Bk + (tid - NDX);
+          const int ld = isq ? NDX : NU;
+          double * dst = isq ? qh + tid : rh + (tid - NDX);
+          double acc = *dst;
+          for (int k = 0; k < NDX; k++)
+            acc = fma(col[k * ld], w[k], acc);
+          *dst = acc;
+        }
+      }
+      SMPC_END
+      // ---- 4. KKT by block LDL^T ----
+      chol_reg<NU, NU>(Rh, colb, invr, bad);
+      SMPC_PAR(tid)
+      for (int e = tid; e < NU * NRY; e += SMPC_NT)
+      {
+        const int a = e / NRY, c = e % NRY;
+        double v;
+        if (c == 0)
+          v = rh[a];
+        else if (c <= NDX)
+          v = Sh[(c - 1) * NU + a];
+        else
+          v = Dk[(c - NDX - 1) * NU + a];
+        YW[e] = v;
+      }
+      SMPC_END
+      sweep_cols<NU, NU, NRY, NRY, true, false>(Rh, invr, YW);
+      if (NC > 0)
+      {
+        // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : four outputs at a time per thread
+        SMPC_PAR(tid)
+        {
+          constexpr int NSG = NC * NC, NGG = NC * LDP, NOUT = NSG + NGG;
+          for (int e0 = tid; e0 < NOUT; e0 += 4 * SMPC_NT)
+          {
+            double acc[4];
+            int wi[4], yc[4];
+            bool live[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+              const int e = e0 + q * SMPC_NT;
+              live[q] = e < NOUT;
+              wi[q] = 0, yc[q] = 0, acc[q] = 0.0;
+              if (live[q])
+              {
+                if (e < NSG)
+                {
+                  const int i = e / NC, j = e % NC;
+                  live[q] = j <= i;
+                  wi[q] = LDP + i, yc[q] = LDP + j;
+                  acc[q] = (i == j) ? mueq : 0.0;
+                }
+                else
+                {
+                  const int g = e - NSG;
+                  const int i = g / LDP, c = g % LDP;
+                  wi[q] = LDP + i, yc[q] = c;
+                  acc[q] = (c == 0) ? dk[i] : Ck[i * NDX + (c - 1)];
+                }
+              }
+            }
+            for (int k = 0; k < NU; k++)
+            {
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+              {
+                const double wv = YW[k * NRY + wi[q]];
+                const double yv = YW[k * NRY + yc[q]];
+                // Sigma accumulates +W W, G accumulates -W Y (the sign sits on the first operand as in the oracle)
+                acc[q] = (yc[q] >= LDP) ? fma(wv, yv, acc[q]) : fma(-wv, yv, acc[q]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (live[q])
+              {
+                const int e = e0 + q * SMPC_NT;
+                if (e < NSG)
+                  Sg[e] = acc[q];
+                else
+                  G[e - NSG] = acc[q];
+              }
+          }
+        }
+        SMPC_END
+        chol_reg<NC, NC>(Sg, colb, invs, bad);
+        sweep_cols<NC, NC, LDP, LDP, true, false>(Sg, invs, G);
+        sweep_cols<NC, NC, LDP, LDP, false, true>(Sg, invs, G);
+        // Y <- Y + W G
+        SMPC_PAR(tid)
+        {
+          constexpr int NOUT = NU * LDP;
+          for (int e0 = tid; e0 < NOUT; e0 += 4 * SMPC_NT)
+          {
+            double acc[4];
+            int ra[4], cc[4];
+            bool live[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+              const int e = e0 + q * SMPC_NT;
+              live[q] = e < NOUT;
+              ra[q] = live[q] ? e / LDP : 0;
+              cc[q] = live[q] ? e % LDP : 0;
+              acc[q] = YW[ra[q] * NRY + cc[q]];
+            }
+            for (int i = 0; i < NC; i++)
+            {
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+                acc[q] = fma(YW[ra[q] * NRY + LDP + i], G[i * LDP + cc[q]], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (live[q])
+                YW[ra[q] * NRY + cc[q]] = acc[q];
+          }
+        }
+        SMPC_END
+      }
+      sweep_cols<NU, NU, LDP, NRY, false, true>(Rh, invr, YW);
+      // ---- gains: [k | K] = -Y, [z | Z] = G ----
+      SMPC_PAR(tid)
+      {
+        for (int e = tid; e < NU * LDP; e += SMPC_NT)
+        {
+          const int a = e / LDP, c = e % LDP;
+          const double val = -YW[a * NRY + c];
+          YW[a * NRY + c] = val;
+          if (c == 0)
+            so[SL.ok + a] = val;
+          else
+            so[SL.oK + a * NDX + (c - 1)] = val;
+        }
+        for (int e = tid; e < NC * LDP; e += SMPC_NT)
+        {
+          const int i = e / LDP, c = e % LDP;
+          if (c == 0)
+            so[SL.oz + i] = G[e];
+          else
+            so[SL.oZ + i * NDX + (c - 1)] = G[e];
+        }
+      }
+      SMPC_END
+      // ---- 5. [p | P] = [qh | Qh] + Sh [k | K] + C^T [z | Z] : 4x3 register tiles, p by the remaining threads ----
+      SMPC_PAR(tid)
+      {
+        constexpr int TR = NDX / 4, TC = NDX / 3;
+        static_assert(TR * TC + (NDX + 1) / 2 <= 128, "one tile per thread plus the p rows");
+        if (tid < TR * TC)
+        {
+          const int a0 = 4 * (tid / TC), b0 = 3 * (tid % TC);
+          double c[4][3];
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              c[r][q] = Qh[(a0 + r) * NDX + b0 + q];
+#pragma unroll 4
+          for (int k = 0; k < NU; k++)
+          {
+            double kv[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              kv[q] = YW[k * NRY + 1 + b0 + q];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+              const double sv = Sh[(a0 + r) * NU + k];
+#pragma unroll
+              for (int q = 0; q < 3; q++)
+                c[r][q] = fma(sv, kv[q], c[r][q]);
+            }
+          }
+#pragma unroll 4
+          for (int i = 0; i < NC; i++)
+          {
+            double cv[4], zv[3];
+            ld2(Ck + i * NDX + a0, cv[0], cv[1]);
+            ld2(Ck + i * NDX + a0 + 2, cv[2], cv[3]);
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              zv[q] = G[i * LDP + 1 + b0 + q];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+              for (int q = 0; q < 3; q++)
+                c[r][q] = fma(cv[r], zv[q], c[r][q]);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+              PP[(a0 + r) * LDP + 1 + b0 + q] = c[r][q];
+        }
+        else
+        {
+          // p: two rows per thread, two independent chains
+          const int a1 = 2 * (tid - TR * TC), a2 = a1 + 1;
+          if (a1 < NDX)
+          {
+            const bool two = a2 < NDX;
+            const int a2c = two ? a2 : a1;
+            double p1 = qh[a1], p2 = qh[a2c];
+            for (int k = 0; k < NU; k++)
+            {
+              const double kv = YW[k * NRY];
+              p1 = fma(Sh[a1 * NU + k], kv, p1);
+              p2 = fma(Sh[a2c * NU + k], kv, p2);
+            }
+            for (int i = 0; i < NC; i++)
+            {
+              const double zv = G[i * LDP];
+              p1 = fma(Ck[i * NDX + a1], zv, p1);
+              p2 = fma(Ck[i * NDX + a2c], zv, p2);
+            }
+            PP[a1 * LDP] = p1;
+            if (two)
+              PP[a2 * LDP] = p2;
+          }
+        }
+      }
+      SMPC_END
+      // symmetrise P (two phases: read both halves, then write)
+      SMPC_PAR(tid)
+      for (int e = tid; e < NDX * NDX; e += SMPC_NT)
+      {
+        const int a = e / NDX, b = e % NDX;
+        if (b < a)
+          Mb[e] = 0.5 * (PP[a * LDP + 1 + b] + PP[b * LDP + 1 + a]);
+      }
+      SMPC_END
+      SMPC_PAR(tid)
+      for (int e = tid; e < NDX * NDX; e += SMPC_NT)
+      {
+        const int a = e / NDX, b = e % NDX;
+        if (b < a)
+        {
+          PP[a * LDP + 1 + b] = Mb[e];
+          PP[b * LDP + 1 + a] = Mb[e];
+        }
+      }
+      SMPC_END
+    }
+    SMPC_PAR(tid)
+    {
+      if (tid == 0 && flag_out)
+        *flag_out = *bad;
+      if (P0out) // layout expected by riccati_forward_inst: [P | p]
+        for (int e = tid; e < NDX * LDP; e += SMPC_NT)
+        {
+          const int a = e / LDP, bb = e % LDP;
+          P0out[a * LDP + (bb == 0 ? NDX : bb - 1)] = PP[e];
+        }
+    }
+    SMPC_END
+  }
+
+} // namespace smpc

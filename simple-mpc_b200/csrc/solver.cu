@@ -13,6 +13,7 @@
 #include "kino_knot.cuh"
 #include "riccati.cuh"
 #include "riccati2.cuh"
+#include "riccati3.cuh"
 #include "host_build.h"
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -262,6 +263,24 @@ namespace
     const size_t xb = (size_t)b * (d.N + 1);
     __shared__ int flag;
     riccati2_backward_inst<NDX, NU, NC>(
+      A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
+      A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
+    if (threadIdx.x == 0 && flag)
+      st.flags |= 1;
+  }
+
+  template <int NDX, int NU, int NC>
+  __global__ void __launch_bounds__(128, SMPC_RIC_MINB) k_riccati3(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    __shared__ int flag;
+    riccati3_backward_inst<NDX, NU, NC>(
       A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
@@ -563,6 +582,29 @@ namespace
     return SMPC_OK;
   }
 
+  template <int NDX, int NU, int NC>
+  void launch_riccati3_impl(smpc_ctx * c)
+  {
+    k_riccati3<NDX, NU, NC><<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
+  }
+  template <int NDX, int NU, int NC>
+  int setup_riccati3(smpc_ctx * c)
+  {
+    typedef Ric3<NDX, NU, NC> R;
+    const KnotLayout & L = c->A.L;
+    if (L.oQ != R::kQ || L.oS != R::kS || L.oR != R::kR || L.oq != R::kq || L.or_ != R::kr || L.oA != R::kA || L.oB != R::kB
+        || L.of != R::kf || L.oC != R::kC || L.oD != R::kD || L.od != R::kd || L.size != R::KSIZE)
+    {
+      g_err = "riccati3: compile-time knot layout differs from make_knot_layout";
+      return SMPC_ERR_INVALID;
+    }
+    c->ric_smem = (size_t)R::SIZE * sizeof(double);
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC>;
+    c->riccati_variant = "tma-staged";
+    return SMPC_OK;
+  }
+
   template <class T>
   int dev_alloc(smpc_ctx * c, T ** p, size_t n)
   {
@@ -721,9 +763,16 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
     return rc;
   }
   // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax)
-  if (O.ndx == 36 && O.nu == 24 && O.ncmax == 24)
+  // SMPC_RICCATI=2 selects the previous specialised sweep (A/B timing), =0 the generic one
+  const char * rv = getenv("SMPC_RICCATI");
+  const int ric = rv ? atoi(rv) : 3;
+  if (ric == 3 && O.ndx == 36 && O.nu == 24 && O.ncmax == 24)
+    rc = setup_riccati3<36, 24, 24>(c);
+  else if (ric == 3 && O.ndx == 36 && O.nu == 24 && O.ncmax == 36)
+    rc = setup_riccati3<36, 24, 36>(c);
+  else if (ric >= 2 && O.ndx == 36 && O.nu == 24 && O.ncmax == 24)
     rc = setup_riccati2<36, 24, 24>(c);
-  else if (O.ndx == 36 && O.nu == 24 && O.ncmax == 36)
+  else if (ric >= 2 && O.ndx == 36 && O.nu == 24 && O.ncmax == 36)
     rc = setup_riccati2<36, 24, 36>(c);
   else
   {
@@ -1268,6 +1317,7 @@ int smpc_last_solve_ms(smpc_ctx * c, float * total_ms, float * riccati_ms)
   return SMPC_OK;
 }
 int64_t smpc_launch_count(smpc_ctx * c) { return c ? c->launches : 0; }
+const char * smpc_riccati_variant(smpc_ctx * c) { return c ? c->riccati_variant : ""; }
 
 // LQ knot t of instance `inst` as assembled by the last linearisation (test hook; device layout -> dense blocks)
 int smpc_get_knot(smpc_ctx * c, int inst, int t, int * nc, double * knot_out /* KnotLayout.size doubles */)

@@ -5,6 +5,7 @@
 #include "../../simple-mpc_b200/csrc/kino_knot.cuh"
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati2.cuh"
+#include "../../simple-mpc_b200/csrc/riccati3.cuh"
 #include "../../simple-mpc_b200/csrc/host_build.h"
 #include <memory>
 #include <vector>
@@ -106,6 +107,34 @@ int emul_riccati2(
   else
   {
     g_err = "emul_riccati2: size not instantiated";
+    return -1;
+  }
+  riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
+  return 0;
+}
+
+// same, through the TMA-staged sweep of riccati3.cuh (the one the library launches)
+int emul_riccati3(
+  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
+  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
+  double * dphi, int * flag)
+{
+  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
+  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
+  std::vector<double> P0((size_t)ndx * (ndx + 1), 0.0), sm2(4 * ndx + nu + 80, 0.0);
+  if (ndx == 36 && nu == 24 && ncmax == 24)
+  {
+    std::vector<double> sm(Ric3<36, 24, 24>::SIZE + 8, 0.0);
+    riccati3_backward_inst<36, 24, 24>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+  }
+  else if (ndx == 36 && nu == 24 && ncmax == 36)
+  {
+    std::vector<double> sm(Ric3<36, 24, 36>::SIZE + 8, 0.0);
+    riccati3_backward_inst<36, 24, 36>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+  }
+  else
+  {
+    g_err = "emul_riccati3: size not instantiated";
     return -1;
   }
   riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());

@@ -104,6 +104,7 @@ def load_cuda():
     lib = C.CDLL(path)
     lib.smpc_last_error.restype = C.c_char_p
     lib.smpc_launch_count.restype = C.c_int64
+    lib.smpc_riccati_variant.restype = C.c_char_p
     return lib
 
 
