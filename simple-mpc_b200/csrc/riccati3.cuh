@@ -118,56 +118,69 @@ namespace smpc
 #endif
   }
 
-  // ---- right-looking Cholesky, trailing matrix in registers ----------------------------------------
+  // ---- right-looking Cholesky, trailing matrix in registers, one warp dedicated to the pivots ---------
   // In: the LOWER triangle (with diagonal) of the N x N matrix M (ld LD). Out: L(i,j), i > j, in M[i][j] AND
   // in the transposed slot M[j][i]; invd[j] = 1 / L(j,j).
-  // Ownership: thread t < N keeps diagonal entry (t,t); the N(N-1)/2 strictly-lower entries are dealt to the
-  // 128 threads (E = ceil(N(N-1)/256) each, folded-rectangle indexing); all stay in registers for the whole
-  // factorisation. Column step j is a runtime loop (a fully unrolled factorisation made the kernel 600 KB of
-  // SASS and the sweep instruction-fetch bound) of ONE phase:
-  //   - read the reciprocal pivot inv_j and the un-scaled column j from `col` (published in step j-1),
-  //   - diagonal owners: d(t) -= L(t,j)^2 ; every lane then forms 1/sqrt of its diagonal, lane j+1 publishes
-  //     it as inv_{j+1}: the only serial chain of a column (sqrt + reciprocal, 139 clocks on B200,
-  //     tools/microbench_fp64.cu) overlaps with the off-diagonal updates below, which do not depend on it,
-  //   - off-diagonal: m(i,k) -= L(i,j) L(k,j) for k > j (branch-free, predicated), entries of column j+1 are
-  //     published un-scaled.
+  // Roles: the LAST warp of the CTA keeps the diagonal (lane l holds d(l), d(l+32), ...); the N(N-1)/2
+  // strictly-lower entries are dealt to the other TPB-32 threads (folded-rectangle indexing) and stay in
+  // registers for the whole factorisation. Column step j is a runtime loop (a fully unrolled factorisation
+  // made the kernel 600 KB of SASS and the sweep instruction-fetch bound) of ONE phase:
+  //   - pivot warp: d(t) -= L(t,j)^2 for t > j, then 1/sqrt(d(j+1)) -> inv_{j+1}: the serial chain of a
+  //     column (LDS + sqrt + reciprocal, ~200 clocks on B200, tools/microbench_fp64.cu) runs BESIDE
+  //   - the other warps: m(i,k) -= L(i,j) L(k,j) for k > j (branch-free), entries of column j+1 are
+  //     published un-scaled for the next step.
   // The factor is written once at the end: L(i,k) = m(i,k) inv_k. Per-entry update order is ascending j,
   // the oracle's order, and every product is the oracle's product, so the factor is bitwise the oracle's.
-  template <int N, int LD>
+  template <int N, int LD, int TPB>
   SMPC_DEV void chol_reg(double * M, double * col /* [2][N+2] */, double * invd, int * bad)
   {
     static_assert(N % 2 == 0, "folded-rectangle indexing assumes an even order");
-    constexpr int NO = N * (N - 1) / 2, E = (NO + 127) / 128, RW = N - 1, CS = N + 2;
-    SMPC_THREAD_ARRAY(m, E + 1)
+    constexpr int TW = TPB - 32; // threads that own off-diagonal entries
+    constexpr int NO = N * (N - 1) / 2, E = (NO + TW - 1) / TW, RW = N - 1, CS = N + 2;
+    constexpr int DS = (N + 31) / 32; // diagonal entries per pivot-warp lane
+    constexpr int NR = (E > DS) ? E : DS;
+    SMPC_THREAD_ARRAY(m, NR)
     SMPC_THREAD_IARRAY(ik, 2 * E)
     SMPC_PAR(tid)
     {
-      double * m = SMPC_THREAD_PTR(m, E + 1, tid);
+      double * m = SMPC_THREAD_PTR(m, NR, tid);
       int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
+      if (tid < TW)
+      {
 #pragma unroll
-      for (int q = 0; q < E; q++)
-      {
-        const int e = tid + SMPC_NT * q;
-        const int r = e / RW, c = e - r * RW;
-        // row r pairs with row N-1-r (r + N-1-r = N-1 entries); r = 0 is row N-1 alone
-        const int i = (r == 0) ? N - 1 : ((c < r) ? r : N - 1 - r);
-        const int k = (r == 0) ? c : ((c < r) ? c : c - r);
-        const bool valid = e < NO;
-        ik[2 * q] = valid ? i : 0; // a dead slot is (0,0): never above any column
-        ik[2 * q + 1] = valid ? k : 0;
-        m[q] = valid ? M[i * LD + k] : 0.0;
-        if (valid && k == 0)
-          col[i] = m[q];
+        for (int q = 0; q < E; q++)
+        {
+          const int e = tid + TW * q;
+          const int r = e / RW, c = e - r * RW;
+          // row r pairs with row N-1-r (r + N-1-r = N-1 entries); r = 0 is row N-1 alone
+          const int i = (r == 0) ? N - 1 : ((c < r) ? r : N - 1 - r);
+          const int k = (r == 0) ? c : ((c < r) ? c : c - r);
+          const bool valid = e < NO;
+          ik[2 * q] = valid ? i : 0; // a dead slot is (0,0): never above any column
+          ik[2 * q + 1] = valid ? k : 0;
+          m[q] = valid ? M[i * LD + k] : 0.0;
+          if (valid && k == 0)
+            col[i] = m[q];
+        }
       }
-      m[E] = (tid < N) ? M[tid * LD + tid] : 1.0;
-      if (tid == 0)
+      else
       {
-        const double d = m[E];
-        const double inv = 1.0 / sqrt(d);
-        col[N] = inv;
-        invd[0] = inv;
-        if (!(d > 0))
-          *bad = 1;
+        const int lane = tid - TW;
+#pragma unroll
+        for (int s = 0; s < DS; s++)
+        {
+          const int t = lane + 32 * s;
+          m[s] = (t < N) ? M[t * LD + t] : 1.0;
+        }
+        if (lane == 0)
+        {
+          const double d = m[0];
+          const double inv = 1.0 / sqrt(d);
+          col[N] = inv;
+          invd[0] = inv;
+          if (!(d > 0))
+            *bad = 1;
+        }
       }
     }
     SMPC_END
@@ -176,61 +189,78 @@ namespace smpc
     {
       SMPC_PAR(tid)
       {
-        double * m = SMPC_THREAD_PTR(m, E + 1, tid);
+        double * m = SMPC_THREAD_PTR(m, NR, tid);
         const int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
         const double * cj = col + (j & 1) * CS;
         double * cn = col + ((j + 1) & 1) * CS;
-        double ca[E], cb[E];
+        if (tid < TW)
+        {
+          double ca[E], cb[E];
 #pragma unroll
-        for (int q = 0; q < E; q++)
-        {
-          ca[q] = cj[ik[2 * q]];
-          cb[q] = cj[ik[2 * q + 1]];
+          for (int q = 0; q < E; q++)
+          {
+            ca[q] = cj[ik[2 * q]];
+            cb[q] = cj[ik[2 * q + 1]];
+          }
+          const double inv = cj[N];
+#pragma unroll
+          for (int q = 0; q < E; q++)
+          {
+            const int i = ik[2 * q], k = ik[2 * q + 1];
+            const double a = ca[q] * inv;
+            const double b = cb[q] * inv;
+            const double upd = fma(-a, b, m[q]);
+            if (k > j)
+              m[q] = upd;
+            if (k == j + 1)
+              cn[i] = upd;
+          }
         }
-        const double inv = cj[N];
+        else
         {
-          const double lt = cj[tid < N ? tid : 0] * inv;
-          const double dn = fma(-lt, lt, m[E]);
-          if (tid > j && tid < N)
-            m[E] = dn;
-          const double d = m[E];
-          const double invn = 1.0 / sqrt(d);
-          if (tid == j + 1 && tid < N)
+          const int lane = tid - TW;
+          const double inv = cj[N];
+          double dsel = 1.0;
+#pragma unroll
+          for (int s = 0; s < DS; s++)
+          {
+            const int t = lane + 32 * s;
+            const double lt = cj[t < N ? t : 0] * inv;
+            const double dn = fma(-lt, lt, m[s]);
+            if (t > j && t < N)
+              m[s] = dn;
+            if (t == j + 1)
+              dsel = m[s];
+          }
+          // lanes that do not hold d(j+1) work on 1.0; only the holder publishes
+          const double invn = 1.0 / sqrt(dsel);
+          if ((lane == ((j + 1) & 31)) && j + 1 < N)
           {
             cn[N] = invn;
             invd[j + 1] = invn;
-            if (!(d > 0))
+            if (!(dsel > 0))
               *bad = 1;
           }
-        }
-#pragma unroll
-        for (int q = 0; q < E; q++)
-        {
-          const int i = ik[2 * q], k = ik[2 * q + 1];
-          const double a = ca[q] * inv;
-          const double b = cb[q] * inv;
-          const double upd = fma(-a, b, m[q]);
-          if (k > j)
-            m[q] = upd;
-          if (k == j + 1)
-            cn[i] = upd;
         }
       }
       SMPC_END
     }
     SMPC_PAR(tid)
     {
-      const double * m = SMPC_THREAD_PTR(m, E + 1, tid);
+      const double * m = SMPC_THREAD_PTR(m, NR, tid);
       const int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
-#pragma unroll
-      for (int q = 0; q < E; q++)
+      if (tid < TW)
       {
-        const int i = ik[2 * q], k = ik[2 * q + 1];
-        if (i > k)
+#pragma unroll
+        for (int q = 0; q < E; q++)
         {
-          const double lik = m[q] * invd[k];
-          M[i * LD + k] = lik;
-          M[k * LD + i] = lik;
+          const int i = ik[2 * q], k = ik[2 * q + 1];
+          if (i > k)
+          {
+            const double lik = m[q] * invd[k];
+            M[i * LD + k] = lik;
+            M[k * LD + i] = lik;
+          }
         }
       }
     }
@@ -319,13 +349,15 @@ namespace smpc
     SMPC_END
   }
 
-  template <int NDX, int NU, int NC>
+  template <int NDX, int NU, int NC, int TPB>
   SMPC_DEV void riccati3_backward_inst(
     const KnotLayout & L, const SolLayout & SL, int N, const double * __restrict__ knots, double * __restrict__ sol,
     double mudyn, double mueq, double * sm, int * flag_out, double * P0out)
   {
     typedef Ric3<NDX, NU, NC> R;
     constexpr int LDP = R::LDP, NAB = R::NAB, NRY = R::NRY;
+    constexpr int TM = (TPB >= 256) ? 2 : 4; // register tile rows: smaller tiles when there are more threads to feed
+    static_assert(TPB == 128 || TPB == 256, "tile maps are written for 128 or 256 threads");
     double * KN = sm + R::oKN;
     double * PP = sm + R::oPP; // [NDX][LDP]: col 0 = p, cols 1.. = P
     double * Mb = sm + R::oM;
@@ -414,7 +446,7 @@ namespace smpc
       // ---- 1. [p~ | P~] = (I + mudyn P)^-1 [p | P], in place ----
       if (mudyn > 0)
       {
-        chol_reg<NDX, NDX>(Mb, colb, invp, bad);
+        chol_reg<NDX, NDX, TPB>(Mb, colb, invp, bad);
         sweep_cols<NDX, NDX, LDP, LDP, true, false>(Mb, invp, PP);
         sweep_cols<NDX, NDX, LDP, LDP, false, true>(Mb, invp, PP);
       }
@@ -430,17 +462,17 @@ namespace smpc
           else
             so[SL.oPt + a * NDX + (bb - 1)] = PP[e];
         }
-        constexpr int TR = NDX / 4, TCA = NDX / 6, TC = NAB / 6;
-        static_assert(TR * TC + NDX <= 128, "one tile per thread plus the w rows");
+        constexpr int TR = NDX / TM, TCA = NDX / 6, TC = NAB / 6;
+        static_assert(TR * TC + NDX <= TPB, "one tile per thread plus the w rows");
         if (tid < TR * TC)
         {
-          const int a0 = 4 * (tid / TC), tc = tid % TC;
+          const int a0 = TM * (tid / TC), tc = tid % TC;
           const bool inA = tc < TCA;
           const double * src = inA ? Ak + 6 * tc : Bk + 6 * (tc - TCA);
           const int lds = inA ? NDX : NU;
-          double c[4][6];
+          double c[TM][6];
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++)
               c[r][q] = 0.0;
@@ -452,7 +484,7 @@ namespace smpc
             ld2(src + k * lds + 2, bv[2], bv[3]);
             ld2(src + k * lds + 4, bv[4], bv[5]);
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int r = 0; r < TM; r++)
             {
               const double pk = PP[(a0 + r) * LDP + 1 + k];
 #pragma unroll
@@ -461,7 +493,7 @@ namespace smpc
             }
           }
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++)
               PAB[(a0 + r) * NAB + 6 * tc + q] = c[r][q];
@@ -480,14 +512,14 @@ namespace smpc
       // ---- 3. [Qh | Sh] = [Q | S] + A^T PAB ; Rh = R + B^T PB ; qh = q + A^T w ; rh = r + B^T w (in place) ----
       SMPC_PAR(tid)
       {
-        constexpr int TR = NDX / 4, TCA = NDX / 6, TC = NAB / 6, TRU = NU / 4, TCU = NU / 6;
-        static_assert(TR * TC + TRU * TCU <= 128, "one tile per thread");
+        constexpr int TR = NDX / TM, TCA = NDX / 6, TC = NAB / 6, TRU = NU / TM, TCU = NU / 6;
+        static_assert(TR * TC + TRU * TCU <= TPB, "one tile per thread");
         if (tid < TR * TC + TRU * TCU)
         {
           const bool isR = tid >= TR * TC;
           const int tt = isR ? tid - TR * TC : tid;
           // left operand: columns a0.. of A (Qh, Sh rows) or of B (Rh rows); right operand: columns b0.. of PAB
-          const int ar = isR ? 4 * (tt / TCU) : 4 * (tt / TC);
+          const int ar = isR ? TM * (tt / TCU) : TM * (tt / TC);
           const int tc = isR ? tt % TCU : tt % TC;
           const double * lhs = isR ? Bk + ar : Ak + ar;
           const int ldl = isR ? NU : NDX;
@@ -500,29 +532,30 @@ namespace smpc
             out = Qh + ar * NDX + 6 * tc, ldo = NDX;
           else
             out = Sh + ar * NU + 6 * (tc - TCA), ldo = NU;
-          double c[4][6];
+          double c[TM][6];
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++)
               c[r][q] = out[r * ldo + q];
 #pragma unroll 4
           for (int k = 0; k < NDX; k++)
           {
-            double av[4], bv[6];
-            ld2(lhs + k * ldl, av[0], av[1]);
-            ld2(lhs + k * ldl + 2, av[2], av[3]);
+            double av[TM], bv[6];
+#pragma unroll
+            for (int r = 0; r < TM; r += 2)
+              ld2(lhs + k * ldl + r, av[r], av[r + 1]);
             ld2(PAB + k * NAB + b0, bv[0], bv[1]);
             ld2(PAB + k * NAB + b0 + 2, bv[2], bv[3]);
             ld2(PAB + k * NAB + b0 + 4, bv[4], bv[5]);
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int r = 0; r < TM; r++)
 #pragma unroll
               for (int q = 0; q < 6; q++)
                 c[r][q] = fma(av[r], bv[q], c[r][q]);
           }
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++)
               out[r * ldo + q] = c[r][q];
@@ -541,7 +574,7 @@ namespace smpc
       }
       SMPC_END
       // ---- 4. KKT by block LDL^T ----
-      chol_reg<NU, NU>(Rh, colb, invr, bad);
+      chol_reg<NU, NU, TPB>(Rh, colb, invr, bad);
       SMPC_PAR(tid)
       for (int e = tid; e < NU * NRY; e += SMPC_NT)
       {
@@ -559,17 +592,17 @@ namespace smpc
       sweep_cols<NU, NU, NRY, NRY, true, false>(Rh, invr, YW);
       if (NC > 0)
       {
-        // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : four outputs at a time per thread
+        // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : QB outputs at a time per thread
         SMPC_PAR(tid)
         {
-          constexpr int NSG = NC * NC, NGG = NC * LDP, NOUT = NSG + NGG;
-          for (int e0 = tid; e0 < NOUT; e0 += 4 * SMPC_NT)
+          constexpr int NSG = NC * NC, NGG = NC * LDP, NOUT = NSG + NGG, QB = 5;
+          for (int e0 = tid; e0 < NOUT; e0 += QB * SMPC_NT)
           {
-            double acc[4];
-            int wi[4], yc[4];
-            bool live[4];
+            double acc[QB];
+            int wi[QB], yc[QB];
+            bool live[QB];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < QB; q++)
             {
               const int e = e0 + q * SMPC_NT;
               live[q] = e < NOUT;
@@ -595,7 +628,7 @@ namespace smpc
             for (int k = 0; k < NU; k++)
             {
 #pragma unroll
-              for (int q = 0; q < 4; q++)
+              for (int q = 0; q < QB; q++)
               {
                 const double wv = YW[k * NRY + wi[q]];
                 const double yv = YW[k * NRY + yc[q]];
@@ -604,7 +637,7 @@ namespace smpc
               }
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < QB; q++)
               if (live[q])
               {
                 const int e = e0 + q * SMPC_NT;
@@ -616,20 +649,20 @@ namespace smpc
           }
         }
         SMPC_END
-        chol_reg<NC, NC>(Sg, colb, invs, bad);
+        chol_reg<NC, NC, TPB>(Sg, colb, invs, bad);
         sweep_cols<NC, NC, LDP, LDP, true, false>(Sg, invs, G);
         sweep_cols<NC, NC, LDP, LDP, false, true>(Sg, invs, G);
         // Y <- Y + W G
         SMPC_PAR(tid)
         {
-          constexpr int NOUT = NU * LDP;
-          for (int e0 = tid; e0 < NOUT; e0 += 4 * SMPC_NT)
+          constexpr int NOUT = NU * LDP, QB = 4;
+          for (int e0 = tid; e0 < NOUT; e0 += QB * SMPC_NT)
           {
-            double acc[4];
-            int ra[4], cc[4];
-            bool live[4];
+            double acc[QB];
+            int ra[QB], cc[QB];
+            bool live[QB];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < QB; q++)
             {
               const int e = e0 + q * SMPC_NT;
               live[q] = e < NOUT;
@@ -640,11 +673,11 @@ namespace smpc
             for (int i = 0; i < NC; i++)
             {
 #pragma unroll
-              for (int q = 0; q < 4; q++)
+              for (int q = 0; q < QB; q++)
                 acc[q] = fma(YW[ra[q] * NRY + LDP + i], G[i * LDP + cc[q]], acc[q]);
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < QB; q++)
               if (live[q])
                 YW[ra[q] * NRY + cc[q]] = acc[q];
           }
@@ -675,17 +708,17 @@ namespace smpc
         }
       }
       SMPC_END
-      // ---- 5. [p | P] = [qh | Qh] + Sh [k | K] + C^T [z | Z] : 4x3 register tiles, p by the remaining threads ----
+      // ---- 5. [p | P] = [qh | Qh] + Sh [k | K] + C^T [z | Z] : TM x 3 register tiles, p by the remaining threads ----
       SMPC_PAR(tid)
       {
-        constexpr int TR = NDX / 4, TC = NDX / 3;
-        static_assert(TR * TC + (NDX + 1) / 2 <= 128, "one tile per thread plus the p rows");
+        constexpr int TR = NDX / TM, TC = NDX / 3, PR = TM / 2; // PR rows of p per leftover thread
+        static_assert(TR * TC + (NDX + PR - 1) / PR <= TPB, "one tile per thread plus the p rows");
         if (tid < TR * TC)
         {
-          const int a0 = 4 * (tid / TC), b0 = 3 * (tid % TC);
-          double c[4][3];
+          const int a0 = TM * (tid / TC), b0 = 3 * (tid % TC);
+          double c[TM][3];
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 3; q++)
               c[r][q] = Qh[(a0 + r) * NDX + b0 + q];
@@ -697,7 +730,7 @@ namespace smpc
             for (int q = 0; q < 3; q++)
               kv[q] = YW[k * NRY + 1 + b0 + q];
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int r = 0; r < TM; r++)
             {
               const double sv = Sh[(a0 + r) * NU + k];
 #pragma unroll
@@ -708,48 +741,57 @@ namespace smpc
 #pragma unroll 4
           for (int i = 0; i < NC; i++)
           {
-            double cv[4], zv[3];
-            ld2(Ck + i * NDX + a0, cv[0], cv[1]);
-            ld2(Ck + i * NDX + a0 + 2, cv[2], cv[3]);
+            double cv[TM], zv[3];
+#pragma unroll
+            for (int r = 0; r < TM; r += 2)
+              ld2(Ck + i * NDX + a0 + r, cv[r], cv[r + 1]);
 #pragma unroll
             for (int q = 0; q < 3; q++)
               zv[q] = G[i * LDP + 1 + b0 + q];
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int r = 0; r < TM; r++)
 #pragma unroll
               for (int q = 0; q < 3; q++)
                 c[r][q] = fma(cv[r], zv[q], c[r][q]);
           }
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 3; q++)
               PP[(a0 + r) * LDP + 1 + b0 + q] = c[r][q];
         }
         else
         {
-          // p: two rows per thread, two independent chains
-          const int a1 = 2 * (tid - TR * TC), a2 = a1 + 1;
+          // p: PR rows per thread, independent chains
+          const int a1 = PR * (tid - TR * TC);
           if (a1 < NDX)
           {
-            const bool two = a2 < NDX;
-            const int a2c = two ? a2 : a1;
-            double p1 = qh[a1], p2 = qh[a2c];
+            double pv[PR];
+            int ar[PR];
+#pragma unroll
+            for (int r = 0; r < PR; r++)
+            {
+              ar[r] = (a1 + r < NDX) ? a1 + r : a1;
+              pv[r] = qh[ar[r]];
+            }
             for (int k = 0; k < NU; k++)
             {
               const double kv = YW[k * NRY];
-              p1 = fma(Sh[a1 * NU + k], kv, p1);
-              p2 = fma(Sh[a2c * NU + k], kv, p2);
+#pragma unroll
+              for (int r = 0; r < PR; r++)
+                pv[r] = fma(Sh[ar[r] * NU + k], kv, pv[r]);
             }
             for (int i = 0; i < NC; i++)
             {
               const double zv = G[i * LDP];
-              p1 = fma(Ck[i * NDX + a1], zv, p1);
-              p2 = fma(Ck[i * NDX + a2c], zv, p2);
+#pragma unroll
+              for (int r = 0; r < PR; r++)
+                pv[r] = fma(Ck[i * NDX + ar[r]], zv, pv[r]);
             }
-            PP[a1 * LDP] = p1;
-            if (two)
-              PP[a2 * LDP] = p2;
+#pragma unroll
+            for (int r = 0; r < PR; r++)
+              if (a1 + r < NDX)
+                PP[(a1 + r) * LDP] = pv[r];
           }
         }
       }

@@ -269,8 +269,11 @@ namespace
       st.flags |= 1;
   }
 
+#ifndef SMPC_RIC3_TPB
+#define SMPC_RIC3_TPB 128
+#endif
   template <int NDX, int NU, int NC>
-  __global__ void __launch_bounds__(128, SMPC_RIC_MINB) k_riccati3(Arrays A)
+  __global__ void __launch_bounds__(SMPC_RIC3_TPB, SMPC_RIC_MINB) k_riccati3(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
     const int b = blockIdx.x;
@@ -280,7 +283,7 @@ namespace
       return;
     const size_t xb = (size_t)b * (d.N + 1);
     __shared__ int flag;
-    riccati3_backward_inst<NDX, NU, NC>(
+    riccati3_backward_inst<NDX, NU, NC, SMPC_RIC3_TPB>(
       A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
@@ -585,7 +588,7 @@ namespace
   template <int NDX, int NU, int NC>
   void launch_riccati3_impl(smpc_ctx * c)
   {
-    k_riccati3<NDX, NU, NC><<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
+    k_riccati3<NDX, NU, NC><<<c->A.dm.B, SMPC_RIC3_TPB, c->ric_smem, c->stream>>>(c->A);
   }
   template <int NDX, int NU, int NC>
   int setup_riccati3(smpc_ctx * c)

@@ -125,12 +125,12 @@ int emul_riccati3(
   if (ndx == 36 && nu == 24 && ncmax == 24)
   {
     std::vector<double> sm(Ric3<36, 24, 24>::SIZE + 8, 0.0);
-    riccati3_backward_inst<36, 24, 24>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+    riccati3_backward_inst<36, 24, 24, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
   }
   else if (ndx == 36 && nu == 24 && ncmax == 36)
   {
     std::vector<double> sm(Ric3<36, 24, 36>::SIZE + 8, 0.0);
-    riccati3_backward_inst<36, 24, 36>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+    riccati3_backward_inst<36, 24, 36, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
   }
   else
   {
