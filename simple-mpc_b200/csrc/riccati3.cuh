@@ -209,11 +209,10 @@ namespace smpc
             const int i = ik[2 * q], k = ik[2 * q + 1];
             const double a = ca[q] * inv;
             const double b = cb[q] * inv;
-            const double upd = fma(-a, b, m[q]);
             if (k > j)
-              m[q] = upd;
+              m[q] = fma(-a, b, m[q]); // predicated FMA: frozen once its column has been processed
             if (k == j + 1)
-              cn[i] = upd;
+              cn[i] = m[q];
           }
         }
         else
@@ -592,94 +591,164 @@ namespace smpc
       sweep_cols<NU, NU, NRY, NRY, true, false>(Rh, invr, YW);
       if (NC > 0)
       {
-        // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : QB outputs at a time per thread
+        // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : register tiles (4x3 on G, 4x4 blocks of the
+        // lower triangle of Sigma), one job list strided over the CTA
         SMPC_PAR(tid)
         {
-          constexpr int NSG = NC * NC, NGG = NC * LDP, NOUT = NSG + NGG, QB = 5;
-          for (int e0 = tid; e0 < NOUT; e0 += QB * SMPC_NT)
+          static_assert(NC % 4 == 0 && NDX % 3 == 0, "tile shapes");
+          constexpr int NB = NC / 4, GT = NB * (NDX / 3), GL = NB, ST = NB * (NB + 1) / 2, NJOBS = GT + GL + ST;
+          for (int job = tid; job < NJOBS; job += SMPC_NT)
           {
-            double acc[QB];
-            int wi[QB], yc[QB];
-            bool live[QB];
-#pragma unroll
-            for (int q = 0; q < QB; q++)
+            if (job < GT)
             {
-              const int e = e0 + q * SMPC_NT;
-              live[q] = e < NOUT;
-              wi[q] = 0, yc[q] = 0, acc[q] = 0.0;
-              if (live[q])
+              const int i0 = 4 * (job / (NDX / 3)), c0 = 3 * (job % (NDX / 3));
+              double acc[4][3];
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  acc[r][q] = (c0 + q == 0) ? dk[i0 + r] : Ck[(i0 + r) * NDX + (c0 + q - 1)];
+#pragma unroll 4
+              for (int k = 0; k < NU; k++)
               {
-                if (e < NSG)
-                {
-                  const int i = e / NC, j = e % NC;
-                  live[q] = j <= i;
-                  wi[q] = LDP + i, yc[q] = LDP + j;
-                  acc[q] = (i == j) ? mueq : 0.0;
-                }
-                else
-                {
-                  const int g = e - NSG;
-                  const int i = g / LDP, c = g % LDP;
-                  wi[q] = LDP + i, yc[q] = c;
-                  acc[q] = (c == 0) ? dk[i] : Ck[i * NDX + (c - 1)];
-                }
+                double wv[4], yv[3];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                  wv[r] = YW[k * NRY + LDP + i0 + r];
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  yv[q] = YW[k * NRY + c0 + q];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                  for (int q = 0; q < 3; q++)
+                    acc[r][q] = fma(-wv[r], yv[q], acc[r][q]);
               }
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  G[(i0 + r) * LDP + c0 + q] = acc[r][q];
             }
-            for (int k = 0; k < NU; k++)
+            else if (job < GT + GL)
             {
+              const int i0 = 4 * (job - GT);
+              double acc[4];
 #pragma unroll
-              for (int q = 0; q < QB; q++)
+              for (int r = 0; r < 4; r++)
+                acc[r] = Ck[(i0 + r) * NDX + (NDX - 1)];
+#pragma unroll 4
+              for (int k = 0; k < NU; k++)
               {
-                const double wv = YW[k * NRY + wi[q]];
-                const double yv = YW[k * NRY + yc[q]];
-                // Sigma accumulates +W W, G accumulates -W Y (the sign sits on the first operand as in the oracle)
-                acc[q] = (yc[q] >= LDP) ? fma(wv, yv, acc[q]) : fma(-wv, yv, acc[q]);
+                const double yv = YW[k * NRY + NDX];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                  acc[r] = fma(-YW[k * NRY + LDP + i0 + r], yv, acc[r]);
               }
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+                G[(i0 + r) * LDP + NDX] = acc[r];
             }
-#pragma unroll
-            for (int q = 0; q < QB; q++)
-              if (live[q])
+            else
+            {
+              int t = job - GT - GL, bi = 0;
+              while (t > bi)
               {
-                const int e = e0 + q * SMPC_NT;
-                if (e < NSG)
-                  Sg[e] = acc[q];
-                else
-                  G[e - NSG] = acc[q];
+                t -= bi + 1;
+                bi++;
               }
+              const int i0 = 4 * bi, j0 = 4 * t;
+              double acc[4][4];
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                  acc[r][q] = (i0 + r == j0 + q) ? mueq : 0.0;
+#pragma unroll 4
+              for (int k = 0; k < NU; k++)
+              {
+                double wi[4], wj[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                  wi[r] = YW[k * NRY + LDP + i0 + r];
+                  wj[r] = YW[k * NRY + LDP + j0 + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                  for (int q = 0; q < 4; q++)
+                    acc[r][q] = fma(wi[r], wj[q], acc[r][q]);
+              }
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                  if (j0 + q <= i0 + r)
+                    Sg[(i0 + r) * NC + j0 + q] = acc[r][q];
+            }
           }
         }
         SMPC_END
         chol_reg<NC, NC, TPB>(Sg, colb, invs, bad);
         sweep_cols<NC, NC, LDP, LDP, true, false>(Sg, invs, G);
         sweep_cols<NC, NC, LDP, LDP, false, true>(Sg, invs, G);
-        // Y <- Y + W G
+        // Y <- Y + W G : 4x3 register tiles, the last column by four-row strips
         SMPC_PAR(tid)
         {
-          constexpr int NOUT = NU * LDP, QB = 4;
-          for (int e0 = tid; e0 < NOUT; e0 += QB * SMPC_NT)
+          constexpr int NBU = NU / 4, YT = NBU * (NDX / 3), NJOBS = YT + NBU;
+          for (int job = tid; job < NJOBS; job += SMPC_NT)
           {
-            double acc[QB];
-            int ra[QB], cc[QB];
-            bool live[QB];
-#pragma unroll
-            for (int q = 0; q < QB; q++)
+            if (job < YT)
             {
-              const int e = e0 + q * SMPC_NT;
-              live[q] = e < NOUT;
-              ra[q] = live[q] ? e / LDP : 0;
-              cc[q] = live[q] ? e % LDP : 0;
-              acc[q] = YW[ra[q] * NRY + cc[q]];
+              const int a0 = 4 * (job / (NDX / 3)), c0 = 3 * (job % (NDX / 3));
+              double acc[4][3];
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  acc[r][q] = YW[(a0 + r) * NRY + c0 + q];
+#pragma unroll 4
+              for (int i = 0; i < NC; i++)
+              {
+                double wv[4], gv[3];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                  wv[r] = YW[(a0 + r) * NRY + LDP + i];
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  gv[q] = G[i * LDP + c0 + q];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                  for (int q = 0; q < 3; q++)
+                    acc[r][q] = fma(wv[r], gv[q], acc[r][q]);
+              }
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                  YW[(a0 + r) * NRY + c0 + q] = acc[r][q];
             }
-            for (int i = 0; i < NC; i++)
+            else
             {
+              const int a0 = 4 * (job - YT);
+              double acc[4];
 #pragma unroll
-              for (int q = 0; q < QB; q++)
-                acc[q] = fma(YW[ra[q] * NRY + LDP + i], G[i * LDP + cc[q]], acc[q]);
+              for (int r = 0; r < 4; r++)
+                acc[r] = YW[(a0 + r) * NRY + NDX];
+#pragma unroll 4
+              for (int i = 0; i < NC; i++)
+              {
+                const double gv = G[i * LDP + NDX];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                  acc[r] = fma(YW[(a0 + r) * NRY + LDP + i], gv, acc[r]);
+              }
+#pragma unroll
+              for (int r = 0; r < 4; r++)
+                YW[(a0 + r) * NRY + NDX] = acc[r];
             }
-#pragma unroll
-            for (int q = 0; q < QB; q++)
-              if (live[q])
-                YW[ra[q] * NRY + cc[q]] = acc[q];
           }
         }
         SMPC_END
