@@ -166,6 +166,7 @@ namespace smpc
       else
       {
         const int lane = tid - TW;
+        ik[0] = 0; // pivot lanes: "met a non-positive pivot"
 #pragma unroll
         for (int s = 0; s < DS; s++)
         {
@@ -190,7 +191,7 @@ namespace smpc
       SMPC_PAR(tid)
       {
         double * m = SMPC_THREAD_PTR(m, NR, tid);
-        const int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
+        int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
         const double * cj = col + (j & 1) * CS;
         double * cn = col + ((j + 1) & 1) * CS;
         if (tid < TW)
@@ -231,14 +232,15 @@ namespace smpc
             if (t == j + 1)
               dsel = m[s];
           }
-          // lanes that do not hold d(j+1) work on 1.0; only the holder publishes
+          // lanes that do not hold d(j+1) work on 1.0; only the holder publishes. A non-positive pivot is
+          // remembered in the lane (the holder of d(j+1) sees it) and reported once after the loop.
           const double invn = 1.0 / sqrt(dsel);
+          if (!(dsel > 0))
+            ik[0] = 1;
           if ((lane == ((j + 1) & 31)) && j + 1 < N)
           {
             cn[N] = invn;
             invd[j + 1] = invn;
-            if (!(dsel > 0))
-              *bad = 1;
           }
         }
       }
@@ -262,6 +264,8 @@ namespace smpc
           }
         }
       }
+      else if (ik[0])
+        *bad = 1;
     }
     SMPC_END
   }
