@@ -29,6 +29,7 @@ namespace smpc
     double w_cent[36], w_centder[36], w_frame[36];
     double w_com[9], w_lmom[9], w_amom[9], w_lacc[9], w_aacc[9];
     double qmin[SMPC_MAX_NV], qmax[SMPC_MAX_NV];
+    double wcone[17 * 6]; // wrench-cone rows A w <= 0 for 6-D contacts (mu, Lfoot, Wfoot)
   };
 
   // Dense LQ knot layout in HBM (offsets in doubles from the knot base), row-major blocks.

@@ -64,6 +64,21 @@ namespace smpc
     return true;
   }
 
+  // [UPSTREAM] aligator CentroidalWrenchConeResidual / MultibodyWrenchConeResidual: 17 rows A w <= 0 on
+  // w = [f; tau] for a rectangular foot of half-length L and half-width W: unilaterality, friction pyramid,
+  // centre-of-pressure box, yaw-torque bounds.
+  inline void build_wrench_cone(double mu, double L, double W, double * A)
+  {
+    const double s = (L + W) * mu;
+    const double rows[17][6] = {
+      {0, 0, -1, 0, 0, 0},     {-1, 0, -mu, 0, 0, 0},    {1, 0, -mu, 0, 0, 0},     {0, -1, -mu, 0, 0, 0},
+      {0, 1, -mu, 0, 0, 0},    {0, 0, -W, -1, 0, 0},     {0, 0, -W, 1, 0, 0},      {0, 0, -L, 0, -1, 0},
+      {0, 0, -L, 0, 1, 0},     {-W, -L, -s, mu, mu, -1}, {-W, L, -s, mu, -mu, -1}, {W, -L, -s, -mu, mu, -1},
+      {W, L, -s, -mu, -mu, -1}, {W, L, -s, mu, mu, 1},    {W, -L, -s, mu, -mu, 1},  {-W, L, -s, -mu, mu, 1},
+      {-W, -L, -s, -mu, -mu, 1}};
+    memcpy(A, rows, sizeof(rows));
+  }
+
   inline void build_dev_ocp(const smpc_model_desc & m, const smpc_ocp_desc & o, DevOcp & O)
   {
     memset(&O, 0, sizeof(O));
@@ -135,6 +150,7 @@ namespace smpc
       cp(O.w_aacc, o.w_angular_acc, 9, "w_angular_acc");
       O.ncmax = O.nk * ((O.fs == 6) ? 17 : 2);
       O.nct = 0;
+      build_wrench_cone(o.mu, o.Lfoot, o.Wfoot, O.wcone);
     }
     else
       throw std::runtime_error("ocp: full-dynamics problems have no CUDA kernels yet");

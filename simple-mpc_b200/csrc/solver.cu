@@ -11,6 +11,7 @@
 // There is NO CPU fallback: every entry point that computes fails with SMPC_ERR_CUDA if the
 // CUDA runtime does.
 #include "kino_knot.cuh"
+#include "centro_knot.cuh"
 #include "riccati.cuh"
 #include "riccati2.cuh"
 #include "riccati3.cuh"
@@ -106,18 +107,11 @@ namespace
     }
   }
 
-  template <class Cfg, bool TRIAL>
-  __global__ void __launch_bounds__(128) k_knots(Arrays A)
+  // global-memory view of knot (b, t) for the linearisation (TRIAL = false) or a linesearch trial
+  template <bool TRIAL>
+  __device__ __forceinline__ void make_knot_io(const Arrays & A, const InstState & st, int b, int t, KnotIO & io, int * nc_dummy)
   {
-    extern __shared__ __align__(16) double smem_raw[];
-    KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
     const Dims & d = A.dm;
-    const int b = blockIdx.x / (d.N + 1);
-    const int t = blockIdx.x % (d.N + 1);
-    const InstState & st = A.inst[b];
-    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
-      return;
-    KnotIO io;
     const size_t xb = (size_t)b * (d.N + 1);
     io.x = A.xs + (xb + t) * d.nx;
     io.u = (t < d.N) ? A.us + ((size_t)b * d.N + t) * d.nu : nullptr;
@@ -147,19 +141,54 @@ namespace
     io.mu = st.mu;
     io.preg = st.preg;
     io.knot = A.knots + (xb + t) * A.L.size;
-    io.nc_out = A.ncs + xb + t;
+    io.nc_out = TRIAL ? nc_dummy : A.ncs + xb + t;
     io.gx = A.gx + (xb + t) * d.ndx;
     io.gu = (t < d.N) ? A.gu + ((size_t)b * d.N + t) * d.nu : nullptr;
     io.lplus_n = (t < d.N) ? A.lplus + (xb + t + 1) * d.ndx : nullptr;
     io.xdot = (t < d.N) ? (TRIAL ? A.xdott : A.xdot) + ((size_t)b * d.N + t) * d.ndx : nullptr;
     io.sc = (TRIAL ? A.sct : A.sc) + xb + t;
+  }
+
+  // kinodynamics: one CTA (one warp by default) per knot
+  template <class Cfg, bool TRIAL>
+  __global__ void __launch_bounds__(128) k_knots(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
+    const Dims & d = A.dm;
+    const int b = blockIdx.x / (d.N + 1);
+    const int t = blockIdx.x % (d.N + 1);
+    const InstState & st = A.inst[b];
+    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
+      return;
+    KnotIO io;
     int nc_dummy;
-    if (TRIAL)
-      io.nc_out = &nc_dummy;
+    make_knot_io<TRIAL>(A, st, b, t, io, &nc_dummy);
     if (t < d.N)
       kino_stage_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, s);
     else
       kino_terminal_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, s);
+  }
+
+  // centroidal: one warp per knot
+  template <class Cfg, bool TRIAL>
+  __global__ void __launch_bounds__(32) k_knots_centro(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    CentroScratch<Cfg> & s = *reinterpret_cast<CentroScratch<Cfg> *>(smem_raw);
+    const Dims & d = A.dm;
+    const int b = blockIdx.x / (d.N + 1);
+    const int t = blockIdx.x % (d.N + 1);
+    const InstState & st = A.inst[b];
+    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
+      return;
+    KnotIO io;
+    int nc_dummy;
+    make_knot_io<TRIAL>(A, st, b, t, io, &nc_dummy);
+    if (t < d.N)
+      centro_stage_knot<Cfg, !TRIAL>(*A.ocp, A.L, io, s);
+    else
+      centro_terminal_knot<Cfg, !TRIAL>(*A.ocp, A.L, io, s);
   }
 
   // per-instance reductions and the ProxDDP control flow between linearisation and the Newton step
@@ -566,6 +595,27 @@ namespace
     return SMPC_OK;
   }
 
+  template <class Cfg>
+  void launch_knots_centro_impl(smpc_ctx * c, bool trial)
+  {
+    const Dims & d = c->A.dm;
+    const int grid = d.B * (d.N + 1);
+    if (trial)
+      k_knots_centro<Cfg, true><<<grid, 32, c->knot_smem, c->stream>>>(c->A);
+    else
+      k_knots_centro<Cfg, false><<<grid, 32, c->knot_smem, c->stream>>>(c->A);
+    c->launches++;
+  }
+  template <class Cfg>
+  int setup_knots_centro(smpc_ctx * c)
+  {
+    c->knot_smem = sizeof(CentroScratch<Cfg>);
+    CU(cudaFuncSetAttribute(k_knots_centro<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    CU(cudaFuncSetAttribute(k_knots_centro<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    c->launch_knots = &launch_knots_centro_impl<Cfg>;
+    return SMPC_OK;
+  }
+
   void launch_riccati_generic(smpc_ctx * c)
   {
     k_riccati<<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
@@ -758,8 +808,13 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   int rc = SMPC_ERR_UNSUPPORTED;
   if (O.kind == SMPC_OCP_KINODYNAMICS && model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3)
     rc = setup_knots<KinoCfg<13, 18, 4, 3>>(c);
+  else if (O.kind == SMPC_OCP_CENTROIDAL && O.nk == 2 && O.fs == 6)
+    rc = setup_knots_centro<CentroCfg<2, 6>>(c);
+  else if (O.kind == SMPC_OCP_CENTROIDAL && O.nk == 4 && O.fs == 3)
+    rc = setup_knots_centro<CentroCfg<4, 3>>(c);
   else
-    g_err = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics, 12-DoF quadruped, point feet)";
+    g_err = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics on a 12-DoF quadruped with point feet; "
+            "centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
   {
     delete c;

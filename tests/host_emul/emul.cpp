@@ -3,6 +3,7 @@
 // thread index) so that kernel LOGIC can be debugged against the oracle on the GPU-less development
 // box. The shipped library (libsmpc_cuda.so) never contains or calls this code.
 #include "../../simple-mpc_b200/csrc/kino_knot.cuh"
+#include "../../simple-mpc_b200/csrc/centro_knot.cuh"
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati2.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
@@ -14,6 +15,28 @@
 using namespace smpc;
 static std::string g_err;
 typedef KinoCfg<13, 18, 4, 3> Go2Cfg;
+
+// one centroidal knot (2 quad feet or 4 point feet); same argument meaning as emul_kino_knot
+template <class Cfg>
+static void centro_knot_any(const DevOcp & O, const KnotLayout & L, const KnotIO & io, bool terminal, bool derivs)
+{
+  auto s = std::make_unique<CentroScratch<Cfg>>();
+  memset(s.get(), 0, sizeof(*s));
+  if (terminal)
+  {
+    if (derivs)
+      centro_terminal_knot<Cfg, true>(O, L, io, *s);
+    else
+      centro_terminal_knot<Cfg, false>(O, L, io, *s);
+  }
+  else
+  {
+    if (derivs)
+      centro_stage_knot<Cfg, true>(O, L, io, *s);
+    else
+      centro_stage_knot<Cfg, false>(O, L, io, *s);
+  }
+}
 
 extern "C" {
 const char * emul_last_error() { return g_err.c_str(); }
@@ -60,6 +83,45 @@ int emul_kino_knot(
       else
         kino_stage_knot<Go2Cfg, false>(*M, *O, L, io, *s);
     }
+    memcpy(scalars, &sc, sizeof(sc));
+  }
+  catch (const std::exception & e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+
+int emul_centro_knot(
+  const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const smpc_terminal * term, int terminal,
+  int derivs, const double * x, const double * u, const double * xn, const double * vs, const double * prev_vs,
+  const double * lam_t, const double * lam_n, const double * prev_lam_n, double mu, double preg, double * knot, int * nc,
+  double * gx, double * gu, double * lplus, double * xdot, double * scalars /*8*/)
+{
+  try
+  {
+    auto O = std::make_unique<DevOcp>();
+    build_dev_ocp(*model, *ocp, *O);
+    KnotLayout L = make_knot_layout(O->ndx, O->nu, O->ncmax);
+    KnotIO io;
+    memset(&io, 0, sizeof(io));
+    io.x = x, io.u = u, io.xn = xn;
+    io.slot = slot, io.term = term;
+    io.vs = vs, io.prev_vs = prev_vs, io.lam_t = lam_t, io.lam_n = lam_n, io.prev_lam_n = prev_lam_n;
+    io.mu = mu, io.preg = preg;
+    io.knot = knot, io.nc_out = nc, io.gx = gx, io.gu = gu, io.lplus_n = lplus, io.xdot = xdot;
+    KnotScalars sc;
+    memset(&sc, 0, sizeof(sc));
+    io.sc = &sc;
+    if (O->kind != SMPC_OCP_CENTROIDAL)
+      throw std::runtime_error("emul_centro_knot: not a centroidal problem");
+    if (O->nk == 2 && O->fs == 6)
+      centro_knot_any<CentroCfg<2, 6>>(*O, L, io, terminal, derivs);
+    else if (O->nk == 4 && O->fs == 3)
+      centro_knot_any<CentroCfg<4, 3>>(*O, L, io, terminal, derivs);
+    else
+      throw std::runtime_error("emul_centro_knot: shape not instantiated");
     memcpy(scalars, &sc, sizeof(sc));
   }
   catch (const std::exception & e)

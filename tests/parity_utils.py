@@ -8,7 +8,8 @@ same C-ABI call sequence that MPC::MPC / MPC::iterate perform (reference src/mpc
 import ctypes as C
 import numpy as np
 from smpc_ctypes import (Slot, Terminal, SolveInfo, SolverOpts, dbl_p, go2_like_model, go2_kino_ocp, standing_slot,
-                         fk_numpy, x_ref_of, total_mass, load_oracle, load_cuda)
+                         fk_numpy, x_ref_of, total_mass, load_oracle, load_cuda, talos_like_model, talos_centroidal_ocp,
+                         centroidal_slot, com_numpy)
 
 
 def P(a):
@@ -159,17 +160,93 @@ class Go2Scenario:
             arr[i] = self.gait_slot(int(self.phase[i]) + tick)
         return arr
 
+    def disturb(self, x, tick):
+        """measured state = predicted next state + a small disturbance (same for both backends)"""
+        for i, r in enumerate(self.noise):
+            x[i, 19:] += r.normal(size=18) * (0.05 if tick == 0 else 0.01)
+            if tick == 0:
+                x[i, 7:19] += r.normal(size=12) * 0.02
+        return x
+
+
+class TalosCentroidalScenario:
+    """Config C2 of SURVEY.md §8d on the synthetic talos-like biped: CentroidalOCP, T = 100, 6-D contacts with
+    wrench cones, walk 20 DS / 80 SS(left stance) / 20 DS / 80 SS(right stance)
+    (reference examples/talos_centroidal.py:49-117). State = [com; h_lin; h_ang]."""
+
+    GAIT = [0b11] * 20 + [0b01] * 80 + [0b11] * 20 + [0b10] * 80  # left = bit0, right = bit1
+    CYCLE = 200
+
+    def __init__(self, batch, seed=0, T=100):
+        self.B, self.T = batch, T
+        self.model, self.limits = talos_like_model()
+        self.ocpb = talos_centroidal_ocp(self.model, T=T)
+        self.nx = self.ndx = 9
+        self.nu = 12
+        q = np.array(self.model.q_ref[: self.model.nq])
+        self.feet = fk_numpy(self.model, q)["feet"]
+        self.mass = total_mass(self.model)
+        self.xref = np.concatenate([com_numpy(self.model, q), np.zeros(6)])
+        # momentum references: velocity_base * mass for both parts (reference src/centroidal-dynamics.cpp:237-238)
+        self.xref_walk = self.xref.copy()
+        self.xref_walk[3] = 0.1 * self.mass
+        rngs = [np.random.default_rng([seed, i]) for i in range(batch)]
+        self.phase = np.array([int(r.integers(0, self.CYCLE)) for r in rngs])
+        self.noise = rngs
+
+    def gait_slot(self, k):
+        mask = self.GAIT[k % self.CYCLE]
+        nact = bin(mask).count("1")
+        return centroidal_slot(self.model, self.ocpb, self.feet, self.xref_walk, contact_mask=mask,
+                               force_z=self.mass * 9.81 / max(nact, 1))
+
+    def initial_slots(self):
+        # createProblem: all feet in contact, Identity foot poses (reference src/ocp-handler.cpp:111-126)
+        ident = [(np.eye(3), np.zeros(3)) for _ in range(2)]
+        s = centroidal_slot(self.model, self.ocpb, ident, self.xref)
+        return (Slot * (self.B * self.T))(*([s] * (self.B * self.T)))
+
+    def terminals(self):
+        t = Terminal()
+        t.x_ref[:9] = self.xref
+        return (Terminal * self.B)(*([t] * self.B))
+
+    def warmstart(self):
+        s0 = centroidal_slot(self.model, self.ocpb, self.feet, self.xref)
+        xs = np.tile(self.xref, (self.B, self.T + 1, 1)).copy()
+        us = np.tile(np.array(s0.u_ref[: self.nu]), (self.B, self.T, 1)).copy()
+        return xs, us
+
+    def x_start(self):
+        xs = np.tile(self.xref, (self.B, 1))
+        for i, r in enumerate(self.noise):
+            xs[i, 0:3] += r.normal(size=3) * 0.01
+            xs[i, 3:9] += r.normal(size=6) * 0.5
+        return xs
+
+    def tails(self, tick):
+        arr = (Slot * self.B)()
+        for i in range(self.B):
+            arr[i] = self.gait_slot(int(self.phase[i]) + tick)
+        return arr
+
+    def disturb(self, x, tick):
+        for i, r in enumerate(self.noise):
+            x[i, 0:3] += r.normal(size=3) * (0.005 if tick == 0 else 0.001)
+            x[i, 3:9] += r.normal(size=6) * (0.5 if tick == 0 else 0.1)
+        return x
+
 
 def relerr(a, b):
     den = max(np.abs(b).max(), 1e-300)
     return float(np.abs(a - b).max() / den)
 
 
-def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, **ocp_kw):
+def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario=None, **ocp_kw):
     """Drive the oracle and the CUDA library through the same constructor solve + `ticks` MPC ticks and return
     the worst normwise relative differences."""
     orc, cu = load_oracle(), load_cuda()
-    sc = Go2Scenario(batch, seed, **ocp_kw)
+    sc = (scenario or Go2Scenario)(batch, seed, **ocp_kw)
     opts_o, opts_c = SolverOpts(), SolverOpts()
     orc.orc_default_solver_opts(C.byref(opts_o))
     cu.smpc_default_solver_opts(C.byref(opts_c))
@@ -212,11 +289,7 @@ def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, **ocp_kw
         for tick in range(ticks):
             tails = sc.tails(tick)
             # measured state: the oracle's predicted next state plus a small disturbance (same for both backends)
-            x = xo[:, 1, :].copy()
-            for i, r in enumerate(sc.noise):
-                x[i, 19:] += r.normal(size=18) * (0.05 if tick == 0 else 0.01)
-                if tick == 0:
-                    x[i, 7:19] += r.normal(size=12) * 0.02
+            x = sc.disturb(xo[:, 1, :].copy(), tick)
             for b in (bo, bc):
                 b.cycle(tails)
                 b.shift()

@@ -180,6 +180,124 @@ def go2_like_model(orc=None):
     return m, limits
 
 
+def talos_like_model():
+    """22-DoF biped (reduced-Talos sizes: nq 29, nv 28): free-flyer + left leg 6 + right leg 6 + torso 2 +
+    left arm 4 + right arm 4, joint order as reference benchmark/talos.cpp:96-107; two QUAD feet (6-D contacts)
+    at the soles. SYNTHETIC: Talos-like link lengths and masses, not the real URDF (absent here)."""
+    m = ModelDesc()
+    I3 = np.eye(3).ravel()
+    X, Y, Z = [1, 0, 0], [0, 1, 0], [0, 0, 1]
+    joints = [(-1, None, [0, 0, 0], 15.36, [-0.05, 0.0, -0.05], [0.20, 0.12, 0.16])]  # root: pelvis
+
+    def add(par, ax, pl, mass, lev, inert):
+        joints.append((par, ax, pl, mass, lev, inert))
+        return len(joints) - 1
+
+    soles = []
+    for sy in (1, -1):  # left, right
+        j = add(0, Z, [-0.02, sy * 0.085, -0.27], 1.85, [0.02, sy * 0.01, 0.03], [0.004, 0.006, 0.005])      # hip yaw
+        j = add(j, X, [0, 0, 0], 1.98, [-0.01, sy * 0.005, 0.0], [0.004, 0.005, 0.004])                      # hip roll
+        j = add(j, Y, [0, 0, 0], 6.24, [0.003, sy * 0.033, -0.21], [0.15, 0.15, 0.02])                        # hip pitch (thigh)
+        j = add(j, Y, [0, 0, -0.38], 3.76, [0.011, sy * 0.003, -0.14], [0.06, 0.06, 0.008])                   # knee (shank)
+        j = add(j, Y, [0, 0, -0.325], 1.29, [-0.01, sy * 0.01, 0.0], [0.002, 0.003, 0.002])                   # ankle pitch
+        j = add(j, X, [0, 0, 0], 1.60, [-0.004, 0.0, -0.08], [0.004, 0.008, 0.008])                           # ankle roll (foot)
+        soles.append(j)
+    t1 = add(0, Z, [0, 0, 0.0722], 2.29, [0.0, 0.0, 0.03], [0.006, 0.006, 0.003])                              # torso yaw
+    t2 = add(t1, Y, [0, 0, 0], 17.55, [-0.04, 0.0, 0.19], [0.45, 0.35, 0.30])                                  # torso pitch
+    for sy in (1, -1):
+        j = add(t2, Z, [0, sy * 0.1575, 0.232], 1.43, [-0.007, sy * 0.12, -0.02], [0.005, 0.002, 0.005])      # shoulder 1
+        j = add(j, X, [0.006, sy * 0.1829, -0.03], 1.81, [0.02, sy * 0.003, -0.06], [0.008, 0.008, 0.003])    # shoulder 2
+        j = add(j, Z, [0, 0, 0], 1.54, [0.007, sy * 0.0003, -0.15], [0.012, 0.012, 0.002])                    # shoulder 3
+        j = add(j, Y, [0.02, 0, -0.273], 2.67, [-0.01, sy * 0.002, -0.12], [0.02, 0.02, 0.003])               # elbow (+ forearm, hand)
+    nj = len(joints)
+    m.njoints, m.nq, m.nv = nj, 7 + nj - 1, 6 + nj - 1
+    for i, (par, ax, pl, mass, lev, inert) in enumerate(joints):
+        m.parent[i] = par
+        m.jtype[i] = 0 if i == 0 else 1
+        m.idx_q[i] = 0 if i == 0 else 7 + (i - 1)
+        m.idx_v[i] = 0 if i == 0 else 6 + (i - 1)
+        if ax is not None:
+            m.axis[i][:] = ax
+        m.place_R[i][:] = I3
+        m.place_p[i][:] = pl
+        m.mass[i] = mass
+        m.lever[i][:] = lev
+        m.inertia[i][:] = np.diag(inert).ravel()
+    m.nfeet = 2
+    for f in range(2):
+        m.foot_joint[f] = soles[f]
+        m.foot_R[f][:] = I3
+        m.foot_p[f][:] = [0.0, 0.0, -0.107]
+    m.base_joint = 0
+    m.base_R[:] = I3
+    leg = [0.0, 0.0, -0.4, 0.8, -0.4, 0.0]
+    arm_l, arm_r = [0.25, 0.17, 0.0, -0.52], [-0.25, -0.17, 0.0, -0.52]
+    qj = leg + leg + [0.0, 0.006] + arm_l + arm_r
+    qref = np.array([0, 0, 1.0, 0, 0, 0, 1] + qj, float)
+    # put the soles on the ground at the reference ("half_sitting") configuration
+    m.q_ref[: m.nq] = qref
+    qref[2] -= fk_numpy(m, qref)["feet"][0][1][2]
+    m.q_ref[: m.nq] = qref
+    for f in range(2):
+        m.footref_joint[f] = 0
+    fp = fk_numpy(m, qref)
+    Mb = fp["base"]
+    for f in range(2):
+        Mf = fp["feet"][f]
+        m.footref_R[f][:] = (Mb[0].T @ Mf[0]).ravel()
+        m.footref_p[f][:] = Mb[0].T @ (Mf[1] - Mb[1])
+    nact = nj - 1
+    limits = dict(qmin=-np.ones(nact) * 2.5, qmax=np.ones(nact) * 2.5, umin=-np.ones(nact) * 300.0, umax=np.ones(nact) * 300.0)
+    return m, limits
+
+
+def com_numpy(m, q):
+    """centre of mass by plain numpy FK (test-side helper, independent of the C oracle)"""
+    fk = fk_numpy(m, q)
+    tot, acc = 0.0, np.zeros(3)
+    for i in range(m.njoints):
+        R, p = fk["joints"][i]
+        acc += m.mass[i] * (R @ np.array(m.lever[i][:]) + p)
+        tot += m.mass[i]
+    return acc / tot
+
+
+def talos_centroidal_ocp(m, T=100):
+    """Problem recipe of reference examples/talos_centroidal.py:49-77."""
+    w_u = np.diag(np.array(([0.001] * 3 + [0.1] * 3) * 2))
+    arrays = dict(w_u=np.ascontiguousarray(w_u), w_com=np.zeros((3, 3)), w_linear_mom=np.diag([0.01, 0.01, 100.0]),
+                  w_angular_mom=np.diag([0.1, 0.1, 1000.0]), w_linear_acc=0.01 * np.eye(3), w_angular_acc=0.01 * np.eye(3))
+    d = OcpDesc()
+    d.kind, d.horizon, d.force_size = CENT, T, 6
+    d.timestep = 0.01
+    d.gravity[:] = [0, 0, -9.81]
+    d.mu, d.Lfoot, d.Wfoot = 0.8, 0.1, 0.075
+    for k, v in arrays.items():
+        setattr(d, k, _p(v))
+    return OcpBundle(d, arrays)
+
+
+def centroidal_slot(m, ocp_bundle, foot_poses, x_ref9, contact_mask=None, force_z=None):
+    """Slot of a stage created by CentroidalOCP::createStage (reference src/centroidal-dynamics.cpp:39-106)."""
+    d = ocp_bundle.desc
+    nk, fs = m.nfeet, d.force_size
+    s = Slot()
+    if contact_mask is None:
+        contact_mask = (1 << nk) - 1
+    s.contact_mask, s.land_mask = contact_mask, 0
+    s.x_ref[:9] = x_ref9
+    nact = bin(contact_mask).count("1")
+    if force_z is None:
+        force_z = -total_mass(m) * d.gravity[2] / max(nact, 1)
+    for f in range(nk):
+        if contact_mask & (1 << f):
+            s.u_ref[fs * f + 2] = force_z
+        R, p = foot_poses[f]
+        s.foot_ref[f][:9] = np.asarray(R).ravel()
+        s.foot_ref[f][9:] = p
+    return s
+
+
 def fk_numpy(m, q):
     """Plain numpy forward kinematics (independent of the C oracle) used only to place the foot reference
     frames and as a known-answer check of the oracle's FK."""

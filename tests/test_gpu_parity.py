@@ -41,3 +41,9 @@ def test_kino_go2_cone_land_terminal():
     r = pu.run_parity(batch=2, ticks=4, seed=2, verbose=True, force_cone=True, land_cstr=True, terminal_constraint=True)
     assert r["iters_equal"], r
     assert r["us"] <= 1e-6 and r["K"] <= 1e-6, r
+
+
+def test_centroidal_talos_single_and_batch():
+    # config C2: CentroidalOCP, T = 100, 6-D contacts with wrench cones, walk 20/80/20/80
+    _check(pu.run_parity(batch=1, ticks=6, seed=0, verbose=True, scenario=pu.TalosCentroidalScenario))
+    _check(pu.run_parity(batch=6, ticks=25, seed=4, scenario=pu.TalosCentroidalScenario))
