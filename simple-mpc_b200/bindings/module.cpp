@@ -1,0 +1,256 @@
+// module.cpp — Python module `simple_mpc`: the surface of the reference bindings for the MPC::iterate path
+// (reference bindings/module.cpp:23-40, expose-robot-handler.cpp, expose-problem.cpp, expose-kinodynamics.cpp,
+// expose-fulldynamics.cpp, expose-centroidal.cpp, expose-mpc.cpp), written with pybind11 (boost.python and
+// eigenpy are not available here). Handlers and MPC take plain dicts with the reference's keys.
+#include "py-convert.hpp"
+
+namespace py = pybind11;
+using namespace simple_mpc;
+using namespace simple_mpc::python;
+
+namespace
+{
+  py::array_t<double> arr3(const Vector3d & v)
+  {
+    py::array_t<double> a(3);
+    std::copy(v.begin(), v.end(), a.mutable_data());
+    return a;
+  }
+  py::array_t<double> arr33(const std::array<double, 9> & R)
+  {
+    py::array_t<double> a({3, 3});
+    std::copy(R.begin(), R.end(), a.mutable_data());
+    return a;
+  }
+  template <class Handler>
+  void exposeHandlerCommon(py::class_<Handler, OCPHandler, std::shared_ptr<Handler>> & c)
+  {
+    (void)c;
+  }
+} // namespace
+
+PYBIND11_MODULE(simple_mpc, m)
+{
+  m.doc() = "simple-mpc on B200: the MPC::iterate -> ProxDDP path behind the reference's Python API";
+  m.attr("__version__") = "0.1.0+b200";
+
+  py::class_<SE3>(m, "SE3")
+    .def(py::init<>())
+    .def(py::init([](const MatrixXd & R, const VectorXd & p) {
+      if (R.rows() != 3 || R.cols() != 3 || p.size() != 3)
+        throw std::runtime_error("SE3(R, p): R must be 3x3 and p of size 3");
+      SE3 M;
+      std::copy(R.data(), R.data() + 9, M.R.begin());
+      std::copy(p.begin(), p.end(), M.p.begin());
+      return M;
+    }))
+    .def_static("Identity", &SE3::Identity)
+    .def_property(
+      "translation", [](const SE3 & M) { return arr3(M.p); }, [](SE3 & M, const VectorXd & p) { M.p = {{p.at(0), p.at(1), p.at(2)}}; })
+    .def_property(
+      "rotation", [](const SE3 & M) { return arr33(M.R); },
+      [](SE3 & M, const MatrixXd & R) {
+        if (R.rows() != 3 || R.cols() != 3)
+          throw std::runtime_error("rotation must be 3x3");
+        std::copy(R.data(), R.data() + 9, M.R.begin());
+      })
+    .def("inverse", &SE3::inverse)
+    .def("actInv", &SE3::actInv)
+    .def("__mul__", [](const SE3 & a, const SE3 & b) { return a * b; });
+
+  py::class_<Frame>(m, "Frame")
+    .def(py::init<const std::string &, int, const SE3 &>(), py::arg("name"), py::arg("parentJoint"), py::arg("placement"))
+    .def_readwrite("name", &Frame::name)
+    .def_readwrite("parentJoint", &Frame::parentJoint)
+    .def_readwrite("placement", &Frame::placement);
+
+  py::class_<Model>(m, "Model", "kinematic tree + frames (stand-in for pinocchio.Model)")
+    .def(py::init<>())
+    .def_readonly("nq", &Model::nq)
+    .def_readonly("nv", &Model::nv)
+    .def_property_readonly("njoints", &Model::njoints)
+    .def_readwrite("referenceConfigurations", &Model::referenceConfigurations)
+    .def_readwrite("lowerPositionLimit", &Model::lowerPositionLimit)
+    .def_readwrite("upperPositionLimit", &Model::upperPositionLimit)
+    .def_readwrite("effortLimit", &Model::effortLimit)
+    .def_readonly("frames", &Model::frames)
+    .def(
+      "addFreeFlyer",
+      [](Model & self, const std::string & name, double mass, const VectorXd & lever, const MatrixXd & inertia) {
+        std::array<double, 9> I;
+        std::copy(inertia.data(), inertia.data() + 9, I.begin());
+        return self.addFreeFlyer(name, mass, {{lever.at(0), lever.at(1), lever.at(2)}}, I);
+      })
+    .def(
+      "addRevoluteJoint",
+      [](Model & self, size_t parent, const std::string & name, const VectorXd & axis, const SE3 & placement, double mass, const VectorXd & lever,
+         const MatrixXd & inertia) {
+        std::array<double, 9> I;
+        std::copy(inertia.data(), inertia.data() + 9, I.begin());
+        return self.addRevoluteJoint(parent, name, {{axis.at(0), axis.at(1), axis.at(2)}}, placement, mass, {{lever.at(0), lever.at(1), lever.at(2)}}, I);
+      })
+    .def("addFrame", &Model::addFrame)
+    .def("existFrame", &Model::existFrame)
+    .def("getFrameId", &Model::getFrameId)
+    .def_static("BuildGo2Like", &Model::BuildGo2Like, "synthetic 12-DoF quadruped with Go2-like dimensions")
+    .def_static("BuildTalosLike", &Model::BuildTalosLike, "synthetic 22-DoF biped with reduced-Talos dimensions");
+
+  py::class_<Data>(m, "Data")
+    .def_property_readonly("com", [](const Data & d) { return std::vector<py::array_t<double>>{arr3(d.com[0])}; })
+    .def_property_readonly(
+      "hg",
+      [](const Data & d) {
+        VectorXd h(6);
+        for (size_t k = 0; k < 3; k++)
+          h[k] = d.hg.lin[k], h[3 + k] = d.hg.ang[k];
+        return h;
+      })
+    .def_readonly("oMf", &Data::oMf)
+    .def_readonly("oMi", &Data::oMi);
+
+  py::class_<RobotModelHandler>(m, "RobotModelHandler")
+    .def(py::init<const Model &, const std::string &, const std::string &>(), py::arg("model"), py::arg("reference_configuration_name"), py::arg("base_frame_name"))
+    .def("addPointFoot", &RobotModelHandler::addPointFoot)
+    .def(
+      "addQuadFoot",
+      [](RobotModelHandler & self, const std::string & foot, const std::string & parent, const MatrixXd & pts) {
+        if (pts.rows() != 4 || pts.cols() != 3)
+          throw std::runtime_error("contact points must be a 4x3 matrix");
+        RobotModelHandler::ContactPointsMatrix c;
+        std::copy(pts.data(), pts.data() + 12, c.begin());
+        return self.addQuadFoot(foot, parent, c);
+      })
+    .def("setFootReferencePlacement", &RobotModelHandler::setFootReferencePlacement)
+    .def("difference", &RobotModelHandler::difference)
+    .def("getBaseFrameName", &RobotModelHandler::getBaseFrameName)
+    .def("getBaseFrameId", &RobotModelHandler::getBaseFrameId)
+    .def("getReferenceState", &RobotModelHandler::getReferenceState)
+    .def("getFeetNb", &RobotModelHandler::getFeetNb)
+    .def("getFootNb", &RobotModelHandler::getFootNb)
+    .def("getFeetFrameIds", &RobotModelHandler::getFeetFrameIds)
+    .def("getFootFrameName", &RobotModelHandler::getFootFrameName)
+    .def("getFeetFrameNames", &RobotModelHandler::getFeetFrameNames)
+    .def("getFootFrameId", &RobotModelHandler::getFootFrameId)
+    .def("getFootRefFrameId", &RobotModelHandler::getFootRefFrameId)
+    .def("getMass", &RobotModelHandler::getMass)
+    .def("getModel", &RobotModelHandler::getModel, py::return_value_policy::reference_internal);
+
+  py::class_<RobotDataHandler, std::shared_ptr<RobotDataHandler>>(m, "RobotDataHandler")
+    .def(py::init<const RobotModelHandler &>(), py::arg("model_handler"))
+    .def("updateInternalData", py::overload_cast<const ConstVectorRef &, const bool>(&RobotDataHandler::updateInternalData))
+    .def("updateJacobiansMassMatrix", &RobotDataHandler::updateJacobiansMassMatrix)
+    .def("getFootRefPose", &RobotDataHandler::getFootRefPose)
+    .def("getFootPose", &RobotDataHandler::getFootPose)
+    .def("getBaseFramePose", &RobotDataHandler::getBaseFramePose)
+    .def("getModelHandler", &RobotDataHandler::getModelHandler, py::return_value_policy::reference_internal)
+    .def("getData", &RobotDataHandler::getData, py::return_value_policy::reference_internal)
+    .def("getCentroidalState", &RobotDataHandler::getCentroidalState)
+    .def("getState", &RobotDataHandler::getState);
+
+  py::class_<CostStack>(m, "CostStack").def_readonly("components", &CostStack::components_);
+  py::class_<StageModel, std::shared_ptr<StageModel>>(m, "StageModel")
+    .def_readonly("contact_states", &StageModel::contact_states)
+    .def_readonly("cost", &StageModel::cost_)
+    .def_readonly("constraint_names", &StageModel::constraint_names)
+    .def("numConstraints", &StageModel::numConstraints)
+    .def_property_readonly("contact_mask", [](const StageModel & s) { return s.slot.contact_mask; })
+    .def_property_readonly("land_mask", [](const StageModel & s) { return s.slot.land_mask; });
+  py::class_<TrajOptProblem>(m, "TrajOptProblem")
+    .def("numSteps", &TrajOptProblem::numSteps)
+    .def_readonly("stages", &TrajOptProblem::stages_)
+    .def_readonly("term_cost", &TrajOptProblem::term_cost_)
+    .def_readonly("term_cstrs", &TrajOptProblem::term_cstrs_)
+    .def_property("x0", &TrajOptProblem::getInitState, &TrajOptProblem::setInitState);
+
+  py::class_<OCPHandler, std::shared_ptr<OCPHandler>>(m, "OCPHandler")
+    .def("createProblem", &OCPHandler::createProblem, py::arg("x0"), py::arg("horizon"), py::arg("force_size"), py::arg("gravity"), py::arg("terminal_constraint"))
+    .def("createTerminalConstraint", [](OCPHandler & o, const VectorXd & c) { o.createTerminalConstraint(toVec3(py::cast(c))); })
+    .def("updateTerminalConstraint", [](OCPHandler & o, const VectorXd & c) { o.updateTerminalConstraint(toVec3(py::cast(c))); })
+    .def("setReferencePose", &OCPHandler::setReferencePose)
+    .def("setReferencePoses", &OCPHandler::setReferencePoses)
+    .def("setTerminalReferencePose", &OCPHandler::setTerminalReferencePose)
+    .def("getReferencePose", &OCPHandler::getReferencePose)
+    .def("setReferenceForces", &OCPHandler::setReferenceForces)
+    .def("setReferenceForce", &OCPHandler::setReferenceForce)
+    .def("getReferenceForce", &OCPHandler::getReferenceForce)
+    .def("setVelocityBase", &OCPHandler::setVelocityBase)
+    .def("getVelocityBase", &OCPHandler::getVelocityBase)
+    .def("setPoseBase", &OCPHandler::setPoseBase)
+    .def("getPoseBase", &OCPHandler::getPoseBase)
+    .def("setReferenceState", &OCPHandler::setReferenceState)
+    .def("getReferenceState", &OCPHandler::getReferenceState)
+    .def("getProblemState", &OCPHandler::getProblemState)
+    .def("getContactSupport", &OCPHandler::getContactSupport)
+    .def("getContactState", &OCPHandler::getContactState)
+    .def("setReferenceControl", &OCPHandler::setReferenceControl)
+    .def("getReferenceControl", &OCPHandler::getReferenceControl)
+    .def("getCostNumber", &OCPHandler::getCostNumber)
+    .def("getSize", &OCPHandler::getSize)
+    .def("getNu", &OCPHandler::getNu)
+    .def("getModelHandler", &OCPHandler::getModelHandler, py::return_value_policy::reference_internal)
+    .def("getProblem", py::overload_cast<>(&OCPHandler::getProblem), py::return_value_policy::reference_internal)
+    .def(
+      "createStage",
+      [](OCPHandler & o, const std::map<std::string, bool> & phase, const std::map<std::string, SE3> & pose,
+         const std::map<std::string, VectorXd> & force, const std::map<std::string, bool> & land) { return o.createStage(phase, pose, force, land); },
+      py::arg("contact_map"), py::arg("contact_pose"), py::arg("force_refs"), py::arg("land_constraint"));
+
+  py::class_<KinodynamicsOCP, OCPHandler, std::shared_ptr<KinodynamicsOCP>>(m, "KinodynamicsOCP")
+    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<KinodynamicsOCP>(kinoSettingsFromDict(s), h); }),
+         py::arg("settings"), py::arg("model_handler"))
+    .def("getSettings", [](KinodynamicsOCP & o) { return kinoSettingsToDict(o.getSettings()); });
+  py::class_<FullDynamicsOCP, OCPHandler, std::shared_ptr<FullDynamicsOCP>>(m, "FullDynamicsOCP")
+    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<FullDynamicsOCP>(fullSettingsFromDict(s), h); }),
+         py::arg("settings"), py::arg("model_handler"))
+    .def("getSettings", [](FullDynamicsOCP & o) { return fullSettingsToDict(o.getSettings()); });
+  py::class_<CentroidalOCP, OCPHandler, std::shared_ptr<CentroidalOCP>>(m, "CentroidalOCP")
+    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<CentroidalOCP>(centroidalSettingsFromDict(s), h); }),
+         py::arg("settings"), py::arg("model_handler"))
+    .def("getSettings", [](CentroidalOCP & o) { return centroidalSettingsToDict(o.getSettings()); });
+
+  py::class_<Results>(m, "Results")
+    .def_readonly("xs", &Results::xs)
+    .def_readonly("us", &Results::us)
+    .def_readonly("num_iters", &Results::num_iters)
+    .def_readonly("al_iter", &Results::al_iter)
+    .def_readonly("conv", &Results::conv)
+    .def_readonly("prim_infeas", &Results::prim_infeas)
+    .def_readonly("dual_infeas", &Results::dual_infeas)
+    .def_readonly("traj_cost", &Results::traj_cost_)
+    .def_readonly("merit_value", &Results::merit_value_)
+    .def("controlFeedbacks", &Results::getCtrlFeedbacks)
+    .def("controlFeedforwards", &Results::getCtrlFeedforwards);
+  py::class_<SolverProxDDP>(m, "SolverProxDDP")
+    .def_readwrite("max_iters", &SolverProxDDP::max_iters)
+    .def_readwrite("target_tol", &SolverProxDDP::target_tol_)
+    .def_readwrite("mu_init", &SolverProxDDP::mu_init)
+    .def_readonly("results", &SolverProxDDP::results_);
+
+  py::class_<MPC>(m, "MPC")
+    .def(py::init([](const py::dict & s, std::shared_ptr<OCPHandler> ocp) { return std::make_unique<MPC>(mpcSettingsFromDict(s), ocp); }),
+         py::arg("settings"), py::arg("problem"))
+    .def("getSettings", [](MPC & self) { return mpcSettingsToDict(self.settings_); })
+    .def("generateCycleHorizon", &MPC::generateCycleHorizon, py::arg("contact_states"))
+    .def("iterate", &MPC::iterate, py::arg("x"))
+    .def("setReferencePose", &MPC::setReferencePose)
+    .def("getReferencePose", &MPC::getReferencePose)
+    .def("setTerminalReferencePose", &MPC::setTerminalReferencePose)
+    .def_readwrite("velocity_base", &MPC::velocity_base_)
+    .def_readwrite("x_reference", &MPC::x_reference_)
+    .def_readonly("ocp_handler", &MPC::ocp_handler_)
+    .def("switchToWalk", &MPC::switchToWalk)
+    .def("switchToStand", &MPC::switchToStand)
+    .def("getFootTakeoffCycle", &MPC::getFootTakeoffCycle)
+    .def("getFootLandCycle", &MPC::getFootLandCycle)
+    .def("getStateDerivative", &MPC::getStateDerivative)
+    .def("getContactForces", &MPC::getContactForces)
+    .def("getCyclingContactState", &MPC::getCyclingContactState)
+    .def("getModelHandler", &MPC::getModelHandler, py::return_value_policy::reference_internal)
+    .def("getDataHandler", &MPC::getDataHandler, py::return_value_policy::reference_internal)
+    .def("getTrajOptProblem", &MPC::getTrajOptProblem, py::return_value_policy::reference_internal)
+    .def("getCycleHorizon", &MPC::getCycleHorizon, py::return_value_policy::reference_internal)
+    .def_property_readonly("solver", [](MPC & self) { return self.solver_.get(); }, py::return_value_policy::reference_internal)
+    .def_readonly("xs", &MPC::xs_)
+    .def_readonly("us", &MPC::us_)
+    .def_readonly("Ks", &MPC::Ks_);
+}

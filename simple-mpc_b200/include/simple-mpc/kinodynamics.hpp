@@ -1,0 +1,61 @@
+///////////////////////////////////////////////////////////////////////////////
+// kinodynamics.hpp — KinodynamicsOCP with the reference's interface
+// (reference include/simple-mpc/kinodynamics.hpp:24-106, src/kinodynamics.cpp).
+// State x = [q; v], control u = [f_0 .. f_{nk-1}; joint accelerations].
+///////////////////////////////////////////////////////////////////////////////
+#pragma once
+#include "simple-mpc/ocp-handler.hpp"
+
+namespace simple_mpc
+{
+
+  struct KinodynamicsSettings
+  {
+    double timestep;
+    MatrixXd w_x, w_u, w_frame, w_cent, w_centder;
+    VectorXd qmin, qmax;
+    Vector3d gravity;
+    double mu, Lfoot, Wfoot;
+    int force_size;
+    bool kinematics_limits, force_cone, land_cstr;
+  };
+
+  class KinodynamicsOCP : public OCPHandler
+  {
+    using Base = OCPHandler;
+
+  public:
+    explicit KinodynamicsOCP(const KinodynamicsSettings & settings, const RobotModelHandler & model_handler);
+    virtual ~KinodynamicsOCP() {}
+
+    StageModel createStage(
+      const std::map<std::string, bool> & contact_phase, const std::map<std::string, SE3> & contact_pose,
+      const std::map<std::string, VectorXd> & contact_force, const std::map<std::string, bool> & land_constraint) override;
+    CostStack createTerminalCost() override;
+    void createTerminalConstraint(const Vector3d & com_ref) override;
+    void updateTerminalConstraint(const Vector3d & com_ref) override;
+
+    void setReferencePose(const std::size_t t, const std::string & ee_name, const SE3 & pose_ref) override;
+    void setReferencePoses(const std::size_t i, const std::map<std::string, SE3> & pose_refs) override;
+    void setTerminalReferencePose(const std::string & ee_name, const SE3 & pose_ref) override;
+    void setReferenceForces(const std::size_t i, const std::map<std::string, VectorXd> & force_refs) override;
+    void setReferenceForce(const std::size_t i, const std::string & ee_name, const ConstVectorRef & force_ref) override;
+    const VectorXd getReferenceForce(const std::size_t i, const std::string & cost_name) override;
+    const SE3 getReferencePose(const std::size_t i, const std::string & cost_name) override;
+    const VectorXd getVelocityBase(const std::size_t t) override;
+    const VectorXd getPoseBase(const std::size_t t) override;
+    void setPoseBase(const std::size_t t, const ConstVectorRef & pose_base) override;
+    void setVelocityBase(const std::size_t t, const ConstVectorRef & velocity_base) override;
+    const VectorXd getProblemState(const RobotDataHandler & data_handler) override;
+    void setReferenceState(const std::size_t t, const ConstVectorRef & x_ref) override;
+    const VectorXd getReferenceState(const std::size_t t) override;
+
+    void computeControlFromForces(const std::map<std::string, VectorXd> & force_refs);
+    KinodynamicsSettings getSettings() { return settings_; }
+    smpc_ocp_desc toOcpDesc() const override;
+
+  protected:
+    KinodynamicsSettings settings_;
+  };
+
+} // namespace simple_mpc

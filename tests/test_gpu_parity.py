@@ -47,3 +47,60 @@ def test_centroidal_talos_single_and_batch():
     # config C2: CentroidalOCP, T = 100, 6-D contacts with wrench cones, walk 20/80/20/80
     _check(pu.run_parity(batch=1, ticks=6, seed=0, verbose=True, scenario=pu.TalosCentroidalScenario))
     _check(pu.run_parity(batch=6, ticks=25, seed=4, scenario=pu.TalosCentroidalScenario))
+
+
+def test_host_api_mpc_cuda_vs_oracle_go2_kinodynamics():
+    """The reference-facing Python API end to end: simple_mpc.MPC (CUDA) and the same host driver bound to the CPU
+    oracle walk the go2-like robot through the constructor solve and 30 ticks of a trot; the measured state fed
+    to both is the oracle's prediction, so every tick compares one solve on identical inputs."""
+    import numpy as np
+    import host_api_utils as hu
+    sm, hooks = hu.import_simple_mpc(), hu.import_hooks()
+    mh = hu.go2_handler(sm)
+    mpcs = []
+    for make in (lambda c, o: sm.MPC(c, o), lambda c, o: hooks.make_oracle_mpc(c, o, hu.LIBORC)):
+        ocp, _ = hu.go2_kino_problem(sm, mh, T=50)
+        mpcs.append(make(hu.go2_mpc_conf(mh), ocp))
+    cu, orc = mpcs
+    for m in mpcs:
+        m.generateCycleHorizon(hu.go2_trot())
+        m.switchToWalk(np.array([0.2, 0, 0, 0, 0, 0.1]))
+    x = mh.getReferenceState()
+    worst = dict(xs=0.0, us=0.0, K=0.0)
+    for k in range(31):
+        if k > 0:
+            for m in mpcs:
+                m.iterate(x)
+        worst["xs"] = max(worst["xs"], pu.relerr(np.array(cu.xs), np.array(orc.xs)))
+        worst["us"] = max(worst["us"], pu.relerr(np.array(cu.us), np.array(orc.us)))
+        worst["K"] = max(worst["K"], max(pu.relerr(cu.Ks[t], orc.Ks[t]) for t in range(50)))
+        assert cu.solver.results.num_iters == orc.solver.results.num_iters
+        x = orc.xs[1]
+    assert [cu.getFootLandCycle(n) for n in mh.getFeetFrameNames()] == [orc.getFootLandCycle(n) for n in mh.getFeetFrameNames()]
+    assert pu.relerr(cu.getStateDerivative(0), orc.getStateDerivative(0)) <= 1e-7
+    assert worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
+
+
+def test_host_api_mpc_cuda_vs_oracle_talos_centroidal():
+    import numpy as np
+    import host_api_utils as hu
+    sm, hooks = hu.import_simple_mpc(), hu.import_hooks()
+    mh = hu.talos_handler(sm)
+    mpcs = []
+    for make in (lambda c, o: sm.MPC(c, o), lambda c, o: hooks.make_oracle_mpc(c, o, hu.LIBORC)):
+        ocp, _ = hu.talos_centroidal_problem(sm, mh, T=100)
+        mpcs.append(make(hu.talos_mpc_conf(mh), ocp))
+    cu, orc = mpcs
+    for m in mpcs:
+        m.generateCycleHorizon(hu.talos_walk(20, 80))
+        m.switchToWalk(np.array([0.1, 0, 0, 0, 0, 0]))
+    x = mh.getReferenceState()
+    worst = dict(xs=0.0, us=0.0, K=0.0)
+    for k in range(40):
+        x[19] = 0.05  # the measured multibody state is reduced to the centroidal state by getProblemState
+        for m in mpcs:
+            m.iterate(x)
+        worst["xs"] = max(worst["xs"], pu.relerr(np.array(cu.xs), np.array(orc.xs)))
+        worst["us"] = max(worst["us"], pu.relerr(np.array(cu.us), np.array(orc.us)))
+        worst["K"] = max(worst["K"], max(pu.relerr(cu.Ks[t], orc.Ks[t]) for t in range(100)))
+    assert worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
