@@ -485,6 +485,34 @@ int orc_terminal_eval(
   ORC_CATCH
 }
 
+// Rigid-contact forward dynamics (orc_full.hpp) exposed for the finite-difference tests. Outputs may be NULL.
+int orc_full_dynamics(
+  const smpc_model_desc * model, const double * q, const double * v, const double * tau, unsigned mask, const double * gravity,
+  const double * Kp, const double * Kd, int derivs, double * a, double * lam, double * da_dq, double * da_dv, double * da_dtau,
+  double * dl_dq, double * dl_dv, double * dl_dtau)
+{
+  ORC_TRY
+  Model m(*model);
+  FullDyn fd;
+  full_dynamics(m, q, v, tau, mask, gravity, Kp, Kd, derivs != 0, fd);
+  auto cp = [](double * dst, const std::vector<double> & vv) {
+    if (dst && !vv.empty())
+      memcpy(dst, vv.data(), vv.size() * sizeof(double));
+  };
+  cp(a, fd.a);
+  cp(lam, fd.lam);
+  if (derivs)
+  {
+    cp(da_dq, fd.da_dq.d);
+    cp(da_dv, fd.da_dv.d);
+    cp(da_dtau, fd.da_dtau.d);
+    cp(dl_dq, fd.dl_dq.d);
+    cp(dl_dv, fd.dl_dv.d);
+    cp(dl_dtau, fd.dl_dtau.d);
+  }
+  ORC_CATCH
+}
+
 // x (+) dx and x1 (-) x0 of the OCP's state space
 int orc_state_integrate(const smpc_model_desc * model, const smpc_ocp_desc * ocp, const double * x, const double * dx, double * xo)
 {

@@ -12,6 +12,7 @@
 //   definition.
 #pragma once
 #include "orc_rbd.hpp"
+#include "orc_full.hpp"
 #include <stdexcept>
 #include <string>
 
@@ -129,6 +130,22 @@ namespace orc
         for (int f = 0; f < nk; f++)
           if (s.contact_mask & (1u << f))
             nc += (fs == 6) ? 17 : 2;
+      }
+      else
+      {
+        // reference src/fulldynamics.cpp:145-211 (point feet)
+        if (ocp.torque_limits)
+          nc += model.nv - 6;
+        if (ocp.kinematics_limits)
+          nc += model.nv - 6;
+        for (int f = 0; f < nk; f++)
+          if (s.contact_mask & (1u << f))
+          {
+            if (ocp.force_cone)
+              nc += 5;
+            if (ocp.land_cstr && (s.land_mask & (1u << f)))
+              nc += 4;
+          }
       }
       return nc;
     }
@@ -753,6 +770,291 @@ namespace orc
       throw std::runtime_error("kino_stage_eval: constraint row count mismatch");
   }
 
+  // ---------------------------------------------------------------------------------------------
+  // Full-dynamics stage (reference src/fulldynamics.cpp:78-214), point feet (force_size = 3)
+  //   u = tau_joint (nv-6), tau = [0; u] (:35-37); a, lam = rigid-contact forward dynamics (orc_full.hpp)
+  //   semi-implicit Euler (:140)
+  // Costs (:88-137): state, control (target u_ref = 0), centroidal momentum, foot translation per foot,
+  //   contact-force lam_f - f_ref per STANCE foot.
+  // Constraint rows, in the reference's insertion order (:145-211):
+  //   [torque box on u] [joint-limit box on q_joints] then per foot IN CONTACT:
+  //   [friction pyramid A lam_f <= 0, 5 rows: aligator MultibodyFrictionConeResidual [UPSTREAM]]
+  //   [on a landing edge: LOCAL_WORLD_ALIGNED foot velocity (3 rows) = 0 and z-height = ref].
+  // ---------------------------------------------------------------------------------------------
+  inline void friction_pyramid(double mu, double * A /*5x3*/)
+  {
+    const double rows[5][3] = {{0, 0, -1}, {-1, 0, -mu}, {1, 0, -mu}, {0, -1, -mu}, {0, 1, -mu}};
+    memcpy(A, rows, sizeof(rows));
+  }
+  inline void full_stage_eval(const Problem & P, const smpc_slot & s, const double * x, const double * u, bool derivs, StageEval & o)
+  {
+    const Model & m = P.model;
+    const int nv = m.nv, nq = m.nq, ndx = P.ndx, nu = P.nu, nk = P.nk, fs = P.fs;
+    const int nj = nv - 6;
+    const double dt = P.ocp.timestep;
+    if (fs != 3)
+      throw std::runtime_error("oracle: full dynamics with 6-D contacts is not restated");
+    const double * q = x;
+    const double * v = x + nq;
+    alloc_eval(P, P.stage_nc(s), derivs, o);
+    Vec tau(nv, 0.0);
+    for (int j = 0; j < nj; j++)
+      tau[6 + j] = u[j];
+    FullDyn fd;
+    full_dynamics(m, q, v, tau.data(), s.contact_mask, P.ocp.gravity, P.ocp.Kp_correction, P.ocp.Kd_correction, derivs, fd);
+    const Kin & k = fd.k;
+    const Vec & a = fd.a;
+    for (int i = 0; i < nv; i++)
+    {
+      o.xdot[i] = v[i];
+      o.xdot[nv + i] = a[i];
+    }
+    Vec vn(nv), dq(nv);
+    for (int i = 0; i < nv; i++)
+    {
+      vn[i] = v[i] + dt * a[i];
+      dq[i] = dt * vn[i];
+    }
+    integrate_q(m, q, dq.data(), o.xnext.data());
+    for (int i = 0; i < nv; i++)
+      o.xnext[nq + i] = vn[i];
+
+    std::vector<Mat> Jp(nk);
+    if (derivs)
+    {
+      for (int f = 0; f < nk; f++)
+      {
+        Jp[f].resize(3, nv);
+        for (int j = 0; j < nv; j++)
+        {
+          double c3[3];
+          point_jac_col(m, k, m.d.foot_joint[f], k.oMf[f].p, j, c3);
+          for (int r = 0; r < 3; r++)
+            Jp[f](r, j) = c3[r];
+        }
+      }
+      double Jq6[36], Jv6[36];
+      {
+        SE3 E = exp6(dq.data());
+        se3_actinv_matrix(E, Jq6);
+        Jexp6(dq.data(), Jv6);
+      }
+      Mat dvn_dx(nv, ndx), dvn_du(nv, nu);
+      for (int r = 0; r < nv; r++)
+      {
+        for (int j = 0; j < nv; j++)
+        {
+          dvn_dx(r, j) = dt * fd.da_dq(r, j);
+          dvn_dx(r, nv + j) = dt * fd.da_dv(r, j);
+        }
+        dvn_dx(r, nv + r) += 1.0;
+        for (int j = 0; j < nu; j++)
+          dvn_du(r, j) = dt * fd.da_dtau(r, 6 + j);
+      }
+      for (int i = 0; i < nv; i++)
+      {
+        for (int j = 0; j < ndx; j++)
+        {
+          o.A(nv + i, j) = dvn_dx(i, j);
+          double sacc = 0;
+          if (i < 6)
+            for (int c = 0; c < 6; c++)
+              sacc += Jv6[6 * i + c] * dvn_dx(c, j);
+          else
+            sacc = dvn_dx(i, j);
+          o.A(i, j) = dt * sacc;
+        }
+        for (int j = 0; j < nu; j++)
+        {
+          o.B(nv + i, j) = dvn_du(i, j);
+          double sacc = 0;
+          if (i < 6)
+            for (int c = 0; c < 6; c++)
+              sacc += Jv6[6 * i + c] * dvn_du(c, j);
+          else
+            sacc = dvn_du(i, j);
+          o.B(i, j) = dt * sacc;
+        }
+      }
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++)
+          o.A(i, j) += Jq6[6 * i + j];
+      for (int i = 6; i < nv; i++)
+        o.A(i, i) += 1.0;
+    }
+
+    // ---------------- costs ----------------
+    {
+      Vec r;
+      Mat J;
+      state_error(P, x, s.x_ref, r, derivs ? &J : nullptr);
+      add_quad_cost(r, P.w_x, &J, nullptr, derivs, o);
+    }
+    {
+      Vec r(nu);
+      for (int i = 0; i < nu; i++)
+        r[i] = u[i] - s.u_ref[i];
+      Mat Ju;
+      if (derivs)
+      {
+        Ju.resize(nu, nu);
+        for (int i = 0; i < nu; i++)
+          Ju(i, i) = 1.0;
+      }
+      add_quad_cost(r, P.w_u, nullptr, &Ju, derivs, o);
+    }
+    {
+      Vec r(k.hg, k.hg + 6);
+      Mat Jx;
+      if (derivs)
+      {
+        Jx.resize(6, ndx);
+        for (int rr = 0; rr < 6; rr++)
+          for (int j = 0; j < nv; j++)
+          {
+            Jx(rr, j) = k.dh_dq(rr, j);
+            Jx(rr, nv + j) = k.Ag(rr, j);
+          }
+      }
+      add_quad_cost(r, P.w_cent, &Jx, nullptr, derivs, o);
+    }
+    for (int f = 0; f < nk; f++)
+    {
+      Vec r(3);
+      for (int rr = 0; rr < 3; rr++)
+        r[rr] = k.oMf[f].p[rr] - s.foot_ref[f][9 + rr];
+      Mat Jx;
+      if (derivs)
+      {
+        Jx.resize(3, ndx);
+        for (int rr = 0; rr < 3; rr++)
+          for (int j = 0; j < nv; j++)
+            Jx(rr, j) = Jp[f](rr, j);
+      }
+      add_quad_cost(r, P.w_frame, &Jx, nullptr, derivs, o);
+    }
+    for (size_t cf = 0; cf < fd.feet.size(); cf++)
+    {
+      const int f = fd.feet[cf];
+      Vec r(3);
+      for (int rr = 0; rr < 3; rr++)
+        r[rr] = fd.lam[3 * cf + rr] - s.f_ref[f][rr];
+      Mat Jx, Ju;
+      if (derivs)
+      {
+        Jx.resize(3, ndx);
+        Ju.resize(3, nu);
+        for (int rr = 0; rr < 3; rr++)
+        {
+          for (int j = 0; j < nv; j++)
+          {
+            Jx(rr, j) = fd.dl_dq(3 * (int)cf + rr, j);
+            Jx(rr, nv + j) = fd.dl_dv(3 * (int)cf + rr, j);
+          }
+          for (int j = 0; j < nu; j++)
+            Ju(rr, j) = fd.dl_dtau(3 * (int)cf + rr, 6 + j);
+        }
+      }
+      add_quad_cost(r, P.w_forces, &Jx, &Ju, derivs, o);
+    }
+
+    // ---------------- constraints ----------------
+    int row = 0;
+    if (P.ocp.torque_limits)
+      for (int j = 0; j < nj; j++, row++)
+      {
+        o.c[row] = u[j];
+        o.ctype[row] = CSTR_BOX;
+        o.lo[row] = P.umin[j];
+        o.hi[row] = P.umax[j];
+        if (derivs)
+          o.Cu(row, j) = 1.0;
+      }
+    if (P.ocp.kinematics_limits)
+      for (int j = 0; j < nj; j++, row++)
+      {
+        o.c[row] = q[7 + j];
+        o.ctype[row] = CSTR_BOX;
+        o.lo[row] = P.qmin[j];
+        o.hi[row] = P.qmax[j];
+        if (derivs)
+          o.Cx(row, 6 + j) = 1.0;
+      }
+    for (size_t cf = 0; cf < fd.feet.size(); cf++)
+    {
+      const int f = fd.feet[cf], jf = m.d.foot_joint[f];
+      if (P.ocp.force_cone)
+      {
+        double Ac[15];
+        friction_pyramid(P.ocp.mu, Ac);
+        for (int rr = 0; rr < 5; rr++, row++)
+        {
+          double sacc = 0;
+          for (int c = 0; c < 3; c++)
+            sacc += Ac[3 * rr + c] * fd.lam[3 * cf + c];
+          o.c[row] = sacc;
+          o.ctype[row] = CSTR_NEG;
+          if (derivs)
+            for (int c = 0; c < 3; c++)
+            {
+              for (int j = 0; j < nv; j++)
+              {
+                o.Cx(row, j) += Ac[3 * rr + c] * fd.dl_dq(3 * (int)cf + c, j);
+                o.Cx(row, nv + j) += Ac[3 * rr + c] * fd.dl_dv(3 * (int)cf + c, j);
+              }
+              for (int j = 0; j < nu; j++)
+                o.Cu(row, j) += Ac[3 * rr + c] * fd.dl_dtau(3 * (int)cf + c, 6 + j);
+            }
+        }
+      }
+      if (P.ocp.land_cstr && (s.land_mask & (1u << f)))
+      {
+        const double * vi = &k.ov[6 * jf];
+        const double * p = k.oMf[f].p;
+        double wxp[3], pd[3];
+        cross3(vi + 3, p, wxp);
+        for (int rr = 0; rr < 3; rr++)
+          pd[rr] = vi[rr] + wxp[rr];
+        for (int rr = 0; rr < 3; rr++)
+        {
+          o.c[row + rr] = pd[rr];
+          o.ctype[row + rr] = CSTR_EQ;
+        }
+        if (derivs)
+          for (int j = 0; j < nv; j++)
+          {
+            const int ij = m.joint_of_dof[j];
+            if (!m.anc[jf][ij])
+              continue;
+            const int pj = m.d.parent[ij];
+            double Jm[6], dvp[6], dvq[6], t1[3], t2[3], Jpj[3] = {Jp[f](0, j), Jp[f](1, j), Jp[f](2, j)};
+            for (int rr = 0; rr < 6; rr++)
+            {
+              Jm[rr] = k.J(rr, j);
+              dvp[rr] = ((pj >= 0) ? k.ov[6 * pj + rr] : 0.0) - vi[rr];
+            }
+            mxm(dvp, Jm, dvq);
+            cross3(dvq + 3, p, t1);
+            cross3(vi + 3, Jpj, t2);
+            for (int rr = 0; rr < 3; rr++)
+            {
+              o.Cx(row + rr, j) = dvq[rr] + t1[rr] + t2[rr];
+              o.Cx(row + rr, nv + j) = Jpj[rr];
+            }
+          }
+        row += 3;
+        o.c[row] = p[2] - s.foot_ref[f][9 + 2];
+        o.ctype[row] = CSTR_EQ;
+        if (derivs)
+          for (int j = 0; j < nv; j++)
+            o.Cx(row, j) = Jp[f](2, j);
+        row++;
+      }
+    }
+    if (row != o.nc)
+      throw std::runtime_error("full_stage_eval: constraint row count mismatch");
+  }
+
   // Terminal node of kinodynamics / full dynamics (reference src/kinodynamics.cpp:352-377):
   // state_cost + centroidal_cost with 10 w_cent; optional DCM equality  c + tau cdot - ref = 0.
   inline void multibody_terminal_eval(const Problem & P, const smpc_terminal & tm, const double * x, bool derivs, StageEval & o)
@@ -988,7 +1290,7 @@ namespace orc
     else if (P.ocp.kind == SMPC_OCP_CENTROIDAL)
       centroidal_stage_eval(P, s, x, u, derivs, o);
     else
-      throw std::runtime_error("oracle: full-dynamics stage not restated yet");
+      full_stage_eval(P, s, x, u, derivs, o);
   }
   inline void terminal_eval(const Problem & P, const smpc_terminal & tm, const double * x, bool derivs, StageEval & o)
   {

@@ -115,6 +115,12 @@ namespace smpc
             s.Lu[j] = s.lu[j] + t1 + Lc;
             s.gu[j] = s.lu[j] + t2 + gc;
           }
+      }
+      SMPC_END
+      // (phase boundary: the full-dynamics knot keeps its Cx / Cu rows in the knot's own C / D blocks, so the
+      //  masking below must not start before every thread has finished reading them above)
+      SMPC_PAR(tid)
+      {
         double * Cm = io.knot + L.oC;
         for (int e = tid; e < L.ncmax * NDX; e += SMPC_NT)
         {

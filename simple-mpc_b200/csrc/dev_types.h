@@ -17,12 +17,12 @@ namespace smpc
     double total_mass;
   };
 
-  // The problem recipe with owned storage (kinodynamics / centroidal).
+  // The problem recipe with owned storage.
   struct DevOcp
   {
     int kind, N, fs, nk;
     int nx, ndx, nu, ncmax, nct; // nct: terminal constraint rows
-    int kinematics_limits, force_cone, land_cstr, terminal_constraint;
+    int kinematics_limits, torque_limits, force_cone, land_cstr, terminal_constraint;
     double dt, gravity[3], mu, Lfoot, Wfoot, mass;
     double w_x[SMPC_MAX_NDX]; // diagonal of w_x (non-diagonal w_x is rejected at create)
     double w_u[SMPC_MAX_NU];  // diagonal of w_u
@@ -30,6 +30,11 @@ namespace smpc
     double w_com[9], w_lmom[9], w_amom[9], w_lacc[9], w_aacc[9];
     double qmin[SMPC_MAX_NV], qmax[SMPC_MAX_NV];
     double wcone[17 * 6]; // wrench-cone rows A w <= 0 for 6-D contacts (mu, Lfoot, Wfoot)
+    // full dynamics (reference src/fulldynamics.cpp)
+    double w_forces[36];
+    double umin[SMPC_MAX_NV], umax[SMPC_MAX_NV];
+    double Kp[6], Kd[6];  // Baumgarte corrector of the rigid contacts
+    double pyramid[5 * 3]; // friction pyramid rows A lam <= 0 (aligator MultibodyFrictionConeResidual [UPSTREAM])
   };
 
   // Dense LQ knot layout in HBM (offsets in doubles from the knot base), row-major blocks.

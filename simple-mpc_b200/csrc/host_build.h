@@ -153,7 +153,48 @@ namespace smpc
       build_wrench_cone(o.mu, o.Lfoot, o.Wfoot, O.wcone);
     }
     else
-      throw std::runtime_error("ocp: full-dynamics problems have no CUDA kernels yet");
+    {
+      // FullDynamicsOCP (reference src/fulldynamics.cpp:30-76): nu = nv - 6, rigid point contacts
+      if (O.fs != 3)
+        throw std::runtime_error("ocp: full dynamics with 6-D contacts is not supported by the CUDA path yet");
+      O.nx = m.nq + m.nv;
+      O.ndx = 2 * m.nv;
+      O.nu = nj;
+      if (!o.w_x || !o.w_u)
+        throw std::runtime_error("ocp: w_x / w_u missing");
+      if (!is_diagonal(o.w_x, O.ndx) || !is_diagonal(o.w_u, O.nu))
+        throw std::runtime_error("ocp: the CUDA path implements diagonal w_x / w_u only");
+      for (int i = 0; i < O.ndx; i++)
+        O.w_x[i] = o.w_x[i * O.ndx + i];
+      for (int i = 0; i < O.nu; i++)
+        O.w_u[i] = o.w_u[i * O.nu + i];
+      cp(O.w_cent, o.w_cent, 36, "w_cent");
+      cp(O.w_frame, o.w_frame, 9, "w_frame");
+      cp(O.w_forces, o.w_forces, 9, "w_forces");
+      O.torque_limits = o.torque_limits;
+      if (o.torque_limits)
+      {
+        cp(O.umin, o.umin, nj, "umin");
+        cp(O.umax, o.umax, nj, "umax");
+      }
+      if (o.kinematics_limits)
+      {
+        cp(O.qmin, o.qmin, nj, "qmin");
+        cp(O.qmax, o.qmax, nj, "qmax");
+      }
+      for (int k = 0; k < 3; k++)
+      {
+        O.Kp[k] = o.Kp_correction[k];
+        O.Kd[k] = o.Kd_correction[k];
+      }
+      const double pyr[5][3] = {{0, 0, -1}, {-1, 0, -o.mu}, {1, 0, -o.mu}, {0, -1, -o.mu}, {0, 1, -o.mu}};
+      memcpy(O.pyramid, pyr, sizeof(pyr));
+      for (int i = 1; i < m.njoints; i++)
+        if (m.idx_v[m.parent[i]] >= m.idx_v[i])
+          throw std::runtime_error("model: velocity indices must increase from parent to child");
+      O.ncmax = (o.torque_limits ? nj : 0) + (o.kinematics_limits ? nj : 0) + O.nk * ((o.force_cone ? 5 : 0) + (o.land_cstr ? 4 : 0));
+      O.nct = o.terminal_constraint ? 3 : 0;
+    }
     if (O.ncmax < O.nct)
       O.ncmax = O.nct;
     if (O.ncmax < 1)

@@ -107,8 +107,8 @@ namespace smpc
   // ------------------------------------------------------------------------------------------
   // kinematics + centroidal quantities shared by stage and terminal knots
   // ------------------------------------------------------------------------------------------
-  template <class Cfg>
-  SMPC_DEV void kino_kinematics(const DevModel & M, KinoScratch<Cfg> & s)
+  template <class Cfg, class S>
+  SMPC_DEV void kino_kinematics(const DevModel & M, S & s)
   {
     constexpr int NV = Cfg::NV, NQ = Cfg::NQ;
     const smpc_model_desc & d = M.d;
@@ -266,8 +266,8 @@ namespace smpc
 
   // spatial accelerations (gravity-free) and inertial forces for joint accelerations `acc` (NULL = 0),
   // then the subtree force sums fs.
-  template <class Cfg>
-  SMPC_DEV void kino_accel_pass(const DevModel & M, KinoScratch<Cfg> & s, const double * acc)
+  template <class Cfg, class S>
+  SMPC_DEV void kino_accel_pass(const DevModel & M, S & s, const double * acc)
   {
     const smpc_model_desc & d = M.d;
     for (int l = 0; l < M.nlevels; l++)
@@ -315,8 +315,8 @@ namespace smpc
   }
 
   // com, momenta, Ag columns, foot placements / velocities
-  template <class Cfg>
-  SMPC_DEV void kino_centroid(const DevModel & M, KinoScratch<Cfg> & s)
+  template <class Cfg, class S>
+  SMPC_DEV void kino_centroid(const DevModel & M, S & s)
   {
     constexpr int NV = Cfg::NV, NK = Cfg::NK;
     const smpc_model_desc & d = M.d;

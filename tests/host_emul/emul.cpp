@@ -4,6 +4,7 @@
 // box. The shipped library (libsmpc_cuda.so) never contains or calls this code.
 #include "../../simple-mpc_b200/csrc/kino_knot.cuh"
 #include "../../simple-mpc_b200/csrc/centro_knot.cuh"
+#include "../../simple-mpc_b200/csrc/full_knot.cuh"
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati2.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
@@ -92,6 +93,63 @@ int emul_kino_knot(
   }
   return 0;
 }
+
+// one full-dynamics knot (Go2 sizes, point feet); same argument meaning as emul_kino_knot. The terminal node is
+// the kinodynamics one (reference src/fulldynamics.cpp:418-445 builds the same terminal cost / constraint).
+int emul_full_knot(
+  const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const smpc_terminal * term, int terminal,
+  int derivs, const double * x, const double * u, const double * xn, const double * vs, const double * prev_vs,
+  const double * lam_t, const double * lam_n, const double * prev_lam_n, double mu, double preg, double * knot, int * nc,
+  double * gx, double * gu, double * lplus, double * xdot, double * scalars /*8*/)
+{
+  try
+  {
+    typedef FullCfg<13, 18, 4> FCfg;
+    auto M = std::make_unique<DevModel>();
+    auto O = std::make_unique<DevOcp>();
+    build_dev_model(*model, *M);
+    build_dev_ocp(*model, *ocp, *O);
+    if (O->kind != SMPC_OCP_FULLDYNAMICS || model->njoints != 13 || model->nv != 18 || model->nfeet != 4 || O->fs != 3)
+      throw std::runtime_error("emul: only the Go2-sized full-dynamics instantiation is built");
+    KnotLayout L = make_knot_layout(O->ndx, O->nu, O->ncmax);
+    KnotIO io;
+    memset(&io, 0, sizeof(io));
+    io.x = x, io.u = u, io.xn = xn;
+    io.slot = slot, io.term = term;
+    io.vs = vs, io.prev_vs = prev_vs, io.lam_t = lam_t, io.lam_n = lam_n, io.prev_lam_n = prev_lam_n;
+    io.mu = mu, io.preg = preg;
+    io.knot = knot, io.nc_out = nc, io.gx = gx, io.gu = gu, io.lplus_n = lplus, io.xdot = xdot;
+    KnotScalars sc;
+    memset(&sc, 0, sizeof(sc));
+    io.sc = &sc;
+    if (terminal)
+    {
+      auto s = std::make_unique<KinoScratch<Go2Cfg>>();
+      memset(s.get(), 0, sizeof(*s));
+      if (derivs)
+        kino_terminal_knot<Go2Cfg, true>(*M, *O, L, io, *s);
+      else
+        kino_terminal_knot<Go2Cfg, false>(*M, *O, L, io, *s);
+    }
+    else
+    {
+      auto s = std::make_unique<FullScratch<FCfg>>();
+      memset(s.get(), 0, sizeof(*s));
+      if (derivs)
+        full_stage_knot<FCfg, true>(*M, *O, L, io, *s);
+      else
+        full_stage_knot<FCfg, false>(*M, *O, L, io, *s);
+    }
+    memcpy(scalars, &sc, sizeof(sc));
+  }
+  catch (const std::exception & e)
+  {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+int emul_full_scratch_bytes() { return (int)sizeof(FullScratch<FullCfg<13, 18, 4>>); }
 
 int emul_centro_knot(
   const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const smpc_terminal * term, int terminal,

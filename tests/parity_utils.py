@@ -7,7 +7,7 @@ same C-ABI call sequence that MPC::MPC / MPC::iterate perform (reference src/mpc
 """
 import ctypes as C
 import numpy as np
-from smpc_ctypes import (Slot, Terminal, SolveInfo, SolverOpts, dbl_p, go2_like_model, go2_kino_ocp, standing_slot,
+from smpc_ctypes import (Slot, Terminal, SolveInfo, SolverOpts, dbl_p, go2_like_model, go2_kino_ocp, go2_full_ocp, full_slot, standing_slot,
                          fk_numpy, x_ref_of, total_mass, load_oracle, load_cuda, talos_like_model, talos_centroidal_ocp,
                          centroidal_slot, com_numpy)
 
@@ -167,6 +167,46 @@ class Go2Scenario:
             if tick == 0:
                 x[i, 7:19] += r.normal(size=12) * 0.02
         return x
+
+
+class Go2FullScenario(Go2Scenario):
+    """Config C3 of SURVEY.md §8d on the synthetic go2-like robot: FullDynamicsOCP (rigid point contacts), T = 50, trot
+    10/30/10/30, torque + joint limits, and (by default) the friction-cone and landing constraints switched on
+    (reference examples/go2_fulldynamics.py:43-77 with force_cone / land_cstr flipped, src/fulldynamics.cpp:185-209)."""
+
+    def __init__(self, batch, seed=0, T=50, **ocp_kw):
+        kw = dict(force_cone=True, land_cstr=True)
+        kw.update(ocp_kw)
+        self.B, self.T = batch, T
+        self.model, self.limits = go2_like_model()
+        self.ocpb = go2_full_ocp(self.model, self.limits, T=T, **kw)
+        self.nq, self.nv = self.model.nq, self.model.nv
+        self.nx, self.ndx, self.nu = self.nq + self.nv, 2 * self.nv, self.nv - 6
+        self.xref = x_ref_of(self.model)
+        self.feet = fk_numpy(self.model, self.xref[: self.nq])["feet"]
+        self.mass = total_mass(self.model)
+        rngs = [np.random.default_rng([seed, i]) for i in range(batch)]
+        self.phase = np.array([int(r.integers(0, 80)) for r in rngs])
+        self.noise = [r for r in rngs]
+        self.tick = 0
+
+    def gait_slot(self, k):
+        mask = self.GAIT[k % 80]
+        prev = self.GAIT[(k - 1) % 80]
+        return full_slot(self.model, self.ocpb, self.feet, contact_mask=mask, land_mask=mask & ~prev)
+
+    def initial_slots(self):
+        # the stages createProblem builds, after the first updateStepTrackerReferences has written the measured foot
+        # poses into every stage (reference src/mpc.cpp:278-324) — with the Identity poses of createProblem itself the
+        # 1000-weight pose cost fights the rigid contacts and the constructor solve is ill-posed
+        s = full_slot(self.model, self.ocpb, self.feet)
+        return (Slot * (self.B * self.T))(*([s] * (self.B * self.T)))
+
+    def warmstart(self):
+        # MPC::MPC: xs = x0, us = getReferenceControl(0) = 0 for the full-dynamics handler (reference src/mpc.cpp:24-26)
+        xs = np.tile(self.xref, (self.B, self.T + 1, 1)).copy()
+        us = np.zeros((self.B, self.T, self.nu))
+        return xs, us
 
 
 class TalosCentroidalScenario:

@@ -364,6 +364,54 @@ def go2_kino_ocp(m, limits, T=50, force_cone=False, land_cstr=False, kinematics_
     return OcpBundle(d, arrays)
 
 
+def go2_full_ocp(m, limits, T=50, force_cone=False, land_cstr=False, kinematics_limits=True, torque_limits=True,
+                 terminal_constraint=False, Kp=(0.0, 0.0, 0.0), Kd=(0.0, 0.0, 0.0), effort=23.7):
+    """Problem recipe of reference examples/go2_fulldynamics.py:43-77 (C3 of SURVEY.md §8d flips force_cone / land_cstr on).
+    effort: symmetric torque limit (Go2 hip/thigh motors, 23.7 N m; the URDF is absent)."""
+    nv = m.nv
+    w_x = np.diag(np.array([0, 0, 0, 0, 0, 0] + [1, 1, 1] * 4 + [10] * 6 + [0.1, 0.1, 0.1] * 4, float))
+    w_u = np.eye(nv - 6) * 1e-4
+    w_cent = np.diag(np.array([0.04, 0.04, 0, 0, 0, 0], float))
+    w_forces = np.eye(3) * 1e-4
+    w_frame = np.eye(3) * 1000.0
+    arrays = dict(w_x=np.ascontiguousarray(w_x), w_u=np.ascontiguousarray(w_u), w_cent=w_cent, w_forces=w_forces,
+                  w_frame=w_frame, qmin=limits["qmin"].copy(), qmax=limits["qmax"].copy(),
+                  umin=-np.ones(nv - 6) * effort, umax=np.ones(nv - 6) * effort)
+    d = OcpDesc()
+    d.kind, d.horizon, d.force_size = FULL, T, 3
+    d.kinematics_limits, d.torque_limits = int(kinematics_limits), int(torque_limits)
+    d.force_cone, d.land_cstr = int(force_cone), int(land_cstr)
+    d.terminal_constraint = int(terminal_constraint)
+    d.timestep = 0.01
+    d.gravity[:] = [0, 0, -9.81]
+    d.mu, d.Lfoot, d.Wfoot = 0.8, 0.01, 0.01
+    d.Kp_correction[:3] = Kp
+    d.Kd_correction[:3] = Kd
+    for k, v in arrays.items():
+        setattr(d, k, _p(v))
+    return OcpBundle(d, arrays)
+
+
+def full_slot(m, ocp_bundle, foot_poses, contact_mask=None, land_mask=0):
+    """Slot of a stage created by FullDynamicsOCP::createStage (reference src/fulldynamics.cpp:78-214):
+    control target 0 (:89), force reference mg/nk on every stance foot (examples/go2_fulldynamics.py:40)."""
+    d = ocp_bundle.desc
+    nk = m.nfeet
+    s = Slot()
+    if contact_mask is None:
+        contact_mask = (1 << nk) - 1
+    s.contact_mask, s.land_mask = contact_mask, land_mask
+    xr = x_ref_of(m)
+    s.x_ref[: len(xr)] = xr
+    for f in range(nk):
+        if contact_mask & (1 << f):
+            s.f_ref[f][2] = -total_mass(m) * d.gravity[2] / nk
+        R, p = foot_poses[f]
+        s.foot_ref[f][:9] = np.asarray(R).ravel()
+        s.foot_ref[f][9:] = p
+    return s
+
+
 def default_opts(lib, prefix="orc"):
     o = SolverOpts()
     getattr(lib, prefix + "_default_solver_opts")(C.byref(o))

@@ -1,0 +1,147 @@
+"""Full-dynamics kernel LOGIC vs the oracle on the CPU-only box (see test_emul_vs_oracle.py for the harness):
+the per-knot linearisation of csrc/full_knot.cuh (rigid-contact forward dynamics, its derivatives, costs, constraints,
+multiplier projection) must reproduce the oracle's LQ knots to rounding, and the generic Riccati sweep fed with those
+knots must return the oracle's gains within the conditioning of the penalised recursion."""
+import ctypes as C
+import numpy as np
+import pytest
+from smpc_ctypes import (load_oracle, go2_like_model, go2_full_ocp, full_slot, fk_numpy, x_ref_of, default_opts, Slot, Terminal,
+                         SolveInfo, dbl_p)
+from test_emul_vs_oracle import load_emul, GAIT
+
+
+def P(a):
+    return a.ctypes.data_as(dbl_p)
+
+
+def run_case(cone, kp):
+    orc, emu = load_oracle(), load_emul()
+    m, lim = go2_like_model()
+    nq, nv, T = m.nq, m.nv, 50
+    nx, ndx, nu = nq + nv, 2 * nv, 12
+    ocpb = go2_full_ocp(m, lim, T=T, force_cone=cone, land_cstr=cone, terminal_constraint=cone,
+                        Kp=(kp, kp, 10 * kp), Kd=(kp, kp, 2 * kp))
+    ocp = ocpb.desc
+    opts = default_opts(orc)
+    ctx = C.c_void_p()
+    assert orc.orc_create(C.byref(ctx), 1, C.byref(m), C.byref(ocp), C.byref(opts)) == 0, orc.orc_last_error()
+    ncmax = orc.orc_get_ncmax(ctx)
+    xref = x_ref_of(m)
+    feet = fk_numpy(m, xref[:nq])['feet']
+    rng = np.random.default_rng(1)
+
+    def gait_slot(i):
+        mask, prev = GAIT[i % 80], GAIT[(i - 1) % 80]
+        return full_slot(m, ocpb, feet, contact_mask=mask, land_mask=mask & ~prev)
+
+    slots = (Slot * T)(*[gait_slot(i) for i in range(T)])
+    orc.orc_set_slots(ctx, 0, 1, slots)
+    term = Terminal()
+    term.x_ref[:nx] = xref
+    term.com_ref[:] = [0.0, 0.0, 0.3]
+    orc.orc_set_terminal(ctx, 0, 1, C.byref(term))
+    xs = np.tile(xref, (T + 1, 1)).copy()
+    us = np.zeros((T, nu))
+    orc.orc_set_warmstart(ctx, 0, 1, P(xs), P(us))
+    x0 = xref.copy()
+    x0[nq:] += rng.normal(size=nv) * 0.1
+    x0[7:19] += rng.normal(size=12) * 0.05
+    info = SolveInfo()
+    assert orc.orc_solve(ctx, P(x0), 2) == 0, orc.orc_last_error()  # two iterations: non-trivial multipliers
+    orc.orc_get_info(ctx, 0, 1, C.byref(info))
+    preg, mu = info.preg, 1e-8
+    xs0, us0 = np.zeros((T + 1, nx)), np.zeros((T, nu))
+    orc.orc_get_results(ctx, 0, 1, P(xs0), P(us0), None, None)
+    vs0, lams0 = np.zeros((T + 1, ncmax)), np.zeros((T + 1, ndx))
+    orc.orc_get_duals(ctx, 0, 1, P(vs0), P(lams0))
+    orc.orc_solve(ctx, P(xs0[0].copy()), 1)  # the iteration whose LQ problem is compared
+    orc.orc_get_info(ctx, 0, 1, C.byref(info))
+    lay = np.zeros(12, np.int32)
+    emu.emul_knot_layout(ndx, nu, ncmax, lay.ctypes.data_as(C.POINTER(C.c_int)))
+    oQ, oS, oR, oq, or_, oA, oB, of, oC, oD, od, size = [int(v) for v in lay]
+    names = ['Q', 'S', 'R', 'q', 'r', 'A', 'B', 'f', 'C', 'D', 'd']
+    worst, pinf, dinf = {}, 0.0, 0.0
+    emu_knots = np.zeros((T + 1, size))
+    ncs = np.zeros(T + 1, np.int32)
+    gxs, gus, lpl = np.zeros((T + 1, ndx)), np.zeros((T, nu)), np.zeros((T + 1, ndx))
+    for t in range(T + 1):
+        knot, nc = np.zeros(size), C.c_int(0)
+        gx, gu, lplus, xdot, sc = np.zeros(ndx), np.zeros(nu), np.zeros(ndx), np.zeros(ndx), np.zeros(8)
+        u = us0[t] if t < T else np.zeros(nu)
+        xn = xs0[t + 1] if t < T else xs0[t]
+        lam_n = lams0[t + 1] if t < T else np.zeros(ndx)
+        r = emu.emul_full_knot(C.byref(m), C.byref(ocp), C.byref(slots[min(t, T - 1)]), C.byref(term), int(t == T), 1, P(xs0[t]), P(u),
+                               P(xn), P(vs0[t]), P(vs0[t]), P(lams0[t]), P(lam_n), P(lam_n), C.c_double(mu), C.c_double(preg),
+                               P(knot), C.byref(nc), P(gx), P(gu), P(lplus), P(xdot), P(sc))
+        assert r == 0, emu.emul_last_error()
+        emu_knots[t], ncs[t], gxs[t] = knot, nc.value, gx
+        if t < T:
+            gus[t], lpl[t + 1] = gu, lplus
+        pinf = max(pinf, sc[2])
+        dinf = max(dinf, sc[7] if t < T else 0, sc[6] if t > 0 else 0)
+        o = dict(Q=np.zeros((ndx, ndx)), S=np.zeros((ndx, nu)), R=np.zeros((nu, nu)), q=np.zeros(ndx), r=np.zeros(nu),
+                 A=np.zeros((ndx, ndx)), B=np.zeros((ndx, nu)), f=np.zeros(ndx), C=np.zeros((ncmax, ndx)), D=np.zeros((ncmax, nu)),
+                 d=np.zeros(ncmax))
+        onc = C.c_int(0)
+        assert orc.orc_get_knot(ctx, 0, t, C.byref(onc), *[P(o[k]) for k in names]) == 0
+        n = onc.value
+        assert n == nc.value, (t, n, nc.value)
+        kn = np.zeros(size)
+        Cm, Dm, dm = np.zeros((ncmax, ndx)), np.zeros((ncmax, nu)), np.zeros(ncmax)
+        Cm[:n] = o['C'].ravel()[:n * ndx].reshape(n, ndx)
+        dm[:n] = o['d'][:n]
+        kn[oQ:oQ + ndx * ndx], kn[oq:oq + ndx] = o['Q'].ravel(), o['q']
+        kn[oC:oC + ncmax * ndx], kn[od:od + ncmax] = Cm.ravel(), dm
+        blocks = dict(Q=(oQ, ndx * ndx), q=(oq, ndx), C=(oC, ncmax * ndx), d=(od, ncmax))
+        if t < T:
+            Dm[:n] = o['D'].ravel()[:n * nu].reshape(n, nu)
+            kn[oS:oS + ndx * nu], kn[oR:oR + nu * nu], kn[or_:or_ + nu] = o['S'].ravel(), o['R'].ravel(), o['r']
+            kn[oA:oA + ndx * ndx], kn[oB:oB + ndx * nu], kn[of:of + ndx] = o['A'].ravel(), o['B'].ravel(), o['f']
+            kn[oD:oD + ncmax * nu] = Dm.ravel()
+            blocks.update(S=(oS, ndx * nu), R=(oR, nu * nu), r=(or_, nu), A=(oA, ndx * ndx), B=(oB, ndx * nu), f=(of, ndx),
+                          D=(oD, ncmax * nu))
+        for k, (o0, sz) in blocks.items():
+            a, b = knot[o0:o0 + sz], kn[o0:o0 + sz]
+            den = np.abs(b).max()
+            err = np.abs(a - b).max() / den if den > 0 else np.abs(a).max()
+            worst[k] = max(worst.get(k, 0.0), err)
+    odx, odu = np.zeros((T + 1, ndx)), np.zeros((T, nu))
+    orc.orc_get_step(ctx, 0, P(odx), P(odu))
+    Ko, ko, xs1, us1 = np.zeros((T, nu, ndx)), np.zeros((T, nu)), np.zeros((T + 1, nx)), np.zeros((T, nu))
+    orc.orc_get_results(ctx, 0, 1, P(xs1), P(us1), P(Ko), P(ko))
+    slay = np.zeros(7, np.int32)
+    emu.emul_sol_layout(ndx, nu, ncmax, slay.ctypes.data_as(C.POINTER(C.c_int)))
+    oK, ssize = int(slay[0]), int(slay[6])
+    sol = np.zeros((T + 1, ssize))
+    dxs, dus = np.zeros((T + 1, ndx)), np.zeros((T, nu))
+    vnew, lnew = np.zeros((T + 1, ncmax)), np.zeros((T + 1, ndx))
+    dphi, flag = C.c_double(0), C.c_int(0)
+    rc = emu.emul_riccati(T, ndx, nu, ncmax, P(emu_knots), ncs.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(mu), C.c_double(mu), P(sol),
+                          P(gxs), P(gus), P(lpl), P(dxs), P(dus), P(vnew), P(lnew), C.byref(dphi), C.byref(flag))
+    assert rc == 0 and flag.value == 0
+    K = np.array([sol[t][oK:oK + nu * ndx].reshape(nu, ndx) for t in range(T)])
+    orc.orc_destroy(ctx)
+    return dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu, K=K, dxs=dxs, dus=dus)
+
+
+@pytest.fixture(scope="module", params=[(False, 0.0), (True, 5.0)], ids=["torque+joint-limits", "cone+landing+dcm+baumgarte"])
+def case(request):
+    return run_case(*request.param)
+
+
+def test_full_knots_match_oracle_to_rounding(case):
+    w = case['worst']
+    for k in ['Q', 'S', 'R', 'q', 'r', 'A', 'B', 'C', 'D', 'd']:
+        assert w[k] < 1e-10, (k, w[k])
+    assert w['f'] < 1e-9
+
+
+def test_full_infeasibility_scalars_match(case):
+    assert abs(case['pinf'] - case['info'].prim_infeas) <= 1e-10 * max(1.0, case['info'].prim_infeas)
+    assert abs(case['dinf'] - case['info'].dual_infeas) <= 1e-8 * max(1.0, case['info'].dual_infeas)
+
+
+def test_full_end_to_end_gains_within_conditioning(case):
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(case['K'], case['Ko']) < 1e-6
+    assert rel(case['dus'], case['odu']) < 1e-6
