@@ -12,6 +12,7 @@
 // CUDA runtime does.
 #include "kino_knot.cuh"
 #include "centro_knot.cuh"
+#include "full_knot.cuh"
 #include "riccati.cuh"
 #include "riccati2.cuh"
 #include "riccati3.cuh"
@@ -189,6 +190,27 @@ namespace
       centro_stage_knot<Cfg, !TRIAL>(*A.ocp, A.L, io, s);
     else
       centro_terminal_knot<Cfg, !TRIAL>(*A.ocp, A.L, io, s);
+  }
+
+  // full dynamics: one CTA per knot; the terminal node is the kinodynamics one (same terminal cost / constraint,
+  // reference src/fulldynamics.cpp:418-445 vs src/kinodynamics.cpp:352-377)
+  template <class Cfg, class TermCfg, bool TRIAL>
+  __global__ void __launch_bounds__(128) k_knots_full(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const Dims & d = A.dm;
+    const int b = blockIdx.x / (d.N + 1);
+    const int t = blockIdx.x % (d.N + 1);
+    const InstState & st = A.inst[b];
+    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
+      return;
+    KnotIO io;
+    int nc_dummy;
+    make_knot_io<TRIAL>(A, st, b, t, io, &nc_dummy);
+    if (t < d.N)
+      full_stage_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, *reinterpret_cast<FullScratch<Cfg> *>(smem_raw));
+    else
+      kino_terminal_knot<TermCfg, !TRIAL>(*A.model, *A.ocp, A.L, io, *reinterpret_cast<KinoScratch<TermCfg> *>(smem_raw));
   }
 
   // per-instance reductions and the ProxDDP control flow between linearisation and the Newton step
@@ -616,6 +638,30 @@ namespace
     return SMPC_OK;
   }
 
+  template <class Cfg, class TermCfg>
+  void launch_knots_full_impl(smpc_ctx * c, bool trial)
+  {
+    const Dims & d = c->A.dm;
+    const int grid = d.B * (d.N + 1);
+    if (trial)
+      k_knots_full<Cfg, TermCfg, true><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
+    else
+      k_knots_full<Cfg, TermCfg, false><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
+    c->launches++;
+  }
+  template <class Cfg, class TermCfg>
+  int setup_knots_full(smpc_ctx * c)
+  {
+    c->knot_smem = sizeof(FullScratch<Cfg>) > sizeof(KinoScratch<TermCfg>) ? sizeof(FullScratch<Cfg>) : sizeof(KinoScratch<TermCfg>);
+    c->knot_threads = 64;
+    if (const char * e = getenv("SMPC_KNOT_THREADS"))
+      c->knot_threads = atoi(e) == 32 ? 32 : (atoi(e) == 128 ? 128 : 64);
+    CU(cudaFuncSetAttribute(k_knots_full<Cfg, TermCfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    CU(cudaFuncSetAttribute(k_knots_full<Cfg, TermCfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    c->launch_knots = &launch_knots_full_impl<Cfg, TermCfg>;
+    return SMPC_OK;
+  }
+
   void launch_riccati_generic(smpc_ctx * c)
   {
     k_riccati<<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
@@ -808,13 +854,15 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   int rc = SMPC_ERR_UNSUPPORTED;
   if (O.kind == SMPC_OCP_KINODYNAMICS && model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3)
     rc = setup_knots<KinoCfg<13, 18, 4, 3>>(c);
+  else if (O.kind == SMPC_OCP_FULLDYNAMICS && model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3)
+    rc = setup_knots_full<FullCfg<13, 18, 4>, KinoCfg<13, 18, 4, 3>>(c);
   else if (O.kind == SMPC_OCP_CENTROIDAL && O.nk == 2 && O.fs == 6)
     rc = setup_knots_centro<CentroCfg<2, 6>>(c);
   else if (O.kind == SMPC_OCP_CENTROIDAL && O.nk == 4 && O.fs == 3)
     rc = setup_knots_centro<CentroCfg<4, 3>>(c);
   else
-    g_err = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics on a 12-DoF quadruped with point feet; "
-            "centroidal with 2 quad feet or 4 point feet)";
+    g_err = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics and full dynamics on a 12-DoF quadruped with "
+            "point feet; centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
   {
     delete c;

@@ -43,6 +43,20 @@ def test_kino_go2_cone_land_terminal():
     assert r["us"] <= 1e-6 and r["K"] <= 1e-6, r
 
 
+def test_full_go2_reference_example_config():
+    # config C3 base (reference examples/go2_fulldynamics.py:43-77): rigid-contact full dynamics, torque + joint limits
+    _check(pu.run_parity(batch=2, ticks=8, seed=0, verbose=True, scenario=pu.Go2FullScenario, force_cone=False, land_cstr=False))
+
+
+def test_full_go2_friction_cone_and_landing_constraints():
+    # config C3: force_cone and land_cstr flipped on (reference src/fulldynamics.cpp:185-209). The merit
+    # function is stiff (1/mu = 1e8 on nonlinear cone rows), the linesearch backtracks on most ticks: trial counts and
+    # accepted steps must still be EQUAL; the looser value tolerance covers the longer chain of amplified roundings.
+    r = pu.run_parity(batch=2, ticks=6, seed=1, verbose=True, scenario=pu.Go2FullScenario)
+    assert r["iters_equal"] and r["alphas_equal"], r
+    assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
+
+
 def test_centroidal_talos_single_and_batch():
     # config C2: CentroidalOCP, T = 100, 6-D contacts with wrench cones, walk 20/80/20/80
     _check(pu.run_parity(batch=1, ticks=6, seed=0, verbose=True, scenario=pu.TalosCentroidalScenario))
