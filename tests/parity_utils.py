@@ -105,7 +105,7 @@ class Go2Scenario:
 
     GAIT = [0b1111] * 10 + [0b0110] * 30 + [0b1111] * 10 + [0b1001] * 30  # FL=bit0 FR=bit1 RL=bit2 RR=bit3
 
-    def __init__(self, batch, seed=0, T=50, **ocp_kw):
+    def __init__(self, batch, seed=0, T=50, first=0, **ocp_kw):
         self.B, self.T = batch, T
         self.model, self.limits = go2_like_model()
         self.ocpb = go2_kino_ocp(self.model, self.limits, T=T, **ocp_kw)
@@ -114,7 +114,7 @@ class Go2Scenario:
         self.xref = x_ref_of(self.model)
         self.feet = fk_numpy(self.model, self.xref[: self.nq])["feet"]
         self.mass = total_mass(self.model)
-        rngs = [np.random.default_rng([seed, i]) for i in range(batch)]
+        rngs = [np.random.default_rng([seed, first + i]) for i in range(batch)]  # global instance index = stream
         self.phase = np.array([int(r.integers(0, 80)) for r in rngs])
         self.noise = [r for r in rngs]
         self.tick = 0
@@ -174,7 +174,7 @@ class Go2FullScenario(Go2Scenario):
     10/30/10/30, torque + joint limits, and (by default) the friction-cone and landing constraints switched on
     (reference examples/go2_fulldynamics.py:43-77 with force_cone / land_cstr flipped, src/fulldynamics.cpp:185-209)."""
 
-    def __init__(self, batch, seed=0, T=50, **ocp_kw):
+    def __init__(self, batch, seed=0, T=50, first=0, **ocp_kw):
         kw = dict(force_cone=True, land_cstr=True)
         kw.update(ocp_kw)
         self.B, self.T = batch, T
@@ -185,7 +185,7 @@ class Go2FullScenario(Go2Scenario):
         self.xref = x_ref_of(self.model)
         self.feet = fk_numpy(self.model, self.xref[: self.nq])["feet"]
         self.mass = total_mass(self.model)
-        rngs = [np.random.default_rng([seed, i]) for i in range(batch)]
+        rngs = [np.random.default_rng([seed, first + i]) for i in range(batch)]  # global instance index = stream
         self.phase = np.array([int(r.integers(0, 80)) for r in rngs])
         self.noise = [r for r in rngs]
         self.tick = 0
@@ -217,7 +217,7 @@ class TalosCentroidalScenario:
     GAIT = [0b11] * 20 + [0b01] * 80 + [0b11] * 20 + [0b10] * 80  # left = bit0, right = bit1
     CYCLE = 200
 
-    def __init__(self, batch, seed=0, T=100):
+    def __init__(self, batch, seed=0, T=100, first=0):
         self.B, self.T = batch, T
         self.model, self.limits = talos_like_model()
         self.ocpb = talos_centroidal_ocp(self.model, T=T)
@@ -230,7 +230,7 @@ class TalosCentroidalScenario:
         # momentum references: velocity_base * mass for both parts (reference src/centroidal-dynamics.cpp:237-238)
         self.xref_walk = self.xref.copy()
         self.xref_walk[3] = 0.1 * self.mass
-        rngs = [np.random.default_rng([seed, i]) for i in range(batch)]
+        rngs = [np.random.default_rng([seed, first + i]) for i in range(batch)]  # global instance index = stream
         self.phase = np.array([int(r.integers(0, self.CYCLE)) for r in rngs])
         self.noise = rngs
 
