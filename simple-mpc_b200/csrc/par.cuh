@@ -16,6 +16,7 @@
 #ifdef __CUDACC__
 #define SMPC_DEV __device__ __forceinline__
 #define SMPC_DEV_NOINLINE __device__ __noinline__
+#define SMPC_HD __host__ __device__ __forceinline__ // integer bookkeeping shared with the host-side setup code
 #define SMPC_PAR(tid)                                                                                                  \
   {                                                                                                                    \
     const int tid = threadIdx.x;                                                                                       \
@@ -40,6 +41,7 @@
 #endif
 #define SMPC_DEV inline
 #define SMPC_DEV_NOINLINE inline
+#define SMPC_HD inline
 #define SMPC_PAR(tid)                                                                                                  \
   for (int tid = 0; tid < SMPC_EMUL_NT; ++tid)                                                                         \
   {                                                                                                                    \

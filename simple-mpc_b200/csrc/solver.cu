@@ -16,6 +16,7 @@
 #include "riccati.cuh"
 #include "riccati2.cuh"
 #include "riccati3.cuh"
+#include "mpc_driver.cuh"
 #include "host_build.h"
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -65,7 +66,13 @@ namespace
     KnotScalars *sc, *sct;
     double *xdot, *xdott;
     InstState * inst;
-    int * counters; // [0] linesearch pending, [1] instances that need another round
+    int * counters; // [0] linesearch pending, [1] instances that need another round, [2] driver queue overflows
+    // batched MPC driver (mpc_driver.cuh); null until smpc_mpc_setup
+    MpcShared * mpcS;
+    MpcInst * mpcI;
+    int * mpc_ids;  // [B] stage-table index of the tail each instance appends this tick
+    double * xmeas; // [B][nq + nv] measured multibody states
+    int nxm, ncycle;
   };
 
   __device__ __forceinline__ const smpc_slot & slot_at(const Arrays & A, const InstState & st, int b, int t)
@@ -539,6 +546,55 @@ namespace
     for (int k = threadIdx.x; k < d.nk * 12; k += blockDim.x)
       sl.foot_ref[k / 12][k % 12] = src[((size_t)blockIdx.x * d.nk) * 12 + k];
   }
+
+  // ---- batched MPC driver (mpc_driver.cuh) ----
+  __global__ void k_mpc_init(Arrays A)
+  {
+    __shared__ MpcScratch s;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0)
+    {
+      MpcInst & I = A.mpcI[b];
+      mpc_init_instance(*A.model, A.model->d.q_ref, b == 0 ? A.mpcS : nullptr, I, s);
+    }
+  }
+  // recedeWithCycle: one thread per instance picks the new tail and updates the take-off / landing queues
+  __global__ void k_mpc_recede(Arrays A)
+  {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const Dims & d = A.dm;
+    if (b >= d.B)
+      return;
+    MpcInst & I = A.mpcI[b];
+    const unsigned tail_mask = slot_at(A, A.inst[b], b, d.N - 1).contact_mask;
+    const int before = I.overflow;
+    A.mpc_ids[b] = mpc_recede(*A.mpcS, I, A.table, A.ncycle, d.nk, d.N, tail_mask);
+    if (I.overflow && !before)
+      atomicAdd(A.counters + 2, 1);
+  }
+  // updateInternalData + updateStepTrackerReferences + getProblemState: one CTA per instance
+  __global__ void __launch_bounds__(64) k_mpc_refs(Arrays A)
+  {
+    __shared__ MpcScratch s;
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    MpcRing ring;
+    ring.base = A.slots + (size_t)b * d.N;
+    ring.head = A.inst[b].head;
+    ring.N = d.N;
+    mpc_refs(*A.model, *A.ocp, *A.mpcS, A.mpcI[b], A.xmeas + (size_t)b * A.nxm, ring, A.term[b], A.x0 + (size_t)b * d.nx, s);
+  }
+  // ring -> horizon order (getters)
+  __global__ void k_load_slots(Arrays A, int first, smpc_slot * dst)
+  {
+    const Dims & d = A.dm;
+    const int bi = blockIdx.x / d.N, t = blockIdx.x % d.N;
+    const int b = first + bi;
+    const int * s = reinterpret_cast<const int *>(&slot_at(A, A.inst[b], b, t));
+    int * o = reinterpret_cast<int *>(dst + blockIdx.x);
+    for (int k = threadIdx.x; k < (int)(sizeof(smpc_slot) / sizeof(int)); k += blockDim.x)
+      o[k] = s[k];
+  }
   // gather rows of a strided device array into a dense staging buffer: dst[r][0..w) = src[r*stride + off .. + w)
   __global__ void k_pack(const double * src, double * dst, size_t rows, int w, size_t stride, int off)
   {
@@ -579,6 +635,9 @@ struct smpc_ctx
   void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
   void (*launch_riccati)(smpc_ctx *) = nullptr;
   const char * riccati_variant = "generic";
+  std::vector<smpc_slot> h_table; // host copy of the stage table (contact masks drive the driver's bookkeeping)
+  MpcShared h_mpc;
+  bool mpc_ready = false;
 };
 
 #define CU(call)                                                                                                       \
