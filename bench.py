@@ -7,8 +7,12 @@ instances PER GPU (weak scaling; ranks never exchange data on the data path), T 
 (max_iters = 1, reference src/mpc.cpp:91,212). One "step" = one MPC tick of every instance.
 Robot: synthetic go2-like quadruped (example-robot-data is not available here; tests/smpc_ctypes.py).
 
-  value : ticks with every input already in HBM (stage ids are the only host input, 4 B/instance);
-          x0 of tick k+1 is the predicted xs[1] of tick k, copied device-to-device.
+One tick = smpc_mpc_iterate = MPC::iterate (reference src/mpc.cpp:189-218) for every instance: forward kinematics of the
+measured state, recedeWithCycle, updateStepTrackerReferences (Raibert foothold + Bezier swing references for all T
+stages), warm-start shift, one ProxDDP iteration.
+
+  value : ticks with every input already in HBM; the measured state of tick k+1 is the predicted xs[1] of tick k,
+          copied device-to-device.
   e2e   : the same tick through the C ABI with HOST buffers: measured states copied H2D from pinned memory,
           (x1, u0, u1, K0) copied D2H every step, next measured state formed on the host.
   roofline : Riccati backward kernel (the dominant kernel), algorithmic bytes of SURVEY.md §8d per launch.
@@ -83,14 +87,23 @@ def setup_backend(lib, prefix, sc, batch, device=0):
     opts = SolverOpts()
     getattr(lib, prefix + "_default_solver_opts")(C.byref(opts))
     b = pu.Backend(lib, prefix, sc.model, sc.ocpb, opts, batch, device)
-    table = (Slot * 80)(*[sc.gait_slot(k) for k in range(80)])
-    rc = getattr(lib, prefix + "_upload_stage_table")(b.ctx, table, 80)
+    table, n = sc.stage_table()  # 80 cycle stages + the standing stage
+    rc = getattr(lib, prefix + "_upload_stage_table")(b.ctx, table, n + 1)
     assert rc == 0
     b.set_slots(sc.initial_slots())
     b.set_terminal(sc.terminals())
     b.set_warmstart(*sc.warmstart())
     # constructor solve at the reference state, <= 100 iterations (reference src/mpc.cpp:17,85)
     b.solve(np.tile(sc.xref, (batch, 1)), 100)
+    if prefix == "smpc":
+        # batched device-side driver: per-instance gait phase, commanded base velocity
+        from smpc_ctypes import MpcSettings
+        st = MpcSettings(T_fly=30, T_contact=10, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
+        ph = (C.c_int * batch)(*[int(p) for p in sc.phase])
+        xref = np.array(sc.xref, float)
+        assert lib.smpc_mpc_setup(b.ctx, C.byref(st), ph, pu.P(xref)) == 0, lib.smpc_last_error()
+        vb = np.ascontiguousarray(sc.vbase)
+        assert lib.smpc_mpc_set_velocity_base(b.ctx, 0, batch, pu.P(vb)) == 0, lib.smpc_last_error()
     return b
 
 
@@ -150,7 +163,7 @@ def main():
     config = {"workload": "go2-like (synthetic) kinodynamics MPC tick, %d instances/GPU, T=50, trot 10/30/10/30, max_iters=1" % args.batch,
               "batch_per_gpu": args.batch, "horizon": 50, "nx": 37, "ndx": 36, "nu": 24,
               "l2": "per-tick working set (LQ knots + gains, ~4 MB/instance) exceeds the 126 MB L2 for batch >= 64",
-              "foot_refs": "stage-table references; per-tick swing-trajectory regeneration lives in the host MPC class, outside this timed region",
+              "foot_refs": "regenerated on the device every tick for every instance (Raibert foothold + degree-8 Bezier, all T stages), inside the timed region",
               "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world}
 
     if args.impl == "reference":
@@ -164,7 +177,7 @@ def main():
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config,
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                             "sample": "%d instances x %d ticks, OpenMP over instances; CPU restatement (oracle/), not Aligator" % (r["n_inst"], r["ticks"])},
+                             "sample": "%d instances x %d ticks, OpenMP over instances, solve only (stage-table references, no per-tick reference regeneration); CPU restatement (oracle/), not Aligator" % (r["n_inst"], r["ticks"])},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -197,19 +210,15 @@ def main():
 
     def tick_e2e(tick):
         x_pinned.numpy()[:] = x
-        cycle_ids(cu, "smpc", b, sc, tick)
-        b.shift()
-        rc = cu.smpc_solve(b.ctx, C.c_void_p(x_pinned.data_ptr()), 1)
+        rc = cu.smpc_mpc_iterate(b.ctx, C.c_void_p(x_pinned.data_ptr()), 1)
         assert rc == 0, cu.smpc_last_error()
         rc = cu.smpc_get_head(b.ctx, 0, B, *[C.c_void_p(h.data_ptr()) for h in head])
         assert rc == 0, cu.smpc_last_error()
         return head[0].numpy() + 0.0
 
     def tick_dev(tick):
-        cycle_ids(cu, "smpc", b, sc, tick)
-        b.shift()
-        cu.smpc_x0_from_prediction(b.ctx)
-        rc = cu.smpc_solve(b.ctx, None, 1)
+        cu.smpc_mpc_xmeas_from_prediction(b.ctx)
+        rc = cu.smpc_mpc_iterate(b.ctx, None, 1)
         assert rc == 0, cu.smpc_last_error()
 
     tick = 0
@@ -276,7 +285,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (sc.nx * 8 + 4),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * sc.nx * 8,
                 "d2h_bytes_per_step": B * 8 * (sc.nx + 2 * sc.nu + sc.nu * sc.ndx), "ms_per_step": 1e3 * e2e_s / K},
         "gpu_launches": int(l1 - l0),
         "clocks": sampler.summary(),
@@ -298,9 +307,8 @@ def main():
         lat = []
         for k in range(220):
             t1 = time.perf_counter()
-            cycle_ids(cu, "smpc", b1, sc1, k)
-            b1.shift()
-            b1.solve(x1, 1)
+            x1 = np.ascontiguousarray(x1)
+            assert cu.smpc_mpc_iterate(b1.ctx, pu.P(x1), 1) == 0
             x1 = b1.head()[0]
             lat.append(time.perf_counter() - t1)
         lat = np.array(lat[20:]) * 1e3
@@ -310,7 +318,7 @@ def main():
         cores = os.cpu_count() or 1
         r = run_cpu(args, 2 * cores, 6, 2)
         out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                               "sample": "%d instances x %d ticks, OpenMP over instances; CPU restatement (oracle/), not Aligator" % (r["n_inst"], r["ticks"]),
+                               "sample": "%d instances x %d ticks, OpenMP over instances, solve only (stage-table references, no per-tick reference regeneration); CPU restatement (oracle/), not Aligator" % (r["n_inst"], r["ticks"]),
                                "ms_per_instance_tick": 1e3 * r["wall"] * r["cores"] / (r["n_inst"] * r["ticks"])}
     b.close()
     if rank == 0:

@@ -244,6 +244,42 @@ int smpc_get_xdot(smpc_ctx *, int first, int n_inst, int t, double * xdot);
 /* replaces: MPC::getContactForces(t)                      (reference src/mpc.cpp:354-380) */
 int smpc_get_contact_forces(smpc_ctx *, int first, int n_inst, int t, double * forces);
 
+/* ---- batched MPC driver: the part of MPC::iterate around run(), per instance, on the device ----------
+ * (SURVEY.md §8a rows a1, a2, a13, a15). With thousands of instances the reference's host loop
+ * (recedeWithCycle + updateStepTrackerReferences: O(T nk) setter calls per instance, reference
+ * src/mpc.cpp:220-324) and the [B][T][nk][3] reference upload would dominate the tick, so each instance
+ * keeps its gait bookkeeping and swing-curve end points in HBM and one launch regenerates all references. */
+typedef struct smpc_mpc_settings
+{
+  int32_t T_fly, T_contact;    /* MPCSettings (reference include/simple-mpc/mpc.hpp:36-58) */
+  double swing_apex, timestep;
+  int32_t ncycle;      /* stage-table entries [0, ncycle) are cycle_horizon_ (reference src/mpc.cpp:101-187) */
+  int32_t standing_id; /* stage-table index of the standing stage (standing_horizon_), -1 if none */
+} smpc_mpc_settings;
+
+/* replaces: the MPC constructor's driver state + generateCycleHorizon's timing tables
+ * (reference src/mpc.cpp:19-41,93-98,112-132). Needs smpc_upload_stage_table first.
+ * phase[i] (NULL = all 0): instance i starts its cycle at table entry phase[i], i.e. behaves like a reference MPC
+ * whose generateCycleHorizon was given the gait rotated left by phase[i].
+ * x_reference [nx]: MPC::x_reference_ (problem state size). Instances start WALKING with zero base velocity. */
+int smpc_mpc_setup(smpc_ctx *, const smpc_mpc_settings *, const int * phase, const double * x_reference);
+/* replaces: mpc.velocity_base = v / switchToWalk(v)     (reference src/mpc.cpp:382-386); vb [n_inst][6] */
+int smpc_mpc_set_velocity_base(smpc_ctx *, int first, int n_inst, const double * vb);
+/* replaces: switchToWalk / switchToStand                (reference src/mpc.cpp:382-392); standing zeroes velocity_base */
+int smpc_mpc_set_walking(smpc_ctx *, int first, int n_inst, int walking);
+/* replaces: MPC::iterate(x)                             (reference src/mpc.cpp:189-218)
+ * x_meas [batch][nq+nv] measured multibody states (NULL: keep the states already on the device).
+ * updateInternalData -> recedeWithCycle -> updateStepTrackerReferences -> warm-start shift -> run(max_iters). */
+int smpc_mpc_iterate(smpc_ctx *, const double * x_meas, int max_iters);
+/* closed loop without a plant (multibody problem states only): x_meas <- predicted xs[1], device to device */
+int smpc_mpc_xmeas_from_prediction(smpc_ctx *);
+/* replaces: getFootTakeoffCycle / getFootLandCycle      (reference include/simple-mpc/mpc.hpp:141-164)
+ * takeoff, land [n_inst][nfeet]: first pending event or -1. */
+int smpc_mpc_get_timings(smpc_ctx *, int first, int n_inst, int * takeoff, int * land);
+/* replaces: getReferencePose / getReferenceState / getVelocityBase / getContactState read-backs
+ * (reference src/mpc.cpp:326-344): slots [n_inst][T] in horizon order; term may be NULL */
+int smpc_get_slots(smpc_ctx *, int first, int n_inst, smpc_slot * slots, smpc_terminal * term);
+
 /* device-side timing of the last smpc_solve (CUDA events on the context's stream), ms */
 int smpc_last_solve_ms(smpc_ctx *, float * total_ms, float * riccati_ms);
 /* number of kernel launches issued by this context so far */

@@ -81,6 +81,31 @@ namespace smpc
     }
   }
 
+  // generateCycleHorizon's timing tables (reference src/mpc.cpp:112-132) for a cycle that starts at table entry
+  // `phase`: masks[k] is the contact mask of table entry k, the cycle seen by this instance is masks[(phase+i) % ncycle].
+  SMPC_HD void mpc_init_queues(const unsigned * masks, int ncycle, int nk, int T, int phase, MpcInst & I)
+  {
+    for (int f = 0; f < nk; f++)
+    {
+      I.nland[f] = I.ntake[f] = 0;
+      for (int i = 1; i < ncycle; i++)
+      {
+        const bool now = (masks[(phase + i) % ncycle] >> f) & 1u, before = (masks[(phase + i - 1) % ncycle] >> f) & 1u;
+        if (!now && before)
+          mpc_queue_push(I.take[f], I.ntake[f], i + T, I.overflow);
+        if (now && !before)
+          mpc_queue_push(I.land[f], I.nland[f], i + T, I.overflow);
+      }
+      // wrap-around switch between the last and the first slot of the cycle (reference src/mpc.cpp:126-131)
+      const bool back = (masks[(phase + ncycle - 1) % ncycle] >> f) & 1u, front = (masks[phase % ncycle] >> f) & 1u;
+      if (back && !front)
+        mpc_queue_push(I.take[f], I.ntake[f], ncycle - 1 + T, I.overflow);
+      if (!back && front)
+        mpc_queue_push(I.land[f], I.nland[f], ncycle - 1 + T, I.overflow);
+    }
+    I.cyc = phase % ncycle;
+  }
+
   // recedeWithCycle (reference src/mpc.cpp:220-254) for one instance, one thread.
   //   tail_mask : contact mask of the stage currently at horizon position T-1 (before the rotation)
   //   table     : the cycle horizon (reference generateCycleHorizon), ntable entries, + the standing stage

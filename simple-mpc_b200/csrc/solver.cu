@@ -550,12 +550,40 @@ namespace
   // ---- batched MPC driver (mpc_driver.cuh) ----
   __global__ void k_mpc_init(Arrays A)
   {
+    // every instance starts from the same reference configuration: instance 0 computes, the others copy
     __shared__ MpcScratch s;
-    const int b = blockIdx.x;
+    __shared__ double pose[SMPC_MAX_FEET][3];
     if (threadIdx.x == 0)
     {
-      MpcInst & I = A.mpcI[b];
-      mpc_init_instance(*A.model, A.model->d.q_ref, b == 0 ? A.mpcS : nullptr, I, s);
+      MpcInst tmp;
+      mpc_init_instance(*A.model, A.model->d.q_ref, blockIdx.x == 0 ? A.mpcS : nullptr, tmp, s);
+      for (int f = 0; f < A.dm.nk; f++)
+        for (int k = 0; k < 3; k++)
+          pose[f][k] = tmp.init_pose[f][k];
+    }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < A.dm.B)
+      for (int f = 0; f < A.dm.nk; f++)
+        for (int k = 0; k < 3; k++)
+          A.mpcI[b].init_pose[f][k] = A.mpcI[b].final_pose[f][k] = pose[f][k];
+  }
+  // velocity_base_ / now_ setters: vb == nullptr -> mode switch (walking 0: standing, zero velocity; 1: walking)
+  __global__ void k_mpc_set_vb(Arrays A, int first, int n, const double * vb, int walking)
+  {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+      return;
+    MpcInst & I = A.mpcI[first + i];
+    if (vb)
+      for (int k = 0; k < 6; k++)
+        I.velocity_base[k] = vb[i * 6 + k];
+    if (walking >= 0)
+    {
+      I.walking = walking;
+      if (!walking)
+        for (int k = 0; k < 6; k++)
+          I.velocity_base[k] = 0.0;
     }
   }
   // recedeWithCycle: one thread per instance picks the new tail and updates the take-off / landing queues
@@ -615,7 +643,7 @@ struct smpc_ctx
 {
   int device = 0;
   cudaStream_t stream = nullptr;
-  Arrays A;
+  Arrays A{};
   DevModel hmodel;
   DevOcp hocp;
   std::vector<void *> allocs;
@@ -1144,6 +1172,8 @@ int smpc_upload_stage_table(smpc_ctx * c, const smpc_slot * stages, int n)
   CU(cudaStreamSynchronize(c->stream));
   c->A.table = tbl;
   c->A.ntable = n;
+  c->h_table.assign(stages, stages + n);
+  c->mpc_ready = false; // the driver's timing tables refer to the previous stage table
   return SMPC_OK;
 }
 int smpc_cycle_ids(smpc_ctx * c, int first, int n, const int * ids)
@@ -1424,6 +1454,236 @@ int smpc_x0_from_prediction(smpc_ctx * c)
     cudaMemcpyDeviceToDevice, c->stream));
   return SMPC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// batched MPC driver (mpc_driver.cuh)
+// ------------------------------------------------------------------------------------------------
+int smpc_mpc_setup(smpc_ctx * c, const smpc_mpc_settings * s, const int * phase, const double * x_reference)
+{
+  if (!c || !s || !x_reference)
+  {
+    g_err = "smpc_mpc_setup: null argument";
+    return SMPC_ERR_INVALID;
+  }
+  if (c->h_table.empty())
+  {
+    g_err = "smpc_mpc_setup: no stage table uploaded";
+    return SMPC_ERR_STATE;
+  }
+  const Dims & d = c->A.dm;
+  const int ntable = (int)c->h_table.size();
+  if (s->ncycle < 2 || s->ncycle > ntable || s->standing_id >= ntable || s->T_fly < 1 || s->T_contact < 0)
+  {
+    g_err = "smpc_mpc_setup: ncycle / standing_id outside the stage table, or bad T_fly / T_contact";
+    return SMPC_ERR_INVALID;
+  }
+  if (s->ncycle < d.N)
+  {
+    g_err = "smpc_mpc_setup: the cycle must be at least as long as the horizon (tile it as generateCycleHorizon does)";
+    return SMPC_ERR_INVALID;
+  }
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if (!c->A.mpcS)
+  {
+    if ((rc = dev_alloc(c, &c->A.mpcS, 1)) != SMPC_OK || (rc = dev_alloc(c, &c->A.mpcI, (size_t)d.B)) != SMPC_OK
+        || (rc = dev_alloc(c, &c->A.mpc_ids, (size_t)d.B)) != SMPC_OK
+        || (rc = dev_alloc(c, &c->A.xmeas, (size_t)d.B * (c->hmodel.d.nq + c->hmodel.d.nv))) != SMPC_OK)
+      return rc;
+  }
+  c->A.nxm = c->hmodel.d.nq + c->hmodel.d.nv;
+  c->A.ncycle = s->ncycle;
+  MpcShared & S = c->h_mpc;
+  memset(&S, 0, sizeof(S));
+  S.T_fly = s->T_fly;
+  S.T_contact = s->T_contact;
+  S.swing_apex = s->swing_apex;
+  S.timestep = s->timestep;
+  S.standing_id = s->standing_id;
+  std::vector<unsigned> masks((size_t)s->ncycle);
+  for (int k = 0; k < s->ncycle; k++)
+    masks[(size_t)k] = c->h_table[(size_t)k].contact_mask;
+  // one MpcInst per distinct phase, then replicated
+  std::vector<MpcInst> per_phase((size_t)s->ncycle);
+  std::vector<char> have((size_t)s->ncycle, 0);
+  std::vector<MpcInst> h((size_t)d.B);
+  for (int b = 0; b < d.B; b++)
+  {
+    const int p = phase ? phase[b] : 0;
+    if (p < 0 || p >= s->ncycle)
+    {
+      g_err = "smpc_mpc_setup: phase outside [0, ncycle)";
+      return SMPC_ERR_INVALID;
+    }
+    if (!have[(size_t)p])
+    {
+      MpcInst & I = per_phase[(size_t)p];
+      memset(&I, 0, sizeof(I));
+      mpc_init_queues(masks.data(), s->ncycle, d.nk, d.N, p, I);
+      if (I.overflow)
+      {
+        g_err = "smpc_mpc_setup: more than SMPC_MPC_QUEUE contact switches of one foot in the cycle";
+        return SMPC_ERR_UNSUPPORTED;
+      }
+      I.walking = 1;
+      for (int k = 0; k < d.nx; k++)
+        I.x_reference[k] = x_reference[k];
+      have[(size_t)p] = 1;
+    }
+    h[(size_t)b] = per_phase[(size_t)p];
+  }
+  CU(cudaMemcpyAsync(c->A.mpcS, &S, sizeof(S), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->A.mpcI, h.data(), h.size() * sizeof(MpcInst), cudaMemcpyHostToDevice, c->stream));
+  // starting foot poses and com0 from the forward kinematics of the reference configuration
+  k_mpc_init<<<(d.B + 63) / 64, 64, 0, c->stream>>>(c->A);
+  c->launches++;
+  CU(cudaMemsetAsync(c->A.counters + 2, 0, sizeof(int), c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  c->mpc_ready = true;
+  return SMPC_OK;
+}
+
+static int mpc_check(smpc_ctx * c, int first, int n, const char * what)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (!c->mpc_ready)
+  {
+    g_err = std::string(what) + ": smpc_mpc_setup has not been called";
+    return SMPC_ERR_STATE;
+  }
+  return SMPC_OK;
+}
+
+int smpc_mpc_set_velocity_base(smpc_ctx * c, int first, int n, const double * vb)
+{
+  int rc = mpc_check(c, first, n, "smpc_mpc_set_velocity_base");
+  if (rc != SMPC_OK)
+    return rc;
+  if (!vb)
+  {
+    g_err = "smpc_mpc_set_velocity_base: null argument";
+    return SMPC_ERR_INVALID;
+  }
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  if ((rc = ensure_staging(c, (size_t)n * 6 * sizeof(double))) != SMPC_OK)
+    return rc;
+  CU(cudaMemcpyAsync(c->staging, vb, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_mpc_set_vb<<<(n + 127) / 128, 128, 0, c->stream>>>(c->A, first, n, (const double *)c->staging, -1);
+  c->launches++;
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
+int smpc_mpc_set_walking(smpc_ctx * c, int first, int n, int walking)
+{
+  int rc = mpc_check(c, first, n, "smpc_mpc_set_walking");
+  if (rc != SMPC_OK)
+    return rc;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  k_mpc_set_vb<<<(n + 127) / 128, 128, 0, c->stream>>>(c->A, first, n, nullptr, walking ? 1 : 0);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SMPC_OK;
+}
+
+int smpc_mpc_iterate(smpc_ctx * c, const double * x_meas, int max_iters)
+{
+  int rc = mpc_check(c, 0, 0, "smpc_mpc_iterate");
+  if (rc != SMPC_OK)
+    return rc;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  cudaStream_t s = c->stream;
+  if (x_meas)
+    CU(cudaMemcpyAsync(c->A.xmeas, x_meas, (size_t)d.B * c->A.nxm * sizeof(double), cudaMemcpyHostToDevice, s));
+  k_mpc_recede<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
+  k_cycle<<<d.B, 64, 0, s>>>(c->A, 0, nullptr, c->A.mpc_ids);
+  k_mpc_refs<<<d.B, 64, 0, s>>>(c->A);
+  k_shift<<<d.B, 64, 0, s>>>(c->A, 0);
+  c->launches += 4;
+  CU(cudaMemcpyAsync(c->h_counters + 2, c->A.counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+  rc = smpc_solve(c, nullptr, max_iters); // synchronises the stream
+  if (rc != SMPC_OK)
+    return rc;
+  if (c->h_counters[2] != 0)
+  {
+    g_err = "smpc_mpc_iterate: a take-off / landing queue overflowed (more than SMPC_MPC_QUEUE pending events of one foot)";
+    return SMPC_ERR_UNSUPPORTED;
+  }
+  return SMPC_OK;
+}
+
+int smpc_mpc_xmeas_from_prediction(smpc_ctx * c)
+{
+  int rc = mpc_check(c, 0, 0, "smpc_mpc_xmeas_from_prediction");
+  if (rc != SMPC_OK)
+    return rc;
+  const Dims & d = c->A.dm;
+  if (d.nx != c->A.nxm)
+  {
+    g_err = "smpc_mpc_xmeas_from_prediction: the problem state is not the multibody state (centroidal OCP)";
+    return SMPC_ERR_UNSUPPORTED;
+  }
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy2DAsync(
+    c->A.xmeas, d.nx * sizeof(double), c->A.xs + d.nx, (size_t)(d.N + 1) * d.nx * sizeof(double), d.nx * sizeof(double), d.B,
+    cudaMemcpyDeviceToDevice, c->stream));
+  return SMPC_OK;
+}
+
+int smpc_mpc_get_timings(smpc_ctx * c, int first, int n, int * takeoff, int * land)
+{
+  int rc = mpc_check(c, first, n, "smpc_mpc_get_timings");
+  if (rc != SMPC_OK)
+    return rc;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  std::vector<MpcInst> h((size_t)n);
+  CU(cudaMemcpyAsync(h.data(), c->A.mpcI + first, (size_t)n * sizeof(MpcInst), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int nk = c->A.dm.nk;
+  for (int i = 0; i < n; i++)
+    for (int f = 0; f < nk; f++)
+    {
+      if (takeoff)
+        takeoff[i * nk + f] = h[(size_t)i].ntake[f] > 0 ? h[(size_t)i].take[f][0] : -1;
+      if (land)
+        land[i * nk + f] = h[(size_t)i].nland[f] > 0 ? h[(size_t)i].land[f][0] : -1;
+    }
+  return SMPC_OK;
+}
+
+int smpc_get_slots(smpc_ctx * c, int first, int n, smpc_slot * slots, smpc_terminal * term)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  if (slots)
+  {
+    const size_t bytes = (size_t)n * d.N * sizeof(smpc_slot);
+    int rc;
+    if ((rc = ensure_staging(c, bytes)) != SMPC_OK)
+      return rc;
+    k_load_slots<<<n * d.N, 64, 0, c->stream>>>(c->A, first, (smpc_slot *)c->staging);
+    c->launches++;
+    CU(cudaMemcpyAsync(slots, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (term)
+    CU(cudaMemcpyAsync(term, c->A.term + first, (size_t)n * sizeof(smpc_terminal), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
 // device timer on the context's stream: which = 0 start, 1 stop
 int smpc_timer_record(smpc_ctx * c, int which)
 {

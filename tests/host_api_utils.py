@@ -58,8 +58,9 @@ def go2_mpc_conf(mh):
 
 def go2_trot(names=("FL_foot", "FR_foot", "RL_foot", "RR_foot"), T_ds=10, T_ss=30):
     quad = {n: True for n in names}
-    p1 = dict(zip(names, [True, False, False, True]))
-    p2 = dict(zip(names, [False, True, True, False]))
+    # FL + RR lift first, then FR + RL (reference examples/go2_kinodynamics.py:117-139)
+    p1 = dict(zip(names, [False, True, True, False]))
+    p2 = dict(zip(names, [True, False, False, True]))
     return [quad] * T_ds + [p1] * T_ss + [quad] * T_ds + [p2] * T_ss
 
 

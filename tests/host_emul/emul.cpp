@@ -8,6 +8,7 @@
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati2.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
+#include "../../simple-mpc_b200/csrc/mpc_driver.cuh"
 #include "../../simple-mpc_b200/csrc/host_build.h"
 #include <memory>
 #include <vector>
@@ -274,5 +275,90 @@ int emul_riccati(
   riccati_backward_inst(L, SL, RS, N, knots, ncs, sol, mudyn, mueq, sm.data(), flag, P0.data());
   riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
   return 0;
+}
+
+// ---- batched MPC driver (mpc_driver.cuh) for ONE instance: the slot ring lives in host memory ----
+struct EmulMpc
+{
+  DevModel M;
+  DevOcp O;
+  MpcShared S;
+  MpcInst I;
+  MpcScratch scratch;
+  std::vector<smpc_slot> table, ring;
+  std::vector<double> x0;
+  smpc_terminal term;
+  int head, ncycle;
+};
+
+void * emul_mpc_create(
+  const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * table, int ntable, const smpc_mpc_settings * st,
+  int phase, const double * x_reference, const smpc_slot * initial_slots /*[T]*/, const smpc_terminal * term)
+{
+  auto * e = new EmulMpc();
+  build_dev_model(*model, e->M);
+  build_dev_ocp(*model, *ocp, e->O);
+  e->table.assign(table, table + ntable);
+  e->ring.assign(initial_slots, initial_slots + e->O.N);
+  e->term = *term;
+  e->head = 0;
+  e->ncycle = st->ncycle;
+  e->x0.assign((size_t)e->O.nx, 0.0);
+  memset(&e->S, 0, sizeof(e->S));
+  e->S.T_fly = st->T_fly;
+  e->S.T_contact = st->T_contact;
+  e->S.swing_apex = st->swing_apex;
+  e->S.timestep = st->timestep;
+  e->S.standing_id = st->standing_id;
+  memset(&e->I, 0, sizeof(e->I));
+  std::vector<unsigned> masks((size_t)st->ncycle);
+  for (int k = 0; k < st->ncycle; k++)
+    masks[(size_t)k] = table[k].contact_mask;
+  mpc_init_queues(masks.data(), st->ncycle, e->O.nk, e->O.N, phase, e->I);
+  e->I.walking = 1;
+  for (int k = 0; k < e->O.nx; k++)
+    e->I.x_reference[k] = x_reference[k];
+  mpc_init_instance(e->M, model->q_ref, &e->S, e->I, e->scratch);
+  return e;
+}
+void emul_mpc_destroy(void * h) { delete static_cast<EmulMpc *>(h); }
+void emul_mpc_set_velocity_base(void * h, const double * vb)
+{
+  for (int k = 0; k < 6; k++)
+    static_cast<EmulMpc *>(h)->I.velocity_base[k] = vb[k];
+}
+void emul_mpc_set_walking(void * h, int walking)
+{
+  auto * e = static_cast<EmulMpc *>(h);
+  e->I.walking = walking;
+  if (!walking)
+    for (int k = 0; k < 6; k++)
+      e->I.velocity_base[k] = 0.0;
+}
+// recede + cycle + references of one tick; outputs in horizon order
+int emul_mpc_tick(void * h, const double * xmeas, smpc_slot * slots_out, smpc_terminal * term_out, double * x0_out, int * takeoff, int * land)
+{
+  auto * e = static_cast<EmulMpc *>(h);
+  const int N = e->O.N, nk = e->O.nk;
+  const unsigned tail_mask = e->ring[(size_t)((e->head + N - 1) % N)].contact_mask;
+  const int id = mpc_recede(e->S, e->I, e->table.data(), e->ncycle, nk, N, tail_mask);
+  e->ring[(size_t)e->head] = e->table[(size_t)id];
+  e->head = (e->head + 1) % N;
+  MpcRing ring;
+  ring.base = e->ring.data();
+  ring.head = e->head;
+  ring.N = N;
+  mpc_refs(e->M, e->O, e->S, e->I, xmeas, ring, e->term, e->x0.data(), e->scratch);
+  for (int t = 0; t < N; t++)
+    slots_out[t] = ring.at(t);
+  *term_out = e->term;
+  for (int k = 0; k < e->O.nx; k++)
+    x0_out[k] = e->x0[(size_t)k];
+  for (int f = 0; f < nk; f++)
+  {
+    takeoff[f] = e->I.ntake[f] > 0 ? e->I.take[f][0] : -1;
+    land[f] = e->I.nland[f] > 0 ? e->I.land[f][0] : -1;
+  }
+  return e->I.overflow;
 }
 }

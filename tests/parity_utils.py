@@ -118,6 +118,17 @@ class Go2Scenario:
         self.phase = np.array([int(r.integers(0, 80)) for r in rngs])
         self.noise = [r for r in rngs]
         self.tick = 0
+        # commanded base velocity per instance: vx, vy, yaw rate; its own stream so that the state
+        # noise streams above are unchanged
+        vr = [np.random.default_rng([seed, first + i, 1]) for i in range(batch)]
+        self.vbase = np.zeros((batch, 6))
+        for i, r in enumerate(vr):
+            self.vbase[i, 0], self.vbase[i, 1], self.vbase[i, 5] = r.uniform(-0.3, 0.3), r.uniform(-0.1, 0.1), r.uniform(-0.3, 0.3)
+
+    def stage_table(self):
+        """cycle horizon (80 stages) + the standing stage, as MPC::generateCycleHorizon / standing_horizon_ build them"""
+        n = len(self.GAIT)
+        return (Slot * (n + 1))(*([self.gait_slot(k) for k in range(n)] + [self.gait_slot(0)])), n
 
     def gait_slot(self, k):
         mask = self.GAIT[k % 80]

@@ -75,6 +75,12 @@ class Terminal(C.Structure):
     _fields_ = [("x_ref", C.c_double * MAX_NX), ("com_ref", C.c_double * 3)]
 
 
+class MpcSettings(C.Structure):
+    """smpc_mpc_settings (include/smpc.h)"""
+    _fields_ = [("T_fly", C.c_int32), ("T_contact", C.c_int32), ("swing_apex", C.c_double), ("timestep", C.c_double),
+                ("ncycle", C.c_int32), ("standing_id", C.c_int32)]
+
+
 class SolveInfo(C.Structure):
     _fields_ = [
         ("num_iters", C.c_int32), ("al_iters", C.c_int32), ("conv", C.c_int32), ("ls_trials", C.c_int32),
@@ -94,6 +100,15 @@ def load_oracle():
         raise RuntimeError("oracle/liborc.so not built: run `make -C oracle` or __graft_entry__.build()")
     lib = C.CDLL(path)
     lib.orc_last_error.restype = C.c_char_p
+    return lib
+
+
+def load_emul():
+    path = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
+    if not os.path.exists(path):
+        raise RuntimeError("tests/host_emul/libemul.so not built: run __graft_entry__.build()")
+    lib = C.CDLL(path)
+    lib.emul_mpc_create.restype = C.c_void_p
     return lib
 
 

@@ -118,3 +118,63 @@ def test_host_api_mpc_cuda_vs_oracle_talos_centroidal():
         worst["us"] = max(worst["us"], pu.relerr(np.array(cu.us), np.array(orc.us)))
         worst["K"] = max(worst["K"], max(pu.relerr(cu.Ks[t], orc.Ks[t]) for t in range(100)))
     assert worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
+
+
+def test_batched_device_driver_vs_host_mpc_on_oracle():
+    """smpc_mpc_iterate (device-side recedeWithCycle + updateStepTrackerReferences + solve for a batch) against one host
+    `MPC` object per instance bound to the CPU oracle: different gait phases, base velocities and measured states per
+    instance; one instance is switched to standing. Per tick: take-off / landing cycles and contact states equal, foot /
+    state references <= 1e-12, xs / us <= TOL, K0 <= TOL_K, same iteration counts."""
+    import ctypes as C
+    import numpy as np
+    import host_api_utils as hu
+    from smpc_ctypes import Slot, Terminal, MpcSettings, SolverOpts, load_cuda
+    from test_mpc_driver_emul import host_mpc, compare_tick, FEET
+    cu = load_cuda()
+    B, phases = 3, [0, 37, 64]
+    vbs = np.array([[0.2, 0, 0, 0, 0, 0.1], [-0.1, 0.05, 0, 0, 0, 0], [0.3, -0.1, 0, 0, 0, -0.2]])
+    hosts = [host_mpc(p) for p in phases]
+    for (mh, ocp, mpc), vb in zip(hosts, vbs):
+        mpc.switchToWalk(vb)
+    sc = pu.Go2Scenario(B, seed=5)
+    opts = SolverOpts()
+    cu.smpc_default_solver_opts(C.byref(opts))
+    b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, B)
+    n = len(sc.GAIT)
+    table = (Slot * (n + 1))(*([sc.gait_slot(k) for k in range(n)] + [sc.gait_slot(0)]))
+    assert cu.smpc_upload_stage_table(b.ctx, table, n + 1) == 0
+    b.set_slots(sc.initial_slots())
+    b.set_terminal(sc.terminals())
+    b.set_warmstart(*sc.warmstart())
+    b.solve(np.tile(sc.xref, (B, 1)), 100)  # the MPC constructor's solve
+    st = MpcSettings(T_fly=30, T_contact=10, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
+    ph = (C.c_int * B)(*phases)
+    xref = np.array(sc.xref, float)
+    assert cu.smpc_mpc_setup(b.ctx, C.byref(st), ph, pu.P(xref)) == 0, cu.smpc_last_error()
+    assert cu.smpc_mpc_set_velocity_base(b.ctx, 0, B, pu.P(vbs)) == 0
+    x = sc.x_start()
+    worst = dict(refs=0.0, xs=0.0, us=0.0, K=0.0)
+    for k in range(45):
+        if k == 20:
+            hosts[1][2].switchToStand()
+            assert cu.smpc_mpc_set_walking(b.ctx, 1, 1, 0) == 0
+        xm = np.ascontiguousarray(x)
+        assert cu.smpc_mpc_iterate(b.ctx, pu.P(xm), 1) == 0, cu.smpc_last_error()
+        slots = (Slot * (B * 50))()
+        assert cu.smpc_get_slots(b.ctx, 0, B, slots, None) == 0
+        take, land = (C.c_int * (4 * B))(), (C.c_int * (4 * B))()
+        assert cu.smpc_mpc_get_timings(b.ctx, 0, B, take, land) == 0
+        xs, us, Ks, _ = b.results()
+        infos = b.info()
+        for i, (mh, ocp, mpc) in enumerate(hosts):
+            mpc.iterate(x[i])
+            worst["refs"] = max(worst["refs"], compare_tick(mpc, ocp, slots[i * 50:(i + 1) * 50], list(take)[4 * i:4 * i + 4],
+                                                            list(land)[4 * i:4 * i + 4]))
+            worst["xs"] = max(worst["xs"], pu.relerr(xs[i], np.array(mpc.xs)))
+            worst["us"] = max(worst["us"], pu.relerr(us[i], np.array(mpc.us)))
+            worst["K"] = max(worst["K"], pu.relerr(Ks[i, 0], mpc.Ks[0]))
+            assert infos[i].num_iters == mpc.solver.results.num_iters
+            x[i] = np.array(mpc.xs[1])
+        x = sc.disturb(x, k + 1)
+    b.close()
+    assert worst["refs"] <= 1e-12 and worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst

@@ -140,27 +140,27 @@ def test_foot_timings_match_reference_known_answers():
 
 def test_go2_kinodynamics_mpc_walks_on_the_oracle():
     """reference examples/go2_kinodynamics.py as a closed loop without a simulator: x <- xs[1]. Checks the driver
-    (gait timings 60/100/90/129, swing references lift the feet by the apex, contact states enter the horizon)."""
+    (gait timings 60/100/90/129 of SURVEY.md appendix D, swing references lift the feet by the apex, contact states enter the horizon)."""
     hooks = hu.import_hooks()
     mh = hu.go2_handler(sm)
     ocp, _ = hu.go2_kino_problem(sm, mh, T=50)
     mpc = hooks.make_oracle_mpc(hu.go2_mpc_conf(mh), ocp, hu.LIBORC)
     assert mpc.solver.results.prim_infeas < 1e-3  # the constructor solve (<= 100 iterations) converged
     mpc.generateCycleHorizon(hu.go2_trot())
-    assert [mpc.getFootTakeoffCycle(n) for n in mh.getFeetFrameNames()] == [100, 60, 60, 100]
-    assert [mpc.getFootLandCycle(n) for n in mh.getFeetFrameNames()] == [129, 90, 90, 129]
+    assert [mpc.getFootTakeoffCycle(n) for n in mh.getFeetFrameNames()] == [60, 100, 100, 60]
+    assert [mpc.getFootLandCycle(n) for n in mh.getFeetFrameNames()] == [90, 129, 129, 90]
     mpc.switchToWalk(np.array([0.2, 0, 0, 0, 0, 0]))
     x = mh.getReferenceState()
     zmax = 0.0
     for k in range(25):
         mpc.iterate(x)
         x = mpc.xs[1]
-        zmax = max(zmax, max(mpc.getReferencePose(t, "FR_foot").translation[2] for t in range(50)))
+        zmax = max(zmax, max(mpc.getReferencePose(t, "FL_foot").translation[2] for t in range(50)))
     assert len(mpc.xs) == 51 and len(mpc.us) == 50 and mpc.Ks[0].shape == (24, 36)
-    assert mpc.getFootTakeoffCycle("FR_foot") == 35 and mpc.getFootLandCycle("FR_foot") == 65
-    # after 25 ticks the first swing of FR/RL (cycle slots 10..39) occupies horizon stages 35..49
-    assert ocp.getContactState(34) == [True] * 4 and ocp.getContactState(36) == [True, False, False, True]
-    foot_z = sm.RobotDataHandler(mh).getFootPose(1).translation[2]
+    assert mpc.getFootTakeoffCycle("FL_foot") == 35 and mpc.getFootLandCycle("FL_foot") == 65
+    # after 25 ticks the first swing of FL/RR (cycle slots 10..39) occupies horizon stages 35..49
+    assert ocp.getContactState(34) == [True] * 4 and ocp.getContactState(36) == [False, True, True, False]
+    foot_z = sm.RobotDataHandler(mh).getFootPose(0).translation[2]
     assert zmax > foot_z + 0.03  # the swing reference lifts the foot (peak of the degree-8 Bezier: 0.273 x apex)
     assert mpc.getStateDerivative(0).shape == (36,)
     assert np.isfinite(np.array(mpc.us)).all()
