@@ -53,28 +53,53 @@ namespace smpc
   {
     static constexpr int NJ = Cfg::NJ, NV = Cfg::NV, NK = Cfg::NK, NX = Cfg::NX, NU = Cfg::NU, NDX = Cfg::NDX;
     double x[NX], u[NU > 0 ? NU : 1], xn_ws[NX];
-    double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6], bias[NJ][6];
-    double Yb[NJ][10], hb[NJ][6]; // own-body inertia / momentum
+    double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6];
+    // Shared memory bounds the resident knots per SM (one warp per knot, profiles/r01e): arrays whose lifetimes do not
+    // overlap share storage. Group 1 is dead once A, B are written (bias: kino_accel_pass; rhs, dhd_*: the implicit
+    // differentiation); group 2 is first written after that (weighted Jacobians, weighted residuals).
+    union
+    {
+      struct
+      {
+        double bias[NJ][6];
+        double rhs[6][Cfg::NRHS];
+        double dhd_dq[6][NV], dhd_dv[6][NV];
+      };
+      struct
+      {
+        double WJc[6][NDX], Wch[6], Wcdh[6], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][3][NV], Wfr[NK][3];
+      };
+    };
+    // own-body inertia / momentum (kinematics and acceleration passes only) share storage with the constraint-row
+    // values, which are first written after the last acceleration pass
+    union
+    {
+      struct
+      {
+        double Yb[NJ][10], hb[NJ][6];
+      };
+      struct
+      {
+        double cval[Cfg::NCMAX], dproj[Cfg::NCMAX], vplus[Cfg::NCMAX], rpinf[Cfg::NCMAX], rcrit[Cfg::NCMAX];
+      };
+    };
     double Y[NJ][10], hs[NJ][6], dIo[NJ][6], fs[NJ][6]; // subtree sums
     double J[6][NV];
     double fR[NK][9], fp[NK][3], lever[NK][3], vf[NK][6];
     double com[3], vcom[3], h0[6], hd0[6], hg[6], hdg[6], hdF[6];
-    double Ag[6][NV], dh_dq[6][NV], dhd_dq[6][NV], dhd_dv[6][NV];
+    double Ag[6][NV], dh_dq[6][NV];
     double Jp[NK][3][NV];
     double vf_dq[NK][Cfg::VR][NV], vf_dv[NK][Cfg::VR][NV];
     double dhF_dq[3][NV], dhF_du[6][Cfg::NF];
     double acc[NV];
     double lu[36];
     int piv[6];
-    double rhs[6][Cfg::NRHS];
     double Jq6[36], Jv6[36], Jl6[36];
     double rs[NDX], xnext[NX], e[NDX], lplus[NDX];
-    double WJc[6][NDX], Wch[6], Wcdh[6], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][3][NV], Wfr[NK][3];
     double Lx[NDX], Lu[NU > 0 ? NU : 1], gx[NDX], gu[NU > 0 ? NU : 1];
     // constraint rows
     int nc;
     int rkind[Cfg::NCMAX], rarg[Cfg::NCMAX], rsub[Cfg::NCMAX];
-    double cval[Cfg::NCMAX], dproj[Cfg::NCMAX], vplus[Cfg::NCMAX], rpinf[Cfg::NCMAX], rcrit[Cfg::NCMAX];
     int ractive[Cfg::NCMAX];
     double costs[8 + NK];
   };

@@ -44,7 +44,7 @@ def main():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
         if m:
             nm = m.group(1)
-            ok = base in nm and targs.search(nm) is not None
+            ok = re.search(r"\d+%s[IE]" % base, nm) is not None and targs.search(nm) is not None
             want = ok
             continue
         if not want:
