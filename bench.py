@@ -116,6 +116,7 @@ def cycle_ids(lib, prefix, b, sc, tick):
 def run_cpu(args, n_inst, ticks, warm):
     """CPU restatement on the host cores: n_inst instances spread over OpenMP threads."""
     orc = load_oracle()
+    orc.orc_set_num_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1; the baseline uses every host core
     sc = pu.Go2Scenario(n_inst, seed=0)
     t0 = time.time()
     b = setup_backend(orc, "orc", sc, n_inst)

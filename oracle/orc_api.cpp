@@ -328,6 +328,16 @@ int orc_get_xdot(orc_ctx * c, int first, int n, int t, double * xdot)
   }
   return SMPC_OK;
 }
+// torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU-baseline leg of bench.py asks for the host cores explicitly
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0)
+    omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

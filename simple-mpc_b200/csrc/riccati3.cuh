@@ -16,8 +16,9 @@
 //   * every product that used strided one-output-per-thread loops (Sigma, G, Y + W G, P update) is register
 //     tiled or processes four outputs at a time, so no thread sits in one dependent FMA chain.
 //
-// Shared memory per CTA (doubles): KN knot copy · PP [NDX][NDX+1] = [p | P] · M (Cholesky of I + mu P, later
-// Sigma) · PAB = P~[A B] · YW [NU][NDX+1+NC] = [Y | W] · G [NC][NDX+1] · small vectors · the mbarrier.
+// Shared memory per CTA (doubles): KN knot copy · PP [NDX][NDX+1] = [p | P] · X = {M (Cholesky of I + mu P) | PAB =
+// P~[A B] | YW [NU][NDX+1+NC] = [Y | W]} time-shared · G [NC][NDX+1] and Sigma inside the dead A / B blocks of the
+// knot copy · small vectors · the mbarrier: 76.6 KB for (36, 24, 24), three CTAs per SM.
 #pragma once
 #include "par.cuh"
 #include "dev_types.h"
@@ -45,19 +46,38 @@ namespace smpc
     static constexpr int kD = kC + NC * NDX;
     static constexpr int kd = kD + NC * NU;
     static constexpr int KSIZE = (kd + NC + 1) & ~1;
-    // shared memory
+    // shared memory. Buffers whose lifetimes inside a stage do not overlap share storage, so that THREE CTAs fit one
+    // SM (profiles/r01e: the sweep is latency-bound on its serial pivot chains and scales with resident CTAs):
+    //   X  : M = chol(I + mu P) in steps 0-1 | rows [0, PR0) of PAB = P~[A B] in steps 2-3 | YW = [Y | W] in steps
+    //        4-5 | symmetrise scratch
+    //   the C D d block of the knot copy: rows [PR0, NDX) of PAB in steps 2-3; C D d arrive by a SECOND bulk copy
+    //        issued after step 3 and awaited after the factorisation of R^ (which hides it)
+    //   G  : in the A block of the knot copy (A, B, f are dead after step 3) when it fits, else its own buffer
+    //   Sg : Sigma, in the B block of the knot copy when G took the A block, else in the A block
     static constexpr int oKN = 0;
     static constexpr int oPP = oKN + KSIZE;
-    static constexpr int oM = (oPP + NDX * LDP + 1) & ~1;
-    static constexpr int szM = (NDX * NDX > NC * NC) ? NDX * NDX : NC * NC;
-    static constexpr int oPAB = oM + szM;
-    static constexpr int oYW = oPAB + NDX * NAB;
-    static constexpr int oG = (oYW + NU * NRY + 1) & ~1;
-    static constexpr int ow = (oG + NC * LDP + 1) & ~1;
-    static constexpr int oinvp = ow + NDX;
-    static constexpr int oinvr = oinvp + NDX;
+    static constexpr int oX = (oPP + NDX * LDP + 1) & ~1;
+    static constexpr int PR0 = 4 * ((2 * NDX / 3) / 4); // PAB rows kept in X
+    static constexpr int szYW = NU * NRY;
+    static constexpr int szX1 = (NDX * NDX > szYW) ? NDX * NDX : szYW;
+    static constexpr int szX0 = (PR0 * NAB > szX1) ? PR0 * NAB : szX1;
+    static constexpr int szX = (szX0 + 1) & ~1;
+    static constexpr int oM = oX, oPAB = oX, oYW = oX;
+    static constexpr int oPAB1 = oKN + kC; // PAB rows [PR0, NDX)
+    static_assert((NDX - PR0) * NAB <= KSIZE - kC, "the tail rows of PAB must fit the C D d block");
+    static_assert(PR0 % 4 == 0 && (NAB % 2) == 0, "tiles never straddle the PAB split; rows stay 16-byte aligned");
+    static constexpr bool G_IN_A = NC * LDP <= NDX * NDX;
+    static_assert(G_IN_A ? (NC * NC <= NDX * NU) : (NC * NC <= NDX * NDX), "Sigma must fit the dead A / B block of the knot");
+    static constexpr int oGown = oX + szX;
+    static constexpr int oG = G_IN_A ? (oKN + kA) : oGown;
+    static constexpr int oSg = G_IN_A ? (oKN + kB) : (oKN + kA);
+    static constexpr int ow = G_IN_A ? oGown : ((oGown + NC * LDP + 1) & ~1);
+    // the pivot reciprocals of I + mu P (steps 0-1) share storage with those of R^ and Sigma (steps 4-5)
+    static constexpr int oinvr = ow + NDX;
     static constexpr int oinvs = oinvr + NU;
-    static constexpr int ocol = oinvs + NC; // published pivot columns, double buffered
+    static constexpr int oinvp = oinvr;
+    static constexpr int szinv = (NU + NC > NDX) ? NU + NC : NDX;
+    static constexpr int ocol = oinvr + szinv; // published pivot columns, double buffered
     static constexpr int NMAX = (NDX > NC) ? (NDX > NU ? NDX : NU) : (NC > NU ? NC : NU);
     static constexpr int obar = (ocol + 2 * (NMAX + 2) + 1) & ~1; // 8-byte mbarrier
     static constexpr int oflag = obar + 2;
@@ -364,8 +384,10 @@ namespace smpc
     double * KN = sm + R::oKN;
     double * PP = sm + R::oPP; // [NDX][LDP]: col 0 = p, cols 1.. = P
     double * Mb = sm + R::oM;
-    double * PAB = sm + R::oPAB;
-    double * YW = sm + R::oYW;
+    double * PAB = sm + R::oPAB;   // rows [0, PR0)
+    double * PAB1 = sm + R::oPAB1; // rows [PR0, NDX)
+    constexpr int PR0 = R::PR0;
+    double * YW = sm + R::oYW; // Mb, PAB and YW are the same buffer at different times (see Ric3)
     double * G = sm + R::oG;
     double * w = sm + R::ow;
     double * invp = sm + R::oinvp;
@@ -385,7 +407,7 @@ namespace smpc
     const double * Ck = KN + R::kC;
     const double * Dk = KN + R::kD;
     const double * dk = KN + R::kd;
-    double * Sg = Mb;
+    double * Sg = sm + R::oSg;
     const double inv_mu = 1.0 / mueq;
     unsigned parity = 0;
 
@@ -436,7 +458,7 @@ namespace smpc
       SMPC_PAR(tid)
       {
         if (tid == 0)
-          bulk_load(KN, kn, R::KSIZE, bar);
+          bulk_load(KN, kn, R::kC, bar); // Q S R q r A B f; C D d follow after step 3
         if (mudyn > 0)
           for (int e = tid; e < NDX * NDX; e += SMPC_NT)
           {
@@ -473,6 +495,7 @@ namespace smpc
           const bool inA = tc < TCA;
           const double * src = inA ? Ak + 6 * tc : Bk + 6 * (tc - TCA);
           const int lds = inA ? NDX : NU;
+          double * pab_dst = (a0 < PR0) ? PAB + a0 * NAB : PAB1 + (a0 - PR0) * NAB;
           double c[TM][6];
 #pragma unroll
           for (int r = 0; r < TM; r++)
@@ -499,7 +522,7 @@ namespace smpc
           for (int r = 0; r < TM; r++)
 #pragma unroll
             for (int q = 0; q < 6; q++)
-              PAB[(a0 + r) * NAB + 6 * tc + q] = c[r][q];
+              pab_dst[r * NAB + 6 * tc + q] = c[r][q];
         }
         else if (tid - TR * TC < NDX)
         {
@@ -541,21 +564,28 @@ namespace smpc
 #pragma unroll
             for (int q = 0; q < 6; q++)
               c[r][q] = out[r * ldo + q];
-#pragma unroll 4
-          for (int k = 0; k < NDX; k++)
+          // rows [0, PR0) of PAB live in X, the rest in the C D d block of the knot copy: same k order, two loops
+#pragma unroll 1
+          for (int half = 0; half < 2; half++)
           {
-            double av[TM], bv[6];
+            const int k0 = half ? PR0 : 0, k1 = half ? NDX : PR0;
+            const double * pab = half ? PAB1 - PR0 * NAB : PAB;
+#pragma unroll 4
+            for (int k = k0; k < k1; k++)
+            {
+              double av[TM], bv[6];
 #pragma unroll
-            for (int r = 0; r < TM; r += 2)
-              ld2(lhs + k * ldl + r, av[r], av[r + 1]);
-            ld2(PAB + k * NAB + b0, bv[0], bv[1]);
-            ld2(PAB + k * NAB + b0 + 2, bv[2], bv[3]);
-            ld2(PAB + k * NAB + b0 + 4, bv[4], bv[5]);
+              for (int r = 0; r < TM; r += 2)
+                ld2(lhs + k * ldl + r, av[r], av[r + 1]);
+              ld2(pab + k * NAB + b0, bv[0], bv[1]);
+              ld2(pab + k * NAB + b0 + 2, bv[2], bv[3]);
+              ld2(pab + k * NAB + b0 + 4, bv[4], bv[5]);
 #pragma unroll
-            for (int r = 0; r < TM; r++)
+              for (int r = 0; r < TM; r++)
 #pragma unroll
-              for (int q = 0; q < 6; q++)
-                c[r][q] = fma(av[r], bv[q], c[r][q]);
+                for (int q = 0; q < 6; q++)
+                  c[r][q] = fma(av[r], bv[q], c[r][q]);
+            }
           }
 #pragma unroll
           for (int r = 0; r < TM; r++)
@@ -577,8 +607,14 @@ namespace smpc
       }
       SMPC_END
       // ---- 4. KKT by block LDL^T ----
+      // PAB is dead: fetch C D d into its tail rows' storage while R^ is factorised
+      SMPC_PAR(tid)
+      if (tid == 0)
+        bulk_load(KN + R::kC, kn + R::kC, R::KSIZE - R::kC, bar);
+      SMPC_END
       chol_reg<NU, NU, TPB>(Rh, colb, invr, bad);
       SMPC_PAR(tid)
+      bulk_wait(bar, parity);
       for (int e = tid; e < NU * NRY; e += SMPC_NT)
       {
         const int a = e / NRY, c = e % NRY;
@@ -592,6 +628,7 @@ namespace smpc
         YW[e] = v;
       }
       SMPC_END
+      parity ^= 1u;
       sweep_cols<NU, NU, NRY, NRY, true, false>(Rh, invr, YW);
       if (NC > 0)
       {

@@ -330,8 +330,15 @@ namespace
 #ifndef SMPC_RIC3_TPB
 #define SMPC_RIC3_TPB 128
 #endif
+  // resident CTAs per SM the shared-memory footprint allows (228 KB per SM, 1 KB reserved per CTA): the register
+  // budget follows it (3 CTAs x 128 threads -> 168 registers, no spills worth naming: ptxas reports 56 bytes)
   template <int NDX, int NU, int NC>
-  __global__ void __launch_bounds__(SMPC_RIC3_TPB, SMPC_RIC_MINB) k_riccati3(Arrays A)
+  constexpr int ric3_ctas_per_sm()
+  {
+    return (233472 / (Ric3<NDX, NU, NC>::SIZE * 8 + 1024 + 16) >= 3 && SMPC_RIC3_TPB == 128) ? 3 : SMPC_RIC_MINB;
+  }
+  template <int NDX, int NU, int NC>
+  __global__ void __launch_bounds__(SMPC_RIC3_TPB, (ric3_ctas_per_sm<NDX, NU, NC>())) k_riccati3(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
     const int b = blockIdx.x;
@@ -786,6 +793,7 @@ namespace
     }
     c->ric_smem = (size_t)R::SIZE * sizeof(double);
     CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC>;
     c->riccati_variant = "tma-staged";
     return SMPC_OK;
