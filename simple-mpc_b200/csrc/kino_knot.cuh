@@ -53,25 +53,30 @@ namespace smpc
   {
     static constexpr int NJ = Cfg::NJ, NV = Cfg::NV, NK = Cfg::NK, NX = Cfg::NX, NU = Cfg::NU, NDX = Cfg::NDX;
     double x[NX], u[NU > 0 ? NU : 1], xn_ws[NX];
-    double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6];
-    // Shared memory bounds the resident knots per SM (one warp per knot, profiles/r01e): arrays whose lifetimes do not
-    // overlap share storage. Group 1 is dead once A, B are written (bias: kino_accel_pass; rhs, dhd_*: the implicit
-    // differentiation); group 2 is first written after that (weighted Jacobians, weighted residuals).
+    // Shared memory bounds the resident knots per SM (one warp per knot; profiles/r01e, r01f: throughput follows the
+    // resident warps), so arrays whose lifetimes do not overlap share storage.
+    //   U1, three eras: (1) kinematics, acceleration passes and the per-dof derivative phase; (2) the right-hand sides
+    //   of the implicit differentiation, consumed by the A / B assembly; (3) weighted Jacobians and constraint rows.
     union
     {
       struct
       {
-        double bias[NJ][6];
-        double rhs[6][Cfg::NRHS];
-        double dhd_dq[6][NV], dhd_dv[6][NV];
+        double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6], bias[NJ][6];
+        double Y[NJ][10], hs[NJ][6], dIo[NJ][6], fs[NJ][6]; // subtree sums
+        double J[6][NV];
       };
       struct
       {
-        double WJc[6][NDX], Wch[6], Wcdh[6], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][3][NV], Wfr[NK][3];
+        double rhs[6][Cfg::NRHS];
+      };
+      struct
+      {
+        double WJc[6][NDX], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][3][NV];
+        double cval[Cfg::NCMAX], dproj[Cfg::NCMAX], vplus[Cfg::NCMAX], rpinf[Cfg::NCMAX], rcrit[Cfg::NCMAX];
       };
     };
-    // own-body inertia / momentum (kinematics and acceleration passes only) share storage with the constraint-row
-    // values, which are first written after the last acceleration pass
+    //   U2: own-body inertia / momentum (until the last acceleration pass) | d(hdot)/d(q, v) (per-dof phase until the
+    //   right-hand sides are built) | Lagrangian-gradient vectors (written by the A / B assembly and later)
     union
     {
       struct
@@ -80,11 +85,15 @@ namespace smpc
       };
       struct
       {
-        double cval[Cfg::NCMAX], dproj[Cfg::NCMAX], vplus[Cfg::NCMAX], rpinf[Cfg::NCMAX], rcrit[Cfg::NCMAX];
+        double dhd_dq[6][NV], dhd_dv[6][NV];
+      };
+      struct
+      {
+        double Lx[NDX], Lu[NU > 0 ? NU : 1], gx[NDX], gu[NU > 0 ? NU : 1];
       };
     };
-    double Y[NJ][10], hs[NJ][6], dIo[NJ][6], fs[NJ][6]; // subtree sums
-    double J[6][NV];
+    double Wch[6], Wcdh[6], Wfr[NK][3]; // weighted residuals (written while era-1 arrays are still read at the terminal node)
+    double mass;                          // Y[0][0], kept past era 1
     double fR[NK][9], fp[NK][3], lever[NK][3], vf[NK][6];
     double com[3], vcom[3], h0[6], hd0[6], hg[6], hdg[6], hdF[6];
     double Ag[6][NV], dh_dq[6][NV];
@@ -96,7 +105,6 @@ namespace smpc
     int piv[6];
     double Jq6[36], Jv6[36], Jl6[36];
     double rs[NDX], xnext[NX], e[NDX], lplus[NDX];
-    double Lx[NDX], Lu[NU > 0 ? NU : 1], gx[NDX], gu[NU > 0 ? NU : 1];
     // constraint rows
     int nc;
     int rkind[Cfg::NCMAX], rarg[Cfg::NCMAX], rsub[Cfg::NCMAX];
@@ -1310,6 +1318,7 @@ namespace smpc
         }
         s.costs[0] = 0.5 * c0 + 0.5 * c2;
         s.nc = nct;
+        s.mass = s.Y[0][0]; // the subtree sums are overwritten by the weighted Jacobians below
       }
       if (DERIVS && tid < NV)
       {
@@ -1370,7 +1379,7 @@ namespace smpc
     {
       SMPC_PAR(tid)
       {
-        const double mass = s.Y[0][0];
+        const double mass = s.mass;
         double * Q = io.knot + L.oQ;
         for (int e = tid; e < NDX * NDX; e += SMPC_NT)
         {

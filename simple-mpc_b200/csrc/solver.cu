@@ -157,9 +157,20 @@ namespace
     io.sc = (TRIAL ? A.sct : A.sc) + xb + t;
   }
 
-  // kinodynamics: one CTA (one warp by default) per knot
+  // kinodynamics: one warp per knot. The kernel is latency-bound and its throughput follows the resident warps per SM
+  // up to 8 (6 -> 8 warps: 1.33x, profiles/r01e vs r01f). A one-warp CTA lives on one SM sub-partition (16 K registers),
+  // so the steps are 2 warps per sub-partition (<= 255 registers), 3 (<= 168) and 4 (<= 128). Measured at B = 4096:
+  // 8 CTAs/SM at 254 registers 59.5 ms per tick; 10 CTAs/SM (shared-memory limit) at 168 registers 61.2 ms - the
+  // register cap costs more per warp than the extra warps return, so the default stays at 8.
+#ifndef SMPC_KNOT_MINB
+#define SMPC_KNOT_MINB 8
+#endif
   template <class Cfg, bool TRIAL>
-  __global__ void __launch_bounds__(128) k_knots(Arrays A)
+#ifdef SMPC_KNOT_MAXREG
+  __global__ void __maxnreg__(SMPC_KNOT_MAXREG) k_knots(Arrays A)
+#else
+  __global__ void __launch_bounds__(32, SMPC_KNOT_MINB) k_knots(Arrays A)
+#endif
   {
     extern __shared__ __align__(16) double smem_raw[];
     KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
@@ -703,11 +714,19 @@ namespace
   int setup_knots(smpc_ctx * c)
   {
     c->knot_smem = sizeof(KinoScratch<Cfg>);
-    if (const char * e = getenv("SMPC_KNOT_THREADS")) // tuning knob: 32, 64 or 128 threads per knot
-      c->knot_threads = atoi(e) == 64 ? 64 : (atoi(e) == 128 ? 128 : 32);
+    c->knot_threads = 32; // one warp per knot: phase barriers are warp syncs (64 / 128 threads measured slower, profiles/r01a)
     CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
     CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
+    CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->launch_knots = &launch_knots_impl<Cfg>;
+    if (getenv("SMPC_VERBOSE"))
+    {
+      int nl = 0, nt = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_knots<Cfg, false>, c->knot_threads, c->knot_smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt, k_knots<Cfg, true>, c->knot_threads, c->knot_smem);
+      fprintf(stderr, "smpc: k_knots %zu B shared memory per knot, resident CTAs per SM: lin %d, trial %d\n", c->knot_smem, nl, nt);
+    }
     return SMPC_OK;
   }
 
@@ -796,6 +815,12 @@ namespace
     CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC>;
     c->riccati_variant = "tma-staged";
+    if (getenv("SMPC_VERBOSE"))
+    {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC>, SMPC_RIC3_TPB, c->ric_smem);
+      fprintf(stderr, "smpc: k_riccati3 %zu B shared memory per instance, resident CTAs per SM: %d\n", c->ric_smem, nb);
+    }
     return SMPC_OK;
   }
 

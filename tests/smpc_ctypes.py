@@ -113,7 +113,8 @@ def load_emul():
 
 
 def load_cuda():
-    path = os.path.join(ROOT, "simple-mpc_b200", "libsmpc_cuda.so")
+    # SMPC_LIB: alternative build of the same library (kernel tuning experiments under gpurun)
+    path = os.environ.get("SMPC_LIB") or os.path.join(ROOT, "simple-mpc_b200", "libsmpc_cuda.so")
     if not os.path.exists(path):
         raise RuntimeError("simple-mpc_b200/libsmpc_cuda.so not built: run __graft_entry__.build()")
     lib = C.CDLL(path)

@@ -23,13 +23,16 @@ def main():
     isamp = hdr.index("# Samples")
     isrc = hdr.index("Source")
     iexec = hdr.index("Instructions Executed")
+    iwf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+    iwfi = hdr.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in hdr else None
     sass = []
     for r in rows[s0 + 2:]:
         if r and r[0] == "Kernel Name":
             break  # next launch
         if len(r) <= isamp or r[0] == "Address":
             continue
-        sass.append((r[isrc].strip(), int(r[isamp] or 0), int(r[iexec] or 0)))
+        sass.append((r[isrc].strip(), int(r[isamp] or 0), int(r[iexec] or 0), int(r[iwf] or 0) if iwf is not None else 0,
+                     int(r[iwfi] or 0) if iwfi is not None else 0))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
     cub = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -61,13 +64,17 @@ def main():
     per = collections.Counter()
     ex = collections.Counter()
     tot = 0
-    for (loc, _), (_, smp, ne) in zip(lines, sass):
+    wf = collections.Counter()
+    wfi = collections.Counter()
+    for (loc, _), (_, smp, ne, w, wi) in zip(lines, sass):
         per[loc] += smp
         ex[loc] += ne
+        wf[loc] += w
+        wfi[loc] += wi
         tot += smp
     print("kernel:", kname, " total samples:", tot)
     for loc, s in per.most_common(top):
-        print("%6.2f%%  %8d samples  %10d inst  %s:%s" % (100.0 * s / max(tot, 1), s, ex[loc], loc[0] if loc else "?", loc[1] if loc else "?"))
+        print("%6.2f%%  %8d samples  %10d inst  %s:%s  smem_wavefronts %d ideal %d" % (100.0 * s / max(tot, 1), s, ex[loc], loc[0] if loc else "?", loc[1] if loc else "?", wf[loc], wfi[loc]))
 
 if __name__ == "__main__":
     main()

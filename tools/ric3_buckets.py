@@ -15,9 +15,12 @@ for n, l in enumerate(src, 1):
     elif 'for (int e = tid; e < NU * NRY; e += SMPC_NT)' in l: marks.append((n - 1, 'YW init'))
 marks.sort()
 acc = {}
+wfa = {}
+wfia = {}
 for l in sys.stdin:
     m = re.match(r'\s*([\d.]+)%\s+(\d+) samples\s+(\d+) inst\s+(\S+):(\d+)', l)
     if not m: continue
+    mw = re.search(r'smem_wavefronts (\d+) ideal (\d+)', l)
     pct, f, ln = float(m.group(1)), m.group(4), int(m.group(5))
     key = 'other:' + f
     if f == 'riccati3.cuh':
@@ -25,4 +28,8 @@ for l in sys.stdin:
         for n, name in marks:
             if ln >= n: key = name
     acc[key] = acc.get(key, 0) + pct
-for k, v in sorted(acc.items(), key=lambda x: -x[1]): print('%6.2f%%  %s' % (v, k))
+    if mw:
+        wfa[key] = wfa.get(key, 0) + int(mw.group(1))
+        wfia[key] = wfia.get(key, 0) + int(mw.group(2))
+tw = max(sum(wfa.values()), 1)
+for k, v in sorted(acc.items(), key=lambda x: -x[1]): print('%6.2f%%  smem wavefronts %5.1f%% (ideal/actual %.2f)  %s' % (v, 100.0 * wfa.get(k, 0) / tw, wfia.get(k, 0) / max(wfa.get(k, 0), 1), k))
