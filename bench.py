@@ -315,6 +315,26 @@ def main():
         lat = np.array(lat[20:]) * 1e3
         out["latency_ms"] = {"batch": 1, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99))}
         b1.close()
+    if rank == 0 and world == 1 and not args.no_latency:
+        # north_star target: 4096 instances at >= 100 Hz on 8 GPUs = 512 instances per GPU with a tick <= 10 ms.
+        # Device-resident ticks of a 512-instance context on this one GPU (CUDA events on the context stream).
+        scT = pu.Go2Scenario(512, seed=2000)
+        bT = setup_backend(cu, "smpc", scT, 512, local_rank)
+        xT = np.ascontiguousarray(scT.x_start())
+        assert cu.smpc_mpc_iterate(bT.ctx, pu.P(xT), 1) == 0
+        for _ in range(5):
+            cu.smpc_mpc_xmeas_from_prediction(bT.ctx)
+            assert cu.smpc_mpc_iterate(bT.ctx, None, 1) == 0
+        cu.smpc_timer_record(bT.ctx, 0)
+        for _ in range(30):
+            cu.smpc_mpc_xmeas_from_prediction(bT.ctx)
+            assert cu.smpc_mpc_iterate(bT.ctx, None, 1) == 0
+        cu.smpc_timer_record(bT.ctx, 1)
+        msT = C.c_float()
+        cu.smpc_timer_elapsed_ms(bT.ctx, C.byref(msT))
+        out["target_check"] = {"what": "512 instances per GPU (4096 over 8 GPUs), device-resident ticks", "batch_per_gpu": 512,
+                               "ms_per_tick": msT.value / 30, "hz_per_instance": 30e3 / msT.value, "target_hz": 100}
+        bT.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         r = run_cpu(args, 2 * cores, 6, 2)
