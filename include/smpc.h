@@ -280,6 +280,20 @@ int smpc_mpc_get_timings(smpc_ctx *, int first, int n_inst, int * takeoff, int *
  * (reference src/mpc.cpp:326-344): slots [n_inst][T] in horizon order; term may be NULL */
 int smpc_get_slots(smpc_ctx *, int first, int n_inst, smpc_slot * slots, smpc_terminal * term);
 
+/* ---- the consumer of (us, Ks, xs) between two MPC ticks, batched --------------------
+ * replaces: the 1 kHz loop of the reference examples,
+ *     u = us[0] - Ks[0] * difference(x_meas, xs[0])
+ * (examples/talos_fulldynamics.py:203-205, examples/go2_fulldynamics.py:282-284; RobotModelHandler::difference,
+ * src/robot-handler.cpp:81-96: difference(x1, x2) = x2 (-) x1 on the multibody state manifold).
+ * x_meas [n_inst][nx] -> u [n_inst][nu]; the plan and the gains stay on the device. */
+int smpc_feedback_control(smpc_ctx *, int first, int n_inst, const double * x_meas, double * u);
+/* replaces: Interpolator::interpolateState / interpolateLinear / interpolateContacts applied to the plan
+ * (reference src/interpolator.cpp:5-78; examples/go2_fulldynamics.py:272-275): step = floor(delay / timestep),
+ * beyond the last knot the last value is returned. x_interp [n][nx] (multibody states: Lie-group interpolation of
+ * q, linear in v; the 9-D centroidal state is interpolated linearly), u_interp [n][nu], contacts [n][nfeet] (0/1).
+ * Any output may be NULL. */
+int smpc_interpolate_plan(smpc_ctx *, int first, int n_inst, double delay, double * x_interp, double * u_interp, int * contacts);
+
 /* device-side timing of the last smpc_solve (CUDA events on the context's stream), ms */
 int smpc_last_solve_ms(smpc_ctx *, float * total_ms, float * riccati_ms);
 /* number of kernel launches issued by this context so far */

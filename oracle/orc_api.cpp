@@ -328,6 +328,76 @@ int orc_get_xdot(orc_ctx * c, int first, int n, int t, double * xdot)
   }
   return SMPC_OK;
 }
+// u = us[0] - Ks[0] * difference(x_meas, xs[0])   (reference examples/talos_fulldynamics.py:203-205;
+// RobotModelHandler::difference(x1, x2) = x2 (-) x1, reference src/robot-handler.cpp:81-96)
+int orc_feedback_control(orc_ctx * c, int first, int n, const double * x_meas, double * u)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    std::vector<double> dx((size_t)s.ndx);
+    state_difference(s.P, x_meas + (size_t)i * s.nx, s.xs[0].data(), dx.data());
+    for (int a = 0; a < s.nu; a++)
+    {
+      double acc = 0;
+      for (int k = 0; k < s.ndx; k++)
+        acc = std::fma(s.sol[0].K.d[(size_t)a * s.ndx + k], dx[(size_t)k], acc);
+      u[(size_t)i * s.nu + a] = s.us[0][a] - acc;
+    }
+  }
+  return SMPC_OK;
+}
+// Interpolator::interpolateState / interpolateLinear / interpolateContacts on the plan (reference src/interpolator.cpp:5-78)
+int orc_interpolate_plan(orc_ctx * c, int first, int n, double delay, double * x_interp, double * u_interp, int * contacts)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    const double timestep = s.P.ocp.timestep;
+    size_t step_nb = static_cast<size_t>(delay / timestep);
+    const double step_progress = (delay - (double)step_nb * timestep) / timestep;
+    if (x_interp)
+    {
+      double * o = x_interp + (size_t)i * s.nx;
+      if (step_nb >= s.xs.size() - 1)
+        memcpy(o, s.xs.back().data(), s.nx * sizeof(double));
+      else if (s.P.ocp.kind == SMPC_OCP_CENTROIDAL)
+        for (int k = 0; k < s.nx; k++)
+          o[k] = s.xs[step_nb + 1][k] * step_progress + s.xs[step_nb][k] * (1. - step_progress);
+      else
+      {
+        const Model & m = s.P.model;
+        std::vector<double> dq((size_t)m.nv);
+        difference_q(m, s.xs[step_nb].data(), s.xs[step_nb + 1].data(), dq.data());
+        for (auto & v : dq)
+          v = step_progress * v;
+        integrate_q(m, s.xs[step_nb].data(), dq.data(), o);
+        for (int k = 0; k < m.nv; k++)
+          o[m.nq + k] = s.xs[step_nb + 1][m.nq + k] * step_progress + s.xs[step_nb][m.nq + k] * (1. - step_progress);
+      }
+    }
+    if (u_interp)
+    {
+      double * o = u_interp + (size_t)i * s.nu;
+      if (step_nb >= s.us.size() - 1)
+        memcpy(o, s.us.back().data(), s.nu * sizeof(double));
+      else
+        for (int k = 0; k < s.nu; k++)
+          o[k] = s.us[step_nb + 1][k] * step_progress + s.us[step_nb][k] * (1. - step_progress);
+    }
+    if (contacts)
+    {
+      const size_t sc = std::min(step_nb, (size_t)s.N - 1);
+      for (int f = 0; f < s.P.nk; f++)
+        contacts[(size_t)i * s.P.nk + f] = (s.slots[sc].contact_mask >> f) & 1u;
+    }
+  }
+  return SMPC_OK;
+}
 // torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU-baseline leg of bench.py asks for the host cores explicitly
 void orc_set_num_threads(int n)
 {

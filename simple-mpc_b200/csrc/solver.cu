@@ -16,6 +16,7 @@
 #include "riccati.cuh"
 #include "riccati2.cuh"
 #include "riccati3.cuh"
+#include "riccati_fwd.cuh"
 #include "mpc_driver.cuh"
 #include "host_build.h"
 #include <cuda_runtime.h>
@@ -50,6 +51,7 @@ namespace
     KnotLayout L;
     SolLayout SL;
     RicSmem RS;
+    FwdSmem FS;
     const DevModel * model;
     const DevOcp * ocp;
     smpc_solver_opts opt;
@@ -341,6 +343,15 @@ namespace
 #ifndef SMPC_RIC3_TPB
 #define SMPC_RIC3_TPB 128
 #endif
+#ifndef SMPC_FWD_STAGED_MAX_WAVES
+#define SMPC_FWD_STAGED_MAX_WAVES 5
+#endif
+// per-instance sweep time with 1, 2, 3 CTAs per SM (ms at T = 50; only the ratios matter), see ric3_pick_ctas
+#ifndef SMPC_RIC_T1
+#define SMPC_RIC_T1 2.41
+#define SMPC_RIC_T2 2.78
+#define SMPC_RIC_T3 3.20
+#endif
   // resident CTAs per SM the shared-memory footprint allows (228 KB per SM, 1 KB reserved per CTA): the register
   // budget follows it (3 CTAs x 128 threads -> 168 registers, no spills worth naming: ptxas reports 56 bytes)
   template <int NDX, int NU, int NC>
@@ -366,7 +377,22 @@ namespace
       st.flags |= 1;
   }
 
-  __global__ void __launch_bounds__(64) k_forward(Arrays A)
+  // shared tail of the two forward kernels: linesearch initialisation
+  __device__ __forceinline__ void forward_epilogue(const Arrays & A, InstState & st, double dphi)
+  {
+    const smpc_solver_opts & o = A.opt;
+    st.dphi0 = dphi;
+    // nonmonotone (Zhang-Hager) reference value
+    st.ls_mov_avg = o.ls_avg_eta * st.ls_avg_weight * st.ls_mov_avg + st.phi0;
+    st.ls_avg_weight = o.ls_avg_eta * st.ls_avg_weight + 1.0;
+    st.ls_mov_avg /= st.ls_avg_weight;
+    st.alpha = 1.0;
+    st.ls_trials = 0;
+    st.phase = PH_LS;
+  }
+  // forward sweep, operands read straight from global memory: many small CTAs (18 per SM) keep enough loads in flight
+  // when the batch fills the GPU several times over; measured faster than the staged kernel from B ~ 3000 up
+  __global__ void __launch_bounds__(64) k_forward_direct(Arrays A)
   {
     __shared__ double sm[4 * SMPC_MAX_NDX + SMPC_MAX_NU + 72];
     __shared__ double dphi;
@@ -381,17 +407,25 @@ namespace
       st.mu, A.gx + xb * d.ndx, A.gu + (size_t)b * d.N * d.nu, A.lplus + xb * d.ndx, A.dxs + xb * d.ndx,
       A.dus + (size_t)b * d.N * d.nu, A.vnew + xb * d.ncmax, A.lnew + xb * d.ndx, &dphi, sm);
     if (threadIdx.x == 0)
-    {
-      const smpc_solver_opts & o = A.opt;
-      st.dphi0 = dphi;
-      // nonmonotone (Zhang-Hager) reference value
-      st.ls_mov_avg = o.ls_avg_eta * st.ls_avg_weight * st.ls_mov_avg + st.phi0;
-      st.ls_avg_weight = o.ls_avg_eta * st.ls_avg_weight + 1.0;
-      st.ls_mov_avg /= st.ls_avg_weight;
-      st.alpha = 1.0;
-      st.ls_trials = 0;
-      st.phase = PH_LS;
-    }
+      forward_epilogue(A, st, dphi);
+  }
+  // forward sweep, stage blocks by TMA into two landing buffers (riccati_fwd.cuh): lowest latency per instance
+  __global__ void __launch_bounds__(128) k_forward(Arrays A)
+  {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double dphi;
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    riccati_forward_staged(
+      A.L, A.SL, A.FS, d.N, A.knots + xb * A.L.size, A.ncs + xb, A.sol + xb * A.SL.size, A.P0 + (size_t)b * d.ndx * (d.ndx + 1),
+      st.mu, A.gx + xb * d.ndx, A.gu + (size_t)b * d.N * d.nu, A.lplus + xb * d.ndx, A.dxs + xb * d.ndx,
+      A.dus + (size_t)b * d.N * d.nu, A.vnew + xb * d.ncmax, A.lnew + xb * d.ndx, &dphi, sm);
+    if (threadIdx.x == 0)
+      forward_epilogue(A, st, dphi);
   }
 
   // reduce the trial merit, test the (nonmonotone) Armijo condition, accept or shrink the step
@@ -641,6 +675,94 @@ namespace
     for (int k = threadIdx.x; k < (int)(sizeof(smpc_slot) / sizeof(int)); k += blockDim.x)
       o[k] = s[k];
   }
+  // u = us[0] - Ks[0] * difference(x_meas, xs[0]) for one instance per CTA (32 threads); dx by lane 0 (Lie-group
+  // difference of the free-flyer), then one control row per lane with the columns in order
+  __global__ void __launch_bounds__(32) k_feedback(Arrays A, int first, const double * xmeas, double * u)
+  {
+    __shared__ double dx[SMPC_MAX_NDX];
+    const Dims & d = A.dm;
+    const int b = first + blockIdx.x;
+    const double * x0 = A.xs + (size_t)b * (d.N + 1) * d.nx;
+    const double * xm = xmeas + (size_t)blockIdx.x * d.nx;
+    if (threadIdx.x == 0)
+    {
+      if (A.ocp->kind == SMPC_OCP_CENTROIDAL)
+        for (int k = 0; k < d.ndx; k++)
+          dx[k] = x0[k] - xm[k];
+      else
+      {
+        const int nv = d.ndx / 2, nq = d.nx - nv;
+        difference_q(nv, xm, x0, dx);
+        for (int k = 0; k < nv; k++)
+          dx[nv + k] = x0[nq + k] - xm[nq + k];
+      }
+    }
+    __syncthreads();
+    const double * K = A.sol + (size_t)b * (d.N + 1) * A.SL.size + A.SL.oK;
+    const double * u0 = A.us + (size_t)b * d.N * d.nu;
+    for (int a = threadIdx.x; a < d.nu; a += blockDim.x)
+    {
+      double acc = 0;
+      for (int k = 0; k < d.ndx; k++)
+        acc = fma(K[a * d.ndx + k], dx[k], acc);
+      u[(size_t)blockIdx.x * d.nu + a] = u0[a] - acc;
+    }
+  }
+  // Interpolator::interpolateState / interpolateLinear / interpolateContacts on the plan of one instance per CTA
+  __global__ void __launch_bounds__(32) k_interpolate(Arrays A, int first, int step, double progress, double * xo, double * uo, int * co)
+  {
+    const Dims & d = A.dm;
+    const int b = first + blockIdx.x;
+    const double * xs = A.xs + (size_t)b * (d.N + 1) * d.nx;
+    const double * us = A.us + (size_t)b * d.N * d.nu;
+    if (xo)
+    {
+      double * o = xo + (size_t)blockIdx.x * d.nx;
+      if (step >= d.N) // xs.size() - 1
+      {
+        for (int k = threadIdx.x; k < d.nx; k += blockDim.x)
+          o[k] = xs[(size_t)d.N * d.nx + k];
+      }
+      else
+      {
+        const double * xa = xs + (size_t)step * d.nx, *xb = xa + d.nx;
+        if (A.ocp->kind == SMPC_OCP_CENTROIDAL)
+        {
+          for (int k = threadIdx.x; k < d.nx; k += blockDim.x)
+            o[k] = xb[k] * progress + xa[k] * (1. - progress);
+        }
+        else
+        {
+          const int nv = d.ndx / 2, nq = d.nx - nv;
+          if (threadIdx.x == 0)
+          {
+            // pinocchio::interpolate(q0, q1, u) = q0 (+) u (q1 (-) q0)
+            double dq[SMPC_MAX_NV];
+            difference_q(nv, xa, xb, dq);
+            for (int k = 0; k < nv; k++)
+              dq[k] = progress * dq[k];
+            integrate_q(nv, xa, dq, o);
+          }
+          for (int k = threadIdx.x; k < nv; k += blockDim.x)
+            o[nq + k] = xb[nq + k] * progress + xa[nq + k] * (1. - progress);
+        }
+      }
+    }
+    if (uo)
+    {
+      double * o = uo + (size_t)blockIdx.x * d.nu;
+      for (int k = threadIdx.x; k < d.nu; k += blockDim.x)
+        o[k] = (step >= d.N - 1) ? us[(size_t)(d.N - 1) * d.nu + k]
+                                 : us[(size_t)(step + 1) * d.nu + k] * progress + us[(size_t)step * d.nu + k] * (1. - progress);
+    }
+    if (co)
+    {
+      const int sc = step > d.N - 1 ? d.N - 1 : step;
+      const unsigned mask = slot_at(A, A.inst[b], b, sc).contact_mask;
+      for (int f = threadIdx.x; f < d.nk; f += blockDim.x)
+        co[(size_t)blockIdx.x * d.nk + f] = (mask >> f) & 1u;
+    }
+  }
   // gather rows of a strided device array into a dense staging buffer: dst[r][0..w) = src[r*stride + off .. + w)
   __global__ void k_pack(const double * src, double * dst, size_t rows, int w, size_t stride, int off)
   {
@@ -664,6 +786,8 @@ struct smpc_ctx
   Arrays A{};
   DevModel hmodel;
   DevOcp hocp;
+  int hmodel_sms = 0; // SM count of the device
+  bool forward_staged = true;
   std::vector<void *> allocs;
   int * h_counters = nullptr; // pinned
   void * staging = nullptr;   // device staging for host<->device conversions
@@ -794,6 +918,33 @@ namespace
     return SMPC_OK;
   }
 
+  // Wave model of the Riccati launch: an instance takes t[k] when k CTAs share its SM (measured on B200 for the
+  // (36, 24, 24) sweep, relative units); `batch` instances run as full waves of k * sms CTAs plus a remainder that
+  // runs at the occupancy it reaches.
+  int ric3_pick_ctas(int batch, int sms, int fit)
+  {
+    static const double t[4] = {0.0, SMPC_RIC_T1, SMPC_RIC_T2, SMPC_RIC_T3};
+    if (fit > 3)
+      fit = 3;
+    if (sms <= 0 || fit < 1)
+      return fit;
+    int best = fit;
+    double best_time = 1e300;
+    for (int k = fit; k >= 1; k--)
+    {
+      const int per_wave = k * sms;
+      const int full = batch / per_wave, rem = batch % per_wave;
+      const int krem = (rem + sms - 1) / sms;
+      const double time = full * t[k] + (rem ? t[krem] : 0.0);
+      if (time < best_time - 1e-12)
+      {
+        best_time = time;
+        best = k;
+      }
+    }
+    return best;
+  }
+
   template <int NDX, int NU, int NC>
   void launch_riccati3_impl(smpc_ctx * c)
   {
@@ -811,6 +962,24 @@ namespace
       return SMPC_ERR_INVALID;
     }
     c->ric_smem = (size_t)R::SIZE * sizeof(double);
+    // Resident CTAs per SM. The footprint allows `fit`; a batch that does not fill whole waves at that occupancy can
+    // finish sooner at a lower one (512 instances on 148 SMs: 444 + 68 at three per SM, 296 + 216 at two), because a
+    // CTA runs faster the fewer neighbours share its SM. ric3_pick_ctas() minimises the wave model below; the
+    // occupancy is imposed by asking for more dynamic shared memory than the kernel uses. SMPC_RIC_CTAS overrides.
+    {
+      const int fit = (int)(233472 / (c->ric_smem + 1024 + 16));
+      int want = ric3_pick_ctas(c->A.dm.B, c->hmodel_sms, fit);
+      if (const char * e = getenv("SMPC_RIC_CTAS"))
+        want = atoi(e);
+      if (want >= 1 && want < fit)
+      {
+        size_t req = (size_t)233472 / want - 1024 - 16;
+        req &= ~(size_t)15;
+        if (req > 232448 - 16)
+          req = 232448 - 16;
+        c->ric_smem = req;
+      }
+    }
     CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
     CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC>;
@@ -962,6 +1131,7 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   }
   c->device = device;
   CU(cudaSetDevice(device));
+  CU(cudaDeviceGetAttribute(&c->hmodel_sms, cudaDevAttrMultiProcessorCount, device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   Arrays & A = c->A;
   const DevOcp & O = c->hocp;
@@ -969,6 +1139,16 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   A.L = make_knot_layout(O.ndx, O.nu, O.ncmax);
   A.SL = make_sol_layout(O.ndx, O.nu, O.ncmax);
   A.RS = make_ric_smem(O.ndx, O.nu, O.ncmax);
+  A.FS = make_fwd_smem(O.ndx, O.nu, O.ncmax);
+  CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(A.FS.size * sizeof(double))));
+  // which forward kernel: the TMA-staged one has the lower latency per instance (two CTAs per SM), the direct one the
+  // higher throughput once the batch is many waves deep (SMPC_FWD_STAGED_MAX_WAVES, measured; SMPC_FWD overrides)
+  {
+    const int per_wave = 2 * (c->hmodel_sms > 0 ? c->hmodel_sms : 148);
+    c->forward_staged = batch <= SMPC_FWD_STAGED_MAX_WAVES * per_wave;
+    if (const char * e = getenv("SMPC_FWD"))
+      c->forward_staged = strcmp(e, "direct") != 0;
+  }
   A.opt = *opts;
   // kernel instantiation for this (robot, problem) shape
   int rc = SMPC_ERR_UNSUPPORTED;
@@ -1307,7 +1487,10 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
     if (!timed_ric)
       CU(cudaEventRecord(c->evr1, s));
     timed_ric = true;
-    k_forward<<<d.B, 64, 0, s>>>(c->A);
+    if (c->forward_staged)
+      k_forward<<<d.B, 128, (size_t)c->A.FS.size * sizeof(double), s>>>(c->A);
+    else
+      k_forward_direct<<<d.B, 64, 0, s>>>(c->A);
     c->launches += 3;
     for (int trial = 0; trial <= c->A.opt.ls_max_steps + 1; trial++)
     {
@@ -1714,6 +1897,73 @@ int smpc_get_slots(smpc_ctx * c, int first, int n, smpc_slot * slots, smpc_termi
   if (term)
     CU(cudaMemcpyAsync(term, c->A.term + first, (size_t)n * sizeof(smpc_terminal), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
+}
+
+int smpc_feedback_control(smpc_ctx * c, int first, int n, const double * x_meas, double * u)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (!x_meas || !u)
+  {
+    g_err = "smpc_feedback_control: null argument";
+    return SMPC_ERR_INVALID;
+  }
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  const size_t in_b = (size_t)n * d.nx * sizeof(double), out_b = (size_t)n * d.nu * sizeof(double);
+  int rc;
+  if ((rc = ensure_staging(c, in_b + out_b)) != SMPC_OK)
+    return rc;
+  double * din = (double *)c->staging;
+  double * dout = din + (size_t)n * d.nx;
+  CU(cudaMemcpyAsync(din, x_meas, in_b, cudaMemcpyHostToDevice, c->stream));
+  k_feedback<<<n, 32, 0, c->stream>>>(c->A, first, din, dout);
+  c->launches++;
+  CU(cudaMemcpyAsync(u, dout, out_b, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return SMPC_OK;
+}
+
+int smpc_interpolate_plan(smpc_ctx * c, int first, int n, double delay, double * x_interp, double * u_interp, int * contacts)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  if (!(delay >= 0))
+  {
+    g_err = "smpc_interpolate_plan: negative delay";
+    return SMPC_ERR_INVALID;
+  }
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const Dims & d = c->A.dm;
+  const double timestep = c->hocp.dt;
+  // reference src/interpolator.cpp:14-15
+  const size_t step_nb = static_cast<size_t>(delay / timestep);
+  const double step_progress = (delay - (double)step_nb * timestep) / timestep;
+  const int step = step_nb > (size_t)d.N ? d.N : (int)step_nb;
+  const size_t xb = (size_t)n * d.nx * sizeof(double), ub = (size_t)n * d.nu * sizeof(double), cb = (size_t)n * d.nk * sizeof(int);
+  int rc;
+  if ((rc = ensure_staging(c, xb + ub + cb)) != SMPC_OK)
+    return rc;
+  double * dx = (double *)c->staging;
+  double * du = dx + (size_t)n * d.nx;
+  int * dc = (int *)(du + (size_t)n * d.nu);
+  k_interpolate<<<n, 32, 0, c->stream>>>(c->A, first, step, step_progress, x_interp ? dx : nullptr, u_interp ? du : nullptr,
+                                        contacts ? dc : nullptr);
+  c->launches++;
+  if (x_interp)
+    CU(cudaMemcpyAsync(x_interp, dx, xb, cudaMemcpyDeviceToHost, c->stream));
+  if (u_interp)
+    CU(cudaMemcpyAsync(u_interp, du, ub, cudaMemcpyDeviceToHost, c->stream));
+  if (contacts)
+    CU(cudaMemcpyAsync(contacts, dc, cb, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
   return SMPC_OK;
 }
 

@@ -8,6 +8,7 @@
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati2.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
+#include "../../simple-mpc_b200/csrc/riccati_fwd.cuh"
 #include "../../simple-mpc_b200/csrc/mpc_driver.cuh"
 #include "../../simple-mpc_b200/csrc/host_build.h"
 #include <memory>
@@ -258,7 +259,10 @@ int emul_riccati3(
     g_err = "emul_riccati3: size not instantiated";
     return -1;
   }
-  riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
+  // the hot path's forward sweep: stage matrices staged through (emulated) shared memory
+  FwdSmem FS = make_fwd_smem(ndx, nu, ncmax);
+  std::vector<double> smf((size_t)FS.size + 8, 0.0);
+  riccati_forward_staged(L, SL, FS, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, smf.data());
   return 0;
 }
 
