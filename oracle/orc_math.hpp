@@ -206,38 +206,17 @@ namespace orc
     TrigCoef k;
     if (t2 < 0.25)
     {
-      // alternating series in t2; enough terms for < 1e-17 truncation at t2 = 0.25
-      double a = 0, b = 0, c = 0, e = 0, f = 0;
+      // alternating Taylor series in t2, ten terms (< 1e-17 truncation at t2 = 0.25), evaluated in Horner form with
+      // constant coefficients (the device code evaluates exactly the same expressions):
       // A = sum (-1)^n t2^n/(2n+1)!   B = sum (-1)^n t2^n/(2n+2)!   C = sum (-1)^n t2^n/(2n+3)!
       // E = sum (-1)^n t2^n/(2n+4)!   F = sum (-1)^n (n+1) t2^n/(2n+5)!
-      double term = 1.0;
-      double fact = 1.0; // (2n)! running
-      int m = 0;         // 2n
-      for (int n = 0; n < 10; n++)
-      {
-        // fact = (2n)!
-        double f1 = fact * (m + 1);       // (2n+1)!
-        double f2 = f1 * (m + 2);         // (2n+2)!
-        double f3 = f2 * (m + 3);         // (2n+3)!
-        double f4 = f3 * (m + 4);         // (2n+4)!
-        double f5 = f4 * (m + 5);         // (2n+5)!
-        double sgn = (n % 2 == 0) ? 1.0 : -1.0;
-        a += sgn * term / f1;
-        b += sgn * term / f2;
-        c += sgn * term / f3;
-        e += sgn * term / f4;
-        // F: (2t - 3 sin t + t cos t)/(2 t^5): coefficient of t^(2n+5) in (−3 sin t + t cos t):
-        //   −3 (−1)^(n+2)/(2n+5)! + (−1)^(n+2)/(2n+4)!  = (−1)^n [ (2n+5) − 3 ]/(2n+5)! = (−1)^n (2n+2)/(2n+5)!
-        f += sgn * term * (double)(m + 2) / f5 * 0.5;
-        term *= t2;
-        fact = f2;
-        m += 2;
-      }
-      k.A = a;
-      k.B = b;
-      k.C = c;
-      k.E = e;
-      k.F = f;
+      //   F: (2t - 3 sin t + t cos t)/(2 t^5): the coefficient of t^(2n+5) in (-3 sin t + t cos t) is
+      //   (-1)^n (2n+2)/(2n+5)!, halved
+      k.A = 1.0 / 1.0 + t2 * (-1.0 / 6.0 + t2 * (1.0 / 120.0 + t2 * (-1.0 / 5040.0 + t2 * (1.0 / 362880.0 + t2 * (-1.0 / 39916800.0 + t2 * (1.0 / 6227020800.0 + t2 * (-1.0 / 1307674368000.0 + t2 * (1.0 / 355687428096000.0 + t2 * (-1.0 / 121645100408832000.0)))))))));
+      k.B = 1.0 / 2.0 + t2 * (-1.0 / 24.0 + t2 * (1.0 / 720.0 + t2 * (-1.0 / 40320.0 + t2 * (1.0 / 3628800.0 + t2 * (-1.0 / 479001600.0 + t2 * (1.0 / 87178291200.0 + t2 * (-1.0 / 20922789888000.0 + t2 * (1.0 / 6402373705728000.0 + t2 * (-1.0 / 2432902008176640000.0)))))))));
+      k.C = 1.0 / 6.0 + t2 * (-1.0 / 120.0 + t2 * (1.0 / 5040.0 + t2 * (-1.0 / 362880.0 + t2 * (1.0 / 39916800.0 + t2 * (-1.0 / 6227020800.0 + t2 * (1.0 / 1307674368000.0 + t2 * (-1.0 / 355687428096000.0 + t2 * (1.0 / 121645100408832000.0 + t2 * (-1.0 / 51090942171709440000.0)))))))));
+      k.E = 1.0 / 24.0 + t2 * (-1.0 / 720.0 + t2 * (1.0 / 40320.0 + t2 * (-1.0 / 3628800.0 + t2 * (1.0 / 479001600.0 + t2 * (-1.0 / 87178291200.0 + t2 * (1.0 / 20922789888000.0 + t2 * (-1.0 / 6402373705728000.0 + t2 * (1.0 / 2432902008176640000.0 + t2 * (-1.0 / 1124000727777607680000.0)))))))));
+      k.F = 1.0 / 120.0 + t2 * (-2.0 / 5040.0 + t2 * (3.0 / 362880.0 + t2 * (-4.0 / 39916800.0 + t2 * (5.0 / 6227020800.0 + t2 * (-6.0 / 1307674368000.0 + t2 * (7.0 / 355687428096000.0 + t2 * (-8.0 / 121645100408832000.0 + t2 * (9.0 / 51090942171709440000.0 + t2 * (-10.0 / 25852016738884976640000.0)))))))));
       // D = 1/t2 - (1+cos)/(2 t sin) = (1 - A/(2B)) / t2 ; series: 1/12 + t2/720 + t2^2/30240 + t2^3/1209600 + ...
       k.D = 1.0 / 12 + t2 * (1.0 / 720 + t2 * (1.0 / 30240 + t2 * (1.0 / 1209600 + t2 * (1.0 / 47900160 + t2 * (691.0 / 1307674368000.0 + t2 * (1.0 / 74724249600.0 + t2 * (3617.0 / 10670622842880000.0)))))));
     }

@@ -92,6 +92,7 @@ namespace smpc
         double Lx[NDX], Lu[NU > 0 ? NU : 1], gx[NDX], gu[NU > 0 ? NU : 1];
       };
     };
+    double lamn[NDX], vsm[Cfg::NCMAX]; // co-state lams[t+1] and constraint multipliers of this knot (linearisation only)
     double Wch[6], Wcdh[6], Wfr[NK][3]; // weighted residuals (written while era-1 arrays are still read at the terminal node)
     double mass;                          // Y[0][0], kept past era 1
     double fR[NK][9], fp[NK][3], lever[NK][3], vf[NK][6];
@@ -511,6 +512,14 @@ namespace smpc
         }
         for (int k = tid; k < NU; k += SMPC_NT)
           s.u[k] = io.u[k];
+        if (DERIVS)
+        {
+          // multipliers read inside the assembly loops: one coalesced fetch instead of a global load per iteration
+          for (int k = tid; k < NDX; k += SMPC_NT)
+            s.lamn[k] = io.lam_n[k];
+          for (int k = tid; k < O.ncmax; k += SMPC_NT) // the multiplier arrays are strided by the run-time ncmax
+            s.vsm[k] = io.vs[k];
+        }
       }
       else
       {
@@ -849,7 +858,7 @@ namespace smpc
             val = isA ? ((j == NV + r) ? 1.0 : 0.0) : ((j == NF + r - 6) ? dt : 0.0);
           }
           out[row * ld + j] = val;
-          Lacc += val * io.lam_n[row];
+          Lacc += val * s.lamn[row];
           gacc += val * s.lplus[row];
         }
         if (isA)
@@ -1117,7 +1126,7 @@ namespace smpc
               cx = (a < NV) ? s.vf_dq[f][s.rsub[row]][a] : s.vf_dv[f][s.rsub[row]][a - NV];
             else if (kind == ROW_LAND)
               cx = (a < NV) ? s.Jp[f][2][a] : 0.0;
-            Lc += cx * io.vs[row];
+            Lc += cx * s.vsm[row];
             gc += cx * s.vplus[row];
           }
           s.Lx[a] = g + s.Lx[a] + Lc - io.lam_t[a];
@@ -1151,7 +1160,7 @@ namespace smpc
               else if (j == FS * f + 2)
                 cu = -2 * O.mu * O.mu * s.u[FS * f + 2];
             }
-            Lc += cu * io.vs[row];
+            Lc += cu * s.vsm[row];
             gc += cu * s.vplus[row];
           }
           s.Lu[j] = g + s.Lu[j] + Lc;
