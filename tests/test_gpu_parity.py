@@ -178,3 +178,76 @@ def test_batched_device_driver_vs_host_mpc_on_oracle():
         x = sc.disturb(x, k + 1)
     b.close()
     assert worst["refs"] <= 1e-12 and worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
+
+
+def test_full_size_batch_4096_sampled_against_the_oracle_and_batch_properties():
+    """BASELINE.json configs[4] at full size: 4096 Go2 kinodynamics instances with random phases and states. The oracle
+    cannot run 4096 instances in seconds, so (1) five sampled instances (global RNG streams 0, 1, 777, 2048, 4095) are
+    compared with the oracle run on exactly those streams - which also shows that an instance's result does not depend
+    on its position in the batch - and (2) size-independent properties are checked on all 4096: every solve finite, no
+    bad-pivot flag, one iteration per tick, primal infeasibility bounded, the dynamics defect of the accepted iterate
+    small, and the feedback control law reproduces us[0] at the plan."""
+    import ctypes as C
+    import numpy as np
+    from smpc_ctypes import SolverOpts, load_cuda, load_oracle
+    cu, orc = load_cuda(), load_oracle()
+    B, ticks = 4096, 3
+    sample = [0, 1, 777, 2048, 4095]
+    sc = pu.Go2Scenario(B, seed=42)
+    opts = SolverOpts()
+    cu.smpc_default_solver_opts(C.byref(opts))
+    bc = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, B)
+    # oracle: one single-instance scenario per sampled stream (first = global instance index)
+    scs = [pu.Go2Scenario(1, seed=42, first=i) for i in sample]
+    bos = [pu.Backend(orc, "orc", s.model, s.ocpb, opts, 1) for s in scs]
+    for b, s in [(bc, sc)] + list(zip(bos, scs)):
+        b.set_slots(s.initial_slots())
+        b.set_terminal(s.terminals())
+        b.set_warmstart(*s.warmstart())
+        b.solve(np.tile(s.xref, (b.B, 1)), 100)
+    for i, s in zip(sample, scs):
+        assert s.phase[0] == sc.phase[i]
+    x = sc.x_start()
+    for i, s in zip(sample, scs):
+        assert np.array_equal(s.x_start()[0], x[i])
+    worst = dict(xs=0.0, us=0.0, K=0.0)
+    for tick in range(ticks):
+        bc.cycle(sc.tails(tick))
+        bc.shift()
+        bc.solve(x, 1)
+        xs, us, Ks, _ = bc.results()
+        infos = bc.info()
+        for k, (i, s, bo) in enumerate(zip(sample, scs, bos)):
+            bo.cycle(s.tails(tick))
+            bo.shift()
+            bo.solve(x[i:i + 1], 1)
+            xo, uo, Ko, _ = bo.results()
+            io = bo.info()[0]
+            worst["xs"] = max(worst["xs"], pu.relerr(xs[i], xo[0]))
+            worst["us"] = max(worst["us"], pu.relerr(us[i], uo[0]))
+            worst["K"] = max(worst["K"], max(pu.relerr(Ks[i, t], Ko[0, t]) for t in range(sc.T)))
+            assert infos[i].num_iters == io.num_iters and infos[i].alpha == io.alpha and infos[i].ls_trials == io.ls_trials
+            assert abs(infos[i].prim_infeas - io.prim_infeas) <= 1e-7 * max(io.prim_infeas, 1e-12)
+        # batch-wide properties
+        assert np.isfinite(xs).all() and np.isfinite(us).all() and np.isfinite(Ks).all()
+        assert all(infos[i].flags == 0 and infos[i].num_iters == 1 for i in range(B))
+        prim = np.array([infos[i].prim_infeas for i in range(B)])
+        assert prim.max() < 5.0, prim.max()  # the measured states violate the contact-velocity rows by their 0.05 noise
+        assert np.allclose(np.linalg.norm(xs[:, :, 3:7], axis=2), 1.0, atol=1e-12)  # unit quaternions along every plan
+        # force_initial_condition: xs[0] is the measured state (up to the rounding of x0 (+) 0 in the linear rollout)
+        assert np.allclose(xs[:, 0], x, rtol=0, atol=1e-14)
+        # next measured state: prediction + disturbance, drawn from each instance's own stream in both worlds
+        xn = xs[:, 1, :].copy()
+        for k, (i, s) in enumerate(zip(sample, scs)):
+            xi = s.disturb(xn[i:i + 1].copy(), tick)
+            xn[i] = xi[0]
+        x = xn
+    # the control law at the plan returns us[0] for every instance
+    u = np.zeros((B, sc.nu))
+    x0 = np.ascontiguousarray(xs[:, 0])
+    assert cu.smpc_feedback_control(bc.ctx, 0, B, pu.P(x0), pu.P(u)) == 0
+    assert np.allclose(u, us[:, 0], rtol=0, atol=1e-9 * np.abs(us).max())
+    bc.close()
+    for b in bos:
+        b.close()
+    assert worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
