@@ -226,6 +226,33 @@ PYBIND11_MODULE(simple_mpc, m)
     .def_readwrite("mu_init", &SolverProxDDP::mu_init)
     .def_readonly("results", &SolverProxDDP::results_);
 
+  // Interpolator (reference bindings/expose-interpolate.cpp:20-62): each method (delay, timestep, list) -> value
+  py::class_<Interpolator>(m, "Interpolator")
+    .def(py::init<const Model &>(), py::arg("model"))
+    .def("interpolateConfiguration",
+         [](Interpolator & self, double delay, double timestep, const std::vector<VectorXd> & qs) {
+           VectorXd q;
+           self.interpolateConfiguration(delay, timestep, qs, q);
+           return q;
+         })
+    .def("interpolateState",
+         [](Interpolator & self, double delay, double timestep, const std::vector<VectorXd> & xs) {
+           VectorXd x;
+           self.interpolateState(delay, timestep, xs, x);
+           return x;
+         })
+    .def("interpolateLinear",
+         [](Interpolator & self, double delay, double timestep, const std::vector<VectorXd> & vs) {
+           VectorXd v;
+           self.interpolateLinear(delay, timestep, vs, v);
+           return v;
+         })
+    .def("interpolateContacts", [](Interpolator & self, double delay, double timestep, const std::vector<std::vector<bool>> & cs) {
+      std::vector<bool> c;
+      self.interpolateContacts(delay, timestep, cs, c);
+      return c;
+    });
+
   py::class_<MPC>(m, "MPC")
     .def(py::init([](const py::dict & s, std::shared_ptr<OCPHandler> ocp) { return std::make_unique<MPC>(mpcSettingsFromDict(s), ocp); }),
          py::arg("settings"), py::arg("problem"))

@@ -10,6 +10,7 @@
 #include "simple-mpc/fulldynamics.hpp"
 #include "simple-mpc/kinodynamics.hpp"
 #include "simple-mpc/mpc.hpp"
+#include "simple-mpc/interpolator.hpp"
 
 namespace pybind11
 {

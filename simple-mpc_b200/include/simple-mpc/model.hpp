@@ -83,5 +83,9 @@ namespace simple_mpc
   void computeCentroidalMomentum(const Model & model, Data & data, const VectorXd & q, const VectorXd & v);
   /// dq = q2 (-) q1 on the configuration manifold (free-flyer: SE(3) log in the body frame)
   VectorXd difference(const Model & model, const VectorXd & q1, const VectorXd & q2);
+  /// q (+) dq on the configuration manifold (free-flyer: q * exp6(dq), body-frame tangent)
+  VectorXd integrate(const Model & model, const VectorXd & q, const VectorXd & dq);
+  /// q0 (+) u (q1 (-) q0)   (pinocchio::interpolate)
+  VectorXd interpolate(const Model & model, const VectorXd & q0, const VectorXd & q1, double u);
 
 } // namespace simple_mpc

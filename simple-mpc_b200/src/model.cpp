@@ -225,6 +225,56 @@ namespace simple_mpc
     return d;
   }
 
+  VectorXd integrate(const Model & model, const VectorXd & q, const VectorXd & dq)
+  {
+    if ((int)q.size() != model.nq || (int)dq.size() != model.nv)
+      throw std::runtime_error("integrate: configuration / tangent of the wrong size");
+    VectorXd out(q);
+    // free-flyer: p <- p + R V(w) v, quat <- quat * quat(exp(w)) with dq = [v; w] in the body frame
+    const Vector3d v{{dq[0], dq[1], dq[2]}}, w{{dq[3], dq[4], dq[5]}};
+    const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], t = std::sqrt(t2);
+    double B, Cc, sh, ch; // (1 - cos t)/t^2, (t - sin t)/t^3, sin(t/2)/t, cos(t/2)
+    if (t < 1e-4)
+    {
+      B = 0.5 - t2 / 24;
+      Cc = 1.0 / 6 - t2 / 120;
+      sh = 0.5 - t2 / 48;
+      ch = 1.0 - t2 / 8;
+    }
+    else
+    {
+      B = (1 - std::cos(t)) / t2;
+      Cc = (t - std::sin(t)) / (t2 * t);
+      sh = std::sin(0.5 * t) / t;
+      ch = std::cos(0.5 * t);
+    }
+    const Vector3d wv = cross(w, v), wwv = cross(w, wv);
+    const Vector3d pl{{v[0] + B * wv[0] + Cc * wwv[0], v[1] + B * wv[1] + Cc * wwv[1], v[2] + B * wv[2] + Cc * wwv[2]}};
+    const std::array<double, 9> R = quatToRot(q[3], q[4], q[5], q[6]);
+    const Vector3d dp = rot(R, pl);
+    for (std::size_t k = 0; k < 3; k++)
+      out[k] = q[k] + dp[k];
+    const double ex = sh * w[0], ey = sh * w[1], ez = sh * w[2], ew = ch;
+    const double x = q[3], y = q[4], z = q[5], s = q[6];
+    double qx = s * ex + x * ew + y * ez - z * ey;
+    double qy = s * ey - x * ez + y * ew + z * ex;
+    double qz = s * ez + x * ey - y * ex + z * ew;
+    double qw = s * ew - x * ex - y * ey - z * ez;
+    const double n = std::sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    out[3] = qx / n, out[4] = qy / n, out[5] = qz / n, out[6] = qw / n;
+    for (std::size_t i = 1; i < model.joints.size(); i++)
+      out[(std::size_t)model.joints[i].idx_q] = q[(std::size_t)model.joints[i].idx_q] + dq[(std::size_t)model.joints[i].idx_v];
+    return out;
+  }
+
+  VectorXd interpolate(const Model & model, const VectorXd & q0, const VectorXd & q1, double u)
+  {
+    VectorXd d = difference(model, q0, q1);
+    for (auto & e : d)
+      e *= u;
+    return integrate(model, q0, d);
+  }
+
   // ---------------------------------------------------------------------------------------------
   // synthetic robots (same numbers as tests/smpc_ctypes.py: go2_like_model / talos_like_model)
   // ---------------------------------------------------------------------------------------------

@@ -185,3 +185,39 @@ def test_fulldynamics_handler_lowers_but_has_no_cpu_path():
     assert ocp.getProblem().stages[0].numConstraints() == 2 + 4  # torque box, joint box, one friction cone per stance foot
     with pytest.raises(RuntimeError):
         sm.MPC(hu.go2_mpc_conf(mh), ocp)
+
+
+def test_interpolator_matches_reference_semantics_and_the_oracle_plan_interpolation():
+    """Interpolator (reference src/interpolator.cpp:5-78): values at the knots, clamping beyond the last knot, linear
+    parts, contact lookup; the state interpolation agrees with the oracle's restatement used for the batched kernel."""
+    import ctypes as C
+    import parity_utils as pu
+    from smpc_ctypes import SolverOpts, load_oracle
+    mh = hu.go2_handler(sm)
+    interp = sm.Interpolator(mh.getModel())
+    orc = load_oracle()
+    sc = pu.Go2Scenario(1, seed=21)
+    opts = SolverOpts()
+    orc.orc_default_solver_opts(C.byref(opts))
+    b = pu.Backend(orc, "orc", sc.model, sc.ocpb, opts, 1)
+    b.set_slots(sc.initial_slots())
+    b.set_terminal(sc.terminals())
+    b.set_warmstart(*sc.warmstart())
+    b.solve(sc.x_start(), 5)  # a plan with a moving base
+    xs, us, _, _ = b.results(gains=False)
+    xl, ul = [xs[0, t] for t in range(51)], [us[0, t] for t in range(50)]
+    dt = 0.01
+    for delay in (0.0, 0.0042, 0.1234, 0.4899, 0.495, 0.5, 0.9):
+        xo, uo = np.zeros((1, 37)), np.zeros((1, 24))
+        assert orc.orc_interpolate_plan(b.ctx, 0, 1, C.c_double(delay), pu.P(xo), pu.P(uo), None) == 0
+        assert np.allclose(interp.interpolateState(delay, dt, xl), xo[0], rtol=0, atol=1e-12)
+        assert np.allclose(interp.interpolateLinear(delay, dt, ul), uo[0], rtol=0, atol=1e-12 * np.abs(us).max())
+        assert np.allclose(interp.interpolateConfiguration(delay, dt, [x[:19] for x in xl]), xo[0, :19], rtol=0, atol=1e-12)
+    assert np.array_equal(interp.interpolateState(3 * dt, dt, xl)[7:], xl[3][7:])
+    cs = [[True, False, True, False]] * 3 + [[False, True, False, True]] * 2
+    assert interp.interpolateContacts(0.025, dt, cs) == [True, False, True, False]
+    assert interp.interpolateContacts(0.031, dt, cs) == [False, True, False, True]
+    assert interp.interpolateContacts(7.0, dt, cs) == [False, True, False, True]
+    with pytest.raises(RuntimeError):
+        interp.interpolateState(0.0, dt, [np.zeros(5)])
+    b.close()
