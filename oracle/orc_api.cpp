@@ -328,6 +328,28 @@ int orc_get_xdot(orc_ctx * c, int first, int n, int t, double * xdot)
   }
   return SMPC_OK;
 }
+// MPC::getContactForces(t) (reference src/mpc.cpp:354-380): [n][nfeet][3], zero rows for swing feet
+int orc_get_contact_forces(orc_ctx * c, int first, int n, int t, double * forces)
+{
+  if (check_range(c, first, n))
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+  {
+    Solver & s = *c->inst[first + i];
+    if (s.P.ocp.kind != SMPC_OCP_FULLDYNAMICS)
+    {
+      g_err = "getContactForces is only available for full-dynamics problems";
+      return SMPC_ERR_UNSUPPORTED;
+    }
+    if (t < 0 || t >= s.N || s.fcs[(size_t)t].size() != (size_t)s.P.nk * 3)
+    {
+      g_err = "orc_get_contact_forces: stage index exceeds the horizon (or no evaluation yet)";
+      return SMPC_ERR_INVALID;
+    }
+    memcpy(forces + (size_t)i * s.P.nk * 3, s.fcs[(size_t)t].data(), (size_t)s.P.nk * 3 * sizeof(double));
+  }
+  return SMPC_OK;
+}
 // u = us[0] - Ks[0] * difference(x_meas, xs[0])   (reference examples/talos_fulldynamics.py:203-205;
 // RobotModelHandler::difference(x1, x2) = x2 (-) x1, reference src/robot-handler.cpp:81-96)
 int orc_feedback_control(orc_ctx * c, int first, int n, const double * x_meas, double * u)

@@ -168,6 +168,7 @@ namespace orc
   {
     int nc = 0;
     Vec xnext, xdot;
+    Vec fc; // contact force of every foot in its contact frame, zero for swing feet (full dynamics; MPC::getContactForces)
     double cost = 0;
     Vec c;
     std::vector<int> ctype;
@@ -933,6 +934,10 @@ namespace orc
       }
       add_quad_cost(r, P.w_frame, &Jx, nullptr, derivs, o);
     }
+    o.fc.assign((size_t)P.nk * 3, 0.0);
+    for (size_t cf = 0; cf < fd.feet.size(); cf++)
+      for (int rr = 0; rr < 3; rr++)
+        o.fc[(size_t)fd.feet[cf] * 3 + rr] = fd.lam[3 * cf + rr];
     for (size_t cf = 0; cf < fd.feet.size(); cf++)
     {
       const int f = fd.feet[cf];

@@ -445,6 +445,7 @@ namespace orc
     std::vector<StageSol> sol;
     std::vector<Vec> dxs, dus, vnew, lnew;
     std::vector<Vec> xdots; // getStateDerivative
+    std::vector<Vec> fcs;   // getContactForces (full dynamics)
     smpc_solve_info info;
 
     Solver(const smpc_model_desc & md, const smpc_ocp_desc & od, const smpc_solver_opts & so) : P(md, od), opt(so)
@@ -465,6 +466,7 @@ namespace orc
       prev_vs = vs;
       prev_lams = lams;
       xdots.assign(N, Vec(ndx, 0.0));
+      fcs.assign(N, Vec());
       mu = opt.mu_init;
       preg = opt.reg_init;
       memset(&info, 0, sizeof(info));
@@ -715,7 +717,10 @@ namespace orc
         // linearise at the current iterate (values + derivatives), multipliers, merit
         double cost = evaluate(xs, us, true, ev);
         for (int t = 0; t < N; t++)
+        {
           xdots[t] = ev[t].xdot;
+          fcs[t] = ev[t].fc;
+        }
         Mults m;
         multipliers(xs, ev, cost, m);
         const double phi0 = m.merit;
@@ -804,6 +809,7 @@ namespace orc
         {
           us[t] = tus[t];
           xdots[t] = tev[t].xdot;
+          fcs[t] = tev[t].fc;
         }
         info.traj_cost = tcost;
         info.merit = phi_new;

@@ -423,7 +423,18 @@ namespace smpc
           Jlog6(s.rs, s.Jl6);
       }
       for (int k = tid; k < NDX; k += SMPC_NT)
+      {
         s.xdot[k] = (k < NV) ? s.x[NQ + k] : s.acc[k - NV];
+        io.xdot[k] = s.xdot[k]; // MPC::getStateDerivative (reference src/mpc.cpp:346-352)
+      }
+      // MPC::getContactForces (reference src/mpc.cpp:354-380): contact force of every foot in its contact frame, zero
+      // rows for swing feet
+      if (io.fc)
+        for (int k = tid; k < 3 * NK; k += SMPC_NT)
+        {
+          const int cf = s.cidx[k / 3];
+          io.fc[k] = (cf >= 0) ? s.lam[3 * cf + k % 3] : 0.0;
+        }
     }
     SMPC_END
 

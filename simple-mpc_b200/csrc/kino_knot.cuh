@@ -135,6 +135,7 @@ namespace smpc
     double * gx, *gu;   // merit gradient pieces (first-order multipliers), without the -lam_plus[t] term
     double * lplus_n;   // lam_plus[t+1] = prev_lam[t+1] + e/mu
     double * xdot;
+    double * fc = nullptr; // contact forces [nfeet][3] (full dynamics only)
     KnotScalars * sc;
   };
 

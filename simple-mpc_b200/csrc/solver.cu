@@ -67,6 +67,7 @@ namespace
     double *dxs, *dus, *vnew, *lnew;
     KnotScalars *sc, *sct;
     double *xdot, *xdott;
+    double *fc, *fct; // contact forces of the last evaluation / trial [B][N][nk * 3] (full dynamics; else null)
     InstState * inst;
     int * counters; // [0] linesearch pending, [1] instances that need another round, [2] driver queue overflows
     // batched MPC driver (mpc_driver.cuh); null until smpc_mpc_setup
@@ -156,6 +157,7 @@ namespace
     io.gu = (t < d.N) ? A.gu + ((size_t)b * d.N + t) * d.nu : nullptr;
     io.lplus_n = (t < d.N) ? A.lplus + (xb + t + 1) * d.ndx : nullptr;
     io.xdot = (t < d.N) ? (TRIAL ? A.xdott : A.xdot) + ((size_t)b * d.N + t) * d.ndx : nullptr;
+    io.fc = (t < d.N && A.fc) ? (TRIAL ? A.fct : A.fc) + ((size_t)b * d.N + t) * d.nk * 3 : nullptr;
     io.sc = (TRIAL ? A.sct : A.sc) + xb + t;
   }
 
@@ -496,6 +498,9 @@ namespace
       A.us[(size_t)b * d.N * d.nu + k] = A.tus[(size_t)b * d.N * d.nu + k];
     for (int k = threadIdx.x; k < d.N * d.ndx; k += blockDim.x)
       A.xdot[(size_t)b * d.N * d.ndx + k] = A.xdott[(size_t)b * d.N * d.ndx + k];
+    if (A.fc)
+      for (int k = threadIdx.x; k < d.N * d.nk * 3; k += blockDim.x)
+        A.fc[(size_t)b * d.N * d.nk * 3 + k] = A.fct[(size_t)b * d.N * d.nk * 3 + k];
     for (int k = threadIdx.x; k < (d.N + 1) * d.ncmax; k += blockDim.x)
     {
       const int t = k / d.ncmax, i = k % d.ncmax;
@@ -1230,6 +1235,11 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   AL(A.sct, B * N1);
   AL(A.xdot, B * d.N * d.ndx);
   AL(A.xdott, B * d.N * d.ndx);
+  if (O.kind == SMPC_OCP_FULLDYNAMICS)
+  {
+    AL(A.fc, B * d.N * d.nk * 3);
+    AL(A.fct, B * d.N * d.nk * 3);
+  }
   AL(A.inst, B);
   AL(A.counters, 4);
 #undef AL
@@ -1647,15 +1657,27 @@ int smpc_get_xdot(smpc_ctx * c, int first, int n, int t, double * xdot)
 
 int smpc_get_contact_forces(smpc_ctx * c, int first, int n, int t, double * forces)
 {
-  (void)first;
-  (void)n;
-  (void)t;
-  (void)forces;
-  if (!c)
+  if (check_range(c, first, n))
     return SMPC_ERR_INVALID;
-  // reference include/simple-mpc/mpc.hpp:174-178: only defined for the full-dynamics handler
-  g_err = "getContactForces is only available for full-dynamics problems";
-  return SMPC_ERR_UNSUPPORTED;
+  if (!c->A.fc)
+  {
+    // reference include/simple-mpc/mpc.hpp:174-178: only defined for the full-dynamics handler
+    g_err = "getContactForces is only available for full-dynamics problems";
+    return SMPC_ERR_UNSUPPORTED;
+  }
+  const Dims & d = c->A.dm;
+  if (t < 0 || t >= d.N || !forces)
+  {
+    g_err = "smpc_get_contact_forces: stage index exceeds the horizon, or null output";
+    return SMPC_ERR_INVALID;
+  }
+  if (n == 0)
+    return SMPC_OK;
+  CU(cudaSetDevice(c->device));
+  const size_t w = (size_t)d.nk * 3 * sizeof(double);
+  CU(cudaMemcpy2DAsync(forces, w, c->A.fc + ((size_t)first * d.N + t) * d.nk * 3, (size_t)d.N * w, w, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SMPC_OK;
 }
 
 // x0 <- xs[1] of every instance (closed loop without a plant: the predicted next state is the measurement)

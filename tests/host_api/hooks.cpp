@@ -18,7 +18,6 @@ namespace
   {
     return g_orc_create(out, batch, m, o, s);
   }
-  int no_contact_forces(smpc_ctx *, int, int, int, double *) { return SMPC_ERR_UNSUPPORTED; }
   SolverApi g_api;
   bool g_loaded = false;
 
@@ -52,7 +51,7 @@ namespace
     sym(h, "orc_get_results", g_api.get_results);
     sym(h, "orc_get_info", g_api.get_info);
     sym(h, "orc_get_xdot", g_api.get_xdot);
-    g_api.get_contact_forces = &no_contact_forces;
+    sym(h, "orc_get_contact_forces", g_api.get_contact_forces);
     g_api.name = "CPU oracle (test harness)";
     g_loaded = true;
     return g_api;

@@ -51,6 +51,22 @@ def go2_kino_problem(sm, mh, T=50, **over):
     return ocp, conf
 
 
+def go2_full_problem(sm, mh, T=50, **over):
+    """reference examples/go2_fulldynamics.py:43-77 on the synthetic go2-like robot"""
+    nv = mh.getModel().nv
+    w_x = np.array([0, 0, 0, 0, 0, 0] + [1, 1, 1] * 4 + [10] * 6 + [0.1, 0.1, 0.1] * 4, float)
+    conf = dict(
+        timestep=0.01, w_x=np.diag(w_x), w_u=np.eye(nv - 6) * 1e-4, w_cent=np.diag([0.04, 0.04, 0, 0, 0, 0.0]), gravity=np.array([0, 0, -9.81]),
+        force_size=3, w_forces=np.diag([1e-4, 1e-4, 1e-4]), w_frame=np.eye(3) * 1000.0, umin=-np.ones(nv - 6) * 23.7, umax=np.ones(nv - 6) * 23.7,
+        qmin=np.array(mh.getModel().lowerPositionLimit), qmax=np.array(mh.getModel().upperPositionLimit),
+        Kp_correction=np.zeros(3), Kd_correction=np.zeros(3), mu=0.8, Lfoot=0.01, Wfoot=0.01, torque_limits=True, kinematics_limits=True,
+        force_cone=False, land_cstr=False)
+    conf.update(over)
+    ocp = sm.FullDynamicsOCP(conf, mh)
+    ocp.createProblem(mh.getReferenceState(), T, 3, -9.81, False)
+    return ocp, conf
+
+
 def go2_mpc_conf(mh):
     return dict(support_force=mh.getMass() * 9.81, TOL=1e-4, mu_init=1e-8, max_iters=1, num_threads=8, swing_apex=0.15,
                 T_fly=30, T_contact=10, timestep=0.01)

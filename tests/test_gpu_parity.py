@@ -251,3 +251,38 @@ def test_full_size_batch_4096_sampled_against_the_oracle_and_batch_properties():
     for b in bos:
         b.close()
     assert worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
+
+
+def test_host_api_mpc_cuda_vs_oracle_go2_fulldynamics():
+    """simple_mpc.MPC with the FullDynamicsOCP handler (reference examples/go2_fulldynamics.py:43-106) on CUDA against
+    the same host driver bound to the CPU oracle, 15 ticks of the trot; getContactForces is read from the device."""
+    import numpy as np
+    import host_api_utils as hu
+    sm, hooks = hu.import_simple_mpc(), hu.import_hooks()
+    mh = hu.go2_handler(sm)
+    mpcs = []
+    for make in (lambda c, o: sm.MPC(c, o), lambda c, o: hooks.make_oracle_mpc(c, o, hu.LIBORC)):
+        ocp, _ = hu.go2_full_problem(sm, mh, T=50)
+        mpcs.append(make(hu.go2_mpc_conf(mh), ocp))
+    cu, orc = mpcs
+    for m in mpcs:
+        m.generateCycleHorizon(hu.go2_trot())
+        m.switchToWalk(np.array([0.2, 0, 0, 0, 0, 0.1]))
+    x = mh.getReferenceState()
+    worst = dict(xs=0.0, us=0.0, K=0.0)
+    for k in range(16):
+        if k > 0:
+            for m in mpcs:
+                m.iterate(x)
+        worst["xs"] = max(worst["xs"], pu.relerr(np.array(cu.xs), np.array(orc.xs)))
+        worst["us"] = max(worst["us"], pu.relerr(np.array(cu.us), np.array(orc.us)))
+        worst["K"] = max(worst["K"], max(pu.relerr(cu.Ks[t], orc.Ks[t]) for t in range(50)))
+        assert cu.solver.results.num_iters == orc.solver.results.num_iters
+        x = orc.xs[1]
+    for t in (0, 20, 49):
+        f, fo = np.array(cu.getContactForces(t)), np.array(orc.getContactForces(t))
+        assert f.shape == (4, 3) and pu.relerr(f, fo) <= 1e-7, (t, pu.relerr(f, fo))
+        assert pu.relerr(cu.getStateDerivative(t), orc.getStateDerivative(t)) <= 1e-7
+    f = np.array(cu.getContactForces(0))
+    assert abs(f[:, 2].sum() - mh.getMass() * 9.81) < 0.25 * mh.getMass() * 9.81  # the stance feet carry the weight
+    assert worst["xs"] <= TOL and worst["us"] <= 1e-7 and worst["K"] <= 1e-6, worst
