@@ -286,3 +286,69 @@ def test_host_api_mpc_cuda_vs_oracle_go2_fulldynamics():
     f = np.array(cu.getContactForces(0))
     assert abs(f[:, 2].sum() - mh.getMass() * 9.81) < 0.25 * mh.getMass() * 9.81  # the stance feet carry the weight
     assert worst["xs"] <= TOL and worst["us"] <= 1e-7 and worst["K"] <= 1e-6, worst
+
+
+def test_fine_grained_entry_points_against_the_oracle():
+    """The per-call entry points a host-side MPC uses between solves: smpc_upload_stage_table + smpc_cycle_ids,
+    smpc_set_slot (setReferenceState / setReferencePose on one stage), smpc_set_foot_refs (all stages),
+    smpc_set_x0 + smpc_solve(NULL), smpc_x0_from_prediction, smpc_get_duals, and the index errors the reference throws
+    (src/ocp-handler.cpp:74-77). Both libraries receive the same calls; results must agree as in the other tests."""
+    import ctypes as C
+    import numpy as np
+    from smpc_ctypes import Slot, SolverOpts, load_cuda, load_oracle
+    cu, orc = load_cuda(), load_oracle()
+    B = 3
+    sc = pu.Go2Scenario(B, seed=9)
+    opts = SolverOpts()
+    cu.smpc_default_solver_opts(C.byref(opts))
+    backs = [pu.Backend(orc, "orc", sc.model, sc.ocpb, opts, B), pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, B)]
+    table, n = sc.stage_table()
+    rng = np.random.default_rng(5)
+    refs = np.zeros((B, sc.T, 4, 12))
+    for t in range(sc.T):
+        for f in range(4):
+            refs[:, t, f, :9] = np.eye(3).ravel()
+            refs[:, t, f, 9:] = sc.feet[f][1] + rng.normal(size=(B, 3)) * 0.01
+    one = (Slot * B)(*[sc.gait_slot(0) for _ in range(B)])
+    for i in range(B):
+        one[i].x_ref[19] = 0.1 * (i + 1)  # setVelocityBase on the last stage
+    x = sc.x_start()
+    for b in backs:
+        assert b.f("upload_stage_table")(b.ctx, table, n + 1) == 0
+        b.set_slots(sc.initial_slots())
+        b.set_terminal(sc.terminals())
+        b.set_warmstart(*sc.warmstart())
+        b.solve(np.tile(sc.xref, (B, 1)), 100)
+    for tick in range(6):
+        ids = ((sc.phase + tick) % 80).astype(np.int32)
+        for b in backs:
+            assert b.f("cycle_ids")(b.ctx, 0, B, ids.ctypes.data_as(C.POINTER(C.c_int))) == 0
+            b.set_foot_refs(refs)
+            assert b.f("set_slot")(b.ctx, 0, B, sc.T - 1, one) == 0
+            b.shift()
+            if b.pre == "smpc":
+                xc = np.ascontiguousarray(x)
+                assert cu.smpc_set_x0(b.ctx, pu.P(xc)) == 0 and cu.smpc_solve(b.ctx, None, 1) == 0  # states already on the device
+            else:
+                b.solve(x, 1)
+        (xo, uo, Ko, _), (xc, uc, Kc, _) = backs[0].results(), backs[1].results()
+        assert pu.relerr(xc, xo) <= TOL and pu.relerr(uc, uo) <= TOL, (tick, pu.relerr(xc, xo), pu.relerr(uc, uo))
+        assert max(pu.relerr(Kc[i, t], Ko[i, t]) for i in range(B) for t in range(sc.T)) <= TOL_K
+        (vo, lo), (vc, lc) = backs[0].duals(), backs[1].duals()
+        assert pu.relerr(vc, vo) <= 1e-6 and pu.relerr(lc, lo) <= 1e-6, (pu.relerr(vc, vo), pu.relerr(lc, lo))
+        x = sc.disturb(xo[:, 1, :].copy(), tick)
+    # closed loop without a plant: x0 <- predicted xs[1], device to device
+    xs_before = backs[1].results(gains=False)[0]
+    assert cu.smpc_x0_from_prediction(backs[1].ctx) == 0 and cu.smpc_solve(backs[1].ctx, None, 1) == 0
+    assert np.allclose(backs[1].results(gains=False)[0][:, 0], xs_before[:, 1], rtol=0, atol=1e-14)
+    # index errors
+    s1 = (Slot * 1)(sc.gait_slot(0))
+    assert cu.smpc_set_slot(backs[1].ctx, 0, 1, sc.T, s1) != 0 and cu.smpc_set_slot(backs[1].ctx, 0, B + 1, 0, s1) != 0
+    out = np.zeros((1, sc.ndx))
+    assert cu.smpc_get_xdot(backs[1].ctx, 0, 1, sc.T, pu.P(out)) != 0
+    bad = np.array([81, 0, 0], dtype=np.int32)
+    assert cu.smpc_cycle_ids(backs[1].ctx, 0, B, bad.ctypes.data_as(C.POINTER(C.c_int))) != 0
+    assert cu.smpc_get_contact_forces(backs[1].ctx, 0, 1, 0, pu.P(np.zeros((1, 12)))) != 0  # kinodynamics: not defined
+    assert b"full-dynamics" in cu.smpc_last_error()
+    for b in backs:
+        b.close()
