@@ -164,6 +164,7 @@ PYBIND11_MODULE(simple_mpc, m)
 
   py::class_<OCPHandler, std::shared_ptr<OCPHandler>>(m, "OCPHandler")
     .def("createProblem", &OCPHandler::createProblem, py::arg("x0"), py::arg("horizon"), py::arg("force_size"), py::arg("gravity"), py::arg("terminal_constraint"))
+    .def("createTerminalCost", &OCPHandler::createTerminalCost)
     .def("createTerminalConstraint", [](OCPHandler & o, const VectorXd & c) { o.createTerminalConstraint(toVec3(py::cast(c))); })
     .def("updateTerminalConstraint", [](OCPHandler & o, const VectorXd & c) { o.updateTerminalConstraint(toVec3(py::cast(c))); })
     .def("setReferencePose", &OCPHandler::setReferencePose)

@@ -352,3 +352,56 @@ def test_fine_grained_entry_points_against_the_oracle():
     assert b"full-dynamics" in cu.smpc_last_error()
     for b in backs:
         b.close()
+
+
+def test_batched_device_driver_centroidal_talos_vs_host_mpc_on_oracle():
+    """smpc_mpc_iterate for the CentroidalOCP (config C2): the device reduces the measured multibody state to [com; hg],
+    regenerates the 6-D contact references and solves; one host `MPC` on the CPU oracle per instance is the checker."""
+    import ctypes as C
+    import numpy as np
+    import host_api_utils as hu
+    from smpc_ctypes import Slot, MpcSettings, SolverOpts, load_cuda
+    sm, hooks = hu.import_simple_mpc(), hu.import_hooks()
+    cu = load_cuda()
+    B = 2
+    vbs = np.array([[0.1, 0.0, 0, 0, 0, 0.05], [0.05, 0.02, 0, 0, 0, 0.0]])
+    mh = hu.talos_handler(sm)
+    hosts = []
+    for i in range(B):
+        ocp, _ = hu.talos_centroidal_problem(sm, mh, T=100)
+        mpc = hooks.make_oracle_mpc(hu.talos_mpc_conf(mh), ocp, hu.LIBORC)
+        mpc.generateCycleHorizon(hu.talos_walk(20, 80))
+        mpc.switchToWalk(vbs[i])
+        hosts.append((ocp, mpc))
+    sc = pu.TalosCentroidalScenario(B, seed=6)
+    opts = SolverOpts()
+    cu.smpc_default_solver_opts(C.byref(opts))
+    b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, B)
+    n = sc.CYCLE
+    table = (Slot * (n + 1))(*([sc.gait_slot(k) for k in range(n)] + [sc.gait_slot(0)]))
+    assert cu.smpc_upload_stage_table(b.ctx, table, n + 1) == 0
+    b.set_slots(sc.initial_slots())
+    b.set_terminal(sc.terminals())
+    b.set_warmstart(*sc.warmstart())
+    b.solve(np.tile(sc.xref, (B, 1)), 100)
+    st = MpcSettings(T_fly=80, T_contact=20, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
+    xref9 = np.ascontiguousarray(hosts[0][1].x_reference, float)
+    assert cu.smpc_mpc_setup(b.ctx, C.byref(st), None, pu.P(xref9)) == 0, cu.smpc_last_error()
+    assert cu.smpc_mpc_set_velocity_base(b.ctx, 0, B, pu.P(vbs)) == 0
+    xr = np.array(mh.getReferenceState())
+    rng = np.random.default_rng(2)
+    worst = dict(xs=0.0, us=0.0, K=0.0)
+    for k in range(12):
+        x = np.tile(xr, (B, 1))
+        x[:, 29:] = rng.normal(size=(B, 28)) * 0.05
+        x[:, 7:29] += rng.normal(size=(B, 22)) * 0.02
+        xm = np.ascontiguousarray(x)
+        assert cu.smpc_mpc_iterate(b.ctx, pu.P(xm), 1) == 0, cu.smpc_last_error()
+        xs, us, Ks, _ = b.results()
+        for i, (ocp, mpc) in enumerate(hosts):
+            mpc.iterate(x[i])
+            worst["xs"] = max(worst["xs"], pu.relerr(xs[i], np.array(mpc.xs)))
+            worst["us"] = max(worst["us"], pu.relerr(us[i], np.array(mpc.us)))
+            worst["K"] = max(worst["K"], pu.relerr(Ks[i, 0], mpc.Ks[0]))
+    b.close()
+    assert worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst

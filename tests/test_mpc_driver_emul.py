@@ -128,3 +128,59 @@ def test_device_driver_timings_at_setup():
     _, _, _, take, land = drv.tick(x)
     assert take == [59, 99, 99, 59] and land == [89, 128, 128, 89]
     drv.close()
+
+
+def test_device_driver_centroidal_talos_matches_host_mpc():
+    """CentroidalOCP on the talos-like biped (config C2): the device routine reduces the measured MULTIBODY state to the
+    9-D problem state [com; hg] (reference src/centroidal-dynamics.cpp:259-262 via RobotDataHandler::getCentroidalState,
+    src/robot-handler.cpp:141-149), writes 6-D contact references (identity rotation + swing translation) and momentum
+    references = velocity * mass on the last stage (src/centroidal-dynamics.cpp:237-238). Checked against the host MPC
+    class on the oracle, tick by tick."""
+    hooks = hu.import_hooks()
+    mh = hu.talos_handler(sm)
+    ocp, _ = hu.talos_centroidal_problem(sm, mh, T=100)
+    mpc = hooks.make_oracle_mpc(hu.talos_mpc_conf(mh), ocp, hu.LIBORC)
+    mpc.generateCycleHorizon(hu.talos_walk(20, 80))
+    vb = np.array([0.1, 0.02, 0, 0, 0, 0.05])
+    mpc.switchToWalk(vb)
+    sc = pu.TalosCentroidalScenario(1, seed=4)
+    emu = load_emul()
+    n = sc.CYCLE
+    table = (Slot * (n + 1))(*([sc.gait_slot(k) for k in range(n)] + [sc.gait_slot(0)]))
+    st = MpcSettings(T_fly=80, T_contact=20, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
+    xref9 = np.ascontiguousarray(mpc.x_reference, float)  # MPC::x_reference_ = getReferenceState(0): [com ref; velocity ref]
+    assert xref9.shape == (9,)
+    h = C.c_void_p(emu.emul_mpc_create(C.byref(sc.model), C.byref(sc.ocpb.desc), table, n + 1, C.byref(st), 0, P(xref9),
+                                       sc.initial_slots(), sc.terminals()))
+    emu.emul_mpc_set_velocity_base(h, P(vb))
+    names = ["left_sole_link", "right_sole_link"]
+    x = np.array(mh.getReferenceState())
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    mass = mh.getMass()
+    for k in range(30):
+        x[29 + 6:] = rng.normal(size=22) * 0.05  # joint velocities: non-zero centroidal momentum
+        x[29:29 + 6] = rng.normal(size=6) * 0.05
+        x[7:29] = np.array(mh.getReferenceState())[7:29] + rng.normal(size=22) * 0.02
+        mpc.iterate(x)
+        slots = (Slot * 100)()
+        term = Terminal()
+        x0 = np.zeros(9)
+        take, land = (C.c_int * 4)(), (C.c_int * 4)()
+        xc = np.ascontiguousarray(x)
+        assert emu.emul_mpc_tick(h, P(xc), slots, C.byref(term), P(x0), take, land) == 0
+        first = lambda v: v if v is not None else -1  # noqa: E731
+        for f, nme in enumerate(names):
+            assert first(mpc.getFootTakeoffCycle(nme)) == take[f] and first(mpc.getFootLandCycle(nme)) == land[f]
+        worst = max(worst, np.abs(np.array(mpc.xs[0]) - x0).max() / max(1.0, np.abs(x0).max()))  # x0 = [com; hg]
+        for t in (0, 17, 50, 99):
+            assert [bool((slots[t].contact_mask >> f) & 1) for f in range(2)] == list(ocp.getContactState(t))
+            for f, nme in enumerate(names):
+                pose = mpc.getReferencePose(t, nme)
+                worst = max(worst, np.abs(np.array(pose.translation) - np.array(slots[t].foot_ref[f][9:12])).max())
+        # last stage: com reference, momentum references = velocity * mass (getVelocityBase divides by the mass again)
+        worst = max(worst, np.abs(np.array(ocp.getPoseBase(99)) - np.array(slots[99].x_ref[:3])).max())
+        worst = max(worst, np.abs(np.array(ocp.getVelocityBase(99)) * mass - np.array(slots[99].x_ref[3:9])).max() / mass)
+        assert np.allclose(np.array(slots[99].x_ref[3:9]), vb * mass, rtol=1e-14)
+    emu.emul_mpc_destroy(h)
+    assert worst < 1e-12, worst
