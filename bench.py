@@ -303,7 +303,8 @@ def main():
                      "algorithmic_bytes": bytes_launch, "launch_ms": 1e3 * ric_avg_s,
                      "share_of_step": ric_ms.value / max(sol_ms.value, 1e-12),
                      "fp64": {"achieved_tflops": flops_launch / ric_avg_s / 1e12 if ric_avg_s > 0 else 0.0,
-                              "nominal_peak_tflops": 37.0}},
+                              "nominal_peak_tflops": 37.0,
+                              "peak_source": "tools/microbench_fp64.cu: 37.0 TFLOP/s DFMA measured on this pool's B200 (profiles/r01g_microbench_fp64.txt)"}},
         "solver": {"iters_per_tick_mean": float(np.mean(iters)), "alpha_mean": float(alphas.mean()),
                    "alpha_lt_1_frac": float((alphas < 1).mean())},
     }
