@@ -356,13 +356,15 @@ namespace
 #endif
   // resident CTAs per SM the shared-memory footprint allows (228 KB per SM, 1 KB reserved per CTA): the register
   // budget follows it (3 CTAs x 128 threads -> 168 registers, no spills worth naming: ptxas reports 56 bytes)
-  template <int NDX, int NU, int NC>
+  template <int NDX, int NU, int NC, int TPB>
   constexpr int ric3_ctas_per_sm()
   {
-    return (233472 / (Ric3<NDX, NU, NC>::SIZE * 8 + 1024 + 16) >= 3 && SMPC_RIC3_TPB == 128) ? 3 : SMPC_RIC_MINB;
+    return (233472 / (Ric3<NDX, NU, NC>::SIZE * 8 + 1024 + 16) >= 3 && TPB == 128) ? 3 : (TPB == 128 ? SMPC_RIC_MINB : 1);
   }
-  template <int NDX, int NU, int NC>
-  __global__ void __launch_bounds__(SMPC_RIC3_TPB, (ric3_ctas_per_sm<NDX, NU, NC>())) k_riccati3(Arrays A)
+  // TPB = 128: throughput variant (three CTAs per SM). TPB = 256: latency variant for batches of at most one instance
+  // per SM - twice the threads on the products and trailing updates of one instance, the whole register file to itself.
+  template <int NDX, int NU, int NC, int TPB>
+  __global__ void __launch_bounds__(TPB, (ric3_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati3(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
     const int b = blockIdx.x;
@@ -372,7 +374,7 @@ namespace
       return;
     const size_t xb = (size_t)b * (d.N + 1);
     __shared__ int flag;
-    riccati3_backward_inst<NDX, NU, NC, SMPC_RIC3_TPB>(
+    riccati3_backward_inst<NDX, NU, NC, TPB>(
       A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
@@ -950,10 +952,25 @@ namespace
     return best;
   }
 
-  template <int NDX, int NU, int NC>
+  template <int NDX, int NU, int NC, int TPB>
   void launch_riccati3_impl(smpc_ctx * c)
   {
-    k_riccati3<NDX, NU, NC><<<c->A.dm.B, SMPC_RIC3_TPB, c->ric_smem, c->stream>>>(c->A);
+    k_riccati3<NDX, NU, NC, TPB><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
+  }
+  template <int NDX, int NU, int NC, int TPB>
+  int finish_setup_riccati3(smpc_ctx * c)
+  {
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB>;
+    c->riccati_variant = TPB == 128 ? "tma-staged" : "tma-staged-256";
+    if (getenv("SMPC_VERBOSE"))
+    {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC, TPB>, TPB, c->ric_smem);
+      fprintf(stderr, "smpc: k_riccati3 (%d threads) %zu B shared memory per instance, resident CTAs per SM: %d\n", TPB, c->ric_smem, nb);
+    }
+    return SMPC_OK;
   }
   template <int NDX, int NU, int NC>
   int setup_riccati3(smpc_ctx * c)
@@ -985,17 +1002,11 @@ namespace
         c->ric_smem = req;
       }
     }
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC>;
-    c->riccati_variant = "tma-staged";
-    if (getenv("SMPC_VERBOSE"))
-    {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC>, SMPC_RIC3_TPB, c->ric_smem);
-      fprintf(stderr, "smpc: k_riccati3 %zu B shared memory per instance, resident CTAs per SM: %d\n", c->ric_smem, nb);
-    }
-    return SMPC_OK;
+    // latency variant when no SM holds more than one instance (SMPC_RIC3_TPB forces one of the two)
+    bool wide = c->hmodel_sms > 0 && c->A.dm.B <= c->hmodel_sms;
+    if (const char * e = getenv("SMPC_RIC3_TPB"))
+      wide = atoi(e) == 256;
+    return wide ? finish_setup_riccati3<NDX, NU, NC, 256>(c) : finish_setup_riccati3<NDX, NU, NC, 128>(c);
   }
 
   template <class T>
