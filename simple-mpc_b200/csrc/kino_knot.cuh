@@ -22,6 +22,7 @@
 // 6 x nv / 3 x nv Jacobian, one thread per column of A/B (rows written coalesced), flat-index loops
 // for Q/S/R/C/D. State that crosses a phase lives in KinoScratch (shared memory).
 #pragma once
+#include <cstddef>
 #include "dev_math.cuh"
 #include "dev_types.h"
 
@@ -92,26 +93,34 @@ namespace smpc
         double Lx[NDX], Lu[NU > 0 ? NU : 1], gx[NDX], gu[NU > 0 ? NU : 1];
       };
     };
-    double lamn[NDX], vsm[Cfg::NCMAX]; // co-state lams[t+1] and constraint multipliers of this knot (linearisation only)
     double Wch[6], Wcdh[6], Wfr[NK][3]; // weighted residuals (written while era-1 arrays are still read at the terminal node)
     double mass;                          // Y[0][0], kept past era 1
     double fR[NK][9], fp[NK][3], lever[NK][3], vf[NK][6];
     double com[3], vcom[3], h0[6], hd0[6], hg[6], hdg[6], hdF[6];
-    double Ag[6][NV], dh_dq[6][NV];
-    double Jp[NK][3][NV];
-    double vf_dq[NK][Cfg::VR][NV], vf_dv[NK][Cfg::VR][NV];
-    double dhF_dq[3][NV], dhF_du[6][Cfg::NF];
+    double Ag[6][NV];
     double acc[NV];
     double lu[36];
     int piv[6];
-    double Jq6[36], Jv6[36], Jl6[36];
     double rs[NDX], xnext[NX], e[NDX], lplus[NDX];
     // constraint rows
     int nc;
     int rkind[Cfg::NCMAX], rarg[Cfg::NCMAX], rsub[Cfg::NCMAX];
     int ractive[Cfg::NCMAX];
     double costs[8 + NK];
+    // ---- linearisation only (DERIVS = true). Everything from dh_dq on is never touched by the value-only (trial)
+    // instantiation, which is launched with trial_bytes() of shared memory and therefore fits more CTAs per SM ----
+    double dh_dq[6][NV];
+    double Jp[NK][3][NV];
+    double vf_dq[NK][Cfg::VR][NV], vf_dv[NK][Cfg::VR][NV];
+    double dhF_dq[3][NV], dhF_du[6][Cfg::NF];
+    double Jq6[36], Jv6[36], Jl6[36];
+    double lamn[NDX], vsm[Cfg::NCMAX]; // co-state lams[t+1] and constraint multipliers of this knot
   };
+  template <class Cfg>
+  constexpr size_t kino_trial_bytes()
+  {
+    return (offsetof(KinoScratch<Cfg>, dh_dq) + 15) & ~(size_t)15;
+  }
 
   // Global-memory view of one knot.
   struct KnotIO

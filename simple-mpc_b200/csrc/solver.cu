@@ -169,11 +169,16 @@ namespace
 #ifndef SMPC_KNOT_MINB
 #define SMPC_KNOT_MINB 8
 #endif
+// the value-only (trial) instantiation needs 13.7 KB of the scratch and no spills at 168 registers: three warps per
+// SM sub-partition (measured: 10 CTAs/SM 55.3 vs 8 CTAs/SM 55.8 ms per tick before the scratch was split)
+#ifndef SMPC_KNOT_MINB_TRIAL
+#define SMPC_KNOT_MINB_TRIAL 12
+#endif
   template <class Cfg, bool TRIAL>
 #ifdef SMPC_KNOT_MAXREG
   __global__ void __maxnreg__(SMPC_KNOT_MAXREG) k_knots(Arrays A)
 #else
-  __global__ void __launch_bounds__(32, SMPC_KNOT_MINB) k_knots(Arrays A)
+  __global__ void __launch_bounds__(32, (TRIAL ? SMPC_KNOT_MINB_TRIAL : SMPC_KNOT_MINB)) k_knots(Arrays A)
 #endif
   {
     extern __shared__ __align__(16) double smem_raw[];
@@ -836,7 +841,7 @@ namespace
     const Dims & d = c->A.dm;
     const int grid = d.B * (d.N + 1);
     if (trial)
-      k_knots<Cfg, true><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
+      k_knots<Cfg, true><<<grid, c->knot_threads, kino_trial_bytes<Cfg>(), c->stream>>>(c->A); // value-only scratch prefix
     else
       k_knots<Cfg, false><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
     c->launches++;
@@ -855,7 +860,7 @@ namespace
     {
       int nl = 0, nt = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_knots<Cfg, false>, c->knot_threads, c->knot_smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt, k_knots<Cfg, true>, c->knot_threads, c->knot_smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt, k_knots<Cfg, true>, c->knot_threads, kino_trial_bytes<Cfg>());
       fprintf(stderr, "smpc: k_knots %zu B shared memory per knot, resident CTAs per SM: lin %d, trial %d\n", c->knot_smem, nl, nt);
     }
     return SMPC_OK;
