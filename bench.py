@@ -285,8 +285,8 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # dram__bytes_read.sum + dram__bytes_write.sum of k_riccati3 from the ncu --set full capture of this tree at
-    # B = 1024 (profiles/r01g_ncu_full_B1024.csv: 2.665 + 1.272 GB per launch), per instance, scaled to this launch
-    ncu_dram_bytes_per_instance = (2.664646e9 + 1.272236e9) / 1024
+    # B = 1024 (profiles/r01i_ncu_full_B1024.csv: 2.666 + 1.272 GB per launch), per instance, scaled to this launch
+    ncu_dram_bytes_per_instance = (2.665893e9 + 1.271974e9) / 1024
     achieved = bytes_launch / ric_avg_s / 1e9 if ric_avg_s > 0 else 0.0
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -299,7 +299,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "proximal Riccati backward sweep, CTA per instance, variant " + cu.smpc_riccati_variant(b.ctx).decode(),
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                     "traffic": ncu_dram_bytes_per_instance * B, "traffic_source": "ncu --set full at B=1024, per instance x batch (profiles/r01g_ncu_full_B1024.csv)",
+                     "traffic": ncu_dram_bytes_per_instance * B, "traffic_source": "ncu --set full at B=1024, per instance x batch (profiles/r01i_ncu_full_B1024.csv)",
                      "algorithmic_bytes": bytes_launch, "launch_ms": 1e3 * ric_avg_s,
                      "share_of_step": ric_ms.value / max(sol_ms.value, 1e-12),
                      "fp64": {"achieved_tflops": flops_launch / ric_avg_s / 1e12 if ric_avg_s > 0 else 0.0,

@@ -161,13 +161,13 @@ namespace
     io.sc = (TRIAL ? A.sct : A.sc) + xb + t;
   }
 
-  // kinodynamics: one warp per knot. The kernel is latency-bound and its throughput follows the resident warps per SM
-  // up to 8 (6 -> 8 warps: 1.33x, profiles/r01e vs r01f). A one-warp CTA lives on one SM sub-partition (16 K registers),
-  // so the steps are 2 warps per sub-partition (<= 255 registers), 3 (<= 168) and 4 (<= 128). Measured at B = 4096:
-  // 8 CTAs/SM at 254 registers 59.5 ms per tick; 10 CTAs/SM (shared-memory limit) at 168 registers 61.2 ms - the
-  // register cap costs more per warp than the extra warps return, so the default stays at 8.
+  // kinodynamics: one warp per knot. The kernels are latency-bound and their throughput follows the resident warps per SM
+  // (6 -> 8 warps: 1.33x, profiles/r01e vs r01f). A one-warp CTA lives on one SM sub-partition (16 K registers), so the
+  // steps are 2 warps per sub-partition (<= 255 registers), 3 (<= 168) and 4 (<= 128). Linearisation kernel: 22.2 KB of
+  // scratch allow 10 CTAs/SM; at 168 registers (72 bytes of spills) that measures 53.3 ms per tick against 53.8 ms for
+  // 8 CTAs/SM at 254 registers (B = 4096), so 10 is the default.
 #ifndef SMPC_KNOT_MINB
-#define SMPC_KNOT_MINB 8
+#define SMPC_KNOT_MINB 10
 #endif
 // the value-only (trial) instantiation needs 13.7 KB of the scratch and no spills at 168 registers: three warps per
 // SM sub-partition (measured: 10 CTAs/SM 55.3 vs 8 CTAs/SM 55.8 ms per tick before the scratch was split)
