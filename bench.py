@@ -183,8 +183,10 @@ def main():
         return
 
     # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) is silenced
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (levels VERSION and WARN both print it; anything more verbose is sent to stderr instead)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     torch.cuda.set_device(local_rank)
     dist = None
