@@ -1,11 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — solved MPC steps/s (batch x Hz) of the Go2-like kinodynamics MPC tick on B200.
+"""bench.py — solved MPC steps/s (batch x Hz) of the MPC tick on B200, and the CPU restatement beside it.
 
-Workload (BASELINE.json configs[4]): B = 4096 independent Go2-kinodynamics MPC
+Default workload (BASELINE.json configs[4]): B = 4096 independent Go2-kinodynamics MPC
 instances PER GPU (weak scaling; ranks never exchange data on the data path), T = 50 knots, trot
 10/30/10/30 with a random gait phase per instance, randomised states, one ProxDDP iteration per tick
 (max_iters = 1, reference src/mpc.cpp:91,212). One "step" = one MPC tick of every instance.
-Robot: synthetic go2-like quadruped (example-robot-data is not available here; tests/smpc_ctypes.py).
+`--config c1|c2|c3|c4|c5` selects the other BASELINE.json configurations (c1 = c5 at batch 1; c2 Talos-like
+centroidal; c3 Go2-like full dynamics with cones + landing constraints; c4 Talos-like full dynamics, 6-D contacts).
+`--total N` is the north-star case: N instances IN TOTAL sharded over the ranks (strong scaling), e.g.
+`torchrun ... bench.py --gpus 8 --total 4096`.
+Robots are SYNTHETIC (example-robot-data is not available here; simple-mpc_b200/python/smpc_ctypes.py).
 
 One tick = smpc_mpc_iterate = MPC::iterate (reference src/mpc.cpp:189-218) for every instance: forward kinematics of the
 measured state, recedeWithCycle, updateStepTrackerReferences (Raibert foothold + Bezier swing references for all T
@@ -16,10 +20,12 @@ stages), warm-start shift, one ProxDDP iteration.
   e2e   : the same tick through the C ABI with HOST buffers: measured states copied H2D from pinned memory,
           (x1, u0, u1, K0) copied D2H every step, next measured state formed on the host.
   roofline : Riccati backward kernel (the dominant kernel), algorithmic bytes of SURVEY.md §8d per launch.
-  cpu_baseline : the oracle (CPU restatement, NOT Aligator) on a bounded sample, OpenMP over instances.
+  cpu_baseline : the oracle (CPU restatement, NOT Aligator) built -O3 with FMA (oracle/liborc_fast.so) running the
+          SAME tick (orc_mpc_iterate: reference regeneration included) on a bounded sample; three rows as BASELINE.md §3:
+          one instance / 1 thread, one instance / 8 threads over knots, one instance per thread on every host core.
 
-`--impl reference` times the CPU restatement on the host cores (the reference's own Aligator/Pinocchio
-stack cannot be built or installed here: SURVEY.md §8c).
+`--impl reference` times that CPU tick on all host cores for exactly --steps ticks (the reference's own
+Aligator/Pinocchio stack cannot be built or installed here: SURVEY.md §8c).
 """
 import argparse
 import ctypes as C
@@ -33,12 +39,24 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import parity_utils as pu  # noqa: E402
-from smpc_ctypes import Slot, SolverOpts, load_cuda, load_oracle  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "simple-mpc_b200", "python"))
+import smpc_scenarios as scn  # noqa: E402
+import smpc_dist  # noqa: E402
+from smpc_ctypes import MpcSettings, SolverOpts, load_cuda  # noqa: E402
 
+P = scn.P
 METRIC = "solved_mpc_steps_per_s"
 UNIT = "steps/s"
+
+# per configuration: scenario class, default instances per GPU, mean active constraint rows per stage (for the
+# algorithmic byte / flop count of the Riccati sweep), sample size of the CPU arm (instances per host thread)
+CONFIGS = {
+    "c1": dict(scenario="Go2Scenario", batch=1, what="go2-like (synthetic) kinodynamics MPC tick, single instance"),
+    "c2": dict(scenario="TalosCentroidalScenario", batch=4096, what="talos-like (synthetic) centroidal MPC tick, 6-D contacts + wrench cones"),
+    "c3": dict(scenario="Go2FullScenario", batch=2048, what="go2-like (synthetic) full-dynamics MPC tick, friction pyramid + landing constraints"),
+    "c4": dict(scenario="TalosFullScenario", batch=256, what="talos-like (synthetic) full-dynamics walking MPC tick, 6-D contacts, wrench cones, torque + joint limits"),
+    "c5": dict(scenario="Go2Scenario", batch=4096, what="go2-like (synthetic) kinodynamics MPC tick"),
+}
 
 
 def algorithmic_bytes_per_stage(nx, nu, nc):
@@ -83,11 +101,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def load_oracle_fast():
+    """The CPU restatement built -O3 with FMA. bench.py executes oracle/ ONLY here, as the timed CPU baseline."""
+    path = os.path.join(ROOT, "oracle", "liborc_fast.so")
+    if not os.path.exists(path):
+        raise RuntimeError("oracle/liborc_fast.so not built: run __graft_entry__.build()")
+    lib = C.CDLL(path)
+    lib.orc_last_error.restype = C.c_char_p
+    return lib
+
+
+def make_scenario(cfg, batch, seed, first=0):
+    return getattr(scn, CONFIGS[cfg]["scenario"])(batch, seed=seed, first=first)
+
+
 def setup_backend(lib, prefix, sc, batch, device=0):
+    """constructor of MPC for every instance: problem, stage table, constructor solve, driver state"""
     opts = SolverOpts()
     getattr(lib, prefix + "_default_solver_opts")(C.byref(opts))
-    b = pu.Backend(lib, prefix, sc.model, sc.ocpb, opts, batch, device)
-    table, n = sc.stage_table()  # 80 cycle stages + the standing stage
+    b = scn.Backend(lib, prefix, sc.model, sc.ocpb, opts, batch, device)
+    table, n = sc.stage_table()  # cycle stages + the standing stage
     rc = getattr(lib, prefix + "_upload_stage_table")(b.ctx, table, n + 1)
     assert rc == 0
     b.set_slots(sc.initial_slots())
@@ -95,55 +128,61 @@ def setup_backend(lib, prefix, sc, batch, device=0):
     b.set_warmstart(*sc.warmstart())
     # constructor solve at the reference state, <= 100 iterations (reference src/mpc.cpp:17,85)
     b.solve(np.tile(sc.xref, (batch, 1)), 100)
-    if prefix == "smpc":
-        # batched device-side driver: per-instance gait phase, commanded base velocity
-        from smpc_ctypes import MpcSettings
-        st = MpcSettings(T_fly=30, T_contact=10, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
-        ph = (C.c_int * batch)(*[int(p) for p in sc.phase])
-        xref = np.array(sc.xref, float)
-        assert lib.smpc_mpc_setup(b.ctx, C.byref(st), ph, pu.P(xref)) == 0, lib.smpc_last_error()
-        vb = np.ascontiguousarray(sc.vbase)
-        assert lib.smpc_mpc_set_velocity_base(b.ctx, 0, batch, pu.P(vb)) == 0, lib.smpc_last_error()
+    # batched driver: per-instance gait phase, commanded base velocity
+    st = MpcSettings(T_fly=sc.T_FLY, T_contact=sc.T_CONTACT, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
+    ph = (C.c_int * batch)(*[int(p) for p in sc.phase])
+    xref = np.array(sc.xref, float)
+    assert getattr(lib, prefix + "_mpc_setup")(b.ctx, C.byref(st), ph, P(xref)) == 0, getattr(lib, prefix + "_last_error")()
+    vb = np.ascontiguousarray(sc.vbase)
+    assert getattr(lib, prefix + "_mpc_set_velocity_base")(b.ctx, 0, batch, P(vb)) == 0, getattr(lib, prefix + "_last_error")()
     return b
 
 
-def cycle_ids(lib, prefix, b, sc, tick):
-    ids = ((sc.phase + tick) % 80).astype(np.int32)
-    rc = getattr(lib, prefix + "_cycle_ids")(b.ctx, 0, b.B, ids.ctypes.data_as(C.POINTER(C.c_int)))
-    assert rc == 0, getattr(lib, prefix + "_last_error")()
-
-
-def run_cpu(args, n_inst, ticks, warm):
-    """CPU restatement on the host cores: n_inst instances spread over OpenMP threads."""
-    orc = load_oracle()
-    orc.orc_set_num_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1; the baseline uses every host core
-    sc = pu.Go2Scenario(n_inst, seed=0)
+def run_cpu_ticks(orc, cfg, n_inst, ticks, warm, threads, knot_threads=1):
+    """`ticks` whole MPC ticks (orc_mpc_iterate) of n_inst instances of the CPU restatement; OpenMP over instances
+    (n_inst > 1) or over the knots of the one instance (knot_threads > 1)."""
+    orc.orc_set_num_threads(max(threads, knot_threads))  # torchrun sets OMP_NUM_THREADS=1; the baseline names its own team
+    sc = make_scenario(cfg, n_inst, seed=0)
     t0 = time.time()
     b = setup_backend(orc, "orc", sc, n_inst)
     ctor_s = time.time() - t0
-    x = sc.x_start()
-    tick = 0
-    for _ in range(warm):
-        cycle_ids(orc, "orc", b, sc, tick)
-        b.shift()
-        b.solve(x, 1)
-        x = b.head()[0]
-        tick += 1
+    orc.orc_set_knot_threads(b.ctx, knot_threads)
+    xm = np.ascontiguousarray(sc.xmeas_start())
     lat = []
-    t0 = time.time()
-    for _ in range(ticks):
-        t1 = time.time()
-        cycle_ids(orc, "orc", b, sc, tick)
-        b.shift()
-        b.solve(x, 1)
-        x = b.head()[0]
-        lat.append(time.time() - t1)
-        tick += 1
-    wall = time.time() - t0
-    cores = orc.orc_num_threads()
+    for k in range(warm + ticks):
+        t1 = time.perf_counter()
+        rc = orc.orc_mpc_iterate(b.ctx, P(xm), 1)
+        assert rc == 0, orc.orc_last_error()
+        x1 = b.head()[0]
+        if k >= warm:
+            lat.append(time.perf_counter() - t1)
+        xm = np.ascontiguousarray(sc.next_measurement(xm, x1, None))
+    wall = float(np.sum(lat))
     b.close()
-    return dict(value=n_inst * ticks / wall, wall=wall, cores=cores, ctor_s=ctor_s, n_inst=n_inst, ticks=ticks,
-                ms_per_step=1e3 * wall / ticks)
+    return dict(value=n_inst * ticks / wall, wall=wall, ctor_s=ctor_s, n_inst=n_inst, ticks=ticks, ms_per_step=1e3 * wall / ticks,
+                p50_ms=float(np.percentile(np.array(lat) * 1e3, 50)))
+
+
+def cpu_rows(cfg, ticks, warm, per_thread=2):
+    """CPU-1, CPU-8 (threads over the knots of one instance), CPU-batch (one instance per thread)."""
+    orc = load_oracle_fast()
+    cores = os.cpu_count() or 1
+    r1 = run_cpu_ticks(orc, cfg, 1, ticks, warm, 1, 1)
+    k8 = min(8, cores)
+    r8 = run_cpu_ticks(orc, cfg, 1, ticks, warm, k8, k8)
+    rb = run_cpu_ticks(orc, cfg, per_thread * cores, ticks, warm, cores, 1)
+    return {
+        "value": rb["value"], "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": "%d instances x %d ticks (after %d warm-up), whole tick incl. reference regeneration (orc_mpc_iterate), OpenMP over "
+                  "instances on %d threads; CPU restatement oracle/liborc_fast.so (-O3, AVX2+FMA), not Aligator" % (rb["n_inst"], ticks, warm, cores),
+        "rows": {
+            "cpu1": {"what": "one instance, 1 thread", "ms_per_tick_p50": r1["p50_ms"], "steps_per_s": r1["value"], "cores": 1},
+            "cpu8": {"what": "one instance, OpenMP over knots (model evaluation only; the Riccati sweep is serial)", "ms_per_tick_p50": r8["p50_ms"],
+                     "steps_per_s": r8["value"], "cores": k8},
+            "batch": {"what": "one instance per thread", "steps_per_s": rb["value"], "cores": cores, "instances": rb["n_inst"],
+                      "ms_per_instance_tick": 1e3 * rb["wall"] * cores / (rb["n_inst"] * ticks)},
+        },
+    }, rb
 
 
 def main():
@@ -152,7 +191,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU (weak scaling)")
+    ap.add_argument("--total", type=int, default=None, help="instances in total, sharded over the ranks (strong scaling)")
+    ap.add_argument("--disturb", type=float, default=0.01, help="std of the velocity noise added to the measured state in the e2e arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
@@ -161,9 +203,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(args.warmup, 3)
     K = args.steps
-    config = {"workload": "go2-like (synthetic) kinodynamics MPC tick, %d instances/GPU, T=50, trot 10/30/10/30, max_iters=1" % args.batch,
-              "batch_per_gpu": args.batch, "horizon": 50, "nx": 37, "ndx": 36, "nu": 24,
-              "l2": "per-tick working set (LQ knots + gains, ~4 MB/instance) exceeds the 126 MB L2 for batch >= 64",
+    cfg = args.config
+    strong = args.total is not None
+    if strong:
+        first, B = smpc_dist.shard_range(args.total, world, rank)
+        total = args.total
+    else:
+        B = args.batch or CONFIGS[cfg]["batch"]
+        first, total = rank * B, B * world
+    probe = make_scenario(cfg, 1, seed=0)
+    config = {"workload": "%s, %s, T=%d, max_iters=1" % (CONFIGS[cfg]["what"], ("%d instances in total" % total) if strong else ("%d instances/GPU" % B), probe.T),
+              "config": cfg, "instances_total": total, "instances_this_rank": B, "horizon": probe.T, "nx": probe.nx, "ndx": probe.ndx, "nu": probe.nu,
+              "l2": "per-tick working set (LQ knots + gains, MBs per instance) exceeds the 126 MB L2 for batch >= 64",
               "foot_refs": "regenerated on the device every tick for every instance (Raibert foothold + degree-8 Bezier, all T stages), inside the timed region",
               "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world}
 
@@ -171,14 +222,19 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        n_inst = 2 * cores
-        r = run_cpu(args, n_inst, max(1, min(K, 8)), min(W, 2))
+        orc = load_oracle_fast()
+        r = run_cpu_ticks(orc, cfg, 2 * cores, K, W, cores, 1)
+        config["instances_total"] = config["instances_this_rank"] = r["n_inst"]
+        config["workload"] = "%s, %d instances (bounded CPU sample of the same workload), T=%d, max_iters=1" % (CONFIGS[cfg]["what"], r["n_inst"], probe.T)
+        config["parallelism"] = "OpenMP, one instance per thread, %d threads" % cores
+        config["foot_refs"] = "regenerated on the host every tick for every instance, inside the timed region (orc_mpc_iterate)"
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                             "sample": "%d instances x %d ticks, OpenMP over instances, solve only (stage-table references, no per-tick reference regeneration); CPU restatement (oracle/), not Aligator" % (r["n_inst"], r["ticks"])},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d instances x %d ticks (after %d warm-up), whole tick incl. reference regeneration, OpenMP over instances; "
+                                       "CPU restatement oracle/liborc_fast.so (-O3, AVX2+FMA), not Aligator" % (r["n_inst"], K, W)},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -194,17 +250,15 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cu = load_cuda()
-    B = args.batch
-    sc = pu.Go2Scenario(B, seed=1000 + rank)
+    sc = make_scenario(cfg, B, seed=1000, first=first)  # RNG stream = global instance index: the same instance on any rank count
     if world > 1:
         # NCCL carries only shared read-only data: rank 0's robot table is broadcast, every rank checks it matches
-        mb = torch.frombuffer(bytearray(bytes(sc.model)), dtype=torch.uint8).cuda()
-        ref = mb.clone()
-        dist.broadcast(ref, 0)
-        assert torch.equal(ref, mb), "model tables differ across ranks"
+        _, same = smpc_dist.broadcast_bytes(dist, bytes(sc.model))
+        assert same, "model tables differ across ranks"
     b = setup_backend(cu, "smpc", sc, B, local_rank)
-    x = sc.x_start()
-    x_pinned = torch.empty((B, sc.nx), dtype=torch.float64).pin_memory()
+    nxm = sc.model.nq + sc.model.nv
+    xm = np.ascontiguousarray(sc.xmeas_start())
+    x_pinned = torch.empty((B, nxm), dtype=torch.float64).pin_memory()
     head = [torch.empty(s, dtype=torch.float64).pin_memory() for s in [(B, sc.nx), (B, sc.nu), (B, sc.nu), (B, sc.nu, sc.ndx)]]
     rng = np.random.default_rng(7 + rank)
 
@@ -214,40 +268,41 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def tick_e2e(tick):
-        x_pinned.numpy()[:] = x
+    def tick_e2e(xm_in):
+        x_pinned.numpy()[:] = xm_in
         rc = cu.smpc_mpc_iterate(b.ctx, C.c_void_p(x_pinned.data_ptr()), 1)
         assert rc == 0, cu.smpc_last_error()
         rc = cu.smpc_get_head(b.ctx, 0, B, *[C.c_void_p(h.data_ptr()) for h in head])
         assert rc == 0, cu.smpc_last_error()
-        return head[0].numpy() + 0.0
+        return head[0].numpy()
 
-    def tick_dev(tick):
-        cu.smpc_mpc_xmeas_from_prediction(b.ctx)
+    def tick_dev():
+        if sc.multibody_state:
+            cu.smpc_mpc_xmeas_from_prediction(b.ctx)
         rc = cu.smpc_mpc_iterate(b.ctx, None, 1)
         assert rc == 0, cu.smpc_last_error()
 
-    tick = 0
     # ---- end-to-end arm ----
     # the synthetic plant disturbance (measured state = prediction + velocity noise) is drawn before the timed region:
     # generating it is input synthesis, not part of the path
-    noise = rng.normal(size=(W + K, B, 18)) * 0.01
+    noise = rng.normal(size=(W + K, B, sc.model.nv)) * args.disturb
+    lat_e2e = []
     for i in range(W):
-        x = tick_e2e(tick)
-        x[:, 19:] += noise[i]
-        tick += 1
+        xm = sc.next_measurement(xm, tick_e2e(xm), noise[i])
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        x = tick_e2e(tick)
-        x[:, 19:] += noise[W + i]
-        tick += 1
+        t1 = time.perf_counter()
+        xm = sc.next_measurement(xm, tick_e2e(xm), noise[W + i])
+        lat_e2e.append(time.perf_counter() - t1)
     barrier()
     e2e_s = time.perf_counter() - t0
+    infos = b.info()
+    e2e_alphas = np.array([infos[i].alpha for i in range(B)])
+    e2e_trials = np.array([infos[i].ls_trials for i in range(B)])
     # ---- device-resident arm (CUDA events on the context stream) ----
     for _ in range(W):
-        tick_dev(tick)
-        tick += 1
+        tick_dev()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -255,8 +310,7 @@ def main():
     l0 = cu.smpc_launch_count(b.ctx)
     cu.smpc_timer_record(b.ctx, 0)
     for _ in range(K):
-        tick_dev(tick)
-        tick += 1
+        tick_dev()
     cu.smpc_timer_record(b.ctx, 1)
     ms = C.c_float()
     cu.smpc_timer_elapsed_ms(b.ctx, C.byref(ms))
@@ -269,19 +323,19 @@ def main():
     iters = [infos[i].num_iters for i in range(B)]
     alphas = np.array([infos[i].alpha for i in range(B)])
     dev_s = ms.value * 1e-3
-    times = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
+    p99_e2e = float(np.percentile(np.array(lat_e2e) * 1e3, 99))
+    times = torch.tensor([dev_s, e2e_s, p99_e2e], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, e2e_s = [float(v) for v in times.cpu()]
+    dev_s, e2e_s, p99_e2e = [float(v) for v in times.cpu()]
     sampler.join(timeout=2)
 
-    total = B * world
     value = total * K / dev_s
     e2e_value = total * K / e2e_s
     # roofline of the dominant kernel: Riccati backward, one launch per tick
-    nc_mean = 18.6  # trot: 12 joint-limit rows + 3 per stance foot (4 feet 20/80, 2 feet 60/80 of the cycle)
-    bytes_launch = B * 50 * algorithmic_bytes_per_stage(36, 24, nc_mean)
-    flops_launch = B * 50 * algorithmic_flops_per_stage(36, 24, nc_mean)
+    nc_mean = sc.mean_active_rows()
+    bytes_launch = B * sc.T * algorithmic_bytes_per_stage(sc.ndx, sc.nu, nc_mean)
+    flops_launch = B * sc.T * algorithmic_flops_per_stage(sc.ndx, sc.nu, nc_mean)
     ric_avg_s = (ric_ms.value / max(ric_n.value, 1)) * 1e-3
     peaks = {}
     try:
@@ -289,22 +343,28 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # dram__bytes_read.sum + dram__bytes_write.sum of k_riccati3 from the ncu --set full capture of this tree at
-    # B = 1024 (profiles/r01i_ncu_full_B1024.csv: 2.666 + 1.272 GB per launch), per instance, scaled to this launch
-    ncu_dram_bytes_per_instance = (2.665893e9 + 1.271974e9) / 1024
+    traffic, traffic_src = None, None
+    if cfg in ("c1", "c5"):
+        # dram__bytes_read.sum + dram__bytes_write.sum of k_riccati3 from the ncu --set full capture at B = 1024
+        # (profiles/r01i_ncu_full_B1024.csv: 2.666 + 1.272 GB per launch), per instance, scaled to this launch
+        traffic = (2.665893e9 + 1.271974e9) / 1024 * B
+        traffic_src = "ncu --set full at B=1024, per instance x batch (profiles/r01i_ncu_full_B1024.csv)"
     achieved = bytes_launch / ric_avg_s / 1e9 if ric_avg_s > 0 else 0.0
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * sc.nx * 8,
-                "d2h_bytes_per_step": B * 8 * (sc.nx + 2 * sc.nu + sc.nu * sc.ndx), "ms_per_step": 1e3 * e2e_s / K},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * nxm * 8,
+                "d2h_bytes_per_step": B * 8 * (sc.nx + 2 * sc.nu + sc.nu * sc.ndx), "ms_per_step": 1e3 * e2e_s / K,
+                "tick_ms_p50": float(np.percentile(np.array(lat_e2e) * 1e3, 50)), "tick_ms_p99_max_over_ranks": p99_e2e,
+                "hz_per_instance": K / e2e_s, "disturb_sigma_v": args.disturb,
+                "alpha_lt_1_frac": float((e2e_alphas < 1).mean()), "ls_trials_mean": float(e2e_trials.mean())},
         "gpu_launches": int(l1 - l0),
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "proximal Riccati backward sweep, CTA per instance, variant " + cu.smpc_riccati_variant(b.ctx).decode(),
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                     "traffic": ncu_dram_bytes_per_instance * B, "traffic_source": "ncu --set full at B=1024, per instance x batch (profiles/r01i_ncu_full_B1024.csv)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": bytes_launch, "launch_ms": 1e3 * ric_avg_s,
                      "share_of_step": ric_ms.value / max(sol_ms.value, 1e-12),
                      "fp64": {"achieved_tflops": flops_launch / ric_avg_s / 1e12 if ric_avg_s > 0 else 0.0,
@@ -313,47 +373,47 @@ def main():
         "solver": {"iters_per_tick_mean": float(np.mean(iters)), "alpha_mean": float(alphas.mean()),
                    "alpha_lt_1_frac": float((alphas < 1).mean())},
     }
-    if rank == 0 and world == 1 and not args.no_latency:
+    if strong:
+        out["target_check"] = {"what": "%d instances in total over %d GPU(s), end to end through host buffers" % (total, world),
+                               "hz_per_instance_e2e": K / e2e_s, "tick_ms_e2e_mean": 1e3 * e2e_s / K, "tick_ms_e2e_p99_max_over_ranks": p99_e2e,
+                               "hz_per_instance_device": K / dev_s, "target_hz": 100}
+    solo = rank == 0 and world == 1 and not strong
+    if solo and not args.no_latency:
         # single-instance latency through the C ABI with host buffers (p50 / p99 over 200 ticks)
-        sc1 = pu.Go2Scenario(1, seed=0)
+        sc1 = make_scenario(cfg, 1, seed=0)
         b1 = setup_backend(cu, "smpc", sc1, 1, local_rank)
-        x1 = sc1.x_start()
+        x1 = np.ascontiguousarray(sc1.xmeas_start())
         lat = []
         for k in range(220):
             t1 = time.perf_counter()
-            x1 = np.ascontiguousarray(x1)
-            assert cu.smpc_mpc_iterate(b1.ctx, pu.P(x1), 1) == 0
-            x1 = b1.head()[0]
+            assert cu.smpc_mpc_iterate(b1.ctx, P(x1), 1) == 0
+            h = b1.head()[0]
             lat.append(time.perf_counter() - t1)
+            x1 = np.ascontiguousarray(sc1.next_measurement(x1, h, None))
         lat = np.array(lat[20:]) * 1e3
         out["latency_ms"] = {"batch": 1, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99))}
         b1.close()
-    if rank == 0 and world == 1 and not args.no_latency:
+    if solo and not args.no_latency and cfg == "c5":
         # north_star target: 4096 instances at >= 100 Hz on 8 GPUs = 512 instances per GPU with a tick <= 10 ms.
-        # Device-resident ticks of a 512-instance context on this one GPU (CUDA events on the context stream).
-        scT = pu.Go2Scenario(512, seed=2000)
+        # Ticks of a 512-instance context on this one GPU, end to end through host buffers (the 8-GPU run itself is
+        # `--gpus 8 --total 4096`).
+        scT = make_scenario(cfg, 512, seed=2000)
         bT = setup_backend(cu, "smpc", scT, 512, local_rank)
-        xT = np.ascontiguousarray(scT.x_start())
-        assert cu.smpc_mpc_iterate(bT.ctx, pu.P(xT), 1) == 0
-        for _ in range(5):
-            cu.smpc_mpc_xmeas_from_prediction(bT.ctx)
-            assert cu.smpc_mpc_iterate(bT.ctx, None, 1) == 0
-        cu.smpc_timer_record(bT.ctx, 0)
-        for _ in range(30):
-            cu.smpc_mpc_xmeas_from_prediction(bT.ctx)
-            assert cu.smpc_mpc_iterate(bT.ctx, None, 1) == 0
-        cu.smpc_timer_record(bT.ctx, 1)
-        msT = C.c_float()
-        cu.smpc_timer_elapsed_ms(bT.ctx, C.byref(msT))
-        out["target_check"] = {"what": "512 instances per GPU (4096 over 8 GPUs), device-resident ticks", "batch_per_gpu": 512,
-                               "ms_per_tick": msT.value / 30, "hz_per_instance": 30e3 / msT.value, "target_hz": 100}
+        xT = np.ascontiguousarray(scT.xmeas_start())
+        latT = []
+        for k in range(35):
+            t1 = time.perf_counter()
+            assert cu.smpc_mpc_iterate(bT.ctx, P(xT), 1) == 0
+            hT = bT.head()[0]
+            latT.append(time.perf_counter() - t1)
+            xT = np.ascontiguousarray(scT.next_measurement(xT, hT, None))
+        latT = np.array(latT[5:]) * 1e3
+        out["target_check"] = {"what": "512 instances per GPU (4096 over 8 GPUs), ticks end to end through host buffers on ONE GPU", "batch_per_gpu": 512,
+                               "ms_per_tick_p50": float(np.percentile(latT, 50)), "ms_per_tick_p99": float(np.percentile(latT, 99)),
+                               "hz_per_instance": 1e3 / float(latT.mean()), "target_hz": 100}
         bT.close()
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        r = run_cpu(args, 2 * cores, 6, 2)
-        out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                               "sample": "%d instances x %d ticks, OpenMP over instances, solve only (stage-table references, no per-tick reference regeneration); CPU restatement (oracle/), not Aligator" % (r["n_inst"], r["ticks"]),
-                               "ms_per_instance_tick": 1e3 * r["wall"] * r["cores"] / (r["n_inst"] * r["ticks"])}
+    if solo and not args.no_cpu_baseline:
+        out["cpu_baseline"], _ = cpu_rows(cfg, 6, 2)
     b.close()
     if rank == 0:
         print(json.dumps(out))

@@ -153,13 +153,19 @@ typedef struct smpc_slot
   double u_ref[SMPC_MAX_NU];
   double foot_ref[SMPC_MAX_FEET][12]; /* R row-major (9) then p (3) */
   double f_ref[SMPC_MAX_FEET][6];     /* contact-force cost reference (full dynamics) */
+  /* target height of the landing-edge equality (FrameTranslationResidual row 2, reference src/kinodynamics.cpp:134-143,
+   * src/fulldynamics.cpp:196-204): the z of contact_pose at createStage time. It is a separate residual from the
+   * <foot>_pose_cost, so setReferencePose / smpc_set_foot_refs / the device driver never touch it. */
+  double land_z[SMPC_MAX_FEET];
 } smpc_slot;
 
 /* Terminal node data (reference createTerminalCost / createTerminalConstraint). */
 typedef struct smpc_terminal
 {
   double x_ref[SMPC_MAX_NX];
-  double com_ref[3]; /* DCM / CoM reference for the terminal constraint */
+  double com_ref[3]; /* DCM / CoM reference for the terminal constraint (updateTerminalConstraint rewrites it) */
+  double tau;        /* DCM time constant, fixed at createTerminalConstraint: sqrt(com_ref_at_creation[2] / 9.81)
+                      * (reference src/kinodynamics.cpp:372, src/fulldynamics.cpp:439) */
 } smpc_terminal;
 
 /* Scalars of aligator::ResultsTpl that the parity target names. */

@@ -14,11 +14,13 @@
 
 using namespace orc;
 
+struct OrcMpcDriver; // orc_mpc_* below (timed CPU baseline of the whole tick)
 struct orc_ctx
 {
   int batch;
   std::vector<std::unique_ptr<Solver>> inst;
   std::vector<smpc_slot> table;
+  std::shared_ptr<OrcMpcDriver> mpc;
 };
 
 static thread_local std::string g_err;
@@ -225,7 +227,8 @@ int orc_solve(orc_ctx * c, const double * x0, int max_iters)
 {
   ORC_TRY
   std::string err;
-#pragma omp parallel for schedule(dynamic, 1)
+  // one instance: no team over instances, so that Solver::knot_threads can open one over the knots
+#pragma omp parallel for schedule(dynamic, 1) if (c->batch > 1)
   for (int i = 0; i < c->batch; i++)
   {
     try
@@ -420,6 +423,30 @@ int orc_interpolate_plan(orc_ctx * c, int first, int n, double delay, double * x
   }
   return SMPC_OK;
 }
+// OpenMP threads over the knots of each instance (aligator's num_threads); meant for batch == 1
+int orc_set_knot_threads(orc_ctx * c, int n)
+{
+  if (!c || n < 1)
+  {
+    g_err = "orc_set_knot_threads: bad arguments";
+    return SMPC_ERR_INVALID;
+  }
+  for (auto & s : c->inst)
+    s->knot_threads = n;
+  return SMPC_OK;
+}
+// seconds spent in {linearisation, Riccati backward, forward sweep, linesearch trials}, summed over instances
+int orc_get_timers(orc_ctx * c, double * out4)
+{
+  if (!c || !out4)
+    return SMPC_ERR_INVALID;
+  for (int k = 0; k < 4; k++)
+    out4[k] = 0;
+  for (auto & s : c->inst)
+    for (int k = 0; k < 4; k++)
+      out4[k] += s->timers[k];
+  return SMPC_OK;
+}
 // torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU-baseline leg of bench.py asks for the host cores explicitly
 void orc_set_num_threads(int n)
 {
@@ -438,6 +465,119 @@ int orc_num_threads(void)
   return 1;
 #endif
 }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// The whole MPC tick on the CPU, for the TIMED BASELINE only (bench.py cpu_baseline / --impl reference): the part
+// of MPC::iterate around run() - updateInternalData, recedeWithCycle, updateStepTrackerReferences, warm-start
+// shift (reference src/mpc.cpp:189-324) - per instance, so that the CPU arm does the same work per tick as
+// smpc_mpc_iterate. This section is NOT a checker: it compiles the product's own driver routines
+// (simple-mpc_b200/csrc/mpc_driver.cuh, written in the phase style of par.cuh that g++ serialises) instead of
+// restating them; the checker of the device driver is the host MPC class (tests/test_mpc_driver_emul.py,
+// tests/test_gpu_parity.py). Signatures mirror smpc_mpc_* (include/smpc.h).
+// ---------------------------------------------------------------------------------------------------
+#include "../simple-mpc_b200/csrc/mpc_driver.cuh"
+#include "../simple-mpc_b200/csrc/host_build.h"
+
+struct OrcMpcDriver
+{
+  smpc::DevModel M;
+  smpc::DevOcp O;
+  smpc::MpcShared S;
+  std::vector<smpc::MpcInst> I;
+  int ncycle = 0, nxm = 0;
+};
+
+extern "C" {
+int orc_mpc_setup(orc_ctx * c, const smpc_mpc_settings * st, const int * phase, const double * x_reference)
+{
+  ORC_TRY
+  if (!c || !st || !x_reference || c->table.empty())
+    throw std::runtime_error("orc_mpc_setup: null argument or no stage table uploaded");
+  auto d = std::make_shared<OrcMpcDriver>();
+  Solver & s0 = *c->inst[0];
+  smpc_ocp_desc od = s0.P.ocp; // weights are not needed by the driver
+  smpc::build_dev_model(s0.P.model.d, d->M);
+  memset(&d->O, 0, sizeof(d->O));
+  d->O.terminal_constraint = od.terminal_constraint;
+  d->O.kind = od.kind, d->O.N = s0.N, d->O.fs = s0.P.fs, d->O.nk = s0.P.nk, d->O.nx = s0.nx, d->O.ndx = s0.ndx, d->O.nu = s0.nu;
+  d->O.dt = od.timestep, d->O.mass = s0.P.mass;
+  memset(&d->S, 0, sizeof(d->S));
+  d->S.T_fly = st->T_fly, d->S.T_contact = st->T_contact, d->S.swing_apex = st->swing_apex, d->S.timestep = st->timestep;
+  d->S.standing_id = st->standing_id;
+  d->ncycle = st->ncycle;
+  d->nxm = s0.P.model.nq + s0.P.model.nv;
+  std::vector<unsigned> masks((size_t)st->ncycle);
+  for (int k = 0; k < st->ncycle; k++)
+    masks[(size_t)k] = c->table[(size_t)k].contact_mask;
+  d->I.resize((size_t)c->batch);
+  smpc::MpcScratch scratch;
+  for (int b = 0; b < c->batch; b++)
+  {
+    smpc::MpcInst & I = d->I[(size_t)b];
+    memset(&I, 0, sizeof(I));
+    smpc::mpc_init_queues(masks.data(), st->ncycle, d->O.nk, d->O.N, phase ? phase[b] : 0, I);
+    I.walking = 1;
+    for (int k = 0; k < s0.nx; k++)
+      I.x_reference[k] = x_reference[k];
+    smpc::mpc_init_instance(d->M, s0.P.model.d.q_ref, b == 0 ? &d->S : nullptr, I, scratch);
+  }
+  c->mpc = d;
+  ORC_CATCH
+}
+int orc_mpc_set_velocity_base(orc_ctx * c, int first, int n, const double * vb)
+{
+  if (check_range(c, first, n) || !c->mpc)
+    return SMPC_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < 6; k++)
+      c->mpc->I[(size_t)(first + i)].velocity_base[k] = vb[i * 6 + k];
+  return SMPC_OK;
+}
+// x_meas [batch][nq + nv]: recede -> cycle -> references -> warm-start shift -> run(max_iters), OpenMP over instances
+int orc_mpc_iterate(orc_ctx * c, const double * x_meas, int max_iters)
+{
+  ORC_TRY
+  if (!c || !c->mpc || !x_meas)
+    throw std::runtime_error("orc_mpc_iterate: orc_mpc_setup has not been called");
+  OrcMpcDriver & D = *c->mpc;
+  std::string err;
+#pragma omp parallel for schedule(dynamic, 1) if (c->batch > 1)
+  for (int b = 0; b < c->batch; b++)
+  {
+    try
+    {
+      Solver & s = *c->inst[(size_t)b];
+      smpc::MpcInst & I = D.I[(size_t)b];
+      const int id = smpc::mpc_recede(D.S, I, c->table.data(), D.ncycle, D.O.nk, s.N, s.slots[(size_t)s.N - 1].contact_mask);
+      s.cycle(c->table[(size_t)id]);
+      smpc::MpcRing ring;
+      ring.base = s.slots.data();
+      ring.head = 0;
+      ring.N = s.N;
+      smpc::MpcScratch scratch;
+      std::vector<double> x0((size_t)s.nx);
+      smpc::mpc_refs(D.M, D.O, D.S, I, x_meas + (size_t)b * D.nxm, ring, s.term, x0.data(), scratch);
+      std::rotate(s.xs.begin(), s.xs.begin() + 1, s.xs.end());
+      s.xs[(size_t)s.N] = s.xs[(size_t)s.N - 1];
+      std::rotate(s.us.begin(), s.us.begin() + 1, s.us.end());
+      s.us[(size_t)s.N - 1] = s.us[(size_t)s.N - 2];
+      s.run(x0.data(), max_iters);
+    }
+    catch (const std::exception & e)
+    {
+#pragma omp critical
+      err = e.what();
+    }
+  }
+  if (!err.empty())
+    throw std::runtime_error(err);
+  ORC_CATCH
+}
+} // extern "C" (driver port)
+
+extern "C" {
 
 // ------------------------------- unit-level entry points -------------------------------------
 

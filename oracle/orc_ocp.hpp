@@ -214,26 +214,38 @@ namespace orc
           WJu(i, j) += w * (*Ju)(k, j);
       }
     }
+    // J^T (W J): (a, i, b) loop nest - contiguous inner loop, every entry still accumulates over ascending i;
+    // rows of J^T that are structurally zero for this residual are skipped (adding 0 * x changes nothing)
     for (int a = 0; a < ndx; a++)
     {
       double g = 0;
       for (int i = 0; i < nr; i++)
         g += (*Jx)(i, a) * Wr[i];
       o.lx[a] += g;
-      for (int b = 0; b < ndx; b++)
+      Vec rxx(ndx, 0.0), rxu(nu, 0.0);
+      bool any = false;
+      for (int i = 0; i < nr; i++)
       {
-        double s = 0;
-        for (int i = 0; i < nr; i++)
-          s += (*Jx)(i, a) * WJx(i, b);
-        o.lxx(a, b) += s;
+        const double jia = (*Jx)(i, a);
+        if (jia == 0.0)
+          continue;
+        any = true;
+        const double * wx = WJx.row(i);
+        for (int b2 = 0; b2 < ndx; b2++)
+          rxx[b2] += jia * wx[b2];
+        if (nu)
+        {
+          const double * wu = WJu.row(i);
+          for (int b2 = 0; b2 < nu; b2++)
+            rxu[b2] += jia * wu[b2];
+        }
       }
-      for (int b = 0; b < nu; b++)
-      {
-        double s = 0;
-        for (int i = 0; i < nr; i++)
-          s += (*Jx)(i, a) * WJu(i, b);
-        o.lxu(a, b) += s;
-      }
+      if (!any)
+        continue;
+      for (int b2 = 0; b2 < ndx; b2++)
+        o.lxx(a, b2) += rxx[b2];
+      for (int b2 = 0; b2 < nu; b2++)
+        o.lxu(a, b2) += rxu[b2];
     }
     for (int a = 0; a < nu; a++)
     {
@@ -241,13 +253,21 @@ namespace orc
       for (int i = 0; i < nr; i++)
         g += (*Ju)(i, a) * Wr[i];
       o.lu[a] += g;
-      for (int b = 0; b < nu; b++)
+      Vec ruu(nu, 0.0);
+      bool any = false;
+      for (int i = 0; i < nr; i++)
       {
-        double s = 0;
-        for (int i = 0; i < nr; i++)
-          s += (*Ju)(i, a) * WJu(i, b);
-        o.luu(a, b) += s;
+        const double jia = (*Ju)(i, a);
+        if (jia == 0.0)
+          continue;
+        any = true;
+        const double * wu = WJu.row(i);
+        for (int b2 = 0; b2 < nu; b2++)
+          ruu[b2] += jia * wu[b2];
       }
+      if (any)
+        for (int b2 = 0; b2 < nu; b2++)
+          o.luu(a, b2) += ruu[b2];
     }
   }
 
@@ -759,7 +779,7 @@ namespace orc
       }
       if (fs == 3 && P.ocp.land_cstr && (s.land_mask & (1u << f)))
       {
-        o.c[row] = k.oMf[f].p[2] - s.foot_ref[f][9 + 2];
+        o.c[row] = k.oMf[f].p[2] - s.land_z[f];
         o.ctype[row] = CSTR_EQ;
         if (derivs)
           for (int j = 0; j < nv; j++)
@@ -1048,7 +1068,7 @@ namespace orc
             }
           }
         row += 3;
-        o.c[row] = p[2] - s.foot_ref[f][9 + 2];
+        o.c[row] = p[2] - s.land_z[f];
         o.ctype[row] = CSTR_EQ;
         if (derivs)
           for (int j = 0; j < nv; j++)
@@ -1095,7 +1115,7 @@ namespace orc
     }
     if (P.term_nc() == 3)
     {
-      const double tau = std::sqrt(tm.com_ref[2] / 9.81); // reference src/kinodynamics.cpp:372
+      const double tau = tm.tau; // fixed at createTerminalConstraint (reference src/kinodynamics.cpp:372); setReference only moves com_ref
       for (int rr = 0; rr < 3; rr++)
       {
         o.c[rr] = k.com[rr] + tau * k.vcom[rr] - tm.com_ref[rr];

@@ -14,6 +14,7 @@
 #pragma once
 #include "orc_ocp.hpp"
 #include <algorithm>
+#include <chrono>
 
 namespace orc
 {
@@ -30,52 +31,108 @@ namespace orc
     Vec k, z, p, pt;
   };
 
-  // in-place Cholesky (lower) of an n x n row-major SPD matrix; returns false if a pivot is <= 0
+  // Loop nests below are written (row, k, column): the innermost loop runs over CONTIGUOUS columns and every output
+  // element still receives its fused multiply-adds in ascending k - the canonical per-element order the kernels follow -
+  // so the compiler can vectorise them (liborc_fast.so: AVX2 + FMA) without reassociating anything: results are
+  // bitwise those of the plain dot-product form.
+
+  // in-place Cholesky (lower) of an n x n row-major SPD matrix; returns false if a pivot is <= 0.
+  // Right-looking: entry (i,c) receives fma(-L(i,j), L(c,j), .) for ascending j, then the scaling by 1/L(c,c).
   inline bool chol_lower(Mat & M, int n)
   {
+    Vec col(n > 0 ? n : 1);
     for (int j = 0; j < n; j++)
     {
-      double s = M(j, j);
-      for (int k = 0; k < j; k++)
-        s = std::fma(-M(j, k), M(j, k), s);
+      const double s = M(j, j);
       if (!(s > 0))
         return false;
-      double l = std::sqrt(s);
+      const double l = std::sqrt(s);
       M(j, j) = l;
-      double inv = 1.0 / l;
+      const double inv = 1.0 / l;
       for (int i = j + 1; i < n; i++)
       {
-        double t = M(i, j);
-        for (int k = 0; k < j; k++)
-          t = std::fma(-M(i, k), M(j, k), t);
-        M(i, j) = t * inv;
+        M(i, j) = M(i, j) * inv;
+        col[i] = M(i, j);
+      }
+      for (int i = j + 1; i < n; i++)
+      {
+        const double lij = col[i];
+        double * Mi = &M(i, 0);
+        for (int c = j + 1; c <= i; c++)
+          Mi[c] = std::fma(-lij, col[c], Mi[c]);
       }
     }
     return true;
   }
-  // X <- L^-1 X  (L lower n x n, X n x m), column by column
+  // X <- L^-1 X  (L lower n x n, X n x m)
   inline void solve_lower(const Mat & L, int n, Mat & X, int m)
   {
-    for (int c = 0; c < m; c++)
-      for (int i = 0; i < n; i++)
+    for (int i = 0; i < n; i++)
+    {
+      double * Xi = &X(i, 0);
+      for (int k = 0; k < i; k++)
       {
-        double s = X(i, c);
-        for (int k = 0; k < i; k++)
-          s = std::fma(-L(i, k), X(k, c), s);
-        X(i, c) = s * (1.0 / L(i, i)); // reciprocal pivot: the kernels keep 1/l, not l
+        const double lik = L(i, k);
+        const double * Xk = &X(k, 0);
+        for (int c = 0; c < m; c++)
+          Xi[c] = std::fma(-lik, Xk[c], Xi[c]);
       }
+      const double inv = 1.0 / L(i, i); // reciprocal pivot: the kernels keep 1/l, not l
+      for (int c = 0; c < m; c++)
+        Xi[c] = Xi[c] * inv;
+    }
   }
   // X <- L^-T X
   inline void solve_lower_T(const Mat & L, int n, Mat & X, int m)
   {
-    for (int c = 0; c < m; c++)
-      for (int i = n - 1; i >= 0; i--)
+    for (int i = n - 1; i >= 0; i--)
+    {
+      double * Xi = &X(i, 0);
+      for (int k = n - 1; k > i; k--)
       {
-        double s = X(i, c);
-        for (int k = n - 1; k > i; k--)
-          s = std::fma(-L(k, i), X(k, c), s);
-        X(i, c) = s * (1.0 / L(i, i)); // reciprocal pivot: the kernels keep 1/l, not l
+        const double lki = L(k, i);
+        const double * Xk = &X(k, 0);
+        for (int c = 0; c < m; c++)
+          Xi[c] = std::fma(-lki, Xk[c], Xi[c]);
       }
+      const double inv = 1.0 / L(i, i); // reciprocal pivot: the kernels keep 1/l, not l
+      for (int c = 0; c < m; c++)
+        Xi[c] = Xi[c] * inv;
+    }
+  }
+  // C(a, 0..nb) += sum_k A(k, a) B(k, 0..nb)   (A^T B, ascending k per element)
+  inline void add_AtB(const Mat & A, const Mat & B, int nk, int na, int nb, Mat & Cm)
+  {
+    if (nk <= 0 || na <= 0 || nb <= 0)
+      return;
+    for (int a = 0; a < na; a++)
+    {
+      double * Ca = &Cm(a, 0);
+      for (int k = 0; k < nk; k++)
+      {
+        const double aka = A(k, a);
+        const double * Bk = &B.d[(size_t)k * B.c];
+        for (int b = 0; b < nb; b++)
+          Ca[b] = std::fma(aka, Bk[b], Ca[b]);
+      }
+    }
+  }
+  // C(a, 0..nb) += sum_k A(a, k) B(k, 0..nb)
+  inline void add_AB(const Mat & A, const Mat & B, int na, int nk, int nb, Mat & Cm)
+  {
+    if (nk <= 0 || na <= 0 || nb <= 0)
+      return;
+    for (int a = 0; a < na; a++)
+    {
+      double * Ca = &Cm(a, 0);
+      for (int k = 0; k < nk; k++)
+      {
+        const double aak = A(a, k);
+        const double * Bk = &B.d[(size_t)k * B.c];
+        for (int b = 0; b < nb; b++)
+          Ca[b] = std::fma(aak, Bk[b], Ca[b]);
+      }
+    }
   }
 
   struct RiccatiStats
@@ -106,15 +163,9 @@ namespace orc
       }
       s.P = kn.Q;
       s.p = kn.q;
+      add_AtB(kn.C, s.Z, nc, ndx, ndx, s.P);
       for (int a = 0; a < ndx; a++)
       {
-        for (int b = 0; b < ndx; b++)
-        {
-          double acc = s.P(a, b);
-          for (int i = 0; i < nc; i++)
-            acc = std::fma(kn.C(i, a), s.Z(i, b), acc);
-          s.P(a, b) = acc;
-        }
         double acc = s.p[a];
         for (int i = 0; i < nc; i++)
           acc = std::fma(kn.C(i, a), s.z[i], acc);
@@ -165,42 +216,16 @@ namespace orc
       }
       // 3. PA = P~ A, PB = P~ B
       Mat PA(ndx, ndx), PB(ndx, nu);
-      for (int a = 0; a < ndx; a++)
-      {
-        for (int b = 0; b < ndx; b++)
-        {
-          double acc = 0;
-          for (int k = 0; k < ndx; k++)
-            acc = std::fma(s.Pt(a, k), kn.A(k, b), acc);
-          PA(a, b) = acc;
-        }
-        for (int b = 0; b < nu; b++)
-        {
-          double acc = 0;
-          for (int k = 0; k < ndx; k++)
-            acc = std::fma(s.Pt(a, k), kn.B(k, b), acc);
-          PB(a, b) = acc;
-        }
-      }
+      add_AB(s.Pt, kn.A, ndx, ndx, ndx, PA);
+      add_AB(s.Pt, kn.B, ndx, ndx, nu, PB);
       // 4. Qh = Q + A^T PA ; Sh = S + A^T PB ; Rh = R + B^T PB ; qh = q + A^T w ; rh = r + B^T w
-      Mat Qh(ndx, ndx), Sh(ndx, nu), Rh(nu, nu);
+      Mat Qh = kn.Q, Sh = kn.S, Rh = kn.R;
       Vec qh(ndx), rh(nu);
+      add_AtB(kn.A, PA, ndx, ndx, ndx, Qh);
+      add_AtB(kn.A, PB, ndx, ndx, nu, Sh);
+      add_AtB(kn.B, PB, ndx, nu, nu, Rh);
       for (int a = 0; a < ndx; a++)
       {
-        for (int b = 0; b < ndx; b++)
-        {
-          double acc = kn.Q(a, b);
-          for (int k = 0; k < ndx; k++)
-            acc = std::fma(kn.A(k, a), PA(k, b), acc);
-          Qh(a, b) = acc;
-        }
-        for (int b = 0; b < nu; b++)
-        {
-          double acc = kn.S(a, b);
-          for (int k = 0; k < ndx; k++)
-            acc = std::fma(kn.A(k, a), PB(k, b), acc);
-          Sh(a, b) = acc;
-        }
         double acc = kn.q[a];
         for (int k = 0; k < ndx; k++)
           acc = std::fma(kn.A(k, a), w[k], acc);
@@ -208,13 +233,6 @@ namespace orc
       }
       for (int a = 0; a < nu; a++)
       {
-        for (int b = 0; b < nu; b++)
-        {
-          double acc = kn.R(a, b);
-          for (int k = 0; k < ndx; k++)
-            acc = std::fma(kn.B(k, a), PB(k, b), acc);
-          Rh(a, b) = acc;
-        }
         double acc = kn.r[a];
         for (int k = 0; k < ndx; k++)
           acc = std::fma(kn.B(k, a), w[k], acc);
@@ -243,34 +261,39 @@ namespace orc
         solve_lower(Rh, nu, W, nc);
         Mat Sg(nc, nc);
         for (int i = 0; i < nc; i++)
-          for (int j = 0; j <= i; j++)
+        {
+          double * Si = &Sg(i, 0);
+          Si[i] = mueq;
+          for (int k = 0; k < nu; k++)
           {
-            double acc = (i == j) ? mueq : 0.0;
-            for (int k = 0; k < nu; k++)
-              acc = std::fma(W(k, i), W(k, j), acc);
-            Sg(i, j) = acc;
-            Sg(j, i) = acc;
+            const double wki = W(k, i);
+            const double * Wk = &W(k, 0);
+            for (int j = 0; j <= i; j++)
+              Si[j] = std::fma(wki, Wk[j], Si[j]);
           }
+        }
+        for (int i = 0; i < nc; i++)
+          for (int j = 0; j < i; j++)
+            Sg(j, i) = Sg(i, j);
         if (!chol_lower(Sg, nc))
           st.ok = false;
         for (int i = 0; i < nc; i++)
-          for (int c = 0; c < ndx + 1; c++)
+        {
+          double * Gi = &G(i, 0);
+          Gi[0] = kn.d[i];
+          for (int c = 0; c < ndx; c++)
+            Gi[1 + c] = kn.C(i, c);
+          for (int k = 0; k < nu; k++)
           {
-            double acc = (c == 0) ? kn.d[i] : kn.C(i, c - 1);
-            for (int k = 0; k < nu; k++)
-              acc = std::fma(-W(k, i), Y(k, c), acc);
-            G(i, c) = acc;
+            const double wki = -W(k, i);
+            const double * Yk = &Y(k, 0);
+            for (int c = 0; c < ndx + 1; c++)
+              Gi[c] = std::fma(wki, Yk[c], Gi[c]);
           }
+        }
         solve_lower(Sg, nc, G, ndx + 1);
         solve_lower_T(Sg, nc, G, ndx + 1);
-        for (int a = 0; a < nu; a++)
-          for (int c = 0; c < ndx + 1; c++)
-          {
-            double acc = Y(a, c);
-            for (int i = 0; i < nc; i++)
-              acc = std::fma(W(a, i), G(i, c), acc);
-            Y(a, c) = acc;
-          }
+        add_AB(W, G, nu, nc, ndx + 1, Y);
       }
       solve_lower_T(Rh, nu, Y, ndx + 1);
       s.K.resize(nu, ndx);
@@ -290,19 +313,12 @@ namespace orc
           s.Z(i, b) = G(i, 1 + b);
       }
       // 6. P = Qh + Sh K + C^T Z (symmetrised) ; p = qh + Sh k + C^T z
-      s.P.resize(ndx, ndx);
+      s.P = Qh;
       s.p.assign(ndx, 0);
+      add_AB(Sh, s.K, ndx, nu, ndx, s.P);
+      add_AtB(kn.C, s.Z, nc, ndx, ndx, s.P);
       for (int a = 0; a < ndx; a++)
       {
-        for (int b = 0; b < ndx; b++)
-        {
-          double acc = Qh(a, b);
-          for (int k = 0; k < nu; k++)
-            acc = std::fma(Sh(a, k), s.K(k, b), acc);
-          for (int i = 0; i < nc; i++)
-            acc = std::fma(kn.C(i, a), s.Z(i, b), acc);
-          s.P(a, b) = acc;
-        }
         double acc = qh[a];
         for (int k = 0; k < nu; k++)
           acc = std::fma(Sh(a, k), s.k[k], acc);
@@ -447,6 +463,10 @@ namespace orc
     std::vector<Vec> xdots; // getStateDerivative
     std::vector<Vec> fcs;   // getContactForces (full dynamics)
     smpc_solve_info info;
+    // wall-clock split of run() for the timed CPU baseline: [0] linearisation, [1] Riccati backward, [2] forward sweep,
+    // [3] linesearch trials (values only), seconds accumulated since construction
+    double timers[4] = {0, 0, 0, 0};
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     Solver(const smpc_model_desc & md, const smpc_ocp_desc & od, const smpc_solver_opts & so) : P(md, od), opt(so)
     {
@@ -485,17 +505,34 @@ namespace orc
     }
 
     // values (and derivatives) of every node at (xs_, us_); fills ev
+    // knot_threads > 1: OpenMP team over the knots of ONE instance, what aligator does with num_threads
+    // (reference src/mpc.cpp:46-52, examples/go2_kinodynamics.py:101); the sum over knots stays in ascending order
+    int knot_threads = 1;
     double evaluate(const std::vector<Vec> & xs_, const std::vector<Vec> & us_, bool derivs, std::vector<StageEval> & e)
     {
       e.resize(N + 1);
-      double cost = 0;
-      for (int t = 0; t < N; t++)
+      std::string err;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(knot_threads) if (knot_threads > 1)
+      for (int t = 0; t <= N; t++)
       {
-        stage_eval(P, slots[t], xs_[t].data(), us_[t].data(), derivs, e[t]);
-        cost += e[t].cost;
+        try
+        {
+          if (t < N)
+            stage_eval(P, slots[t], xs_[t].data(), us_[t].data(), derivs, e[t]);
+          else
+            terminal_eval(P, term, xs_[N].data(), derivs, e[N]);
+        }
+        catch (const std::exception & ex)
+        {
+#pragma omp critical
+          err = ex.what();
+        }
       }
-      terminal_eval(P, term, xs_[N].data(), derivs, e[N]);
-      cost += e[N].cost;
+      if (!err.empty())
+        throw std::runtime_error(err);
+      double cost = 0;
+      for (int t = 0; t <= N; t++)
+        cost += e[t].cost;
       return cost;
     }
 
@@ -715,7 +752,9 @@ namespace orc
       for (; info.num_iters < max_iters;)
       {
         // linearise at the current iterate (values + derivatives), multipliers, merit
+        double tm0 = now();
         double cost = evaluate(xs, us, true, ev);
+        timers[0] += now() - tm0;
         for (int t = 0; t < N; t++)
         {
           xdots[t] = ev[t].xdot;
@@ -743,9 +782,13 @@ namespace orc
           return true;
         }
         // Newton step of the proximal subproblem
+        tm0 = now();
         if (!riccati_backward(knots, ndx, nu, mu, mu, sol).ok)
           info.flags |= 1;
+        timers[1] += now() - tm0;
+        tm0 = now();
         riccati_forward(knots, sol, ndx, nu, mu, dxs, dus, vnew, lnew);
+        timers[2] += now() - tm0;
         if (inner_crit <= inner_tol)
           return true;
         // directional derivative of the merit: gradient with the first-order multipliers lam_plus, nu_plus
@@ -787,6 +830,7 @@ namespace orc
           return tm.merit;
         };
         double phi_new;
+        tm0 = now();
         while (true)
         {
           phi_new = try_step(alpha);
@@ -796,6 +840,7 @@ namespace orc
             break;
           alpha = std::max(alpha * opt.ls_contraction, opt.ls_alpha_min);
         }
+        timers[3] += now() - tm0;
         // accept
         for (int t = 0; t <= N; t++)
         {

@@ -871,7 +871,7 @@ namespace smpc
           c = s.v[jf][sub] + wxp[sub];
         }
         else
-          c = s.fp[f][2] - slot.foot_ref[f][9 + 2];
+          c = s.fp[f][2] - slot.land_z[f];
         s.cval[row] = c;
         s.lo[row] = lo;
         s.hi[row] = hi;

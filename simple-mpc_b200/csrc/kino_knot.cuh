@@ -1006,7 +1006,7 @@ namespace smpc
       else if (kind == ROW_VEL)
         c = s.vf[f][s.rsub[row]];
       else
-        c = s.fp[f][2] - slot.foot_ref[f][9 + 2];
+        c = s.fp[f][2] - slot.land_z[f];
       const double z = c + mu * io.prev_vs[row];
       int act;
       const double pr = ncone_proj(type, z, lo, hi, act);
@@ -1369,7 +1369,7 @@ namespace smpc
     }
     SMPC_END
     // DCM rows: c + tau cdot - ref
-    const double tau = sqrt(tm.com_ref[2] / 9.81); // reference src/kinodynamics.cpp:372
+    const double tau = tm.tau; // fixed at createTerminalConstraint (reference src/kinodynamics.cpp:372); updateTerminalConstraint only moves com_ref
     SMPC_PAR(tid)
     {
       for (int row = tid; row < nct; row += SMPC_NT)

@@ -1,0 +1,6 @@
+// full-dynamics knots, 12-DoF quadruped with point feet (Go2 / Solo12 shape)
+#include "knot_kernels.cuh"
+namespace smpc
+{
+  int setup_knots_full_go2(smpc_ctx * c) { return setup_knots_full<FullCfg<13, 18, 4>, KinoCfg<13, 18, 4, 3>>(c); }
+} // namespace smpc

@@ -50,3 +50,16 @@
 #define SMPC_END }
 #define __restrict__
 #endif
+
+// two consecutive doubles from a 16-byte aligned shared address in one LDS.128
+SMPC_DEV void ld2(const double * p, double & a, double & b)
+{
+#ifdef __CUDACC__
+  const double2 v = *reinterpret_cast<const double2 *>(p);
+  a = v.x;
+  b = v.y;
+#else
+  a = p[0];
+  b = p[1];
+#endif
+}

@@ -1,7 +1,7 @@
-// riccati3.cuh — proximal Riccati backward sweep, third layout (supersedes riccati2.cuh on the hot path).
+// riccati3.cuh — proximal Riccati backward sweep, compile-time shapes, TMA-staged knots.
 //
 // Same recursion and same per-element operation order as oracle/orc_solver.hpp (see riccati.cuh for the
-// algebra), so it stays bitwise equal to the oracle on identical knots. What changed against riccati2.cuh,
+// algebra), so it stays bitwise equal to the oracle on identical knots. What it does beyond the generic sweep of riccati.cuh,
 // each item answering a line of profiles/r01a_ncu_summary.md:
 //   * stage data arrive by ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) of the whole dense
 //     knot (Q S R q r A B f C D d are contiguous in HBM) into shared memory, issued at the top of the stage
@@ -22,7 +22,6 @@
 #pragma once
 #include "par.cuh"
 #include "dev_types.h"
-#include "riccati2.cuh" // ld2
 
 namespace smpc
 {

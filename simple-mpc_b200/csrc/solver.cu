@@ -10,79 +10,25 @@
 //
 // There is NO CPU fallback: every entry point that computes fails with SMPC_ERR_CUDA if the
 // CUDA runtime does.
-#include "kino_knot.cuh"
-#include "centro_knot.cuh"
-#include "full_knot.cuh"
-#include "riccati.cuh"
-#include "riccati2.cuh"
-#include "riccati3.cuh"
-#include "riccati_fwd.cuh"
-#include "mpc_driver.cuh"
+#include "ctx.h"
 #include "host_build.h"
-#include <cuda_runtime.h>
-#include <cstdio>
-#include <cstdlib>
-#include <string>
-#include <vector>
 
 using namespace smpc;
 
+#ifndef SMPC_FWD_STAGED_MAX_WAVES
+#define SMPC_FWD_STAGED_MAX_WAVES 5
+#endif
+namespace smpc
+{
+  std::string & err()
+  {
+    thread_local std::string e;
+    return e;
+  }
+} // namespace smpc
+
 namespace
 {
-  thread_local std::string g_err;
-
-  enum Phase
-  {
-    PH_DONE = 0,
-    PH_ACTIVE = 1,    // needs a linearisation
-    PH_NEED_STEP = 2, // linearised, Newton step wanted
-    PH_LS = 3         // step computed, linesearch pending
-  };
-
-  struct Dims
-  {
-    int B, N, nx, ndx, nu, ncmax, nk;
-  };
-
-  // device array pointers, passed by value to the kernels
-  struct Arrays
-  {
-    Dims dm;
-    KnotLayout L;
-    SolLayout SL;
-    RicSmem RS;
-    FwdSmem FS;
-    const DevModel * model;
-    const DevOcp * ocp;
-    smpc_solver_opts opt;
-    smpc_slot * slots;   // [B][N] ring buffer, head in InstState
-    smpc_slot * table;   // stage table (the cycle horizon of MPC::generateCycleHorizon), ntable entries
-    int ntable;
-    smpc_terminal * term; // [B]
-    double *x0, *xs, *us, *vs, *lams, *prev_vs, *prev_lams, *txs, *tus;
-    double * knots;
-    int * ncs;
-    double *sol, *P0;
-    double *gx, *gu, *lplus;
-    double *dxs, *dus, *vnew, *lnew;
-    KnotScalars *sc, *sct;
-    double *xdot, *xdott;
-    double *fc, *fct; // contact forces of the last evaluation / trial [B][N][nk * 3] (full dynamics; else null)
-    InstState * inst;
-    int * counters; // [0] linesearch pending, [1] instances that need another round, [2] driver queue overflows
-    // batched MPC driver (mpc_driver.cuh); null until smpc_mpc_setup
-    MpcShared * mpcS;
-    MpcInst * mpcI;
-    int * mpc_ids;  // [B] stage-table index of the tail each instance appends this tick
-    double * xmeas; // [B][nq + nv] measured multibody states
-    int nxm, ncycle;
-  };
-
-  __device__ __forceinline__ const smpc_slot & slot_at(const Arrays & A, const InstState & st, int b, int t)
-  {
-    return A.slots[(size_t)b * A.dm.N + (st.head + t) % A.dm.N];
-  }
-
   // ------------------------------------------------------------------------------------------
   // kernels
   // ------------------------------------------------------------------------------------------
@@ -118,137 +64,19 @@ namespace
     }
   }
 
-  // global-memory view of knot (b, t) for the linearisation (TRIAL = false) or a linesearch trial
-  template <bool TRIAL>
-  __device__ __forceinline__ void make_knot_io(const Arrays & A, const InstState & st, int b, int t, KnotIO & io, int * nc_dummy)
-  {
-    const Dims & d = A.dm;
-    const size_t xb = (size_t)b * (d.N + 1);
-    io.x = A.xs + (xb + t) * d.nx;
-    io.u = (t < d.N) ? A.us + ((size_t)b * d.N + t) * d.nu : nullptr;
-    io.xn = (t < d.N) ? A.xs + (xb + t + 1) * d.nx : nullptr;
-    if (TRIAL)
-    {
-      io.dx = A.dxs + (xb + t) * d.ndx;
-      io.du = (t < d.N) ? A.dus + ((size_t)b * d.N + t) * d.nu : nullptr;
-      io.dxn = (t < d.N) ? A.dxs + (xb + t + 1) * d.ndx : nullptr;
-      io.alpha = st.alpha;
-      io.tx = A.txs + (xb + t) * d.nx;
-      io.tu = (t < d.N) ? A.tus + ((size_t)b * d.N + t) * d.nu : nullptr;
-    }
-    else
-    {
-      io.dx = io.du = io.dxn = nullptr;
-      io.alpha = 0;
-      io.tx = io.tu = nullptr;
-    }
-    io.slot = (t < d.N) ? &slot_at(A, st, b, t) : nullptr;
-    io.term = A.term + b;
-    io.vs = A.vs + (xb + t) * d.ncmax;
-    io.prev_vs = A.prev_vs + (xb + t) * d.ncmax;
-    io.lam_t = A.lams + (xb + t) * d.ndx;
-    io.lam_n = (t < d.N) ? A.lams + (xb + t + 1) * d.ndx : nullptr;
-    io.prev_lam_n = (t < d.N) ? A.prev_lams + (xb + t + 1) * d.ndx : nullptr;
-    io.mu = st.mu;
-    io.preg = st.preg;
-    io.knot = A.knots + (xb + t) * A.L.size;
-    io.nc_out = TRIAL ? nc_dummy : A.ncs + xb + t;
-    io.gx = A.gx + (xb + t) * d.ndx;
-    io.gu = (t < d.N) ? A.gu + ((size_t)b * d.N + t) * d.nu : nullptr;
-    io.lplus_n = (t < d.N) ? A.lplus + (xb + t + 1) * d.ndx : nullptr;
-    io.xdot = (t < d.N) ? (TRIAL ? A.xdott : A.xdot) + ((size_t)b * d.N + t) * d.ndx : nullptr;
-    io.fc = (t < d.N && A.fc) ? (TRIAL ? A.fct : A.fc) + ((size_t)b * d.N + t) * d.nk * 3 : nullptr;
-    io.sc = (TRIAL ? A.sct : A.sc) + xb + t;
-  }
-
-  // kinodynamics: one warp per knot. The kernels are latency-bound and their throughput follows the resident warps per SM
-  // (6 -> 8 warps: 1.33x, profiles/r01e vs r01f). A one-warp CTA lives on one SM sub-partition (16 K registers), so the
-  // steps are 2 warps per sub-partition (<= 255 registers), 3 (<= 168) and 4 (<= 128). Linearisation kernel: 22.2 KB of
-  // scratch allow 10 CTAs/SM; at 168 registers (72 bytes of spills) that measures 53.3 ms per tick against 53.8 ms for
-  // 8 CTAs/SM at 254 registers (B = 4096), so 10 is the default.
-#ifndef SMPC_KNOT_MINB
-#define SMPC_KNOT_MINB 10
-#endif
-// the value-only (trial) instantiation needs 13.7 KB of the scratch and no spills at 168 registers: three warps per
-// SM sub-partition (measured: 10 CTAs/SM 55.3 vs 8 CTAs/SM 55.8 ms per tick before the scratch was split)
-#ifndef SMPC_KNOT_MINB_TRIAL
-#define SMPC_KNOT_MINB_TRIAL 12
-#endif
-  template <class Cfg, bool TRIAL>
-#ifdef SMPC_KNOT_MAXREG
-  __global__ void __maxnreg__(SMPC_KNOT_MAXREG) k_knots(Arrays A)
-#else
-  __global__ void __launch_bounds__(32, (TRIAL ? SMPC_KNOT_MINB_TRIAL : SMPC_KNOT_MINB)) k_knots(Arrays A)
-#endif
-  {
-    extern __shared__ __align__(16) double smem_raw[];
-    KinoScratch<Cfg> & s = *reinterpret_cast<KinoScratch<Cfg> *>(smem_raw);
-    const Dims & d = A.dm;
-    const int b = blockIdx.x / (d.N + 1);
-    const int t = blockIdx.x % (d.N + 1);
-    const InstState & st = A.inst[b];
-    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
-      return;
-    KnotIO io;
-    int nc_dummy;
-    make_knot_io<TRIAL>(A, st, b, t, io, &nc_dummy);
-    if (t < d.N)
-      kino_stage_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, s);
-    else
-      kino_terminal_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, s);
-  }
-
-  // centroidal: one warp per knot
-  template <class Cfg, bool TRIAL>
-  __global__ void __launch_bounds__(32) k_knots_centro(Arrays A)
-  {
-    extern __shared__ __align__(16) double smem_raw[];
-    CentroScratch<Cfg> & s = *reinterpret_cast<CentroScratch<Cfg> *>(smem_raw);
-    const Dims & d = A.dm;
-    const int b = blockIdx.x / (d.N + 1);
-    const int t = blockIdx.x % (d.N + 1);
-    const InstState & st = A.inst[b];
-    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
-      return;
-    KnotIO io;
-    int nc_dummy;
-    make_knot_io<TRIAL>(A, st, b, t, io, &nc_dummy);
-    if (t < d.N)
-      centro_stage_knot<Cfg, !TRIAL>(*A.ocp, A.L, io, s);
-    else
-      centro_terminal_knot<Cfg, !TRIAL>(*A.ocp, A.L, io, s);
-  }
-
-  // full dynamics: one CTA per knot; the terminal node is the kinodynamics one (same terminal cost / constraint,
-  // reference src/fulldynamics.cpp:418-445 vs src/kinodynamics.cpp:352-377)
-  template <class Cfg, class TermCfg, bool TRIAL>
-  __global__ void __launch_bounds__(128) k_knots_full(Arrays A)
-  {
-    extern __shared__ __align__(16) double smem_raw[];
-    const Dims & d = A.dm;
-    const int b = blockIdx.x / (d.N + 1);
-    const int t = blockIdx.x % (d.N + 1);
-    const InstState & st = A.inst[b];
-    if (st.phase != (TRIAL ? PH_LS : PH_ACTIVE))
-      return;
-    KnotIO io;
-    int nc_dummy;
-    make_knot_io<TRIAL>(A, st, b, t, io, &nc_dummy);
-    if (t < d.N)
-      full_stage_knot<Cfg, !TRIAL>(*A.model, *A.ocp, A.L, io, *reinterpret_cast<FullScratch<Cfg> *>(smem_raw));
-    else
-      kino_terminal_knot<TermCfg, !TRIAL>(*A.model, *A.ocp, A.L, io, *reinterpret_cast<KinoScratch<TermCfg> *>(smem_raw));
-  }
-
   // per-instance reductions and the ProxDDP control flow between linearisation and the Newton step
   __global__ void k_decide(Arrays A)
   {
     const int b = blockIdx.x;
     const Dims & d = A.dm;
     InstState & st = A.inst[b];
-    if (st.phase != PH_ACTIVE)
+    // the phase is read ONCE per CTA before thread 0 rewrites it below (a late warp must not see the new value)
+    __shared__ int copy_prev, s_phase;
+    if (threadIdx.x == 0)
+      s_phase = st.phase;
+    __syncthreads();
+    if (s_phase != PH_ACTIVE)
       return;
-    __shared__ int copy_prev;
     if (threadIdx.x == 0)
     {
       const smpc_solver_opts & o = A.opt;
@@ -326,66 +154,6 @@ namespace
       st.flags |= 1;
   }
 
-#ifndef SMPC_RIC_MINB
-#define SMPC_RIC_MINB 2
-#endif
-  template <int NDX, int NU, int NC>
-  __global__ void __launch_bounds__(128, SMPC_RIC_MINB) k_riccati2(Arrays A)
-  {
-    extern __shared__ __align__(16) double smem_raw[];
-    const int b = blockIdx.x;
-    const Dims & d = A.dm;
-    InstState & st = A.inst[b];
-    if (st.phase != PH_NEED_STEP)
-      return;
-    const size_t xb = (size_t)b * (d.N + 1);
-    __shared__ int flag;
-    riccati2_backward_inst<NDX, NU, NC>(
-      A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
-      A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
-    if (threadIdx.x == 0 && flag)
-      st.flags |= 1;
-  }
-
-#ifndef SMPC_RIC3_TPB
-#define SMPC_RIC3_TPB 128
-#endif
-#ifndef SMPC_FWD_STAGED_MAX_WAVES
-#define SMPC_FWD_STAGED_MAX_WAVES 5
-#endif
-// per-instance sweep time with 1, 2, 3 CTAs per SM (ms at T = 50; only the ratios matter), see ric3_pick_ctas
-#ifndef SMPC_RIC_T1
-#define SMPC_RIC_T1 2.41
-#define SMPC_RIC_T2 2.78
-#define SMPC_RIC_T3 3.20
-#endif
-  // resident CTAs per SM the shared-memory footprint allows (228 KB per SM, 1 KB reserved per CTA): the register
-  // budget follows it (3 CTAs x 128 threads -> 168 registers, no spills worth naming: ptxas reports 56 bytes)
-  template <int NDX, int NU, int NC, int TPB>
-  constexpr int ric3_ctas_per_sm()
-  {
-    return (233472 / (Ric3<NDX, NU, NC>::SIZE * 8 + 1024 + 16) >= 3 && TPB == 128) ? 3 : (TPB == 128 ? SMPC_RIC_MINB : 1);
-  }
-  // TPB = 128: throughput variant (three CTAs per SM). TPB = 256: latency variant for batches of at most one instance
-  // per SM - twice the threads on the products and trailing updates of one instance, the whole register file to itself.
-  template <int NDX, int NU, int NC, int TPB>
-  __global__ void __launch_bounds__(TPB, (ric3_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati3(Arrays A)
-  {
-    extern __shared__ __align__(16) double smem_raw[];
-    const int b = blockIdx.x;
-    const Dims & d = A.dm;
-    InstState & st = A.inst[b];
-    if (st.phase != PH_NEED_STEP)
-      return;
-    const size_t xb = (size_t)b * (d.N + 1);
-    __shared__ int flag;
-    riccati3_backward_inst<NDX, NU, NC, TPB>(
-      A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
-      A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
-    if (threadIdx.x == 0 && flag)
-      st.flags |= 1;
-  }
-
   // shared tail of the two forward kernels: linesearch initialisation
   __device__ __forceinline__ void forward_epilogue(const Arrays & A, InstState & st, double dphi)
   {
@@ -443,14 +211,18 @@ namespace
     const int b = blockIdx.x;
     const Dims & d = A.dm;
     InstState & st = A.inst[b];
-    if (st.phase != PH_LS)
+    // the phase is read ONCE per CTA before thread 0 rewrites it below (a late warp must not see the new value)
+    __shared__ int accept, s_phase;
+    __shared__ double s_alpha;
+    if (threadIdx.x == 0)
+      s_phase = st.phase;
+    __syncthreads();
+    if (s_phase != PH_LS)
     {
-      if (threadIdx.x == 0 && st.phase == PH_ACTIVE)
+      if (threadIdx.x == 0 && s_phase == PH_ACTIVE)
         atomicAdd(A.counters + 1, 1);
       return;
     }
-    __shared__ int accept;
-    __shared__ double s_alpha;
     if (threadIdx.x == 0)
     {
       const smpc_solver_opts & o = A.opt;
@@ -788,232 +560,12 @@ namespace
   }
 } // namespace
 
-// ------------------------------------------------------------------------------------------------
-// context
-// ------------------------------------------------------------------------------------------------
-struct smpc_ctx
-{
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  Arrays A{};
-  DevModel hmodel;
-  DevOcp hocp;
-  int hmodel_sms = 0; // SM count of the device
-  bool forward_staged = true;
-  std::vector<void *> allocs;
-  int * h_counters = nullptr; // pinned
-  void * staging = nullptr;   // device staging for host<->device conversions
-  size_t staging_bytes = 0;
-  void * h_staging = nullptr; // pinned host staging
-  size_t h_staging_bytes = 0;
-  cudaEvent_t ev0, ev1, evr0, evr1;
-  float last_ms = 0, last_ric_ms = 0;
-  double acc_ric_ms = 0, acc_solve_ms = 0; // accumulated since smpc_timer_reset
-  int64_t acc_ric_launches = 0, acc_solves = 0;
-  cudaEvent_t evu0, evu1; // user timer on the context stream
-  int64_t launches = 0;
-  size_t knot_smem = 0, ric_smem = 0;
-  int knot_threads = 32;
-  void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
-  void (*launch_riccati)(smpc_ctx *) = nullptr;
-  const char * riccati_variant = "generic";
-  std::vector<smpc_slot> h_table; // host copy of the stage table (contact masks drive the driver's bookkeeping)
-  MpcShared h_mpc;
-  bool mpc_ready = false;
-};
-
-#define CU(call)                                                                                                       \
-  do                                                                                                                   \
-  {                                                                                                                    \
-    cudaError_t e_ = (call);                                                                                           \
-    if (e_ != cudaSuccess)                                                                                             \
-    {                                                                                                                  \
-      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                                      \
-      return SMPC_ERR_CUDA;                                                                                            \
-    }                                                                                                                  \
-  } while (0)
-
 namespace
 {
-  template <class Cfg>
-  void launch_knots_impl(smpc_ctx * c, bool trial)
-  {
-    const Dims & d = c->A.dm;
-    const int grid = d.B * (d.N + 1);
-    if (trial)
-      k_knots<Cfg, true><<<grid, c->knot_threads, kino_trial_bytes<Cfg>(), c->stream>>>(c->A); // value-only scratch prefix
-    else
-      k_knots<Cfg, false><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
-    c->launches++;
-  }
-  template <class Cfg>
-  int setup_knots(smpc_ctx * c)
-  {
-    c->knot_smem = sizeof(KinoScratch<Cfg>);
-    c->knot_threads = 32; // one warp per knot: phase barriers are warp syncs (64 / 128 threads measured slower, profiles/r01a)
-    CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
-    CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
-    CU(cudaFuncSetAttribute(k_knots<Cfg, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_knots<Cfg, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->launch_knots = &launch_knots_impl<Cfg>;
-    if (getenv("SMPC_VERBOSE"))
-    {
-      int nl = 0, nt = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_knots<Cfg, false>, c->knot_threads, c->knot_smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt, k_knots<Cfg, true>, c->knot_threads, kino_trial_bytes<Cfg>());
-      fprintf(stderr, "smpc: k_knots %zu B shared memory per knot, resident CTAs per SM: lin %d, trial %d\n", c->knot_smem, nl, nt);
-    }
-    return SMPC_OK;
-  }
-
-  template <class Cfg>
-  void launch_knots_centro_impl(smpc_ctx * c, bool trial)
-  {
-    const Dims & d = c->A.dm;
-    const int grid = d.B * (d.N + 1);
-    if (trial)
-      k_knots_centro<Cfg, true><<<grid, 32, c->knot_smem, c->stream>>>(c->A);
-    else
-      k_knots_centro<Cfg, false><<<grid, 32, c->knot_smem, c->stream>>>(c->A);
-    c->launches++;
-  }
-  template <class Cfg>
-  int setup_knots_centro(smpc_ctx * c)
-  {
-    c->knot_smem = sizeof(CentroScratch<Cfg>);
-    CU(cudaFuncSetAttribute(k_knots_centro<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
-    CU(cudaFuncSetAttribute(k_knots_centro<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
-    c->launch_knots = &launch_knots_centro_impl<Cfg>;
-    return SMPC_OK;
-  }
-
-  template <class Cfg, class TermCfg>
-  void launch_knots_full_impl(smpc_ctx * c, bool trial)
-  {
-    const Dims & d = c->A.dm;
-    const int grid = d.B * (d.N + 1);
-    if (trial)
-      k_knots_full<Cfg, TermCfg, true><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
-    else
-      k_knots_full<Cfg, TermCfg, false><<<grid, c->knot_threads, c->knot_smem, c->stream>>>(c->A);
-    c->launches++;
-  }
-  template <class Cfg, class TermCfg>
-  int setup_knots_full(smpc_ctx * c)
-  {
-    c->knot_smem = sizeof(FullScratch<Cfg>) > sizeof(KinoScratch<TermCfg>) ? sizeof(FullScratch<Cfg>) : sizeof(KinoScratch<TermCfg>);
-    c->knot_threads = 64;
-    if (const char * e = getenv("SMPC_KNOT_THREADS"))
-      c->knot_threads = atoi(e) == 32 ? 32 : (atoi(e) == 128 ? 128 : 64);
-    CU(cudaFuncSetAttribute(k_knots_full<Cfg, TermCfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
-    CU(cudaFuncSetAttribute(k_knots_full<Cfg, TermCfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->knot_smem));
-    c->launch_knots = &launch_knots_full_impl<Cfg, TermCfg>;
-    return SMPC_OK;
-  }
-
   void launch_riccati_generic(smpc_ctx * c)
   {
     k_riccati<<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
   }
-  template <int NDX, int NU, int NC>
-  void launch_riccati2_impl(smpc_ctx * c)
-  {
-    k_riccati2<NDX, NU, NC><<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
-  }
-  template <int NDX, int NU, int NC>
-  int setup_riccati2(smpc_ctx * c)
-  {
-    c->ric_smem = (size_t)Ric2<NDX, NU, NC>::SIZE * sizeof(double);
-    CU(cudaFuncSetAttribute(k_riccati2<NDX, NU, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
-    c->launch_riccati = &launch_riccati2_impl<NDX, NU, NC>;
-    c->riccati_variant = "specialised";
-    return SMPC_OK;
-  }
-
-  // Wave model of the Riccati launch: an instance takes t[k] when k CTAs share its SM (measured on B200 for the
-  // (36, 24, 24) sweep, relative units); `batch` instances run as full waves of k * sms CTAs plus a remainder that
-  // runs at the occupancy it reaches.
-  int ric3_pick_ctas(int batch, int sms, int fit)
-  {
-    static const double t[4] = {0.0, SMPC_RIC_T1, SMPC_RIC_T2, SMPC_RIC_T3};
-    if (fit > 3)
-      fit = 3;
-    if (sms <= 0 || fit < 1)
-      return fit;
-    int best = fit;
-    double best_time = 1e300;
-    for (int k = fit; k >= 1; k--)
-    {
-      const int per_wave = k * sms;
-      const int full = batch / per_wave, rem = batch % per_wave;
-      const int krem = (rem + sms - 1) / sms;
-      const double time = full * t[k] + (rem ? t[krem] : 0.0);
-      if (time < best_time - 1e-12)
-      {
-        best_time = time;
-        best = k;
-      }
-    }
-    return best;
-  }
-
-  template <int NDX, int NU, int NC, int TPB>
-  void launch_riccati3_impl(smpc_ctx * c)
-  {
-    k_riccati3<NDX, NU, NC, TPB><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
-  }
-  template <int NDX, int NU, int NC, int TPB>
-  int finish_setup_riccati3(smpc_ctx * c)
-  {
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB>;
-    c->riccati_variant = TPB == 128 ? "tma-staged" : "tma-staged-256";
-    if (getenv("SMPC_VERBOSE"))
-    {
-      int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC, TPB>, TPB, c->ric_smem);
-      fprintf(stderr, "smpc: k_riccati3 (%d threads) %zu B shared memory per instance, resident CTAs per SM: %d\n", TPB, c->ric_smem, nb);
-    }
-    return SMPC_OK;
-  }
-  template <int NDX, int NU, int NC>
-  int setup_riccati3(smpc_ctx * c)
-  {
-    typedef Ric3<NDX, NU, NC> R;
-    const KnotLayout & L = c->A.L;
-    if (L.oQ != R::kQ || L.oS != R::kS || L.oR != R::kR || L.oq != R::kq || L.or_ != R::kr || L.oA != R::kA || L.oB != R::kB
-        || L.of != R::kf || L.oC != R::kC || L.oD != R::kD || L.od != R::kd || L.size != R::KSIZE)
-    {
-      g_err = "riccati3: compile-time knot layout differs from make_knot_layout";
-      return SMPC_ERR_INVALID;
-    }
-    c->ric_smem = (size_t)R::SIZE * sizeof(double);
-    // Resident CTAs per SM. The footprint allows `fit`; a batch that does not fill whole waves at that occupancy can
-    // finish sooner at a lower one (512 instances on 148 SMs: 444 + 68 at three per SM, 296 + 216 at two), because a
-    // CTA runs faster the fewer neighbours share its SM. ric3_pick_ctas() minimises the wave model below; the
-    // occupancy is imposed by asking for more dynamic shared memory than the kernel uses. SMPC_RIC_CTAS overrides.
-    {
-      const int fit = (int)(233472 / (c->ric_smem + 1024 + 16));
-      int want = ric3_pick_ctas(c->A.dm.B, c->hmodel_sms, fit);
-      if (const char * e = getenv("SMPC_RIC_CTAS"))
-        want = atoi(e);
-      if (want >= 1 && want < fit)
-      {
-        size_t req = (size_t)233472 / want - 1024 - 16;
-        req &= ~(size_t)15;
-        if (req > 232448 - 16)
-          req = 232448 - 16;
-        c->ric_smem = req;
-      }
-    }
-    // latency variant when no SM holds more than one instance (SMPC_RIC3_TPB forces one of the two)
-    bool wide = c->hmodel_sms > 0 && c->A.dm.B <= c->hmodel_sms;
-    if (const char * e = getenv("SMPC_RIC3_TPB"))
-      wide = atoi(e) == 256;
-    return wide ? finish_setup_riccati3<NDX, NU, NC, 256>(c) : finish_setup_riccati3<NDX, NU, NC, 128>(c);
-  }
-
   template <class T>
   int dev_alloc(smpc_ctx * c, T ** p, size_t n)
   {
@@ -1046,7 +598,7 @@ namespace
   {
     if (!c || first < 0 || n < 0 || first + n > c->A.dm.B)
     {
-      g_err = "instance range out of bounds";
+      smpc::err() = "instance range out of bounds";
       return SMPC_ERR_INVALID;
     }
     return 0;
@@ -1066,7 +618,7 @@ namespace
 
 extern "C" {
 
-const char * smpc_last_error(void) { return g_err.c_str(); }
+const char * smpc_last_error(void) { return smpc::err().c_str(); }
 
 void smpc_default_solver_opts(smpc_solver_opts * o)
 {
@@ -1099,7 +651,7 @@ int smpc_problem_dims(const smpc_model_desc * m, const smpc_ocp_desc * o, int * 
 {
   if (!m || !o)
   {
-    g_err = "null descriptor";
+    smpc::err() = "null descriptor";
     return SMPC_ERR_INVALID;
   }
   const int fs = o->force_size;
@@ -1123,14 +675,29 @@ int smpc_problem_dims(const smpc_model_desc * m, const smpc_ocp_desc * o, int * 
   return SMPC_OK;
 }
 
+static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_solver_opts * opts);
+
 int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_solver_opts * opts)
 {
   if (!out || !model || !ocp || !opts || batch < 1)
   {
-    g_err = "smpc_create: bad arguments";
+    smpc::err() = "smpc_create: bad arguments";
     return SMPC_ERR_INVALID;
   }
   smpc_ctx * c = new smpc_ctx;
+  // every failure below releases what was acquired so far (device allocations, stream, events, pinned memory)
+  const int rc = create_impl(c, device, batch, model, ocp, opts);
+  if (rc != SMPC_OK)
+  {
+    smpc_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SMPC_OK;
+}
+
+static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_solver_opts * opts)
+{
   try
   {
     build_dev_model(*model, c->hmodel);
@@ -1138,16 +705,14 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   }
   catch (const std::exception & e)
   {
-    g_err = e.what();
-    const bool unsup = g_err.find("CUDA") != std::string::npos || g_err.find("supported") != std::string::npos;
-    delete c;
+    smpc::err() = e.what();
+    const bool unsup = smpc::err().find("CUDA") != std::string::npos || smpc::err().find("supported") != std::string::npos;
     return unsup ? SMPC_ERR_UNSUPPORTED : SMPC_ERR_INVALID;
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
   {
-    g_err = "no CUDA device: libsmpc_cuda has no CPU fallback";
-    delete c;
+    smpc::err() = "no CUDA device: libsmpc_cuda has no CPU fallback";
     return SMPC_ERR_CUDA;
   }
   c->device = device;
@@ -1171,46 +736,34 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
       c->forward_staged = strcmp(e, "direct") != 0;
   }
   A.opt = *opts;
-  // kernel instantiation for this (robot, problem) shape
+  // kernel instantiation for this (robot, problem) shape; each family lives in its own translation unit
   int rc = SMPC_ERR_UNSUPPORTED;
-  if (O.kind == SMPC_OCP_KINODYNAMICS && model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3)
-    rc = setup_knots<KinoCfg<13, 18, 4, 3>>(c);
-  else if (O.kind == SMPC_OCP_FULLDYNAMICS && model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3)
-    rc = setup_knots_full<FullCfg<13, 18, 4>, KinoCfg<13, 18, 4, 3>>(c);
-  else if (O.kind == SMPC_OCP_CENTROIDAL && O.nk == 2 && O.fs == 6)
-    rc = setup_knots_centro<CentroCfg<2, 6>>(c);
-  else if (O.kind == SMPC_OCP_CENTROIDAL && O.nk == 4 && O.fs == 3)
-    rc = setup_knots_centro<CentroCfg<4, 3>>(c);
+  const bool go2_shape = model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3;
+  if (O.kind == SMPC_OCP_KINODYNAMICS && go2_shape)
+    rc = setup_knots_kino_go2(c);
+  else if (O.kind == SMPC_OCP_FULLDYNAMICS && go2_shape)
+    rc = setup_knots_full_go2(c);
+  else if (O.kind == SMPC_OCP_CENTROIDAL && ((O.nk == 2 && O.fs == 6) || (O.nk == 4 && O.fs == 3)))
+    rc = setup_knots_centro(c);
   else
-    g_err = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics and full dynamics on a 12-DoF quadruped with "
-            "point feet; centroidal with 2 quad feet or 4 point feet)";
+    smpc::err() = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics and full dynamics on a 12-DoF quadruped with "
+                  "point feet; centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
-  {
-    delete c;
     return rc;
-  }
   // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax)
-  // SMPC_RICCATI=2 selects the previous specialised sweep (A/B timing), =0 the generic one
+  // SMPC_RICCATI=0 selects the generic sweep (A/B timing)
   const char * rv = getenv("SMPC_RICCATI");
   const int ric = rv ? atoi(rv) : 3;
-  if (ric == 3 && O.ndx == 36 && O.nu == 24 && O.ncmax == 24)
-    rc = setup_riccati3<36, 24, 24>(c);
-  else if (ric == 3 && O.ndx == 36 && O.nu == 24 && O.ncmax == 36)
-    rc = setup_riccati3<36, 24, 36>(c);
-  else if (ric >= 2 && O.ndx == 36 && O.nu == 24 && O.ncmax == 24)
-    rc = setup_riccati2<36, 24, 24>(c);
-  else if (ric >= 2 && O.ndx == 36 && O.nu == 24 && O.ncmax == 36)
-    rc = setup_riccati2<36, 24, 36>(c);
-  else
+  bool tuned = false;
+  if (ric == 3)
+    rc = setup_riccati_tuned(c, O.ndx, O.nu, O.ncmax, &tuned);
+  if (rc != SMPC_OK)
+    return rc;
+  if (!tuned)
   {
     c->ric_smem = (size_t)A.RS.size * sizeof(double);
     CU(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
     c->launch_riccati = &launch_riccati_generic;
-  }
-  if (rc != SMPC_OK)
-  {
-    delete c;
-    return rc;
   }
   const Dims & d = A.dm;
   const size_t B = d.B, N1 = d.N + 1;
@@ -1278,7 +831,6 @@ int smpc_create(smpc_ctx ** out, int device, int batch, const smpc_model_desc * 
   CU(cudaEventCreate(&c->evr1));
   CU(cudaEventCreate(&c->evu0));
   CU(cudaEventCreate(&c->evu1));
-  *out = c;
   return SMPC_OK;
 }
 
@@ -1297,12 +849,9 @@ void smpc_destroy(smpc_ctx * c)
     cudaFreeHost(c->h_staging);
   if (c->h_counters)
     cudaFreeHost(c->h_counters);
-  cudaEventDestroy(c->ev0);
-  cudaEventDestroy(c->ev1);
-  cudaEventDestroy(c->evr0);
-  cudaEventDestroy(c->evr1);
-  cudaEventDestroy(c->evu0);
-  cudaEventDestroy(c->evu1);
+  for (cudaEvent_t e : {c->ev0, c->ev1, c->evr0, c->evr1, c->evu0, c->evu1})
+    if (e)
+      cudaEventDestroy(e);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -1332,7 +881,7 @@ int smpc_set_slot(smpc_ctx * c, int first, int n, int t, const smpc_slot * slots
     return SMPC_ERR_INVALID;
   if (t < 0 || t >= c->A.dm.N)
   {
-    g_err = "Stage index exceeds stage vector size";
+    smpc::err() = "Stage index exceeds stage vector size";
     return SMPC_ERR_INVALID;
   }
   if (n == 0)
@@ -1399,10 +948,24 @@ int smpc_upload_stage_table(smpc_ctx * c, const smpc_slot * stages, int n)
 {
   if (!c || !stages || n < 1)
   {
-    g_err = "smpc_upload_stage_table: bad arguments";
+    smpc::err() = "smpc_upload_stage_table: bad arguments";
     return SMPC_ERR_INVALID;
   }
   CU(cudaSetDevice(c->device));
+  if (c->A.table)
+  {
+    // a new table replaces the previous one: release it
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < c->allocs.size(); i++)
+      if (c->allocs[i] == (void *)c->A.table)
+      {
+        cudaFree(c->allocs[i]);
+        c->allocs.erase(c->allocs.begin() + (long)i);
+        break;
+      }
+    c->A.table = nullptr;
+    c->A.ntable = 0;
+  }
   smpc_slot * tbl = nullptr;
   int rc = dev_alloc(c, &tbl, (size_t)n);
   if (rc != SMPC_OK)
@@ -1421,13 +984,13 @@ int smpc_cycle_ids(smpc_ctx * c, int first, int n, const int * ids)
     return SMPC_ERR_INVALID;
   if (!c->A.table)
   {
-    g_err = "smpc_cycle_ids: no stage table uploaded";
+    smpc::err() = "smpc_cycle_ids: no stage table uploaded";
     return SMPC_ERR_STATE;
   }
   for (int i = 0; i < n; i++)
     if (ids[i] < 0 || ids[i] >= c->A.ntable)
     {
-      g_err = "smpc_cycle_ids: stage id out of range";
+      smpc::err() = "smpc_cycle_ids: stage id out of range";
       return SMPC_ERR_INVALID;
     }
   if (n == 0)
@@ -1473,7 +1036,7 @@ int smpc_set_x0(smpc_ctx * c, const double * x0)
 {
   if (!c || !x0)
   {
-    g_err = "smpc_set_x0: null argument";
+    smpc::err() = "smpc_set_x0: null argument";
     return SMPC_ERR_INVALID;
   }
   CU(cudaSetDevice(c->device));
@@ -1486,7 +1049,7 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
 {
   if (!c)
   {
-    g_err = "smpc_solve: null context";
+    smpc::err() = "smpc_solve: null context";
     return SMPC_ERR_INVALID;
   }
   CU(cudaSetDevice(c->device));
@@ -1660,7 +1223,7 @@ int smpc_get_xdot(smpc_ctx * c, int first, int n, int t, double * xdot)
   const Dims & d = c->A.dm;
   if (t < 0 || t >= d.N)
   {
-    g_err = "Stage index exceeds stage vector size";
+    smpc::err() = "Stage index exceeds stage vector size";
     return SMPC_ERR_INVALID;
   }
   CU(cudaSetDevice(c->device));
@@ -1678,13 +1241,13 @@ int smpc_get_contact_forces(smpc_ctx * c, int first, int n, int t, double * forc
   if (!c->A.fc)
   {
     // reference include/simple-mpc/mpc.hpp:174-178: only defined for the full-dynamics handler
-    g_err = "getContactForces is only available for full-dynamics problems";
+    smpc::err() = "getContactForces is only available for full-dynamics problems";
     return SMPC_ERR_UNSUPPORTED;
   }
   const Dims & d = c->A.dm;
   if (t < 0 || t >= d.N || !forces)
   {
-    g_err = "smpc_get_contact_forces: stage index exceeds the horizon, or null output";
+    smpc::err() = "smpc_get_contact_forces: stage index exceeds the horizon, or null output";
     return SMPC_ERR_INVALID;
   }
   if (n == 0)
@@ -1716,24 +1279,24 @@ int smpc_mpc_setup(smpc_ctx * c, const smpc_mpc_settings * s, const int * phase,
 {
   if (!c || !s || !x_reference)
   {
-    g_err = "smpc_mpc_setup: null argument";
+    smpc::err() = "smpc_mpc_setup: null argument";
     return SMPC_ERR_INVALID;
   }
   if (c->h_table.empty())
   {
-    g_err = "smpc_mpc_setup: no stage table uploaded";
+    smpc::err() = "smpc_mpc_setup: no stage table uploaded";
     return SMPC_ERR_STATE;
   }
   const Dims & d = c->A.dm;
   const int ntable = (int)c->h_table.size();
   if (s->ncycle < 2 || s->ncycle > ntable || s->standing_id >= ntable || s->T_fly < 1 || s->T_contact < 0)
   {
-    g_err = "smpc_mpc_setup: ncycle / standing_id outside the stage table, or bad T_fly / T_contact";
+    smpc::err() = "smpc_mpc_setup: ncycle / standing_id outside the stage table, or bad T_fly / T_contact";
     return SMPC_ERR_INVALID;
   }
   if (s->ncycle < d.N)
   {
-    g_err = "smpc_mpc_setup: the cycle must be at least as long as the horizon (tile it as generateCycleHorizon does)";
+    smpc::err() = "smpc_mpc_setup: the cycle must be at least as long as the horizon (tile it as generateCycleHorizon does)";
     return SMPC_ERR_INVALID;
   }
   CU(cudaSetDevice(c->device));
@@ -1766,7 +1329,7 @@ int smpc_mpc_setup(smpc_ctx * c, const smpc_mpc_settings * s, const int * phase,
     const int p = phase ? phase[b] : 0;
     if (p < 0 || p >= s->ncycle)
     {
-      g_err = "smpc_mpc_setup: phase outside [0, ncycle)";
+      smpc::err() = "smpc_mpc_setup: phase outside [0, ncycle)";
       return SMPC_ERR_INVALID;
     }
     if (!have[(size_t)p])
@@ -1776,7 +1339,7 @@ int smpc_mpc_setup(smpc_ctx * c, const smpc_mpc_settings * s, const int * phase,
       mpc_init_queues(masks.data(), s->ncycle, d.nk, d.N, p, I);
       if (I.overflow)
       {
-        g_err = "smpc_mpc_setup: more than SMPC_MPC_QUEUE contact switches of one foot in the cycle";
+        smpc::err() = "smpc_mpc_setup: more than SMPC_MPC_QUEUE contact switches of one foot in the cycle";
         return SMPC_ERR_UNSUPPORTED;
       }
       I.walking = 1;
@@ -1804,7 +1367,7 @@ static int mpc_check(smpc_ctx * c, int first, int n, const char * what)
     return SMPC_ERR_INVALID;
   if (!c->mpc_ready)
   {
-    g_err = std::string(what) + ": smpc_mpc_setup has not been called";
+    smpc::err() = std::string(what) + ": smpc_mpc_setup has not been called";
     return SMPC_ERR_STATE;
   }
   return SMPC_OK;
@@ -1817,7 +1380,7 @@ int smpc_mpc_set_velocity_base(smpc_ctx * c, int first, int n, const double * vb
     return rc;
   if (!vb)
   {
-    g_err = "smpc_mpc_set_velocity_base: null argument";
+    smpc::err() = "smpc_mpc_set_velocity_base: null argument";
     return SMPC_ERR_INVALID;
   }
   if (n == 0)
@@ -1867,7 +1430,7 @@ int smpc_mpc_iterate(smpc_ctx * c, const double * x_meas, int max_iters)
     return rc;
   if (c->h_counters[2] != 0)
   {
-    g_err = "smpc_mpc_iterate: a take-off / landing queue overflowed (more than SMPC_MPC_QUEUE pending events of one foot)";
+    smpc::err() = "smpc_mpc_iterate: a take-off / landing queue overflowed (more than SMPC_MPC_QUEUE pending events of one foot)";
     return SMPC_ERR_UNSUPPORTED;
   }
   return SMPC_OK;
@@ -1881,7 +1444,7 @@ int smpc_mpc_xmeas_from_prediction(smpc_ctx * c)
   const Dims & d = c->A.dm;
   if (d.nx != c->A.nxm)
   {
-    g_err = "smpc_mpc_xmeas_from_prediction: the problem state is not the multibody state (centroidal OCP)";
+    smpc::err() = "smpc_mpc_xmeas_from_prediction: the problem state is not the multibody state (centroidal OCP)";
     return SMPC_ERR_UNSUPPORTED;
   }
   CU(cudaSetDevice(c->device));
@@ -1944,7 +1507,7 @@ int smpc_feedback_control(smpc_ctx * c, int first, int n, const double * x_meas,
     return SMPC_ERR_INVALID;
   if (!x_meas || !u)
   {
-    g_err = "smpc_feedback_control: null argument";
+    smpc::err() = "smpc_feedback_control: null argument";
     return SMPC_ERR_INVALID;
   }
   if (n == 0)
@@ -1972,7 +1535,7 @@ int smpc_interpolate_plan(smpc_ctx * c, int first, int n, double delay, double *
     return SMPC_ERR_INVALID;
   if (!(delay >= 0))
   {
-    g_err = "smpc_interpolate_plan: negative delay";
+    smpc::err() = "smpc_interpolate_plan: negative delay";
     return SMPC_ERR_INVALID;
   }
   if (n == 0)
@@ -2073,7 +1636,7 @@ int smpc_get_knot(smpc_ctx * c, int inst, int t, int * nc, double * knot_out /* 
   const Dims & d = c->A.dm;
   if (t < 0 || t > d.N)
   {
-    g_err = "bad knot index";
+    smpc::err() = "bad knot index";
     return SMPC_ERR_INVALID;
   }
   CU(cudaSetDevice(c->device));

@@ -1,5 +1,5 @@
-"""ctypes mirror of include/smpc.h plus synthetic robot / problem builders shared by the tests,
-bench.py and __graft_entry__.smoke().
+"""ctypes binding of the C ABI (include/smpc.h, libsmpc_cuda.so) plus the synthetic robot / problem builders
+used by bench.py, __graft_entry__.smoke() and the tests.
 
 The robots are SYNTHETIC: example-robot-data (Go2 / Talos URDF + SRDF) is not available in this
 environment, so `go2_like_model()` is a 12-DoF quadruped with Go2-like link lengths,
@@ -10,7 +10,7 @@ import ctypes as C
 import os
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 MAX_JOINTS, MAX_NV, MAX_NQ, MAX_NX, MAX_NDX, MAX_NU, MAX_FEET = 32, 32, 36, 64, 64, 40, 4
 KINO, FULL, CENT = 0, 1, 2
@@ -68,11 +68,12 @@ class Slot(C.Structure):
         ("contact_mask", C.c_uint32), ("land_mask", C.c_uint32),
         ("x_ref", C.c_double * MAX_NX), ("u_ref", C.c_double * MAX_NU),
         ("foot_ref", (C.c_double * 12) * MAX_FEET), ("f_ref", (C.c_double * 6) * MAX_FEET),
+        ("land_z", C.c_double * MAX_FEET),
     ]
 
 
 class Terminal(C.Structure):
-    _fields_ = [("x_ref", C.c_double * MAX_NX), ("com_ref", C.c_double * 3)]
+    _fields_ = [("x_ref", C.c_double * MAX_NX), ("com_ref", C.c_double * 3), ("tau", C.c_double)]
 
 
 class MpcSettings(C.Structure):
@@ -92,24 +93,6 @@ class SolveInfo(C.Structure):
 
 def _p(a):
     return a.ctypes.data_as(dbl_p)
-
-
-def load_oracle():
-    path = os.path.join(ROOT, "oracle", "liborc.so")
-    if not os.path.exists(path):
-        raise RuntimeError("oracle/liborc.so not built: run `make -C oracle` or __graft_entry__.build()")
-    lib = C.CDLL(path)
-    lib.orc_last_error.restype = C.c_char_p
-    return lib
-
-
-def load_emul():
-    path = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
-    if not os.path.exists(path):
-        raise RuntimeError("tests/host_emul/libemul.so not built: run __graft_entry__.build()")
-    lib = C.CDLL(path)
-    lib.emul_mpc_create.restype = C.c_void_p
-    return lib
 
 
 def load_cuda():
@@ -311,6 +294,7 @@ def centroidal_slot(m, ocp_bundle, foot_poses, x_ref9, contact_mask=None, force_
         R, p = foot_poses[f]
         s.foot_ref[f][:9] = np.asarray(R).ravel()
         s.foot_ref[f][9:] = p
+        s.land_z[f] = p[2]
     return s
 
 
@@ -425,6 +409,7 @@ def full_slot(m, ocp_bundle, foot_poses, contact_mask=None, land_mask=0):
         R, p = foot_poses[f]
         s.foot_ref[f][:9] = np.asarray(R).ravel()
         s.foot_ref[f][9:] = p
+        s.land_z[f] = p[2]
     return s
 
 
@@ -457,4 +442,5 @@ def standing_slot(m, ocp_bundle, foot_poses, contact_mask=None, land_mask=0, for
         R, p = foot_poses[f]
         s.foot_ref[f][:9] = np.asarray(R).ravel()
         s.foot_ref[f][9:] = p
+        s.land_z[f] = p[2]
     return s

@@ -36,6 +36,7 @@ namespace simple_mpc
         stm.slot.foot_ref[f][k] = pose.R[(size_t)k];
       for (int k = 0; k < 3; k++)
         stm.slot.foot_ref[f][9 + k] = pose.p[(size_t)k];
+      stm.slot.land_z[f] = pose.p[2]; // target of the landing-edge height equality, fixed at stage creation
       stm.contact_states.push_back(contact_phase.at(name));
       if (contact_phase.at(name))
         stm.slot.contact_mask |= 1u << f;
@@ -192,8 +193,10 @@ namespace simple_mpc
   {
     if (!problem_initialized_)
       throw std::runtime_error("Create problem first!");
+    // tau is fixed here (reference src/fulldynamics.cpp:432-445); updateTerminalConstraint only moves com_ref
     for (int k = 0; k < 3; k++)
       problem_->term_.com_ref[k] = com_ref[(size_t)k];
+    problem_->term_.tau = std::sqrt(com_ref[2] / 9.81);
     problem_->term_cstrs_ = {"dcm_position"};
     terminal_constraint_ = true;
   }

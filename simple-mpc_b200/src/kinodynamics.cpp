@@ -47,6 +47,7 @@ namespace simple_mpc
         stm.slot.foot_ref[f][k] = pose.R[(size_t)k];
       for (int k = 0; k < 3; k++)
         stm.slot.foot_ref[f][9 + k] = pose.p[(size_t)k];
+      stm.slot.land_z[f] = pose.p[2]; // target of the landing-edge height equality, fixed at stage creation
       if (contact_phase.at(name))
       {
         stm.slot.contact_mask |= 1u << f;
@@ -185,9 +186,11 @@ namespace simple_mpc
   {
     if (!problem_initialized_)
       throw std::runtime_error("Create problem first!");
-    // DCMPositionResidual(com_ref, tau = sqrt(com_ref[2] / 9.81)) = 0 ; the kernels derive tau from com_ref
+    // DCMPositionResidual(com_ref, tau = sqrt(com_ref[2] / 9.81)) = 0 ; tau is fixed here, updateTerminalConstraint
+    // (DCMres->setReference) only moves com_ref (reference src/kinodynamics.cpp:366-388)
     for (int k = 0; k < 3; k++)
       problem_->term_.com_ref[k] = com_ref[(size_t)k];
+    problem_->term_.tau = std::sqrt(com_ref[2] / 9.81);
     problem_->term_cstrs_ = {"dcm_position"};
     terminal_constraint_ = true;
   }

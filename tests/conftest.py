@@ -1,7 +1,9 @@
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "simple-mpc_b200", "python"))  # the product's ctypes binding
+sys.path.insert(0, HERE)
 
 
 def pytest_configure(config):

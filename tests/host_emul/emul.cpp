@@ -6,7 +6,6 @@
 #include "../../simple-mpc_b200/csrc/centro_knot.cuh"
 #include "../../simple-mpc_b200/csrc/full_knot.cuh"
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
-#include "../../simple-mpc_b200/csrc/riccati2.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
 #include "../../simple-mpc_b200/csrc/riccati_fwd.cuh"
 #include "../../simple-mpc_b200/csrc/mpc_driver.cuh"
@@ -205,34 +204,6 @@ void emul_sol_layout(int ndx, int nu, int ncmax, int * out /*7*/)
   SolLayout L = make_sol_layout(ndx, nu, ncmax);
   int v[7] = {L.oK, L.ok, L.oZ, L.oz, L.oPt, L.opt, L.size};
   memcpy(out, v, sizeof(v));
-}
-
-// same, through the compile-time specialised sweep of riccati2.cuh (instantiated sizes only)
-int emul_riccati2(
-  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
-  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
-  double * dphi, int * flag)
-{
-  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
-  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
-  std::vector<double> P0((size_t)ndx * (ndx + 1), 0.0), sm2(4 * ndx + nu + 80, 0.0);
-  if (ndx == 36 && nu == 24 && ncmax == 24)
-  {
-    std::vector<double> sm(Ric2<36, 24, 24>::SIZE + 8, 0.0);
-    riccati2_backward_inst<36, 24, 24>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
-  }
-  else if (ndx == 36 && nu == 24 && ncmax == 36)
-  {
-    std::vector<double> sm(Ric2<36, 24, 36>::SIZE + 8, 0.0);
-    riccati2_backward_inst<36, 24, 36>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
-  }
-  else
-  {
-    g_err = "emul_riccati2: size not instantiated";
-    return -1;
-  }
-  riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
-  return 0;
 }
 
 // same, through the TMA-staged sweep of riccati3.cuh (the one the library launches)

@@ -3,7 +3,8 @@
 import ctypes as C
 import os
 import re
-from smpc_ctypes import ROOT, load_cuda, load_oracle, ModelDesc, OcpDesc, SolverOpts, Slot, Terminal, SolveInfo
+from smpc_ctypes import ROOT, load_cuda, ModelDesc, OcpDesc, SolverOpts, Slot, Terminal, SolveInfo
+from oracle_libs import load_oracle
 
 
 def declared_functions():
@@ -30,8 +31,8 @@ def test_oracle_mirrors_the_solver_level_entry_points():
 
 def test_struct_sizes_match_the_header():
     # sizes computed from the header's field list (8-byte alignment, no padding surprises)
-    assert C.sizeof(Slot) == 8 + 8 * (64 + 40 + 4 * 12 + 4 * 6)
-    assert C.sizeof(Terminal) == 8 * (64 + 3)
+    assert C.sizeof(Slot) == 8 + 8 * (64 + 40 + 4 * 12 + 4 * 6 + 4)
+    assert C.sizeof(Terminal) == 8 * (64 + 3 + 1)
     assert C.sizeof(SolveInfo) == 6 * 4 + 7 * 8
     assert C.sizeof(SolverOpts) == 8 * 2 + 4 * 2 + 8 * 18 + 8
     assert C.sizeof(ModelDesc) % 8 == 0 and C.sizeof(OcpDesc) % 8 == 0

@@ -10,7 +10,8 @@ import ctypes as C
 import numpy as np
 import pytest
 import parity_utils as pu
-from smpc_ctypes import load_oracle, default_opts, Slot, SolveInfo, dbl_p
+from smpc_ctypes import default_opts, Slot, SolveInfo, dbl_p
+from oracle_libs import load_oracle
 from test_emul_vs_oracle import load_emul, P
 
 

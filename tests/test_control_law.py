@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import parity_utils as pu
-from smpc_ctypes import SolverOpts, load_oracle, load_cuda
+from smpc_ctypes import SolverOpts, load_cuda
+from oracle_libs import load_oracle
 
 DT = 0.01
 

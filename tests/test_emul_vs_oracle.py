@@ -4,15 +4,15 @@ tests/host_emul/libemul.so is the device code of simple-mpc_b200/csrc/*.cuh comp
 parallel phase serialised over the thread index (par.cuh). It is a test harness, not a product path.
   * knots: the per-knot linearisation (kino_knot.cuh) must reproduce the oracle's LQ knots to rounding
     (two independent implementations of the same derivatives: compact world-frame inertias vs dense 6x6);
-  * Riccati: fed with the ORACLE's knots, both sweeps (generic riccati.cuh and the specialised riccati2.cuh)
+  * Riccati: fed with the ORACLE's knots, both sweeps (generic riccati.cuh and the TMA-staged riccati3.cuh)
     must return gains and steps that are BITWISE equal to the oracle's (same canonical operation order).
 """
 import ctypes as C
 import os
 import numpy as np
 import pytest
-from smpc_ctypes import (ROOT, load_oracle, go2_like_model, go2_kino_ocp, standing_slot, fk_numpy, x_ref_of, total_mass,
-                         default_opts, Slot, Terminal, SolveInfo, dbl_p)
+from smpc_ctypes import (ROOT, go2_like_model, go2_kino_ocp, standing_slot, fk_numpy, x_ref_of, total_mass, default_opts, Slot, Terminal, SolveInfo, dbl_p)
+from oracle_libs import load_oracle
 
 
 def P(a):
@@ -56,6 +56,7 @@ def run_case(cone):
     term = Terminal()
     term.x_ref[:nx] = xref
     term.com_ref[:] = [0.0, 0.0, 0.3]
+    term.tau = np.sqrt(0.3 / 9.81)
     orc.orc_set_terminal(ctx, 0, 1, C.byref(term))
     xs = np.tile(xref, (T + 1, 1)).copy()
     us = np.tile(np.array(slots[0].u_ref[:nu]), (T, 1)).copy()
@@ -145,7 +146,6 @@ def run_case(cone):
 
     out = dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu)
     out['generic_on_oracle'] = sweep(emu.emul_riccati, orc_knots)
-    out['special_on_oracle'] = sweep(emu.emul_riccati2, orc_knots)
     out['tma_on_oracle'] = sweep(emu.emul_riccati3, orc_knots)
     out['special_on_emul'] = sweep(emu.emul_riccati3, emu_knots)
     orc.orc_destroy(ctx)
@@ -170,7 +170,7 @@ def test_infeasibility_scalars_match(case):
 
 
 def test_riccati_bitwise(case):
-    for name in ['generic_on_oracle', 'special_on_oracle', 'tma_on_oracle']:
+    for name in ['generic_on_oracle', 'tma_on_oracle']:
         K, dxs, dus = case[name]
         assert np.array_equal(K, case['Ko']), name
         assert np.array_equal(dxs, case['odx']), name

@@ -5,8 +5,8 @@ knots must return the oracle's gains within the conditioning of the penalised re
 import ctypes as C
 import numpy as np
 import pytest
-from smpc_ctypes import (load_oracle, go2_like_model, go2_full_ocp, full_slot, fk_numpy, x_ref_of, default_opts, Slot, Terminal,
-                         SolveInfo, dbl_p)
+from smpc_ctypes import (go2_like_model, go2_full_ocp, full_slot, fk_numpy, x_ref_of, default_opts, Slot, Terminal, SolveInfo, dbl_p)
+from oracle_libs import load_oracle
 from test_emul_vs_oracle import load_emul, GAIT
 
 
@@ -39,6 +39,7 @@ def run_case(cone, kp):
     term = Terminal()
     term.x_ref[:nx] = xref
     term.com_ref[:] = [0.0, 0.0, 0.3]
+    term.tau = np.sqrt(0.3 / 9.81)
     orc.orc_set_terminal(ctx, 0, 1, C.byref(term))
     xs = np.tile(xref, (T + 1, 1)).copy()
     us = np.zeros((T, nu))

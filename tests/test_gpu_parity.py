@@ -189,7 +189,8 @@ def test_full_size_batch_4096_sampled_against_the_oracle_and_batch_properties():
     small, and the feedback control law reproduces us[0] at the plan."""
     import ctypes as C
     import numpy as np
-    from smpc_ctypes import SolverOpts, load_cuda, load_oracle
+    from smpc_ctypes import SolverOpts, load_cuda
+    from oracle_libs import load_oracle
     cu, orc = load_cuda(), load_oracle()
     B, ticks = 4096, 3
     sample = [0, 1, 777, 2048, 4095]
@@ -295,7 +296,8 @@ def test_fine_grained_entry_points_against_the_oracle():
     (src/ocp-handler.cpp:74-77). Both libraries receive the same calls; results must agree as in the other tests."""
     import ctypes as C
     import numpy as np
-    from smpc_ctypes import Slot, SolverOpts, load_cuda, load_oracle
+    from smpc_ctypes import Slot, SolverOpts, load_cuda
+    from oracle_libs import load_oracle
     cu, orc = load_cuda(), load_oracle()
     B = 3
     sc = pu.Go2Scenario(B, seed=9)

@@ -39,7 +39,7 @@ def test_robot_handler_matches_reference_contract():
 
 
 def test_python_fixtures_equal_cpp_models():
-    """tests/smpc_ctypes.py (ctypes fixtures of the C-ABI tests) and Model::BuildGo2Like/BuildTalosLike are the
+    """simple-mpc_b200/python/smpc_ctypes.py (ctypes binding + synthetic robots) and Model::BuildGo2Like/BuildTalosLike are the
     same robots: identical FK and mass."""
     import smpc_ctypes as S
     for build, handler in [(S.go2_like_model, hu.go2_handler), (S.talos_like_model, hu.talos_handler)]:
@@ -200,7 +200,8 @@ def test_interpolator_matches_reference_semantics_and_the_oracle_plan_interpolat
     parts, contact lookup; the state interpolation agrees with the oracle's restatement used for the batched kernel."""
     import ctypes as C
     import parity_utils as pu
-    from smpc_ctypes import SolverOpts, load_oracle
+    from smpc_ctypes import SolverOpts
+    from oracle_libs import load_oracle
     mh = hu.go2_handler(sm)
     interp = sm.Interpolator(mh.getModel())
     orc = load_oracle()

@@ -13,7 +13,8 @@ import pytest
 
 import host_api_utils as hu
 import parity_utils as pu
-from smpc_ctypes import Slot, Terminal, MpcSettings, dbl_p, load_emul
+from smpc_ctypes import Slot, Terminal, MpcSettings, dbl_p
+from oracle_libs import load_emul
 
 sm = hu.import_simple_mpc()
 FEET = ["FL_foot", "FR_foot", "RL_foot", "RR_foot"]

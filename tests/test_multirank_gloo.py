@@ -44,7 +44,8 @@ def _drive(first, count, ticks):
     """constructor solve + `ticks` MPC ticks of instances [first, first+count) through the oracle"""
     import ctypes as C
     import parity_utils as pu
-    from smpc_ctypes import SolverOpts, load_oracle
+    from smpc_ctypes import SolverOpts
+    from oracle_libs import load_oracle
     orc = load_oracle()
     sc = pu.Go2Scenario(count, seed=5, first=first)
     opts = SolverOpts()

@@ -9,7 +9,8 @@
 import ctypes as C
 import numpy as np
 import pytest
-from smpc_ctypes import (load_oracle, go2_like_model, go2_kino_ocp, standing_slot, fk_numpy, x_ref_of, dbl_p)
+from smpc_ctypes import go2_like_model, go2_kino_ocp, standing_slot, fk_numpy, x_ref_of, dbl_p
+from oracle_libs import load_oracle
 
 
 def P(a):

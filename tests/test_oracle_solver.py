@@ -11,7 +11,8 @@ import ctypes as C
 import numpy as np
 import pytest
 import parity_utils as pu
-from smpc_ctypes import load_oracle, SolverOpts, Slot, dbl_p
+from smpc_ctypes import SolverOpts, Slot, dbl_p
+from oracle_libs import load_oracle
 
 
 def P(a):
