@@ -731,12 +731,12 @@ int orc_terminal_eval(
 int orc_full_dynamics(
   const smpc_model_desc * model, const double * q, const double * v, const double * tau, unsigned mask, const double * gravity,
   const double * Kp, const double * Kd, int derivs, double * a, double * lam, double * da_dq, double * da_dv, double * da_dtau,
-  double * dl_dq, double * dl_dv, double * dl_dtau)
+  double * dl_dq, double * dl_dv, double * dl_dtau, int contact_dim)
 {
   ORC_TRY
   Model m(*model);
   FullDyn fd;
-  full_dynamics(m, q, v, tau, mask, gravity, Kp, Kd, derivs != 0, fd);
+  full_dynamics(m, q, v, tau, mask, gravity, Kp, Kd, derivs != 0, fd, contact_dim == 6 ? 6 : 3);
   auto cp = [](double * dst, const std::vector<double> & vv) {
     if (dst && !vv.empty())
       memcpy(dst, vv.data(), vv.size() * sizeof(double));

@@ -18,7 +18,13 @@
 // Derivatives: implicit differentiation of the two equations above with the same factorisations,
 //   dtau/dq, dtau/dv of RNEA(q, v, a) with the contact forces as external forces held fixed in the foot frame,
 //   d(Jc a + gamma)/dq, /dv in closed form (world-frame spatial algebra, see contact_acc_derivs).
-// 6-D (CONTACT_6D, LOCAL_WORLD_ALIGNED) contacts are not restated: force_size == 6 throws.
+//   * quad feet (force_size 6): CONTACT_6D rigid constraint, reference frame LOCAL_WORLD_ALIGNED (reference :56-64):
+//       c = [R 0; 0 R] (a_loc + Kd o v_loc + Kp o log6(oMc))        6 rows per foot, lam = [f; tau] in world-aligned
+//     axes at the contact-frame origin. a_loc / v_loc: SPATIAL acceleration / velocity of the contact frame in its own
+//     axes (no classical term for CONTACT_6D), placement error -log6(c1Mc2) = log6(oMc1) (joint 2 is the universe with
+//     an identity placement), the diagonal gains act on the LOCAL components and the result is rotated back
+//     (Pinocchio 3.8 constrained-dynamics.hxx [UPSTREAM]). A force held fixed in world-aligned axes does not turn
+//     with the foot, which adds one term to the RNEA partials (see `lwa` below).
 #pragma once
 #include "orc_rbd.hpp"
 #include <stdexcept>
@@ -75,7 +81,8 @@ namespace orc
 
   struct FullDyn
   {
-    int ncon = 0;              // 3 rows per foot in contact
+    int cd = 3;                // rows per contact: 3 (CONTACT_3D, LOCAL) or 6 (CONTACT_6D, LOCAL_WORLD_ALIGNED)
+    int ncon = 0;              // cd rows per foot in contact
     std::vector<int> feet;     // feet in contact, insertion order (the order of `cms`, reference :116-119)
     Vec a, lam;                // joint acceleration, contact forces (foot frame, environment on robot)
     Mat Jc;                    // ncon x nv
@@ -177,10 +184,119 @@ namespace orc
       dc_v[r] = o1[r] + Kd[r] * o4[r];
   }
 
-  // Forward dynamics with rigid point contacts on the feet of `mask`; derivatives if `derivs`.
+  // ---- CONTACT_6D / LOCAL_WORLD_ALIGNED ----------------------------------------------------------------------
+  // world-axes motion of the contact-frame origin: [lin + ang x p ; ang]
+  inline void frame_motion_lwa(const double * mo, const double * p, double * out)
+  {
+    double t[3];
+    cross3(mo + 3, p, t);
+    for (int r = 0; r < 3; r++)
+    {
+      out[r] = mo[r] + t[r];
+      out[3 + r] = mo[3 + r];
+    }
+  }
+  // y = [R 0; 0 R] diag(K) [R^T 0; 0 R^T] x
+  inline void rkrt6(const double * R, const double * K, const double * x, double * y)
+  {
+    double l[6];
+    matTvec3(R, x, l);
+    matTvec3(R, x + 3, l + 3);
+    for (int r = 0; r < 6; r++)
+      l[r] *= K[r];
+    matvec3(R, l, y);
+    matvec3(R, l + 3, y + 3);
+  }
+  inline void contact_row6(const SE3 & F, const double * Kp, const double * Kd, const double * vi, const double * ai, double * c)
+  {
+    double V[6], A[6], e[6], ke[6], t1[6], t2[6];
+    frame_motion_lwa(vi, F.p, V);
+    frame_motion_lwa(ai, F.p, A);
+    log6(F, e);
+    rkrt6(F.R, Kd, V, t1);
+    for (int r = 0; r < 6; r++)
+      ke[r] = Kp[r] * e[r];
+    matvec3(F.R, ke, t2);
+    matvec3(F.R, ke + 3, t2 + 3);
+    for (int r = 0; r < 6; r++)
+      c[r] = A[r] + t1[r] + t2[r];
+  }
+  // partial derivatives of contact_row6 with respect to q_m and v_m (dof m on the support chain of the foot joint)
+  inline void contact_acc_derivs6(
+    const SE3 & F, const double * Kp, const double * Kd, const double * vi, const double * ai, const double * vim, const double * vp,
+    const double * ap, const double * Jm, double * dc_q, double * dc_v)
+  {
+    const double * p = F.p;
+    double dvp[6], dap[6], dvi[6], vs[6], dv_q[6], w[6], da1[6], da2[6], da_q[6], da_v[6];
+    for (int r = 0; r < 6; r++)
+    {
+      dvp[r] = vp[r] - vi[r];
+      dap[r] = ap[r] - ai[r];
+      dvi[r] = vi[r] - vp[r];
+      vs[r] = vim[r] + vp[r] - vi[r];
+    }
+    mxm(dvp, Jm, dv_q); // d v_i / d q_m
+    mxm(vp, Jm, w);
+    mxm(dap, Jm, da1);
+    mxm(w, dvi, da2);
+    for (int r = 0; r < 6; r++)
+      da_q[r] = da1[r] + da2[r]; // d a_i / d q_m
+    mxm(vs, Jm, da_v);           // d a_i / d v_m
+    double Jp[6];
+    frame_motion_lwa(Jm, p, Jp); // [d p / d q_m ; angular part of J_m]
+    const double * wm = Jm + 3;
+    double V[6], e[6];
+    frame_motion_lwa(vi, p, V);
+    log6(F, e);
+    // dV/dq, dA/dq: the motion changes and the point moves
+    double dV_q[6], dA_q[6], dA_v[6], t[3];
+    frame_motion_lwa(dv_q, p, dV_q);
+    cross3(vi + 3, Jp, t);
+    for (int r = 0; r < 3; r++)
+      dV_q[r] += t[r];
+    frame_motion_lwa(da_q, p, dA_q);
+    cross3(ai + 3, Jp, t);
+    for (int r = 0; r < 3; r++)
+      dA_q[r] += t[r];
+    frame_motion_lwa(da_v, p, dA_v);
+    // d/dq [R Kd R^T V] = w_m x (R Kd R^T V) + R Kd R^T (dV - w_m x V), lin and ang blocks alike
+    double kv[6], wxV[6], dVr[6], t2[6], c1[6];
+    rkrt6(F.R, Kd, V, kv);
+    cross3(wm, V, wxV);
+    cross3(wm, V + 3, wxV + 3);
+    for (int r = 0; r < 6; r++)
+      dVr[r] = dV_q[r] - wxV[r];
+    rkrt6(F.R, Kd, dVr, t2);
+    cross3(wm, kv, c1);
+    cross3(wm, kv + 3, c1 + 3);
+    // d/dq [R (Kp o e)] = w_m x (R Kp e) + R Kp Jlog6(e) (X_F^-1 J_m)
+    double ke[6], rke[6], c2[6], Jl[36], X[36], Jloc[6], de[6], rde[6];
+    for (int r = 0; r < 6; r++)
+      ke[r] = Kp[r] * e[r];
+    matvec3(F.R, ke, rke);
+    matvec3(F.R, ke + 3, rke + 3);
+    cross3(wm, rke, c2);
+    cross3(wm, rke + 3, c2 + 3);
+    Jlog6(e, Jl);
+    se3_actinv_matrix(F, X);
+    mat6vec(X, Jm, Jloc);
+    mat6vec(Jl, Jloc, de);
+    for (int r = 0; r < 6; r++)
+      de[r] *= Kp[r];
+    matvec3(F.R, de, rde);
+    matvec3(F.R, de + 3, rde + 3);
+    for (int r = 0; r < 6; r++)
+      dc_q[r] = dA_q[r] + c1[r] + t2[r] + c2[r] + rde[r];
+    double t3[6];
+    rkrt6(F.R, Kd, Jp, t3); // dV/dv_m = [J_lin + J_ang x p ; J_ang]
+    for (int r = 0; r < 6; r++)
+      dc_v[r] = dA_v[r] + t3[r];
+  }
+
+  // Forward dynamics with rigid contacts on the feet of `mask` (cd = 3: point feet, 6: quad feet); derivatives if `derivs`.
   inline void full_dynamics(
     const Model & m, const double * q, const double * v, const double * tau, unsigned mask, const double * gravity, const double * Kp,
-    const double * Kd, bool derivs, FullDyn & o)
+    const double * Kd, bool derivs, FullDyn & o, int cd = 3)
   {
     const smpc_model_desc & d = m.d;
     const int nv = m.nv, nj = m.nj;
@@ -189,7 +305,11 @@ namespace orc
     for (int f = 0; f < m.nfeet; f++)
       if (mask & (1u << f))
         o.feet.push_back(f);
-    const int ncon = o.ncon = 3 * (int)o.feet.size();
+    if (cd != 3 && cd != 6)
+      throw std::runtime_error("full_dynamics: contact dimension must be 3 or 6");
+    const bool lwa = (cd == 6);
+    o.cd = cd;
+    const int ncon = o.ncon = cd * (int)o.feet.size();
 
     // pass 1: drift quantities (a = 0)
     Kin k0;
@@ -224,6 +344,22 @@ namespace orc
     {
       const int f = o.feet[cf], jf = d.foot_joint[f];
       const SE3 & F = k0.oMf[f];
+      if (lwa)
+      {
+        contact_row6(F, Kp, Kd, &k0.ov[6 * jf], &k0.oa[6 * jf], &o.gamma[6 * cf]);
+        for (int c = 0; c < nv; c++)
+        {
+          if (!m.anc[jf][m.joint_of_dof[c]])
+            continue;
+          double Jm[6], Jp[6];
+          for (int r = 0; r < 6; r++)
+            Jm[r] = k0.J(r, c);
+          frame_motion_lwa(Jm, F.p, Jp);
+          for (int r = 0; r < 6; r++)
+            o.Jc(6 * (int)cf + r, c) = Jp[r];
+        }
+        continue;
+      }
       contact_row(F.R, F.p, Kp, Kd, &k0.ov[6 * jf], &k0.oa[6 * jf], &o.gamma[3 * cf]);
       for (int c = 0; c < nv; c++)
       {
@@ -304,8 +440,19 @@ namespace orc
     {
       const int f = o.feet[cf], jf = d.foot_joint[f];
       double fw[3], nw[3];
-      matvec3(k.oMf[f].R, &o.lam[3 * cf], fw);
-      cross3(k.oMf[f].p, fw, nw);
+      if (lwa)
+      {
+        for (int r = 0; r < 3; r++)
+          fw[r] = o.lam[6 * cf + r];
+        cross3(k.oMf[f].p, fw, nw);
+        for (int r = 0; r < 3; r++)
+          nw[r] += o.lam[6 * cf + 3 + r];
+      }
+      else
+      {
+        matvec3(k.oMf[f].R, &o.lam[3 * cf], fw);
+        cross3(k.oMf[f].p, fw, nw);
+      }
       for (int i = jf; i >= 0; i = d.parent[i])
         for (int r = 0; r < 3; r++)
         {
@@ -374,6 +521,34 @@ namespace orc
         dtau_dv(j, c) = sv;
       }
     }
+    // `lwa`: the RNEA partials above treat an external force as attached to its body (it turns with the foot). A force
+    // held fixed in world-aligned axes does not: per dof c on the support chain, d(wrench)/dq_c lacks the rotation
+    // [w_c x f ; p x (w_c x f) + w_c x tau], so  d tau_k / d q_c  gains  J_k . [w_c x f ; p x (w_c x f) + w_c x tau].
+    if (lwa)
+      for (size_t cf = 0; cf < o.feet.size(); cf++)
+      {
+        const int f = o.feet[cf], jf = d.foot_joint[f];
+        const double * lf = &o.lam[6 * cf];
+        for (int c = 0; c < nv; c++)
+        {
+          if (!m.anc[jf][m.joint_of_dof[c]])
+            continue;
+          const double wc[3] = {k.J(3, c), k.J(4, c), k.J(5, c)};
+          double g[3], pg[3], wt[3];
+          cross3(wc, lf, g);
+          cross3(k.oMf[f].p, g, pg);
+          cross3(wc, lf + 3, wt);
+          for (int j = 0; j < nv; j++)
+          {
+            if (!m.anc[jf][m.joint_of_dof[j]])
+              continue;
+            double sacc = 0;
+            for (int r = 0; r < 3; r++)
+              sacc += k.J(r, j) * g[r] + k.J(3 + r, j) * (pg[r] + wt[r]);
+            dtau_dq(j, c) += sacc;
+          }
+        }
+      }
     // contact-acceleration partial derivatives
     Mat dc_dq(ncon > 0 ? ncon : 1, nv), dc_dv(ncon > 0 ? ncon : 1, nv);
     for (size_t cf = 0; cf < o.feet.size(); cf++)
@@ -388,6 +563,19 @@ namespace orc
         double Jm[6], dq3[3], dv3[3];
         for (int r = 0; r < 6; r++)
           Jm[r] = k.J(r, c);
+        if (lwa)
+        {
+          double dq6[6], dv6[6];
+          contact_acc_derivs6(
+            k.oMf[f], Kp, Kd, &k.ov[6 * jf], &k.oa[6 * jf], &k.ov[6 * ic], (p >= 0) ? &k.ov[6 * p] : zero6,
+            (p >= 0) ? &k.oa[6 * p] : zero6, Jm, dq6, dv6);
+          for (int r = 0; r < 6; r++)
+          {
+            dc_dq(6 * (int)cf + r, c) = dq6[r];
+            dc_dv(6 * (int)cf + r, c) = dv6[r];
+          }
+          continue;
+        }
         contact_acc_derivs(
           k.oMf[f].R, k.oMf[f].p, Kp, Kd, &k.ov[6 * jf], &k.oa[6 * jf], &k.ov[6 * ic], (p >= 0) ? &k.ov[6 * p] : zero6,
           (p >= 0) ? &k.oa[6 * p] : zero6, Jm, dq3, dv3);

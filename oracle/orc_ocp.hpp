@@ -133,7 +133,7 @@ namespace orc
       }
       else
       {
-        // reference src/fulldynamics.cpp:145-211 (point feet)
+        // reference src/fulldynamics.cpp:145-211
         if (ocp.torque_limits)
           nc += model.nv - 6;
         if (ocp.kinematics_limits)
@@ -142,9 +142,9 @@ namespace orc
           if (s.contact_mask & (1u << f))
           {
             if (ocp.force_cone)
-              nc += 5;
+              nc += (fs == 6) ? 17 : 5; // MultibodyWrenchCone / 5-row friction pyramid
             if (ocp.land_cstr && (s.land_mask & (1u << f)))
-              nc += 4;
+              nc += (fs == 6) ? 6 : 4; // 6-D LWA velocity / 3 velocity rows + z-height
           }
       }
       return nc;
@@ -389,6 +389,42 @@ namespace orc
       for (int i = 6; i < 2 * nv; i++)
         (*J)(i, i) = 1.0;
     }
+  }
+
+  // <foot>_pose_cost of a quad foot: FramePlacementResidual log6(ref^-1 oMf) with weight w_frame (6 x 6),
+  // J = Jlog6(r) * (LOCAL frame Jacobian)   (reference src/kinodynamics.cpp:67-73, src/fulldynamics.cpp:99-104)
+  inline void frame_placement_cost(const Problem & P, const smpc_slot & s, const Kin & k, int f, bool derivs, StageEval & o)
+  {
+    const Model & m = P.model;
+    const int nv = m.nv;
+    SE3 Mref;
+    memcpy(Mref.R, s.foot_ref[f], sizeof(Mref.R));
+    memcpy(Mref.p, s.foot_ref[f] + 9, sizeof(Mref.p));
+    SE3 rMf = se3_mul(se3_inv(Mref), k.oMf[f]);
+    Vec r(6);
+    log6(rMf, r.data());
+    Mat Jx;
+    if (derivs)
+    {
+      Jx.resize(6, P.ndx);
+      double Jl[36], X[36];
+      Jlog6(r.data(), Jl);
+      se3_actinv_matrix(k.oMf[f], X);
+      const int jf = m.d.foot_joint[f];
+      for (int j = 0; j < nv; j++)
+      {
+        if (!m.anc[jf][m.joint_of_dof[j]])
+          continue;
+        double Jc[6], loc[6], out[6];
+        for (int rr = 0; rr < 6; rr++)
+          Jc[rr] = k.J(rr, j);
+        mat6vec(X, Jc, loc);
+        mat6vec(Jl, loc, out);
+        for (int rr = 0; rr < 6; rr++)
+          Jx(rr, j) = out[rr];
+      }
+    }
+    add_quad_cost(r, P.w_frame, &Jx, nullptr, derivs, o);
   }
 
   // ---------------------------------------------------------------------------------------------
@@ -675,34 +711,7 @@ namespace orc
       else
       {
         // FramePlacementResidual: log6(ref^-1 oMf), J = Jlog6 * (LOCAL frame Jacobian)
-        SE3 Mref;
-        memcpy(Mref.R, s.foot_ref[f], sizeof(Mref.R));
-        memcpy(Mref.p, s.foot_ref[f] + 9, sizeof(Mref.p));
-        SE3 rMf = se3_mul(se3_inv(Mref), k.oMf[f]);
-        Vec r(6);
-        log6(rMf, r.data());
-        Mat Jx;
-        if (derivs)
-        {
-          Jx.resize(6, ndx);
-          double Jl[36], X[36];
-          Jlog6(r.data(), Jl);
-          se3_actinv_matrix(k.oMf[f], X);
-          const int jf = m.d.foot_joint[f];
-          for (int j = 0; j < nv; j++)
-          {
-            if (!m.anc[jf][m.joint_of_dof[j]])
-              continue;
-            double Jc[6], loc[6], out[6];
-            for (int rr = 0; rr < 6; rr++)
-              Jc[rr] = k.J(rr, j);
-            mat6vec(X, Jc, loc);
-            mat6vec(Jl, loc, out);
-            for (int rr = 0; rr < 6; rr++)
-              Jx(rr, j) = out[rr];
-          }
-        }
-        add_quad_cost(r, P.w_frame, &Jx, nullptr, derivs, o);
+        frame_placement_cost(P, s, k, f, derivs, o);
       }
     }
 
@@ -792,7 +801,7 @@ namespace orc
   }
 
   // ---------------------------------------------------------------------------------------------
-  // Full-dynamics stage (reference src/fulldynamics.cpp:78-214), point feet (force_size = 3)
+  // Full-dynamics stage (reference src/fulldynamics.cpp:78-214), point feet (force_size 3) or quad feet (force_size 6)
   //   u = tau_joint (nv-6), tau = [0; u] (:35-37); a, lam = rigid-contact forward dynamics (orc_full.hpp)
   //   semi-implicit Euler (:140)
   // Costs (:88-137): state, control (target u_ref = 0), centroidal momentum, foot translation per foot,
@@ -813,8 +822,7 @@ namespace orc
     const int nv = m.nv, nq = m.nq, ndx = P.ndx, nu = P.nu, nk = P.nk, fs = P.fs;
     const int nj = nv - 6;
     const double dt = P.ocp.timestep;
-    if (fs != 3)
-      throw std::runtime_error("oracle: full dynamics with 6-D contacts is not restated");
+    const int cd = fs; // rows per contact: 3 (CONTACT_3D, LOCAL) or 6 (CONTACT_6D, LOCAL_WORLD_ALIGNED)
     const double * q = x;
     const double * v = x + nq;
     alloc_eval(P, P.stage_nc(s), derivs, o);
@@ -822,7 +830,7 @@ namespace orc
     for (int j = 0; j < nj; j++)
       tau[6 + j] = u[j];
     FullDyn fd;
-    full_dynamics(m, q, v, tau.data(), s.contact_mask, P.ocp.gravity, P.ocp.Kp_correction, P.ocp.Kd_correction, derivs, fd);
+    full_dynamics(m, q, v, tau.data(), s.contact_mask, P.ocp.gravity, P.ocp.Kp_correction, P.ocp.Kd_correction, derivs, fd, cd);
     const Kin & k = fd.k;
     const Vec & a = fd.a;
     for (int i = 0; i < nv; i++)
@@ -941,6 +949,12 @@ namespace orc
     }
     for (int f = 0; f < nk; f++)
     {
+      if (fs == 6)
+      {
+        // FramePlacementResidual (reference src/fulldynamics.cpp:99-104): log6(ref^-1 oMf), J = Jlog6 * (LOCAL frame Jacobian)
+        frame_placement_cost(P, s, k, f, derivs, o);
+        continue;
+      }
       Vec r(3);
       for (int rr = 0; rr < 3; rr++)
         r[rr] = k.oMf[f].p[rr] - s.foot_ref[f][9 + rr];
@@ -955,29 +969,30 @@ namespace orc
       add_quad_cost(r, P.w_frame, &Jx, nullptr, derivs, o);
     }
     o.fc.assign((size_t)P.nk * 3, 0.0);
+    // MPC::getContactForces keeps the linear part of the contact force (reference src/mpc.cpp:369)
     for (size_t cf = 0; cf < fd.feet.size(); cf++)
       for (int rr = 0; rr < 3; rr++)
-        o.fc[(size_t)fd.feet[cf] * 3 + rr] = fd.lam[3 * cf + rr];
+        o.fc[(size_t)fd.feet[cf] * 3 + rr] = fd.lam[cd * cf + rr];
     for (size_t cf = 0; cf < fd.feet.size(); cf++)
     {
       const int f = fd.feet[cf];
-      Vec r(3);
-      for (int rr = 0; rr < 3; rr++)
-        r[rr] = fd.lam[3 * cf + rr] - s.f_ref[f][rr];
+      Vec r(cd);
+      for (int rr = 0; rr < cd; rr++)
+        r[rr] = fd.lam[cd * cf + rr] - s.f_ref[f][rr];
       Mat Jx, Ju;
       if (derivs)
       {
-        Jx.resize(3, ndx);
-        Ju.resize(3, nu);
-        for (int rr = 0; rr < 3; rr++)
+        Jx.resize(cd, ndx);
+        Ju.resize(cd, nu);
+        for (int rr = 0; rr < cd; rr++)
         {
           for (int j = 0; j < nv; j++)
           {
-            Jx(rr, j) = fd.dl_dq(3 * (int)cf + rr, j);
-            Jx(rr, nv + j) = fd.dl_dv(3 * (int)cf + rr, j);
+            Jx(rr, j) = fd.dl_dq(cd * (int)cf + rr, j);
+            Jx(rr, nv + j) = fd.dl_dv(cd * (int)cf + rr, j);
           }
           for (int j = 0; j < nu; j++)
-            Ju(rr, j) = fd.dl_dtau(3 * (int)cf + rr, 6 + j);
+            Ju(rr, j) = fd.dl_dtau(cd * (int)cf + rr, 6 + j);
         }
       }
       add_quad_cost(r, P.w_forces, &Jx, &Ju, derivs, o);
@@ -1010,29 +1025,74 @@ namespace orc
       const int f = fd.feet[cf], jf = m.d.foot_joint[f];
       if (P.ocp.force_cone)
       {
-        double Ac[15];
-        friction_pyramid(P.ocp.mu, Ac);
-        for (int rr = 0; rr < 5; rr++, row++)
+        // point feet: 5-row friction pyramid on lam_f (MultibodyFrictionConeResidual); quad feet: 17-row wrench cone on the
+        // 6-D contact force, which constraintDynamics returns in the LOCAL_WORLD_ALIGNED frame (MultibodyWrenchConeResidual)
+        double Ac[17 * 6];
+        const int nrows = (fs == 6) ? 17 : 5;
+        if (fs == 6)
+          wrench_cone_matrix(P.ocp.mu, P.ocp.Lfoot, P.ocp.Wfoot, Ac);
+        else
+          friction_pyramid(P.ocp.mu, Ac);
+        for (int rr = 0; rr < nrows; rr++, row++)
         {
           double sacc = 0;
-          for (int c = 0; c < 3; c++)
-            sacc += Ac[3 * rr + c] * fd.lam[3 * cf + c];
+          for (int c = 0; c < cd; c++)
+            sacc += Ac[cd * rr + c] * fd.lam[cd * cf + c];
           o.c[row] = sacc;
           o.ctype[row] = CSTR_NEG;
           if (derivs)
-            for (int c = 0; c < 3; c++)
+            for (int c = 0; c < cd; c++)
             {
               for (int j = 0; j < nv; j++)
               {
-                o.Cx(row, j) += Ac[3 * rr + c] * fd.dl_dq(3 * (int)cf + c, j);
-                o.Cx(row, nv + j) += Ac[3 * rr + c] * fd.dl_dv(3 * (int)cf + c, j);
+                o.Cx(row, j) += Ac[cd * rr + c] * fd.dl_dq(cd * (int)cf + c, j);
+                o.Cx(row, nv + j) += Ac[cd * rr + c] * fd.dl_dv(cd * (int)cf + c, j);
               }
               for (int j = 0; j < nu; j++)
-                o.Cu(row, j) += Ac[3 * rr + c] * fd.dl_dtau(3 * (int)cf + c, 6 + j);
+                o.Cu(row, j) += Ac[cd * rr + c] * fd.dl_dtau(cd * (int)cf + c, 6 + j);
             }
         }
       }
-      if (P.ocp.land_cstr && (s.land_mask & (1u << f)))
+      if (fs == 6 && P.ocp.land_cstr && (s.land_mask & (1u << f)))
+      {
+        // 6-D LOCAL_WORLD_ALIGNED frame velocity = 0 on a landing edge (reference src/fulldynamics.cpp:175-181)
+        const double * vi = &k.ov[6 * jf];
+        const double * p = k.oMf[f].p;
+        double V[6];
+        frame_motion_lwa(vi, p, V);
+        for (int rr = 0; rr < 6; rr++)
+        {
+          o.c[row + rr] = V[rr];
+          o.ctype[row + rr] = CSTR_EQ;
+        }
+        if (derivs)
+          for (int j = 0; j < nv; j++)
+          {
+            const int ij = m.joint_of_dof[j];
+            if (!m.anc[jf][ij])
+              continue;
+            const int pj = m.d.parent[ij];
+            double Jm[6], dvp[6], dvq[6], dV[6], Jpm[6], t2[3];
+            for (int rr = 0; rr < 6; rr++)
+            {
+              Jm[rr] = k.J(rr, j);
+              dvp[rr] = ((pj >= 0) ? k.ov[6 * pj + rr] : 0.0) - vi[rr];
+            }
+            mxm(dvp, Jm, dvq);
+            frame_motion_lwa(dvq, p, dV);
+            frame_motion_lwa(Jm, p, Jpm);
+            cross3(vi + 3, Jpm, t2);
+            for (int rr = 0; rr < 3; rr++)
+              dV[rr] += t2[rr];
+            for (int rr = 0; rr < 6; rr++)
+            {
+              o.Cx(row + rr, j) = dV[rr];
+              o.Cx(row + rr, nv + j) = Jpm[rr];
+            }
+          }
+        row += 6;
+      }
+      if (fs == 3 && P.ocp.land_cstr && (s.land_mask & (1u << f)))
       {
         const double * vi = &k.ov[6 * jf];
         const double * p = k.oMf[f].p;

@@ -3,12 +3,13 @@
 // What it replaces (all [UPSTREAM] aligator/pinocchio code reached from the stage that
 // FullDynamicsOCP::createStage builds, reference src/fulldynamics.cpp:78-214):
 //   MultibodyConstraintFwdDynamics::forward/dForward  (pinocchio::constraintDynamics +
-//   computeConstraintDynamicsDerivatives with CONTACT_3D / LOCAL rigid constraints, Baumgarte corrector,
-//   proximal settings 1e-9 / 1e-10 / 10, reference :39,50-75), IntegratorSemiImplEuler, QuadraticStateCost,
-//   QuadraticControlCost, CentroidalMomentumResidual, FrameTranslationResidual, ContactForceResidual,
-//   ControlErrorResidual box (torque limits), StateErrorResidual slice box (joint limits),
-//   MultibodyFrictionConeResidual (5-row pyramid), FrameVelocityResidual(LOCAL_WORLD_ALIGNED) and
-//   FrameTranslationResidual slice on landing edges, and the per-stage ProxDDP work (dense_knot.cuh).
+//   computeConstraintDynamicsDerivatives with CONTACT_3D / LOCAL rigid constraints on point feet or CONTACT_6D /
+//   LOCAL_WORLD_ALIGNED ones on quad feet, Baumgarte corrector, proximal settings 1e-9 / 1e-10 / 10, reference
+//   :39,50-75), IntegratorSemiImplEuler, QuadraticStateCost, QuadraticControlCost, CentroidalMomentumResidual,
+//   FrameTranslationResidual / FramePlacementResidual, ContactForceResidual, ControlErrorResidual box (torque limits),
+//   StateErrorResidual slice box (joint limits), MultibodyFrictionConeResidual (5-row pyramid) /
+//   MultibodyWrenchConeResidual (17 rows), FrameVelocityResidual(LOCAL_WORLD_ALIGNED) and FrameTranslationResidual
+//   slice on landing edges, and the per-stage ProxDDP work (dense_knot.cuh).
 //   SURVEY.md §8a rows a4, a6, a8, a9, a10. The contact dynamics is computed ONCE per knot and shared by every
 //   residual that needs lam or its derivatives (the reference re-runs it inside each residual).
 //
@@ -17,6 +18,9 @@
 //   with the same factors:  X1 = M^-1 [-dtau/dq | -dtau/dv | I],  dlam = G^-1 (r2 - Jc X1),  da = X1 + M^-1 Jc^T dlam.
 //   dtau/dq, dtau/dv: world-frame RNEA derivatives (Carpentier & Mansard 2018) with the contact forces as external
 //   forces held fixed in the foot frames; d(Jc a + gamma)/dq, /dv in closed form. Same formulas as oracle/orc_full.hpp.
+//   Quad feet (FS = 6): 6 rows per contact, c = [R 0; 0 R](a_loc + Kd o v_loc + Kp o log6(oMc)), lam = [f; tau] in
+//   world-aligned axes at the contact-frame origin; such a force does not turn with the foot, which adds
+//   J_k . [w_c x f ; p x (w_c x f) + w_c x tau] to d tau_k / d q_c (see oracle/orc_full.hpp, `lwa`).
 //
 // Work distribution: tree levels / dof columns / flat (row, col) index loops as in kino_knot.cuh; the two Cholesky
 // factorisations are left-looking with one thread per row (two barriers per column, same dot-product order as the
@@ -28,15 +32,19 @@
 namespace smpc
 {
 
-  template <int NJ_, int NV_, int NK_>
+  template <int NJ_, int NV_, int NK_, int FS_ = 3>
   struct FullCfg
   {
-    static constexpr int NJ = NJ_, NV = NV_, NK = NK_, FS = 3;
+    static constexpr int NJ = NJ_, NV = NV_, NK = NK_, FS = FS_;
+    static_assert(FS == 3 || FS == 6, "point feet (CONTACT_3D) or quad feet (CONTACT_6D)");
     static constexpr int NQ = NV + 1, NX = NQ + NV, NDX = 2 * NV, NJNT = NV - 6, NU = NJNT;
-    static constexpr int NCON = 3 * NK;  // contact rows when every foot is in contact
+    static constexpr int CD = FS;        // rows per contact
+    static constexpr int NCON = CD * NK; // contact rows when every foot is in contact
     static constexpr int NCOL = 3 * NV;  // columns of the sensitivity systems: q | v | tau
     static constexpr int NZ = NDX + NU;  // columns of a stage Jacobian: x | u
-    static constexpr int NCMAX = 2 * NJNT + NK * (5 + 4);
+    static constexpr int NCONE = (FS == 6) ? 17 : 5; // wrench cone / friction pyramid rows per stance foot
+    static constexpr int NLAND = (FS == 6) ? 6 : 4;  // landing-edge rows: 6-D velocity / 3 velocity rows + height
+    static constexpr int NCMAX = 2 * NJNT + NK * (NCONE + NLAND);
   };
 
   enum FullRowKind
@@ -52,7 +60,8 @@ namespace smpc
   struct FullScratch
   {
     static constexpr int NJ = Cfg::NJ, NV = Cfg::NV, NK = Cfg::NK, NX = Cfg::NX, NU = Cfg::NU, NDX = Cfg::NDX;
-    static constexpr int NCON = Cfg::NCON, NCOL = Cfg::NCOL, NZ = Cfg::NZ, NCMAX = Cfg::NCMAX;
+    static constexpr int NCON = Cfg::NCON, NCOL = Cfg::NCOL, NZ = Cfg::NZ, NCMAX = Cfg::NCMAX, FS = Cfg::FS;
+    static constexpr int Q6 = (FS == 6) ? 6 : 1, Q36 = (FS == 6) ? 36 : 1; // sizes of the quad-foot-only arrays
     double x[NX], u[NU], xn_ws[NX], xnext[NX];
     // kinematics (member names shared with kino_kinematics / kino_accel_pass / kino_centroid)
     double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6], bias[NJ][6];
@@ -62,7 +71,11 @@ namespace smpc
     double fR[NK][9], fp[NK][3], lever[NK][3], vf[NK][6];
     double com[3], vcom[3], h0[6], hd0[6], hg[6], hdg[6];
     double Ag[6][NV], dh_dq[6][NV];
-    double Jp[NK][3][NV];
+    // foot Jacobians in world-aligned axes at the foot-frame origin: rows 0-2 linear; quad feet also rows 3-5 angular
+    double Jp[NK][FS][NV];
+    // quad feet: log6 of the foot pose and its Jacobian (Baumgarte position term), pose-cost residual log6(ref^-1 oMf)
+    // and T = Jlog6(residual) blkdiag(R^T, R^T), which maps the world-aligned Jacobian to the residual's
+    double flog[NK][Q6], fJl[NK][Q36], rpl[NK][Q6], Tpl[NK][Q36];
     // contact dynamics
     int ncon, cidx[NK]; // cidx[f]: index of foot f among the feet in contact, -1 if swinging
     double Mm[NV][NV], dgM[NV];
@@ -74,7 +87,7 @@ namespace smpc
     double Jq6[36], Jv6[36], Jl6[36];
     double rs[NDX];
     // costs
-    double WJc[6][NDX], Wch[6], WJp[NK][3][NV], Wfr[NK][3], WJl[NCON][NZ], Wlr[NCON];
+    double WJc[6][NDX], Wch[6], WJp[NK][FS][NV], Wfr[NK][FS], WJl[NCON][NZ], Wlr[NCON];
     double costs[3 + 2 * NK];
     // constraint rows
     int rkind[NCMAX], rarg[NCMAX], rsub[NCMAX];
@@ -158,11 +171,198 @@ namespace smpc
       pdd[r] = a[r] + t1[r] + t2[r];
   }
 
+  // world-axes motion of a frame origin p carried by a body with world-frame spatial motion mo: [lin + ang x p ; ang]
+  SMPC_DEV void frame_motion_lwa(const double * mo, const double * p, double * out)
+  {
+    double t[3];
+    v3cross(mo + 3, p, t);
+    for (int r = 0; r < 3; r++)
+    {
+      out[r] = mo[r] + t[r];
+      out[3 + r] = mo[3 + r];
+    }
+  }
+  // y = [R 0; 0 R] diag(K) [R^T 0; 0 R^T] x
+  SMPC_DEV void rkrt6(const double * R, const double * K, const double * x, double * y)
+  {
+    double l[6];
+    m3tv(R, x, l);
+    m3tv(R, x + 3, l + 3);
+    for (int r = 0; r < 6; r++)
+      l[r] *= K[r];
+    m3v(R, l, y);
+    m3v(R, l + 3, y + 3);
+  }
+  SMPC_DEV void mat6v(const double * A, const double * v, double * o)
+  {
+    for (int r = 0; r < 6; r++)
+    {
+      double sacc = 0;
+      for (int k = 0; k < 6; k++)
+        sacc += A[6 * r + k] * v[k];
+      o[r] = sacc;
+    }
+  }
+
+  // ---- quad feet (CONTACT_6D, LOCAL_WORLD_ALIGNED): the pieces of full_stage_knot that differ from point feet ----
+  // contact-row value gamma (6) of foot f at zero joint acceleration; keeps log6(oMf) and its Jacobian
+  template <class Cfg, bool DERIVS>
+  SMPC_DEV void full6_gamma(const DevOcp & O, FullScratch<Cfg> & s, int f, int jf, double * gamma6)
+  {
+    double V[6], Aw[6], t1[6], ke[6], t2[6], e6[6];
+    frame_motion_lwa(s.v[jf], s.fp[f], V);
+    frame_motion_lwa(s.a[jf], s.fp[f], Aw);
+    log6(s.fR[f], s.fp[f], e6);
+    for (int r = 0; r < 6; r++)
+      s.flog[f][r % FullScratch<Cfg>::Q6] = e6[r];
+    if (DERIVS)
+    {
+      double Jl[36];
+      Jlog6(e6, Jl);
+      for (int r = 0; r < 36; r++)
+        s.fJl[f][r % FullScratch<Cfg>::Q36] = Jl[r];
+    }
+    rkrt6(s.fR[f], O.Kd, V, t1);
+    for (int r = 0; r < 6; r++)
+      ke[r] = O.Kp[r] * e6[r];
+    m3v(s.fR[f], ke, t2);
+    m3v(s.fR[f], ke + 3, t2 + 3);
+    for (int r = 0; r < 6; r++)
+      gamma6[r] = Aw[r] + t1[r] + t2[r];
+  }
+  // partial derivatives of the 6-D contact row of foot f with respect to q_c and v_c (dof c on the support chain)
+  template <class Cfg>
+  SMPC_DEV void full6_contact_derivs(const DevModel & M, const DevOcp & O, const FullScratch<Cfg> & s, int f, int jf, int c, double * dq6, double * dv6)
+  {
+    const smpc_model_desc & d = M.d;
+    const int ic = M.joint_of_dof[c];
+    const int par = d.parent[ic];
+    const double z6[6] = {0, 0, 0, 0, 0, 0};
+    const double * vp = (par >= 0) ? s.v[par] : z6;
+    const double * ap = (par >= 0) ? s.a[par] : z6;
+    const double * vi = s.v[jf];
+    const double * ai = s.a[jf];
+    const double * vim = s.v[ic];
+    const double * p = s.fp[f];
+    const double * Rf = s.fR[f];
+    double Jm[6], dvp[6], dap[6], dvi[6], vs[6], dv_q[6], w[6], da1[6], da2[6], da_q[6], da_v[6];
+    for (int r = 0; r < 6; r++)
+    {
+      Jm[r] = s.J[r][c];
+      dvp[r] = vp[r] - vi[r];
+      dap[r] = ap[r] - ai[r];
+      dvi[r] = vi[r] - vp[r];
+      vs[r] = vim[r] + vp[r] - vi[r];
+    }
+    mxm(dvp, Jm, dv_q);
+    mxm(vp, Jm, w);
+    mxm(dap, Jm, da1);
+    mxm(w, dvi, da2);
+    for (int r = 0; r < 6; r++)
+      da_q[r] = da1[r] + da2[r];
+    mxm(vs, Jm, da_v);
+    double Jpm[6], V[6], dV_q[6], dA_q[6], dA_v[6], t[3];
+    frame_motion_lwa(Jm, p, Jpm);
+    const double * wm = Jm + 3;
+    frame_motion_lwa(vi, p, V);
+    frame_motion_lwa(dv_q, p, dV_q);
+    v3cross(vi + 3, Jpm, t);
+    for (int r = 0; r < 3; r++)
+      dV_q[r] += t[r];
+    frame_motion_lwa(da_q, p, dA_q);
+    v3cross(ai + 3, Jpm, t);
+    for (int r = 0; r < 3; r++)
+      dA_q[r] += t[r];
+    frame_motion_lwa(da_v, p, dA_v);
+    // d/dq [R Kd R^T V] = w_m x (R Kd R^T V) + R Kd R^T (dV - w_m x V)
+    double kv[6], wxV[6], dVr[6], t2[6], c1[6];
+    rkrt6(Rf, O.Kd, V, kv);
+    v3cross(wm, V, wxV);
+    v3cross(wm, V + 3, wxV + 3);
+    for (int r = 0; r < 6; r++)
+      dVr[r] = dV_q[r] - wxV[r];
+    rkrt6(Rf, O.Kd, dVr, t2);
+    v3cross(wm, kv, c1);
+    v3cross(wm, kv + 3, c1 + 3);
+    // d/dq [R (Kp o e)] = w_m x (R Kp e) + R Kp Jlog6(e) (X_F^-1 J_m),  X_F^-1 J_m = blkdiag(R^T) [J_lin + J_ang x p ; J_ang]
+    double ke[6], rke[6], c2[6], Jloc[6], de[6], rde[6], Jl[36];
+    for (int r = 0; r < 6; r++)
+      ke[r] = O.Kp[r] * s.flog[f][r % FullScratch<Cfg>::Q6];
+    for (int r = 0; r < 36; r++)
+      Jl[r] = s.fJl[f][r % FullScratch<Cfg>::Q36];
+    m3v(Rf, ke, rke);
+    m3v(Rf, ke + 3, rke + 3);
+    v3cross(wm, rke, c2);
+    v3cross(wm, rke + 3, c2 + 3);
+    m3tv(Rf, Jpm, Jloc);
+    m3tv(Rf, Jpm + 3, Jloc + 3);
+    mat6v(Jl, Jloc, de);
+    for (int r = 0; r < 6; r++)
+      de[r] *= O.Kp[r];
+    m3v(Rf, de, rde);
+    m3v(Rf, de + 3, rde + 3);
+    double t3[6];
+    rkrt6(Rf, O.Kd, Jpm, t3);
+    for (int r = 0; r < 6; r++)
+    {
+      dq6[r] = dA_q[r] + c1[r] + t2[r] + c2[r] + rde[r];
+      dv6[r] = dA_v[r] + t3[r];
+    }
+  }
+  // <foot>_pose_cost of a quad foot: FramePlacementResidual r = log6(ref^-1 oMf), weight w_frame (6 x 6). The residual
+  // Jacobian is T Jp with T = Jlog6(r) blkdiag(R^T, R^T) and Jp the world-aligned foot Jacobian; stores r, T and the
+  // gradient weights Wfr = T^T W r. Returns 1/2 r^T W r.
+  template <class Cfg, bool DERIVS>
+  SMPC_DEV double full6_pose_cost(const DevOcp & O, const smpc_slot & slot, FullScratch<Cfg> & s, int f)
+  {
+    constexpr int Q6 = FullScratch<Cfg>::Q6, Q36 = FullScratch<Cfg>::Q36, FS = Cfg::FS;
+    const double * Rr = slot.foot_ref[f];
+    double Rrel[9], dp[3], prel[3], rr[6], Wr[6], cst = 0;
+    m3tm(Rr, s.fR[f], Rrel);
+    for (int r = 0; r < 3; r++)
+      dp[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
+    m3tv(Rr, dp, prel);
+    log6(Rrel, prel, rr);
+    for (int r = 0; r < 6; r++)
+    {
+      s.rpl[f][r % Q6] = rr[r];
+      double a = 0;
+      for (int k = 0; k < 6; k++)
+        a += O.w_frame[6 * r + k] * rr[k];
+      Wr[r] = a;
+      cst += rr[r] * a;
+    }
+    if (DERIVS)
+    {
+      double Jl[36], T[36];
+      Jlog6(rr, Jl);
+      for (int r = 0; r < 6; r++)
+        for (int half = 0; half < 2; half++)
+          for (int k = 0; k < 3; k++)
+          {
+            double a = 0;
+            for (int m2 = 0; m2 < 3; m2++)
+              a += Jl[6 * r + 3 * half + m2] * s.fR[f][3 * k + m2];
+            T[6 * r + 3 * half + k] = a;
+          }
+      for (int r = 0; r < 36; r++)
+        s.Tpl[f][r % Q36] = T[r];
+      for (int k = 0; k < 6; k++)
+      {
+        double a = 0;
+        for (int r = 0; r < 6; r++)
+          a += T[6 * r + k] * Wr[r];
+        s.Wfr[f][k % FS] = a;
+      }
+    }
+    return 0.5 * cst;
+  }
+
   template <class Cfg, bool DERIVS>
   SMPC_DEV void full_stage_knot(const DevModel & M, const DevOcp & O, const KnotLayout & L, const KnotIO & io, FullScratch<Cfg> & s)
   {
     constexpr int NV = Cfg::NV, NQ = Cfg::NQ, NX = Cfg::NX, NDX = Cfg::NDX, NU = Cfg::NU, NK = Cfg::NK, NJ = Cfg::NJ;
-    constexpr int NJNT = Cfg::NJNT, NCOL = Cfg::NCOL, NZ = Cfg::NZ;
+    constexpr int NJNT = Cfg::NJNT, NCOL = Cfg::NCOL, NZ = Cfg::NZ, FS = Cfg::FS, CD = Cfg::CD;
     const smpc_model_desc & d = M.d;
     const smpc_slot & slot = *io.slot;
     const unsigned cmask = slot.contact_mask;
@@ -215,7 +415,7 @@ namespace smpc
         int n = 0;
         for (int f = 0; f < NK; f++)
           s.cidx[f] = (cmask & (1u << f)) ? n++ : -1;
-        s.ncon = 3 * n;
+        s.ncon = CD * n;
         s.Cx = reinterpret_cast<double(*)[NDX]>(io.knot + L.oC);
         s.Cu = reinterpret_cast<double(*)[NU]>(io.knot + L.oD);
         // constraint rows in the reference's insertion order (src/fulldynamics.cpp:145-211)
@@ -231,13 +431,15 @@ namespace smpc
           if (!(cmask & (1u << f)))
             continue;
           if (O.force_cone)
-            for (int r = 0; r < 5; r++, row++)
+            for (int r = 0; r < Cfg::NCONE; r++, row++)
               s.rkind[row] = FROW_CONE, s.rarg[row] = f, s.rsub[row] = r;
           if (O.land_cstr && (slot.land_mask & (1u << f)))
           {
-            for (int r = 0; r < 3; r++, row++)
+            // point feet: 3 LWA velocity rows + the height; quad feet: the 6-D LWA velocity (reference src/fulldynamics.cpp:175-209)
+            for (int r = 0; r < (FS == 6 ? 6 : 3); r++, row++)
               s.rkind[row] = FROW_LVEL, s.rarg[row] = f, s.rsub[row] = r;
-            s.rkind[row] = FROW_LZ, s.rarg[row] = f, s.rsub[row] = 2, row++;
+            if (FS == 3)
+              s.rkind[row] = FROW_LZ, s.rarg[row] = f, s.rsub[row] = 2, row++;
           }
         }
         s.nc = row;
@@ -287,10 +489,20 @@ namespace smpc
           if (cf < 0)
             continue;
           const int jf = d.foot_joint[f];
-          double l3[3] = {0, 0, 0};
-          if ((M.anc_mask[jf] >> M.joint_of_dof[c]) & 1u)
+          const bool on = (M.anc_mask[jf] >> M.joint_of_dof[c]) & 1u;
+          const double Jm[6] = {s.J[0][c], s.J[1][c], s.J[2][c], s.J[3][c], s.J[4][c], s.J[5][c]};
+          if (FS == 6)
           {
-            const double Jm[6] = {s.J[0][c], s.J[1][c], s.J[2][c], s.J[3][c], s.J[4][c], s.J[5][c]};
+            double Jl[6] = {0, 0, 0, 0, 0, 0};
+            if (on)
+              frame_motion_lwa(Jm, s.fp[f], Jl);
+            for (int r = 0; r < CD; r++)
+              s.Jc[CD * cf + r][c] = Jl[r];
+            continue;
+          }
+          double l3[3] = {0, 0, 0};
+          if (on)
+          {
             double wxp[3], c3[3];
             v3cross(Jm + 3, s.fp[f], wxp);
             for (int r = 0; r < 3; r++)
@@ -307,6 +519,14 @@ namespace smpc
           if (cf < 0)
             continue;
           const int jf = d.foot_joint[f];
+          if (FS == 6)
+          {
+            double g6[6];
+            full6_gamma<Cfg, DERIVS>(O, s, f, jf, g6);
+            for (int r = 0; r < CD; r++)
+              s.gamma[CD * cf + r] = g6[r];
+            continue;
+          }
           double pd[3], pdd[3], a1[3], a2[3], a3[3];
           point_va(s.v[jf], s.a[jf], s.fp[f], pd, pdd);
           m3tv(s.fR[f], pdd, a1);
@@ -433,7 +653,7 @@ namespace smpc
         for (int k = tid; k < 3 * NK; k += SMPC_NT)
         {
           const int cf = s.cidx[k / 3];
-          io.fc[k] = (cf >= 0) ? s.lam[3 * cf + k % 3] : 0.0;
+          io.fc[k] = (cf >= 0) ? s.lam[CD * cf + k % 3] : 0.0; // linear part (reference src/mpc.cpp:369)
         }
     }
     SMPC_END
@@ -456,8 +676,19 @@ namespace smpc
             if (cf < 0 || !((M.anc_mask[d.foot_joint[f]] >> i) & 1u))
               continue;
             double fw[3], nw[3];
-            m3v(s.fR[f], &s.lam[3 * cf], fw);
-            v3cross(s.fp[f], fw, nw);
+            if (FS == 6)
+            {
+              for (int r = 0; r < 3; r++)
+                fw[r] = s.lam[CD * cf + r];
+              v3cross(s.fp[f], fw, nw);
+              for (int r = 0; r < 3; r++)
+                nw[r] += s.lam[CD * cf + (FS == 6 ? 3 : 0) + r];
+            }
+            else
+            {
+              m3v(s.fR[f], &s.lam[3 * cf], fw);
+              v3cross(s.fp[f], fw, nw);
+            }
             for (int r = 0; r < 3; r++)
             {
               F[r] -= fw[r];
@@ -492,15 +723,10 @@ namespace smpc
             s.dh_dq[r][j] = o1[r];
           for (int f = 0; f < NK; f++)
           {
-            double jp[3] = {0, 0, 0};
+            double jp[6] = {0, 0, 0, 0, 0, 0};
             if ((M.anc_mask[d.foot_joint[f]] >> i) & 1u)
-            {
-              double t[3];
-              v3cross(Jm + 3, s.fp[f], t);
-              for (int r = 0; r < 3; r++)
-                jp[r] = Jm[r] + t[r];
-            }
-            for (int r = 0; r < 3; r++)
+              frame_motion_lwa(Jm, s.fp[f], jp);
+            for (int r = 0; r < FS; r++)
               s.Jp[f][r][j] = jp[r];
           }
         }
@@ -571,6 +797,25 @@ namespace smpc
               vv += s.J[r][j] * Tv[r];
             }
           }
+          if (FS == 6)
+          {
+            // forces held in world-aligned axes do not turn with the foot (see the header)
+            for (int f = 0; f < NK; f++)
+            {
+              const int cf = s.cidx[f];
+              const unsigned am = M.anc_mask[d.foot_joint[f]];
+              if (cf < 0 || !((am >> ic) & 1u) || !((am >> ij) & 1u))
+                continue;
+              const double * lf = &s.lam[CD * cf];
+              const double wc[3] = {s.J[3][c], s.J[4][c], s.J[5][c]};
+              double g[3], pg[3], wt[3];
+              v3cross(wc, lf, g);
+              v3cross(s.fp[f], g, pg);
+              v3cross(wc, lf + (FS == 6 ? 3 : 0), wt);
+              for (int r = 0; r < 3; r++)
+                vq += s.J[r][j] * g[r] + s.J[3 + r][j] * (pg[r] + wt[r]);
+            }
+          }
           s.X1[j][c] = -vq;
           s.X1[j][NV + c] = -vv;
           s.X1[j][2 * NV + c] = (j == c) ? 1.0 : 0.0;
@@ -583,6 +828,19 @@ namespace smpc
             continue;
           const int jf = d.foot_joint[f];
           const int ic = M.joint_of_dof[c];
+          if (FS == 6)
+          {
+            double dq6[6] = {0, 0, 0, 0, 0, 0}, dv6[6] = {0, 0, 0, 0, 0, 0};
+            if ((M.anc_mask[jf] >> ic) & 1u)
+              full6_contact_derivs<Cfg>(M, O, s, f, jf, c, dq6, dv6);
+            for (int r = 0; r < CD; r++)
+            {
+              s.DL[CD * cf + r][c] = -dq6[r];
+              s.DL[CD * cf + r][NV + c] = -dv6[r];
+              s.DL[CD * cf + r][2 * NV + c] = 0.0;
+            }
+            continue;
+          }
           double dcq[3] = {0, 0, 0}, dcv[3] = {0, 0, 0};
           if ((M.anc_mask[jf] >> ic) & 1u)
           {
@@ -735,22 +993,23 @@ namespace smpc
             sacc += O.w_cent[6 * r + k] * (a < NV ? s.dh_dq[k][a] : s.Ag[k][a - NV]);
           s.WJc[r][a] = sacc;
         }
-        for (int e = tid; e < NK * 3 * NV; e += SMPC_NT)
-        {
-          const int f = e / (3 * NV), r = (e / NV) % 3, a = e % NV;
-          double sacc = 0;
-          for (int k = 0; k < 3; k++)
-            sacc += O.w_frame[3 * r + k] * s.Jp[f][k][a];
-          s.WJp[f][r][a] = sacc;
-        }
+        if (FS == 3)
+          for (int e = tid; e < NK * 3 * NV; e += SMPC_NT)
+          {
+            const int f = e / (3 * NV), r = (e / NV) % 3, a = e % NV;
+            double sacc = 0;
+            for (int k = 0; k < 3; k++)
+              sacc += O.w_frame[3 * r + k] * s.Jp[f][k][a];
+            s.WJp[f][r][a] = sacc;
+          }
         for (int e = tid; e < ncon * NZ; e += SMPC_NT)
         {
           const int row = e / NZ, a = e % NZ;
-          const int cf = row / 3, r = row % 3;
+          const int cf = row / CD, r = row % CD;
           const int col = (a < NDX) ? a : 2 * NV + 6 + (a - NDX);
           double sacc = 0;
-          for (int k = 0; k < 3; k++)
-            sacc += O.w_forces[3 * r + k] * s.DL[3 * cf + k][col];
+          for (int k = 0; k < CD; k++)
+            sacc += O.w_forces[CD * r + k] * s.DL[CD * cf + k][col];
           s.WJl[row][a] = sacc;
         }
       }
@@ -790,18 +1049,23 @@ namespace smpc
       if (tid >= 2 && tid < 2 + NK)
       {
         const int f = tid - 2;
-        double rf[3], cst = 0;
-        for (int r = 0; r < 3; r++)
-          rf[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
-        for (int r = 0; r < 3; r++)
+        if (FS == 6)
+          s.costs[3 + f] = full6_pose_cost<Cfg, DERIVS>(O, slot, s, f);
+        else
         {
-          double a = 0;
-          for (int k = 0; k < 3; k++)
-            a += O.w_frame[3 * r + k] * rf[k];
-          s.Wfr[f][r] = a;
-          cst += rf[r] * a;
+          double rf[3], cst = 0;
+          for (int r = 0; r < 3; r++)
+            rf[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
+          for (int r = 0; r < 3; r++)
+          {
+            double a = 0;
+            for (int k = 0; k < 3; k++)
+              a += O.w_frame[3 * r + k] * rf[k];
+            s.Wfr[f][r] = a;
+            cst += rf[r] * a;
+          }
+          s.costs[3 + f] = 0.5 * cst;
         }
-        s.costs[3 + f] = 0.5 * cst;
       }
       if (tid >= 2 + NK && tid < 2 + 2 * NK)
       {
@@ -810,15 +1074,15 @@ namespace smpc
         double cst = 0;
         if (cf >= 0)
         {
-          double rl[3];
-          for (int r = 0; r < 3; r++)
-            rl[r] = s.lam[3 * cf + r] - slot.f_ref[f][r];
-          for (int r = 0; r < 3; r++)
+          double rl[CD];
+          for (int r = 0; r < CD; r++)
+            rl[r] = s.lam[CD * cf + r] - slot.f_ref[f][r];
+          for (int r = 0; r < CD; r++)
           {
             double a = 0;
-            for (int k = 0; k < 3; k++)
-              a += O.w_forces[3 * r + k] * rl[k];
-            s.Wlr[3 * cf + r] = a;
+            for (int k = 0; k < CD; k++)
+              a += O.w_forces[CD * r + k] * rl[k];
+            s.Wlr[CD * cf + r] = a;
             cst += rl[r] * a;
           }
         }
@@ -859,16 +1123,17 @@ namespace smpc
         else if (kind == FROW_CONE)
         {
           const int cf = s.cidx[f];
-          for (int k = 0; k < 3; k++)
-            c += O.pyramid[3 * sub + k] * s.lam[3 * cf + k];
+          const double * Ac = (FS == 6) ? O.wcone : O.pyramid; // 17 x 6 wrench cone on [f; tau] / 5 x 3 friction pyramid
+          for (int k = 0; k < CD; k++)
+            c += Ac[CD * sub + k] * s.lam[CD * cf + k];
           type = 1;
         }
         else if (kind == FROW_LVEL)
         {
           const int jf = d.foot_joint[f];
-          double wxp[3];
-          v3cross(s.v[jf] + 3, s.fp[f], wxp);
-          c = s.v[jf][sub] + wxp[sub];
+          double V[6];
+          frame_motion_lwa(s.v[jf], s.fp[f], V);
+          c = V[sub];
         }
         else
           c = s.fp[f][2] - slot.land_z[f];
@@ -876,6 +1141,29 @@ namespace smpc
         s.lo[row] = lo;
         s.hi[row] = hi;
         s.ctype[row] = type;
+      }
+      if (DERIVS && FS == 6)
+      {
+        // pose cost of a quad foot: residual Jacobian T Jp (T from full6_pose_cost, previous phase); weighted: (T^T W T) Jp
+        constexpr int Q36 = FullScratch<Cfg>::Q36;
+        for (int e = tid; e < NK * FS * NV; e += SMPC_NT)
+        {
+          const int f = e / (FS * NV), r = (e / NV) % FS, a = e % NV;
+          double sacc = 0;
+          for (int i2 = 0; i2 < 6; i2++)
+          {
+            double wtj = 0; // (W T Jp)(i2, a)
+            for (int j2 = 0; j2 < 6; j2++)
+            {
+              double tj = 0; // (T Jp)(j2, a)
+              for (int k = 0; k < 6; k++)
+                tj += s.Tpl[f][(6 * j2 + k) % Q36] * s.Jp[f][k % FS][a];
+              wtj += O.w_frame[6 * i2 + j2] * tj;
+            }
+            sacc += s.Tpl[f][(6 * i2 + r) % Q36] * wtj;
+          }
+          s.WJp[f][r][a] = sacc;
+        }
       }
       if (DERIVS)
       {
@@ -892,8 +1180,9 @@ namespace smpc
           {
             const int cf = s.cidx[f];
             const int col = (a < NDX) ? a : 2 * NV + 6 + (a - NDX);
-            for (int k = 0; k < 3; k++)
-              val += O.pyramid[3 * sub + k] * s.DL[3 * cf + k][col];
+            const double * Ac = (FS == 6) ? O.wcone : O.pyramid;
+            for (int k = 0; k < CD; k++)
+              val += Ac[CD * sub + k] * s.DL[CD * cf + k][col];
           }
           else if (kind == FROW_LVEL)
           {
@@ -913,13 +1202,18 @@ namespace smpc
                   dvp[r] = ((par >= 0) ? s.v[par][r] : 0.0) - vi[r];
                 }
                 mxm(dvp, Jm, dvq);
-                v3cross(dvq + 3, s.fp[f], t1);
-                v3cross(vi + 3, jp, t2);
-                val = dvq[sub] + t1[sub] + t2[sub];
+                if (sub < 3)
+                {
+                  v3cross(dvq + 3, s.fp[f], t1);
+                  v3cross(vi + 3, jp, t2);
+                  val = dvq[sub] + t1[sub] + t2[sub];
+                }
+                else
+                  val = dvq[sub]; // angular rows of the 6-D landing velocity
               }
             }
             else if (a < NDX)
-              val = s.Jp[f][sub][a - NV];
+              val = s.Jp[f][sub % FS][a - NV];
           }
           else
             val = (a < NV) ? s.Jp[f][2][a] : 0.0;
@@ -961,7 +1255,7 @@ namespace smpc
             for (int f = 0; f < NK; f++)
             {
               double tf = 0;
-              for (int r = 0; r < 3; r++)
+              for (int r = 0; r < FS; r++)
                 tf += s.Jp[f][r][a] * s.WJp[f][r][b];
               acc += tf;
             }
@@ -1012,7 +1306,7 @@ namespace smpc
             for (int f = 0; f < NK; f++)
             {
               double tf = 0;
-              for (int r = 0; r < 3; r++)
+              for (int r = 0; r < FS; r++)
                 tf += s.Jp[f][r][a] * s.Wfr[f][r];
               g += tf;
             }

@@ -154,9 +154,7 @@ namespace smpc
     }
     else
     {
-      // FullDynamicsOCP (reference src/fulldynamics.cpp:30-76): nu = nv - 6, rigid point contacts
-      if (O.fs != 3)
-        throw std::runtime_error("ocp: full dynamics with 6-D contacts is not supported by the CUDA path yet");
+      // FullDynamicsOCP (reference src/fulldynamics.cpp:30-76): nu = nv - 6, rigid contacts (3-D point or 6-D quad feet)
       O.nx = m.nq + m.nv;
       O.ndx = 2 * m.nv;
       O.nu = nj;
@@ -169,8 +167,8 @@ namespace smpc
       for (int i = 0; i < O.nu; i++)
         O.w_u[i] = o.w_u[i * O.nu + i];
       cp(O.w_cent, o.w_cent, 36, "w_cent");
-      cp(O.w_frame, o.w_frame, 9, "w_frame");
-      cp(O.w_forces, o.w_forces, 9, "w_forces");
+      cp(O.w_frame, o.w_frame, O.fs * O.fs, "w_frame");
+      cp(O.w_forces, o.w_forces, O.fs * O.fs, "w_forces");
       O.torque_limits = o.torque_limits;
       if (o.torque_limits)
       {
@@ -182,17 +180,19 @@ namespace smpc
         cp(O.qmin, o.qmin, nj, "qmin");
         cp(O.qmax, o.qmax, nj, "qmax");
       }
-      for (int k = 0; k < 3; k++)
+      for (int k = 0; k < O.fs; k++)
       {
         O.Kp[k] = o.Kp_correction[k];
         O.Kd[k] = o.Kd_correction[k];
       }
+      build_wrench_cone(o.mu, o.Lfoot, o.Wfoot, O.wcone);
       const double pyr[5][3] = {{0, 0, -1}, {-1, 0, -o.mu}, {1, 0, -o.mu}, {0, -1, -o.mu}, {0, 1, -o.mu}};
       memcpy(O.pyramid, pyr, sizeof(pyr));
       for (int i = 1; i < m.njoints; i++)
         if (m.idx_v[m.parent[i]] >= m.idx_v[i])
           throw std::runtime_error("model: velocity indices must increase from parent to child");
-      O.ncmax = (o.torque_limits ? nj : 0) + (o.kinematics_limits ? nj : 0) + O.nk * ((o.force_cone ? 5 : 0) + (o.land_cstr ? 4 : 0));
+      O.ncmax = (o.torque_limits ? nj : 0) + (o.kinematics_limits ? nj : 0)
+                + O.nk * ((o.force_cone ? (O.fs == 6 ? 17 : 5) : 0) + (o.land_cstr ? (O.fs == 6 ? 6 : 4) : 0));
       O.nct = o.terminal_constraint ? 3 : 0;
     }
     if (O.ncmax < O.nct)

@@ -726,28 +726,36 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   A.SL = make_sol_layout(O.ndx, O.nu, O.ncmax);
   A.RS = make_ric_smem(O.ndx, O.nu, O.ncmax);
   A.FS = make_fwd_smem(O.ndx, O.nu, O.ncmax);
-  CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(A.FS.size * sizeof(double))));
   // which forward kernel: the TMA-staged one has the lower latency per instance (two CTAs per SM), the direct one the
-  // higher throughput once the batch is many waves deep (SMPC_FWD_STAGED_MAX_WAVES, measured; SMPC_FWD overrides)
+  // higher throughput once the batch is many waves deep (SMPC_FWD_STAGED_MAX_WAVES, measured; SMPC_FWD overrides).
+  // Shapes whose two landing buffers exceed the shared memory of an SM use the direct kernel.
   {
+    const size_t fwd_bytes = (size_t)A.FS.size * sizeof(double);
+    const bool fits = fwd_bytes <= 232448 - 64;
     const int per_wave = 2 * (c->hmodel_sms > 0 ? c->hmodel_sms : 148);
     c->forward_staged = batch <= SMPC_FWD_STAGED_MAX_WAVES * per_wave;
     if (const char * e = getenv("SMPC_FWD"))
       c->forward_staged = strcmp(e, "direct") != 0;
+    c->forward_staged = c->forward_staged && fits;
+    if (fits)
+      CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_bytes));
   }
   A.opt = *opts;
   // kernel instantiation for this (robot, problem) shape; each family lives in its own translation unit
   int rc = SMPC_ERR_UNSUPPORTED;
   const bool go2_shape = model->njoints == 13 && model->nv == 18 && O.nk == 4 && O.fs == 3;
+  const bool talos_shape = model->njoints == 23 && model->nv == 28 && O.nk == 2 && O.fs == 6;
   if (O.kind == SMPC_OCP_KINODYNAMICS && go2_shape)
     rc = setup_knots_kino_go2(c);
   else if (O.kind == SMPC_OCP_FULLDYNAMICS && go2_shape)
     rc = setup_knots_full_go2(c);
+  else if (O.kind == SMPC_OCP_FULLDYNAMICS && talos_shape)
+    rc = setup_knots_full_talos(c);
   else if (O.kind == SMPC_OCP_CENTROIDAL && ((O.nk == 2 && O.fs == 6) || (O.nk == 4 && O.fs == 3)))
     rc = setup_knots_centro(c);
   else
     smpc::err() = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics and full dynamics on a 12-DoF quadruped with "
-                  "point feet; centroidal with 2 quad feet or 4 point feet)";
+                  "point feet; full dynamics on a 22-DoF biped with quad feet; centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
     return rc;
   // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax)

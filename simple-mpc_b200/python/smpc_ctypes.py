@@ -392,6 +392,56 @@ def go2_full_ocp(m, limits, T=50, force_cone=False, land_cstr=False, kinematics_
     return OcpBundle(d, arrays)
 
 
+def talos_full_ocp(m, limits, T=100, force_cone=True, land_cstr=False, kinematics_limits=True, torque_limits=True,
+                   terminal_constraint=False, Kp=(0.0, 0.0, 50.0, 0.0, 0.0, 0.0), Kd=(100.0,) * 6):
+    """Problem recipe of reference examples/talos_fulldynamics.py:48-95 (C4 of SURVEY.md §8d): 6-D contacts, wrench cones,
+    torque + joint limits, Baumgarte Kp = [0, 0, 50, 0, 0, 0], Kd = 100."""
+    nv = m.nv
+    w_basepos, w_legpos, w_torsopos, w_armpos = [0, 0, 0, 10, 10, 10], [0.1] * 6, [1, 100], [1, 1, 10, 10]
+    w_basevel, w_legvel, w_torsovel, w_armvel = [10] * 6, [1] * 6, [1, 100], [10] * 4
+    w_x = np.diag(np.array(w_basepos + w_legpos * 2 + w_torsopos + w_armpos * 2 + w_basevel + w_legvel * 2 + w_torsovel + w_armvel * 2, float))
+    arrays = dict(w_x=np.ascontiguousarray(w_x), w_u=np.eye(nv - 6) * 1e-4, w_cent=np.diag([0.1, 0.1, 10, 0.1, 0.1, 10.0]),
+                  w_forces=np.eye(6) * 0.001, w_frame=np.eye(6) * 2000.0, qmin=limits["qmin"].copy(), qmax=limits["qmax"].copy(),
+                  umin=limits["umin"].copy(), umax=limits["umax"].copy())
+    d = OcpDesc()
+    d.kind, d.horizon, d.force_size = FULL, T, 6
+    d.kinematics_limits, d.torque_limits = int(kinematics_limits), int(torque_limits)
+    d.force_cone, d.land_cstr = int(force_cone), int(land_cstr)
+    d.terminal_constraint = int(terminal_constraint)
+    d.timestep = 0.01
+    d.gravity[:] = [0, 0, -9.81]
+    d.mu, d.Lfoot, d.Wfoot = 0.8, 0.1, 0.075
+    d.Kp_correction[:] = Kp
+    d.Kd_correction[:] = Kd
+    for k, v in arrays.items():
+        setattr(d, k, _p(v))
+    return OcpBundle(d, arrays)
+
+
+def talos_kino_ocp(m, limits, T=100, force_cone=True, kinematics_limits=True, terminal_constraint=False):
+    """Problem recipe of reference examples/talos_kinodynamics.py:44-112: 6-D contact wrenches as controls,
+    CentroidalWrenchCone + 6-D LOCAL frame-velocity equality per stance foot (reference src/kinodynamics.cpp:104-121)."""
+    nv = m.nv
+    w_basepos, w_legpos, w_torsopos, w_armpos = [0, 0, 1000, 1000, 1000, 1000], [0.1] * 6, [1, 1000], [1, 1, 10, 10]
+    w_basevel, w_legvel, w_torsovel, w_armvel = [10] * 6, [1] * 6, [0.1, 100], [10] * 4
+    w_x = 10.0 * np.diag(np.array(w_basepos + w_legpos * 2 + w_torsopos + w_armpos * 2 + w_basevel + w_legvel * 2 + w_torsovel + w_armvel * 2, float))
+    w_force = [0.001, 0.001, 0.01, 0.1, 0.1, 0.1]
+    w_u = np.diag(np.array(w_force * 2 + [1e-4] * (nv - 6), float))
+    arrays = dict(w_x=np.ascontiguousarray(w_x), w_u=np.ascontiguousarray(w_u), w_cent=np.diag([0.0, 0.0, 1, 0.1, 0.1, 10.0]),
+                  w_centder=np.diag([0.0, 0, 0, 0.1, 0.1, 0.1]), w_frame=np.eye(6) * 100000.0,
+                  qmin=limits["qmin"].copy(), qmax=limits["qmax"].copy())
+    d = OcpDesc()
+    d.kind, d.horizon, d.force_size = KINO, T, 6
+    d.kinematics_limits, d.force_cone, d.land_cstr = int(kinematics_limits), int(force_cone), 0
+    d.terminal_constraint = int(terminal_constraint)
+    d.timestep = 0.01
+    d.gravity[:] = [0, 0, -9.81]
+    d.mu, d.Lfoot, d.Wfoot = 0.8, 0.1, 0.075
+    for k, v in arrays.items():
+        setattr(d, k, _p(v))
+    return OcpBundle(d, arrays)
+
+
 def full_slot(m, ocp_bundle, foot_poses, contact_mask=None, land_mask=0):
     """Slot of a stage created by FullDynamicsOCP::createStage (reference src/fulldynamics.cpp:78-214):
     control target 0 (:89), force reference mg/nk on every stance foot (examples/go2_fulldynamics.py:40)."""

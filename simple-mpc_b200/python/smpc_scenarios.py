@@ -9,7 +9,8 @@ also point it at the CPU oracle, prefix "orc", which mirrors the same signatures
 import ctypes as C
 import numpy as np
 from smpc_ctypes import (Slot, Terminal, SolveInfo, dbl_p, go2_like_model, go2_kino_ocp, go2_full_ocp, full_slot, standing_slot,
-                         fk_numpy, x_ref_of, total_mass, talos_like_model, talos_centroidal_ocp, centroidal_slot, com_numpy)
+                         fk_numpy, x_ref_of, total_mass, talos_like_model, talos_centroidal_ocp, centroidal_slot, com_numpy,
+                         talos_full_ocp, talos_kino_ocp)
 
 
 def P(a):
@@ -349,3 +350,119 @@ class TalosCentroidalScenario:
             x[i, 0:3] += r.normal(size=3) * (0.005 if tick == 0 else 0.001)
             x[i, 3:9] += r.normal(size=6) * (0.5 if tick == 0 else 0.1)
         return x
+
+
+class TalosFullScenario:
+    """Config C4 of SURVEY.md §8d on the synthetic talos-like biped: FullDynamicsOCP with 6-D rigid contacts (CONTACT_6D,
+    LOCAL_WORLD_ALIGNED, Baumgarte Kp = [0,0,50,0,0,0], Kd = 100), wrench cones, torque + joint limits, T = 100, walk
+    20 DS / 80 SS / 20 DS / 80 SS (reference examples/talos_fulldynamics.py:48-135)."""
+
+    GAIT = [0b11] * 20 + [0b01] * 80 + [0b11] * 20 + [0b10] * 80  # left = bit0, right = bit1
+    CYCLE = 200
+    T_FLY, T_CONTACT = 80, 20
+    multibody_state = True
+    KIND = "full"
+
+    def __init__(self, batch, seed=0, T=100, first=0, **ocp_kw):
+        self.B, self.T = batch, T
+        self.model, self.limits = talos_like_model()
+        self.ocpb = self.make_ocp(T, **ocp_kw)
+        self.nq, self.nv = self.model.nq, self.model.nv
+        self.nx, self.ndx = self.nq + self.nv, 2 * self.nv
+        self.nu = self.nv - 6 + (12 if self.KIND == "kino" else 0)
+        self.xref = x_ref_of(self.model)
+        self.feet = fk_numpy(self.model, self.xref[: self.nq])["feet"]
+        self.mass = total_mass(self.model)
+        rngs = [np.random.default_rng([seed, first + i]) for i in range(batch)]  # global instance index = stream
+        self.phase = np.array([int(r.integers(0, self.CYCLE)) for r in rngs])
+        self.noise = rngs
+        self.vbase = np.zeros((batch, 6))
+        self.vbase[:, 0] = 0.1      # reference examples/talos_fulldynamics.py:170-172
+
+    def make_ocp(self, T, **kw):
+        return talos_full_ocp(self.model, self.limits, T=T, **kw)
+
+    def gait_slot(self, k):
+        mask = self.GAIT[k % self.CYCLE]
+        prev = self.GAIT[(k - 1) % self.CYCLE]
+        s = full_slot(self.model, self.ocpb, self.feet, contact_mask=mask, land_mask=mask & ~prev)
+        return s
+
+    def stage_table(self):
+        n = len(self.GAIT)
+        return (Slot * (n + 1))(*([self.gait_slot(k) for k in range(n)] + [self.gait_slot(0)])), n
+
+    def initial_slots(self):
+        s = self.gait_slot(0)
+        return (Slot * (self.B * self.T))(*([s] * (self.B * self.T)))
+
+    def terminals(self):
+        t = Terminal()
+        t.x_ref[: self.nx] = self.xref
+        c = com_numpy(self.model, self.xref[: self.nq])
+        t.com_ref[:] = c
+        t.tau = np.sqrt(c[2] / 9.81)
+        return (Terminal * self.B)(*([t] * self.B))
+
+    def warmstart(self):
+        xs = np.tile(self.xref, (self.B, self.T + 1, 1)).copy()
+        us = np.tile(np.array(self.gait_slot(0).u_ref[: self.nu]), (self.B, self.T, 1)).copy()
+        return xs, us
+
+    def x_start(self):
+        xs = np.tile(self.xref, (self.B, 1))
+        for i, r in enumerate(self.noise):
+            xs[i, 7:self.nq] += r.normal(size=self.nq - 7) * 0.01
+            xs[i, 0:3] += r.normal(size=3) * 0.005
+            xs[i, self.nq:] += r.normal(size=self.nv) * 0.02
+        return xs
+
+    def xmeas_start(self):
+        return self.x_start()
+
+    def next_measurement(self, xm, x1, noise):
+        x = np.array(x1, float)
+        if noise is not None:
+            x[:, self.nq:] += noise
+        return x
+
+    def tails(self, tick):
+        arr = (Slot * self.B)()
+        for i in range(self.B):
+            arr[i] = self.gait_slot(int(self.phase[i]) + tick)
+        return arr
+
+    def disturb(self, x, tick):
+        for i, r in enumerate(self.noise):
+            x[i, self.nq:] += r.normal(size=self.nv) * (0.02 if tick == 0 else 0.005)
+            if tick == 0:
+                x[i, 7:self.nq] += r.normal(size=self.nq - 7) * 0.01
+        return x
+
+    def mean_active_rows(self):
+        d = self.ocpb.desc
+        rows = []
+        for k in range(len(self.GAIT)):
+            mask, prev = self.GAIT[k], self.GAIT[k - 1]
+            nst, nland = bin(mask).count("1"), bin(mask & ~prev).count("1")
+            rows.append((self.nv - 6) * (d.kinematics_limits + d.torque_limits) + nst * 17 * d.force_cone + nland * 6 * d.land_cstr)
+        return float(np.mean(rows))
+
+
+class TalosKinoScenario(TalosFullScenario):
+    """Talos-like kinodynamics (reference examples/talos_kinodynamics.py:44-130): 6-D contact wrenches as controls,
+    6-D LOCAL frame-velocity equalities on the stance feet, optional CentroidalWrenchCone; T = 100, walk 20/80/20/80."""
+
+    KIND = "kino"
+
+    def make_ocp(self, T, **kw):
+        return talos_kino_ocp(self.model, self.limits, T=T, **kw)
+
+    def gait_slot(self, k):
+        mask = self.GAIT[k % self.CYCLE]
+        nact = bin(mask).count("1")
+        return standing_slot(self.model, self.ocpb, self.feet, contact_mask=mask, land_mask=0, force_z=self.mass * 9.81 / max(nact, 1))
+
+    def mean_active_rows(self):
+        d = self.ocpb.desc
+        return float(np.mean([(self.nv - 6) * d.kinematics_limits + bin(m).count("1") * (6 + 17 * d.force_cone) for m in self.GAIT]))

@@ -40,6 +40,30 @@ static void centro_knot_any(const DevOcp & O, const KnotLayout & L, const KnotIO
   }
 }
 
+// one full-dynamics knot of shape FCfg (terminal node: the kinodynamics one of shape TCfg)
+template <class FCfg, class TCfg>
+static void full_knot_any(const DevModel & M, const DevOcp & O, const KnotLayout & L, const KnotIO & io, bool terminal, bool derivs)
+{
+  if (terminal)
+  {
+    auto s = std::make_unique<KinoScratch<TCfg>>();
+    memset(s.get(), 0, sizeof(*s));
+    if (derivs)
+      kino_terminal_knot<TCfg, true>(M, O, L, io, *s);
+    else
+      kino_terminal_knot<TCfg, false>(M, O, L, io, *s);
+  }
+  else
+  {
+    auto s = std::make_unique<FullScratch<FCfg>>();
+    memset(s.get(), 0, sizeof(*s));
+    if (derivs)
+      full_stage_knot<FCfg, true>(M, O, L, io, *s);
+    else
+      full_stage_knot<FCfg, false>(M, O, L, io, *s);
+  }
+}
+
 extern "C" {
 const char * emul_last_error() { return g_err.c_str(); }
 
@@ -95,8 +119,9 @@ int emul_kino_knot(
   return 0;
 }
 
-// one full-dynamics knot (Go2 sizes, point feet); same argument meaning as emul_kino_knot. The terminal node is
-// the kinodynamics one (reference src/fulldynamics.cpp:418-445 builds the same terminal cost / constraint).
+// one full-dynamics knot (Go2 sizes with point feet, or talos-like sizes with quad feet); same argument meaning as
+// emul_kino_knot. The terminal node is the kinodynamics one (reference src/fulldynamics.cpp:418-445 builds the same
+// terminal cost / constraint).
 int emul_full_knot(
   const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const smpc_terminal * term, int terminal,
   int derivs, const double * x, const double * u, const double * xn, const double * vs, const double * prev_vs,
@@ -105,13 +130,14 @@ int emul_full_knot(
 {
   try
   {
-    typedef FullCfg<13, 18, 4> FCfg;
     auto M = std::make_unique<DevModel>();
     auto O = std::make_unique<DevOcp>();
     build_dev_model(*model, *M);
     build_dev_ocp(*model, *ocp, *O);
-    if (O->kind != SMPC_OCP_FULLDYNAMICS || model->njoints != 13 || model->nv != 18 || model->nfeet != 4 || O->fs != 3)
-      throw std::runtime_error("emul: only the Go2-sized full-dynamics instantiation is built");
+    const bool go2 = model->njoints == 13 && model->nv == 18 && model->nfeet == 4 && O->fs == 3;
+    const bool talos = model->njoints == 23 && model->nv == 28 && model->nfeet == 2 && O->fs == 6;
+    if (O->kind != SMPC_OCP_FULLDYNAMICS || !(go2 || talos))
+      throw std::runtime_error("emul: only the Go2-sized (point feet) and talos-sized (quad feet) full-dynamics instantiations are built");
     KnotLayout L = make_knot_layout(O->ndx, O->nu, O->ncmax);
     KnotIO io;
     memset(&io, 0, sizeof(io));
@@ -123,24 +149,10 @@ int emul_full_knot(
     KnotScalars sc;
     memset(&sc, 0, sizeof(sc));
     io.sc = &sc;
-    if (terminal)
-    {
-      auto s = std::make_unique<KinoScratch<Go2Cfg>>();
-      memset(s.get(), 0, sizeof(*s));
-      if (derivs)
-        kino_terminal_knot<Go2Cfg, true>(*M, *O, L, io, *s);
-      else
-        kino_terminal_knot<Go2Cfg, false>(*M, *O, L, io, *s);
-    }
+    if (go2)
+      full_knot_any<FullCfg<13, 18, 4>, Go2Cfg>(*M, *O, L, io, terminal != 0, derivs != 0);
     else
-    {
-      auto s = std::make_unique<FullScratch<FCfg>>();
-      memset(s.get(), 0, sizeof(*s));
-      if (derivs)
-        full_stage_knot<FCfg, true>(*M, *O, L, io, *s);
-      else
-        full_stage_knot<FCfg, false>(*M, *O, L, io, *s);
-    }
+      full_knot_any<FullCfg<23, 28, 2, 6>, KinoCfg<23, 28, 2, 6>>(*M, *O, L, io, terminal != 0, derivs != 0);
     memcpy(scalars, &sc, sizeof(sc));
   }
   catch (const std::exception & e)

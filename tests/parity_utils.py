@@ -3,13 +3,23 @@ the same C-ABI call sequence (smpc_scenarios.Backend) and compares the results."
 import ctypes as C
 import numpy as np
 from smpc_ctypes import SolverOpts, load_cuda
-from smpc_scenarios import P, Backend, Go2Scenario, Go2FullScenario, TalosCentroidalScenario  # noqa: F401
+from smpc_scenarios import (P, Backend, Go2Scenario, Go2FullScenario, TalosCentroidalScenario, TalosFullScenario,  # noqa: F401
+                            TalosKinoScenario)
 from oracle_libs import load_oracle
 
 
 def relerr(a, b):
     den = max(np.abs(b).max(), 1e-300)
     return float(np.abs(a - b).max() / den)
+
+
+def relerr_elem(a, b, floor_frac=1e-3):
+    """ELEMENTWISE relative error with an absolute floor: max_i |a_i - b_i| / max(|b_i|, floor_frac * max|b|). Unlike the
+    normwise figure above it does not hide the small entries of u0 / K0 - the numbers a robot consumes - behind the
+    largest one; entries below floor_frac of the array's scale are compared against that floor."""
+    b = np.asarray(b)
+    den = np.maximum(np.abs(b), floor_frac * max(np.abs(b).max(), 1e-300))
+    return float((np.abs(np.asarray(a) - b) / den).max())
 
 
 def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario=None, **ocp_kw):
@@ -23,7 +33,7 @@ def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario
     assert bytes(opts_o) == bytes(opts_c), "default solver options differ"
     bo = Backend(orc, "orc", sc.model, sc.ocpb, opts_o, batch)
     bc = Backend(cu, "smpc", sc.model, sc.ocpb, opts_c, batch)
-    worst = dict(xs=0.0, us=0.0, K=0.0, k=0.0, iters_equal=True, alphas_equal=True, prim=0.0, dual=0.0)
+    worst = dict(xs=0.0, us=0.0, K=0.0, k=0.0, iters_equal=True, alphas_equal=True, prim=0.0, dual=0.0, u0_elem=0.0, K0_elem=0.0)
     try:
         for b in (bo, bc):
             b.set_slots(sc.initial_slots())
@@ -42,6 +52,9 @@ def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario
                 worst["us"] = max(worst["us"], relerr(uc[i], uo[i]))
                 worst["K"] = max(worst["K"], max(relerr(Kc[i, t], Ko[i, t]) for t in range(sc.T)))
                 worst["k"] = max(worst["k"], relerr(kc[i], ko[i]))
+                # what the controller consumes each tick: u0 and K0, element by element
+                worst["u0_elem"] = max(worst["u0_elem"], relerr_elem(uc[i, 0], uo[i, 0]))
+                worst["K0_elem"] = max(worst["K0_elem"], relerr_elem(Kc[i, 0], Ko[i, 0]))
                 if io[i].num_iters != ic[i].num_iters or io[i].conv != ic[i].conv:
                     worst["iters_equal"] = False
                 if io[i].alpha != ic[i].alpha or io[i].ls_trials != ic[i].ls_trials:

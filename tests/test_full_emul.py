@@ -5,7 +5,8 @@ knots must return the oracle's gains within the conditioning of the penalised re
 import ctypes as C
 import numpy as np
 import pytest
-from smpc_ctypes import (go2_like_model, go2_full_ocp, full_slot, fk_numpy, x_ref_of, default_opts, Slot, Terminal, SolveInfo, dbl_p)
+from smpc_ctypes import (go2_like_model, go2_full_ocp, full_slot, fk_numpy, x_ref_of, default_opts, Slot, Terminal, SolveInfo, dbl_p,
+                         talos_like_model, talos_full_ocp)
 from oracle_libs import load_oracle
 from test_emul_vs_oracle import load_emul, GAIT
 
@@ -14,13 +15,25 @@ def P(a):
     return a.ctypes.data_as(dbl_p)
 
 
-def run_case(cone, kp):
+TALOS_GAIT = [0b11] * 6 + [0b01] * 10 + [0b11] * 6 + [0b10] * 10  # short cycle: every phase and both landing edges inside T
+
+
+def run_case(cone, kp, robot="go2"):
     orc, emu = load_oracle(), load_emul()
-    m, lim = go2_like_model()
-    nq, nv, T = m.nq, m.nv, 50
-    nx, ndx, nu = nq + nv, 2 * nv, 12
-    ocpb = go2_full_ocp(m, lim, T=T, force_cone=cone, land_cstr=cone, terminal_constraint=cone,
-                        Kp=(kp, kp, 10 * kp), Kd=(kp, kp, 2 * kp))
+    if robot == "go2":
+        m, lim = go2_like_model()
+        T, gait = 50, GAIT
+        nq, nv = m.nq, m.nv
+        ocpb = go2_full_ocp(m, lim, T=T, force_cone=cone, land_cstr=cone, terminal_constraint=cone,
+                            Kp=(kp, kp, 10 * kp), Kd=(kp, kp, 2 * kp))
+    else:
+        # config C4: talos-like biped, 6-D contacts (CONTACT_6D, LOCAL_WORLD_ALIGNED), wrench cones, 6-D landing velocity
+        m, lim = talos_like_model()
+        T, gait = 24, TALOS_GAIT
+        nq, nv = m.nq, m.nv
+        ocpb = talos_full_ocp(m, lim, T=T, force_cone=cone, land_cstr=cone, terminal_constraint=cone,
+                              Kp=(kp, 0.5 * kp, 10 * kp, 0.3 * kp, 0.2 * kp, kp), Kd=(20.0 * kp,) * 6 if kp else (100.0,) * 6)
+    nx, ndx, nu = nq + nv, 2 * nv, nv - 6
     ocp = ocpb.desc
     opts = default_opts(orc)
     ctx = C.c_void_p()
@@ -31,7 +44,7 @@ def run_case(cone, kp):
     rng = np.random.default_rng(1)
 
     def gait_slot(i):
-        mask, prev = GAIT[i % 80], GAIT[(i - 1) % 80]
+        mask, prev = gait[i % len(gait)], gait[(i - 1) % len(gait)]
         return full_slot(m, ocpb, feet, contact_mask=mask, land_mask=mask & ~prev)
 
     slots = (Slot * T)(*[gait_slot(i) for i in range(T)])
@@ -45,8 +58,8 @@ def run_case(cone, kp):
     us = np.zeros((T, nu))
     orc.orc_set_warmstart(ctx, 0, 1, P(xs), P(us))
     x0 = xref.copy()
-    x0[nq:] += rng.normal(size=nv) * 0.1
-    x0[7:19] += rng.normal(size=12) * 0.05
+    x0[nq:] += rng.normal(size=nv) * (0.1 if robot == "go2" else 0.03)
+    x0[7:nq] += rng.normal(size=nq - 7) * (0.05 if robot == "go2" else 0.01)
     info = SolveInfo()
     assert orc.orc_solve(ctx, P(x0), 2) == 0, orc.orc_last_error()  # two iterations: non-trivial multipliers
     orc.orc_get_info(ctx, 0, 1, C.byref(info))
@@ -125,7 +138,8 @@ def run_case(cone, kp):
     return dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu, K=K, dxs=dxs, dus=dus)
 
 
-@pytest.fixture(scope="module", params=[(False, 0.0), (True, 5.0)], ids=["torque+joint-limits", "cone+landing+dcm+baumgarte"])
+@pytest.fixture(scope="module", params=[(False, 0.0), (True, 5.0), (True, 0.0, "talos"), (True, 5.0, "talos")],
+                ids=["torque+joint-limits", "cone+landing+dcm+baumgarte", "talos-6d-wrench-cone", "talos-6d-cone+landing+dcm+baumgarte"])
 def case(request):
     return run_case(*request.param)
 

@@ -57,6 +57,23 @@ def test_full_go2_friction_cone_and_landing_constraints():
     assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
 
 
+def test_full_talos_wrench_cone_reference_example_config():
+    # config C4 (BASELINE.json configs[3]; reference examples/talos_fulldynamics.py:48-95): talos-like 22-DoF biped, 6-D
+    # rigid contacts (CONTACT_6D, LOCAL_WORLD_ALIGNED, Kp = [0,0,50,0,0,0], Kd = 100), wrench cones on the contact
+    # forces, torque + joint limits, FramePlacement pose costs, T = 100, walk 20/80/20/80
+    r = pu.run_parity(batch=2, ticks=5, seed=0, verbose=True, scenario=pu.TalosFullScenario)
+    assert r["iters_equal"] and r["alphas_equal"], r
+    assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
+
+
+def test_full_talos_landing_velocity_and_terminal_constraint():
+    # the 6-D landing-velocity equality (reference src/fulldynamics.cpp:175-181) and the DCM terminal constraint switched on;
+    # 25 ticks with per-instance gait phases so that landing edges enter the horizon
+    r = pu.run_parity(batch=3, ticks=25, seed=5, scenario=pu.TalosFullScenario, land_cstr=True, terminal_constraint=True)
+    assert r["iters_equal"] and r["alphas_equal"], r
+    assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
+
+
 def test_centroidal_talos_single_and_batch():
     # config C2: CentroidalOCP, T = 100, 6-D contacts with wrench cones, walk 20/80/20/80
     _check(pu.run_parity(batch=1, ticks=6, seed=0, verbose=True, scenario=pu.TalosCentroidalScenario))

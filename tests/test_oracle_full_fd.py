@@ -53,7 +53,7 @@ def fdyn(orc, m, ocp, x, tau, mask, derivs=1, Kp=None, Kd=None):
     Kd = np.array(ocp.Kd_correction[:3]) if Kd is None else np.asarray(Kd, float)
     q, v, tau = [np.ascontiguousarray(z) for z in (x[:nq], x[nq:], tau)]
     r = orc.orc_full_dynamics(C.byref(m), P(q), P(v), P(tau), C.c_uint(mask), P(g), P(Kp), P(Kd), derivs,
-                              *[P(o[k]) for k in ['a', 'lam', 'da_dq', 'da_dv', 'da_dtau', 'dl_dq', 'dl_dv', 'dl_dtau']])
+                              *[P(o[k]) for k in ['a', 'lam', 'da_dq', 'da_dv', 'da_dtau', 'dl_dq', 'dl_dv', 'dl_dtau']], 3)
     assert r == 0, orc.orc_last_error()
     o['lam'] = o['lam'][:ncon]
     for k in ['dl_dq', 'dl_dv', 'dl_dtau']:
