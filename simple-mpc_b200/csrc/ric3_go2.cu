@@ -13,3 +13,18 @@ namespace smpc
     return SMPC_OK;
   }
 } // namespace smpc
+
+#ifdef SMPC_RIC_PROFILE
+// debug builds only (make SMPC_DEFS=-DSMPC_RIC_PROFILE): per-phase clock64() totals of the Riccati kernel, see tools/ric_phases.py
+extern "C" int smpc_debug_ric_profile(unsigned long long * out16, int reset)
+{
+  if (cudaMemcpyFromSymbol(out16, g_ric_prof, 16 * sizeof(unsigned long long)) != cudaSuccess)
+    return -1;
+  if (reset)
+  {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ric_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

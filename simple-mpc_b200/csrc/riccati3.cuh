@@ -23,6 +23,23 @@
 #include "par.cuh"
 #include "dev_types.h"
 
+// -DSMPC_RIC_PROFILE: thread 0 of every CTA adds the clock64() span of each phase of a stage to g_ric_prof[phase]
+// (tools/ric_phases.py prints the split); never defined in the shipped build.
+#if defined(__CUDACC__) && defined(SMPC_RIC_PROFILE)
+__device__ unsigned long long g_ric_prof[16];
+#define RIC_T(k)                                                                                                       \
+  if (threadIdx.x == 0)                                                                                                \
+  {                                                                                                                    \
+    const long long now_ = clock64();                                                                                  \
+    atomicAdd(&g_ric_prof[k], (unsigned long long)(now_ - ric_t0_));                                                   \
+    ric_t0_ = now_;                                                                                                    \
+  }
+#define RIC_T0 long long ric_t0_ = clock64();
+#else
+#define RIC_T(k)
+#define RIC_T0
+#endif
+
 namespace smpc
 {
 
@@ -466,6 +483,7 @@ namespace smpc
       SMPC_END
     }
 
+    RIC_T0
     for (int t = N - 1; t >= 0; t--)
     {
       const double * kn = knots + (size_t)t * L.size;
@@ -487,9 +505,12 @@ namespace smpc
       // ---- 1. [p~ | P~] = (I + mudyn P)^-1 [p | P], in place ----
       if (mudyn > 0)
       {
+        RIC_T(0)
         chol_reg<NDX, NDX, TPB>(Mb, colb, invp, bad);
+        RIC_T(1)
         sweep_cols<NDX, NDX, LDP, LDP, true, false>(Mb, invp, PP);
         sweep_cols<NDX, NDX, LDP, LDP, false, true>(Mb, invp, PP);
+        RIC_T(2)
       }
       // ---- 2. knot landed ; P~ p~ out (for the forward sweep) ; w = P~ f + p~ ; PAB = P~ [A B] ----
       SMPC_PAR(tid)
@@ -551,6 +572,7 @@ namespace smpc
       }
       SMPC_END
       parity ^= 1u;
+      RIC_T(3)
       // ---- 3. [Qh | Sh] = [Q | S] + A^T PAB ; Rh = R + B^T PB ; qh = q + A^T w ; rh = r + B^T w (in place) ----
       SMPC_PAR(tid)
       {
@@ -622,6 +644,7 @@ namespace smpc
         }
       }
       SMPC_END
+      RIC_T(4)
       // ---- 4. KKT by block LDL^T ----
       // PAB is dead: fetch C D d into its tail rows' storage while R^ is factorised
       SMPC_PAR(tid)
@@ -629,6 +652,7 @@ namespace smpc
         bulk_load(KN + R::kC, kn + R::kC, R::KSIZE - R::kC, bar);
       SMPC_END
       chol_reg<NU, NU, TPB>(Rh, colb, invr, bad);
+      RIC_T(5)
       SMPC_PAR(tid)
       bulk_wait(bar, parity);
       for (int e = tid; e < NU * NRY; e += SMPC_NT)
@@ -646,6 +670,7 @@ namespace smpc
       SMPC_END
       parity ^= 1u;
       sweep_cols<NU, NU, NRY, NRY, true, false>(Rh, invr, YW);
+      RIC_T(6)
       if (NC > 0)
       {
         // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : register tiles (4x3 on G, 4x4 blocks of the
@@ -747,9 +772,12 @@ namespace smpc
           }
         }
         SMPC_END
+        RIC_T(7)
         chol_reg<NC, NC, TPB>(Sg, colb, invs, bad);
+        RIC_T(8)
         sweep_cols<NC, NC, LDP, LDP, true, false>(Sg, invs, G);
         sweep_cols<NC, NC, LDP, LDP, false, true>(Sg, invs, G);
+        RIC_T(9)
         // Y <- Y + W G : 4x3 register tiles, the last column by four-row strips
         SMPC_PAR(tid)
         {
@@ -810,7 +838,9 @@ namespace smpc
         }
         SMPC_END
       }
+      RIC_T(10)
       sweep_cols<NU, NU, LDP, NRY, false, true>(Rh, invr, YW);
+      RIC_T(11)
       // ---- gains: [k | K] = -Y, [z | Z] = G ----
       SMPC_PAR(tid)
       {
@@ -834,6 +864,7 @@ namespace smpc
         }
       }
       SMPC_END
+      RIC_T(12)
       // ---- 5. [p | P] = [qh | Qh] + Sh [k | K] + C^T [z | Z] : TM x 3 register tiles, p by the remaining threads ----
       SMPC_PAR(tid)
       {
@@ -922,6 +953,7 @@ namespace smpc
         }
       }
       SMPC_END
+      RIC_T(13)
       // symmetrise P (two phases: read both halves, then write)
       SMPC_PAR(tid)
       for (int e = tid; e < NDX * NDX; e += SMPC_NT)
@@ -942,6 +974,7 @@ namespace smpc
         }
       }
       SMPC_END
+      RIC_T(14)
     }
     SMPC_PAR(tid)
     {
