@@ -169,5 +169,8 @@ namespace smpc
   int setup_knots_full_go2(smpc_ctx * c);    // FullCfg<13, 18, 4>               knots_full_go2.cu
   int setup_knots_full_talos(smpc_ctx * c);  // FullCfg<23, 28, 2, 6>            knots_full_talos.cu
   int setup_knots_centro(smpc_ctx * c);      // CentroCfg<2, 6>, CentroCfg<4, 3> knots_centro.cu
-  int setup_riccati_tuned(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati3 instantiations, ric3_*.cu
+  // shape-specialised Riccati sweeps: *found = false when the shape is not instantiated in that translation unit
+  int setup_ric3_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati3.cuh, ric3_go2.cu
+  int setup_ric4_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati4.cuh, ric4_go2.cu
+  int setup_ric4_big(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati4.cuh, ric4_big.cu
 } // namespace smpc

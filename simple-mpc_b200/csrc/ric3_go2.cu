@@ -2,7 +2,7 @@
 #include "riccati3_kernel.cuh"
 namespace smpc
 {
-  int setup_riccati_tuned(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found)
+  int setup_ric3_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found)
   {
     *found = true;
     if (ndx == 36 && nu == 24 && ncmax == 24)

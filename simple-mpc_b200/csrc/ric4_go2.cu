@@ -1,0 +1,27 @@
+// generic-shape two-column Riccati sweeps (riccati4.cuh) for the Go2 shapes: kinodynamics (ndx 36, nu 24; ncmax 24 without /
+// 36 with cone + landing rows) and full dynamics (ndx 36, nu 12; ncmax 24 with torque + joint limits)
+#include "riccati4_kernel.cuh"
+namespace smpc
+{
+  // 128 threads: throughput variant (three CTAs per SM); 256: latency variant when no SM holds more than one instance
+  template <int NDX, int NU, int NC>
+  static int pick(smpc_ctx * c)
+  {
+    bool wide = c->hmodel_sms > 0 && c->A.dm.B <= c->hmodel_sms;
+    if (const char * e = getenv("SMPC_RIC_TPB"))
+      wide = atoi(e) == 256;
+    return wide ? setup_riccati4<NDX, NU, NC, 256>(c, "two-column-256") : setup_riccati4<NDX, NU, NC, 128>(c, "two-column");
+  }
+  int setup_ric4_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found)
+  {
+    *found = true;
+    if (ndx == 36 && nu == 24 && ncmax == 24)
+      return pick<36, 24, 24>(c);
+    if (ndx == 36 && nu == 24 && ncmax == 36)
+      return pick<36, 24, 36>(c);
+    if (ndx == 36 && nu == 12 && ncmax == 24)
+      return pick<36, 12, 24>(c);
+    *found = false;
+    return SMPC_OK;
+  }
+} // namespace smpc

@@ -1,0 +1,66 @@
+// riccati4_kernel.cuh — the generic-shape TMA-staged Riccati backward kernel (riccati4.cuh) and its host-side setup.
+// Included by the ric4_*.cu translation units, each of which instantiates the (ndx, nu, ncmax) shapes of one robot.
+#pragma once
+#include "ctx.h"
+#include "riccati4.cuh"
+
+namespace smpc
+{
+  // resident CTAs per SM the shared-memory footprint allows (228 KB per SM, 1 KB reserved per CTA), capped by the
+  // register file (TPB x CTAs x registers <= 64 K)
+  template <int NDX, int NU, int NC, int TPB>
+  constexpr int ric4_ctas_per_sm()
+  {
+    // 256 threads = the latency variant: one instance per SM with the whole register file (255 registers, no spills)
+    constexpr int fit = 233472 / (Ric4<NDX, NU, NC>::SIZE * 8 + 1024 + 16);
+    constexpr int cap = TPB >= 256 ? 1 : 512 / TPB; // at least 128 registers per thread
+    return fit < 1 ? 1 : (fit > cap ? cap : fit);
+  }
+  template <int NDX, int NU, int NC, int TPB>
+  __global__ void __launch_bounds__(TPB, (ric4_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati4(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int b = blockIdx.x;
+    const Dims & d = A.dm;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    __shared__ int flag;
+    riccati4_backward_inst<NDX, NU, NC, TPB>(
+      A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
+      A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
+    if (threadIdx.x == 0 && flag)
+      st.flags |= 1;
+  }
+  template <int NDX, int NU, int NC, int TPB>
+  void launch_riccati4_impl(smpc_ctx * c)
+  {
+    k_riccati4<NDX, NU, NC, TPB><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
+  }
+  template <int NDX, int NU, int NC, int TPB>
+  int setup_riccati4(smpc_ctx * c, const char * name)
+  {
+    typedef Ric4<NDX, NU, NC> R;
+    const KnotLayout & L = c->A.L;
+    if (L.oQ != R::kQ || L.oS != R::kS || L.oR != R::kR || L.oq != R::kq || L.or_ != R::kr || L.oA != R::kA || L.oB != R::kB
+        || L.of != R::kf || L.oC != R::kC || L.oD != R::kD || L.od != R::kd || L.size != R::KSIZE)
+    {
+      smpc::err() = "riccati4: compile-time knot layout differs from make_knot_layout";
+      return SMPC_ERR_INVALID;
+    }
+    c->ric_smem = (size_t)R::SIZE * sizeof(double);
+    CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c->launch_riccati = &launch_riccati4_impl<NDX, NU, NC, TPB>;
+    c->riccati_variant = name;
+    if (getenv("SMPC_VERBOSE"))
+    {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati4<NDX, NU, NC, TPB>, TPB, c->ric_smem);
+      fprintf(stderr, "smpc: k_riccati4<%d,%d,%d> (%d threads) %zu B shared memory per instance, resident CTAs per SM: %d\n", NDX, NU, NC, TPB,
+              c->ric_smem, nb);
+    }
+    return SMPC_OK;
+  }
+} // namespace smpc

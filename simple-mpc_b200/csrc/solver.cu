@@ -758,13 +758,19 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
                   "point feet; full dynamics on a 22-DoF biped with quad feet; centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
     return rc;
-  // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax)
-  // SMPC_RICCATI=0 selects the generic sweep (A/B timing)
+  // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax).
+  // SMPC_RICCATI (A/B timing): 4 = two-column sweep of riccati4.cuh (default), 3 = riccati3.cuh, 0 = the generic sweep
   const char * rv = getenv("SMPC_RICCATI");
-  const int ric = rv ? atoi(rv) : 3;
+  const int ric = rv ? atoi(rv) : 4;
   bool tuned = false;
-  if (ric == 3)
-    rc = setup_riccati_tuned(c, O.ndx, O.nu, O.ncmax, &tuned);
+  if (ric == 4)
+  {
+    rc = setup_ric4_go2(c, O.ndx, O.nu, O.ncmax, &tuned);
+    if (rc == SMPC_OK && !tuned)
+      rc = setup_ric4_big(c, O.ndx, O.nu, O.ncmax, &tuned);
+  }
+  if (rc == SMPC_OK && !tuned && ric >= 3)
+    rc = setup_ric3_go2(c, O.ndx, O.nu, O.ncmax, &tuned);
   if (rc != SMPC_OK)
     return rc;
   if (!tuned)

@@ -7,6 +7,7 @@
 #include "../../simple-mpc_b200/csrc/full_knot.cuh"
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
+#include "../../simple-mpc_b200/csrc/riccati4.cuh"
 #include "../../simple-mpc_b200/csrc/riccati_fwd.cuh"
 #include "../../simple-mpc_b200/csrc/mpc_driver.cuh"
 #include "../../simple-mpc_b200/csrc/host_build.h"
@@ -62,6 +63,13 @@ static void full_knot_any(const DevModel & M, const DevOcp & O, const KnotLayout
     else
       full_stage_knot<FCfg, false>(M, O, L, io, *s);
   }
+}
+
+template <int NDX, int NU, int NC>
+static void ric4_any(const KnotLayout & L, const SolLayout & SL, int N, const double * knots, double * sol, double mudyn, double mueq, int * flag, double * P0)
+{
+  std::vector<double> sm(Ric4<NDX, NU, NC>::SIZE + 16, 0.0);
+  riccati4_backward_inst<NDX, NU, NC, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0);
 }
 
 extern "C" {
@@ -246,6 +254,36 @@ int emul_riccati3(
   FwdSmem FS = make_fwd_smem(ndx, nu, ncmax);
   std::vector<double> smf((size_t)FS.size + 8, 0.0);
   riccati_forward_staged(L, SL, FS, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, smf.data());
+  return 0;
+}
+
+// same, through the generic-shape two-column sweep of riccati4.cuh
+int emul_riccati4(
+  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
+  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
+  double * dphi, int * flag)
+{
+  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
+  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
+  std::vector<double> P0((size_t)ndx * (ndx + 1), 0.0), sm2(4 * ndx + nu + 80, 0.0);
+  if (ndx == 36 && nu == 24 && ncmax == 24)
+    ric4_any<36, 24, 24>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 36 && nu == 24 && ncmax == 36)
+    ric4_any<36, 24, 36>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 36 && nu == 12 && ncmax == 24)
+    ric4_any<36, 12, 24>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 36 && nu == 12 && ncmax == 60)
+    ric4_any<36, 12, 60>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 56 && nu == 22 && ncmax == 78)
+    ric4_any<56, 22, 78>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 56 && nu == 22 && ncmax == 90)
+    ric4_any<56, 22, 90>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else
+  {
+    g_err = "emul_riccati4: size not instantiated";
+    return -1;
+  }
+  riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
   return 0;
 }
 

@@ -147,6 +147,7 @@ def run_case(cone):
     out = dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu)
     out['generic_on_oracle'] = sweep(emu.emul_riccati, orc_knots)
     out['tma_on_oracle'] = sweep(emu.emul_riccati3, orc_knots)
+    out['two_column_on_oracle'] = sweep(emu.emul_riccati4, orc_knots)
     out['special_on_emul'] = sweep(emu.emul_riccati3, emu_knots)
     orc.orc_destroy(ctx)
     return out
@@ -170,7 +171,7 @@ def test_infeasibility_scalars_match(case):
 
 
 def test_riccati_bitwise(case):
-    for name in ['generic_on_oracle', 'tma_on_oracle']:
+    for name in ['generic_on_oracle', 'tma_on_oracle', 'two_column_on_oracle']:
         K, dxs, dus = case[name]
         assert np.array_equal(K, case['Ko']), name
         assert np.array_equal(dxs, case['odx']), name

@@ -134,8 +134,30 @@ def run_case(cone, kp, robot="go2"):
                           P(gxs), P(gus), P(lpl), P(dxs), P(dus), P(vnew), P(lnew), C.byref(dphi), C.byref(flag))
     assert rc == 0 and flag.value == 0
     K = np.array([sol[t][oK:oK + nu * ndx].reshape(nu, ndx) for t in range(T)])
+    # the shape-specialised two-column sweep (riccati4.cuh) on the ORACLE's knots: bitwise the oracle's gains and steps
+    orc_knots = np.zeros((T + 1, size))
+    for t in range(T + 1):
+        o = dict(Q=np.zeros((ndx, ndx)), S=np.zeros((ndx, nu)), R=np.zeros((nu, nu)), q=np.zeros(ndx), r=np.zeros(nu),
+                 A=np.zeros((ndx, ndx)), B=np.zeros((ndx, nu)), f=np.zeros(ndx), C=np.zeros((ncmax, ndx)), D=np.zeros((ncmax, nu)),
+                 d=np.zeros(ncmax))
+        onc = C.c_int(0)
+        assert orc.orc_get_knot(ctx, 0, t, C.byref(onc), *[P(o[k]) for k in names]) == 0
+        n = onc.value
+        kn = orc_knots[t]
+        kn[oQ:oQ + ndx * ndx], kn[oq:oq + ndx] = o['Q'].ravel(), o['q']
+        kn[oC:oC + n * ndx], kn[od:od + n] = o['C'].ravel()[:n * ndx], o['d'][:n]
+        if t < T:
+            kn[oS:oS + ndx * nu], kn[oR:oR + nu * nu], kn[or_:or_ + nu] = o['S'].ravel(), o['R'].ravel(), o['r']
+            kn[oA:oA + ndx * ndx], kn[oB:oB + ndx * nu], kn[of:of + ndx] = o['A'].ravel(), o['B'].ravel(), o['f']
+            kn[oD:oD + n * nu] = o['D'].ravel()[:n * nu]
+    sol4 = np.zeros((T + 1, ssize))
+    dxs4, dus4 = np.zeros((T + 1, ndx)), np.zeros((T, nu))
+    rc = emu.emul_riccati4(T, ndx, nu, ncmax, P(orc_knots), ncs.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(mu), C.c_double(mu), P(sol4),
+                           P(gxs), P(gus), P(lpl), P(dxs4), P(dus4), P(vnew), P(lnew), C.byref(dphi), C.byref(flag))
+    assert rc == 0 and flag.value == 0, emu.emul_last_error()
+    K4 = np.array([sol4[t][oK:oK + nu * ndx].reshape(nu, ndx) for t in range(T)])
     orc.orc_destroy(ctx)
-    return dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu, K=K, dxs=dxs, dus=dus)
+    return dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu, K=K, dxs=dxs, dus=dus, K4=K4, dxs4=dxs4, dus4=dus4)
 
 
 @pytest.fixture(scope="module", params=[(False, 0.0), (True, 5.0), (True, 0.0, "talos"), (True, 5.0, "talos")],
@@ -160,3 +182,11 @@ def test_full_end_to_end_gains_within_conditioning(case):
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     assert rel(case['K'], case['Ko']) < 1e-6
     assert rel(case['dus'], case['odu']) < 1e-6
+
+
+def test_full_two_column_riccati_bitwise(case):
+    """riccati4.cuh (generic shapes, two columns per factorisation step) fed with the ORACLE's knots returns the oracle's
+    gains and Newton step bit for bit, for the Go2 full-dynamics shapes (36, 12, 24 | 60) and the Talos ones (56, 22, 78 | 90)."""
+    assert np.array_equal(case['K4'], case['Ko'])
+    assert np.array_equal(case['dxs4'], case['odx'])
+    assert np.array_equal(case['dus4'], case['odu'])
