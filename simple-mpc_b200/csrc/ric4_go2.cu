@@ -25,3 +25,18 @@ namespace smpc
     return SMPC_OK;
   }
 } // namespace smpc
+
+#ifdef SMPC_RIC_PROFILE
+// debug builds only: g_ric_prof is a per-translation-unit symbol; this reads the copy the riccati4 Go2 kernels write
+extern "C" int smpc_debug_ric4_profile(unsigned long long * out16, int reset)
+{
+  if (cudaMemcpyFromSymbol(out16, g_ric_prof, 16 * sizeof(unsigned long long)) != cudaSuccess)
+    return -1;
+  if (reset)
+  {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ric_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

@@ -8,8 +8,8 @@
 //     and waited for after the factorisation of I + mu P, which does not need it. Nothing in the stage reads
 //     global memory inside a k-loop any more (C, D, d used to be read from HBM in the P update);
 //   * Q^, S^, R^, q^, r^ accumulate IN PLACE in the staged knot (no second copy of [Q S]);
-//   * factorisations are right-looking over ALL threads with the trailing matrix in registers: one barrier
-//     per column, the pivot's sqrt/reciprocal is the only serial part, and the column loop is a runtime loop
+//   * factorisations are right-looking over ALL threads with the trailing matrix in registers, TWO columns per
+//     barrier (chol2.cuh), the pivot chain inside one lane of a dedicated warp, and the column loop a runtime loop
 //     (a fully unrolled factorisation made the kernel 600 KB of SASS and the sweep instruction-fetch bound);
 //     the scaled column is also written to the transposed (upper) slot, so the forward sweep reads L by rows
 //     (128-bit shared loads) exactly like the backward sweep;
@@ -22,6 +22,7 @@
 #pragma once
 #include "par.cuh"
 #include "dev_types.h"
+#include "chol2.cuh"
 
 // -DSMPC_RIC_PROFILE: thread 0 of every CTA adds the clock64() span of each phase of a stage to g_ric_prof[phase]
 // (tools/ric_phases.py prints the split); never defined in the shipped build.
@@ -93,32 +94,15 @@ namespace smpc
     static constexpr int oinvs = oinvr + NU;
     static constexpr int oinvp = oinvr;
     static constexpr int szinv = (NU + NC > NDX) ? NU + NC : NDX;
-    static constexpr int ocol = oinvr + szinv; // published pivot columns, double buffered
+    static constexpr int ocol = (oinvr + szinv + 1) & ~1; // published column pairs of chol2, double buffered
     static constexpr int NMAX = (NDX > NC) ? (NDX > NU ? NDX : NU) : (NC > NU ? NC : NU);
-    static constexpr int obar = (ocol + 2 * (NMAX + 2) + 1) & ~1; // 8-byte mbarrier
+    static constexpr int obar = (ocol + 2 * (2 * NMAX + 4) + 1) & ~1; // 8-byte mbarrier
     static constexpr int oflag = obar + 2;
     static constexpr int SIZE = oflag + 2;
     static_assert((kA % 2) == 0 && (kB % 2) == 0 && (kC % 2) == 0 && (kQ % 2) == 0 && (kS % 2) == 0 && (kR % 2) == 0,
                   "128-bit shared loads need even block offsets");
     static_assert(NDX % 4 == 0 && NDX % 6 == 0 && NU % 4 == 0 && NU % 6 == 0, "4x6 tiles must divide the blocks");
   };
-
-  // Reciprocal square root of a Cholesky pivot. The pivot chain is the serial critical path of the sweep (one per
-  // column, 84 columns per stage; profiles/r01e: the pivot warp's sqrt-then-divide is 2 MUFU + 12 dependent FP64
-  // operations and the other three warps wait for it at the column barrier). The default keeps the correctly rounded
-  // 1.0 / sqrt(d) of oracle/orc_solver.hpp, so the device sweep stays bitwise equal to the oracle on identical knots.
-  // -DSMPC_FAST_PIVOTS switches to CUDA's rsqrt() (MUFU.RSQ64H + one cubic Newton step: 1 MUFU + 4 dependent
-  // operations, <= 1 ulp). Measured on B200 at B = 4096: 29.45 -> 28.16 ms per launch, parity against the oracle
-  // unchanged (K 1.6e-8 vs 1.8e-8, equal iteration counts and step sizes) - a 2 % tick gain that is not worth giving
-  // up the exact operation order by default.
-  SMPC_DEV double pivot_rsqrt(double d)
-  {
-#if defined(__CUDACC__) && defined(SMPC_FAST_PIVOTS)
-    return rsqrt(d);
-#else
-    return 1.0 / sqrt(d);
-#endif
-  }
 
   // ---- bulk asynchronous global -> shared copy (TMA) -------------------------------------------------
   // Device: cp.async.bulk completing on an mbarrier; CPU emulation harness: memcpy.
@@ -169,158 +153,6 @@ namespace smpc
     (void)bar;
     (void)parity;
 #endif
-  }
-
-  // ---- right-looking Cholesky, trailing matrix in registers, one warp dedicated to the pivots ---------
-  // In: the LOWER triangle (with diagonal) of the N x N matrix M (ld LD). Out: L(i,j), i > j, in M[i][j] AND
-  // in the transposed slot M[j][i]; invd[j] = 1 / L(j,j).
-  // Roles: the LAST warp of the CTA keeps the diagonal (lane l holds d(l), d(l+32), ...); the N(N-1)/2
-  // strictly-lower entries are dealt to the other TPB-32 threads (folded-rectangle indexing) and stay in
-  // registers for the whole factorisation. Column step j is a runtime loop (a fully unrolled factorisation
-  // made the kernel 600 KB of SASS and the sweep instruction-fetch bound) of ONE phase:
-  //   - pivot warp: d(t) -= L(t,j)^2 for t > j, then 1/sqrt(d(j+1)) -> inv_{j+1}: the serial chain of a
-  //     column (LDS + sqrt + reciprocal, ~200 clocks on B200, tools/microbench_fp64.cu) runs BESIDE
-  //   - the other warps: m(i,k) -= L(i,j) L(k,j) for k > j (branch-free), entries of column j+1 are
-  //     published un-scaled for the next step.
-  // The factor is written once at the end: L(i,k) = m(i,k) inv_k. Per-entry update order is ascending j,
-  // the oracle's order, and every product is the oracle's product, so the factor is bitwise the oracle's.
-  template <int N, int LD, int TPB>
-  SMPC_DEV void chol_reg(double * M, double * col /* [2][N+2] */, double * invd, int * bad)
-  {
-    static_assert(N % 2 == 0, "folded-rectangle indexing assumes an even order");
-    constexpr int TW = TPB - 32; // threads that own off-diagonal entries
-    constexpr int NO = N * (N - 1) / 2, E = (NO + TW - 1) / TW, RW = N - 1, CS = N + 2;
-    constexpr int DS = (N + 31) / 32; // diagonal entries per pivot-warp lane
-    constexpr int NR = (E > DS) ? E : DS;
-    SMPC_THREAD_ARRAY(m, NR)
-    SMPC_THREAD_IARRAY(ik, 2 * E)
-    SMPC_PAR(tid)
-    {
-      double * m = SMPC_THREAD_PTR(m, NR, tid);
-      int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
-      if (tid < TW)
-      {
-#pragma unroll
-        for (int q = 0; q < E; q++)
-        {
-          const int e = tid + TW * q;
-          const int r = e / RW, c = e - r * RW;
-          // row r pairs with row N-1-r (r + N-1-r = N-1 entries); r = 0 is row N-1 alone
-          const int i = (r == 0) ? N - 1 : ((c < r) ? r : N - 1 - r);
-          const int k = (r == 0) ? c : ((c < r) ? c : c - r);
-          const bool valid = e < NO;
-          ik[2 * q] = valid ? i : 0; // a dead slot is (0,0): never above any column
-          ik[2 * q + 1] = valid ? k : 0;
-          m[q] = valid ? M[i * LD + k] : 0.0;
-          if (valid && k == 0)
-            col[i] = m[q];
-        }
-      }
-      else
-      {
-        const int lane = tid - TW;
-        ik[0] = 0; // pivot lanes: "met a non-positive pivot"
-#pragma unroll
-        for (int s = 0; s < DS; s++)
-        {
-          const int t = lane + 32 * s;
-          m[s] = (t < N) ? M[t * LD + t] : 1.0;
-        }
-        if (lane == 0)
-        {
-          const double d = m[0];
-          const double inv = pivot_rsqrt(d);
-          col[N] = inv;
-          invd[0] = inv;
-          if (!(d > 0))
-            *bad = 1;
-        }
-      }
-    }
-    SMPC_END
-#pragma unroll 1
-    for (int j = 0; j < N; j++)
-    {
-      SMPC_PAR(tid)
-      {
-        double * m = SMPC_THREAD_PTR(m, NR, tid);
-        int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
-        const double * cj = col + (j & 1) * CS;
-        double * cn = col + ((j + 1) & 1) * CS;
-        if (tid < TW)
-        {
-          double ca[E], cb[E];
-#pragma unroll
-          for (int q = 0; q < E; q++)
-          {
-            ca[q] = cj[ik[2 * q]];
-            cb[q] = cj[ik[2 * q + 1]];
-          }
-          const double inv = cj[N];
-#pragma unroll
-          for (int q = 0; q < E; q++)
-          {
-            const int i = ik[2 * q], k = ik[2 * q + 1];
-            const double a = ca[q] * inv;
-            const double b = cb[q] * inv;
-            if (k > j)
-              m[q] = fma(-a, b, m[q]); // predicated FMA: frozen once its column has been processed
-            if (k == j + 1)
-              cn[i] = m[q];
-          }
-        }
-        else
-        {
-          const int lane = tid - TW;
-          const double inv = cj[N];
-          double dsel = 1.0;
-#pragma unroll
-          for (int s = 0; s < DS; s++)
-          {
-            const int t = lane + 32 * s;
-            const double lt = cj[t < N ? t : 0] * inv;
-            const double dn = fma(-lt, lt, m[s]);
-            if (t > j && t < N)
-              m[s] = dn;
-            if (t == j + 1)
-              dsel = m[s];
-          }
-          // lanes that do not hold d(j+1) work on 1.0; only the holder publishes. A non-positive pivot is
-          // remembered in the lane (the holder of d(j+1) sees it) and reported once after the loop.
-          const double invn = pivot_rsqrt(dsel);
-          if (!(dsel > 0))
-            ik[0] = 1;
-          if ((lane == ((j + 1) & 31)) && j + 1 < N)
-          {
-            cn[N] = invn;
-            invd[j + 1] = invn;
-          }
-        }
-      }
-      SMPC_END
-    }
-    SMPC_PAR(tid)
-    {
-      const double * m = SMPC_THREAD_PTR(m, NR, tid);
-      const int * ik = SMPC_THREAD_PTR(ik, 2 * E, tid);
-      if (tid < TW)
-      {
-#pragma unroll
-        for (int q = 0; q < E; q++)
-        {
-          const int i = ik[2 * q], k = ik[2 * q + 1];
-          if (i > k)
-          {
-            const double lik = m[q] * invd[k];
-            M[i * LD + k] = lik;
-            M[k * LD + i] = lik;
-          }
-        }
-      }
-      else if (ik[0])
-        *bad = 1;
-    }
-    SMPC_END
   }
 
   // x[i] -= row[i] * xk for i in [I0, I1): row is a shared-memory row of the factor (16-byte aligned when its
@@ -481,6 +313,15 @@ namespace smpc
         PP[e] = acc;
       }
       SMPC_END
+      SMPC_PAR(tid)
+      if (mudyn > 0)
+        for (int e = tid; e < NDX * NDX; e += SMPC_NT)
+        {
+          const int a = e / NDX, b = e % NDX;
+          if (b <= a)
+            Mb[e] = mul_then_add(mudyn, PP[a * LDP + 1 + b], (a == b ? 1.0 : 0.0));
+        }
+      SMPC_END
     }
 
     RIC_T0
@@ -488,25 +329,16 @@ namespace smpc
     {
       const double * kn = knots + (size_t)t * L.size;
       double * so = sol + (size_t)t * SL.size;
-      // ---- 0. start the copy of this stage's knot; M = I + mudyn P (lower) ----
+      // ---- 0. start the copy of this stage's knot (M = I + mudyn P was left in X by the previous symmetrisation) ----
       SMPC_PAR(tid)
-      {
-        if (tid == 0)
-          bulk_load(KN, kn, R::kC, bar); // Q S R q r A B f; C D d follow after step 3
-        if (mudyn > 0)
-          for (int e = tid; e < NDX * NDX; e += SMPC_NT)
-          {
-            const int a = e / NDX, b = e % NDX;
-            if (b <= a)
-              Mb[e] = mudyn * PP[a * LDP + 1 + b] + (a == b ? 1.0 : 0.0);
-          }
-      }
+      if (tid == 0)
+        bulk_load(KN, kn, R::kC, bar); // Q S R q r A B f; C D d follow after step 3
       SMPC_END
       // ---- 1. [p~ | P~] = (I + mudyn P)^-1 [p | P], in place ----
       if (mudyn > 0)
       {
         RIC_T(0)
-        chol_reg<NDX, NDX, TPB>(Mb, colb, invp, bad);
+        chol2<NDX, NDX, TPB>(Mb, colb, invp, bad);
         RIC_T(1)
         sweep_cols<NDX, NDX, LDP, LDP, true, false>(Mb, invp, PP);
         sweep_cols<NDX, NDX, LDP, LDP, false, true>(Mb, invp, PP);
@@ -651,7 +483,7 @@ namespace smpc
       if (tid == 0)
         bulk_load(KN + R::kC, kn + R::kC, R::KSIZE - R::kC, bar);
       SMPC_END
-      chol_reg<NU, NU, TPB>(Rh, colb, invr, bad);
+      chol2<NU, NU, TPB>(Rh, colb, invr, bad);
       RIC_T(5)
       SMPC_PAR(tid)
       bulk_wait(bar, parity);
@@ -773,7 +605,7 @@ namespace smpc
         }
         SMPC_END
         RIC_T(7)
-        chol_reg<NC, NC, TPB>(Sg, colb, invs, bad);
+        chol2<NC, NC, TPB>(Sg, colb, invs, bad);
         RIC_T(8)
         sweep_cols<NC, NC, LDP, LDP, true, false>(Sg, invs, G);
         sweep_cols<NC, NC, LDP, LDP, false, true>(Sg, invs, G);
@@ -954,23 +786,31 @@ namespace smpc
       }
       SMPC_END
       RIC_T(13)
-      // symmetrise P (two phases: read both halves, then write)
+      // symmetrise P (two phases: read both halves, then write); the same pass leaves M = I + mudyn P (lower triangle)
+      // for the next stage in X (YW is dead), the symmetrised value parked in M's upper triangle
       SMPC_PAR(tid)
       for (int e = tid; e < NDX * NDX; e += SMPC_NT)
       {
-        const int a = e / NDX, b = e % NDX;
+        const int a = e / NDX, b = e - a * NDX;
         if (b < a)
-          Mb[e] = 0.5 * (PP[a * LDP + 1 + b] + PP[b * LDP + 1 + a]);
+        {
+          const double v = 0.5 * (PP[a * LDP + 1 + b] + PP[b * LDP + 1 + a]);
+          Mb[e] = mudyn * v;
+          Mb[b * NDX + a] = v;
+        }
+        else if (b == a)
+          Mb[e] = mul_then_add(mudyn, PP[a * LDP + 1 + a], 1.0);
       }
       SMPC_END
       SMPC_PAR(tid)
       for (int e = tid; e < NDX * NDX; e += SMPC_NT)
       {
-        const int a = e / NDX, b = e % NDX;
+        const int a = e / NDX, b = e - a * NDX;
         if (b < a)
         {
-          PP[a * LDP + 1 + b] = Mb[e];
-          PP[b * LDP + 1 + a] = Mb[e];
+          const double v = Mb[b * NDX + a];
+          PP[a * LDP + 1 + b] = v;
+          PP[b * LDP + 1 + a] = v;
         }
       }
       SMPC_END

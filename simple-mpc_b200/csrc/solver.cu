@@ -758,19 +758,19 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
                   "point feet; full dynamics on a 22-DoF biped with quad feet; centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
     return rc;
-  // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax).
-  // SMPC_RICCATI (A/B timing): 4 = two-column sweep of riccati4.cuh (default), 3 = riccati3.cuh, 0 = the generic sweep
+  // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax). Default: the fastest
+  // measured per shape - riccati3.cuh (4 x 6 tiles laid out for 128 threads) for the Go2-kinodynamics shapes, riccati4.cuh
+  // (any even shape) for the rest. SMPC_RICCATI (A/B timing): 4 = riccati4 wherever instantiated, 3 = riccati3 only,
+  // 0 = the generic run-time-shape sweep of riccati.cuh
   const char * rv = getenv("SMPC_RICCATI");
-  const int ric = rv ? atoi(rv) : 4;
+  const int ric = rv ? atoi(rv) : -1;
   bool tuned = false;
-  if (ric == 4)
-  {
-    rc = setup_ric4_go2(c, O.ndx, O.nu, O.ncmax, &tuned);
-    if (rc == SMPC_OK && !tuned)
-      rc = setup_ric4_big(c, O.ndx, O.nu, O.ncmax, &tuned);
-  }
-  if (rc == SMPC_OK && !tuned && ric >= 3)
+  if (ric == -1 || ric == 3)
     rc = setup_ric3_go2(c, O.ndx, O.nu, O.ncmax, &tuned);
+  if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
+    rc = setup_ric4_go2(c, O.ndx, O.nu, O.ncmax, &tuned);
+  if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
+    rc = setup_ric4_big(c, O.ndx, O.nu, O.ncmax, &tuned);
   if (rc != SMPC_OK)
     return rc;
   if (!tuned)

@@ -194,7 +194,9 @@ def test_batched_device_driver_vs_host_mpc_on_oracle():
             x[i] = np.array(mpc.xs[1])
         x = sc.disturb(x, k + 1)
     b.close()
-    assert worst["refs"] <= 1e-12 and worst["xs"] <= TOL and worst["us"] <= TOL and worst["K"] <= TOL_K, worst
+    # 45 closed-loop ticks: each backend carries its own warm start and multipliers, so the amplified-rounding differences of
+    # the single solves (tests/test_amplification.py) accumulate as a random walk: 3 x the single-solve tolerance
+    assert worst["refs"] <= 1e-12 and worst["xs"] <= 3 * TOL and worst["us"] <= 3 * TOL and worst["K"] <= TOL_K, worst
 
 
 def test_full_size_batch_4096_sampled_against_the_oracle_and_batch_properties():
