@@ -166,6 +166,7 @@ struct smpc_ctx
 namespace smpc
 {
   int setup_knots_kino_go2(smpc_ctx * c);    // KinoCfg<13, 18, 4, 3>            knots_kino_go2.cu
+  int setup_knots_kino_talos(smpc_ctx * c);  // KinoCfg<23, 28, 2, 6>            knots_kino_talos.cu
   int setup_knots_full_go2(smpc_ctx * c);    // FullCfg<13, 18, 4>               knots_full_go2.cu
   int setup_knots_full_talos(smpc_ctx * c);  // FullCfg<23, 28, 2, 6>            knots_full_talos.cu
   int setup_knots_centro(smpc_ctx * c);      // CentroCfg<2, 6>, CentroCfg<4, 3> knots_centro.cu

@@ -309,53 +309,11 @@ namespace smpc
       dv6[r] = dA_v[r] + t3[r];
     }
   }
-  // <foot>_pose_cost of a quad foot: FramePlacementResidual r = log6(ref^-1 oMf), weight w_frame (6 x 6). The residual
-  // Jacobian is T Jp with T = Jlog6(r) blkdiag(R^T, R^T) and Jp the world-aligned foot Jacobian; stores r, T and the
-  // gradient weights Wfr = T^T W r. Returns 1/2 r^T W r.
+  // <foot>_pose_cost of a quad foot: quad_pose_cost of kino_knot.cuh (shared with the kinodynamics knot)
   template <class Cfg, bool DERIVS>
   SMPC_DEV double full6_pose_cost(const DevOcp & O, const smpc_slot & slot, FullScratch<Cfg> & s, int f)
   {
-    constexpr int Q6 = FullScratch<Cfg>::Q6, Q36 = FullScratch<Cfg>::Q36, FS = Cfg::FS;
-    const double * Rr = slot.foot_ref[f];
-    double Rrel[9], dp[3], prel[3], rr[6], Wr[6], cst = 0;
-    m3tm(Rr, s.fR[f], Rrel);
-    for (int r = 0; r < 3; r++)
-      dp[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
-    m3tv(Rr, dp, prel);
-    log6(Rrel, prel, rr);
-    for (int r = 0; r < 6; r++)
-    {
-      s.rpl[f][r % Q6] = rr[r];
-      double a = 0;
-      for (int k = 0; k < 6; k++)
-        a += O.w_frame[6 * r + k] * rr[k];
-      Wr[r] = a;
-      cst += rr[r] * a;
-    }
-    if (DERIVS)
-    {
-      double Jl[36], T[36];
-      Jlog6(rr, Jl);
-      for (int r = 0; r < 6; r++)
-        for (int half = 0; half < 2; half++)
-          for (int k = 0; k < 3; k++)
-          {
-            double a = 0;
-            for (int m2 = 0; m2 < 3; m2++)
-              a += Jl[6 * r + 3 * half + m2] * s.fR[f][3 * k + m2];
-            T[6 * r + 3 * half + k] = a;
-          }
-      for (int r = 0; r < 36; r++)
-        s.Tpl[f][r % Q36] = T[r];
-      for (int k = 0; k < 6; k++)
-      {
-        double a = 0;
-        for (int r = 0; r < 6; r++)
-          a += T[6 * r + k] * Wr[r];
-        s.Wfr[f][k % FS] = a;
-      }
-    }
-    return 0.5 * cst;
+    return quad_pose_cost<Cfg, DERIVS>(O, slot, s, f);
   }
 
   template <class Cfg, bool DERIVS>

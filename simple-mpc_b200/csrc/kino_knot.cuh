@@ -36,6 +36,7 @@ namespace smpc
     static constexpr int NQ = NV + 1, NX = NQ + NV, NDX = 2 * NV, NF = FS * NK, NJNT = NV - 6, NU = NJNT + NF;
     static constexpr int NRHS = 2 * NV + NU;
     static constexpr int VR = (FS == 6) ? 6 : 3; // frame-velocity rows per foot
+    static constexpr int PR = FS;                  // rows of the <foot>_pose_cost residual: translation / log6 placement
     static constexpr int NCMAX = NJNT + NK * (((FS == 6) ? 17 : 2) + VR + ((FS == 3) ? 1 : 0));
   };
 
@@ -46,7 +47,8 @@ namespace smpc
     ROW_CONE1 = 2,
     ROW_VEL = 3,
     ROW_LAND = 4,
-    ROW_DCM = 5
+    ROW_DCM = 5,
+    ROW_WCONE = 6 // one of the 17 rows of the wrench cone of a quad foot (rsub = row)
   };
 
   template <class Cfg>
@@ -72,7 +74,7 @@ namespace smpc
       };
       struct
       {
-        double WJc[6][NDX], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][3][NV];
+        double WJc[6][NDX], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][Cfg::PR][NV];
         double cval[Cfg::NCMAX], dproj[Cfg::NCMAX], vplus[Cfg::NCMAX], rpinf[Cfg::NCMAX], rcrit[Cfg::NCMAX];
       };
     };
@@ -93,7 +95,8 @@ namespace smpc
         double Lx[NDX], Lu[NU > 0 ? NU : 1], gx[NDX], gu[NU > 0 ? NU : 1];
       };
     };
-    double Wch[6], Wcdh[6], Wfr[NK][3]; // weighted residuals (written while era-1 arrays are still read at the terminal node)
+    static constexpr int Q6 = (Cfg::FS == 6) ? 6 : 1, Q36 = (Cfg::FS == 6) ? 36 : 1; // sizes of the quad-foot-only arrays
+    double Wch[6], Wcdh[6], Wfr[NK][Cfg::PR]; // weighted residuals (written while era-1 arrays are still read at the terminal node)
     double mass;                          // Y[0][0], kept past era 1
     double fR[NK][9], fp[NK][3], lever[NK][3], vf[NK][6];
     double com[3], vcom[3], h0[6], hd0[6], hg[6], hdg[6], hdF[6];
@@ -110,7 +113,8 @@ namespace smpc
     // ---- linearisation only (DERIVS = true). Everything from dh_dq on is never touched by the value-only (trial)
     // instantiation, which is launched with trial_bytes() of shared memory and therefore fits more CTAs per SM ----
     double dh_dq[6][NV];
-    double Jp[NK][3][NV];
+    double Jp[NK][Cfg::PR][NV];       // world-aligned foot Jacobian: translation rows (+ rotation rows for quad feet)
+    double rpl[NK][Q6], Tpl[NK][Q36]; // quad feet: pose residual log6(ref^-1 oMf) and T = Jlog6(r) blkdiag(R^T, R^T)
     double vf_dq[NK][Cfg::VR][NV], vf_dv[NK][Cfg::VR][NV];
     double dhF_dq[3][NV], dhF_du[6][Cfg::NF];
     double Jq6[36], Jv6[36], Jl6[36];
@@ -497,6 +501,56 @@ namespace smpc
     return 0.0;
   }
 
+  // <foot>_pose_cost of a quad foot: FramePlacementResidual r = log6(ref^-1 oMf), weight w_frame (6 x 6). The residual
+  // Jacobian is T Jp with T = Jlog6(r) blkdiag(R^T, R^T) and Jp the world-aligned foot Jacobian; stores r, T and the
+  // gradient weights Wfr = T^T W r. Returns 1/2 r^T W r. S = KinoScratch or FullScratch (reference src/kinodynamics.cpp:67-73,
+  // src/fulldynamics.cpp:99-104).
+  template <class Cfg, bool DERIVS, class S>
+  SMPC_DEV double quad_pose_cost(const DevOcp & O, const smpc_slot & slot, S & s, int f)
+  {
+    constexpr int Q6 = S::Q6, Q36 = S::Q36, FS = Cfg::FS;
+    const double * Rr = slot.foot_ref[f];
+    double Rrel[9], dp[3], prel[3], rr[6], Wr[6], cst = 0;
+    m3tm(Rr, s.fR[f], Rrel);
+    for (int r = 0; r < 3; r++)
+      dp[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
+    m3tv(Rr, dp, prel);
+    log6(Rrel, prel, rr);
+    for (int r = 0; r < 6; r++)
+    {
+      s.rpl[f][r % Q6] = rr[r];
+      double a = 0;
+      for (int k = 0; k < 6; k++)
+        a += O.w_frame[6 * r + k] * rr[k];
+      Wr[r] = a;
+      cst += rr[r] * a;
+    }
+    if (DERIVS)
+    {
+      double Jl[36], T[36];
+      Jlog6(rr, Jl);
+      for (int r = 0; r < 6; r++)
+        for (int half = 0; half < 2; half++)
+          for (int k = 0; k < 3; k++)
+          {
+            double a = 0;
+            for (int m2 = 0; m2 < 3; m2++)
+              a += Jl[6 * r + 3 * half + m2] * s.fR[f][3 * k + m2];
+            T[6 * r + 3 * half + k] = a;
+          }
+      for (int r = 0; r < 36; r++)
+        s.Tpl[f][r % Q36] = T[r];
+      for (int k = 0; k < 6; k++)
+      {
+        double a = 0;
+        for (int r = 0; r < 6; r++)
+          a += T[6 * r + k] * Wr[r];
+        s.Wfr[f][k % FS] = a;
+      }
+    }
+    return 0.5 * cst;
+  }
+
   // ------------------------------------------------------------------------------------------
   // stage knot
   // ------------------------------------------------------------------------------------------
@@ -505,7 +559,8 @@ namespace smpc
   {
     constexpr int NV = Cfg::NV, NQ = Cfg::NQ, NX = Cfg::NX, NDX = Cfg::NDX, NU = Cfg::NU, NK = Cfg::NK, FS = Cfg::FS;
     constexpr int NF = Cfg::NF, NJNT = Cfg::NJNT, NRHS = Cfg::NRHS, VR = Cfg::VR;
-    static_assert(FS == 3, "kinodynamics CUDA knot: only point feet (force_size 3) are implemented");
+    static_assert(FS == 3 || FS == 6, "point feet (3-D forces) or quad feet (6-D wrenches)");
+    constexpr int PR = Cfg::PR;
     const smpc_slot & slot = *io.slot;
     const unsigned cmask = slot.contact_mask;
     const double dt = O.dt, mu = io.mu, inv_mu = 1.0 / io.mu;
@@ -583,6 +638,8 @@ namespace smpc
             {
               hdF[r] += u[FS * f + r];
               hdF[3 + r] += t[r];
+              if (FS == 6)
+                hdF[3 + r] += u[FS * f + 3 + r]; // contact torque of a quad foot
             }
           }
         double b[6];
@@ -652,8 +709,17 @@ namespace smpc
             continue;
           if (O.force_cone)
           {
-            s.rkind[row] = ROW_CONE0, s.rarg[row] = f, s.rsub[row] = 0, row++;
-            s.rkind[row] = ROW_CONE1, s.rarg[row] = f, s.rsub[row] = 0, row++;
+            if (FS == 6)
+            {
+              // CentroidalWrenchConeResidual: 17 rows A [f; tau] <= 0 (reference src/kinodynamics.cpp:104-111)
+              for (int r = 0; r < 17; r++, row++)
+                s.rkind[row] = ROW_WCONE, s.rarg[row] = f, s.rsub[row] = r;
+            }
+            else
+            {
+              s.rkind[row] = ROW_CONE0, s.rarg[row] = f, s.rsub[row] = 0, row++;
+              s.rkind[row] = ROW_CONE1, s.rarg[row] = f, s.rsub[row] = 0, row++;
+            }
           }
           for (int r = 0; r < VR; r++, row++)
           {
@@ -661,7 +727,7 @@ namespace smpc
             s.rarg[row] = f;
             s.rsub[row] = r;
           }
-          if (O.land_cstr && (slot.land_mask & (1u << f)))
+          if (FS == 3 && O.land_cstr && (slot.land_mask & (1u << f)))
           {
             s.rkind[row] = ROW_LAND, s.rarg[row] = f, s.rsub[row] = 2, row++;
           }
@@ -769,6 +835,19 @@ namespace smpc
             s.vf_dq[f][r][j] = a3[r];
             s.vf_dv[f][r][j] = b3[r];
           }
+          if (FS == 6)
+          {
+            // rotation rows: world-aligned Jacobian J_ang, LOCAL angular velocity partials R^T (v_p x J_j)_ang, R^T J_ang
+            const double z3[3] = {0, 0, 0};
+            m3tv(s.fR[f], on ? w + 3 : z3, a3);
+            m3tv(s.fR[f], on ? Jc + 3 : z3, b3);
+            for (int r = 0; r < 3; r++)
+            {
+              s.Jp[f][(3 + r) % PR][j] = on ? Jc[3 + r] : 0.0;
+              s.vf_dq[f][(3 + r) % VR][j] = a3[r];
+              s.vf_dv[f][(3 + r) % VR][j] = b3[r];
+            }
+          }
           if (cmask & (1u << f))
           {
             const double dl[3] = {jp[0] - Jcj[0], jp[1] - Jcj[1], jp[2] - Jcj[2]};
@@ -809,12 +888,15 @@ namespace smpc
             b[r] = 0;
           if (cmask & (1u << f))
           {
-            // d/df_k [f ; lever x f] = [e_k ; lever x e_k]
+            // d/df_k [f ; lever x f] = [e_k ; lever x e_k] ; contact torque of a quad foot: d/dtau_k = [0 ; e_k]
             b[k] = 1.0;
-            double ek[3] = {0, 0, 0}, t[3];
-            ek[k] = 1.0;
-            v3cross(s.lever[f], ek, t);
-            b[3] = t[0], b[4] = t[1], b[5] = t[2];
+            if (k < 3)
+            {
+              double ek[3] = {0, 0, 0}, t[3];
+              ek[k] = 1.0;
+              v3cross(s.lever[f], ek, t);
+              b[3] = t[0], b[4] = t[1], b[5] = t[2];
+            }
           }
           for (int r = 0; r < 6; r++)
             s.dhF_du[r][jf] = b[r];
@@ -911,14 +993,15 @@ namespace smpc
             sacc += O.w_centder[6 * r + k] * s.dhF_du[k][a];
           s.WJcdu[r][a] = sacc;
         }
-        for (int e = tid; e < NK * 3 * NV; e += SMPC_NT)
-        {
-          const int f = e / (3 * NV), r = (e / NV) % 3, a = e % NV;
-          double sacc = 0;
-          for (int k = 0; k < 3; k++)
-            sacc += O.w_frame[3 * r + k] * s.Jp[f][k][a];
-          s.WJp[f][r][a] = sacc;
-        }
+        if (FS == 3)
+          for (int e = tid; e < NK * 3 * NV; e += SMPC_NT)
+          {
+            const int f = e / (3 * NV), r = (e / NV) % 3, a = e % NV;
+            double sacc = 0;
+            for (int k = 0; k < 3; k++)
+              sacc += O.w_frame[3 * r + k] * s.Jp[f][k][a];
+            s.WJp[f][r][a] = sacc;
+          }
       }
       SMPC_END
     }
@@ -962,24 +1045,53 @@ namespace smpc
       if (tid >= 2 && tid < 2 + NK)
       {
         const int f = tid - 2;
-        double rf[3], cst = 0;
-        for (int r = 0; r < 3; r++)
-          rf[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
-        for (int r = 0; r < 3; r++)
+        if (FS == 6)
+          s.costs[4 + f] = quad_pose_cost<Cfg, DERIVS>(O, slot, s, f);
+        else
         {
-          double a = 0;
-          for (int k = 0; k < 3; k++)
-            a += O.w_frame[3 * r + k] * rf[k];
-          s.Wfr[f][r] = a;
-          cst += rf[r] * a;
+          double rf[3], cst = 0;
+          for (int r = 0; r < 3; r++)
+            rf[r] = s.fp[f][r] - slot.foot_ref[f][9 + r];
+          for (int r = 0; r < 3; r++)
+          {
+            double a = 0;
+            for (int k = 0; k < 3; k++)
+              a += O.w_frame[3 * r + k] * rf[k];
+            s.Wfr[f][r] = a;
+            cst += rf[r] * a;
+          }
+          s.costs[4 + f] = 0.5 * cst;
         }
-        s.costs[4 + f] = 0.5 * cst;
       }
     }
     SMPC_END
 
     // ---- constraint values, multiplier projection ----
     SMPC_PAR(tid)
+    {
+    if (DERIVS && FS == 6)
+    {
+      // pose cost of a quad foot: residual Jacobian T Jp (T from kino6_pose_cost, previous phase); weighted: (T^T W T) Jp
+      constexpr int Q36 = KinoScratch<Cfg>::Q36;
+      for (int e = tid; e < NK * PR * NV; e += SMPC_NT)
+      {
+        const int f = e / (PR * NV), r = (e / NV) % PR, a = e % NV;
+        double sacc = 0;
+        for (int i2 = 0; i2 < 6; i2++)
+        {
+          double wtj = 0; // (W T Jp)(i2, a)
+          for (int j2 = 0; j2 < 6; j2++)
+          {
+            double tj = 0; // (T Jp)(j2, a)
+            for (int k = 0; k < 6; k++)
+              tj += s.Tpl[f][(6 * j2 + k) % Q36] * s.Jp[f][k % PR][a];
+            wtj += O.w_frame[6 * i2 + j2] * tj;
+          }
+          sacc += s.Tpl[f][(6 * i2 + r) % Q36] * wtj;
+        }
+        s.WJp[f][r][a] = sacc;
+      }
+    }
     for (int row = tid; row < s.nc; row += SMPC_NT)
     {
       const int kind = s.rkind[row], f = s.rarg[row];
@@ -991,6 +1103,13 @@ namespace smpc
         lo = O.qmin[f];
         hi = O.qmax[f];
         type = 2;
+      }
+      else if (kind == ROW_WCONE)
+      {
+        const double * Ac = O.wcone + 6 * s.rsub[row];
+        for (int k = 0; k < 6; k++)
+          c += Ac[k] * s.u[FS * f + (k % FS)];
+        type = 1;
       }
       else if (kind == ROW_CONE0)
       {
@@ -1016,6 +1135,7 @@ namespace smpc
       s.vplus[row] = pr * inv_mu;
       s.rpinf[row] = fabs(pr - mu * io.prev_vs[row]);
       s.rcrit[row] = fabs(pr - mu * io.vs[row]);
+    }
     }
     SMPC_END
 
@@ -1057,7 +1177,7 @@ namespace smpc
             for (int f = 0; f < NK; f++)
             {
               double tf = 0;
-              for (int r = 0; r < 3; r++)
+              for (int r = 0; r < PR; r++)
                 tf += s.Jp[f][r][a] * s.WJp[f][r][b];
               acc += tf;
             }
@@ -1118,7 +1238,7 @@ namespace smpc
             for (int f = 0; f < NK; f++)
             {
               double tf = 0;
-              for (int r = 0; r < 3; r++)
+              for (int r = 0; r < PR; r++)
                 tf += s.Jp[f][r][a] * s.Wfr[f][r];
               g += tf;
             }
@@ -1159,7 +1279,9 @@ namespace smpc
           {
             const int kind = s.rkind[row], f = s.rarg[row];
             double cu = 0;
-            if (kind == ROW_CONE0)
+            if (kind == ROW_WCONE)
+              cu = (j >= FS * f && j < FS * f + FS) ? O.wcone[6 * s.rsub[row] + (j - FS * f) % 6] : 0.0;
+            else if (kind == ROW_CONE0)
               cu = (j == FS * f + 2) ? -1.0 : 0.0;
             else if (kind == ROW_CONE1)
             {
@@ -1202,7 +1324,9 @@ namespace smpc
           if (row < s.nc && s.ractive[row])
           {
             const int kind = s.rkind[row], f = s.rarg[row];
-            if (kind == ROW_CONE0)
+            if (kind == ROW_WCONE)
+              cu = (j >= FS * f && j < FS * f + FS) ? O.wcone[6 * s.rsub[row] + (j - FS * f) % 6] : 0.0;
+            else if (kind == ROW_CONE0)
               cu = (j == FS * f + 2) ? -1.0 : 0.0;
             else if (kind == ROW_CONE1)
             {

@@ -747,6 +747,8 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   const bool talos_shape = model->njoints == 23 && model->nv == 28 && O.nk == 2 && O.fs == 6;
   if (O.kind == SMPC_OCP_KINODYNAMICS && go2_shape)
     rc = setup_knots_kino_go2(c);
+  else if (O.kind == SMPC_OCP_KINODYNAMICS && talos_shape)
+    rc = setup_knots_kino_talos(c);
   else if (O.kind == SMPC_OCP_FULLDYNAMICS && go2_shape)
     rc = setup_knots_full_go2(c);
   else if (O.kind == SMPC_OCP_FULLDYNAMICS && talos_shape)
@@ -755,7 +757,7 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
     rc = setup_knots_centro(c);
   else
     smpc::err() = "no CUDA kernel instantiation for this robot/problem shape (built: kinodynamics and full dynamics on a 12-DoF quadruped with "
-                  "point feet; full dynamics on a 22-DoF biped with quad feet; centroidal with 2 quad feet or 4 point feet)";
+                  "point feet and on a 22-DoF biped with quad feet; centroidal with 2 quad feet or 4 point feet)";
   if (rc != SMPC_OK)
     return rc;
   // Riccati sweep: compile-time specialised kernel when one is instantiated for (ndx, nu, ncmax). Default: the fastest

@@ -65,6 +65,28 @@ static void full_knot_any(const DevModel & M, const DevOcp & O, const KnotLayout
   }
 }
 
+// one kinodynamics knot of shape Cfg
+template <class Cfg>
+static void kino_knot_any(const DevModel & M, const DevOcp & O, const KnotLayout & L, const KnotIO & io, bool terminal, bool derivs)
+{
+  auto s = std::make_unique<KinoScratch<Cfg>>();
+  memset(s.get(), 0, sizeof(*s));
+  if (terminal)
+  {
+    if (derivs)
+      kino_terminal_knot<Cfg, true>(M, O, L, io, *s);
+    else
+      kino_terminal_knot<Cfg, false>(M, O, L, io, *s);
+  }
+  else
+  {
+    if (derivs)
+      kino_stage_knot<Cfg, true>(M, O, L, io, *s);
+    else
+      kino_stage_knot<Cfg, false>(M, O, L, io, *s);
+  }
+}
+
 template <int NDX, int NU, int NC>
 static void ric4_any(const KnotLayout & L, const SolLayout & SL, int N, const double * knots, double * sol, double mudyn, double mueq, int * flag, double * P0)
 {
@@ -75,7 +97,7 @@ static void ric4_any(const KnotLayout & L, const SolLayout & SL, int N, const do
 extern "C" {
 const char * emul_last_error() { return g_err.c_str(); }
 
-// one kinodynamics knot (Go2 sizes). knot buffer must hold KnotLayout(ndx,nu,ncmax).size doubles.
+// one kinodynamics knot (Go2 sizes with point feet, or talos-like sizes with quad feet). knot buffer must hold KnotLayout(ndx,nu,ncmax).size doubles.
 int emul_kino_knot(
   const smpc_model_desc * model, const smpc_ocp_desc * ocp, const smpc_slot * slot, const smpc_terminal * term, int terminal,
   int derivs, const double * x, const double * u, const double * xn, const double * vs, const double * prev_vs,
@@ -88,11 +110,11 @@ int emul_kino_knot(
     auto O = std::make_unique<DevOcp>();
     build_dev_model(*model, *M);
     build_dev_ocp(*model, *ocp, *O);
-    if (model->njoints != 13 || model->nv != 18 || model->nfeet != 4 || O->fs != 3)
-      throw std::runtime_error("emul: only the Go2-sized kinodynamics instantiation is built");
+    const bool go2 = model->njoints == 13 && model->nv == 18 && model->nfeet == 4 && O->fs == 3;
+    const bool talos = model->njoints == 23 && model->nv == 28 && model->nfeet == 2 && O->fs == 6;
+    if (!go2 && !talos)
+      throw std::runtime_error("emul: kinodynamics instantiations: Go2-sized (point feet) and talos-sized (quad feet)");
     KnotLayout L = make_knot_layout(O->ndx, O->nu, O->ncmax);
-    auto s = std::make_unique<KinoScratch<Go2Cfg>>();
-    memset(s.get(), 0, sizeof(*s));
     KnotIO io;
     memset(&io, 0, sizeof(io));
     io.x = x, io.u = u, io.xn = xn;
@@ -103,20 +125,10 @@ int emul_kino_knot(
     KnotScalars sc;
     memset(&sc, 0, sizeof(sc));
     io.sc = &sc;
-    if (terminal)
-    {
-      if (derivs)
-        kino_terminal_knot<Go2Cfg, true>(*M, *O, L, io, *s);
-      else
-        kino_terminal_knot<Go2Cfg, false>(*M, *O, L, io, *s);
-    }
+    if (go2)
+      kino_knot_any<Go2Cfg>(*M, *O, L, io, terminal != 0, derivs != 0);
     else
-    {
-      if (derivs)
-        kino_stage_knot<Go2Cfg, true>(*M, *O, L, io, *s);
-      else
-        kino_stage_knot<Go2Cfg, false>(*M, *O, L, io, *s);
-    }
+      kino_knot_any<KinoCfg<23, 28, 2, 6>>(*M, *O, L, io, terminal != 0, derivs != 0);
     memcpy(scalars, &sc, sizeof(sc));
   }
   catch (const std::exception & e)
@@ -278,6 +290,10 @@ int emul_riccati4(
     ric4_any<56, 22, 78>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
   else if (ndx == 56 && nu == 22 && ncmax == 90)
     ric4_any<56, 22, 90>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 56 && nu == 34 && ncmax == 34)
+    ric4_any<56, 34, 34>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 56 && nu == 34 && ncmax == 46)
+    ric4_any<56, 34, 46>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
   else
   {
     g_err = "emul_riccati4: size not instantiated";

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 import numpy as np
 import pytest
-from smpc_ctypes import (ROOT, go2_like_model, go2_kino_ocp, standing_slot, fk_numpy, x_ref_of, total_mass, default_opts, Slot, Terminal, SolveInfo, dbl_p)
+from smpc_ctypes import (ROOT, go2_like_model, go2_kino_ocp, talos_like_model, talos_kino_ocp, standing_slot, fk_numpy, x_ref_of, total_mass, default_opts, Slot, Terminal, SolveInfo, dbl_p)
 from oracle_libs import load_oracle
 
 
@@ -20,6 +20,7 @@ def P(a):
 
 
 GAIT = [0b1111] * 10 + [0b0110] * 30 + [0b1111] * 10 + [0b1001] * 30
+TALOS_GAIT = [0b11] * 6 + [0b01] * 10 + [0b11] * 6 + [0b10] * 10  # short cycle: every phase inside T
 
 
 def load_emul():
@@ -31,12 +32,20 @@ def load_emul():
     return lib
 
 
-def run_case(cone):
+def run_case(cone, robot="go2"):
     orc, emu = load_oracle(), load_emul()
-    m, lim = go2_like_model()
-    nq, nv, T = m.nq, m.nv, 50
-    nx, ndx, nu = nq + nv, 2 * nv, 24
-    ocpb = go2_kino_ocp(m, lim, T=T, force_cone=cone, land_cstr=cone, terminal_constraint=cone)
+    if robot == "go2":
+        m, lim = go2_like_model()
+        nq, nv, T, gait = m.nq, m.nv, 50, GAIT
+        ocpb = go2_kino_ocp(m, lim, T=T, force_cone=cone, land_cstr=cone, terminal_constraint=cone)
+    else:
+        # talos-like biped, quad feet: 6-D contact wrenches as controls, 6-D LOCAL contact velocity rows, FramePlacement pose
+        # cost; cone = True adds the 17-row wrench cones and drops the joint limits (the (56, 34, 46) Riccati shape)
+        m, lim = talos_like_model()
+        nq, nv, T, gait = m.nq, m.nv, 24, TALOS_GAIT
+        ocpb = talos_kino_ocp(m, lim, T=T, force_cone=cone, kinematics_limits=not cone, terminal_constraint=cone)
+    nk, fs = m.nfeet, ocpb.desc.force_size
+    nx, ndx, nu = nq + nv, 2 * nv, nv - 6 + nk * fs
     ocp = ocpb.desc
     opts = default_opts(orc)
     ctx = C.c_void_p()
@@ -47,7 +56,7 @@ def run_case(cone):
     rng = np.random.default_rng(1)
 
     def gait_slot(i):
-        mask, prev = GAIT[i % 80], GAIT[(i - 1) % 80]
+        mask, prev = gait[i % len(gait)], gait[(i - 1) % len(gait)]
         return standing_slot(m, ocpb, feet, contact_mask=mask, land_mask=mask & ~prev,
                              force_z=total_mass(m) * 9.81 / max(bin(mask).count('1'), 1))
 
@@ -62,8 +71,8 @@ def run_case(cone):
     us = np.tile(np.array(slots[0].u_ref[:nu]), (T, 1)).copy()
     orc.orc_set_warmstart(ctx, 0, 1, P(xs), P(us))
     x0 = xref.copy()
-    x0[nq:] += rng.normal(size=nv) * 0.1
-    x0[7:19] += rng.normal(size=12) * 0.05
+    x0[nq:] += rng.normal(size=nv) * (0.1 if robot == "go2" else 0.03)
+    x0[7:nq] += rng.normal(size=nq - 7) * (0.05 if robot == "go2" else 0.01)
     info = SolveInfo()
     orc.orc_solve(ctx, P(x0), 2)  # two iterations: non-trivial multipliers
     orc.orc_get_info(ctx, 0, 1, C.byref(info))
@@ -145,17 +154,18 @@ def run_case(cone):
         return K, dxs, dus
 
     out = dict(worst=worst, pinf=pinf, dinf=dinf, info=info, Ko=Ko, odx=odx, odu=odu)
+    tuned = emu.emul_riccati3 if robot == "go2" else emu.emul_riccati4  # riccati3.cuh is instantiated for the Go2 shapes only
     out['generic_on_oracle'] = sweep(emu.emul_riccati, orc_knots)
-    out['tma_on_oracle'] = sweep(emu.emul_riccati3, orc_knots)
+    out['tma_on_oracle'] = sweep(tuned, orc_knots)
     out['two_column_on_oracle'] = sweep(emu.emul_riccati4, orc_knots)
-    out['special_on_emul'] = sweep(emu.emul_riccati3, emu_knots)
+    out['special_on_emul'] = sweep(tuned, emu_knots)
     # conditioning of the penalised recursion, measured: the oracle's own knots with every entry moved by at most ONE ULP
     # (relative 2^-52, the size of the difference between two correct evaluations of the same Jacobians)
     spread = []
     for seed in range(4):
         r = np.random.default_rng(100 + seed)
         pert = orc_knots * (1.0 + (2.0 ** -52) * r.uniform(-1, 1, size=orc_knots.shape))
-        Kp, dxp, dup = sweep(emu.emul_riccati3, pert)
+        Kp, dxp, dup = sweep(tuned, pert)
         rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
         spread.append(dict(K=max(rel(Kp[t], Ko[t]) for t in range(T)), K0=rel(Kp[0], Ko[0]), du=rel(dup, odu), dx=rel(dxp, odx)))
     out['ulp_spread'] = spread
@@ -163,9 +173,10 @@ def run_case(cone):
     return out
 
 
-@pytest.fixture(scope="module", params=[False, True], ids=["joint-limits+contact-velocity", "cone+landing+dcm"])
+@pytest.fixture(scope="module", params=[(False, "go2"), (True, "go2"), (False, "talos"), (True, "talos")],
+                ids=["joint-limits+contact-velocity", "cone+landing+dcm", "talos-6d-limits+contact-velocity", "talos-6d-wrench-cone+dcm"])
 def case(request):
-    return run_case(request.param)
+    return run_case(*request.param)
 
 
 def test_knots_match_oracle_to_rounding(case):

@@ -74,6 +74,22 @@ def test_full_talos_landing_velocity_and_terminal_constraint():
     assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
 
 
+def test_kino_talos_reference_example_config():
+    # reference examples/talos_kinodynamics.py:44-130: talos-like 22-DoF biped, 6-D contact wrenches as controls, joint limits
+    # + 6-D LOCAL contact-velocity equalities (src/kinodynamics.cpp:113-121), FramePlacement pose costs (:67-73), T = 100
+    r = pu.run_parity(batch=2, ticks=5, seed=0, verbose=True, scenario=pu.TalosKinoScenario, force_cone=False)
+    assert r["iters_equal"] and r["alphas_equal"], r
+    assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
+
+
+def test_kino_talos_wrench_cone_and_terminal_constraint():
+    # CentroidalWrenchConeResidual (17 rows per stance foot, src/kinodynamics.cpp:104-111) and the DCM terminal constraint
+    # switched on; per-instance gait phases, 12 ticks
+    r = pu.run_parity(batch=3, ticks=12, seed=2, scenario=pu.TalosKinoScenario, force_cone=True, terminal_constraint=True)
+    assert r["iters_equal"] and r["alphas_equal"], r
+    assert r["us"] <= 1e-6 and r["xs"] <= 1e-6 and r["K"] <= 1e-5, r
+
+
 def test_centroidal_talos_single_and_batch():
     # config C2: CentroidalOCP, T = 100, 6-D contacts with wrench cones, walk 20/80/20/80
     _check(pu.run_parity(batch=1, ticks=6, seed=0, verbose=True, scenario=pu.TalosCentroidalScenario))

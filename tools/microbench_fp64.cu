@@ -47,6 +47,62 @@ __global__ void thr(double * out, double c, int iters)
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA (mma.sync.aligned.m8n8k4.row.col.f64): D(8x8) += A(8x4) B(4x8), 256 FMA per warp instruction.
+__device__ __forceinline__ void dmma(double & d0, double & d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NACC>
+__global__ void dmma_thr(double * out, long long * cyc, double c, int iters)
+{
+  double d[NACC][2];
+#pragma unroll
+  for (int k = 0; k < NACC; k++) d[k][0] = d[k][1] = threadIdx.x * 1e-3 + k;
+  const double a = 1e-3 * (threadIdx.x & 7), b = c;
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int k = 0; k < NACC; k++) dmma(d[k][0], d[k][1], a, b);
+  }
+  long long t1 = clock64();
+  double s = 0;
+  for (int k = 0; k < NACC; k++) s += d[k][0] + d[k][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+template <int NACC>
+static void run_dmma(double * out, long long * cyc, const cudaDeviceProp & p)
+{
+  // latency: one warp, NACC independent chains
+  long long h = 0;
+  for (int rep = 0; rep < 2; rep++)
+  {
+    dmma_thr<NACC><<<1, 32>>>(out, cyc, 0.999, 1000);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+  }
+  printf("DMMA m8n8k4, one warp, %d independent accumulators: %.1f cycles per mma (issue-to-issue)\n", NACC, h / (4000.0 * NACC));
+  for (int tpb = 128; tpb <= 512; tpb *= 2)
+  {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int iters = 5000, blocks = p.multiProcessorCount * (1024 / tpb);
+    dmma_thr<NACC><<<blocks, tpb>>>(out, cyc, 0.999, 100);
+    cudaEventRecord(e0);
+    dmma_thr<NACC><<<blocks, tpb>>>(out, cyc, 0.999, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double fl = 2.0 * 256.0 * 4.0 * NACC * iters * (double)blocks * (tpb / 32);
+    printf("DMMA throughput, %d acc/warp: %d blocks x %d threads (%d warps/SM): %.2f TFLOP/s (%.1f FMA/clk/SM)\n", NACC, blocks, tpb, 1024 / 32,
+           fl / ms / 1e9, fl / 2 / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3));
+  }
+}
+
 int main()
 {
   double * out; long long * cyc;
@@ -86,5 +142,9 @@ int main()
     printf("DFMA throughput: %d blocks x %d threads: %.2f TFLOP/s (%.1f DFMA/clk/SM at %d MHz nominal)\n", blocks, tpb, fl / ms / 1e9,
            fl / 2 / (ms * 1e-3) / p.multiProcessorCount / (p.clockRate * 1e3), p.clockRate / 1000);
   }
+  run_dmma<1>(out, cyc, p);
+  run_dmma<2>(out, cyc, p);
+  run_dmma<4>(out, cyc, p);
+  run_dmma<8>(out, cyc, p);
   return 0;
 }
