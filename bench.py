@@ -319,6 +319,8 @@ def main():
     l1 = cu.smpc_launch_count(b.ctx)
     ric_ms, ric_n, sol_ms, sol_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     cu.smpc_timer_stats(b.ctx, 0, C.byref(ric_ms), C.byref(ric_n), C.byref(sol_ms), C.byref(sol_n))
+    kms = (C.c_double * 4)()
+    cu.smpc_kernel_times(b.ctx, kms)
     infos = b.info()
     iters = [infos[i].num_iters for i in range(B)]
     alphas = np.array([infos[i].alpha for i in range(B)])
@@ -370,6 +372,10 @@ def main():
                      "fp64": {"achieved_tflops": flops_launch / ric_avg_s / 1e12 if ric_avg_s > 0 else 0.0,
                               "nominal_peak_tflops": 37.0,
                               "peak_source": "tools/microbench_fp64.cu: 37.0 TFLOP/s DFMA measured on this pool's B200 (profiles/r01g_microbench_fp64.txt)"}},
+        # every kernel of the solve, CUDA events on the context's stream around the first round of each solve, ms per launch
+        "kernels": [{"name": n, "launch_ms": kms[i] / max(sol_n.value, 1)} for i, n in enumerate(
+            ["linearisation (k_knots: dynamics, costs, constraints, LQ knot)", "Riccati backward sweep", "forward sweep",
+             "trial evaluation (k_knots value-only) + linesearch decision"])],
         "solver": {"iters_per_tick_mean": float(np.mean(iters)), "alpha_mean": float(alphas.mean()),
                    "alpha_lt_1_frac": float((alphas < 1).mean())},
     }

@@ -312,6 +312,9 @@ int smpc_x0_from_prediction(smpc_ctx *);
 int smpc_timer_record(smpc_ctx *, int which);
 int smpc_timer_elapsed_ms(smpc_ctx *, float * ms);
 int smpc_timer_stats(smpc_ctx *, int reset, double * riccati_ms, int64_t * riccati_launches, double * solve_ms, int64_t * solves);
+/* per-kernel device time (ms) of the first round of every solve since the last smpc_timer_stats(reset = 1):
+ * ms4 = {linearisation, Riccati backward sweep, forward sweep, first trial evaluation + linesearch decision} */
+int smpc_kernel_times(smpc_ctx *, double * ms4);
 int smpc_sync(smpc_ctx *);
 
 /* test hooks: the dense LQ knot of (instance, t) from the last linearisation, in the device layout

@@ -16,17 +16,18 @@
 namespace smpc
 {
 
-  // Reciprocal square root of a Cholesky pivot. The pivot chain is the serial critical path of the sweep (one per
-  // column, 84 columns per stage; profiles/r01e: the pivot warp's sqrt-then-divide is 2 MUFU + 12 dependent FP64
-  // operations and the other three warps wait for it at the column barrier). The default keeps the correctly rounded
-  // 1.0 / sqrt(d) of oracle/orc_solver.hpp, so the device sweep stays bitwise equal to the oracle on identical knots.
-  // -DSMPC_FAST_PIVOTS switches to CUDA's rsqrt() (MUFU.RSQ64H + one cubic Newton step: 1 MUFU + 4 dependent
-  // operations, <= 1 ulp). Measured on B200 at B = 4096: 29.45 -> 28.16 ms per launch, parity against the oracle
-  // unchanged (K 1.6e-8 vs 1.8e-8, equal iteration counts and step sizes) - a 2 % tick gain that is not worth giving
-  // up the exact operation order by default.
+  // Reciprocal square root of a Cholesky pivot. The pivot chain is the serial critical path of the sweep (one per column,
+  // 84 columns per stage): ncu attributes 17 % of the kernel's stall samples to the barrier the other warps wait at while
+  // the pivot lane runs sqrt-then-divide (2 MUFU + 12 dependent FP64 operations, 147 cycles measured,
+  // profiles/r02g_microbench_fp64.txt). The device build therefore uses CUDA's rsqrt() (MUFU.RSQ64H + one cubic Newton
+  // step, 61 cycles, <= 1 ulp): measured on B200 at B = 4096 26.2 -> 24.4 ms per launch, single-instance tick 2.53 -> 2.33 ms
+  // (profiles/r02i). Consequence: on the device the factor differs from the oracle's correctly rounded 1.0 / sqrt(d) in the last
+  // bit, i.e. by the same 1-ulp perturbation the two independent knot evaluations already differ by; the GPU parity tolerances are
+  // unchanged (tests/test_gpu_parity.py). -DSMPC_EXACT_PIVOTS restores 1.0 / sqrt(d); the CPU emulation harness always uses
+  // it, so tests/test_emul_vs_oracle.py keeps checking the sweep's operation order bit for bit.
   SMPC_DEV double pivot_rsqrt(double d)
   {
-#if defined(__CUDACC__) && defined(SMPC_FAST_PIVOTS)
+#if defined(__CUDACC__) && !defined(SMPC_EXACT_PIVOTS)
     return rsqrt(d);
 #else
     return 1.0 / sqrt(d);

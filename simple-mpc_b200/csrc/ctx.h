@@ -134,6 +134,8 @@ struct smpc_ctx
   void * h_staging = nullptr; // pinned host staging
   size_t h_staging_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+  cudaEvent_t evk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // first round of a solve: lin | decide+riccati | forward | first trial
+  double acc_kernel_ms[4] = {0, 0, 0, 0};                                      // linearisation, Riccati backward, forward sweep, first trial (+ ls_decide)
   float last_ms = 0, last_ric_ms = 0;
   double acc_ric_ms = 0, acc_solve_ms = 0; // accumulated since smpc_timer_reset
   int64_t acc_ric_launches = 0, acc_solves = 0;

@@ -107,14 +107,15 @@ namespace smpc
     double rs[NDX], xnext[NX], e[NDX], lplus[NDX];
     // constraint rows
     int nc;
-    int rkind[Cfg::NCMAX], rarg[Cfg::NCMAX], rsub[Cfg::NCMAX];
-    int ractive[Cfg::NCMAX];
+    // row table as bytes (kind < 7, joint / foot index < 64, sub-row < 17): shared memory bounds the resident knots per SM
+    unsigned char rkind[Cfg::NCMAX], rarg[Cfg::NCMAX], rsub[Cfg::NCMAX], ractive[Cfg::NCMAX];
     double costs[8 + NK];
+    double rpl[NK][Q6]; // quad feet: pose residual log6(ref^-1 oMf) (written by the value-only instantiation too)
     // ---- linearisation only (DERIVS = true). Everything from dh_dq on is never touched by the value-only (trial)
     // instantiation, which is launched with trial_bytes() of shared memory and therefore fits more CTAs per SM ----
     double dh_dq[6][NV];
     double Jp[NK][Cfg::PR][NV];       // world-aligned foot Jacobian: translation rows (+ rotation rows for quad feet)
-    double rpl[NK][Q6], Tpl[NK][Q36]; // quad feet: pose residual log6(ref^-1 oMf) and T = Jlog6(r) blkdiag(R^T, R^T)
+    double Tpl[NK][Q36];              // quad feet: T = Jlog6(r) blkdiag(R^T, R^T) of the pose residual r
     double vf_dq[NK][Cfg::VR][NV], vf_dv[NK][Cfg::VR][NV];
     double dhF_dq[3][NV], dhF_du[6][Cfg::NF];
     double Jq6[36], Jv6[36], Jl6[36];
@@ -1104,7 +1105,7 @@ namespace smpc
         hi = O.qmax[f];
         type = 2;
       }
-      else if (kind == ROW_WCONE)
+      else if (FS == 6 && kind == ROW_WCONE)
       {
         const double * Ac = O.wcone + 6 * s.rsub[row];
         for (int k = 0; k < 6; k++)
@@ -1279,7 +1280,7 @@ namespace smpc
           {
             const int kind = s.rkind[row], f = s.rarg[row];
             double cu = 0;
-            if (kind == ROW_WCONE)
+            if (FS == 6 && kind == ROW_WCONE)
               cu = (j >= FS * f && j < FS * f + FS) ? O.wcone[6 * s.rsub[row] + (j - FS * f) % 6] : 0.0;
             else if (kind == ROW_CONE0)
               cu = (j == FS * f + 2) ? -1.0 : 0.0;
@@ -1324,7 +1325,7 @@ namespace smpc
           if (row < s.nc && s.ractive[row])
           {
             const int kind = s.rkind[row], f = s.rarg[row];
-            if (kind == ROW_WCONE)
+            if (FS == 6 && kind == ROW_WCONE)
               cu = (j >= FS * f && j < FS * f + FS) ? O.wcone[6 * s.rsub[row] + (j - FS * f) % 6] : 0.0;
             else if (kind == ROW_CONE0)
               cu = (j == FS * f + 2) ? -1.0 : 0.0;

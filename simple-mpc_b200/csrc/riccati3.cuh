@@ -237,7 +237,34 @@ namespace smpc
     SMPC_END
   }
 
-  template <int NDX, int NU, int NC, int TPB>
+  // Structure of the kinodynamics stage dynamics (kino_knot.cuh, semi-implicit Euler with the joint accelerations as controls):
+  // of the 2 NV rows of [A B] only the base rows [0, 6) and [NV, NV + 6) are dense; row k in [6, NV) holds A(k,k) = 1,
+  // A(k,NV+k) = dt, B(k,NF+k-6) = dt^2 and row NV + r, r >= 6, holds A(NV+r,NV+r) = 1, B(NV+r,NF+r-6) = dt. Seen by columns, column c
+  // of [A B] meets at most one sparse row in [6, NV) and one in [NV + 6, 2 NV). The two products that touch [A B] skip the
+  // structural zeros: every output still receives its non-zero terms in ascending k, i.e. the same fused multiply-adds
+  // in the same order as the dense product (adding an exact zero product changes nothing), at a third of the work.
+  template <int NV, int NF>
+  struct KinoRows
+  {
+    // sparse row of [A B] met by column c in [6, NV) (-1: none)
+    static SMPC_DEV int s1(int c)
+    {
+      if (c < 2 * NV)
+        return (c >= 6 && c < NV) ? c : ((c >= NV + 6) ? c - NV : -1);
+      const int m = c - 2 * NV - NF;
+      return m >= 0 ? 6 + m : -1;
+    }
+    // ... in [NV + 6, 2 NV)
+    static SMPC_DEV int s2(int c)
+    {
+      if (c < 2 * NV)
+        return (c >= NV + 6) ? c : -1;
+      const int m = c - 2 * NV - NF;
+      return m >= 0 ? NV + 6 + m : -1;
+    }
+  };
+
+  template <int NDX, int NU, int NC, int TPB, int SNV = 0>
   SMPC_DEV void riccati3_backward_inst(
     const KnotLayout & L, const SolLayout & SL, int N, const double * __restrict__ knots, double * __restrict__ sol,
     double mudyn, double mueq, double * sm, int * flag_out, double * P0out)
@@ -371,20 +398,65 @@ namespace smpc
 #pragma unroll
             for (int q = 0; q < 6; q++)
               c[r][q] = 0.0;
-#pragma unroll 4
-          for (int k = 0; k < NDX; k++)
+          if (SNV == 0)
           {
-            double bv[6];
-            ld2(src + k * lds, bv[0], bv[1]);
-            ld2(src + k * lds + 2, bv[2], bv[3]);
-            ld2(src + k * lds + 4, bv[4], bv[5]);
-#pragma unroll
-            for (int r = 0; r < TM; r++)
+#pragma unroll 4
+            for (int k = 0; k < NDX; k++)
             {
-              const double pk = PP[(a0 + r) * LDP + 1 + k];
+              double bv[6];
+              ld2(src + k * lds, bv[0], bv[1]);
+              ld2(src + k * lds + 2, bv[2], bv[3]);
+              ld2(src + k * lds + 4, bv[4], bv[5]);
 #pragma unroll
-              for (int q = 0; q < 6; q++)
-                c[r][q] = fma(pk, bv[q], c[r][q]);
+              for (int r = 0; r < TM; r++)
+              {
+                const double pk = PP[(a0 + r) * LDP + 1 + k];
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                  c[r][q] = fma(pk, bv[q], c[r][q]);
+              }
+            }
+          }
+          else
+          {
+            // kinodynamics structure (KinoRows): dense rows [0, 6), the tile's sparse rows in [6, NV), dense rows [NV, NV + 6),
+            // sparse rows in [NV + 6, 2 NV). A 6-column tile never straddles a structure block (NV, NF multiples of 6): its
+            // sparse rows are six consecutive ones, met on the diagonal of a 6 x 6 sub-block.
+            typedef KinoRows<(SNV > 0 ? SNV : 6), NU - (SNV > 0 ? SNV : 6) + 6> KR;
+            static_assert(SNV == 0 || (SNV % 6 == 0 && (NU - SNV + 6) % 6 == 0 && 2 * SNV == NDX), "structure blocks are whole 6-column tiles");
+            const int cg = 6 * tc; // first column of the tile in [A B]
+#pragma unroll 1
+            for (int half = 0; half < 2; half++)
+            {
+              const int kd = half ? SNV : 0;
+#pragma unroll 2
+              for (int k = kd; k < kd + 6; k++)
+              {
+                double bv[6];
+                ld2(src + k * lds, bv[0], bv[1]);
+                ld2(src + k * lds + 2, bv[2], bv[3]);
+                ld2(src + k * lds + 4, bv[4], bv[5]);
+#pragma unroll
+                for (int r = 0; r < TM; r++)
+                {
+                  const double pk = PP[(a0 + r) * LDP + 1 + k];
+#pragma unroll
+                  for (int q = 0; q < 6; q++)
+                    c[r][q] = fma(pk, bv[q], c[r][q]);
+                }
+              }
+              const int ks = half ? KR::s2(cg) : KR::s1(cg);
+              if (ks >= 0)
+              {
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                {
+                  const double v = src[(ks + q) * lds + q];
+#pragma unroll
+                  for (int r = 0; r < TM; r++)
+                    c[r][q] = fma(PP[(a0 + r) * LDP + 1 + ks + q], v, c[r][q]);
+                }
+              }
             }
           }
 #pragma unroll
@@ -435,26 +507,74 @@ namespace smpc
             for (int q = 0; q < 6; q++)
               c[r][q] = out[r * ldo + q];
           // rows [0, PR0) of PAB live in X, the rest in the C D d block of the knot copy: same k order, two loops
-#pragma unroll 1
-          for (int half = 0; half < 2; half++)
+          if (SNV == 0)
           {
-            const int k0 = half ? PR0 : 0, k1 = half ? NDX : PR0;
-            const double * pab = half ? PAB1 - PR0 * NAB : PAB;
-#pragma unroll 4
-            for (int k = k0; k < k1; k++)
+#pragma unroll 1
+            for (int half = 0; half < 2; half++)
             {
-              double av[TM], bv[6];
+              const int k0 = half ? PR0 : 0, k1 = half ? NDX : PR0;
+              const double * pab = half ? PAB1 - PR0 * NAB : PAB;
+#pragma unroll 4
+              for (int k = k0; k < k1; k++)
+              {
+                double av[TM], bv[6];
 #pragma unroll
-              for (int r = 0; r < TM; r += 2)
-                ld2(lhs + k * ldl + r, av[r], av[r + 1]);
-              ld2(pab + k * NAB + b0, bv[0], bv[1]);
-              ld2(pab + k * NAB + b0 + 2, bv[2], bv[3]);
-              ld2(pab + k * NAB + b0 + 4, bv[4], bv[5]);
+                for (int r = 0; r < TM; r += 2)
+                  ld2(lhs + k * ldl + r, av[r], av[r + 1]);
+                ld2(pab + k * NAB + b0, bv[0], bv[1]);
+                ld2(pab + k * NAB + b0 + 2, bv[2], bv[3]);
+                ld2(pab + k * NAB + b0 + 4, bv[4], bv[5]);
+#pragma unroll
+                for (int r = 0; r < TM; r++)
+#pragma unroll
+                  for (int q = 0; q < 6; q++)
+                    c[r][q] = fma(av[r], bv[q], c[r][q]);
+              }
+            }
+          }
+          else
+          {
+            // kinodynamics structure: output row i = column i of [A B] meets the dense rows and at most two sparse rows
+            typedef KinoRows<(SNV > 0 ? SNV : 6), NU - (SNV > 0 ? SNV : 6) + 6> KR;
+            static_assert(SNV == 0 || SNV + 6 <= PR0, "the dense rows of PAB all live in X");
+            const int ig = isR ? NDX + ar : ar; // first output row as a column of [A B]
+#pragma unroll 1
+            for (int half = 0; half < 2; half++)
+            {
+              const int kd = half ? SNV : 0;
+#pragma unroll 2
+              for (int k = kd; k < kd + 6; k++)
+              {
+                double av[TM], bv[6];
+#pragma unroll
+                for (int r = 0; r < TM; r += 2)
+                  ld2(lhs + k * ldl + r, av[r], av[r + 1]);
+                ld2(PAB + k * NAB + b0, bv[0], bv[1]);
+                ld2(PAB + k * NAB + b0 + 2, bv[2], bv[3]);
+                ld2(PAB + k * NAB + b0 + 4, bv[4], bv[5]);
+#pragma unroll
+                for (int r = 0; r < TM; r++)
+#pragma unroll
+                  for (int q = 0; q < 6; q++)
+                    c[r][q] = fma(av[r], bv[q], c[r][q]);
+              }
 #pragma unroll
               for (int r = 0; r < TM; r++)
+              {
+                const int ks = half ? KR::s2(ig + r) : KR::s1(ig + r);
+                if (ks >= 0)
+                {
+                  const double v = lhs[ks * ldl + r];
+                  const double * prow = (ks < PR0 ? PAB + ks * NAB : PAB1 + (ks - PR0) * NAB) + b0;
+                  double bv[6];
+                  ld2(prow, bv[0], bv[1]);
+                  ld2(prow + 2, bv[2], bv[3]);
+                  ld2(prow + 4, bv[4], bv[5]);
 #pragma unroll
-                for (int q = 0; q < 6; q++)
-                  c[r][q] = fma(av[r], bv[q], c[r][q]);
+                  for (int q = 0; q < 6; q++)
+                    c[r][q] = fma(v, bv[q], c[r][q]);
+                }
+              }
             }
           }
 #pragma unroll
@@ -470,8 +590,24 @@ namespace smpc
           const int ld = isq ? NDX : NU;
           double * dst = isq ? qh + tid : rh + (tid - NDX);
           double acc = *dst;
-          for (int k = 0; k < NDX; k++)
-            acc = fma(col[k * ld], w[k], acc);
+          if (SNV == 0)
+          {
+            for (int k = 0; k < NDX; k++)
+              acc = fma(col[k * ld], w[k], acc);
+          }
+          else
+          {
+            typedef KinoRows<(SNV > 0 ? SNV : 6), NU - (SNV > 0 ? SNV : 6) + 6> KR;
+            for (int half = 0; half < 2; half++)
+            {
+              const int kd = half ? SNV : 0;
+              for (int k = kd; k < kd + 6; k++)
+                acc = fma(col[k * ld], w[k], acc);
+              const int ks = half ? KR::s2(tid) : KR::s1(tid);
+              if (ks >= 0)
+                acc = fma(col[ks * ld], w[ks], acc);
+            }
+          }
           *dst = acc;
         }
       }

@@ -27,7 +27,8 @@ namespace smpc
   }
   // TPB = 128: throughput variant (three CTAs per SM). TPB = 256: latency variant for batches of at most one instance
   // per SM - twice the threads on the products and trailing updates of one instance, the whole register file to itself.
-  template <int NDX, int NU, int NC, int TPB>
+  // SNV > 0: the stage dynamics have the kinodynamics structure (riccati3.cuh KinoRows) with NV = SNV
+  template <int NDX, int NU, int NC, int TPB, int SNV>
   __global__ void __launch_bounds__(TPB, (ric3_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati3(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
@@ -38,7 +39,7 @@ namespace smpc
       return;
     const size_t xb = (size_t)b * (d.N + 1);
     __shared__ int flag;
-    riccati3_backward_inst<NDX, NU, NC, TPB>(
+    riccati3_backward_inst<NDX, NU, NC, TPB, SNV>(
       A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
@@ -72,22 +73,22 @@ namespace smpc
     return best;
   }
 
-  template <int NDX, int NU, int NC, int TPB>
+  template <int NDX, int NU, int NC, int TPB, int SNV>
   void launch_riccati3_impl(smpc_ctx * c)
   {
-    k_riccati3<NDX, NU, NC, TPB><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
+    k_riccati3<NDX, NU, NC, TPB, SNV><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
   }
-  template <int NDX, int NU, int NC, int TPB>
+  template <int NDX, int NU, int NC, int TPB, int SNV>
   int finish_setup_riccati3(smpc_ctx * c)
   {
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB>;
-    c->riccati_variant = TPB == 128 ? "tma-staged" : "tma-staged-256";
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB, SNV>;
+    c->riccati_variant = SNV ? (TPB == 128 ? "tma-staged-kinostruct" : "tma-staged-kinostruct-256") : (TPB == 128 ? "tma-staged" : "tma-staged-256");
     if (getenv("SMPC_VERBOSE"))
     {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC, TPB>, TPB, c->ric_smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC, TPB, SNV>, TPB, c->ric_smem);
       fprintf(stderr, "smpc: k_riccati3 (%d threads) %zu B shared memory per instance, resident CTAs per SM: %d\n", TPB, c->ric_smem, nb);
     }
     return SMPC_OK;
@@ -126,6 +127,13 @@ namespace smpc
     bool wide = c->hmodel_sms > 0 && c->A.dm.B <= c->hmodel_sms;
     if (const char * e = getenv("SMPC_RIC3_TPB"))
       wide = atoi(e) == 256;
-    return wide ? finish_setup_riccati3<NDX, NU, NC, 256>(c) : finish_setup_riccati3<NDX, NU, NC, 128>(c);
+    // kinodynamics problems (kino_knot.cuh writes A, B with the KinoRows structure) take the structure-exploiting products;
+    // SMPC_RIC_STRUCT=0 forces the dense ones (A/B timing)
+    bool kino = c->hocp.kind == SMPC_OCP_KINODYNAMICS && 2 * c->hmodel.d.nv == NDX;
+    if (const char * e = getenv("SMPC_RIC_STRUCT"))
+      kino = kino && atoi(e) != 0;
+    if (kino)
+      return wide ? finish_setup_riccati3<NDX, NU, NC, 256, NDX / 2>(c) : finish_setup_riccati3<NDX, NU, NC, 128, NDX / 2>(c);
+    return wide ? finish_setup_riccati3<NDX, NU, NC, 256, 0>(c) : finish_setup_riccati3<NDX, NU, NC, 128, 0>(c);
   }
 } // namespace smpc

@@ -845,6 +845,8 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreate(&c->evr0));
   CU(cudaEventCreate(&c->evr1));
+  for (cudaEvent_t & e : c->evk)
+    CU(cudaEventCreate(&e));
   CU(cudaEventCreate(&c->evu0));
   CU(cudaEventCreate(&c->evu1));
   return SMPC_OK;
@@ -865,7 +867,7 @@ void smpc_destroy(smpc_ctx * c)
     cudaFreeHost(c->h_staging);
   if (c->h_counters)
     cudaFreeHost(c->h_counters);
-  for (cudaEvent_t e : {c->ev0, c->ev1, c->evr0, c->evr1, c->evu0, c->evu1})
+  for (cudaEvent_t e : {c->ev0, c->ev1, c->evr0, c->evr1, c->evu0, c->evu1, c->evk[0], c->evk[1], c->evk[2], c->evk[3], c->evk[4], c->evk[5]})
     if (e)
       cudaEventDestroy(e);
   if (c->stream)
@@ -1084,7 +1086,13 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
   bool timed_ric = false;
   for (int round = 0; round < max_rounds; round++)
   {
+    // the first round of a solve is timed kernel by kernel (CUDA events on this stream; smpc_kernel_times)
+    const bool tk = !timed_ric;
+    if (tk)
+      CU(cudaEventRecord(c->evk[0], s));
     c->launch_knots(c, false);
+    if (tk)
+      CU(cudaEventRecord(c->evk[1], s));
     k_decide<<<d.B, 64, 0, s>>>(c->A);
     if (!timed_ric)
       CU(cudaEventRecord(c->evr0, s));
@@ -1092,19 +1100,27 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
     if (!timed_ric)
       CU(cudaEventRecord(c->evr1, s));
     timed_ric = true;
+    if (tk)
+      CU(cudaEventRecord(c->evk[2], s));
     if (c->forward_staged)
       k_forward<<<d.B, 128, (size_t)c->A.FS.size * sizeof(double), s>>>(c->A);
     else
       k_forward_direct<<<d.B, 64, 0, s>>>(c->A);
+    if (tk)
+      CU(cudaEventRecord(c->evk[3], s));
     c->launches += 3;
     for (int trial = 0; trial <= c->A.opt.ls_max_steps + 1; trial++)
     {
+      if (tk && trial == 0)
+        CU(cudaEventRecord(c->evk[4], s));
       // counters: [0] instances whose linesearch needs another trial, [1] instances that need another round
       // (both recounted by every k_ls_decide launch; the host reads the last one)
       CU(cudaMemsetAsync(c->A.counters, 0, 2 * sizeof(int), s));
       c->launch_knots(c, true);
       k_ls_decide<<<d.B, 128, 0, s>>>(c->A);
       c->launches++;
+      if (tk && trial == 0)
+        CU(cudaEventRecord(c->evk[5], s));
       CU(cudaMemcpyAsync(c->h_counters, c->A.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
       if (c->h_counters[0] == 0)
@@ -1121,6 +1137,16 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   CU(cudaEventElapsedTime(&c->last_ric_ms, c->evr0, c->evr1));
   c->acc_ric_ms += c->last_ric_ms;
+  {
+    float ms;
+    CU(cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]));
+    c->acc_kernel_ms[0] += ms;
+    c->acc_kernel_ms[1] += c->last_ric_ms;
+    CU(cudaEventElapsedTime(&ms, c->evk[2], c->evk[3]));
+    c->acc_kernel_ms[2] += ms;
+    CU(cudaEventElapsedTime(&ms, c->evk[4], c->evk[5]));
+    c->acc_kernel_ms[3] += ms;
+  }
   c->acc_solve_ms += c->last_ms;
   c->acc_ric_launches += 1;
   c->acc_solves += 1;
@@ -1619,7 +1645,19 @@ int smpc_timer_stats(smpc_ctx * c, int reset, double * riccati_ms, int64_t * ric
   {
     c->acc_ric_ms = c->acc_solve_ms = 0;
     c->acc_ric_launches = c->acc_solves = 0;
+    for (double & v : c->acc_kernel_ms)
+      v = 0;
   }
+  return SMPC_OK;
+}
+// accumulated device time per kernel of the FIRST round of every solve since the last smpc_timer_stats(reset):
+// [0] linearisation (k_knots), [1] Riccati backward sweep, [2] forward sweep, [3] first trial evaluation + linesearch decision
+int smpc_kernel_times(smpc_ctx * c, double * ms4)
+{
+  if (!c || !ms4)
+    return SMPC_ERR_INVALID;
+  for (int k = 0; k < 4; k++)
+    ms4[k] = c->acc_kernel_ms[k];
   return SMPC_OK;
 }
 int smpc_sync(smpc_ctx * c)

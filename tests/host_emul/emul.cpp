@@ -94,6 +94,39 @@ static void ric4_any(const KnotLayout & L, const SolLayout & SL, int N, const do
   riccati4_backward_inst<NDX, NU, NC, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0);
 }
 
+// the TMA-staged sweep of riccati3.cuh (the one the library launches); SNV = 18: the kinodynamics-structure products
+template <int SNV>
+static int emul_riccati3_impl(
+  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
+  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
+  double * dphi, int * flag)
+{
+  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
+  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
+  std::vector<double> P0((size_t)ndx * (ndx + 1), 0.0), sm2(4 * ndx + nu + 80, 0.0);
+  if (ndx == 36 && nu == 24 && ncmax == 24)
+  {
+    std::vector<double> sm(Ric3<36, 24, 24>::SIZE + 8, 0.0);
+    riccati3_backward_inst<36, 24, 24, SMPC_EMUL_NT, SNV>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+  }
+  else if (ndx == 36 && nu == 24 && ncmax == 36)
+  {
+    std::vector<double> sm(Ric3<36, 24, 36>::SIZE + 8, 0.0);
+    riccati3_backward_inst<36, 24, 36, SMPC_EMUL_NT, SNV>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+  }
+  else
+  {
+    g_err = "emul_riccati3: size not instantiated";
+    return -1;
+  }
+  // the hot path's forward sweep: stage matrices staged through (emulated) shared memory
+  FwdSmem FS = make_fwd_smem(ndx, nu, ncmax);
+  std::vector<double> smf((size_t)FS.size + 8, 0.0);
+  riccati_forward_staged(L, SL, FS, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, smf.data());
+  return 0;
+}
+
+
 extern "C" {
 const char * emul_last_error() { return g_err.c_str(); }
 
@@ -238,36 +271,12 @@ void emul_sol_layout(int ndx, int nu, int ncmax, int * out /*7*/)
   memcpy(out, v, sizeof(v));
 }
 
-// same, through the TMA-staged sweep of riccati3.cuh (the one the library launches)
-int emul_riccati3(
-  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
-  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
-  double * dphi, int * flag)
-{
-  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
-  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
-  std::vector<double> P0((size_t)ndx * (ndx + 1), 0.0), sm2(4 * ndx + nu + 80, 0.0);
-  if (ndx == 36 && nu == 24 && ncmax == 24)
-  {
-    std::vector<double> sm(Ric3<36, 24, 24>::SIZE + 8, 0.0);
-    riccati3_backward_inst<36, 24, 24, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
-  }
-  else if (ndx == 36 && nu == 24 && ncmax == 36)
-  {
-    std::vector<double> sm(Ric3<36, 24, 36>::SIZE + 8, 0.0);
-    riccati3_backward_inst<36, 24, 36, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
-  }
-  else
-  {
-    g_err = "emul_riccati3: size not instantiated";
-    return -1;
-  }
-  // the hot path's forward sweep: stage matrices staged through (emulated) shared memory
-  FwdSmem FS = make_fwd_smem(ndx, nu, ncmax);
-  std::vector<double> smf((size_t)FS.size + 8, 0.0);
-  riccati_forward_staged(L, SL, FS, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, smf.data());
-  return 0;
-}
+// same, through the TMA-staged sweep of riccati3.cuh, dense products / kinodynamics-structure products (the one the library launches)
+#define EMUL_RIC_ARGS                                                                                                  \
+  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,   \
+    const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew, double * dphi, int * flag
+int emul_riccati3(EMUL_RIC_ARGS) { return emul_riccati3_impl<0>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
+int emul_riccati3_kino(EMUL_RIC_ARGS) { return emul_riccati3_impl<18>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
 
 // same, through the generic-shape two-column sweep of riccati4.cuh
 int emul_riccati4(

@@ -35,7 +35,7 @@ def main():
                      int(r[iwfi] or 0) if iwfi is not None else 0))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    cub = max([os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")], key=os.path.getsize)
     dis = subprocess.run(["nvdisasm", "-g", "-c", cub], stdout=subprocess.PIPE, text=True).stdout.splitlines()
     # mangled name fragment from the demangled kernel name
     base = re.search(r"(k_\w+)", kname).group(1)
