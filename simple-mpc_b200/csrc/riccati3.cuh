@@ -264,7 +264,12 @@ namespace smpc
     }
   };
 
-  template <int NDX, int NU, int NC, int TPB, int SNV = 0>
+  // DZ: no constraint row of any stage depends on the control (D = 0: joint limits, contact-velocity and landing-height rows;
+  // the kinodynamics problem without force cones, i.e. the reference's Go2 example). Then W = R^-1 D^T = 0, Sigma = mu I and
+  // G = Sigma^-1 [d | C]: the W columns of the forward sweep, the Sigma build and factorisation, the sweeps of G and Y += W G
+  // drop out. What is left performs exactly the operations the general path would (its other terms are products with exact
+  // zeros), so the result is bitwise the same.
+  template <int NDX, int NU, int NC, int TPB, int SNV = 0, bool DZ = false>
   SMPC_DEV void riccati3_backward_inst(
     const KnotLayout & L, const SolLayout & SL, int N, const double * __restrict__ knots, double * __restrict__ sol,
     double mudyn, double mueq, double * sm, int * flag_out, double * P0out)
@@ -621,11 +626,12 @@ namespace smpc
       SMPC_END
       chol2<NU, NU, TPB>(Rh, colb, invr, bad);
       RIC_T(5)
+      constexpr int NYW = DZ ? LDP : NRY; // columns of [Y | W] that exist
       SMPC_PAR(tid)
       bulk_wait(bar, parity);
-      for (int e = tid; e < NU * NRY; e += SMPC_NT)
+      for (int e = tid; e < NU * NYW; e += SMPC_NT)
       {
-        const int a = e / NRY, c = e % NRY;
+        const int a = e / NYW, c = e % NYW;
         double v;
         if (c == 0)
           v = rh[a];
@@ -633,13 +639,29 @@ namespace smpc
           v = Sh[(c - 1) * NU + a];
         else
           v = Dk[(c - NDX - 1) * NU + a];
-        YW[e] = v;
+        YW[a * NRY + c] = v;
       }
       SMPC_END
       parity ^= 1u;
-      sweep_cols<NU, NU, NRY, NRY, true, false>(Rh, invr, YW);
+      sweep_cols<NU, NU, NYW, NRY, true, false>(Rh, invr, YW);
       RIC_T(6)
-      if (NC > 0)
+      if (NC > 0 && DZ)
+      {
+        // G = Sigma^-1 [d | C] with Sigma = mu I: the two sweeps of the general path reduce to two scalings by 1 / sqrt(mu)
+        SMPC_PAR(tid)
+        {
+          const double inv = pivot_rsqrt(mueq);
+          for (int e = tid; e < NC * LDP; e += SMPC_NT)
+          {
+            const int i = e / LDP, c = e % LDP;
+            const double g = (c == 0) ? dk[i] : Ck[i * NDX + (c - 1)];
+            G[e] = (g * inv) * inv;
+          }
+        }
+        SMPC_END
+        RIC_T(9)
+      }
+      if (NC > 0 && !DZ)
       {
         // Sigma = mu I + W^T W (lower) and G = [d | C] - W^T Y : register tiles (4x3 on G, 4x4 blocks of the
         // lower triangle of Sigma), one job list strided over the CTA

@@ -28,7 +28,7 @@ namespace smpc
   // TPB = 128: throughput variant (three CTAs per SM). TPB = 256: latency variant for batches of at most one instance
   // per SM - twice the threads on the products and trailing updates of one instance, the whole register file to itself.
   // SNV > 0: the stage dynamics have the kinodynamics structure (riccati3.cuh KinoRows) with NV = SNV
-  template <int NDX, int NU, int NC, int TPB, int SNV>
+  template <int NDX, int NU, int NC, int TPB, int SNV, bool DZ>
   __global__ void __launch_bounds__(TPB, (ric3_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati3(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
@@ -39,7 +39,7 @@ namespace smpc
       return;
     const size_t xb = (size_t)b * (d.N + 1);
     __shared__ int flag;
-    riccati3_backward_inst<NDX, NU, NC, TPB, SNV>(
+    riccati3_backward_inst<NDX, NU, NC, TPB, SNV, DZ>(
       A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
@@ -73,22 +73,24 @@ namespace smpc
     return best;
   }
 
-  template <int NDX, int NU, int NC, int TPB, int SNV>
+  template <int NDX, int NU, int NC, int TPB, int SNV, bool DZ>
   void launch_riccati3_impl(smpc_ctx * c)
   {
-    k_riccati3<NDX, NU, NC, TPB, SNV><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
+    k_riccati3<NDX, NU, NC, TPB, SNV, DZ><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
   }
-  template <int NDX, int NU, int NC, int TPB, int SNV>
+  template <int NDX, int NU, int NC, int TPB, int SNV, bool DZ>
   int finish_setup_riccati3(smpc_ctx * c)
   {
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
-    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB, SNV>;
-    c->riccati_variant = SNV ? (TPB == 128 ? "tma-staged-kinostruct" : "tma-staged-kinostruct-256") : (TPB == 128 ? "tma-staged" : "tma-staged-256");
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV, DZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV, DZ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB, SNV, DZ>;
+    c->riccati_variant = SNV ? (DZ ? (TPB == 128 ? "tma-staged-kinostruct-D0" : "tma-staged-kinostruct-D0-256")
+                                   : (TPB == 128 ? "tma-staged-kinostruct" : "tma-staged-kinostruct-256"))
+                             : (TPB == 128 ? "tma-staged" : "tma-staged-256");
     if (getenv("SMPC_VERBOSE"))
     {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC, TPB, SNV>, TPB, c->ric_smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati3<NDX, NU, NC, TPB, SNV, DZ>, TPB, c->ric_smem);
       fprintf(stderr, "smpc: k_riccati3 (%d threads) %zu B shared memory per instance, resident CTAs per SM: %d\n", TPB, c->ric_smem, nb);
     }
     return SMPC_OK;
@@ -132,8 +134,12 @@ namespace smpc
     bool kino = c->hocp.kind == SMPC_OCP_KINODYNAMICS && 2 * c->hmodel.d.nv == NDX;
     if (const char * e = getenv("SMPC_RIC_STRUCT"))
       kino = kino && atoi(e) != 0;
+    // ... and without force cones no constraint row depends on the control (DZ, riccati3.cuh)
+    const bool dz = kino && !c->hocp.force_cone;
+    if (kino && dz)
+      return wide ? finish_setup_riccati3<NDX, NU, NC, 256, NDX / 2, true>(c) : finish_setup_riccati3<NDX, NU, NC, 128, NDX / 2, true>(c);
     if (kino)
-      return wide ? finish_setup_riccati3<NDX, NU, NC, 256, NDX / 2>(c) : finish_setup_riccati3<NDX, NU, NC, 128, NDX / 2>(c);
-    return wide ? finish_setup_riccati3<NDX, NU, NC, 256, 0>(c) : finish_setup_riccati3<NDX, NU, NC, 128, 0>(c);
+      return wide ? finish_setup_riccati3<NDX, NU, NC, 256, NDX / 2, false>(c) : finish_setup_riccati3<NDX, NU, NC, 128, NDX / 2, false>(c);
+    return wide ? finish_setup_riccati3<NDX, NU, NC, 256, 0, false>(c) : finish_setup_riccati3<NDX, NU, NC, 128, 0, false>(c);
   }
 } // namespace smpc

@@ -95,7 +95,7 @@ static void ric4_any(const KnotLayout & L, const SolLayout & SL, int N, const do
 }
 
 // the TMA-staged sweep of riccati3.cuh (the one the library launches); SNV = 18: the kinodynamics-structure products
-template <int SNV>
+template <int SNV, bool DZ = false>
 static int emul_riccati3_impl(
   int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
   const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
@@ -107,12 +107,12 @@ static int emul_riccati3_impl(
   if (ndx == 36 && nu == 24 && ncmax == 24)
   {
     std::vector<double> sm(Ric3<36, 24, 24>::SIZE + 8, 0.0);
-    riccati3_backward_inst<36, 24, 24, SMPC_EMUL_NT, SNV>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+    riccati3_backward_inst<36, 24, 24, SMPC_EMUL_NT, SNV, DZ>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
   }
   else if (ndx == 36 && nu == 24 && ncmax == 36)
   {
     std::vector<double> sm(Ric3<36, 24, 36>::SIZE + 8, 0.0);
-    riccati3_backward_inst<36, 24, 36, SMPC_EMUL_NT, SNV>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
+    riccati3_backward_inst<36, 24, 36, SMPC_EMUL_NT, SNV, DZ>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0.data());
   }
   else
   {
@@ -276,6 +276,7 @@ void emul_sol_layout(int ndx, int nu, int ncmax, int * out /*7*/)
   int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,   \
     const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew, double * dphi, int * flag
 int emul_riccati3(EMUL_RIC_ARGS) { return emul_riccati3_impl<0>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
+int emul_riccati3_kino_d0(EMUL_RIC_ARGS) { return emul_riccati3_impl<18, true>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
 int emul_riccati3_kino(EMUL_RIC_ARGS) { return emul_riccati3_impl<18>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
 
 // same, through the generic-shape two-column sweep of riccati4.cuh

@@ -161,6 +161,9 @@ def run_case(cone, robot="go2"):
     if robot == "go2":
         # the products that skip the structural zeros of the kinodynamics A, B (riccati3.cuh KinoRows): same operations in the same order
         out['kino_structure_on_oracle'] = sweep(emu.emul_riccati3_kino, orc_knots)
+        if not cone:
+            # no row depends on the control (D = 0): Sigma = mu I, the W / Sigma phases drop out (riccati3.cuh DZ)
+            out['kino_structure_d0_on_oracle'] = sweep(emu.emul_riccati3_kino_d0, orc_knots)
     out['special_on_emul'] = sweep(tuned, emu_knots)
     # conditioning of the penalised recursion, measured: the oracle's own knots with every entry moved by at most ONE ULP
     # (relative 2^-52, the size of the difference between two correct evaluations of the same Jacobians)
@@ -195,7 +198,7 @@ def test_infeasibility_scalars_match(case):
 
 
 def test_riccati_bitwise(case):
-    for name in ['generic_on_oracle', 'tma_on_oracle', 'two_column_on_oracle', 'kino_structure_on_oracle']:
+    for name in ['generic_on_oracle', 'tma_on_oracle', 'two_column_on_oracle', 'kino_structure_on_oracle', 'kino_structure_d0_on_oracle']:
         if name not in case:
             continue
         K, dxs, dus = case[name]
