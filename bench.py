@@ -64,10 +64,24 @@ def algorithmic_bytes_per_stage(nx, nu, nc):
     return 8 * (2 * nx * nx + 2 * nx * nu + nu * nu + nx + nu + nc * (nx + nu + 1) + nx + (k + 2 * nx) * (nx + 1) + nx * nx + nx)
 
 
-def algorithmic_flops_per_stage(nx, nu, nc):
-    k = nu + nc
-    return (7.0 / 3 * nx ** 3 + 4 * nx ** 3 + 4 * nx * nx * nu + 2 * nx * nu * nu + k ** 3 / 3.0 + 2 * k * k * (nx + 1)
-            + 2 * nx * k * (nx + 1))
+def algorithmic_flops_per_stage(nx, nu, nc, variant=""):
+    """FP64 operations of one proximal Riccati stage as the kernel performs them (a fused multiply-add = 2), phase by
+    phase of riccati3.cuh. variant: the name smpc_riccati_variant() returns - "kinostruct" products skip the structural
+    zeros of the kinodynamics [A B] (12 dense rows of 2 nv + 60 isolated entries), "D0" drops the W / Sigma phases."""
+    nab, ld = nx + nu, nx + 1
+    struct, d0 = "kinostruct" in variant, "D0" in variant
+    dense_rows = 12 if struct else nx
+    extra = 60 if struct else 0                      # non-zeros of the sparse rows
+    f = nx ** 3 / 3.0 + 2 * nx * nx * ld            # chol(I + mu P), two sweeps of [p | P]
+    f += 2 * nx * (dense_rows * nab + extra) + 2 * nx * nx                        # P~ [A B], w
+    f += 2 * (dense_rows * (nx * nab + nu * nu) + extra * nab) + 2 * dense_rows * nab   # [Q S R] += [A B]^T PAB, q, r
+    f += nu ** 3 / 3.0 + nu * nu * (ld + (0 if d0 else nc))                        # chol(R^), forward sweep of [Y | W]
+    if d0:
+        f += 2 * nc * ld                                                          # G = [d | C] / mu
+    else:
+        f += nu * nc * nc + 2 * nc * nu * ld + nc ** 3 / 3.0 + 2 * nc * nc * ld + 2 * nu * nc * ld   # Sigma, G, chol, sweeps, Y += W G
+    f += nu * nu * ld + 2 * nx * (nu + nc) * ld                                    # backward sweep of Y, P update
+    return f
 
 
 class ClockSampler(threading.Thread):
@@ -337,7 +351,9 @@ def main():
     # roofline of the dominant kernel: Riccati backward, one launch per tick
     nc_mean = sc.mean_active_rows()
     bytes_launch = B * sc.T * algorithmic_bytes_per_stage(sc.ndx, sc.nu, nc_mean)
-    flops_launch = B * sc.T * algorithmic_flops_per_stage(sc.ndx, sc.nu, nc_mean)
+    variant = cu.smpc_riccati_variant(b.ctx).decode()
+    flops_launch = B * sc.T * algorithmic_flops_per_stage(sc.ndx, sc.nu, nc_mean, variant)
+    flops_dense = B * sc.T * algorithmic_flops_per_stage(sc.ndx, sc.nu, nc_mean)
     ric_avg_s = (ric_ms.value / max(ric_n.value, 1)) * 1e-3
     peaks = {}
     try:
@@ -347,10 +363,10 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic, traffic_src = None, None
     if cfg in ("c1", "c5"):
-        # dram__bytes_read.sum + dram__bytes_write.sum of k_riccati3 from the ncu --set full capture at B = 1024
-        # (profiles/r01i_ncu_full_B1024.csv: 2.666 + 1.272 GB per launch), per instance, scaled to this launch
-        traffic = (2.665893e9 + 1.271974e9) / 1024 * B
-        traffic_src = "ncu --set full at B=1024, per instance x batch (profiles/r01i_ncu_full_B1024.csv)"
+        # dram__bytes_read.sum + dram__bytes_write.sum of k_riccati3<36,24,24,128,18,1> from the ncu --set full capture at B = 1024
+        # (profiles/r02l_ncu_summary.txt: 2.663 + 1.265 GB per launch), per instance, scaled to this launch
+        traffic = (2.663405e9 + 1.265249e9) / 1024 * B
+        traffic_src = "ncu --set full at B=1024, per instance x batch (profiles/r02l_ncu_summary.txt)"
     achieved = bytes_launch / ric_avg_s / 1e9 if ric_avg_s > 0 else 0.0
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -370,6 +386,9 @@ def main():
                      "algorithmic_bytes": bytes_launch, "launch_ms": 1e3 * ric_avg_s,
                      "share_of_step": ric_ms.value / max(sol_ms.value, 1e-12),
                      "fp64": {"achieved_tflops": flops_launch / ric_avg_s / 1e12 if ric_avg_s > 0 else 0.0,
+                              "what": "operations the launched variant performs (structural zeros skipped); dense_equivalent_tflops = the dense "
+                                      "stage of the reference algorithm / the same time",
+                              "dense_equivalent_tflops": flops_dense / ric_avg_s / 1e12 if ric_avg_s > 0 else 0.0,
                               "nominal_peak_tflops": 37.0,
                               "peak_source": "tools/microbench_fp64.cu: 37.0 TFLOP/s DFMA measured on this pool's B200 (profiles/r01g_microbench_fp64.txt)"}},
         # every kernel of the solve, CUDA events on the context's stream around the first round of each solve, ms per launch

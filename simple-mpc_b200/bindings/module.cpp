@@ -22,11 +22,116 @@ namespace
     std::copy(R.begin(), R.end(), a.mutable_data());
     return a;
   }
-  template <class Handler>
-  void exposeHandlerCommon(py::class_<Handler, OCPHandler, std::shared_ptr<Handler>> & c)
+
+  // Trampoline for Python-derived handlers (reference include/simple-mpc/python/py-ocp-handler.hpp:71-192: PyOCPHandler,
+  // bp::wrapper<OCPHandler> with SIMPLE_MPC_PYTHON_OVERRIDE[_PURE] on every virtual). Here one template serves the
+  // abstract OCPHandler (every method pure, as in the reference) and the three concrete handlers (a Python subclass
+  // overrides what it needs and inherits the rest), so MPC drives Python overrides through the same virtual calls.
+#define SMPC_PY_OVERRIDE(ret, name, ...)                                                                               \
+  {                                                                                                                    \
+    py::gil_scoped_acquire gil;                                                                                        \
+    py::function ovr = py::get_override(static_cast<const Base *>(this), #name);                                       \
+    if (ovr)                                                                                                           \
+      return ovr(__VA_ARGS__).template cast<ret>();                                                                    \
+  }                                                                                                                    \
+  if constexpr (std::is_abstract_v<Base>)                                                                              \
+    throw std::runtime_error("Tried to call pure virtual function \"OCPHandler::" #name "\"");                          \
+  else                                                                                                                 \
+    return Base::name(__VA_ARGS__);
+#define SMPC_PY_OVERRIDE_VOID(name, ...)                                                                               \
+  {                                                                                                                    \
+    py::gil_scoped_acquire gil;                                                                                        \
+    py::function ovr = py::get_override(static_cast<const Base *>(this), #name);                                       \
+    if (ovr)                                                                                                           \
+    {                                                                                                                  \
+      ovr(__VA_ARGS__);                                                                                                \
+      return;                                                                                                          \
+    }                                                                                                                  \
+  }                                                                                                                    \
+  if constexpr (std::is_abstract_v<Base>)                                                                              \
+    throw std::runtime_error("Tried to call pure virtual function \"OCPHandler::" #name "\"");                          \
+  else                                                                                                                 \
+    Base::name(__VA_ARGS__);
+
+  template <class Base>
+  struct PyHandler : Base
   {
-    (void)c;
-  }
+    using Base::Base;
+    typedef std::map<std::string, bool> BoolMap;
+    typedef std::map<std::string, SE3> PoseMap;
+    typedef std::map<std::string, VectorXd> ForceMap;
+    StageModel createStage(const BoolMap & contact_phase, const PoseMap & contact_pose, const ForceMap & contact_force, const BoolMap & land_constraint) override
+    {
+      SMPC_PY_OVERRIDE(StageModel, createStage, contact_phase, contact_pose, contact_force, land_constraint)
+    }
+    CostStack createTerminalCost() override { SMPC_PY_OVERRIDE(CostStack, createTerminalCost, ) }
+    void createTerminalConstraint(const Vector3d & com_ref) override { SMPC_PY_OVERRIDE_VOID(createTerminalConstraint, com_ref) }
+    void updateTerminalConstraint(const Vector3d & com_ref) override { SMPC_PY_OVERRIDE_VOID(updateTerminalConstraint, com_ref) }
+    void setReferencePose(const std::size_t t, const std::string & ee_name, const SE3 & pose_ref) override
+    {
+      SMPC_PY_OVERRIDE_VOID(setReferencePose, t, ee_name, pose_ref)
+    }
+    void setReferencePoses(const std::size_t t, const PoseMap & pose_refs) override { SMPC_PY_OVERRIDE_VOID(setReferencePoses, t, pose_refs) }
+    void setTerminalReferencePose(const std::string & ee_name, const SE3 & pose_ref) override
+    {
+      SMPC_PY_OVERRIDE_VOID(setTerminalReferencePose, ee_name, pose_ref)
+    }
+    const SE3 getReferencePose(const std::size_t t, const std::string & ee_name) override { SMPC_PY_OVERRIDE(SE3, getReferencePose, t, ee_name) }
+    void setReferenceForces(const std::size_t t, const ForceMap & force_refs) override { SMPC_PY_OVERRIDE_VOID(setReferenceForces, t, force_refs) }
+    void setReferenceForce(const std::size_t t, const std::string & ee_name, const ConstVectorRef & force_ref) override
+    {
+      SMPC_PY_OVERRIDE_VOID(setReferenceForce, t, ee_name, force_ref)
+    }
+    const VectorXd getReferenceForce(const std::size_t t, const std::string & ee_name) override { SMPC_PY_OVERRIDE(VectorXd, getReferenceForce, t, ee_name) }
+    void setVelocityBase(const std::size_t t, const ConstVectorRef & velocity_base) override { SMPC_PY_OVERRIDE_VOID(setVelocityBase, t, velocity_base) }
+    const VectorXd getVelocityBase(const std::size_t t) override { SMPC_PY_OVERRIDE(VectorXd, getVelocityBase, t) }
+    void setPoseBase(const std::size_t t, const ConstVectorRef & pose_base) override { SMPC_PY_OVERRIDE_VOID(setPoseBase, t, pose_base) }
+    const VectorXd getPoseBase(const std::size_t t) override { SMPC_PY_OVERRIDE(VectorXd, getPoseBase, t) }
+    const VectorXd getProblemState(const RobotDataHandler & data_handler) override
+    {
+      {
+        py::gil_scoped_acquire gil;
+        py::function ovr = py::get_override(static_cast<const Base *>(this), "getProblemState");
+        if (ovr)
+          return ovr(py::cast(&data_handler, py::return_value_policy::reference)).template cast<VectorXd>();
+      }
+      if constexpr (std::is_abstract_v<Base>)
+        throw std::runtime_error("Tried to call pure virtual function \"OCPHandler::getProblemState\"");
+      else
+        return Base::getProblemState(data_handler);
+    }
+    size_t getContactSupport(const std::size_t t) override
+    {
+      {
+        py::gil_scoped_acquire gil;
+        py::function ovr = py::get_override(static_cast<const Base *>(this), "getContactSupport");
+        if (ovr)
+          return ovr(t).template cast<size_t>();
+      }
+      return Base::getContactSupport(t);
+    }
+    std::vector<bool> getContactState(const std::size_t t) override
+    {
+      {
+        py::gil_scoped_acquire gil;
+        py::function ovr = py::get_override(static_cast<const Base *>(this), "getContactState");
+        if (ovr)
+          return ovr(t).template cast<std::vector<bool>>();
+      }
+      return Base::getContactState(t);
+    }
+    void setReferenceState(const std::size_t t, const ConstVectorRef & x_ref) override { SMPC_PY_OVERRIDE_VOID(setReferenceState, t, x_ref) }
+    const VectorXd getReferenceState(const std::size_t t) override { SMPC_PY_OVERRIDE(VectorXd, getReferenceState, t) }
+    // the lowering to the CUDA library's problem recipe stays C++: a handler derived in Python from OCPHandler itself has no
+    // kernels behind it (the reference's Python handlers build aligator stage models; here a stage is an smpc_slot record)
+    smpc_ocp_desc toOcpDesc() const override
+    {
+      if constexpr (std::is_abstract_v<Base>)
+        throw std::runtime_error("OCPHandler derived in Python: derive from KinodynamicsOCP, FullDynamicsOCP or CentroidalOCP to run on the CUDA path");
+      else
+        return Base::toOcpDesc();
+    }
+  };
 } // namespace
 
 PYBIND11_MODULE(simple_mpc, m)
@@ -162,7 +267,8 @@ PYBIND11_MODULE(simple_mpc, m)
     .def_readonly("term_cstrs", &TrajOptProblem::term_cstrs_)
     .def_property("x0", &TrajOptProblem::getInitState, &TrajOptProblem::setInitState);
 
-  py::class_<OCPHandler, std::shared_ptr<OCPHandler>>(m, "OCPHandler")
+  py::class_<OCPHandler, PyHandler<OCPHandler>, std::shared_ptr<OCPHandler>>(m, "OCPHandler")
+    .def(py::init<const RobotModelHandler &>(), py::arg("model_handler"))
     .def("createProblem", &OCPHandler::createProblem, py::arg("x0"), py::arg("horizon"), py::arg("force_size"), py::arg("gravity"), py::arg("terminal_constraint"))
     .def("createTerminalCost", &OCPHandler::createTerminalCost)
     .def("createTerminalConstraint", [](OCPHandler & o, const VectorXd & c) { o.createTerminalConstraint(toVec3(py::cast(c))); })
@@ -196,16 +302,19 @@ PYBIND11_MODULE(simple_mpc, m)
          const std::map<std::string, VectorXd> & force, const std::map<std::string, bool> & land) { return o.createStage(phase, pose, force, land); },
       py::arg("contact_map"), py::arg("contact_pose"), py::arg("force_refs"), py::arg("land_constraint"));
 
-  py::class_<KinodynamicsOCP, OCPHandler, std::shared_ptr<KinodynamicsOCP>>(m, "KinodynamicsOCP")
-    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<KinodynamicsOCP>(kinoSettingsFromDict(s), h); }),
+  py::class_<KinodynamicsOCP, OCPHandler, PyHandler<KinodynamicsOCP>, std::shared_ptr<KinodynamicsOCP>>(m, "KinodynamicsOCP")
+    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<KinodynamicsOCP>(kinoSettingsFromDict(s), h); },
+                  [](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<PyHandler<KinodynamicsOCP>>(kinoSettingsFromDict(s), h); }),
          py::arg("settings"), py::arg("model_handler"))
     .def("getSettings", [](KinodynamicsOCP & o) { return kinoSettingsToDict(o.getSettings()); });
-  py::class_<FullDynamicsOCP, OCPHandler, std::shared_ptr<FullDynamicsOCP>>(m, "FullDynamicsOCP")
-    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<FullDynamicsOCP>(fullSettingsFromDict(s), h); }),
+  py::class_<FullDynamicsOCP, OCPHandler, PyHandler<FullDynamicsOCP>, std::shared_ptr<FullDynamicsOCP>>(m, "FullDynamicsOCP")
+    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<FullDynamicsOCP>(fullSettingsFromDict(s), h); },
+                  [](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<PyHandler<FullDynamicsOCP>>(fullSettingsFromDict(s), h); }),
          py::arg("settings"), py::arg("model_handler"))
     .def("getSettings", [](FullDynamicsOCP & o) { return fullSettingsToDict(o.getSettings()); });
-  py::class_<CentroidalOCP, OCPHandler, std::shared_ptr<CentroidalOCP>>(m, "CentroidalOCP")
-    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<CentroidalOCP>(centroidalSettingsFromDict(s), h); }),
+  py::class_<CentroidalOCP, OCPHandler, PyHandler<CentroidalOCP>, std::shared_ptr<CentroidalOCP>>(m, "CentroidalOCP")
+    .def(py::init([](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<CentroidalOCP>(centroidalSettingsFromDict(s), h); },
+                  [](const py::dict & s, const RobotModelHandler & h) { return std::make_shared<PyHandler<CentroidalOCP>>(centroidalSettingsFromDict(s), h); }),
          py::arg("settings"), py::arg("model_handler"))
     .def("getSettings", [](CentroidalOCP & o) { return centroidalSettingsToDict(o.getSettings()); });
 

@@ -170,6 +170,51 @@ def test_go2_kinodynamics_mpc_walks_on_the_oracle():
         mpc.getContactForces(0)  # only defined for the full-dynamics handler
 
 
+def test_python_derived_handlers_are_driven_through_the_trampoline():
+    """reference include/simple-mpc/python/py-ocp-handler.hpp:71-192 (PyOCPHandler): handlers derived in Python. The C++ driver
+    (createProblem, MPC::generateCycleHorizon, MPC::iterate -> updateStepTrackerReferences) must reach the Python overrides
+    through the virtual calls, and super() must reach the C++ implementation without recursion."""
+    hooks = hu.import_hooks()
+    mh = hu.go2_handler(sm)
+    calls = dict(createStage=0, setReferencePose=0, setReferenceState=0)
+
+    class MyKino(sm.KinodynamicsOCP):
+        def createStage(self, contact_map, contact_pose, force_refs, land_constraint):
+            calls["createStage"] += 1
+            return super().createStage(contact_map, contact_pose, force_refs, land_constraint)
+
+        def setReferencePose(self, t, ee_name, pose_ref):
+            calls["setReferencePose"] += 1
+            super().setReferencePose(t, ee_name, pose_ref)
+
+        def setReferenceState(self, t, x_ref):
+            calls["setReferenceState"] += 1
+            super().setReferenceState(t, x_ref)
+
+    _, conf = hu.go2_kino_problem(sm, mh, T=50)
+    ocp = MyKino(conf, mh)
+    ocp.createProblem(mh.getReferenceState(), 50, 3, -9.81, False)
+    assert calls["createStage"] == 50  # one standing stage per knot (reference src/ocp-handler.cpp:96-137)
+    mpc = hooks.make_oracle_mpc(hu.go2_mpc_conf(mh), ocp, hu.LIBORC)
+    mpc.generateCycleHorizon(hu.go2_trot())
+    assert calls["createStage"] >= 50 + 80  # the cycle horizon is built through the same virtual
+    mpc.switchToWalk(np.array([0.2, 0, 0, 0, 0, 0]))
+    n0 = calls["setReferencePose"]
+    mpc.iterate(mh.getReferenceState())
+    assert calls["setReferencePose"] > n0 and calls["setReferenceState"] > 0  # updateStepTrackerReferences, reference src/mpc.cpp:278-324
+    assert len(mpc.xs) == 51 and np.isfinite(np.array(mpc.us)).all()
+
+    # a handler derived from the abstract OCPHandler: implemented methods are used, missing ones are "pure virtual" errors
+    class Bare(sm.OCPHandler):
+        def getReferenceState(self, t):
+            return np.arange(3.0) + t
+
+    bare = Bare(mh)
+    assert np.allclose(bare.getReferenceState(2), [2, 3, 4])
+    with pytest.raises(RuntimeError, match="pure virtual"):
+        bare.createTerminalCost()
+
+
 def test_fulldynamics_handler_lowers_but_has_no_cpu_path():
     """no CPU fallback: on a box without a CUDA device the product `MPC` (always bound to libsmpc_cuda) refuses to
     construct - smpc_create fails with SMPC_ERR_CUDA -> RuntimeError - instead of solving on the CPU. (The driver
