@@ -416,7 +416,14 @@ def main():
             lat.append(time.perf_counter() - t1)
             x1 = np.ascontiguousarray(sc1.next_measurement(x1, h, None))
         lat = np.array(lat[20:]) * 1e3
-        out["latency_ms"] = {"batch": 1, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99))}
+        k1, n1 = (C.c_double * 4)(), C.c_int64()
+        cu.smpc_kernel_times(b1.ctx, k1)
+        cu.smpc_timer_stats(b1.ctx, 0, None, None, None, C.byref(n1))
+        out["latency_ms"] = {"batch": 1, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                             "what": "smpc_mpc_iterate + head read-back through host buffers, one host synchronisation per tick",
+                             "device_ms": {"linearisation": k1[0] / max(n1.value, 1), "riccati": k1[1] / max(n1.value, 1),
+                                           "forward": k1[2] / max(n1.value, 1), "trial+decision": k1[3] / max(n1.value, 1)},
+                             "riccati_variant": cu.smpc_riccati_variant(b1.ctx).decode()}
         b1.close()
     if solo and not args.no_latency and cfg == "c5":
         # north_star target: 4096 instances at >= 100 Hz on 8 GPUs = 512 instances per GPU with a tick <= 10 ms.

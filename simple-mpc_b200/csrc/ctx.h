@@ -137,6 +137,7 @@ struct smpc_ctx
   cudaEvent_t evk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // first round of a solve: lin | decide+riccati | forward | first trial
   double acc_kernel_ms[4] = {0, 0, 0, 0};                                      // linearisation, Riccati backward, forward sweep, first trial (+ ls_decide)
   float last_ms = 0, last_ric_ms = 0;
+  int ric_generic_tpb = 128; // CTA width of the run-time-shape Riccati sweep (riccati.cuh)
   double acc_ric_ms = 0, acc_solve_ms = 0; // accumulated since smpc_timer_reset
   int64_t acc_ric_launches = 0, acc_solves = 0;
   cudaEvent_t evu0 = nullptr, evu1 = nullptr; // user timer on the context stream

@@ -564,7 +564,7 @@ namespace
 {
   void launch_riccati_generic(smpc_ctx * c)
   {
-    k_riccati<<<c->A.dm.B, 128, c->ric_smem, c->stream>>>(c->A);
+    k_riccati<<<c->A.dm.B, c->ric_generic_tpb, c->ric_smem, c->stream>>>(c->A);
   }
   template <class T>
   int dev_alloc(smpc_ctx * c, T ** p, size_t n)
@@ -780,6 +780,11 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
     c->ric_smem = (size_t)A.RS.size * sizeof(double);
     CU(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
     c->launch_riccati = &launch_riccati_generic;
+    // CTA width of the run-time-shape sweep: its phases are loops strided over the CTA, so any multiple of 32 works. A small
+    // stage (the centroidal problem: ndx 9, nu 12) cannot feed 128 threads and pays for their barriers; SMPC_RIC_GENERIC_TPB overrides
+    c->ric_generic_tpb = (O.ndx * (O.ndx + O.nu) <= 512) ? 32 : 128;
+    if (const char * e = getenv("SMPC_RIC_GENERIC_TPB"))
+      c->ric_generic_tpb = (atoi(e) == 32 || atoi(e) == 64) ? atoi(e) : 128;
   }
   const Dims & d = A.dm;
   const size_t B = d.B, N1 = d.N + 1;
@@ -1122,6 +1127,12 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
       if (tk && trial == 0)
         CU(cudaEventRecord(c->evk[5], s));
       CU(cudaMemcpyAsync(c->h_counters, c->A.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      // k_finish (scalars -> smpc_solve_info) rides behind every linesearch decision: when the step is accepted and no
+      // instance needs another round - the normal MPC tick - the one synchronisation below ends the solve; otherwise the
+      // next decision's k_finish overwrites what this one wrote
+      k_finish<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
+      c->launches++;
+      CU(cudaEventRecord(c->ev1, s));
       CU(cudaStreamSynchronize(s));
       if (c->h_counters[0] == 0)
         break;
@@ -1129,10 +1140,6 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
     if (c->h_counters[1] == 0)
       break;
   }
-  k_finish<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
-  c->launches++;
-  CU(cudaEventRecord(c->ev1, s));
-  CU(cudaStreamSynchronize(s));
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   CU(cudaEventElapsedTime(&c->last_ric_ms, c->evr0, c->evr1));
