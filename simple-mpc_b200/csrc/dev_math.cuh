@@ -161,6 +161,20 @@ namespace smpc
   {
     double A, B, C, D, E, F;
   };
+  // closed forms for rotations beyond 0.5 rad: rare on this path (steps dt v, state errors), and sqrt / sin / cos with their
+  // range-reduction slow paths are ~450 instructions per inlined copy - six copies were 13 % of the knot kernel's code, which
+  // already runs short of instruction cache (ncu: "no instruction" stalls 1.3 per issue) - so ONE out-of-line copy
+  static SMPC_DEV_NOINLINE void trig_coef_large(double t2, TrigCoef & k)
+  {
+    const double t = sqrt(t2);
+    const double s = sin(t), c = cos(t);
+    k.A = s / t;
+    k.B = (1 - c) / t2;
+    k.C = (t - s) / (t2 * t);
+    k.D = 1.0 / t2 - (1 + c) / (2 * t * s);
+    k.E = (t2 + 2 * c - 2) / (2 * t2 * t2);
+    k.F = (2 * t - 3 * s + t * c) / (2 * t2 * t2 * t);
+  }
   SMPC_DEV TrigCoef trig_coef(double t2)
   {
     TrigCoef k;
@@ -178,16 +192,7 @@ namespace smpc
             + t2 * (1.0 / 720 + t2 * (1.0 / 30240 + t2 * (1.0 / 1209600 + t2 * (1.0 / 47900160 + t2 * (691.0 / 1307674368000.0 + t2 * (1.0 / 74724249600.0 + t2 * (3617.0 / 10670622842880000.0)))))));
     }
     else
-    {
-      const double t = sqrt(t2);
-      const double s = sin(t), c = cos(t);
-      k.A = s / t;
-      k.B = (1 - c) / t2;
-      k.C = (t - s) / (t2 * t);
-      k.D = 1.0 / t2 - (1 + c) / (2 * t * s);
-      k.E = (t2 + 2 * c - 2) / (2 * t2 * t2);
-      k.F = (2 * t - 3 * s + t * c) / (2 * t2 * t2 * t);
-    }
+      trig_coef_large(t2, k);
     return k;
   }
   SMPC_DEV void eye3(double * R)

@@ -24,9 +24,13 @@ namespace simple_mpc
     const std::map<std::string, VectorXd> & contact_force, const std::map<std::string, bool> & land_constraint)
   {
     StageModel stm;
-    // the reference collects the contact states in std::map (alphabetical) order
-    for (auto const & x : contact_phase)
-      stm.contact_states.push_back(x.second);
+    // Contact states in HANDLER (feet registration) order, like the contact / landing masks the kernels use and like the
+    // other two handlers. The reference's kinodynamics handler collects them in std::map (alphabetical) order
+    // (src/kinodynamics.cpp:45-49) and then pairs them with frame ids in handler order; the two orders coincide whenever the
+    // feet are registered alphabetically (every example of the reference), otherwise the reference's pairing is a latent bug
+    // that is deliberately not reproduced.
+    for (auto const & name : model_handler_.getFeetFrameNames())
+      stm.contact_states.push_back(contact_phase.at(name));
     computeControlFromForces(contact_force);
 
     stm.cost_.components_ = {"state_cost", "control_cost", "centroidal_cost", "centroidal_derivative_cost"};

@@ -170,6 +170,26 @@ def test_go2_kinodynamics_mpc_walks_on_the_oracle():
         mpc.getContactForces(0)  # only defined for the full-dynamics handler
 
 
+def test_contact_state_order_follows_the_feet_registration_order():
+    """Feet registered in a non-alphabetical order: getContactState, the device contact mask and the constraint names must
+    all describe the same feet (handler order everywhere; the reference's kinodynamics handler mixes std::map order and handler
+    order, src/kinodynamics.cpp:45-49 - equal only for alphabetical registration)."""
+    model = sm.Model.BuildGo2Like()
+    mh = sm.RobotModelHandler(model, "standing", "base")
+    order = ["RR_foot", "FL_foot", "RL_foot", "FR_foot"]
+    for n in order:
+        mh.addPointFoot(n, "base")
+    ocp, _ = hu.go2_kino_problem(sm, mh, T=4)
+    dh = sm.RobotDataHandler(mh)
+    phase = {"RR_foot": False, "FL_foot": True, "RL_foot": True, "FR_foot": False}
+    pose = {n: dh.getFootPose(mh.getFootNb(n)) for n in order}
+    force = {n: np.array([0, 0, 10.0]) for n in order}
+    st = ocp.createStage(phase, pose, force, {n: False for n in order})
+    assert list(st.contact_states) == [phase[n] for n in order] == [False, True, True, False]
+    assert st.contact_mask == sum(1 << i for i, n in enumerate(order) if phase[n])
+    assert [c for c in st.constraint_names if c.endswith("_frame_velocity")] == ["FL_foot_frame_velocity", "RL_foot_frame_velocity"]
+
+
 def test_python_derived_handlers_are_driven_through_the_trampoline():
     """reference include/simple-mpc/python/py-ocp-handler.hpp:71-192 (PyOCPHandler): handlers derived in Python. The C++ driver
     (createProblem, MPC::generateCycleHorizon, MPC::iterate -> updateStepTrackerReferences) must reach the Python overrides
