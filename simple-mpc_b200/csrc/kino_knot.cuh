@@ -64,18 +64,21 @@ namespace smpc
     {
       struct
       {
-        double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6], bias[NJ][6];
+        double R[NJ][9], p[NJ][3], v[NJ][6], a[NJ][6];
         double Y[NJ][10], hs[NJ][6], dIo[NJ][6], fs[NJ][6]; // subtree sums
         double J[6][NV];
       };
       struct
       {
         double rhs[6][Cfg::NRHS];
+        double lamn[NDX]; // co-state lams[t+1], staged for the A / B assembly loops
+        double Jq6[36], Jv6[36]; // free-flyer blocks of dIntegrate (built in the right-hand-side phase, read by the A / B assembly)
       };
       struct
       {
         double WJc[6][NDX], WJcdx[6][NV], WJcdu[6][Cfg::NF], WJp[NK][Cfg::PR][NV];
         double cval[Cfg::NCMAX], dproj[Cfg::NCMAX], vplus[Cfg::NCMAX], rpinf[Cfg::NCMAX], rcrit[Cfg::NCMAX];
+        double vsm[Cfg::NCMAX]; // constraint multipliers of this knot, staged for the gradient loops
       };
     };
     //   U2: own-body inertia / momentum (until the last acceleration pass) | d(hdot)/d(q, v) (per-dof phase until the
@@ -109,17 +112,18 @@ namespace smpc
     int nc;
     // row table as bytes (kind < 7, joint / foot index < 64, sub-row < 17): shared memory bounds the resident knots per SM
     unsigned char rkind[Cfg::NCMAX], rarg[Cfg::NCMAX], rsub[Cfg::NCMAX], ractive[Cfg::NCMAX];
-    double costs[8 + NK];
+    double costs[4 + NK];
     double rpl[NK][Q6]; // quad feet: pose residual log6(ref^-1 oMf) (written by the value-only instantiation too)
     // ---- linearisation only (DERIVS = true). Everything from dh_dq on is never touched by the value-only (trial)
     // instantiation, which is launched with trial_bytes() of shared memory and therefore fits more CTAs per SM ----
     double dh_dq[6][NV];
     double Jp[NK][Cfg::PR][NV];       // world-aligned foot Jacobian: translation rows (+ rotation rows for quad feet)
     double Tpl[NK][Q36];              // quad feet: T = Jlog6(r) blkdiag(R^T, R^T) of the pose residual r
-    double vf_dq[NK][Cfg::VR][NV], vf_dv[NK][Cfg::VR][NV];
-    double dhF_dq[3][NV], dhF_du[6][Cfg::NF];
-    double Jq6[36], Jv6[36], Jl6[36];
-    double lamn[NDX], vsm[Cfg::NCMAX]; // co-state lams[t+1] and constraint multipliers of this knot
+    // d(LOCAL foot velocity)/dq. The partial w.r.t. v is R^T Jp (vf_dv below) and d(hdot_F)/du is [e_k ; lever x e_k]
+    // (dhF_du below): both are rebuilt where they are read - 2.3 KB of scratch less, which is what lets 12 knots share an SM
+    double vf_dq[NK][Cfg::VR][NV];
+    double dhF_dq[3][NV];
+    double Jl6[36];
   };
   template <class Cfg>
   constexpr size_t kino_trial_bytes()
@@ -152,6 +156,34 @@ namespace smpc
     double * fc = nullptr; // contact forces [nfeet][3] (full dynamics only)
     KnotScalars * sc;
   };
+
+  // d(LOCAL velocity of foot f, row r)/dv_a = (R_f^T Jp_f)(r, a): translation rows from the point Jacobian, rotation rows
+  // (quad feet) from the world-aligned angular Jacobian kept in rows 3..5 of Jp
+  template <class Cfg>
+  SMPC_DEV double kino_vf_dv(const KinoScratch<Cfg> & s, int f, int r, int a)
+  {
+    constexpr int PR = Cfg::PR;
+    const int r3 = r % 3, k0 = (r >= 3) ? 3 : 0;
+    const double * R = s.fR[f];
+    return R[r3] * s.Jp[f][k0 % PR][a] + R[3 + r3] * s.Jp[f][(k0 + 1) % PR][a] + R[6 + r3] * s.Jp[f][(k0 + 2) % PR][a];
+  }
+  // d(hdot_F)(r)/du_jf for the contact-wrench entry jf = FS f + k: [e_k ; lever_f x e_k] for a force, [0 ; e_k] for a torque
+  template <class Cfg>
+  SMPC_DEV double kino_dhF_du(const KinoScratch<Cfg> & s, unsigned cmask, int r, int jf)
+  {
+    constexpr int FS = Cfg::FS;
+    const int f = jf / FS, k = jf % FS;
+    if (!(cmask & (1u << f)))
+      return 0.0;
+    if (k >= 3 || r < 3)
+      return (r == k) ? 1.0 : 0.0;
+    const double * l = s.lever[f];
+    const int i = r - 3; // (l x e_k)(i)
+    if (i == k)
+      return 0.0;
+    const int m = 3 - i - k; // the remaining axis
+    return ((k - i + 3) % 3 == 1) ? -l[m] : l[m];
+  }
 
   // ------------------------------------------------------------------------------------------
   // kinematics + centroidal quantities shared by stage and terminal knots
@@ -251,7 +283,6 @@ namespace smpc
         double * vi = s.v[i];
         for (int r = 0; r < 6; r++)
           vi[r] = (par >= 0 ? s.v[par][r] : 0.0) + vJ[r];
-        mxm(vi, vJ, s.bias[i]);
         // world-frame inertia about the origin
         double cw[3], T[9], Ic[9];
         m3v(oR, d.lever[i], cw);
@@ -329,13 +360,24 @@ namespace smpc
         const int iv = d.idx_v[i];
         const int ndof = (d.jtype[i] == SMPC_JOINT_FREEFLYER) ? 6 : 1;
         double * ai = s.a[i];
+        // velocity-product term v_i x (S_i qdot_i), rebuilt from the Jacobian columns (it used to be kept in scratch)
+        const double * vq = s.x + Cfg::NQ;
+        double vJ[6], bias[6];
+        for (int r = 0; r < 6; r++)
+        {
+          double t = 0;
+          for (int c = 0; c < ndof; c++)
+            t += s.J[r][iv + c] * vq[iv + c];
+          vJ[r] = t;
+        }
+        mxm(s.v[i], vJ, bias);
         for (int r = 0; r < 6; r++)
         {
           double aJ = 0;
           if (acc)
             for (int c = 0; c < ndof; c++)
               aJ += s.J[r][iv + c] * acc[iv + c];
-          ai[r] = (par >= 0 ? s.a[par][r] : 0.0) + aJ + s.bias[i][r];
+          ai[r] = (par >= 0 ? s.a[par][r] : 0.0) + aJ + bias[r];
         }
         double Ia[6], vxh[6];
         inertia_apply(s.Yb[i], ai, Ia);
@@ -578,14 +620,6 @@ namespace smpc
         }
         for (int k = tid; k < NU; k += SMPC_NT)
           s.u[k] = io.u[k];
-        if (DERIVS)
-        {
-          // multipliers read inside the assembly loops: one coalesced fetch instead of a global load per iteration
-          for (int k = tid; k < NDX; k += SMPC_NT)
-            s.lamn[k] = io.lam_n[k];
-          for (int k = tid; k < O.ncmax; k += SMPC_NT) // the multiplier arrays are strided by the run-time ncmax
-            s.vsm[k] = io.vs[k];
-        }
       }
       else
       {
@@ -677,13 +711,6 @@ namespace smpc
           s.e[NV + k] = s.xnext[NQ + k] - s.xn_ws[NQ + k];
         for (int k = 0; k < NDX; k++)
           s.lplus[k] = io.prev_lam_n[k] + s.e[k] * inv_mu;
-        if (DERIVS)
-        {
-          double E[9], ep[3];
-          exp6(dq, E, ep);
-          actinv6(E, ep, s.Jq6);
-          Jexp6(dq, s.Jv6);
-        }
       }
       else if (tid == 1)
       {
@@ -834,7 +861,6 @@ namespace smpc
           {
             s.Jp[f][r][j] = jp[r];
             s.vf_dq[f][r][j] = a3[r];
-            s.vf_dv[f][r][j] = b3[r];
           }
           if (FS == 6)
           {
@@ -846,7 +872,6 @@ namespace smpc
             {
               s.Jp[f][(3 + r) % PR][j] = on ? Jc[3 + r] : 0.0;
               s.vf_dq[f][(3 + r) % VR][j] = a3[r];
-              s.vf_dv[f][(3 + r) % VR][j] = b3[r];
             }
           }
           if (cmask & (1u << f))
@@ -899,8 +924,6 @@ namespace smpc
               b[3] = t[0], b[4] = t[1], b[5] = t[2];
             }
           }
-          for (int r = 0; r < 6; r++)
-            s.dhF_du[r][jf] = b[r];
         }
         else
         {
@@ -911,6 +934,19 @@ namespace smpc
         lu6_solve(s.lu, s.piv, b);
         for (int r = 0; r < 6; r++)
           s.rhs[r][c] = b[r];
+      }
+      // multipliers read inside the A / B assembly loops: one coalesced fetch instead of a global load per iteration
+      for (int k = tid; k < NDX; k += SMPC_NT)
+        s.lamn[k] = io.lam_n[k];
+      // dIntegrate blocks of q+ = q (+) dt v+ on the free-flyer: by the lane with the fewest right-hand sides
+      if (tid == SMPC_NT - 1)
+      {
+        double dq6[6], E[9], ep[3];
+        for (int k = 0; k < 6; k++)
+          dq6[k] = dt * s.xnext[NQ + k];
+        exp6(dq6, E, ep);
+        actinv6(E, ep, s.Jq6);
+        Jexp6(dq6, s.Jv6);
       }
       SMPC_END
 
@@ -991,7 +1027,7 @@ namespace smpc
           const int r = e / NF, a = e % NF;
           double sacc = 0;
           for (int k = 0; k < 6; k++)
-            sacc += O.w_centder[6 * r + k] * s.dhF_du[k][a];
+            sacc += O.w_centder[6 * r + k] * kino_dhF_du<Cfg>(s, cmask, k, a);
           s.WJcdu[r][a] = sacc;
         }
         if (FS == 3)
@@ -1093,6 +1129,9 @@ namespace smpc
         s.WJp[f][r][a] = sacc;
       }
     }
+    if (DERIVS)
+      for (int k = tid; k < O.ncmax; k += SMPC_NT) // the multiplier arrays are strided by the run-time ncmax
+        s.vsm[k] = io.vs[k];
     for (int row = tid; row < s.nc; row += SMPC_NT)
     {
       const int kind = s.rkind[row], f = s.rarg[row];
@@ -1206,7 +1245,7 @@ namespace smpc
           {
             double t = 0;
             for (int r = 0; r < 6; r++)
-              t += s.dhF_du[r][i] * s.WJcdu[r][j];
+              t += kino_dhF_du<Cfg>(s, cmask, r, i) * s.WJcdu[r][j];
             acc += t;
           }
           if (i == j)
@@ -1254,7 +1293,7 @@ namespace smpc
             if (kind == ROW_BOX)
               cx = (a == 6 + f) ? 1.0 : 0.0;
             else if (kind == ROW_VEL)
-              cx = (a < NV) ? s.vf_dq[f][s.rsub[row]][a] : s.vf_dv[f][s.rsub[row]][a - NV];
+              cx = (a < NV) ? s.vf_dq[f][s.rsub[row]][a] : kino_vf_dv<Cfg>(s, f, s.rsub[row], a - NV);
             else if (kind == ROW_LAND)
               cx = (a < NV) ? s.Jp[f][2][a] : 0.0;
             Lc += cx * s.vsm[row];
@@ -1271,7 +1310,7 @@ namespace smpc
           {
             double t = 0;
             for (int r = 0; r < 6; r++)
-              t += s.dhF_du[r][j] * s.Wcdh[r];
+              t += kino_dhF_du<Cfg>(s, cmask, r, j) * s.Wcdh[r];
             g += t;
           }
           io.knot[L.or_ + j] = g;
@@ -1311,7 +1350,7 @@ namespace smpc
             if (kind == ROW_BOX)
               cx = (a == 6 + f) ? 1.0 : 0.0;
             else if (kind == ROW_VEL)
-              cx = (a < NV) ? s.vf_dq[f][s.rsub[row]][a] : s.vf_dv[f][s.rsub[row]][a - NV];
+              cx = (a < NV) ? s.vf_dq[f][s.rsub[row]][a] : kino_vf_dv<Cfg>(s, f, s.rsub[row], a - NV);
             else if (kind == ROW_LAND)
               cx = (a < NV) ? s.Jp[f][2][a] : 0.0;
           }

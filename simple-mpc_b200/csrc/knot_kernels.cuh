@@ -9,16 +9,16 @@ namespace smpc
 {
   // kinodynamics: one warp per knot. The kernels are latency-bound and their throughput follows the resident warps per SM
   // (6 -> 8 warps: 1.33x, profiles/r01e vs r01f). A one-warp CTA lives on one SM sub-partition (16 K registers), so the
-  // steps are 2 warps per sub-partition (<= 255 registers), 3 (<= 168) and 4 (<= 128). Linearisation kernel: 22.2 KB of
-  // scratch allow 10 CTAs/SM; at 168 registers (72 bytes of spills) that measures 53.3 ms per tick against 53.8 ms for
-  // 8 CTAs/SM at 254 registers (B = 4096), so 10 is the default.
+  // steps are 2 warps per sub-partition (<= 255 registers), 3 (<= 168) and 4 (<= 128). Linearisation kernel: 18.1 KB of
+  // scratch (round 2: vf_dv, dhF_du, the velocity-product terms and the dIntegrate blocks are rebuilt where they are read or
+  // share storage with dead arrays) allow 12 CTAs/SM at 168 registers: 15.6 -> 14.2 ms per launch at B = 4096 (profiles/r02o).
 #ifndef SMPC_KNOT_MINB
-#define SMPC_KNOT_MINB 10
+#define SMPC_KNOT_MINB 12
 #endif
-// the value-only (trial) instantiation needs 13.7 KB of the scratch and no spills at 168 registers: three warps per
-// SM sub-partition (measured: 10 CTAs/SM 55.3 vs 8 CTAs/SM 55.8 ms per tick before the scratch was split)
+// the value-only (trial) instantiation needs 13.0 KB of the scratch: four warps per SM sub-partition at 128 registers
+// (224 bytes of spills) measure 4.65 ms against 5.1 ms for three at 168 registers (B = 4096, profiles/r02o)
 #ifndef SMPC_KNOT_MINB_TRIAL
-#define SMPC_KNOT_MINB_TRIAL 12
+#define SMPC_KNOT_MINB_TRIAL 16
 #endif
   template <class Cfg, bool TRIAL>
 #ifdef SMPC_KNOT_MAXREG

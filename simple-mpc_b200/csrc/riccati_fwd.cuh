@@ -22,12 +22,15 @@ namespace smpc
   // (TMA) that complete on one mbarrier per buffer. Stage t+1 is in flight while stage t is computed.
   struct FwdSmem
   {
-    int obuf[2]; // landing buffers
+    int obuf[2]; // landing buffers (nbuf = 1: both name the same buffer)
+    int nbuf;    // 2: stage t+1 in flight while stage t is computed (lowest latency per instance, two CTAs per SM);
+                 // 1: one buffer, the next stage fetched while the last phase of this one runs - five CTAs per SM hide each other's
+                 //    fetches (highest throughput for batches many waves deep)
     int okn;     // offset of the A B f block inside a landing buffer (after the solution block)
     int odx, odu, oy, olam, opart, obar, size;
     int sol_doubles, kn_doubles;
   };
-  inline FwdSmem make_fwd_smem(int ndx, int nu, int ncmax)
+  inline FwdSmem make_fwd_smem(int ndx, int nu, int ncmax, int nbuf = 2)
   {
     const KnotLayout L = make_knot_layout(ndx, nu, ncmax);
     const SolLayout SL = make_sol_layout(ndx, nu, ncmax);
@@ -36,8 +39,12 @@ namespace smpc
     F.kn_doubles = (L.of + ndx - L.oA + 1) & ~1; // A B f (+ one pad double when odd; stays inside the knot)
     const int stage = F.sol_doubles + F.kn_doubles;
     int o = 0;
+    F.nbuf = nbuf;
     F.obuf[0] = o, o += stage;
-    F.obuf[1] = o, o += stage;
+    if (nbuf == 2)
+      F.obuf[1] = o, o += stage;
+    else
+      F.obuf[1] = F.obuf[0];
     F.okn = F.sol_doubles;
     F.odx = o, o += ndx;
     F.odu = o, o += nu;
@@ -152,9 +159,10 @@ namespace smpc
       fwd_copy(sm + F.obuf[0] + F.okn, knots + L.oA, F.kn_doubles, bars + 0);
     }
     SMPC_END
+    const bool two = F.nbuf == 2;
     for (int t = 0; t < N; t++)
     {
-      const int cur = t & 1;
+      const int cur = two ? (t & 1) : 0;
       const double * buf = sm + F.obuf[cur];
       const double * Ks = buf + SL.oK;
       const double * kv = buf + SL.ok;
@@ -169,7 +177,7 @@ namespace smpc
       SMPC_PAR(tid)
       {
         // stage t+1 goes into the other buffer (last read in stage t-1; every thread has passed a barrier since)
-        if (tid == 0 && t + 1 < N)
+        if (two && tid == 0 && t + 1 < N)
         {
           void * nb = bars + (cur ^ 1);
           double * nbuf = sm + F.obuf[cur ^ 1];
@@ -177,7 +185,7 @@ namespace smpc
           fwd_copy(nbuf, sol + (size_t)(t + 1) * SL.size, F.sol_doubles, nb);
           fwd_copy(nbuf + F.okn, knots + (size_t)(t + 1) * L.size + L.oA, F.kn_doubles, nb);
         }
-        fwd_wait(bars + cur, (unsigned)((t >> 1) & 1));
+        fwd_wait(bars + cur, (unsigned)((two ? (t >> 1) : t) & 1));
         // (the dot products are unrolled by 6 so that the shared-memory loads of a group issue ahead of its fma chain;
         // the chain order itself is unchanged)
         for (int a = tid; a < nu; a += SMPC_NT)
@@ -242,11 +250,21 @@ namespace smpc
       }
       SMPC_END
       SMPC_PAR(tid)
-      for (int a = tid; a < ndx; a += SMPC_NT)
       {
-        const double v = y[a] - mudyn * lam[a];
-        dx[a] = v;
-        dxs[(size_t)(t + 1) * ndx + a] = v;
+        // one landing buffer: nothing reads it after the barrier above, fetch stage t+1 behind this last phase
+        if (!two && tid == 0 && t + 1 < N)
+        {
+          double * nbuf = sm + F.obuf[0];
+          fwd_arm(bars + 0, (unsigned)(F.sol_doubles + F.kn_doubles) * 8u);
+          fwd_copy(nbuf, sol + (size_t)(t + 1) * SL.size, F.sol_doubles, bars + 0);
+          fwd_copy(nbuf + F.okn, knots + (size_t)(t + 1) * L.size + L.oA, F.kn_doubles, bars + 0);
+        }
+        for (int a = tid; a < ndx; a += SMPC_NT)
+        {
+          const double v = y[a] - mudyn * lam[a];
+          dx[a] = v;
+          dxs[(size_t)(t + 1) * ndx + a] = v;
+        }
       }
       SMPC_END
     }

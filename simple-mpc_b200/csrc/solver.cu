@@ -15,9 +15,6 @@
 
 using namespace smpc;
 
-#ifndef SMPC_FWD_STAGED_MAX_WAVES
-#define SMPC_FWD_STAGED_MAX_WAVES 5
-#endif
 namespace smpc
 {
   std::string & err()
@@ -725,20 +722,30 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   A.L = make_knot_layout(O.ndx, O.nu, O.ncmax);
   A.SL = make_sol_layout(O.ndx, O.nu, O.ncmax);
   A.RS = make_ric_smem(O.ndx, O.nu, O.ncmax);
-  A.FS = make_fwd_smem(O.ndx, O.nu, O.ncmax);
-  // which forward kernel: the TMA-staged one has the lower latency per instance (two CTAs per SM), the direct one the
-  // higher throughput once the batch is many waves deep (SMPC_FWD_STAGED_MAX_WAVES, measured; SMPC_FWD overrides).
-  // Shapes whose two landing buffers exceed the shared memory of an SM use the direct kernel.
+  // which forward kernel. The TMA-staged sweep with two landing buffers (stage t+1 in flight while stage t is computed, two CTAs
+  // per SM) has the lowest latency when no SM holds more than one instance; beyond that the same sweep with ONE landing buffer
+  // wins at every batch size: five CTAs per SM hide each other's fetches (B = 512: 0.31 vs 0.46 ms, B = 4096: 1.90 vs 3.19 ms, and
+  // 2.76 ms for the direct kernel that reads rows straight from global memory - profiles/r02p). The direct kernel is left for
+  // shapes whose stage does not fit the shared memory of an SM. SMPC_FWD = staged | staged1 | direct overrides.
   {
+    int nbuf = batch <= (c->hmodel_sms > 0 ? c->hmodel_sms : 148) ? 2 : 1;
+    c->forward_staged = true;
+    if (const char * e = getenv("SMPC_FWD"))
+    {
+      c->forward_staged = strcmp(e, "direct") != 0;
+      nbuf = strcmp(e, "staged1") == 0 ? 1 : (strcmp(e, "staged") == 0 ? 2 : nbuf);
+    }
+    A.FS = make_fwd_smem(O.ndx, O.nu, O.ncmax, nbuf);
+    if (nbuf == 2 && (size_t)A.FS.size * sizeof(double) > 232448 - 64)
+      A.FS = make_fwd_smem(O.ndx, O.nu, O.ncmax, 1);
     const size_t fwd_bytes = (size_t)A.FS.size * sizeof(double);
     const bool fits = fwd_bytes <= 232448 - 64;
-    const int per_wave = 2 * (c->hmodel_sms > 0 ? c->hmodel_sms : 148);
-    c->forward_staged = batch <= SMPC_FWD_STAGED_MAX_WAVES * per_wave;
-    if (const char * e = getenv("SMPC_FWD"))
-      c->forward_staged = strcmp(e, "direct") != 0;
     c->forward_staged = c->forward_staged && fits;
     if (fits)
+    {
       CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_bytes));
+      CU(cudaFuncSetAttribute(k_forward, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
   }
   A.opt = *opts;
   // kernel instantiation for this (robot, problem) shape; each family lives in its own translation unit

@@ -120,7 +120,7 @@ static int emul_riccati3_impl(
     return -1;
   }
   // the hot path's forward sweep: stage matrices staged through (emulated) shared memory
-  FwdSmem FS = make_fwd_smem(ndx, nu, ncmax);
+  FwdSmem FS = make_fwd_smem(ndx, nu, ncmax, getenv("SMPC_EMUL_FWD_NBUF") ? atoi(getenv("SMPC_EMUL_FWD_NBUF")) : 2);
   std::vector<double> smf((size_t)FS.size + 8, 0.0);
   riccati_forward_staged(L, SL, FS, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, smf.data());
   return 0;

@@ -165,6 +165,11 @@ def run_case(cone, robot="go2"):
             # no row depends on the control (D = 0): Sigma = mu I, the W / Sigma phases drop out (riccati3.cuh DZ)
             out['kino_structure_d0_on_oracle'] = sweep(emu.emul_riccati3_kino_d0, orc_knots)
     out['special_on_emul'] = sweep(tuned, emu_knots)
+    if robot == "go2":
+        # the forward sweep with ONE landing buffer (riccati_fwd.cuh, nbuf = 1: the variant large batches run)
+        os.environ["SMPC_EMUL_FWD_NBUF"] = "1"
+        out['tma_one_buffer_on_oracle'] = sweep(emu.emul_riccati3, orc_knots)
+        del os.environ["SMPC_EMUL_FWD_NBUF"]
     # conditioning of the penalised recursion, measured: the oracle's own knots with every entry moved by at most ONE ULP
     # (relative 2^-52, the size of the difference between two correct evaluations of the same Jacobians)
     spread = []
@@ -198,7 +203,7 @@ def test_infeasibility_scalars_match(case):
 
 
 def test_riccati_bitwise(case):
-    for name in ['generic_on_oracle', 'tma_on_oracle', 'two_column_on_oracle', 'kino_structure_on_oracle', 'kino_structure_d0_on_oracle']:
+    for name in ['generic_on_oracle', 'tma_on_oracle', 'two_column_on_oracle', 'kino_structure_on_oracle', 'kino_structure_d0_on_oracle', 'tma_one_buffer_on_oracle']:
         if name not in case:
             continue
         K, dxs, dus = case[name]
