@@ -151,7 +151,55 @@ namespace smpc
     }
   }
 
-  template <int NDX, int NU, int NC, int TPB>
+  // ---- padded mode (GN < NDX): the problem's state dimension GN is not a multiple of 4 (the centroidal problem: 9) ----
+  // The kernel computes on NDX = GN rounded up to 4 with the extra rows / columns of every matrix held at exact zeros in
+  // shared memory (P, A, Q: zero; I + mu P: identity there), so every real entry receives the operations of the unpadded
+  // recursion plus products with exact zeros: bitwise the same values. Global memory keeps the unpadded layouts (L, SL built
+  // with ndx = GN); the knot is expanded into the padded regions by ordinary loads instead of bulk copies (a stage is ~10 KB).
+  template <int GN, int NDX, int NU, int NC>
+  SMPC_DEV void ric4_expand_H_ABf(const KnotLayout & L, const double * __restrict__ kn, double * H, double * ABf, int tid, int nt)
+  {
+    typedef Ric4<NDX, NU, NC> R;
+    constexpr int NAB = NDX + NU;
+    for (int e = tid; e < NDX * NDX; e += nt)
+    {
+      const int a = e / NDX, b = e - a * NDX;
+      const bool in = a < GN && b < GN;
+      H[R::kQ + e] = in ? kn[L.oQ + a * GN + b] : 0.0;
+      ABf[e] = in ? kn[L.oA + a * GN + b] : 0.0;
+    }
+    for (int e = tid; e < NDX * NU; e += nt)
+    {
+      const int a = e / NU;
+      H[R::kS + e] = a < GN ? kn[L.oS + e] : 0.0;
+      ABf[NDX * NDX + e] = a < GN ? kn[L.oB + e] : 0.0;
+    }
+    for (int e = tid; e < NU * NU; e += nt)
+      H[R::kR + e] = kn[L.oR + e];
+    for (int a = tid; a < NDX; a += nt)
+    {
+      H[R::kq + a] = a < GN ? kn[L.oq + a] : 0.0;
+      ABf[NDX * NAB + a] = a < GN ? kn[L.of + a] : 0.0;
+    }
+    for (int j = tid; j < NU; j += nt)
+      H[R::kr + j] = kn[L.or_ + j];
+  }
+  template <int GN, int NDX, int NU, int NC>
+  SMPC_DEV void ric4_expand_CDd(const KnotLayout & L, const double * __restrict__ kn, double * CDd, int tid, int nt)
+  {
+    constexpr int NAB = NDX + NU;
+    for (int e = tid; e < NC * NDX; e += nt)
+    {
+      const int i = e / NDX, b = e - i * NDX;
+      CDd[e] = b < GN ? kn[L.oC + i * GN + b] : 0.0;
+    }
+    for (int e = tid; e < NC * NU; e += nt)
+      CDd[NC * NDX + e] = kn[L.oD + e];
+    for (int i = tid; i < NC; i += nt)
+      CDd[NC * NAB + i] = kn[L.od + i];
+  }
+
+  template <int NDX, int NU, int NC, int TPB, int GN = NDX>
   SMPC_DEV void riccati4_backward_inst(
     const KnotLayout & L, const SolLayout & SL, int N, const double * __restrict__ knots, double * __restrict__ sol,
     double mudyn, double mueq, double * sm, int * flag_out, double * P0out)
@@ -188,6 +236,8 @@ namespace smpc
     const double * dk = CDd + NC * NAB;
     const double inv_mu = 1.0 / mueq;
     unsigned parity = 0;
+    static_assert(GN <= NDX && NDX - GN < 4, "GN is the problem's state dimension, NDX the same rounded up to a multiple of 4");
+    constexpr bool PAD = GN != NDX;
 
     // ---- terminal node: Z = C/mu, z = d/mu ; P = Q + C^T Z ; p = q + C^T z ; M = I + mudyn P ----
     {
@@ -200,7 +250,7 @@ namespace smpc
           *bad = 0;
           bulk_init(bar);
         }
-        for (int e = tid; e < NC * NDX; e += SMPC_NT)
+        for (int e = tid; e < NC * GN; e += SMPC_NT)
           so[SL.oZ + e] = kn[L.oC + e] * inv_mu;
         for (int i = tid; i < NC; i += SMPC_NT)
           so[SL.oz + i] = kn[L.od + i] * inv_mu;
@@ -210,18 +260,20 @@ namespace smpc
       for (int e = tid; e < NDX * LDP; e += SMPC_NT)
       {
         const int a = e / LDP, bb = e % LDP;
-        double acc;
-        if (bb == 0)
+        double acc = 0.0;
+        if (PAD && (a >= GN || bb > GN))
+          acc = 0.0; // padding rows / columns
+        else if (bb == 0)
         {
           acc = kn[L.oq + a];
           for (int i = 0; i < NC; i++)
-            acc = fma(kn[L.oC + i * NDX + a], so[SL.oz + i], acc);
+            acc = fma(kn[L.oC + i * GN + a], so[SL.oz + i], acc);
         }
         else
         {
-          acc = kn[L.oQ + a * NDX + (bb - 1)];
+          acc = kn[L.oQ + a * GN + (bb - 1)];
           for (int i = 0; i < NC; i++)
-            acc = fma(kn[L.oC + i * NDX + a], so[SL.oZ + i * NDX + (bb - 1)], acc);
+            acc = fma(kn[L.oC + i * GN + a], so[SL.oZ + i * GN + (bb - 1)], acc);
         }
         PP[e] = acc;
       }
@@ -244,7 +296,9 @@ namespace smpc
       double * so = sol + (size_t)t * SL.size;
       // ---- 0. start the copies of this stage's [Q S R q r] and [A B f]; C D d follow after step 3 ----
       SMPC_PAR(tid)
-      if (tid == 0)
+      if (PAD)
+        ric4_expand_H_ABf<GN, NDX, NU, NC>(L, kn, H, ABf, tid, SMPC_NT);
+      else if (tid == 0)
         bulk_load2(H, kn, R::szH, ABf, kn + R::kA, R::szABf, bar);
       SMPC_END
       RIC_T(0)
@@ -260,12 +314,13 @@ namespace smpc
       // ---- 2. knot landed ; P~ p~ out (for the forward sweep) ; w = P~ f + p~ ; PAB = P~ [A B] ----
       SMPC_PAR(tid)
       {
-        bulk_wait(bar, parity);
-        for (int a = tid; a < NDX; a += SMPC_NT)
+        if (!PAD)
+          bulk_wait(bar, parity);
+        for (int a = tid; a < GN; a += SMPC_NT)
           so[SL.opt + a] = PP[a * LDP];
-        for (int e = tid; e < NDX * NDX; e += SMPC_NT)
+        for (int e = tid; e < GN * GN; e += SMPC_NT)
         {
-          const int a = e / NDX, b = e - a * NDX;
+          const int a = e / GN, b = e - a * GN;
           so[SL.oPt + e] = PP[a * LDP + 1 + b];
         }
         // 4 x 4 tiles of PAB: rows a0.., columns over A (NDX / 4 tiles) then over B (ceil(NU / 4) tiles, the last may be 2 wide)
@@ -394,14 +449,17 @@ namespace smpc
       // ---- 4. KKT by block LDL^T ----
       // PAB is dead: fetch C D d into its tail rows' storage while R^ is factorised
       SMPC_PAR(tid)
-      if (tid == 0)
+      if (PAD)
+        ric4_expand_CDd<GN, NDX, NU, NC>(L, kn, CDd, tid, SMPC_NT);
+      else if (tid == 0)
         bulk_load2(CDd, kn + R::kC, R::szCDd, nullptr, nullptr, 0, bar);
       SMPC_END
       chol2<NU, NU, TPB>(Rh, colb, invr, bad);
       RIC_T(5)
       SMPC_PAR(tid)
       {
-        bulk_wait(bar, parity);
+        if (!PAD)
+          bulk_wait(bar, parity);
         for (int e = tid; e < NU * NRY; e += SMPC_NT)
         {
           const int a = e / NRY, c = e - a * NRY;
@@ -616,14 +674,16 @@ namespace smpc
           const int a = e / NDX, c = e - a * NDX;
           const double val = -YW[a * NRY + 1 + c];
           YW[a * NRY + 1 + c] = val;
-          so[SL.oK + e] = val;
+          if (!PAD || c < GN)
+            so[SL.oK + a * GN + c] = val;
         }
         for (int i = tid; i < NC; i += SMPC_NT)
           so[SL.oz + i] = G[i * LDP];
         for (int e = tid; e < NC * NDX; e += SMPC_NT)
         {
           const int i = e / NDX, c = e - i * NDX;
-          so[SL.oZ + e] = G[i * LDP + 1 + c];
+          if (!PAD || c < GN)
+            so[SL.oZ + i * GN + c] = G[i * LDP + 1 + c];
         }
       }
       SMPC_END
@@ -738,11 +798,12 @@ namespace smpc
     {
       if (tid == 0 && flag_out)
         *flag_out = *bad;
-      if (P0out) // layout expected by riccati_forward_inst: [P | p]
+      if (P0out) // layout expected by riccati_forward_inst: [P | p], (GN + 1) columns
         for (int e = tid; e < NDX * LDP; e += SMPC_NT)
         {
           const int a = e / LDP, bb = e % LDP;
-          P0out[a * LDP + (bb == 0 ? NDX : bb - 1)] = PP[e];
+          if (!PAD || (a < GN && bb <= GN))
+            P0out[a * (GN + 1) + (bb == 0 ? GN : bb - 1)] = PP[e];
         }
     }
     SMPC_END

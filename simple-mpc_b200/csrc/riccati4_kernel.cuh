@@ -13,10 +13,12 @@ namespace smpc
   {
     // 256 threads = the latency variant: one instance per SM with the whole register file (255 registers, no spills)
     constexpr int fit = 233472 / (Ric4<NDX, NU, NC>::SIZE * 8 + 1024 + 16);
-    constexpr int cap = TPB >= 256 ? 1 : 512 / TPB; // at least 128 registers per thread
+    // at least 128 registers per thread; the small stages of the centroidal problem (ndx 12) live with 80
+    constexpr int cap = TPB >= 256 ? 1 : (NDX <= 16 ? 768 / TPB : 512 / TPB);
     return fit < 1 ? 1 : (fit > cap ? cap : fit);
   }
-  template <int NDX, int NU, int NC, int TPB>
+  // GN: the problem's state dimension when it is not a multiple of 4 (padded mode of riccati4.cuh), else = NDX
+  template <int NDX, int NU, int NC, int TPB, int GN>
   __global__ void __launch_bounds__(TPB, (ric4_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati4(Arrays A)
   {
     extern __shared__ __align__(16) double smem_raw[];
@@ -27,37 +29,45 @@ namespace smpc
       return;
     const size_t xb = (size_t)b * (d.N + 1);
     __shared__ int flag;
-    riccati4_backward_inst<NDX, NU, NC, TPB>(
+    riccati4_backward_inst<NDX, NU, NC, TPB, GN>(
       A.L, A.SL, d.N, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag,
       A.P0 + (size_t)b * d.ndx * (d.ndx + 1));
     if (threadIdx.x == 0 && flag)
       st.flags |= 1;
   }
-  template <int NDX, int NU, int NC, int TPB>
+  template <int NDX, int NU, int NC, int TPB, int GN>
   void launch_riccati4_impl(smpc_ctx * c)
   {
-    k_riccati4<NDX, NU, NC, TPB><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
+    k_riccati4<NDX, NU, NC, TPB, GN><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
   }
-  template <int NDX, int NU, int NC, int TPB>
+  template <int NDX, int NU, int NC, int TPB, int GN = NDX>
   int setup_riccati4(smpc_ctx * c, const char * name)
   {
     typedef Ric4<NDX, NU, NC> R;
     const KnotLayout & L = c->A.L;
-    if (L.oQ != R::kQ || L.oS != R::kS || L.oR != R::kR || L.oq != R::kq || L.or_ != R::kr || L.oA != R::kA || L.oB != R::kB
+    if (GN != NDX)
+    {
+      if (L.ndx != GN || L.nu != NU || L.ncmax != NC)
+      {
+        smpc::err() = "riccati4 (padded): problem dimensions differ from the instantiated shape";
+        return SMPC_ERR_INVALID;
+      }
+    }
+    else if (L.oQ != R::kQ || L.oS != R::kS || L.oR != R::kR || L.oq != R::kq || L.or_ != R::kr || L.oA != R::kA || L.oB != R::kB
         || L.of != R::kf || L.oC != R::kC || L.oD != R::kD || L.od != R::kd || L.size != R::KSIZE)
     {
       smpc::err() = "riccati4: compile-time knot layout differs from make_knot_layout";
       return SMPC_ERR_INVALID;
     }
     c->ric_smem = (size_t)R::SIZE * sizeof(double);
-    CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
-    CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    c->launch_riccati = &launch_riccati4_impl<NDX, NU, NC, TPB>;
+    CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+    CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB, GN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c->launch_riccati = &launch_riccati4_impl<NDX, NU, NC, TPB, GN>;
     c->riccati_variant = name;
     if (getenv("SMPC_VERBOSE"))
     {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati4<NDX, NU, NC, TPB>, TPB, c->ric_smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_riccati4<NDX, NU, NC, TPB, GN>, TPB, c->ric_smem);
       fprintf(stderr, "smpc: k_riccati4<%d,%d,%d> (%d threads) %zu B shared memory per instance, resident CTAs per SM: %d\n", NDX, NU, NC, TPB,
               c->ric_smem, nb);
     }

@@ -780,6 +780,8 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
     rc = setup_ric4_go2(c, O.ndx, O.nu, O.ncmax, &tuned);
   if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
     rc = setup_ric4_big(c, O.ndx, O.nu, O.ncmax, &tuned);
+  if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
+    rc = setup_ric4_centro(c, O.ndx, O.nu, O.ncmax, &tuned);
   if (rc != SMPC_OK)
     return rc;
   if (!tuned)
@@ -787,9 +789,10 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
     c->ric_smem = (size_t)A.RS.size * sizeof(double);
     CU(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
     c->launch_riccati = &launch_riccati_generic;
-    // CTA width of the run-time-shape sweep: its phases are loops strided over the CTA, so any multiple of 32 works. A small
-    // stage (the centroidal problem: ndx 9, nu 12) cannot feed 128 threads and pays for their barriers; SMPC_RIC_GENERIC_TPB overrides
-    c->ric_generic_tpb = (O.ndx * (O.ndx + O.nu) <= 512) ? 32 : 128;
+    // CTA width of the run-time-shape sweep: its phases are loops strided over the CTA, so any multiple of 32 works; measured on
+    // the smallest stage there is (centroidal, ndx 9, nu 12, 34 rows) 128 threads still win (49 ms vs 53 / 63 ms for 64 / 32 at
+    // B = 4096, T = 100), so 128 everywhere; SMPC_RIC_GENERIC_TPB overrides
+    c->ric_generic_tpb = 128;
     if (const char * e = getenv("SMPC_RIC_GENERIC_TPB"))
       c->ric_generic_tpb = (atoi(e) == 32 || atoi(e) == 64) ? atoi(e) : 128;
   }

@@ -87,11 +87,11 @@ static void kino_knot_any(const DevModel & M, const DevOcp & O, const KnotLayout
   }
 }
 
-template <int NDX, int NU, int NC>
+template <int NDX, int NU, int NC, int GN = NDX>
 static void ric4_any(const KnotLayout & L, const SolLayout & SL, int N, const double * knots, double * sol, double mudyn, double mueq, int * flag, double * P0)
 {
   std::vector<double> sm(Ric4<NDX, NU, NC>::SIZE + 16, 0.0);
-  riccati4_backward_inst<NDX, NU, NC, SMPC_EMUL_NT>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0);
+  riccati4_backward_inst<NDX, NU, NC, SMPC_EMUL_NT, GN>(L, SL, N, knots, sol, mudyn, mueq, sm.data(), flag, P0);
 }
 
 // the TMA-staged sweep of riccati3.cuh (the one the library launches); SNV = 18: the kinodynamics-structure products
@@ -300,6 +300,10 @@ int emul_riccati4(
     ric4_any<56, 22, 78>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
   else if (ndx == 56 && nu == 22 && ncmax == 90)
     ric4_any<56, 22, 90>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 9 && nu == 12 && ncmax == 34)
+    ric4_any<12, 12, 34, 9>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
+  else if (ndx == 9 && nu == 12 && ncmax == 8)
+    ric4_any<12, 12, 8, 9>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
   else if (ndx == 56 && nu == 34 && ncmax == 34)
     ric4_any<56, 34, 34>(L, SL, N, knots, sol, mudyn, mueq, flag, P0.data());
   else if (ndx == 56 && nu == 34 && ncmax == 46)

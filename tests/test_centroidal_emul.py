@@ -111,8 +111,15 @@ def case():
                           P(sol), P(gxs), P(gus), P(lpl), P(dxs), P(dus), P(vnew), P(lnew), C.byref(dphi), C.byref(flag))
     assert rc == 0 and flag.value == 0
     K = np.array([sol[t][oK:oK + nu * ndx].reshape(nu, ndx) for t in range(T)])
+    # the two-column sweep in padded mode (riccati4.cuh: state dimension 9 computed on 12 x 12 blocks with exact-zero padding)
+    sol4 = np.zeros((T + 1, ssize))
+    dxs4, dus4 = np.zeros((T + 1, ndx)), np.zeros((T, nu))
+    rc = emu.emul_riccati4(T, ndx, nu, ncmax, P(orc_knots), ncs.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(mu), C.c_double(mu),
+                           P(sol4), P(gxs), P(gus), P(lpl), P(dxs4), P(dus4), P(vnew), P(lnew), C.byref(dphi), C.byref(flag))
+    assert rc == 0 and flag.value == 0, emu.emul_last_error()
+    K4 = np.array([sol4[t][oK:oK + nu * ndx].reshape(nu, ndx) for t in range(T)])
     orc.orc_destroy(ctx)
-    return dict(worst=worst, pinf=pinf, dinf=dinf, cost=cost, info=info, K=K, Ko=Ko, dxs=dxs, dus=dus, odx=odx, odu=odu,
+    return dict(K4=K4, dxs4=dxs4, dus4=dus4, worst=worst, pinf=pinf, dinf=dinf, cost=cost, info=info, K=K, Ko=Ko, dxs=dxs, dus=dus, odx=odx, odu=odu,
                 n_active=n_active)
 
 
@@ -132,6 +139,12 @@ def test_centroidal_riccati_bitwise(case):
     assert np.array_equal(case['K'], case['Ko'])
     assert np.array_equal(case['dxs'], case['odx'])
     assert np.array_equal(case['dus'], case['odu'])
+
+
+def test_centroidal_padded_two_column_riccati_bitwise(case):
+    assert np.array_equal(case['K4'], case['Ko'])
+    assert np.array_equal(case['dxs4'], case['odx'])
+    assert np.array_equal(case['dus4'], case['odu'])
 
 
 def test_centroidal_oracle_solve_converges():
