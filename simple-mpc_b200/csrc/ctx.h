@@ -177,5 +177,6 @@ namespace smpc
   int setup_ric3_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati3.cuh, ric3_go2.cu
   int setup_ric4_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati4.cuh, ric4_go2.cu
   int setup_ric4_big(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati4.cuh, ric4_big.cu
+  int setup_ric4_talos_kino(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati4.cuh, ric4_talos_kino.cu
   int setup_ric4_centro(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found); // riccati4.cuh padded mode, ric4_centro.cu
 } // namespace smpc

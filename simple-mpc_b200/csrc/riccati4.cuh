@@ -767,28 +767,23 @@ namespace smpc
       RIC_T(13)
       // symmetrise P; the same pass leaves M = I + mudyn P (lower triangle) for the next stage in X (YW is dead)
       SMPC_PAR(tid)
-      for (int e = tid; e < NDX * NDX; e += SMPC_NT)
       {
-        const int a = e / NDX, b = e - a * NDX;
-        if (b < a)
+        // one thread per entry of the lower triangle (rows r and NDX-1-r share a strip of NDX + 1 entries): each thread reads and
+        // rewrites its own pair P(a,b), P(b,a) only, so one phase suffices
+        static_assert(NDX % 2 == 0, "row pairing");
+        for (int e = tid; e < (NDX / 2) * (NDX + 1); e += SMPC_NT)
         {
-          const double v = 0.5 * (PP[a * LDP + 1 + b] + PP[b * LDP + 1 + a]);
-          Mb[e] = mudyn * v;
-          Mb[b * NDX + a] = v; // parked in the upper triangle of M (never read by the factorisation)
-        }
-        else if (b == a)
-          Mb[e] = mul_then_add(mudyn, PP[a * LDP + 1 + a], 1.0);
-      }
-      SMPC_END
-      SMPC_PAR(tid)
-      for (int e = tid; e < NDX * NDX; e += SMPC_NT)
-      {
-        const int a = e / NDX, b = e - a * NDX;
-        if (b < a)
-        {
-          const double v = Mb[b * NDX + a];
-          PP[a * LDP + 1 + b] = v;
-          PP[b * LDP + 1 + a] = v;
+          const int r = e / (NDX + 1), c = e - r * (NDX + 1);
+          const int a = (c <= r) ? r : NDX - 1 - r, b = (c <= r) ? c : c - r - 1;
+          if (b < a)
+          {
+            const double v = 0.5 * (PP[a * LDP + 1 + b] + PP[b * LDP + 1 + a]);
+            Mb[a * NDX + b] = mudyn * v;
+            PP[a * LDP + 1 + b] = v;
+            PP[b * LDP + 1 + a] = v;
+          }
+          else
+            Mb[a * NDX + a] = mul_then_add(mudyn, PP[a * LDP + 1 + a], 1.0);
         }
       }
       SMPC_END

@@ -781,6 +781,8 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
     rc = setup_ric4_big(c, O.ndx, O.nu, O.ncmax, &tuned);
   if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
+    rc = setup_ric4_talos_kino(c, O.ndx, O.nu, O.ncmax, &tuned);
+  if (rc == SMPC_OK && !tuned && (ric == -1 || ric == 4))
     rc = setup_ric4_centro(c, O.ndx, O.nu, O.ncmax, &tuned);
   if (rc != SMPC_OK)
     return rc;
