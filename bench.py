@@ -408,6 +408,7 @@ def main():
         sc1 = make_scenario(cfg, 1, seed=0)
         b1 = setup_backend(cu, "smpc", sc1, 1, local_rank)
         x1 = np.ascontiguousarray(sc1.xmeas_start())
+        assert cu.smpc_mpc_use_graph(b1.ctx, 0) == 0  # plain launches first: the per-kernel event timers only exist outside the graph
         lat = []
         for k in range(220):
             t1 = time.perf_counter()
@@ -424,6 +425,18 @@ def main():
                              "device_ms": {"linearisation": k1[0] / max(n1.value, 1), "riccati": k1[1] / max(n1.value, 1),
                                            "forward": k1[2] / max(n1.value, 1), "trial+decision": k1[3] / max(n1.value, 1)},
                              "riccati_variant": cu.smpc_riccati_variant(b1.ctx).decode()}
+        # the same loop with the tick replayed as ONE CUDA Graph (smpc_mpc_use_graph): A/B of the launch mechanics
+        assert cu.smpc_mpc_use_graph(b1.ctx, 1) == 0
+        latg = []
+        for k in range(220):
+            t1 = time.perf_counter()
+            assert cu.smpc_mpc_iterate(b1.ctx, P(x1), 1) == 0, cu.smpc_last_error()
+            h = b1.head()[0]
+            latg.append(time.perf_counter() - t1)
+            x1 = np.ascontiguousarray(sc1.next_measurement(x1, h, None))
+        latg = np.array(latg[20:]) * 1e3
+        out["latency_ms"]["cuda_graph"] = {"p50": float(np.percentile(latg, 50)), "p99": float(np.percentile(latg, 99)),
+                                           "what": "same loop, smpc_mpc_use_graph(1) - the default for batches up to the SM count: one graph launch per tick, the head of the plan copied to pinned memory by the graph"}
         b1.close()
     if solo and not args.no_latency and cfg == "c5":
         # north_star target: 4096 instances at >= 100 Hz on 8 GPUs = 512 instances per GPU with a tick <= 10 ms.

@@ -277,6 +277,13 @@ int smpc_mpc_set_walking(smpc_ctx *, int first, int n_inst, int walking);
  * x_meas [batch][nq+nv] measured multibody states (NULL: keep the states already on the device).
  * updateInternalData -> recedeWithCycle -> updateStepTrackerReferences -> warm-start shift -> run(max_iters). */
 int smpc_mpc_iterate(smpc_ctx *, const double * x_meas, int max_iters);
+/* no reference counterpart (launch mechanics only): on != 0 makes smpc_mpc_iterate replay ONE captured CUDA Graph per tick
+ * (driver kernels + one ProxDDP round + its first linesearch trial, one host synchronisation); a linesearch that
+ * backtracks or an extra round continues with plain launches, so results are identical either way (GPU test). For batches
+ * up to 256 instances the graph also copies the head of the plan to pinned memory, which the next smpc_get_head serves
+ * without a second synchronisation. Default: on when the batch does not exceed the SM count (latency-bound ticks), off
+ * otherwise; the environment variable SMPC_GRAPH=0|1 at smpc_create overrides. */
+int smpc_mpc_use_graph(smpc_ctx *, int on);
 /* closed loop without a plant (multibody problem states only): x_meas <- predicted xs[1], device to device */
 int smpc_mpc_xmeas_from_prediction(smpc_ctx *);
 /* replaces: getFootTakeoffCycle / getFootLandCycle      (reference include/simple-mpc/mpc.hpp:141-164)

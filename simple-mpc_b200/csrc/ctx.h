@@ -150,6 +150,17 @@ struct smpc_ctx
   std::vector<smpc_slot> h_table; // host copy of the stage table (contact masks drive the driver's bookkeeping)
   MpcShared h_mpc;
   bool mpc_ready = false;
+  // CUDA Graph of the normal MPC tick (smpc_mpc_use_graph): driver kernels + one round + its first linesearch trial
+  int use_graph = 0;
+  cudaGraphExec_t tick_graph = nullptr;
+  Arrays tick_graph_A{};   // kernel arguments the graph was captured with (re-captured when they change)
+  int tick_graph_iters = 0; // max_iters baked into k_run_begin's node
+  int tick_graph_fwd = 0;   // forward-sweep variant baked in
+  int64_t graph_ticks = 0;
+  // small batches: the graph also copies the head of the plan (x1, u0, u1, K0 of every instance) into this pinned buffer, so
+  // the smpc_get_head that follows a tick is a host memcpy without a second synchronisation
+  double * h_head = nullptr;
+  bool head_cached = false;
 };
 
 #define CU(call)                                                                                                       \

@@ -272,8 +272,10 @@ namespace smpc
   template <int NDX, int NU, int NC, int TPB, int SNV = 0, bool DZ = false>
   SMPC_DEV void riccati3_backward_inst(
     const KnotLayout & L, const SolLayout & SL, int N, const double * __restrict__ knots, double * __restrict__ sol,
-    double mudyn, double mueq, double * sm, int * flag_out, double * P0out)
+    double mudyn, double mueq, double * sm, int * flag_out, double * P0out, const double * Pterm = nullptr)
   {
+    // Pterm != nullptr (a leg of the PARALLEL sweep, riccati_par.cuh): the cost-to-go [P | p] at node N is given (layout of
+    // P0out) and node N's own knot is not touched - it belongs to the next leg
     typedef Ric3<NDX, NU, NC> R;
     constexpr int LDP = R::LDP, NAB = R::NAB, NRY = R::NRY;
     constexpr int TM = (TPB >= 256) ? 2 : 4; // register tile rows: smaller tiles when there are more threads to feed
@@ -312,39 +314,59 @@ namespace smpc
     {
       const double * kn = knots + (size_t)N * L.size;
       double * so = sol + (size_t)N * SL.size;
-      SMPC_PAR(tid)
+      if (Pterm)
       {
-        if (tid == 0)
+        SMPC_PAR(tid)
         {
-          *bad = 0;
-          bulk_init(bar);
+          if (tid == 0)
+          {
+            *bad = 0;
+            bulk_init(bar);
+          }
+          for (int e = tid; e < NDX * LDP; e += SMPC_NT)
+          {
+            const int a = e / LDP, bb = e % LDP;
+            PP[e] = Pterm[a * LDP + (bb == 0 ? NDX : bb - 1)];
+          }
         }
-        for (int e = tid; e < NC * NDX; e += SMPC_NT)
-          so[SL.oZ + e] = kn[L.oC + e] * inv_mu;
-        for (int i = tid; i < NC; i += SMPC_NT)
-          so[SL.oz + i] = kn[L.od + i] * inv_mu;
+        SMPC_END
       }
-      SMPC_END
-      SMPC_PAR(tid)
-      for (int e = tid; e < NDX * LDP; e += SMPC_NT)
+      else
       {
-        const int a = e / LDP, bb = e % LDP;
-        double acc;
-        if (bb == 0)
+        SMPC_PAR(tid)
         {
-          acc = kn[L.oq + a];
-          for (int i = 0; i < NC; i++)
-            acc = fma(kn[L.oC + i * NDX + a], so[SL.oz + i], acc);
+          if (tid == 0)
+          {
+            *bad = 0;
+            bulk_init(bar);
+          }
+          for (int e = tid; e < NC * NDX; e += SMPC_NT)
+            so[SL.oZ + e] = kn[L.oC + e] * inv_mu;
+          for (int i = tid; i < NC; i += SMPC_NT)
+            so[SL.oz + i] = kn[L.od + i] * inv_mu;
         }
-        else
+        SMPC_END
+        SMPC_PAR(tid)
+        for (int e = tid; e < NDX * LDP; e += SMPC_NT)
         {
-          acc = kn[L.oQ + a * NDX + (bb - 1)];
-          for (int i = 0; i < NC; i++)
-            acc = fma(kn[L.oC + i * NDX + a], so[SL.oZ + i * NDX + (bb - 1)], acc);
+          const int a = e / LDP, bb = e % LDP;
+          double acc;
+          if (bb == 0)
+          {
+            acc = kn[L.oq + a];
+            for (int i = 0; i < NC; i++)
+              acc = fma(kn[L.oC + i * NDX + a], so[SL.oz + i], acc);
+          }
+          else
+          {
+            acc = kn[L.oQ + a * NDX + (bb - 1)];
+            for (int i = 0; i < NC; i++)
+              acc = fma(kn[L.oC + i * NDX + a], so[SL.oZ + i * NDX + (bb - 1)], acc);
+          }
+          PP[e] = acc;
         }
-        PP[e] = acc;
+        SMPC_END
       }
-      SMPC_END
       SMPC_PAR(tid)
       if (mudyn > 0)
         for (int e = tid; e < NDX * NDX; e += SMPC_NT)

@@ -727,6 +727,11 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   // wins at every batch size: five CTAs per SM hide each other's fetches (B = 512: 0.31 vs 0.46 ms, B = 4096: 1.90 vs 3.19 ms, and
   // 2.76 ms for the direct kernel that reads rows straight from global memory - profiles/r02p). The direct kernel is left for
   // shapes whose stage does not fit the shared memory of an SM. SMPC_FWD = staged | staged1 | direct overrides.
+  // the MPC tick of a batch that leaves SMs idle is latency-bound: replay it as one CUDA Graph (61 us of a 1.57 ms
+  // single-instance tick, profiles/r02r; bitwise equal results). Larger batches gain nothing and keep the per-kernel timers
+  c->use_graph = batch <= (c->hmodel_sms > 0 ? c->hmodel_sms : 148);
+  if (const char * e = getenv("SMPC_GRAPH"))
+    c->use_graph = atoi(e) != 0;
   {
     int nbuf = batch <= (c->hmodel_sms > 0 ? c->hmodel_sms : 148) ? 2 : 1;
     c->forward_staged = true;
@@ -887,6 +892,10 @@ void smpc_destroy(smpc_ctx * c)
   for (cudaEvent_t e : {c->ev0, c->ev1, c->evr0, c->evr1, c->evu0, c->evu1, c->evk[0], c->evk[1], c->evk[2], c->evk[3], c->evk[4], c->evk[5]})
     if (e)
       cudaEventDestroy(e);
+  if (c->tick_graph)
+    cudaGraphExecDestroy(c->tick_graph);
+  if (c->h_head)
+    cudaFreeHost(c->h_head);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -1045,6 +1054,7 @@ int smpc_set_warmstart(smpc_ctx * c, int first, int n, const double * xs, const 
 {
   if (check_range(c, first, n))
     return SMPC_ERR_INVALID;
+  c->head_cached = false;
   CU(cudaSetDevice(c->device));
   const Dims & d = c->A.dm;
   if (xs)
@@ -1060,6 +1070,7 @@ int smpc_shift_warmstart(smpc_ctx * c, int first, int n)
     return SMPC_ERR_INVALID;
   if (n == 0)
     return SMPC_OK;
+  c->head_cached = false;
   CU(cudaSetDevice(c->device));
   k_shift<<<n, 64, 0, c->stream>>>(c->A, first);
   c->launches++;
@@ -1080,6 +1091,91 @@ int smpc_set_x0(smpc_ctx * c, const double * x0)
   return SMPC_OK;
 }
 
+// One round of the solve up to the step direction: linearisation, decision, backward and forward sweeps. `tk`: record the
+// per-kernel CUDA events of smpc_kernel_times (never inside a stream capture)
+static int enqueue_round_head(smpc_ctx * c, bool tk)
+{
+  const Dims & d = c->A.dm;
+  cudaStream_t s = c->stream;
+  if (tk)
+    CU(cudaEventRecord(c->evk[0], s));
+  c->launch_knots(c, false);
+  if (tk)
+    CU(cudaEventRecord(c->evk[1], s));
+  k_decide<<<d.B, 64, 0, s>>>(c->A);
+  if (tk)
+    CU(cudaEventRecord(c->evr0, s));
+  c->launch_riccati(c);
+  if (tk)
+  {
+    CU(cudaEventRecord(c->evr1, s));
+    CU(cudaEventRecord(c->evk[2], s));
+  }
+  if (c->forward_staged)
+    k_forward<<<d.B, 128, (size_t)c->A.FS.size * sizeof(double), s>>>(c->A);
+  else
+    k_forward_direct<<<d.B, 64, 0, s>>>(c->A);
+  if (tk)
+    CU(cudaEventRecord(c->evk[3], s));
+  c->launches += 4;
+  return SMPC_OK;
+}
+
+// One linesearch trial: value-only knots at the trial point, the Armijo decision, the two counters to the host, and k_finish
+// (scalars -> smpc_solve_info) behind every decision: when the step is accepted and no instance needs another round - the
+// normal MPC tick - the synchronisation that follows ends the solve; otherwise the next decision's k_finish overwrites it
+static int enqueue_trial(smpc_ctx * c, bool tk)
+{
+  const Dims & d = c->A.dm;
+  cudaStream_t s = c->stream;
+  if (tk)
+    CU(cudaEventRecord(c->evk[4], s));
+  // counters: [0] instances whose linesearch needs another trial, [1] instances that need another round
+  // (both recounted by every k_ls_decide launch; the host reads the last one)
+  CU(cudaMemsetAsync(c->A.counters, 0, 2 * sizeof(int), s));
+  c->launch_knots(c, true);
+  k_ls_decide<<<d.B, 128, 0, s>>>(c->A);
+  if (tk)
+    CU(cudaEventRecord(c->evk[5], s));
+  CU(cudaMemcpyAsync(c->h_counters, c->A.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  k_finish<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
+  c->launches += 3;
+  return SMPC_OK;
+}
+
+// The round / trial loops of a solve. `resumed`: the first round and its first trial have already run (the captured tick
+// graph of smpc_mpc_iterate) and h_counters holds their outcome
+static int solve_rounds(smpc_ctx * c, int max_iters, bool resumed)
+{
+  cudaStream_t s = c->stream;
+  const int max_rounds = max_iters + c->A.opt.max_al_iters + 1;
+  int rc;
+  for (int round = 0; round < max_rounds; round++)
+  {
+    // the first round of a solve is timed kernel by kernel (CUDA events on this stream; smpc_kernel_times)
+    const bool tk = round == 0 && !resumed;
+    if (!(resumed && round == 0))
+      if ((rc = enqueue_round_head(c, tk)) != SMPC_OK)
+        return rc;
+    for (int trial = 0; trial <= c->A.opt.ls_max_steps + 1; trial++)
+    {
+      if (!(resumed && round == 0 && trial == 0))
+      {
+        if ((rc = enqueue_trial(c, tk && trial == 0)) != SMPC_OK)
+          return rc;
+        CU(cudaEventRecord(c->ev1, s));
+        CU(cudaStreamSynchronize(s));
+      }
+      if (c->h_counters[0] == 0)
+        break;
+    }
+    if (c->h_counters[1] == 0)
+      break;
+  }
+  CU(cudaGetLastError());
+  return SMPC_OK;
+}
+
 int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
 {
   if (!c)
@@ -1096,63 +1192,13 @@ int smpc_solve(smpc_ctx * c, const double * x0, int max_iters)
       return rc;
   }
   cudaStream_t s = c->stream;
+  c->head_cached = false;
   CU(cudaEventRecord(c->ev0, s));
   k_run_begin<<<d.B, 128, 0, s>>>(c->A, max_iters);
   c->launches++;
-  const int max_rounds = max_iters + c->A.opt.max_al_iters + 1;
-  bool timed_ric = false;
-  for (int round = 0; round < max_rounds; round++)
-  {
-    // the first round of a solve is timed kernel by kernel (CUDA events on this stream; smpc_kernel_times)
-    const bool tk = !timed_ric;
-    if (tk)
-      CU(cudaEventRecord(c->evk[0], s));
-    c->launch_knots(c, false);
-    if (tk)
-      CU(cudaEventRecord(c->evk[1], s));
-    k_decide<<<d.B, 64, 0, s>>>(c->A);
-    if (!timed_ric)
-      CU(cudaEventRecord(c->evr0, s));
-    c->launch_riccati(c);
-    if (!timed_ric)
-      CU(cudaEventRecord(c->evr1, s));
-    timed_ric = true;
-    if (tk)
-      CU(cudaEventRecord(c->evk[2], s));
-    if (c->forward_staged)
-      k_forward<<<d.B, 128, (size_t)c->A.FS.size * sizeof(double), s>>>(c->A);
-    else
-      k_forward_direct<<<d.B, 64, 0, s>>>(c->A);
-    if (tk)
-      CU(cudaEventRecord(c->evk[3], s));
-    c->launches += 3;
-    for (int trial = 0; trial <= c->A.opt.ls_max_steps + 1; trial++)
-    {
-      if (tk && trial == 0)
-        CU(cudaEventRecord(c->evk[4], s));
-      // counters: [0] instances whose linesearch needs another trial, [1] instances that need another round
-      // (both recounted by every k_ls_decide launch; the host reads the last one)
-      CU(cudaMemsetAsync(c->A.counters, 0, 2 * sizeof(int), s));
-      c->launch_knots(c, true);
-      k_ls_decide<<<d.B, 128, 0, s>>>(c->A);
-      c->launches++;
-      if (tk && trial == 0)
-        CU(cudaEventRecord(c->evk[5], s));
-      CU(cudaMemcpyAsync(c->h_counters, c->A.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-      // k_finish (scalars -> smpc_solve_info) rides behind every linesearch decision: when the step is accepted and no
-      // instance needs another round - the normal MPC tick - the one synchronisation below ends the solve; otherwise the
-      // next decision's k_finish overwrites what this one wrote
-      k_finish<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
-      c->launches++;
-      CU(cudaEventRecord(c->ev1, s));
-      CU(cudaStreamSynchronize(s));
-      if (c->h_counters[0] == 0)
-        break;
-    }
-    if (c->h_counters[1] == 0)
-      break;
-  }
-  CU(cudaGetLastError());
+  int rc = solve_rounds(c, max_iters, false);
+  if (rc != SMPC_OK)
+    return rc;
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   CU(cudaEventElapsedTime(&c->last_ric_ms, c->evr0, c->evr1));
   c->acc_ric_ms += c->last_ric_ms;
@@ -1231,6 +1277,24 @@ int smpc_get_head(smpc_ctx * c, int first, int n, double * x1, double * u0, doub
   const Dims & d = c->A.dm;
   const size_t N1 = d.N + 1;
   cudaStream_t s = c->stream;
+  if (c->head_cached && c->h_head)
+  {
+    // written by the tick graph (capture_tick_graph): [B][nx] | [B][nu] | [B][nu] | [B][nu * ndx]
+    const double * h = c->h_head;
+    const size_t K = (size_t)d.nu * d.ndx;
+    if (x1)
+      memcpy(x1, h + (size_t)first * d.nx, (size_t)n * d.nx * sizeof(double));
+    h += (size_t)d.B * d.nx;
+    if (u0)
+      memcpy(u0, h + (size_t)first * d.nu, (size_t)n * d.nu * sizeof(double));
+    h += (size_t)d.B * d.nu;
+    if (u1)
+      memcpy(u1, h + (size_t)first * d.nu, (size_t)n * d.nu * sizeof(double));
+    h += (size_t)d.B * d.nu;
+    if (K0)
+      memcpy(K0, h + (size_t)first * K, (size_t)n * K * sizeof(double));
+    return SMPC_OK;
+  }
   if (x1)
     CU(cudaMemcpy2DAsync(x1, d.nx * sizeof(double), c->A.xs + ((size_t)first * N1 + 1) * d.nx, N1 * d.nx * sizeof(double), d.nx * sizeof(double), n, cudaMemcpyDeviceToHost, s));
   if (u0)
@@ -1470,6 +1534,101 @@ int smpc_mpc_set_walking(smpc_ctx * c, int first, int n, int walking)
   return SMPC_OK;
 }
 
+// The device-side part of MPC::iterate up to the solve (reference src/mpc.cpp:189-209), enqueued on the context's stream
+static int enqueue_tick_driver(smpc_ctx * c)
+{
+  const Dims & d = c->A.dm;
+  cudaStream_t s = c->stream;
+  k_mpc_recede<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
+  k_cycle<<<d.B, 64, 0, s>>>(c->A, 0, nullptr, c->A.mpc_ids);
+  k_mpc_refs<<<d.B, 64, 0, s>>>(c->A);
+  k_shift<<<d.B, 64, 0, s>>>(c->A, 0);
+  c->launches += 4;
+  CU(cudaMemcpyAsync(c->h_counters + 2, c->A.counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+  return SMPC_OK;
+}
+
+static void drop_tick_graph(smpc_ctx * c)
+{
+  if (c->tick_graph)
+    cudaGraphExecDestroy(c->tick_graph);
+  c->tick_graph = nullptr;
+}
+
+// Capture the normal tick - driver kernels, k_run_begin, one round, its first linesearch trial, k_finish and the two
+// read-backs of counters - into one executable graph. The kernels take their arguments (the Arrays view) by value, so the
+// graph is re-captured whenever that view changes (stage table re-upload, smpc_mpc_setup)
+static int capture_tick_graph(smpc_ctx * c, int max_iters)
+{
+  drop_tick_graph(c);
+  const Dims & d = c->A.dm;
+  cudaStream_t s = c->stream;
+  if (!c->h_head && d.B <= 256)
+    CU(cudaMallocHost(&c->h_head, (size_t)d.B * (d.nx + 2 * d.nu + (size_t)d.nu * d.ndx) * sizeof(double)));
+  const int64_t launches0 = c->launches;
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_tick_driver(c);
+  if (rc == SMPC_OK)
+  {
+    k_run_begin<<<d.B, 128, 0, s>>>(c->A, max_iters);
+    c->launches++;
+    rc = enqueue_round_head(c, false);
+  }
+  if (rc == SMPC_OK)
+    rc = enqueue_trial(c, false);
+  if (rc == SMPC_OK && c->h_head)
+  {
+    const size_t N1 = d.N + 1, K = (size_t)d.nu * d.ndx;
+    double * h = c->h_head;
+    cudaMemcpy2DAsync(h, d.nx * sizeof(double), c->A.xs + d.nx, N1 * d.nx * sizeof(double), d.nx * sizeof(double), d.B, cudaMemcpyDeviceToHost, s);
+    h += (size_t)d.B * d.nx;
+    cudaMemcpy2DAsync(h, d.nu * sizeof(double), c->A.us, (size_t)d.N * d.nu * sizeof(double), d.nu * sizeof(double), d.B, cudaMemcpyDeviceToHost, s);
+    h += (size_t)d.B * d.nu;
+    cudaMemcpy2DAsync(h, d.nu * sizeof(double), c->A.us + d.nu, (size_t)d.N * d.nu * sizeof(double), d.nu * sizeof(double), d.B, cudaMemcpyDeviceToHost, s);
+    h += (size_t)d.B * d.nu;
+    cudaMemcpy2DAsync(h, K * sizeof(double), c->A.sol + c->A.SL.oK, N1 * c->A.SL.size * sizeof(double), K * sizeof(double), d.B, cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  c->launches = launches0; // nothing ran
+  if (rc != SMPC_OK || e != cudaSuccess)
+  {
+    if (g)
+      cudaGraphDestroy(g);
+    if (rc == SMPC_OK)
+    {
+      smpc::err() = std::string("smpc_mpc_iterate: stream capture failed: ") + cudaGetErrorString(e);
+      rc = SMPC_ERR_CUDA;
+    }
+    return rc;
+  }
+  e = cudaGraphInstantiate(&c->tick_graph, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess)
+  {
+    c->tick_graph = nullptr;
+    smpc::err() = std::string("smpc_mpc_iterate: cudaGraphInstantiate: ") + cudaGetErrorString(e);
+    return SMPC_ERR_CUDA;
+  }
+  c->tick_graph_A = c->A;
+  c->tick_graph_iters = max_iters;
+  c->tick_graph_fwd = c->forward_staged ? 1 : 0;
+  return SMPC_OK;
+}
+
+int smpc_mpc_use_graph(smpc_ctx * c, int on)
+{
+  if (!c)
+  {
+    smpc::err() = "smpc_mpc_use_graph: null context";
+    return SMPC_ERR_INVALID;
+  }
+  c->use_graph = on ? 1 : 0;
+  if (!on)
+    drop_tick_graph(c);
+  return SMPC_OK;
+}
+
 int smpc_mpc_iterate(smpc_ctx * c, const double * x_meas, int max_iters)
 {
   int rc = mpc_check(c, 0, 0, "smpc_mpc_iterate");
@@ -1480,15 +1639,34 @@ int smpc_mpc_iterate(smpc_ctx * c, const double * x_meas, int max_iters)
   cudaStream_t s = c->stream;
   if (x_meas)
     CU(cudaMemcpyAsync(c->A.xmeas, x_meas, (size_t)d.B * c->A.nxm * sizeof(double), cudaMemcpyHostToDevice, s));
-  k_mpc_recede<<<(d.B + 127) / 128, 128, 0, s>>>(c->A);
-  k_cycle<<<d.B, 64, 0, s>>>(c->A, 0, nullptr, c->A.mpc_ids);
-  k_mpc_refs<<<d.B, 64, 0, s>>>(c->A);
-  k_shift<<<d.B, 64, 0, s>>>(c->A, 0);
-  c->launches += 4;
-  CU(cudaMemcpyAsync(c->h_counters + 2, c->A.counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
-  rc = smpc_solve(c, nullptr, max_iters); // synchronises the stream
-  if (rc != SMPC_OK)
-    return rc;
+  c->head_cached = false;
+  if (c->use_graph)
+  {
+    // one graph launch and one host synchronisation per tick; a linesearch that backtracks or an instance that needs
+    // another round (both rare in MPC mode, profiles/r02m) continues on the stream below
+    if (!c->tick_graph || c->tick_graph_iters != max_iters || c->tick_graph_fwd != (c->forward_staged ? 1 : 0) ||
+        memcmp(&c->tick_graph_A, &c->A, sizeof(c->A)) != 0)
+      if ((rc = capture_tick_graph(c, max_iters)) != SMPC_OK)
+        return rc;
+    CU(cudaEventRecord(c->ev0, s));
+    CU(cudaGraphLaunch(c->tick_graph, s));
+    CU(cudaEventRecord(c->ev1, s));
+    CU(cudaStreamSynchronize(s));
+    c->launches += 12;
+    c->graph_ticks++;
+    c->head_cached = c->h_head && c->h_counters[0] == 0 && c->h_counters[1] == 0;
+    if ((rc = solve_rounds(c, max_iters, true)) != SMPC_OK)
+      return rc;
+    CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1)); // the per-kernel timers only see ticks outside the graph
+  }
+  else
+  {
+    if ((rc = enqueue_tick_driver(c)) != SMPC_OK)
+      return rc;
+    rc = smpc_solve(c, nullptr, max_iters); // synchronises the stream
+    if (rc != SMPC_OK)
+      return rc;
+  }
   if (c->h_counters[2] != 0)
   {
     smpc::err() = "smpc_mpc_iterate: a take-off / landing queue overflowed (more than SMPC_MPC_QUEUE pending events of one foot)";

@@ -215,6 +215,54 @@ def test_batched_device_driver_vs_host_mpc_on_oracle():
     assert worst["refs"] <= 1e-12 and worst["xs"] <= 3 * TOL and worst["us"] <= 3 * TOL and worst["K"] <= TOL_K, worst
 
 
+def test_tick_as_cuda_graph_is_bitwise_equal_to_plain_launches():
+    """smpc_mpc_use_graph: the captured tick (driver kernels + one round + first trial) replays the very same kernels, so two
+    contexts fed the same measured states - one with the graph, one without - agree bit for bit, including the ticks on
+    which a strongly disturbed instance backtracks (the linesearch then continues with plain launches behind the graph)."""
+    import ctypes as C
+    import numpy as np
+    from smpc_ctypes import Slot, MpcSettings, SolverOpts, load_cuda
+    cu = load_cuda()
+    B = 6
+    sc = pu.Go2Scenario(B, seed=11)
+    opts = SolverOpts()
+    cu.smpc_default_solver_opts(C.byref(opts))
+    n = len(sc.GAIT)
+    backs = []
+    for on in (0, 1):
+        b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, B)
+        table = (Slot * (n + 1))(*([sc.gait_slot(k) for k in range(n)] + [sc.gait_slot(0)]))
+        assert cu.smpc_upload_stage_table(b.ctx, table, n + 1) == 0
+        b.set_slots(sc.initial_slots())
+        b.set_terminal(sc.terminals())
+        b.set_warmstart(*sc.warmstart())
+        b.solve(np.tile(sc.xref, (B, 1)), 100)
+        st = MpcSettings(T_fly=30, T_contact=10, swing_apex=0.15, timestep=0.01, ncycle=n, standing_id=n)
+        ph = (C.c_int * B)(*[0, 11, 23, 37, 52, 64])
+        assert cu.smpc_mpc_setup(b.ctx, C.byref(st), ph, pu.P(np.array(sc.xref, float))) == 0, cu.smpc_last_error()
+        assert cu.smpc_mpc_use_graph(b.ctx, on) == 0
+        backs.append(b)
+    rng = np.random.default_rng(3)
+    x = sc.x_start()
+    trials = 0
+    for k in range(25):
+        xm = np.ascontiguousarray(x)
+        res = []
+        for b in backs:
+            assert cu.smpc_mpc_iterate(b.ctx, pu.P(xm), 1) == 0, cu.smpc_last_error()
+            xs, us, Ks, _ = b.results()
+            res.append((xs.copy(), us.copy(), Ks.copy(), [(i.num_iters, i.ls_trials, i.alpha) for i in b.info()]))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+        assert res[0][3] == res[1][3]
+        trials = max(trials, max(t[1] for t in res[1][3]))
+        x = res[1][0][:, 1].copy()
+        # velocity kicks large enough that some ticks backtrack
+        x[:, 19:] += rng.normal(0, 0.8, size=x[:, 19:].shape)
+    for b in backs:
+        b.close()
+    assert trials >= 2, "no tick backtracked: the resume path behind the graph was not exercised"
+
+
 def test_full_size_batch_4096_sampled_against_the_oracle_and_batch_properties():
     """BASELINE.json configs[4] at full size: 4096 Go2 kinodynamics instances with random phases and states. The oracle
     cannot run 4096 instances in seconds, so (1) five sampled instances (global RNG streams 0, 1, 777, 2048, 4095) are
