@@ -140,6 +140,11 @@ typedef struct smpc_solver_opts
   double reg_init, reg_min, reg_max, reg_inc_k, reg_inc_critical, reg_dec_k;
   double ls_armijo_c1, ls_alpha_min, ls_contraction, ls_avg_eta;
   int32_t ls_max_steps;
+  /* MPCSettings::num_threads (reference src/mpc.cpp:46-50): > 1 selects the PARALLEL (leg-condensed) Riccati sweep with
+   * that many legs - one CTA per leg, csrc/riccati_par.cuh - when the batch leaves SMs idle (batch x legs <= SM count)
+   * and a tuned sweep exists for the shape; throughput-bound batches always run the serial sweep (same results up to
+   * rounding either way). 0 or 1: serial. */
+  int32_t num_threads;
 } smpc_solver_opts;
 
 /* One horizon slot = what one aligator StageModel holds that simple-mpc ever mutates: the contact

@@ -73,6 +73,7 @@ void orc_default_solver_opts(smpc_solver_opts * o)
   o->ls_contraction = 0.5;
   o->ls_avg_eta = 0.85;
   o->ls_max_steps = 20;
+  o->num_threads = 1;
 }
 
 int orc_problem_dims(const smpc_model_desc * m, const smpc_ocp_desc * o, int * nx, int * ndx, int * nu)

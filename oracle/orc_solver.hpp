@@ -142,12 +142,23 @@ namespace orc
 
   // Backward sweep of the proximal Riccati recursion (gar::ProximalRiccatiSolver::backward(mudyn, mueq)).
   // knots[0..N-1] are stages, knots[N] the terminal node (Q,q,C,d only).
-  inline RiccatiStats riccati_backward(const std::vector<Knot> & knots, int ndx, int nu, double mudyn, double mueq, std::vector<StageSol> & sol)
+  // Stages [t0, t1) only when t1 >= 0; a given cost-to-go (Pterm, pterm) at node t1 replaces the terminal-node computation
+  // (the legs of riccati_backward_parallel).
+  inline RiccatiStats riccati_backward(
+    const std::vector<Knot> & knots, int ndx, int nu, double mudyn, double mueq, std::vector<StageSol> & sol, int t0 = 0, int t1 = -1,
+    const Mat * Pterm = nullptr, const Vec * pterm = nullptr)
   {
     RiccatiStats st;
-    const int N = (int)knots.size() - 1;
-    sol.resize(N + 1);
+    const int N = (t1 >= 0) ? t1 : (int)knots.size() - 1;
+    if ((int)sol.size() != (int)knots.size())
+      sol.resize(knots.size());
     const double inv_mu = 1.0 / mueq;
+    if (Pterm)
+    {
+      sol[N].P = *Pterm;
+      sol[N].p = *pterm;
+    }
+    else
     // terminal: nu_N = (d + C dx)/mu ; P = Q + C^T Z ; p = q + C^T z
     {
       const Knot & kn = knots[N];
@@ -172,7 +183,7 @@ namespace orc
         s.p[a] = acc;
       }
     }
-    for (int t = N - 1; t >= 0; t--)
+    for (int t = N - 1; t >= t0; t--)
     {
       const Knot & kn = knots[t];
       const StageSol & nx = sol[t + 1];
@@ -337,6 +348,366 @@ namespace orc
     return st;
   }
 
+  // ---- PARALLEL (leg-condensed) backward sweep: aligator's gar::ParallelRiccatiSolver, selected by the reference when
+  // num_threads > 1 (reference src/mpc.cpp:46-50), restated for one CTA per leg (simple-mpc_b200/csrc/riccati_par.cuh).
+  // The horizon is cut into J legs [a_j, a_{j+1}). With the co-state theta at the end of a leg as a parameter (cost-to-go
+  // P = 0, p = theta there) the leg's end state is affine in its start state and theta:
+  //     x_b = Psi x_a + psi - Lam theta ,   lambda_a = P_a x_a + p_a + Psi^T theta
+  // (Psi = product of the closed-loop transition matrices, Lam >= 0 the reduced dual Hessian). Four passes:
+  //   1. legs 1..J-1 in parallel: the ordinary backward sweep with zero cost-to-go at the leg end (true terminal node for the
+  //      last leg) -> gains, P~, and (P_a, p_a);
+  //   2. legs 1..J-2 in parallel: (Psi, psi, Lam) from the stored gains, stage by stage:
+  //        Pi~ = (I - mu P~) Pi+ ; Y = B^T Pi~ ; X = H Y with H = the (u,u) block of the stage's KKT inverse ;
+  //        Lam += Y^T X + mu Pi+^T Pi~ ; psi += Pi+^T [(I - mu P~)(B k + f) - mu p~] ; Pi = A^T Pi~ + K^T Y   (Pi = Psi^T)
+  //   3. serial over the J-2 inner boundaries: the TRUE cost-to-go at every leg start,
+  //        calP_j = P_j + Psi_j^T calP_{j+1} (I + Lam_j calP_{j+1})^-1 Psi_j   (and the vector part);
+  //   4. legs 0..J-2 in parallel: the ordinary backward sweep again, now from the true cost-to-go.
+  // After pass 4 `sol` holds what the serial sweep computes, up to rounding in the hand-over of calP.
+  inline void leg_bounds(int N, int J, std::vector<int> & a)
+  {
+    a.resize(J + 1);
+    for (int j = 0; j <= J; j++)
+      a[j] = (int)(((long long)j * N) / J);
+  }
+  // LU with partial pivoting, in place; solves M X = R for the m columns of R (row-major), returns false if singular
+  inline bool lu_solve(Mat & M, int n, Mat & R, int m)
+  {
+    for (int k = 0; k < n; k++)
+    {
+      int piv = k;
+      double best = std::fabs(M(k, k));
+      for (int i = k + 1; i < n; i++)
+        if (std::fabs(M(i, k)) > best)
+          best = std::fabs(M(i, k)), piv = i;
+      if (best == 0.0)
+        return false;
+      if (piv != k)
+      {
+        for (int j = 0; j < n; j++)
+          std::swap(M(k, j), M(piv, j));
+        for (int j = 0; j < m; j++)
+          std::swap(R(k, j), R(piv, j));
+      }
+      const double inv = 1.0 / M(k, k);
+      for (int i = k + 1; i < n; i++)
+      {
+        const double l = M(i, k) * inv;
+        M(i, k) = l;
+        for (int j = k + 1; j < n; j++)
+          M(i, j) = std::fma(-l, M(k, j), M(i, j));
+        for (int j = 0; j < m; j++)
+          R(i, j) = std::fma(-l, R(k, j), R(i, j));
+      }
+    }
+    for (int k = n - 1; k >= 0; k--)
+    {
+      const double inv = 1.0 / M(k, k);
+      for (int j = 0; j < m; j++)
+      {
+        double acc = R(k, j);
+        for (int i = k + 1; i < n; i++)
+          acc = std::fma(-M(k, i), R(i, j), acc);
+        R(k, j) = acc * inv;
+      }
+    }
+    return true;
+  }
+  struct LegElement
+  {
+    Mat Pi, Lam; // Pi = Psi^T
+    Vec psi;
+  };
+  // pass 2 for the leg [a, b): reads the gains the zero-terminal sweep left in sol
+  inline bool leg_element(
+    const std::vector<Knot> & knots, const std::vector<StageSol> & sol, int ndx, int nu, double mudyn, double mueq, int a, int b,
+    LegElement & E)
+  {
+    bool ok = true;
+    E.Pi.resize(ndx, ndx);
+    E.Lam.resize(ndx, ndx);
+    E.psi.assign(ndx, 0.0);
+    for (int i = 0; i < ndx; i++)
+      E.Pi(i, i) = 1.0;
+    Mat Pit(ndx, ndx), Y(nu, ndx), X(nu, ndx), PB(ndx, nu), Rh(nu, nu), Pin(ndx, ndx);
+    Vec v(ndx), phi(ndx);
+    for (int t = b - 1; t >= a; t--)
+    {
+      const Knot & kn = knots[t];
+      const StageSol & s = sol[t];
+      const int nc = kn.nc;
+      // Pi~ = (I + mu P+)^-1 Pi+ = Pi+ - mu P~ Pi+ (measured: as accurate here as solving with the factor of I + mu P+)
+      for (int i = 0; i < ndx; i++)
+        for (int j = 0; j < ndx; j++)
+        {
+          double acc = 0.0;
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(s.Pt(i, k), E.Pi(k, j), acc);
+          Pit(i, j) = std::fma(-mudyn, acc, E.Pi(i, j));
+        }
+      // Y = B^T Pi~
+      for (int i = 0; i < nu; i++)
+        for (int j = 0; j < ndx; j++)
+        {
+          double acc = 0.0;
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(kn.B(k, i), Pit(k, j), acc);
+          Y(i, j) = acc;
+        }
+      // R^ = R + B^T P~ B = L L^T
+      PB.zero();
+      add_AB(s.Pt, kn.B, ndx, ndx, nu, PB);
+      Rh = kn.R;
+      add_AtB(kn.B, PB, ndx, nu, nu, Rh);
+      if (!chol_lower(Rh, nu))
+        ok = false;
+      // X = H Y, H = L^-T (I - W (mu I + W^T W)^-1 W^T) L^-1, W = L^-1 D^T
+      X = Y;
+      solve_lower(Rh, nu, X, ndx);
+      if (nc > 0)
+      {
+        Mat W(nu, nc), Sg(nc, nc), G(nc, ndx);
+        for (int i = 0; i < nu; i++)
+          for (int c = 0; c < nc; c++)
+            W(i, c) = kn.D(c, i);
+        solve_lower(Rh, nu, W, nc);
+        for (int i = 0; i < nc; i++)
+          for (int j = 0; j < nc; j++)
+          {
+            double acc = (i == j) ? mueq : 0.0;
+            for (int k = 0; k < nu; k++)
+              acc = std::fma(W(k, i), W(k, j), acc);
+            Sg(i, j) = acc;
+          }
+        if (!chol_lower(Sg, nc))
+          ok = false;
+        for (int i = 0; i < nc; i++)
+          for (int j = 0; j < ndx; j++)
+          {
+            double acc = 0.0;
+            for (int k = 0; k < nu; k++)
+              acc = std::fma(W(k, i), X(k, j), acc);
+            G(i, j) = acc;
+          }
+        solve_lower(Sg, nc, G, ndx);
+        solve_lower_T(Sg, nc, G, ndx);
+        for (int i = 0; i < nu; i++)
+          for (int j = 0; j < ndx; j++)
+          {
+            double acc = X(i, j);
+            for (int c = 0; c < nc; c++)
+              acc = std::fma(-W(i, c), G(c, j), acc);
+            X(i, j) = acc;
+          }
+      }
+      solve_lower_T(Rh, nu, X, ndx);
+      // Lam += Y^T X + mu Pi+^T Pi~
+      for (int i = 0; i < ndx; i++)
+        for (int j = 0; j < ndx; j++)
+        {
+          double acc = E.Lam(i, j);
+          for (int k = 0; k < nu; k++)
+            acc = std::fma(Y(k, i), X(k, j), acc);
+          double acc2 = 0.0;
+          for (int k = 0; k < ndx; k++)
+            acc2 = std::fma(E.Pi(k, i), Pit(k, j), acc2);
+          E.Lam(i, j) = std::fma(mudyn, acc2, acc);
+        }
+      // psi += Pi+^T phi, phi = (I - mu P~)(B k + f) - mu p~
+      for (int i = 0; i < ndx; i++)
+      {
+        double acc = kn.f[i];
+        for (int k = 0; k < nu; k++)
+          acc = std::fma(kn.B(i, k), s.k[k], acc);
+        v[i] = acc;
+      }
+      for (int i = 0; i < ndx; i++)
+      {
+        double acc = s.pt[i];
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(s.Pt(i, k), v[k], acc);
+        phi[i] = std::fma(-mudyn, acc, v[i]);
+      }
+      for (int i = 0; i < ndx; i++)
+      {
+        double acc = E.psi[i];
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(E.Pi(k, i), phi[k], acc);
+        E.psi[i] = acc;
+      }
+      // Pi = A^T Pi~ + K^T Y
+      for (int i = 0; i < ndx; i++)
+        for (int j = 0; j < ndx; j++)
+        {
+          double acc = 0.0;
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(kn.A(k, i), Pit(k, j), acc);
+          for (int k = 0; k < nu; k++)
+            acc = std::fma(s.K(k, i), Y(k, j), acc);
+          Pin(i, j) = acc;
+        }
+      E.Pi = Pin;
+    }
+    for (int i = 0; i < ndx; i++)
+      for (int j = 0; j < i; j++)
+      {
+        const double m = 0.5 * (E.Lam(i, j) + E.Lam(j, i));
+        E.Lam(i, j) = m;
+        E.Lam(j, i) = m;
+      }
+    return ok;
+  }
+  // pass 3, one boundary: cost-to-go (Pn, pn) at the end of a leg with element E and start values (Pa, pa) -> (P, p) at its start
+  inline bool leg_condense(const LegElement & E, const Mat & Pa, const Vec & pa, const Mat & Pn, const Vec & pn, int ndx, Mat & P, Vec & p)
+  {
+    // Pn (I + Lam Pn)^-1 = C (I + C^T Lam C)^-1 C^T with Pn = C C^T: symmetric positive definite all the way (measured: gains
+    // within 1e-9 of the serial sweep for 3 to 10 legs; the LU form below, kept for a cost-to-go that is only semi-definite,
+    // loses a digit or two to the 1/mu stiffness of the penalised directions)
+    {
+      // S = I + C^T Lam C ; T = C S^-1 C^T [Psi | psi - Lam pn] (+ pn)
+      Mat Cc = Pn;
+      if (chol_lower(Cc, ndx))
+      {
+        for (int i = 0; i < ndx; i++)
+          for (int j = i + 1; j < ndx; j++)
+            Cc(i, j) = 0.0;
+        Mat LC(ndx, ndx), S(ndx, ndx), R(ndx, ndx + 1), U(ndx, ndx + 1), T(ndx, ndx + 1);
+        add_AB(E.Lam, Cc, ndx, ndx, ndx, LC);
+        for (int i = 0; i < ndx; i++)
+          S(i, i) = 1.0;
+        add_AtB(Cc, LC, ndx, ndx, ndx, S);
+        for (int i = 0; i < ndx; i++)
+          for (int j = 0; j < i; j++)
+            S(i, j) = S(j, i) = 0.5 * (S(i, j) + S(j, i));
+        chol_lower(S, ndx);
+        for (int i = 0; i < ndx; i++)
+        {
+          for (int j = 0; j < ndx; j++)
+            R(i, j) = E.Pi(j, i);
+          double acc = E.psi[i];
+          for (int k = 0; k < ndx; k++)
+            acc = std::fma(-E.Lam(i, k), pn[k], acc);
+          R(i, ndx) = acc;
+        }
+        add_AtB(Cc, R, ndx, ndx, ndx + 1, U);
+        solve_lower(S, ndx, U, ndx + 1);
+        solve_lower_T(S, ndx, U, ndx + 1);
+        add_AB(Cc, U, ndx, ndx, ndx + 1, T);
+        for (int i = 0; i < ndx; i++)
+          T(i, ndx) += pn[i];
+        P.resize(ndx, ndx);
+        p.assign(ndx, 0.0);
+        for (int i = 0; i < ndx; i++)
+          for (int j = 0; j <= ndx; j++)
+          {
+            double acc = (j == ndx) ? pa[i] : Pa(i, j);
+            for (int k = 0; k < ndx; k++)
+              acc = std::fma(E.Pi(i, k), T(k, j), acc);
+            if (j == ndx)
+              p[i] = acc;
+            else
+              P(i, j) = acc;
+          }
+        for (int i = 0; i < ndx; i++)
+          for (int j = 0; j < i; j++)
+          {
+            const double m = 0.5 * (P(i, j) + P(j, i));
+            P(i, j) = m;
+            P(j, i) = m;
+          }
+        return true;
+      }
+    }
+    // M = I + Lam Pn ; [Xi | xi] = M^-1 [Psi | psi - Lam pn]
+    Mat M(ndx, ndx), R(ndx, ndx + 1);
+    for (int i = 0; i < ndx; i++)
+      for (int j = 0; j < ndx; j++)
+      {
+        double acc = (i == j) ? 1.0 : 0.0;
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(E.Lam(i, k), Pn(k, j), acc);
+        M(i, j) = acc;
+      }
+    for (int i = 0; i < ndx; i++)
+    {
+      for (int j = 0; j < ndx; j++)
+        R(i, j) = E.Pi(j, i);
+      double acc = E.psi[i];
+      for (int k = 0; k < ndx; k++)
+        acc = std::fma(-E.Lam(i, k), pn[k], acc);
+      R(i, ndx) = acc;
+    }
+    if (!lu_solve(M, ndx, R, ndx + 1))
+      return false;
+    // T = Pn [Xi | xi] (+ pn on the vector column) ; [P | p] = [Pa | pa] + Psi^T T
+    Mat T(ndx, ndx + 1);
+    for (int i = 0; i < ndx; i++)
+      for (int j = 0; j <= ndx; j++)
+      {
+        double acc = (j == ndx) ? pn[i] : 0.0;
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(Pn(i, k), R(k, j), acc);
+        T(i, j) = acc;
+      }
+    P.resize(ndx, ndx);
+    p.assign(ndx, 0.0);
+    for (int i = 0; i < ndx; i++)
+      for (int j = 0; j <= ndx; j++)
+      {
+        double acc = (j == ndx) ? pa[i] : Pa(i, j);
+        for (int k = 0; k < ndx; k++)
+          acc = std::fma(E.Pi(i, k), T(k, j), acc);
+        if (j == ndx)
+          p[i] = acc;
+        else
+          P(i, j) = acc;
+      }
+    for (int i = 0; i < ndx; i++)
+      for (int j = 0; j < i; j++)
+      {
+        const double m = 0.5 * (P(i, j) + P(j, i));
+        P(i, j) = m;
+        P(j, i) = m;
+      }
+    return true;
+  }
+  inline int riccati_legs_used(int N, int J) { return (J >= 2 && N >= 2 * J) ? J : 1; }
+  inline RiccatiStats riccati_backward_parallel(
+    const std::vector<Knot> & knots, int ndx, int nu, double mudyn, double mueq, std::vector<StageSol> & sol, int J)
+  {
+    const int N = (int)knots.size() - 1;
+    if (riccati_legs_used(N, J) < 2)
+      return riccati_backward(knots, ndx, nu, mudyn, mueq, sol);
+    RiccatiStats st;
+    std::vector<int> a;
+    leg_bounds(N, J, a);
+    sol.resize(N + 1);
+    Mat Zero(ndx, ndx);
+    Vec zero(ndx, 0.0);
+    std::vector<Mat> P0(J), PT(J);
+    std::vector<Vec> p0(J), pT(J);
+    for (int j = 1; j < J; j++) // pass 1
+    {
+      const bool last = j == J - 1;
+      if (!riccati_backward(knots, ndx, nu, mudyn, mueq, sol, a[j], a[j + 1], last ? nullptr : &Zero, last ? nullptr : &zero).ok)
+        st.ok = false;
+      P0[j] = sol[a[j]].P;
+      p0[j] = sol[a[j]].p;
+    }
+    std::vector<LegElement> E(J);
+    for (int j = 1; j < J - 1; j++) // pass 2
+      if (!leg_element(knots, sol, ndx, nu, mudyn, mueq, a[j], a[j + 1], E[j]))
+        st.ok = false;
+    PT[J - 1] = P0[J - 1]; // pass 3
+    pT[J - 1] = p0[J - 1];
+    for (int j = J - 2; j >= 1; j--)
+      if (!leg_condense(E[j], P0[j], p0[j], PT[j + 1], pT[j + 1], ndx, PT[j], pT[j]))
+        st.ok = false;
+    for (int j = J - 2; j >= 0; j--) // pass 4
+      if (!riccati_backward(knots, ndx, nu, mudyn, mueq, sol, a[j], a[j + 1], &PT[j + 1], &pT[j + 1]).ok)
+        st.ok = false;
+    return st;
+  }
+
   // Forward sweep: dx0 given (0 with force_initial_condition). Outputs steps dx, du and the TOTAL new
   // multipliers nu+ (per stage, plus terminal) and lambda+ (lam[0] initial condition, lam[t+1] dynamics t).
   inline void riccati_forward(
@@ -466,10 +837,12 @@ namespace orc
     // wall-clock split of run() for the timed CPU baseline: [0] linearisation, [1] Riccati backward, [2] forward sweep,
     // [3] linesearch trials (values only), seconds accumulated since construction
     double timers[4] = {0, 0, 0, 0};
+    int riccati_legs = 1; // > 1: PARALLEL (leg-condensed) backward sweep (smpc_solver_opts::num_threads)
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     Solver(const smpc_model_desc & md, const smpc_ocp_desc & od, const smpc_solver_opts & so) : P(md, od), opt(so)
     {
+      riccati_legs = so.num_threads > 1 ? so.num_threads : 1;
       N = P.N;
       nx = P.nx;
       ndx = P.ndx;
@@ -783,7 +1156,7 @@ namespace orc
         }
         // Newton step of the proximal subproblem
         tm0 = now();
-        if (!riccati_backward(knots, ndx, nu, mu, mu, sol).ok)
+        if (!(riccati_legs > 1 ? riccati_backward_parallel(knots, ndx, nu, mu, mu, sol, riccati_legs) : riccati_backward(knots, ndx, nu, mu, mu, sol)).ok)
           info.flags |= 1;
         timers[1] += now() - tm0;
         tm0 = now();

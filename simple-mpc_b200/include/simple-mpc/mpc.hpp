@@ -21,7 +21,7 @@ namespace simple_mpc
     double TOL = 1e-4;
     double mu_init = 1e-8;
     std::size_t max_iters = 1;
-    std::size_t num_threads = 2; // kept for source compatibility: the GPU solve has no thread-count knob
+    std::size_t num_threads = 2; // > 1: PARALLEL Riccati with that many legs (reference src/mpc.cpp:46-50)
     int T_fly = 80;
     int T_contact = 20;
     size_t T = 100;
@@ -50,6 +50,8 @@ namespace simple_mpc
     SolverProxDDP(const SolverProxDDP &) = delete;
     SolverProxDDP & operator=(const SolverProxDDP &) = delete;
 
+    /// aligator SolverProxDDP::setNumThreads + linear_solver_choice = PARALLEL when n > 1 (reference src/mpc.cpp:46-50)
+    void setNumThreads(std::size_t n) { opts_.num_threads = (int)n; }
     /// allocate the device-resident solver state for this problem (aligator SolverProxDDP::setup)
     void setup(const OCPHandler & ocp);
     /// one ProxDDP run from the warm start (xs_init, us_init); returns the convergence flag

@@ -59,7 +59,7 @@ class SolverOpts(C.Structure):
         ("reg_init", C.c_double), ("reg_min", C.c_double), ("reg_max", C.c_double), ("reg_inc_k", C.c_double),
         ("reg_inc_critical", C.c_double), ("reg_dec_k", C.c_double),
         ("ls_armijo_c1", C.c_double), ("ls_alpha_min", C.c_double), ("ls_contraction", C.c_double),
-        ("ls_avg_eta", C.c_double), ("ls_max_steps", C.c_int32),
+        ("ls_avg_eta", C.c_double), ("ls_max_steps", C.c_int32), ("num_threads", C.c_int32),
     ]
 
 

@@ -174,9 +174,10 @@ namespace simple_mpc
     x0_ = ocp_handler_->getProblemState(*data_handler_);
     x_reference_ = ocp_handler_->getReferenceState(0);
 
-    // LINEAR rollout, serial Riccati and force_initial_condition are what the CUDA solver implements
-    // (reference src/mpc.cpp:43-53); num_threads has no meaning on the GPU
+    // LINEAR rollout and force_initial_condition are what the CUDA solver implements (reference src/mpc.cpp:43-53);
+    // num_threads > 1 selects the PARALLEL (leg-condensed) Riccati sweep with that many legs, as in the reference (:46-50)
     solver_ = std::make_unique<SolverProxDDP>(settings_.TOL, settings_.mu_init, maxiters, api);
+    solver_->setNumThreads(settings_.num_threads);
 
     ee_names_ = model_handler.getFeetFrameNames();
     VectorXd force_ref(ocp_handler_->getReferenceForce(0, model_handler.getFootFrameName(0)));

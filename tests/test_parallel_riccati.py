@@ -1,0 +1,51 @@
+"""PARALLEL (leg-condensed) Riccati sweep, reference src/mpc.cpp:46-50 (num_threads > 1 -> LQSolverChoice::PARALLEL).
+CPU part: the oracle's leg-parallel sweep (oracle/orc_solver.hpp: riccati_backward_parallel) against its serial sweep on
+whole MPC runs - the two must agree to the amplified-rounding floor of the serial recursion itself."""
+import ctypes as C
+import numpy as np
+import pytest
+import parity_utils as pu
+from smpc_ctypes import SolverOpts
+from oracle_libs import load_oracle
+
+
+def _run(orc, sc, legs, ticks, batch):
+    opts = SolverOpts()
+    orc.orc_default_solver_opts(C.byref(opts))
+    opts.num_threads = legs
+    b = pu.Backend(orc, "orc", sc.model, sc.ocpb, opts, batch)
+    out = []
+    try:
+        b.set_slots(sc.initial_slots())
+        b.set_terminal(sc.terminals())
+        b.set_warmstart(*sc.warmstart())
+        x = np.tile(sc.xref, (batch, 1))
+        b.solve(x, 100)
+        out.append(tuple(np.array(a) for a in b.results()) + ([(i.num_iters, i.ls_trials, i.alpha) for i in b.info()],))
+        for tick in range(ticks):
+            x = sc.disturb(out[-1][0][:, 1, :].copy(), tick)
+            b.cycle(sc.tails(tick))
+            b.shift()
+            b.solve(x, 1)
+            out.append(tuple(np.array(a) for a in b.results()) + ([(i.num_iters, i.ls_trials, i.alpha) for i in b.info()],))
+    finally:
+        b.close()
+    return out
+
+
+@pytest.mark.parametrize("legs", [2, 3, 5, 10])
+def test_oracle_parallel_sweep_equals_the_serial_sweep(legs):
+    orc = load_oracle()
+    sc = pu.Go2Scenario(1, 3)
+    ser = _run(orc, pu.Go2Scenario(1, 3), 1, 3, 1)  # a scenario draws its disturbances from its own generator: one per run
+    par = _run(orc, pu.Go2Scenario(1, 3), legs, 3, 1)
+    worst = dict(xs=0.0, us=0.0, K=0.0)
+    for (xs, us, Ks, ks, inf), (xp, up, Kp, kp, infp) in zip(ser, par):
+        assert inf == infp
+        worst["xs"] = max(worst["xs"], pu.relerr(xp, xs))
+        worst["us"] = max(worst["us"], pu.relerr(up, us))
+        worst["K"] = max(worst["K"], max(pu.relerr(Kp[0, t], Ks[0, t]) for t in range(sc.T)))
+    if legs == 2:
+        # two legs are the serial sweep cut in two: the hand-over of the cost-to-go is exact
+        assert worst == dict(xs=0.0, us=0.0, K=0.0), worst
+    assert worst["xs"] <= 1e-8 and worst["us"] <= 1e-8 and worst["K"] <= 1e-7, worst
