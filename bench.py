@@ -129,10 +129,11 @@ def make_scenario(cfg, batch, seed, first=0):
     return getattr(scn, CONFIGS[cfg]["scenario"])(batch, seed=seed, first=first)
 
 
-def setup_backend(lib, prefix, sc, batch, device=0):
+def setup_backend(lib, prefix, sc, batch, device=0, num_threads=1):
     """constructor of MPC for every instance: problem, stage table, constructor solve, driver state"""
     opts = SolverOpts()
     getattr(lib, prefix + "_default_solver_opts")(C.byref(opts))
+    opts.num_threads = num_threads  # > 1: PARALLEL (leg-condensed) Riccati sweep with that many legs (reference src/mpc.cpp:46-50)
     b = scn.Backend(lib, prefix, sc.model, sc.ocpb, opts, batch, device)
     table, n = sc.stage_table()  # cycle stages + the standing stage
     rc = getattr(lib, prefix + "_upload_stage_table")(b.ctx, table, n + 1)
@@ -438,6 +439,35 @@ def main():
         out["latency_ms"]["cuda_graph"] = {"p50": float(np.percentile(latg, 50)), "p99": float(np.percentile(latg, 99)),
                                            "what": "same loop, smpc_mpc_use_graph(1) - the default for batches up to the SM count: one graph launch per tick, the head of the plan copied to pinned memory by the graph"}
         b1.close()
+        # MPCSettings::num_threads > 1 = the PARALLEL (leg-condensed) Riccati sweep, one CTA per leg (csrc/riccati_par.cuh)
+        par = []
+        for legs in (5, 10):
+            scp = make_scenario(cfg, 1, seed=0)
+            bp = setup_backend(cu, "smpc", scp, 1, local_rank, num_threads=legs)
+            used = cu.smpc_riccati_legs(bp.ctx)
+            if used > 1:
+                xp = np.ascontiguousarray(scp.xmeas_start())
+                for graph in (0, 1):
+                    assert cu.smpc_mpc_use_graph(bp.ctx, graph) == 0
+                    cu.smpc_timer_stats(bp.ctx, 1, None, None, None, None)
+                    latp = []
+                    for k in range(220):
+                        t1 = time.perf_counter()
+                        assert cu.smpc_mpc_iterate(bp.ctx, P(xp), 1) == 0, cu.smpc_last_error()
+                        h = bp.head()[0]
+                        latp.append(time.perf_counter() - t1)
+                        xp = np.ascontiguousarray(scp.next_measurement(xp, h, None))
+                    latp = np.array(latp[20:]) * 1e3
+                    if graph == 0:
+                        kp, npk = (C.c_double * 4)(), C.c_int64()
+                        cu.smpc_kernel_times(bp.ctx, kp)
+                        cu.smpc_timer_stats(bp.ctx, 0, None, None, None, C.byref(npk))
+                        ric_ms = kp[1] / max(npk.value, 1)
+                    else:
+                        par.append({"legs": used, "p50": float(np.percentile(latp, 50)), "p99": float(np.percentile(latp, 99)),
+                                    "riccati_device_ms": ric_ms})
+            bp.close()
+        out["latency_ms"]["parallel_riccati"] = {"what": "same loop (one graph launch per tick) with smpc_solver_opts.num_threads = legs: four launches per backward sweep, one CTA per leg; riccati_device_ms from the event timers of the plain-launch loop", "rows": par}
     if solo and not args.no_latency and cfg == "c5":
         # north_star target: 4096 instances at >= 100 Hz on 8 GPUs = 512 instances per GPU with a tick <= 10 ms.
         # Ticks of a 512-instance context on this one GPU, end to end through host buffers (the 8-GPU run itself is

@@ -289,6 +289,8 @@ int smpc_mpc_iterate(smpc_ctx *, const double * x_meas, int max_iters);
  * without a second synchronisation. Default: on when the batch does not exceed the SM count (latency-bound ticks), off
  * otherwise; the environment variable SMPC_GRAPH=0|1 at smpc_create overrides. */
 int smpc_mpc_use_graph(smpc_ctx *, int on);
+/* legs of the PARALLEL Riccati sweep this context runs (1 = serial), see smpc_solver_opts::num_threads */
+int smpc_riccati_legs(smpc_ctx *);
 /* closed loop without a plant (multibody problem states only): x_meas <- predicted xs[1], device to device */
 int smpc_mpc_xmeas_from_prediction(smpc_ctx *);
 /* replaces: getFootTakeoffCycle / getFootLandCycle      (reference include/simple-mpc/mpc.hpp:141-164)

@@ -178,6 +178,8 @@ PYBIND11_MODULE(simple_mpc, m)
     .def_readwrite("lowerPositionLimit", &Model::lowerPositionLimit)
     .def_readwrite("upperPositionLimit", &Model::upperPositionLimit)
     .def_readwrite("effortLimit", &Model::effortLimit)
+    .def_readwrite("friction", &Model::friction)
+    .def_readwrite("damping", &Model::damping)
     .def_readonly("frames", &Model::frames)
     .def(
       "addFreeFlyer",
@@ -335,6 +337,18 @@ PYBIND11_MODULE(simple_mpc, m)
     .def_readwrite("target_tol", &SolverProxDDP::target_tol_)
     .def_readwrite("mu_init", &SolverProxDDP::mu_init)
     .def_readonly("results", &SolverProxDDP::results_);
+
+  // FrictionCompensation (reference bindings/expose-friction-compensation.cpp): computeFriction returns the corrected torque
+  py::class_<FrictionCompensation>(m, "FrictionCompensation")
+    .def(py::init<const Model &, bool>(), py::arg("model"), py::arg("with_free_flyer") = true)
+    .def("computeFriction",
+         [](FrictionCompensation & self, const VectorXd & velocity, VectorXd torque) {
+           self.computeFriction(velocity, torque);
+           return torque;
+         })
+    .def_readonly("nu", &FrictionCompensation::nu_)
+    .def_readonly("dry_friction", &FrictionCompensation::dry_friction_)
+    .def_readonly("viscuous_friction", &FrictionCompensation::viscuous_friction_);
 
   // Interpolator (reference bindings/expose-interpolate.cpp:20-62): each method (delay, timestep, list) -> value
   py::class_<Interpolator>(m, "Interpolator")

@@ -11,6 +11,7 @@
 #include "simple-mpc/kinodynamics.hpp"
 #include "simple-mpc/mpc.hpp"
 #include "simple-mpc/interpolator.hpp"
+#include "simple-mpc/friction-compensation.hpp"
 
 namespace pybind11
 {

@@ -5,6 +5,7 @@
 #pragma once
 #include "kino_knot.cuh" // KnotIO
 #include "riccati.cuh"
+#include "riccati_par.cuh"
 #include "riccati_fwd.cuh"
 #include "mpc_driver.cuh"
 #include <cuda_runtime.h>
@@ -63,6 +64,13 @@ namespace smpc
     int * mpc_ids;  // [B] stage-table index of the tail each instance appends this tick
     double * xmeas; // [B][nq + nv] measured multibody states
     int nxm, ncycle;
+    // PARALLEL (leg-condensed) Riccati sweep, riccati_par.cuh; legs <= 1: serial sweep, pointers null
+    int legs;
+    ParSmem PS;
+    CoarseSmem CS;
+    double *legP0, *legT; // [B][legs][ndx (ndx + 1)]: (P_a, p_a) of the zero-terminal sweeps / true cost-to-go at the leg starts
+    double * legE;        // [B][legs][leg_elem_size]: Pi, Lam, psi of the inner legs
+    const double * legZero; // ndx (ndx + 1) zeros: the cost-to-go of pass 1
   };
 
   __device__ __forceinline__ const smpc_slot & slot_at(const Arrays & A, const InstState & st, int b, int t)
@@ -146,6 +154,8 @@ struct smpc_ctx
   int knot_threads = 32;
   void (*launch_knots)(smpc_ctx *, bool trial) = nullptr;
   void (*launch_riccati)(smpc_ctx *) = nullptr;
+  // pass 1 / pass 4 of the leg-parallel sweep with the tuned kernel of this shape (null: the shape has no tuned sweep)
+  void (*launch_riccati_legs)(smpc_ctx *, int pass) = nullptr;
   const char * riccati_variant = "generic";
   std::vector<smpc_slot> h_table; // host copy of the stage table (contact masks drive the driver's bookkeeping)
   MpcShared h_mpc;

@@ -8,9 +8,9 @@ namespace smpc
   {
     *found = true;
     if (ndx == 9 && nu == 12 && ncmax == 34)
-      return setup_riccati4<12, 12, 34, 128, 9>(c, "two-column-padded");
+      return setup_riccati4<12, 12, 34, 128, 9, true>(c, "two-column-padded");
     if (ndx == 9 && nu == 12 && ncmax == 8)
-      return setup_riccati4<12, 12, 8, 128, 9>(c, "two-column-padded");
+      return setup_riccati4<12, 12, 8, 128, 9, true>(c, "two-column-padded");
     *found = false;
     return SMPC_OK;
   }

@@ -10,7 +10,7 @@ namespace smpc
     bool wide = c->hmodel_sms > 0 && c->A.dm.B <= c->hmodel_sms;
     if (const char * e = getenv("SMPC_RIC_TPB"))
       wide = atoi(e) == 256;
-    return wide ? setup_riccati4<NDX, NU, NC, 256>(c, "two-column-256") : setup_riccati4<NDX, NU, NC, 128>(c, "two-column");
+    return wide ? setup_riccati4<NDX, NU, NC, 256, NDX, (NU == 12)>(c, "two-column-256") : setup_riccati4<NDX, NU, NC, 128>(c, "two-column");
   }
   int setup_ric4_go2(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found)
   {

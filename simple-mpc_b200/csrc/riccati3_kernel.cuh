@@ -46,6 +46,29 @@ namespace smpc
       st.flags |= 1;
   }
 
+  // One CTA per LEG of the PARALLEL sweep (riccati_par.cuh): grid = B x (legs - 1). pass 1: legs 1..J-1 from a zero cost-to-go
+  // (the true terminal node for the last leg), (P_a, p_a) to legP0; pass 4: legs 0..J-2 from the true cost-to-go legT[j + 1]
+  template <int NDX, int NU, int NC, int TPB, int SNV, bool DZ>
+  __global__ void __launch_bounds__(TPB, (ric3_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati3_legs(Arrays A, int pass)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const Dims & d = A.dm;
+    const int J = A.legs, b = blockIdx.x / (J - 1), j = blockIdx.x % (J - 1) + (pass == 1 ? 1 : 0);
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const int a0 = leg_begin(d.N, J, j), a1 = leg_begin(d.N, J, j + 1);
+    const size_t xb = (size_t)b * (d.N + 1) + a0;
+    const size_t pp = leg_pp_size(d.ndx);
+    const double * Pterm = pass == 1 ? (j == J - 1 ? nullptr : A.legZero) : A.legT + ((size_t)b * J + j + 1) * pp;
+    double * P0 = (pass != 1 && j == 0) ? A.P0 + (size_t)b * pp : A.legP0 + ((size_t)b * J + j) * pp;
+    __shared__ int flag;
+    riccati3_backward_inst<NDX, NU, NC, TPB, SNV, DZ>(
+      A.L, A.SL, a1 - a0, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag, P0, Pterm);
+    if (threadIdx.x == 0 && flag)
+      atomicOr(&st.flags, 1);
+  }
+
   // Wave model of the Riccati launch: an instance takes t[k] when k CTAs share its SM (measured on B200 for the
   // (36, 24, 24) sweep, relative units); `batch` instances run as full waves of k * sms CTAs plus a remainder that
   // runs at the occupancy it reaches.
@@ -79,11 +102,23 @@ namespace smpc
     k_riccati3<NDX, NU, NC, TPB, SNV, DZ><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
   }
   template <int NDX, int NU, int NC, int TPB, int SNV, bool DZ>
+  void launch_riccati3_legs_impl(smpc_ctx * c, int pass)
+  {
+    k_riccati3_legs<NDX, NU, NC, TPB, SNV, DZ><<<c->A.dm.B * (c->A.legs - 1), TPB, c->ric_smem, c->stream>>>(c->A, pass);
+  }
+  template <int NDX, int NU, int NC, int TPB, int SNV, bool DZ>
   int finish_setup_riccati3(smpc_ctx * c)
   {
     CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV, DZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
     CU(cudaFuncSetAttribute(k_riccati3<NDX, NU, NC, TPB, SNV, DZ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->launch_riccati = &launch_riccati3_impl<NDX, NU, NC, TPB, SNV, DZ>;
+    if constexpr (TPB == 256)
+    {
+      // the leg-parallel sweep only runs when SMs are idle, i.e. where the latency variant is selected
+      CU(cudaFuncSetAttribute(k_riccati3_legs<NDX, NU, NC, TPB, SNV, DZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+      CU(cudaFuncSetAttribute(k_riccati3_legs<NDX, NU, NC, TPB, SNV, DZ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      c->launch_riccati_legs = &launch_riccati3_legs_impl<NDX, NU, NC, TPB, SNV, DZ>;
+    }
     c->riccati_variant = SNV ? (DZ ? (TPB == 128 ? "tma-staged-kinostruct-D0" : "tma-staged-kinostruct-D0-256")
                                    : (TPB == 128 ? "tma-staged-kinostruct" : "tma-staged-kinostruct-256"))
                              : (TPB == 128 ? "tma-staged" : "tma-staged-256");

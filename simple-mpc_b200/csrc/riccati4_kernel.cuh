@@ -35,12 +35,40 @@ namespace smpc
     if (threadIdx.x == 0 && flag)
       st.flags |= 1;
   }
+  // one CTA per leg of the PARALLEL sweep, see k_riccati3_legs
+  template <int NDX, int NU, int NC, int TPB, int GN>
+  __global__ void __launch_bounds__(TPB, (ric4_ctas_per_sm<NDX, NU, NC, TPB>())) k_riccati4_legs(Arrays A, int pass)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const Dims & d = A.dm;
+    const int J = A.legs, b = blockIdx.x / (J - 1), j = blockIdx.x % (J - 1) + (pass == 1 ? 1 : 0);
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const int a0 = leg_begin(d.N, J, j), a1 = leg_begin(d.N, J, j + 1);
+    const size_t xb = (size_t)b * (d.N + 1) + a0;
+    const size_t pp = leg_pp_size(d.ndx);
+    const double * Pterm = pass == 1 ? (j == J - 1 ? nullptr : A.legZero) : A.legT + ((size_t)b * J + j + 1) * pp;
+    double * P0 = (pass != 1 && j == 0) ? A.P0 + (size_t)b * pp : A.legP0 + ((size_t)b * J + j) * pp;
+    __shared__ int flag;
+    riccati4_backward_inst<NDX, NU, NC, TPB, GN>(
+      A.L, A.SL, a1 - a0, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag, P0, Pterm);
+    if (threadIdx.x == 0 && flag)
+      atomicOr(&st.flags, 1);
+  }
+  template <int NDX, int NU, int NC, int TPB, int GN>
+  void launch_riccati4_legs_impl(smpc_ctx * c, int pass)
+  {
+    k_riccati4_legs<NDX, NU, NC, TPB, GN><<<c->A.dm.B * (c->A.legs - 1), TPB, c->ric_smem, c->stream>>>(c->A, pass);
+  }
   template <int NDX, int NU, int NC, int TPB, int GN>
   void launch_riccati4_impl(smpc_ctx * c)
   {
     k_riccati4<NDX, NU, NC, TPB, GN><<<c->A.dm.B, TPB, c->ric_smem, c->stream>>>(c->A);
   }
-  template <int NDX, int NU, int NC, int TPB, int GN = NDX>
+  // LEGS: also instantiate the leg kernel of the PARALLEL sweep (each instantiation of the sweep compiles for minutes, so
+  // only the shapes whose single-instance latency matters carry it)
+  template <int NDX, int NU, int NC, int TPB, int GN = NDX, bool LEGS = false>
   int setup_riccati4(smpc_ctx * c, const char * name)
   {
     typedef Ric4<NDX, NU, NC> R;
@@ -63,6 +91,12 @@ namespace smpc
     CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
     CU(cudaFuncSetAttribute(k_riccati4<NDX, NU, NC, TPB, GN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c->launch_riccati = &launch_riccati4_impl<NDX, NU, NC, TPB, GN>;
+    if constexpr (LEGS)
+    {
+      CU(cudaFuncSetAttribute(k_riccati4_legs<NDX, NU, NC, TPB, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ric_smem));
+      CU(cudaFuncSetAttribute(k_riccati4_legs<NDX, NU, NC, TPB, GN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      c->launch_riccati_legs = &launch_riccati4_legs_impl<NDX, NU, NC, TPB, GN>;
+    }
     c->riccati_variant = name;
     if (getenv("SMPC_VERBOSE"))
     {

@@ -563,6 +563,56 @@ namespace
   {
     k_riccati<<<c->A.dm.B, c->ric_generic_tpb, c->ric_smem, c->stream>>>(c->A);
   }
+  // ---- PARALLEL (leg-condensed) sweep, riccati_par.cuh: pass 2 (one CTA per inner leg) and pass 3 (one CTA per instance) ----
+  __global__ void __launch_bounds__(256) k_leg_elements(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const Dims & d = A.dm;
+    const int J = A.legs, b = blockIdx.x / (J - 2), j = 1 + blockIdx.x % (J - 2);
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    const size_t xb = (size_t)b * (d.N + 1);
+    __shared__ int flag;
+    leg_element_inst(
+      A.L, A.SL, A.PS, leg_begin(d.N, J, j), leg_begin(d.N, J, j + 1), A.knots + xb * A.L.size, A.ncs + xb, A.sol + xb * A.SL.size,
+      st.mu, st.mu, smem_raw, &flag, A.legE + ((size_t)b * J + j) * leg_elem_size(d.ndx));
+    if (threadIdx.x == 0 && flag)
+      atomicOr(&st.flags, 1);
+  }
+  __global__ void __launch_bounds__(256) k_leg_coarse(Arrays A)
+  {
+    extern __shared__ __align__(16) double smem_raw[];
+    const Dims & d = A.dm;
+    const int J = A.legs, b = blockIdx.x;
+    InstState & st = A.inst[b];
+    if (st.phase != PH_NEED_STEP)
+      return;
+    __shared__ int flag;
+    const size_t pp = leg_pp_size(d.ndx);
+    leg_coarse_inst(
+      d.ndx, J, A.CS, A.legP0 + (size_t)b * J * pp, A.legE + (size_t)b * J * leg_elem_size(d.ndx), A.legT + (size_t)b * J * pp, smem_raw,
+      &flag);
+    if (threadIdx.x == 0 && flag)
+      atomicOr(&st.flags, 1);
+  }
+  // the backward sweep of one round: serial (one CTA per instance) or leg-parallel (four launches, riccati_par.cuh)
+  void launch_backward(smpc_ctx * c)
+  {
+    const int J = c->A.legs;
+    if (J <= 1)
+    {
+      c->launch_riccati(c);
+      return;
+    }
+    const int B = c->A.dm.B;
+    c->launch_riccati_legs(c, 1);
+    if (J > 2)
+      k_leg_elements<<<B * (J - 2), 256, (size_t)c->A.PS.size * sizeof(double), c->stream>>>(c->A);
+    k_leg_coarse<<<B, 256, (size_t)c->A.CS.size * sizeof(double), c->stream>>>(c->A);
+    c->launch_riccati_legs(c, 4);
+    c->launches += J > 2 ? 3 : 2;
+  }
   template <class T>
   int dev_alloc(smpc_ctx * c, T ** p, size_t n)
   {
@@ -850,6 +900,32 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   }
   AL(A.inst, B);
   AL(A.counters, 4);
+  // PARALLEL Riccati sweep (smpc_solver_opts::num_threads > 1, reference src/mpc.cpp:46-50): only where it shortens the
+  // critical path - SMs left idle by the batch, a tuned sweep for the shape, at least three legs (two legs are the serial
+  // sweep cut in two). SMPC_LEGS overrides the leg count.
+  {
+    int J = opts->num_threads;
+    if (const char * e = getenv("SMPC_LEGS"))
+      J = atoi(e);
+    J = riccati_legs_used(d.N, J);
+    const int sms = c->hmodel_sms > 0 ? c->hmodel_sms : 148;
+    A.legs = 1;
+    A.PS = make_par_smem(d.ndx, d.nu, d.ncmax);
+    A.CS = make_coarse_smem(d.ndx);
+    const size_t par_bytes = (size_t)A.PS.size * sizeof(double), coarse_bytes = (size_t)A.CS.size * sizeof(double);
+    if (J >= 3 && c->launch_riccati_legs && (int)B * (J - 1) <= sms && par_bytes <= 227 * 1024 && coarse_bytes <= 227 * 1024)
+    {
+      A.legs = J;
+      double * zero;
+      AL(A.legP0, B * J * leg_pp_size(d.ndx));
+      AL(A.legT, B * J * leg_pp_size(d.ndx));
+      AL(A.legE, B * J * leg_elem_size(d.ndx));
+      AL(zero, (size_t)leg_pp_size(d.ndx));
+      A.legZero = zero;
+      CU(cudaFuncSetAttribute(k_leg_elements, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par_bytes));
+      CU(cudaFuncSetAttribute(k_leg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_bytes));
+    }
+  }
 #undef AL
   // persistent solver scalars (aligator: set in setup())
   {
@@ -1106,7 +1182,7 @@ static int enqueue_round_head(smpc_ctx * c, bool tk)
   k_decide<<<d.B, 64, 0, s>>>(c->A);
   if (tk)
     CU(cudaEventRecord(c->evr0, s));
-  c->launch_riccati(c);
+  launch_backward(c);
   if (tk)
   {
     CU(cudaEventRecord(c->evr1, s));
@@ -1879,6 +1955,7 @@ int smpc_last_solve_ms(smpc_ctx * c, float * total_ms, float * riccati_ms)
 }
 int64_t smpc_launch_count(smpc_ctx * c) { return c ? c->launches : 0; }
 const char * smpc_riccati_variant(smpc_ctx * c) { return c ? c->riccati_variant : ""; }
+int smpc_riccati_legs(smpc_ctx * c) { return c ? (c->A.legs > 1 ? c->A.legs : 1) : SMPC_ERR_INVALID; }
 
 // LQ knot t of instance `inst` as assembled by the last linearisation (test hook; device layout -> dense blocks)
 int smpc_get_knot(smpc_ctx * c, int inst, int t, int * nc, double * knot_out /* KnotLayout.size doubles */)

@@ -45,6 +45,7 @@ namespace simple_mpc
     std::vector<Frame> frames;
     std::map<std::string, VectorXd> referenceConfigurations;
     VectorXd lowerPositionLimit, upperPositionLimit, effortLimit;
+    VectorXd friction, damping; // nv entries each (pinocchio's convention) or empty = zero; read by FrictionCompensation only
 
     /// root free-flyer (must be added first); returns joint index 0
     JointIndex addFreeFlyer(const std::string & name, double mass, const Vector3d & lever, const std::array<double, 9> & inertia);

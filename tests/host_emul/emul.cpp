@@ -8,6 +8,7 @@
 #include "../../simple-mpc_b200/csrc/riccati.cuh"
 #include "../../simple-mpc_b200/csrc/riccati3.cuh"
 #include "../../simple-mpc_b200/csrc/riccati4.cuh"
+#include "../../simple-mpc_b200/csrc/riccati_par.cuh"
 #include "../../simple-mpc_b200/csrc/riccati_fwd.cuh"
 #include "../../simple-mpc_b200/csrc/mpc_driver.cuh"
 #include "../../simple-mpc_b200/csrc/host_build.h"
@@ -126,6 +127,71 @@ static int emul_riccati3_impl(
   return 0;
 }
 
+
+// The PARALLEL (leg-condensed) sweep of riccati_par.cuh with J legs: pass 1 / pass 4 through the tuned sweeps (riccati3 for
+// the Go2 kinodynamics shapes, riccati4 otherwise), leg elements, coarse condensation, then the ordinary forward sweep.
+// The legs of a pass run one after the other here; on the device they are concurrent CTAs.
+template <int NDX, int NU, int NC, bool R3>
+static void leg_sweep(const KnotLayout & L, const SolLayout & SL, int n, const double * knots, double * sol, double mudyn, double mueq, int * flag, double * P0, const double * Pterm)
+{
+  if constexpr (R3)
+  {
+    std::vector<double> sm(Ric3<NDX, NU, NC>::SIZE + 8, 0.0);
+    riccati3_backward_inst<NDX, NU, NC, SMPC_EMUL_NT, 0, false>(L, SL, n, knots, sol, mudyn, mueq, sm.data(), flag, P0, Pterm);
+  }
+  else
+  {
+    std::vector<double> sm(Ric4<NDX, NU, NC>::SIZE + 16, 0.0);
+    riccati4_backward_inst<NDX, NU, NC, SMPC_EMUL_NT, NDX>(L, SL, n, knots, sol, mudyn, mueq, sm.data(), flag, P0, Pterm);
+  }
+}
+template <int NDX, int NU, int NC, bool R3>
+static int parallel_any(
+  int N, int J, const double * knots, const int * ncs, double mudyn, double mueq, double * sol, const double * gx, const double * gu,
+  const double * lplus, double * dxs, double * dus, double * vnew, double * lnew, double * dphi, int * flag)
+{
+  const int ndx = NDX, nu = NU, ncmax = NC;
+  KnotLayout L = make_knot_layout(ndx, nu, ncmax);
+  SolLayout SL = make_sol_layout(ndx, nu, ncmax);
+  J = riccati_legs_used(N, J);
+  if (J < 2)
+  {
+    g_err = "emul_riccati_parallel: fewer than two legs";
+    return -1;
+  }
+  const size_t pp = leg_pp_size(ndx), es = leg_elem_size(ndx);
+  std::vector<double> legP0(J * pp, 0.0), legT(J * pp, 0.0), legE(J * es, 0.0), zero(pp, 0.0), P0(pp, 0.0);
+  int fl = 0;
+  *flag = 0;
+  for (int j = 1; j < J; j++) // pass 1
+  {
+    const int a0 = leg_begin(N, J, j), a1 = leg_begin(N, J, j + 1);
+    leg_sweep<NDX, NU, NC, R3>(L, SL, a1 - a0, knots + (size_t)a0 * L.size, sol + (size_t)a0 * SL.size, mudyn, mueq, &fl, &legP0[j * pp], j == J - 1 ? nullptr : zero.data());
+    *flag |= fl;
+  }
+  ParSmem PS = make_par_smem(ndx, nu, ncmax);
+  for (int j = 1; j < J - 1; j++) // pass 2
+  {
+    std::vector<double> sm(PS.size + 8, 0.0);
+    leg_element_inst(L, SL, PS, leg_begin(N, J, j), leg_begin(N, J, j + 1), knots, ncs, sol, mudyn, mueq, sm.data(), &fl, &legE[j * es]);
+    *flag |= fl;
+  }
+  {
+    CoarseSmem CS = make_coarse_smem(ndx); // pass 3
+    std::vector<double> sm(CS.size + 8, 0.0);
+    leg_coarse_inst(ndx, J, CS, legP0.data(), legE.data(), legT.data(), sm.data(), &fl);
+    *flag |= fl;
+  }
+  for (int j = 0; j < J - 1; j++) // pass 4
+  {
+    const int a0 = leg_begin(N, J, j), a1 = leg_begin(N, J, j + 1);
+    leg_sweep<NDX, NU, NC, R3>(L, SL, a1 - a0, knots + (size_t)a0 * L.size, sol + (size_t)a0 * SL.size, mudyn, mueq, &fl, j == 0 ? P0.data() : &legP0[j * pp], &legT[(j + 1) * pp]);
+    *flag |= fl;
+  }
+  std::vector<double> sm2(4 * ndx + nu + 80, 0.0);
+  riccati_forward_inst(L, SL, N, knots, ncs, sol, P0.data(), mudyn, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, sm2.data());
+  return 0;
+}
 
 extern "C" {
 const char * emul_last_error() { return g_err.c_str(); }
@@ -278,6 +344,25 @@ void emul_sol_layout(int ndx, int nu, int ncmax, int * out /*7*/)
 int emul_riccati3(EMUL_RIC_ARGS) { return emul_riccati3_impl<0>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
 int emul_riccati3_kino_d0(EMUL_RIC_ARGS) { return emul_riccati3_impl<18, true>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
 int emul_riccati3_kino(EMUL_RIC_ARGS) { return emul_riccati3_impl<18>(N, ndx, nu, ncmax, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag); }
+
+int emul_riccati_parallel(
+  int N, int ndx, int nu, int ncmax, const double * knots, const int * ncs, double mudyn, double mueq, double * sol,
+  const double * gx, const double * gu, const double * lplus, double * dxs, double * dus, double * vnew, double * lnew,
+  double * dphi, int * flag, int J)
+{
+#define PAR_ARGS N, J, knots, ncs, mudyn, mueq, sol, gx, gu, lplus, dxs, dus, vnew, lnew, dphi, flag
+  if (ndx == 36 && nu == 24 && ncmax == 24)
+    return parallel_any<36, 24, 24, true>(PAR_ARGS);
+  if (ndx == 36 && nu == 24 && ncmax == 36)
+    return parallel_any<36, 24, 36, true>(PAR_ARGS);
+  if (ndx == 56 && nu == 34 && ncmax == 34)
+    return parallel_any<56, 34, 34, false>(PAR_ARGS);
+  if (ndx == 56 && nu == 34 && ncmax == 46)
+    return parallel_any<56, 34, 46, false>(PAR_ARGS);
+#undef PAR_ARGS
+  g_err = "emul_riccati_parallel: size not instantiated";
+  return -1;
+}
 
 // same, through the generic-shape two-column sweep of riccati4.cuh
 int emul_riccati4(

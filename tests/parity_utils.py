@@ -22,7 +22,7 @@ def relerr_elem(a, b, floor_frac=1e-3):
     return float((np.abs(np.asarray(a) - b) / den).max())
 
 
-def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario=None, **ocp_kw):
+def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario=None, cuda_threads=1, **ocp_kw):
     """Drive the oracle and the CUDA library through the same constructor solve + `ticks` MPC ticks and return
     the worst normwise relative differences."""
     orc, cu = load_oracle(), load_cuda()
@@ -31,6 +31,7 @@ def run_parity(batch=2, ticks=3, seed=0, ctor_iters=100, verbose=False, scenario
     orc.orc_default_solver_opts(C.byref(opts_o))
     cu.smpc_default_solver_opts(C.byref(opts_c))
     assert bytes(opts_o) == bytes(opts_c), "default solver options differ"
+    opts_c.num_threads = cuda_threads  # > 1: the CUDA side runs the PARALLEL (leg-condensed) sweep, the oracle stays serial
     bo = Backend(orc, "orc", sc.model, sc.ocpb, opts_o, batch)
     bc = Backend(cu, "smpc", sc.model, sc.ocpb, opts_c, batch)
     worst = dict(xs=0.0, us=0.0, K=0.0, k=0.0, iters_equal=True, alphas_equal=True, prim=0.0, dual=0.0, u0_elem=0.0, K0_elem=0.0)

@@ -164,6 +164,9 @@ def run_case(cone, robot="go2"):
         if not cone:
             # no row depends on the control (D = 0): Sigma = mu I, the W / Sigma phases drop out (riccati3.cuh DZ)
             out['kino_structure_d0_on_oracle'] = sweep(emu.emul_riccati3_kino_d0, orc_knots)
+    # the PARALLEL (leg-condensed) sweep of riccati_par.cuh on the same knots: tuned sweeps per leg + leg elements + condensation
+    for legs in (3, 5, 10):
+        out['parallel%d_on_oracle' % legs] = sweep(lambda *a, J=legs: emu.emul_riccati_parallel(*a, J), orc_knots)
     out['special_on_emul'] = sweep(tuned, emu_knots)
     if robot == "go2":
         # the forward sweep with ONE landing buffer (riccati_fwd.cuh, nbuf = 1: the variant large batches run)
@@ -210,6 +213,23 @@ def test_riccati_bitwise(case):
         assert np.array_equal(K, case['Ko']), name
         assert np.array_equal(dxs, case['odx']), name
         assert np.array_equal(dus, case['odu']), name
+
+
+def test_parallel_sweep_matches_the_serial_sweep(case):
+    """riccati_par.cuh (CPU emulation of the four passes) against the oracle's SERIAL sweep on identical knots: the hand-over
+    of the cost-to-go between legs goes through the condensed system, so equality is to rounding amplified by the penalised
+    recursion - the same floor two correct evaluations of the knots differ by (test_one_ulp_...)."""
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    for legs in (3, 5, 10):
+        K, dxs, dus = case['parallel%d_on_oracle' % legs]
+        T = K.shape[0]
+        eK = max(rel(K[t], case['Ko'][t]) for t in range(T))
+        print("legs %d: K %.2e dx %.2e du %.2e ; one-ulp spread of the serial sweep: K %.2e dx %.2e du %.2e" % (
+            legs, eK, rel(dxs, case['odx']), rel(dus, case['odu']), max(s['K'] for s in case['ulp_spread']),
+            max(s['dx'] for s in case['ulp_spread']), max(s['du'] for s in case['ulp_spread'])))
+        # measured: 3 legs within the one-ulp spread of the serial sweep, 10 legs up to 20 x above it (K 2e-8, du 7e-8 at worst):
+        # every hand-over adds a condensation step; the tolerance is the one of the GPU parity tests (TOL_K)
+        assert eK <= 1e-7 and rel(dxs, case['odx']) <= 1e-7 and rel(dus, case['odu']) <= 1e-7, (legs, eK, rel(dxs, case['odx']), rel(dus, case['odu']))
 
 
 def test_end_to_end_gains_within_conditioning(case):

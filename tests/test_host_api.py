@@ -323,3 +323,24 @@ def test_go2_fulldynamics_mpc_walks_on_the_oracle():
         mpc.getContactForces(50)
     # after 12 ticks the horizon tail holds cycle slots 10 and 11: the first FL + RR swing has entered the horizon
     assert ocp.getContactState(49) == [False, True, True, False] and ocp.getContactState(47) == [True] * 4
+
+
+def test_friction_compensation_matches_the_reference_test():
+    # reference tests/friction.cpp:10-43: dry 0.5 / viscous 0.05 on every actuated joint, random velocity and torque
+    mh = hu.go2_handler(sm)
+    model = mh.getModel()
+    nu = model.nv - 6
+    fr, dm = np.zeros(model.nv), np.zeros(model.nv)
+    fr[-nu:], dm[-nu:] = 0.5, 0.05
+    model.friction, model.damping = fr, dm
+    fc = sm.FrictionCompensation(model, True)
+    assert np.array_equal(fc.dry_friction, fr[-nu:]) and np.array_equal(fc.viscuous_friction, dm[-nu:])
+    rng = np.random.default_rng(0)
+    v, tau = rng.uniform(-1, 1, nu), rng.uniform(-1, 1, nu)
+    v[3] = 0.0
+    expect = tau + fr[6:] * np.sign(v) + dm[6:] * v
+    assert np.allclose(fc.computeFriction(v, tau), expect, rtol=0, atol=1e-15)
+    with pytest.raises(RuntimeError):
+        fc.computeFriction(v[:-1], tau)
+    # without a free flyer every dof is actuated; unset coefficients mean no friction
+    assert sm.FrictionCompensation(sm.Model(), False).nu == 0
