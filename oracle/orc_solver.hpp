@@ -579,6 +579,8 @@ namespace orc
           for (int j = 0; j < i; j++)
             S(i, j) = S(j, i) = 0.5 * (S(i, j) + S(j, i));
         chol_lower(S, ndx);
+        // (the algebraically equal vector part C S^-1 (C^T psi + C^-1 pn) was measured too: C^-1 pn loses more to the
+        // conditioning of C than psi - Lam pn loses to cancellation)
         for (int i = 0; i < ndx; i++)
         {
           for (int j = 0; j < ndx; j++)

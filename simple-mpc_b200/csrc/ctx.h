@@ -5,7 +5,7 @@
 #pragma once
 #include "kino_knot.cuh" // KnotIO
 #include "riccati.cuh"
-#include "riccati_par.cuh"
+#include "riccati_par_layout.h"
 #include "riccati_fwd.cuh"
 #include "mpc_driver.cuh"
 #include <cuda_runtime.h>

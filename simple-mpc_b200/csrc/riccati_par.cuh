@@ -25,58 +25,97 @@
 // Critical path: 2 x N/J tuned stages + N/J element stages + (J-2) condensation steps instead of N tuned stages.
 #pragma once
 #include "riccati.cuh"
+#include "riccati_par_layout.h"
 
 namespace smpc
 {
-  // leg boundaries a_j = floor(j N / J)
-  SMPC_HD int leg_begin(int N, int J, int j) { return (int)(((long long)j * N) / J); }
-  SMPC_HD int riccati_legs_used(int N, int J) { return (J >= 2 && N >= 2 * J) ? J : 1; }
-  // per-leg records in HBM: [P | p] blocks use the layout of P0out (g rows of g + 1 columns, p last)
-  SMPC_HD int leg_pp_size(int g) { return g * (g + 1); }
-  SMPC_HD int leg_elem_size(int g) { return 2 * g * g + g; } // Pi [g][g] | Lam [g][g] | psi [g]
-
-  struct ParSmem
+  // ---- small dense kernels of the leg-element / condensation kernels. These kernels sit on the critical path of a
+  // latency-bound tick, so their factorisations and triangular solves avoid CTA-wide barriers (the right-looking routines
+  // of riccati.cuh take two per pivot: 350 barriers per stage made pass 2 slower than the sweep it is meant to shorten) ----
+  // Cholesky of an n x n matrix (lower triangle, in place) by ONE warp, lane i owning rows i, i + 32, ...
+  SMPC_DEV void chol_lower_warp(double * M, int n, int ld, int * bad)
   {
-    int oPi, oPit, oLam, oY, oX, oRh, oW, oSg, oG, ov, ophi, opsi, oflag, size;
-  };
-  inline ParSmem make_par_smem(int ndx, int nu, int ncmax)
-  {
-    ParSmem R;
-    int o = 0;
-    R.oPi = o, o += ndx * ndx;
-    R.oPit = o, o += ndx * ndx;
-    R.oLam = o, o += ndx * ndx;
-    R.oY = o, o += nu * ndx;
-    R.oX = o, o += (nu * ndx > ndx * nu ? nu * ndx : ndx * nu); // P~ B (ndx x nu) before X (nu x ndx) exists
-    R.oRh = o, o += nu * nu;
-    R.oW = o, o += nu * ncmax;
-    R.oSg = o, o += ncmax * ncmax;
-    R.oG = o, o += ncmax * ndx;
-    R.ov = o, o += ndx;
-    R.ophi = o, o += ndx;
-    R.opsi = o, o += ndx;
-    R.oflag = o, o += 2;
-    R.size = o;
-    return R;
+#ifdef __CUDACC__
+    if (threadIdx.x < 32)
+    {
+      const int lane = threadIdx.x;
+      for (int k = 0; k < n; k++)
+      {
+        if (lane == (k & 31))
+        {
+          double dk = M[k * ld + k];
+          if (!(dk > 0.0))
+          {
+            *bad = 1;
+            dk = 1.0;
+          }
+          M[k * ld + k] = sqrt(dk);
+        }
+        __syncwarp();
+        const double inv = 1.0 / M[k * ld + k];
+        for (int i = lane; i < n; i += 32)
+          if (i > k)
+            M[i * ld + k] *= inv;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32)
+          if (i > k)
+          {
+            const double lik = M[i * ld + k];
+            for (int j = k + 1; j <= i; j++)
+              M[i * ld + j] = fma(-lik, M[j * ld + k], M[i * ld + j]);
+          }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+#else
+    for (int k = 0; k < n; k++)
+    {
+      double dk = M[k * ld + k];
+      if (!(dk > 0.0))
+      {
+        *bad = 1;
+        dk = 1.0;
+      }
+      M[k * ld + k] = sqrt(dk);
+      const double inv = 1.0 / M[k * ld + k];
+      for (int i = k + 1; i < n; i++)
+        M[i * ld + k] *= inv;
+      for (int i = k + 1; i < n; i++)
+      {
+        const double lik = M[i * ld + k];
+        for (int j = k + 1; j <= i; j++)
+          M[i * ld + j] = fma(-lik, M[j * ld + k], M[i * ld + j]);
+      }
+    }
+#endif
   }
-  // the condensation step works on (ndx x ndx) blocks only
-  struct CoarseSmem
+  // X <- L^-1 X and X <- L^-T X, one thread per column of X (its column is touched by no other thread: no barrier inside)
+  SMPC_DEV void solve_lower_cols(const double * L, int n, int ldl, double * X, int m, int ldx)
   {
-    int oC, oLC, oS, oR, oU, oPn, oflag, size;
-  };
-  inline CoarseSmem make_coarse_smem(int ndx)
+    SMPC_PAR(tid)
+    for (int c = tid; c < m; c += SMPC_NT)
+      for (int i = 0; i < n; i++)
+      {
+        double acc = X[i * ldx + c];
+        for (int k = 0; k < i; k++)
+          acc = fma(-L[i * ldl + k], X[k * ldx + c], acc);
+        X[i * ldx + c] = acc / L[i * ldl + i];
+      }
+    SMPC_END
+  }
+  SMPC_DEV void solve_lower_T_cols(const double * L, int n, int ldl, double * X, int m, int ldx)
   {
-    CoarseSmem R;
-    int o = 0;
-    R.oC = o, o += ndx * ndx;
-    R.oLC = o, o += ndx * ndx;
-    R.oS = o, o += ndx * ndx;
-    R.oR = o, o += ndx * (ndx + 1);
-    R.oU = o, o += ndx * (ndx + 1);
-    R.oPn = o, o += ndx * (ndx + 1);
-    R.oflag = o, o += 2;
-    R.size = o;
-    return R;
+    SMPC_PAR(tid)
+    for (int c = tid; c < m; c += SMPC_NT)
+      for (int i = n - 1; i >= 0; i--)
+      {
+        double acc = X[i * ldx + c];
+        for (int k = i + 1; k < n; k++)
+          acc = fma(-L[k * ldl + i], X[k * ldx + c], acc);
+        X[i * ldx + c] = acc / L[i * ldl + i];
+      }
+    SMPC_END
   }
 
   // pass 2 for the leg [a, b) of one instance. knots / ncs / sol are the INSTANCE's arrays; out = leg_elem_size doubles.
@@ -103,7 +142,7 @@ namespace smpc
     SMPC_PAR(tid)
     {
       if (tid == 0)
-        *bad = 0;
+        bad[0] = bad[1] = 0;
       for (int e = tid; e < n * n; e += SMPC_NT)
       {
         Pi[e] = (e / n == e % n) ? 1.0 : 0.0;
@@ -182,23 +221,30 @@ namespace smpc
         }
       }
       SMPC_END
-      chol_lower_par(Rh, nu, nu, bad);
-      // X = L^-1 Y (PB is dead: X takes its storage) ; W = L^-1 D^T
+      chol_lower_warp(Rh, nu, nu, bad);
+      // X = L^-1 Y (PB is dead: X takes its storage) ; W = L^-1 D^T. bad[1]: some entry of D is non-zero (without force
+      // cones no row of the kinodynamics problem depends on the control: W = 0, H = R^-1 and the Sigma block drops out)
       SMPC_PAR(tid)
       {
         for (int e = tid; e < nu * n; e += SMPC_NT)
           X[e] = Y[e];
+        bool any = false;
         for (int e = tid; e < nu * nc; e += SMPC_NT)
         {
           const int i = e / nc, c = e % nc;
-          W[e] = kn[L.oD + c * nu + i];
+          const double dv = kn[L.oD + c * nu + i];
+          W[e] = dv;
+          any = any || dv != 0.0;
         }
+        if (any)
+          bad[1] = 1;
       }
       SMPC_END
-      solve_lower_par(Rh, nu, nu, X, n, n);
-      if (nc > 0)
+      solve_lower_cols(Rh, nu, nu, X, n, n);
+      const bool has_d = nc > 0 && bad[1] != 0; // monotonic over the leg: the structure is the same at every stage
+      if (has_d)
       {
-        solve_lower_par(Rh, nu, nu, W, nc, nc);
+        solve_lower_cols(Rh, nu, nu, W, nc, nc);
         // Sigma = mu I + W^T W (lower) ; G = W^T X
         SMPC_PAR(tid)
         {
@@ -223,9 +269,9 @@ namespace smpc
           }
         }
         SMPC_END
-        chol_lower_par(Sg, nc, nc, bad);
-        solve_lower_par(Sg, nc, nc, G, n, n);
-        solve_lower_T_par(Sg, nc, nc, G, n, n);
+        chol_lower_warp(Sg, nc, nc, bad);
+        solve_lower_cols(Sg, nc, nc, G, n, n);
+        solve_lower_T_cols(Sg, nc, nc, G, n, n);
         SMPC_PAR(tid)
         for (int e = tid; e < nu * n; e += SMPC_NT)
         {
@@ -237,7 +283,7 @@ namespace smpc
         }
         SMPC_END
       }
-      solve_lower_T_par(Rh, nu, nu, X, n, n);
+      solve_lower_T_cols(Rh, nu, nu, X, n, n);
       // Lam += Y^T X + mu Pi+^T Pi~ ; psi += Pi+^T phi
       SMPC_PAR(tid)
       {
@@ -331,7 +377,7 @@ namespace smpc
         Cc[e] = (c <= i) ? Pn[i * ldp + c] : 0.0;
       }
       SMPC_END
-      chol_lower_par(Cc, n, n, bad);
+      chol_lower_warp(Cc, n, n, bad);
       // LC = Lam C ; R = [Psi | psi - Lam pn] (Psi = Pi^T)
       SMPC_PAR(tid)
       {
@@ -384,9 +430,9 @@ namespace smpc
         }
       }
       SMPC_END
-      chol_lower_par(S, n, n, bad);
-      solve_lower_par(S, n, n, U, ldp, ldp);
-      solve_lower_T_par(S, n, n, U, ldp, ldp);
+      chol_lower_warp(S, n, n, bad);
+      solve_lower_cols(S, n, n, U, ldp, ldp);
+      solve_lower_T_cols(S, n, n, U, ldp, ldp);
       // T = C U (+ pn on the vector column), into R
       SMPC_PAR(tid)
       for (int e = tid; e < n * ldp; e += SMPC_NT)

@@ -11,6 +11,7 @@
 // There is NO CPU fallback: every entry point that computes fails with SMPC_ERR_CUDA if the
 // CUDA runtime does.
 #include "ctx.h"
+#include "riccati_par.cuh"
 #include "host_build.h"
 
 using namespace smpc;

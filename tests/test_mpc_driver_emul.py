@@ -67,7 +67,9 @@ def host_mpc(phase, **over):
     hooks = hu.import_hooks()
     mh = hu.go2_handler(sm)
     ocp, _ = hu.go2_kino_problem(sm, mh, T=50, **over)
-    mpc = hooks.make_oracle_mpc(hu.go2_mpc_conf(mh), ocp, hu.LIBORC)
+    # num_threads = 1: the batched device driver this object checks runs the SERIAL Riccati sweep (the leg-parallel sweep
+    # is compared with the serial one in tests/test_parallel_riccati.py)
+    mpc = hooks.make_oracle_mpc(dict(hu.go2_mpc_conf(mh), num_threads=1), ocp, hu.LIBORC)
     mpc.generateCycleHorizon(rotated(hu.go2_trot(), phase))
     return mh, ocp, mpc
 
