@@ -441,9 +441,11 @@ def main():
         b1.close()
         # MPCSettings::num_threads > 1 = the PARALLEL (leg-condensed) Riccati sweep, one CTA per leg (csrc/riccati_par.cuh)
         par = []
-        for legs in (5, 10):
+        for legs in (5, 10, 20):
             scp = make_scenario(cfg, 1, seed=0)
+            os.environ["SMPC_LEGS"] = str(legs)  # measure every supported shape, also those for which the serial sweep stays the default
             bp = setup_backend(cu, "smpc", scp, 1, local_rank, num_threads=legs)
+            del os.environ["SMPC_LEGS"]
             used = cu.smpc_riccati_legs(bp.ctx)
             if used > 1:
                 xp = np.ascontiguousarray(scp.xmeas_start())

@@ -141,9 +141,10 @@ typedef struct smpc_solver_opts
   double ls_armijo_c1, ls_alpha_min, ls_contraction, ls_avg_eta;
   int32_t ls_max_steps;
   /* MPCSettings::num_threads (reference src/mpc.cpp:46-50): > 1 selects the PARALLEL (leg-condensed) Riccati sweep with
-   * that many legs - one CTA per leg, csrc/riccati_par.cuh - when the batch leaves SMs idle (batch x legs <= SM count)
-   * and a tuned sweep exists for the shape; throughput-bound batches always run the serial sweep (same results up to
-   * rounding either way). 0 or 1: serial. */
+   * that many legs - one CTA per leg, csrc/riccati_par.cuh - when the batch leaves SMs idle (batch x legs <= SM count),
+   * a tuned sweep exists for the shape and the leg-parallel sweep was measured to be the faster one for it (today: the
+   * centroidal problems; the environment variable SMPC_LEGS=n forces n legs for any supported shape). Everything else runs
+   * the serial sweep; results agree up to rounding either way. 0 or 1: serial. smpc_riccati_legs() reports what runs. */
   int32_t num_threads;
 } smpc_solver_opts;
 

@@ -29,92 +29,118 @@
 
 namespace smpc
 {
-  // ---- small dense kernels of the leg-element / condensation kernels. These kernels sit on the critical path of a
-  // latency-bound tick, so their factorisations and triangular solves avoid CTA-wide barriers (the right-looking routines
-  // of riccati.cuh take two per pivot: 350 barriers per stage made pass 2 slower than the sweep it is meant to shorten) ----
-  // Cholesky of an n x n matrix (lower triangle, in place) by ONE warp, lane i owning rows i, i + 32, ...
-  SMPC_DEV void chol_lower_warp(double * M, int n, int ld, int * bad)
+  // ---- small dense products of the leg-element / condensation kernels. These kernels sit on the critical path of a
+  // latency-bound tick: a product written as one fused-multiply-add chain per output (operands from shared memory / L1) runs
+  // at the load latency (measured: 99 us per element stage, 169 us per condensation step - slower than the sweep they are
+  // meant to shorten). 2 x 2 register tiles with the k loop unrolled by four give every load two uses and every thread four
+  // independent chains. ----
+  // this thread's share of C = op(A) op(B): A(i,k) = pa[i * sai + k * sak], B(k,j) = pb[k * sbk + j * sbj]; epi(i, j, sum)
+  template <class Epi>
+  SMPC_DEV void gemm22(
+    int tid, int nt, int M, int N, int K, const double * __restrict__ pa, int sai, int sak, const double * __restrict__ pb, int sbk,
+    int sbj, Epi epi)
   {
-#ifdef __CUDACC__
-    if (threadIdx.x < 32)
+    const int TN = (N + 1) / 2, tiles = ((M + 1) / 2) * TN;
+    for (int e = tid; e < tiles; e += nt)
     {
-      const int lane = threadIdx.x;
-      for (int k = 0; k < n; k++)
+      const int i0 = 2 * (e / TN), j0 = 2 * (e % TN);
+      const int i1 = (i0 + 1 < M) ? i0 + 1 : i0, j1 = (j0 + 1 < N) ? j0 + 1 : j0;
+      const double * a0 = pa + i0 * sai;
+      const double * a1 = pa + i1 * sai;
+      const double * b0 = pb + j0 * sbj;
+      const double * b1 = pb + j1 * sbj;
+      double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < K; k++)
       {
-        if (lane == (k & 31))
-        {
-          double dk = M[k * ld + k];
-          if (!(dk > 0.0))
-          {
-            *bad = 1;
-            dk = 1.0;
-          }
-          M[k * ld + k] = sqrt(dk);
-        }
-        __syncwarp();
-        const double inv = 1.0 / M[k * ld + k];
-        for (int i = lane; i < n; i += 32)
-          if (i > k)
-            M[i * ld + k] *= inv;
-        __syncwarp();
-        for (int i = lane; i < n; i += 32)
-          if (i > k)
-          {
-            const double lik = M[i * ld + k];
-            for (int j = k + 1; j <= i; j++)
-              M[i * ld + j] = fma(-lik, M[j * ld + k], M[i * ld + j]);
-          }
-        __syncwarp();
+        const double x0 = a0[k * sak], x1 = a1[k * sak], y0 = b0[k * sbk], y1 = b1[k * sbk];
+        c00 = fma(x0, y0, c00);
+        c01 = fma(x0, y1, c01);
+        c10 = fma(x1, y0, c10);
+        c11 = fma(x1, y1, c11);
+      }
+      epi(i0, j0, c00);
+      if (j1 != j0)
+        epi(i0, j1, c01);
+      if (i1 != i0)
+      {
+        epi(i1, j0, c10);
+        if (j1 != j0)
+          epi(i1, j1, c11);
       }
     }
-    __syncthreads();
-#else
+  }
+
+  // Right-looking LDL^T of a symmetric positive definite S (lower triangle, in place) whose elimination carries up to two
+  // blocks of right-hand sides along: U <- L^-1 U with the UNIT lower factor, ONE CTA barrier per pivot (the scale-then-update
+  // routines of riccati.cuh take two, and a separate forward substitution two more). On return the strict lower triangle
+  // of S holds L D (column k = L(:,k) d_k), the diagonal d, and invd[k] = 1 / d_k.
+  SMPC_DEV void ldl_fused(
+    double * S, int n, int lds, double * invd, double * U1, int m1, int ld1, double * U2, int m2, int ld2, int * bad)
+  {
     for (int k = 0; k < n; k++)
     {
-      double dk = M[k * ld + k];
-      if (!(dk > 0.0))
+      SMPC_PAR(tid)
       {
-        *bad = 1;
-        dk = 1.0;
+        double dk = S[k * lds + k];
+        if (!(dk > 0.0))
+        {
+          if (tid == 0)
+            *bad = 1;
+          dk = 1.0;
+        }
+        const double id = 1.0 / dk;
+        if (tid == 0)
+          invd[k] = id;
+        const int rows = n - k - 1, w = rows + m1 + m2;
+        for (int e = tid; e < rows * w; e += SMPC_NT)
+        {
+          const int r = e / w, c = e - r * w, i = k + 1 + r;
+          const double l = S[i * lds + k] * id;
+          if (c < rows)
+          {
+            const int j = k + 1 + c;
+            if (j <= i)
+              S[i * lds + j] = fma(-l, S[j * lds + k], S[i * lds + j]);
+          }
+          else if (c < rows + m1)
+          {
+            const int cc = c - rows;
+            U1[i * ld1 + cc] = fma(-l, U1[k * ld1 + cc], U1[i * ld1 + cc]);
+          }
+          else
+          {
+            const int cc = c - rows - m1;
+            U2[i * ld2 + cc] = fma(-l, U2[k * ld2 + cc], U2[i * ld2 + cc]);
+          }
+        }
       }
-      M[k * ld + k] = sqrt(dk);
-      const double inv = 1.0 / M[k * ld + k];
-      for (int i = k + 1; i < n; i++)
-        M[i * ld + k] *= inv;
-      for (int i = k + 1; i < n; i++)
-      {
-        const double lik = M[i * ld + k];
-        for (int j = k + 1; j <= i; j++)
-          M[i * ld + j] = fma(-lik, M[j * ld + k], M[i * ld + j]);
-      }
+      SMPC_END
     }
-#endif
   }
-  // X <- L^-1 X and X <- L^-T X, one thread per column of X (its column is touched by no other thread: no barrier inside)
-  SMPC_DEV void solve_lower_cols(const double * L, int n, int ldl, double * X, int m, int ldx)
+  // U <- L^-T U with the unit lower factor ldl_fused left in S: one barrier per pivot
+  SMPC_DEV void ldl_backward(const double * S, int n, int lds, const double * invd, double * U, int m, int ld)
+  {
+    for (int k = n - 1; k >= 1; k--)
+    {
+      SMPC_PAR(tid)
+      for (int e = tid; e < k * m; e += SMPC_NT)
+      {
+        const int i = e / m, c = e - i * m;
+        U[i * ld + c] = fma(-(S[k * lds + i] * invd[i]), U[k * ld + c], U[i * ld + c]);
+      }
+      SMPC_END
+    }
+  }
+  // rows of U scaled by invd[k] (power = 2) or sqrt(invd[k]) (power = 1)
+  SMPC_DEV void scale_rows(double * U, int n, int m, int ld, const double * invd, int power)
   {
     SMPC_PAR(tid)
-    for (int c = tid; c < m; c += SMPC_NT)
-      for (int i = 0; i < n; i++)
-      {
-        double acc = X[i * ldx + c];
-        for (int k = 0; k < i; k++)
-          acc = fma(-L[i * ldl + k], X[k * ldx + c], acc);
-        X[i * ldx + c] = acc / L[i * ldl + i];
-      }
-    SMPC_END
-  }
-  SMPC_DEV void solve_lower_T_cols(const double * L, int n, int ldl, double * X, int m, int ldx)
-  {
-    SMPC_PAR(tid)
-    for (int c = tid; c < m; c += SMPC_NT)
-      for (int i = n - 1; i >= 0; i--)
-      {
-        double acc = X[i * ldx + c];
-        for (int k = i + 1; k < n; k++)
-          acc = fma(-L[k * ldl + i], X[k * ldx + c], acc);
-        X[i * ldx + c] = acc / L[i * ldl + i];
-      }
+    for (int e = tid; e < n * m; e += SMPC_NT)
+    {
+      const int i = e / m, c = e - i * m;
+      U[i * ld + c] *= (power == 2) ? invd[i] : sqrt(invd[i]);
+    }
     SMPC_END
   }
 
@@ -138,6 +164,8 @@ namespace smpc
     double * v = sm + RS.ov;
     double * phi = sm + RS.ophi;
     double * psi = sm + RS.opsi;
+    double * invr = sm + RS.oinvd;
+    double * invs = invr + nu;
     int * bad = (int *)(sm + RS.oflag);
     SMPC_PAR(tid)
     {
@@ -161,17 +189,11 @@ namespace smpc
       const double * Ak = kn + L.oA;
       const double * Bk = kn + L.oB;
       const int nc = ncs[t];
-      // Pi~ = Pi+ - mu P~ Pi+ ; v = B k + f
+      // Pi~ = Pi+ - mu P~ Pi+ ; P~ B ; v = B k + f
       SMPC_PAR(tid)
       {
-        for (int e = tid; e < n * n; e += SMPC_NT)
-        {
-          const int i = e / n, j = e % n;
-          double acc = 0.0;
-          for (int k = 0; k < n; k++)
-            acc = fma(Pt[i * n + k], Pi[k * n + j], acc);
-          Pit[e] = fma(-mudyn, acc, Pi[e]);
-        }
+        gemm22(tid, SMPC_NT, n, n, n, Pt, n, 1, Pi, n, 1, [&](int i, int j, double acc) { Pit[i * n + j] = fma(-mudyn, acc, Pi[i * n + j]); });
+        gemm22(tid, SMPC_NT, n, nu, n, Pt, n, 1, Bk, nu, 1, [&](int i, int j, double acc) { PB[i * nu + j] = acc; });
         for (int i = tid; i < n; i += SMPC_NT)
         {
           double acc = kn[L.of + i];
@@ -179,39 +201,13 @@ namespace smpc
             acc = fma(Bk[i * nu + k], so[SL.ok + k], acc);
           v[i] = acc;
         }
-        // P~ B (the products of this phase read Pi / global memory only)
-        for (int e = tid; e < n * nu; e += SMPC_NT)
-        {
-          const int i = e / nu, j = e % nu;
-          double acc = 0.0;
-          for (int k = 0; k < n; k++)
-            acc = fma(Pt[i * n + k], Bk[k * nu + j], acc);
-          PB[e] = acc;
-        }
       }
       SMPC_END
-      // Y = B^T Pi~ ; R^ = R + B^T (P~ B) (lower triangle) ; phi = v - mu (P~ v + p~)
+      // Y = B^T Pi~ ; R^ = R + B^T (P~ B) ; phi = v - mu (P~ v + p~)
       SMPC_PAR(tid)
       {
-        for (int e = tid; e < nu * n; e += SMPC_NT)
-        {
-          const int i = e / n, j = e % n;
-          double acc = 0.0;
-          for (int k = 0; k < n; k++)
-            acc = fma(Bk[k * nu + i], Pit[k * n + j], acc);
-          Y[e] = acc;
-        }
-        for (int e = tid; e < nu * nu; e += SMPC_NT)
-        {
-          const int i = e / nu, j = e % nu;
-          if (j <= i)
-          {
-            double acc = kn[L.oR + e];
-            for (int k = 0; k < n; k++)
-              acc = fma(Bk[k * nu + i], PB[k * nu + j], acc);
-            Rh[e] = acc;
-          }
-        }
+        gemm22(tid, SMPC_NT, nu, n, n, Bk, 1, nu, Pit, n, 1, [&](int i, int j, double acc) { Y[i * n + j] = acc; });
+        gemm22(tid, SMPC_NT, nu, nu, n, Bk, 1, nu, PB, nu, 1, [&](int i, int j, double acc) { Rh[i * nu + j] = kn[L.oR + i * nu + j] + acc; });
         for (int i = tid; i < n; i += SMPC_NT)
         {
           double acc = so[SL.opt + i];
@@ -221,9 +217,8 @@ namespace smpc
         }
       }
       SMPC_END
-      chol_lower_warp(Rh, nu, nu, bad);
-      // X = L^-1 Y (PB is dead: X takes its storage) ; W = L^-1 D^T. bad[1]: some entry of D is non-zero (without force
-      // cones no row of the kinodynamics problem depends on the control: W = 0, H = R^-1 and the Sigma block drops out)
+      // X = Y (PB is dead: X takes its storage) ; W = D^T. bad[1]: some entry of D is non-zero (without force cones no row
+      // of the kinodynamics problem depends on the control: W = 0, H = R^-1 and the Sigma block drops out)
       SMPC_PAR(tid)
       {
         for (int e = tid; e < nu * n; e += SMPC_NT)
@@ -240,64 +235,35 @@ namespace smpc
           bad[1] = 1;
       }
       SMPC_END
-      solve_lower_cols(Rh, nu, nu, X, n, n);
       const bool has_d = nc > 0 && bad[1] != 0; // monotonic over the leg: the structure is the same at every stage
+      // R^ = L D L^T ; X <- L^-1 Y, W <- L^-1 D^T in the same elimination ; H = L^-T [D^-1 - D^-1 W Sigma^-1 W^T D^-1] L^-1
+      ldl_fused(Rh, nu, nu, invr, X, n, n, W, has_d ? nc : 0, nc, bad);
       if (has_d)
       {
-        solve_lower_cols(Rh, nu, nu, W, nc, nc);
-        // Sigma = mu I + W^T W (lower) ; G = W^T X
+        scale_rows(X, nu, n, n, invr, 1);
+        scale_rows(W, nu, nc, nc, invr, 1);
+        // Sigma = mu I + W^T W ; G = W^T X
         SMPC_PAR(tid)
         {
-          for (int e = tid; e < nc * nc; e += SMPC_NT)
-          {
-            const int i = e / nc, j = e % nc;
-            if (j <= i)
-            {
-              double acc = (i == j) ? mueq : 0.0;
-              for (int k = 0; k < nu; k++)
-                acc = fma(W[k * nc + i], W[k * nc + j], acc);
-              Sg[e] = acc;
-            }
-          }
-          for (int e = tid; e < nc * n; e += SMPC_NT)
-          {
-            const int i = e / n, j = e % n;
-            double acc = 0.0;
-            for (int k = 0; k < nu; k++)
-              acc = fma(W[k * nc + i], X[k * n + j], acc);
-            G[e] = acc;
-          }
+          gemm22(tid, SMPC_NT, nc, nc, nu, W, 1, nc, W, nc, 1, [&](int i, int j, double acc) { Sg[i * nc + j] = acc + ((i == j) ? mueq : 0.0); });
+          gemm22(tid, SMPC_NT, nc, n, nu, W, 1, nc, X, n, 1, [&](int i, int j, double acc) { G[i * n + j] = acc; });
         }
         SMPC_END
-        chol_lower_warp(Sg, nc, nc, bad);
-        solve_lower_cols(Sg, nc, nc, G, n, n);
-        solve_lower_T_cols(Sg, nc, nc, G, n, n);
+        ldl_fused(Sg, nc, nc, invs, G, n, n, nullptr, 0, 0, bad);
+        scale_rows(G, nc, n, n, invs, 2);
+        ldl_backward(Sg, nc, nc, invs, G, n, n);
         SMPC_PAR(tid)
-        for (int e = tid; e < nu * n; e += SMPC_NT)
-        {
-          const int i = e / n, j = e % n;
-          double acc = X[e];
-          for (int c = 0; c < nc; c++)
-            acc = fma(-W[i * nc + c], G[c * n + j], acc);
-          X[e] = acc;
-        }
+        gemm22(tid, SMPC_NT, nu, n, nc, W, nc, 1, G, n, 1, [&](int i, int j, double acc) { X[i * n + j] -= acc; });
         SMPC_END
+        scale_rows(X, nu, n, n, invr, 1);
       }
-      solve_lower_T_cols(Rh, nu, nu, X, n, n);
+      else
+        scale_rows(X, nu, n, n, invr, 2);
+      ldl_backward(Rh, nu, nu, invr, X, n, n);
       // Lam += Y^T X + mu Pi+^T Pi~ ; psi += Pi+^T phi
       SMPC_PAR(tid)
       {
-        for (int e = tid; e < n * n; e += SMPC_NT)
-        {
-          const int i = e / n, j = e % n;
-          double acc = Lam[e];
-          for (int k = 0; k < nu; k++)
-            acc = fma(Y[k * n + i], X[k * n + j], acc);
-          double acc2 = 0.0;
-          for (int k = 0; k < n; k++)
-            acc2 = fma(Pi[k * n + i], Pit[k * n + j], acc2);
-          Lam[e] = fma(mudyn, acc2, acc);
-        }
+        gemm22(tid, SMPC_NT, n, n, nu, Y, 1, n, X, n, 1, [&](int i, int j, double acc) { Lam[i * n + j] += acc; });
         for (int i = tid; i < n; i += SMPC_NT)
         {
           double acc = psi[i];
@@ -307,18 +273,15 @@ namespace smpc
         }
       }
       SMPC_END
-      // Pi = A^T Pi~ + K^T Y
       SMPC_PAR(tid)
-      for (int e = tid; e < n * n; e += SMPC_NT)
-      {
-        const int i = e / n, j = e % n;
-        double acc = 0.0;
-        for (int k = 0; k < n; k++)
-          acc = fma(Ak[k * n + i], Pit[k * n + j], acc);
-        for (int k = 0; k < nu; k++)
-          acc = fma(Kk[k * n + i], Y[k * n + j], acc);
-        Pi[e] = acc;
-      }
+      gemm22(tid, SMPC_NT, n, n, n, Pi, 1, n, Pit, n, 1, [&](int i, int j, double acc) { Lam[i * n + j] = fma(mudyn, acc, Lam[i * n + j]); });
+      SMPC_END
+      // Pi = A^T Pi~ + K^T Y (Pi+ is dead)
+      SMPC_PAR(tid)
+      gemm22(tid, SMPC_NT, n, n, n, Ak, 1, n, Pit, n, 1, [&](int i, int j, double acc) { Pi[i * n + j] = acc; });
+      SMPC_END
+      SMPC_PAR(tid)
+      gemm22(tid, SMPC_NT, n, n, nu, Kk, 1, n, Y, n, 1, [&](int i, int j, double acc) { Pi[i * n + j] += acc; });
       SMPC_END
     }
     SMPC_PAR(tid)
@@ -350,6 +313,7 @@ namespace smpc
     double * R = sm + RS.oR;
     double * U = sm + RS.oU;
     double * Pn = sm + RS.oPn; // [P | p] of the next boundary
+    double * wv = sm + RS.owv; // inverse pivots
     int * bad = (int *)(sm + RS.oflag);
     SMPC_PAR(tid)
     {
@@ -377,18 +341,19 @@ namespace smpc
         Cc[e] = (c <= i) ? Pn[i * ldp + c] : 0.0;
       }
       SMPC_END
-      chol_lower_warp(Cc, n, n, bad);
+      ldl_fused(Cc, n, n, wv, nullptr, 0, 0, nullptr, 0, 0, bad);
+      SMPC_PAR(tid)
+      for (int e = tid; e < n * n; e += SMPC_NT)
+      {
+        const int i = e / n, c = e % n;
+        if (c <= i)
+          Cc[e] = (c == i) ? 1.0 / sqrt(wv[c]) : Cc[e] * sqrt(wv[c]); // C = L D^1/2
+      }
+      SMPC_END
       // LC = Lam C ; R = [Psi | psi - Lam pn] (Psi = Pi^T)
       SMPC_PAR(tid)
       {
-        for (int e = tid; e < n * n; e += SMPC_NT)
-        {
-          const int i = e / n, c = e % n;
-          double acc = 0.0;
-          for (int k = c; k < n; k++) // C is lower triangular
-            acc = fma(Lam[i * n + k], Cc[k * n + c], acc);
-          LC[e] = acc;
-        }
+        gemm22(tid, SMPC_NT, n, n, n, Lam, n, 1, Cc, n, 1, [&](int i, int c, double acc) { LC[i * n + c] = acc; });
         for (int e = tid; e < n * ldp; e += SMPC_NT)
         {
           const int i = e / ldp, c = e % ldp;
@@ -404,56 +369,31 @@ namespace smpc
         }
       }
       SMPC_END
-      // S = I + C^T LC (lower) ; U = C^T R
+      // S = I + C^T LC ; U = C^T R
       SMPC_PAR(tid)
       {
-        for (int e = tid; e < n * n; e += SMPC_NT)
-        {
-          const int i = e / n, c = e % n;
-          if (c <= i)
-          {
-            double acc1 = (i == c) ? 1.0 : 0.0, acc2 = acc1;
-            for (int k = i; k < n; k++)
-              acc1 = fma(Cc[k * n + i], LC[k * n + c], acc1);
-            for (int k = c; k < n; k++)
-              acc2 = fma(Cc[k * n + c], LC[k * n + i], acc2);
-            S[e] = 0.5 * (acc1 + acc2);
-          }
-        }
-        for (int e = tid; e < n * ldp; e += SMPC_NT)
-        {
-          const int i = e / ldp, c = e % ldp;
-          double acc = 0.0;
-          for (int k = i; k < n; k++)
-            acc = fma(Cc[k * n + i], R[k * ldp + c], acc);
-          U[e] = acc;
-        }
+        gemm22(tid, SMPC_NT, n, n, n, Cc, 1, n, LC, n, 1, [&](int i, int c, double acc) { S[i * n + c] = acc + ((i == c) ? 1.0 : 0.0); });
+        gemm22(tid, SMPC_NT, n, ldp, n, Cc, 1, n, R, ldp, 1, [&](int i, int c, double acc) { U[i * ldp + c] = acc; });
       }
       SMPC_END
-      chol_lower_warp(S, n, n, bad);
-      solve_lower_cols(S, n, n, U, ldp, ldp);
-      solve_lower_T_cols(S, n, n, U, ldp, ldp);
+      SMPC_PAR(tid)
+      for (int e = tid; e < n * n; e += SMPC_NT)
+      {
+        const int i = e / n, c = e % n;
+        if (c < i)
+          S[e] = 0.5 * (S[e] + S[c * n + i]); // the factorisation reads the lower triangle only
+      }
+      SMPC_END
+      ldl_fused(S, n, n, wv, U, ldp, ldp, nullptr, 0, 0, bad);
+      scale_rows(U, n, ldp, ldp, wv, 2);
+      ldl_backward(S, n, n, wv, U, ldp, ldp);
       // T = C U (+ pn on the vector column), into R
       SMPC_PAR(tid)
-      for (int e = tid; e < n * ldp; e += SMPC_NT)
-      {
-        const int i = e / ldp, c = e % ldp;
-        double acc = (c == n) ? Pn[i * ldp + n] : 0.0;
-        for (int k = 0; k <= i; k++)
-          acc = fma(Cc[i * n + k], U[k * ldp + c], acc);
-        R[e] = acc;
-      }
+      gemm22(tid, SMPC_NT, n, ldp, n, Cc, n, 1, U, ldp, 1, [&](int i, int c, double acc) { R[i * ldp + c] = acc + ((c == n) ? Pn[i * ldp + n] : 0.0); });
       SMPC_END
       // [P | p] = [Pa | pa] + Pi T, into U ; then symmetrised into Pn and legT[j]
       SMPC_PAR(tid)
-      for (int e = tid; e < n * ldp; e += SMPC_NT)
-      {
-        const int i = e / ldp, c = e % ldp;
-        double acc = Pa[e];
-        for (int k = 0; k < n; k++)
-          acc = fma(Pi[i * n + k], R[k * ldp + c], acc);
-        U[e] = acc;
-      }
+      gemm22(tid, SMPC_NT, n, ldp, n, Pi, n, 1, R, ldp, 1, [&](int i, int c, double acc) { U[i * ldp + c] = Pa[i * ldp + c] + acc; });
       SMPC_END
       SMPC_PAR(tid)
       for (int e = tid; e < n * ldp; e += SMPC_NT)

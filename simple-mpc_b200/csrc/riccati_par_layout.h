@@ -15,7 +15,7 @@ namespace smpc
 
   struct ParSmem
   {
-    int oPi, oPit, oLam, oY, oX, oRh, oW, oSg, oG, ov, ophi, opsi, oflag, size;
+    int oPi, oPit, oLam, oY, oX, oRh, oW, oSg, oG, ov, ophi, opsi, oinvd, oflag, size;
   };
   inline ParSmem make_par_smem(int ndx, int nu, int ncmax)
   {
@@ -33,6 +33,7 @@ namespace smpc
     R.ov = o, o += ndx;
     R.ophi = o, o += ndx;
     R.opsi = o, o += ndx;
+    R.oinvd = o, o += nu + ncmax; // inverse pivots of R^ and of Sigma
     R.oflag = o, o += 2;
     R.size = o;
     return R;

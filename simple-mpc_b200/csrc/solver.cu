@@ -903,18 +903,25 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   AL(A.counters, 4);
   // PARALLEL Riccati sweep (smpc_solver_opts::num_threads > 1, reference src/mpc.cpp:46-50): only where it shortens the
   // critical path - SMs left idle by the batch, a tuned sweep for the shape, at least three legs (two legs are the serial
-  // sweep cut in two). SMPC_LEGS overrides the leg count.
+  // sweep cut in two) and a shape for which it was MEASURED to pay on B200 (profiles/r02v, single instance): the
+  // centroidal problems (T = 100, 9 states: backward sweep 3.56 ms serial, 1.05 ms with 10 legs, 0.73 ms with 20), not the
+  // Go2 kinodynamics problem (T = 50, 36 states: 1.04 ms serial against 1.35 ms with 10 legs - its run-time-shape element and
+  // condensation kernels cost more than the tuned stages they save). SMPC_LEGS = n forces n legs for any supported shape.
   {
     int J = opts->num_threads;
+    bool pays = O.kind == SMPC_OCP_CENTROIDAL;
     if (const char * e = getenv("SMPC_LEGS"))
+    {
       J = atoi(e);
+      pays = true;
+    }
     J = riccati_legs_used(d.N, J);
     const int sms = c->hmodel_sms > 0 ? c->hmodel_sms : 148;
     A.legs = 1;
     A.PS = make_par_smem(d.ndx, d.nu, d.ncmax);
     A.CS = make_coarse_smem(d.ndx);
     const size_t par_bytes = (size_t)A.PS.size * sizeof(double), coarse_bytes = (size_t)A.CS.size * sizeof(double);
-    if (J >= 3 && c->launch_riccati_legs && (int)B * (J - 1) <= sms && par_bytes <= 227 * 1024 && coarse_bytes <= 227 * 1024)
+    if (J >= 3 && pays && c->launch_riccati_legs && (int)B * (J - 1) <= sms && par_bytes <= 227 * 1024 && coarse_bytes <= 227 * 1024)
     {
       A.legs = J;
       double * zero;

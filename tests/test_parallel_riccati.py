@@ -53,35 +53,59 @@ def test_oracle_parallel_sweep_equals_the_serial_sweep(legs):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("legs,cone", [(5, False), (10, False), (5, True)])
-def test_cuda_parallel_sweep_against_the_serial_oracle(legs, cone):
-    """smpc_solver_opts.num_threads = legs on the CUDA side (four launches per backward sweep: tuned sweep per leg from a
-    zero cost-to-go, leg elements, condensation, tuned sweep per leg from the true cost-to-go) against the SERIAL oracle:
+def test_cuda_parallel_sweep_against_the_serial_oracle(legs, cone, monkeypatch):
+    """The leg-parallel sweep on the Go2 kinodynamics problem (riccati3 legs; forced with SMPC_LEGS because the serial sweep
+    is the faster one for this shape and therefore the default): four launches per backward sweep - tuned sweep per leg from
+    a zero cost-to-go, leg elements, condensation, tuned sweep per leg from the true cost-to-go - against the SERIAL oracle:
     constructor solve + 4 MPC ticks, same iteration counts / step sizes, xs, us, K within the tolerances of the serial test."""
     from smpc_ctypes import load_cuda
     cu = load_cuda()
+    monkeypatch.setenv("SMPC_LEGS", str(legs))
     kw = dict(force_cone=True, land_cstr=True, terminal_constraint=True) if cone else {}
     # the context must really run the leg-parallel sweep
     sc = pu.Go2Scenario(2, 0, **kw)
     opts = SolverOpts()
     cu.smpc_default_solver_opts(C.byref(opts))
-    opts.num_threads = legs
     b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, 2)
     assert cu.smpc_riccati_legs(b.ctx) == legs
     b.close()
-    res = pu.run_parity(batch=2, ticks=4, seed=0, cuda_threads=legs, **kw)
+    res = pu.run_parity(batch=2, ticks=4, seed=0, **kw)
     assert res["iters_equal"] and res["alphas_equal"], res
     assert res["xs"] <= 1e-7 and res["us"] <= 1e-7 and res["K"] <= (1e-5 if cone else 1e-6), res
 
 
 @pytest.mark.gpu
-def test_cuda_parallel_sweep_is_not_used_for_throughput_bound_batches():
+def test_num_threads_selects_the_parallel_sweep_for_the_centroidal_problem():
+    """MPCSettings::num_threads > 1 -> PARALLEL (reference src/mpc.cpp:46-50): for the centroidal problem (config C2, T = 100)
+    the leg-parallel sweep is the measured winner and num_threads alone selects it; results against the SERIAL oracle."""
+    from smpc_ctypes import load_cuda
+    cu = load_cuda()
+    sc = pu.TalosCentroidalScenario(2, 0)
+    opts = SolverOpts()
+    cu.smpc_default_solver_opts(C.byref(opts))
+    opts.num_threads = 8
+    b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, 2)
+    assert cu.smpc_riccati_legs(b.ctx) == 8
+    b.close()
+    res = pu.run_parity(batch=2, ticks=6, seed=0, cuda_threads=8, scenario=pu.TalosCentroidalScenario)
+    assert res["iters_equal"] and res["alphas_equal"], res
+    assert res["xs"] <= 1e-8 and res["us"] <= 1e-8 and res["K"] <= 1e-7, res
+    # Go2 kinodynamics: the serial sweep is faster, num_threads does not change what runs
+    sc = pu.Go2Scenario(1, 0)
+    b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, 1)
+    assert cu.smpc_riccati_legs(b.ctx) == 1
+    b.close()
+
+
+@pytest.mark.gpu
+def test_cuda_parallel_sweep_is_not_used_for_throughput_bound_batches(monkeypatch):
     """batch x (legs - 1) CTAs must fit the SMs once: a 64-instance context asked for 5 legs runs the serial sweep."""
     from smpc_ctypes import load_cuda
     cu = load_cuda()
+    monkeypatch.setenv("SMPC_LEGS", "5")
     sc = pu.Go2Scenario(64, 0)
     opts = SolverOpts()
     cu.smpc_default_solver_opts(C.byref(opts))
-    opts.num_threads = 5
     b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, 64)
     assert cu.smpc_riccati_legs(b.ctx) == 1
     b.close()
