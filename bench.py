@@ -365,9 +365,9 @@ def main():
     traffic, traffic_src = None, None
     if cfg in ("c1", "c5"):
         # dram__bytes_read.sum + dram__bytes_write.sum of k_riccati3<36,24,24,128,18,1> from the ncu --set full capture at B = 1024
-        # (profiles/r02l_ncu_summary.txt: 2.663 + 1.265 GB per launch), per instance, scaled to this launch
-        traffic = (2.663405e9 + 1.265249e9) / 1024 * B
-        traffic_src = "ncu --set full at B=1024, per instance x batch (profiles/r02l_ncu_summary.txt)"
+        # (profiles/r02w_ncu_summary.txt: 2.663 + 1.265 GB per launch), per instance, scaled to this launch
+        traffic = (2.663376e9 + 1.264518e9) / 1024 * B
+        traffic_src = "ncu --set full at B=1024, per instance x batch (profiles/r02w_ncu_summary.txt)"
     achieved = bytes_launch / ric_avg_s / 1e9 if ric_avg_s > 0 else 0.0
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -92,27 +92,26 @@ namespace smpc
         const double id = 1.0 / dk;
         if (tid == 0)
           invd[k] = id;
+        // a thread owns ONE column of the trailing block [S(:, k+1..) | U1 | U2] and every g-th row of it: the pivot-row entry
+        // of its column is loaded once, and the only index arithmetic per element is an increment
         const int rows = n - k - 1, w = rows + m1 + m2;
-        for (int e = tid; e < rows * w; e += SMPC_NT)
+        if (w > 0 && tid < (SMPC_NT / w) * w)
         {
-          const int r = e / w, c = e - r * w, i = k + 1 + r;
-          const double l = S[i * lds + k] * id;
+          const int g = SMPC_NT / w, c = tid % w, r0 = tid / w;
+          double * col;
+          int ld, jrow = -1;
           if (c < rows)
           {
-            const int j = k + 1 + c;
-            if (j <= i)
-              S[i * lds + j] = fma(-l, S[j * lds + k], S[i * lds + j]);
+            col = S + (k + 1 + c), ld = lds, jrow = k + 1 + c; // column j of S: rows i >= j only
           }
           else if (c < rows + m1)
-          {
-            const int cc = c - rows;
-            U1[i * ld1 + cc] = fma(-l, U1[k * ld1 + cc], U1[i * ld1 + cc]);
-          }
+            col = U1 + (c - rows), ld = ld1;
           else
-          {
-            const int cc = c - rows - m1;
-            U2[i * ld2 + cc] = fma(-l, U2[k * ld2 + cc], U2[i * ld2 + cc]);
-          }
+            col = U2 + (c - rows - m1), ld = ld2;
+          const double piv = (jrow >= 0) ? S[jrow * lds + k] : col[k * ld];
+          for (int i = k + 1 + r0; i < n; i += g)
+            if (i >= jrow)
+              col[i * ld] = fma(-(S[i * lds + k] * id), piv, col[i * ld]);
         }
       }
       SMPC_END
@@ -124,10 +123,12 @@ namespace smpc
     for (int k = n - 1; k >= 1; k--)
     {
       SMPC_PAR(tid)
-      for (int e = tid; e < k * m; e += SMPC_NT)
+      if (tid < (SMPC_NT / m) * m)
       {
-        const int i = e / m, c = e - i * m;
-        U[i * ld + c] = fma(-(S[k * lds + i] * invd[i]), U[k * ld + c], U[i * ld + c]);
+        const int g = SMPC_NT / m, c = tid % m;
+        const double piv = U[k * ld + c];
+        for (int i = tid / m; i < k; i += g)
+          U[i * ld + c] = fma(-(S[k * lds + i] * invd[i]), piv, U[i * ld + c]);
       }
       SMPC_END
     }
