@@ -181,7 +181,8 @@ typedef struct smpc_solve_info
   int32_t al_iters;
   int32_t conv;
   int32_t ls_trials;   /* merit evaluations of the last iteration */
-  int32_t flags;       /* bit 0: a Riccati factorisation met a non-positive pivot */
+  int32_t flags;       /* bit 0: a Riccati factorisation met a non-positive pivot; bit 2: the leg-parallel sweep could not
+                          factorise its condensed system and the serial sweep ran instead (results are the serial ones) */
   int32_t pad_;
   double alpha;        /* accepted step of the last iteration */
   double prim_infeas, dual_infeas;

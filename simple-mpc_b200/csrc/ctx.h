@@ -71,6 +71,8 @@ namespace smpc
     double *legP0, *legT; // [B][legs][ndx (ndx + 1)]: (P_a, p_a) of the zero-terminal sweeps / true cost-to-go at the leg starts
     double * legE;        // [B][legs][leg_elem_size]: Pi, Lam, psi of the inner legs
     const double * legZero; // ndx (ndx + 1) zeros: the cost-to-go of pass 1
+    int * legFail;          // [B]: a factorisation of pass 2 / 3 met a non-positive pivot -> pass 4 runs the serial sweep instead
+    int leg_force_fail;     // test hook (SMPC_LEGS_FORCE_FALLBACK): every instance takes that fallback
   };
 
   __device__ __forceinline__ const smpc_slot & slot_at(const Arrays & A, const InstState & st, int b, int t)

@@ -4,13 +4,22 @@
 #include "riccati4_kernel.cuh"
 namespace smpc
 {
+  // 128 threads: throughput variant; 256: latency variant when no SM holds more than one instance (SMPC_RIC_TPB overrides)
+  template <int NC>
+  static int pick(smpc_ctx * c)
+  {
+    bool wide = c->hmodel_sms > 0 && c->A.dm.B <= c->hmodel_sms;
+    if (const char * e = getenv("SMPC_RIC_TPB"))
+      wide = atoi(e) == 256;
+    return wide ? setup_riccati4<12, 12, NC, 256, 9, true>(c, "two-column-padded-256") : setup_riccati4<12, 12, NC, 128, 9, true>(c, "two-column-padded");
+  }
   int setup_ric4_centro(smpc_ctx * c, int ndx, int nu, int ncmax, bool * found)
   {
     *found = true;
     if (ndx == 9 && nu == 12 && ncmax == 34)
-      return setup_riccati4<12, 12, 34, 128, 9, true>(c, "two-column-padded");
+      return pick<34>(c);
     if (ndx == 9 && nu == 12 && ncmax == 8)
-      return setup_riccati4<12, 12, 8, 128, 9, true>(c, "two-column-padded");
+      return pick<8>(c);
     *found = false;
     return SMPC_OK;
   }

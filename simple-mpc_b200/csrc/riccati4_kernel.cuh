@@ -45,12 +45,30 @@ namespace smpc
     InstState & st = A.inst[b];
     if (st.phase != PH_NEED_STEP)
       return;
+    const size_t pp = leg_pp_size(d.ndx);
+    __shared__ int flag;
+    if (pass == 1)
+    {
+      if (j == 1 && threadIdx.x == 0)
+        A.legFail[b] = 0;
+    }
+    else if (A.legFail[b])
+    {
+      // the condensed system could not be factorised (a cost-to-go that is not positive definite): the CTA of leg 0 runs the
+      // serial sweep over the whole horizon instead, the other legs have nothing to do
+      if (j != 0)
+        return;
+      const size_t x0 = (size_t)b * (d.N + 1);
+      riccati4_backward_inst<NDX, NU, NC, TPB, GN>(
+        A.L, A.SL, d.N, A.knots + x0 * A.L.size, A.sol + x0 * A.SL.size, st.mu, st.mu, smem_raw, &flag, A.P0 + (size_t)b * pp);
+      if (threadIdx.x == 0)
+        atomicOr(&st.flags, flag ? 5 : 4);
+      return;
+    }
     const int a0 = leg_begin(d.N, J, j), a1 = leg_begin(d.N, J, j + 1);
     const size_t xb = (size_t)b * (d.N + 1) + a0;
-    const size_t pp = leg_pp_size(d.ndx);
     const double * Pterm = pass == 1 ? (j == J - 1 ? nullptr : A.legZero) : A.legT + ((size_t)b * J + j + 1) * pp;
     double * P0 = (pass != 1 && j == 0) ? A.P0 + (size_t)b * pp : A.legP0 + ((size_t)b * J + j) * pp;
-    __shared__ int flag;
     riccati4_backward_inst<NDX, NU, NC, TPB, GN>(
       A.L, A.SL, a1 - a0, A.knots + xb * A.L.size, A.sol + xb * A.SL.size, st.mu, st.mu, smem_raw, &flag, P0, Pterm);
     if (threadIdx.x == 0 && flag)

@@ -579,7 +579,7 @@ namespace
       A.L, A.SL, A.PS, leg_begin(d.N, J, j), leg_begin(d.N, J, j + 1), A.knots + xb * A.L.size, A.ncs + xb, A.sol + xb * A.SL.size,
       st.mu, st.mu, smem_raw, &flag, A.legE + ((size_t)b * J + j) * leg_elem_size(d.ndx));
     if (threadIdx.x == 0 && flag)
-      atomicOr(&st.flags, 1);
+      atomicOr(&A.legFail[b], 1); // pass 4 falls back to the serial sweep
   }
   __global__ void __launch_bounds__(256) k_leg_coarse(Arrays A)
   {
@@ -594,8 +594,8 @@ namespace
     leg_coarse_inst(
       d.ndx, J, A.CS, A.legP0 + (size_t)b * J * pp, A.legE + (size_t)b * J * leg_elem_size(d.ndx), A.legT + (size_t)b * J * pp, smem_raw,
       &flag);
-    if (threadIdx.x == 0 && flag)
-      atomicOr(&st.flags, 1);
+    if (threadIdx.x == 0 && (flag || A.leg_force_fail))
+      atomicOr(&A.legFail[b], 1); // pass 4 falls back to the serial sweep
   }
   // the backward sweep of one round: serial (one CTA per instance) or leg-parallel (four launches, riccati_par.cuh)
   void launch_backward(smpc_ctx * c)
@@ -930,6 +930,8 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
       AL(A.legE, B * J * leg_elem_size(d.ndx));
       AL(zero, (size_t)leg_pp_size(d.ndx));
       A.legZero = zero;
+      AL(A.legFail, B);
+      A.leg_force_fail = getenv("SMPC_LEGS_FORCE_FALLBACK") != nullptr;
       CU(cudaFuncSetAttribute(k_leg_elements, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)par_bytes));
       CU(cudaFuncSetAttribute(k_leg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coarse_bytes));
     }

@@ -109,3 +109,38 @@ def test_cuda_parallel_sweep_is_not_used_for_throughput_bound_batches(monkeypatc
     b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, 64)
     assert cu.smpc_riccati_legs(b.ctx) == 1
     b.close()
+
+
+@pytest.mark.gpu
+def test_serial_fallback_of_the_parallel_sweep_is_the_serial_sweep(monkeypatch):
+    """When the condensed system of the leg-parallel sweep cannot be factorised (a cost-to-go that is not positive definite)
+    pass 4 runs the serial sweep for that instance. SMPC_LEGS_FORCE_FALLBACK takes that branch for every instance: results
+    are bitwise those of a context that runs the serial sweep, and smpc_solve_info.flags carries bit 2."""
+    from smpc_ctypes import load_cuda
+    cu = load_cuda()
+
+    def run(legs, force):
+        if legs:
+            monkeypatch.setenv("SMPC_LEGS", str(legs))
+        else:
+            monkeypatch.delenv("SMPC_LEGS", raising=False)
+        if force:
+            monkeypatch.setenv("SMPC_LEGS_FORCE_FALLBACK", "1")
+        else:
+            monkeypatch.delenv("SMPC_LEGS_FORCE_FALLBACK", raising=False)
+        sc = pu.Go2Scenario(2, 4)
+        opts = SolverOpts()
+        cu.smpc_default_solver_opts(C.byref(opts))
+        b = pu.Backend(cu, "smpc", sc.model, sc.ocpb, opts, 2)
+        assert cu.smpc_riccati_legs(b.ctx) == (legs or 1)
+        b.set_slots(sc.initial_slots())
+        b.set_terminal(sc.terminals())
+        b.set_warmstart(*sc.warmstart())
+        b.solve(np.tile(sc.xref, (2, 1)), 100)
+        out = [np.array(a) for a in b.results()] + [[i.flags for i in b.info()]]
+        b.close()
+        return out
+
+    ser, fb = run(0, False), run(5, True)
+    assert all(np.array_equal(a, c) for a, c in zip(ser[:4], fb[:4]))
+    assert all(f & 4 for f in fb[4]) and not any(f & 4 for f in ser[4])
