@@ -405,71 +405,51 @@ def main():
                                "hz_per_instance_device": K / dev_s, "target_hz": 100}
     solo = rank == 0 and world == 1 and not strong
     if solo and not args.no_latency:
-        # single-instance latency through the C ABI with host buffers (p50 / p99 over 200 ticks)
-        sc1 = make_scenario(cfg, 1, seed=0)
-        b1 = setup_backend(cu, "smpc", sc1, 1, local_rank)
-        x1 = np.ascontiguousarray(sc1.xmeas_start())
-        assert cu.smpc_mpc_use_graph(b1.ctx, 0) == 0  # plain launches first: the per-kernel event timers only exist outside the graph
-        lat = []
-        for k in range(220):
-            t1 = time.perf_counter()
-            assert cu.smpc_mpc_iterate(b1.ctx, P(x1), 1) == 0
-            h = b1.head()[0]
-            lat.append(time.perf_counter() - t1)
-            x1 = np.ascontiguousarray(sc1.next_measurement(x1, h, None))
-        lat = np.array(lat[20:]) * 1e3
-        k1, n1 = (C.c_double * 4)(), C.c_int64()
-        cu.smpc_kernel_times(b1.ctx, k1)
-        cu.smpc_timer_stats(b1.ctx, 0, None, None, None, C.byref(n1))
-        out["latency_ms"] = {"batch": 1, "p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
-                             "what": "smpc_mpc_iterate + head read-back through host buffers, one host synchronisation per tick",
-                             "device_ms": {"linearisation": k1[0] / max(n1.value, 1), "riccati": k1[1] / max(n1.value, 1),
-                                           "forward": k1[2] / max(n1.value, 1), "trial+decision": k1[3] / max(n1.value, 1)},
-                             "riccati_variant": cu.smpc_riccati_variant(b1.ctx).decode()}
-        # the same loop with the tick replayed as ONE CUDA Graph (smpc_mpc_use_graph): A/B of the launch mechanics
-        assert cu.smpc_mpc_use_graph(b1.ctx, 1) == 0
-        latg = []
-        for k in range(220):
-            t1 = time.perf_counter()
-            assert cu.smpc_mpc_iterate(b1.ctx, P(x1), 1) == 0, cu.smpc_last_error()
-            h = b1.head()[0]
-            latg.append(time.perf_counter() - t1)
-            x1 = np.ascontiguousarray(sc1.next_measurement(x1, h, None))
-        latg = np.array(latg[20:]) * 1e3
-        out["latency_ms"]["cuda_graph"] = {"p50": float(np.percentile(latg, 50)), "p99": float(np.percentile(latg, 99)),
-                                           "what": "same loop, smpc_mpc_use_graph(1) - the default for batches up to the SM count: one graph launch per tick, the head of the plan copied to pinned memory by the graph"}
-        b1.close()
+        # single-instance latency through the C ABI with host buffers (p50 / p99 over 200 ticks). Every row starts from a
+        # fresh context on the same scenario, so all rows see the same sequence of ticks
+        def latency_row(graph, legs):
+            sc1 = make_scenario(cfg, 1, seed=0)
+            if legs > 1:
+                os.environ["SMPC_LEGS"] = str(legs)  # measure every supported shape, also those for which the serial sweep stays the default
+            b1 = setup_backend(cu, "smpc", sc1, 1, local_rank, num_threads=max(legs, 1))
+            os.environ.pop("SMPC_LEGS", None)
+            row = None
+            if legs <= 1 or cu.smpc_riccati_legs(b1.ctx) == legs:
+                assert cu.smpc_mpc_use_graph(b1.ctx, graph) == 0
+                cu.smpc_timer_stats(b1.ctx, 1, None, None, None, None)
+                x1 = np.ascontiguousarray(sc1.xmeas_start())
+                lat = []
+                for k in range(220):
+                    t1 = time.perf_counter()
+                    assert cu.smpc_mpc_iterate(b1.ctx, P(x1), 1) == 0, cu.smpc_last_error()
+                    h = b1.head()[0]
+                    lat.append(time.perf_counter() - t1)
+                    x1 = np.ascontiguousarray(sc1.next_measurement(x1, h, None))
+                lat = np.array(lat[20:]) * 1e3
+                row = {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99))}
+                if not graph:  # the per-kernel event timers only exist outside the graph
+                    k1, n1 = (C.c_double * 4)(), C.c_int64()
+                    cu.smpc_kernel_times(b1.ctx, k1)
+                    cu.smpc_timer_stats(b1.ctx, 0, None, None, None, C.byref(n1))
+                    row["device_ms"] = {"linearisation": k1[0] / max(n1.value, 1), "riccati": k1[1] / max(n1.value, 1),
+                                        "forward": k1[2] / max(n1.value, 1), "trial+decision": k1[3] / max(n1.value, 1)}
+                row["riccati_variant"] = cu.smpc_riccati_variant(b1.ctx).decode()
+            b1.close()
+            return row
+
+        plain, graph = latency_row(0, 1), latency_row(1, 1)
+        out["latency_ms"] = {"batch": 1, "p50": plain["p50"], "p99": plain["p99"],
+                             "what": "smpc_mpc_iterate + head read-back through host buffers, plain launches, one host synchronisation per tick",
+                             "device_ms": plain["device_ms"], "riccati_variant": plain["riccati_variant"],
+                             "cuda_graph": {"p50": graph["p50"], "p99": graph["p99"],
+                                            "what": "same ticks, smpc_mpc_use_graph(1) - the default for batches up to the SM count: one graph launch per tick, the head of the plan copied to pinned memory by the graph"}}
         # MPCSettings::num_threads > 1 = the PARALLEL (leg-condensed) Riccati sweep, one CTA per leg (csrc/riccati_par.cuh)
         par = []
         for legs in (5, 10, 20):
-            scp = make_scenario(cfg, 1, seed=0)
-            os.environ["SMPC_LEGS"] = str(legs)  # measure every supported shape, also those for which the serial sweep stays the default
-            bp = setup_backend(cu, "smpc", scp, 1, local_rank, num_threads=legs)
-            del os.environ["SMPC_LEGS"]
-            used = cu.smpc_riccati_legs(bp.ctx)
-            if used > 1:
-                xp = np.ascontiguousarray(scp.xmeas_start())
-                for graph in (0, 1):
-                    assert cu.smpc_mpc_use_graph(bp.ctx, graph) == 0
-                    cu.smpc_timer_stats(bp.ctx, 1, None, None, None, None)
-                    latp = []
-                    for k in range(220):
-                        t1 = time.perf_counter()
-                        assert cu.smpc_mpc_iterate(bp.ctx, P(xp), 1) == 0, cu.smpc_last_error()
-                        h = bp.head()[0]
-                        latp.append(time.perf_counter() - t1)
-                        xp = np.ascontiguousarray(scp.next_measurement(xp, h, None))
-                    latp = np.array(latp[20:]) * 1e3
-                    if graph == 0:
-                        kp, npk = (C.c_double * 4)(), C.c_int64()
-                        cu.smpc_kernel_times(bp.ctx, kp)
-                        cu.smpc_timer_stats(bp.ctx, 0, None, None, None, C.byref(npk))
-                        ric_ms = kp[1] / max(npk.value, 1)
-                    else:
-                        par.append({"legs": used, "p50": float(np.percentile(latp, 50)), "p99": float(np.percentile(latp, 99)),
-                                    "riccati_device_ms": ric_ms})
-            bp.close()
-        out["latency_ms"]["parallel_riccati"] = {"what": "same loop (one graph launch per tick) with smpc_solver_opts.num_threads = legs: four launches per backward sweep, one CTA per leg; riccati_device_ms from the event timers of the plain-launch loop", "rows": par}
+            rp, rg = latency_row(0, legs), latency_row(1, legs)
+            if rp and rg:
+                par.append({"legs": legs, "p50": rg["p50"], "p99": rg["p99"], "riccati_device_ms": rp["device_ms"]["riccati"]})
+        out["latency_ms"]["parallel_riccati"] = {"what": "same ticks (one graph launch per tick) with smpc_solver_opts.num_threads = legs: four launches per backward sweep, one CTA per leg; riccati_device_ms from the event timers of a plain-launch run", "rows": par}
     if solo and not args.no_latency and cfg == "c5":
         # north_star target: 4096 instances at >= 100 Hz on 8 GPUs = 512 instances per GPU with a tick <= 10 ms.
         # Ticks of a 512-instance context on this one GPU, end to end through host buffers (the 8-GPU run itself is
