@@ -769,6 +769,20 @@ static int create_impl(smpc_ctx * c, int device, int batch, const smpc_model_des
   CU(cudaDeviceGetAttribute(&c->hmodel_sms, cudaDevAttrMultiProcessorCount, device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   Arrays & A = c->A;
+  // Row capacity of the problem rounded UP to the nearest shape with a tuned Riccati sweep: rows beyond a stage's active count
+  // are zero-padded anyway, and the padded sweep is several times faster than the run-time-shape sweep a configuration without
+  // any inequality would otherwise fall to (the reference's benchmark/go2.cpp: no limits, no cones -> capacity 1; its
+  // single-instance MPC::iterate went 7.05 -> 1.97 ms on the (36, 12, 24) sweep, profiles/r02ab, r02ad). SMPC_RICCATI != default keeps the exact capacity.
+  if (!getenv("SMPC_RICCATI"))
+  {
+    static const int tuned[][3] = {{36, 24, 24}, {36, 24, 36}, {36, 12, 24}, {36, 12, 60}, {56, 22, 44}, {56, 22, 78}, {56, 34, 34}, {56, 34, 46}, {9, 12, 8}, {9, 12, 34}};
+    int best = 0;
+    for (const auto & t : tuned)
+      if (t[0] == c->hocp.ndx && t[1] == c->hocp.nu && t[2] >= c->hocp.ncmax && (best == 0 || t[2] < best))
+        best = t[2];
+    if (best > 0)
+      c->hocp.ncmax = best;
+  }
   const DevOcp & O = c->hocp;
   A.dm = Dims{batch, O.N, O.nx, O.ndx, O.nu, O.ncmax, O.nk};
   A.L = make_knot_layout(O.ndx, O.nu, O.ncmax);
