@@ -167,6 +167,10 @@ namespace smpc
     double * psi = sm + RS.opsi;
     double * invr = sm + RS.oinvd;
     double * invs = invr + nu;
+    double * sPt = sm + RS.osPt;
+    double * sA = sm + RS.osA;
+    double * sB = sm + RS.osB;
+    double * sK = sm + RS.osK;
     int * bad = (int *)(sm + RS.oflag);
     SMPC_PAR(tid)
     {
@@ -185,11 +189,27 @@ namespace smpc
     {
       const double * kn = knots + (size_t)t * L.size;
       const double * so = sol + (size_t)t * SL.size;
-      const double * Pt = so + SL.oPt;
-      const double * Kk = so + SL.oK;
-      const double * Ak = kn + L.oA;
-      const double * Bk = kn + L.oB;
       const int nc = ncs[t];
+      // stage the operands (coalesced, all loads independent): with the products reading global memory the kernel spent
+      // 5 warp-cycles per issue waiting on the long scoreboard (profiles/r02y)
+      SMPC_PAR(tid)
+      {
+        for (int e = tid; e < n * n; e += SMPC_NT)
+        {
+          sPt[e] = so[SL.oPt + e];
+          sA[e] = kn[L.oA + e];
+        }
+        for (int e = tid; e < n * nu; e += SMPC_NT)
+        {
+          sB[e] = kn[L.oB + e];
+          sK[e] = so[SL.oK + e];
+        }
+      }
+      SMPC_END
+      const double * Pt = sPt;
+      const double * Kk = sK;
+      const double * Ak = sA;
+      const double * Bk = sB;
       // Pi~ = Pi+ - mu P~ Pi+ ; P~ B ; v = B k + f
       SMPC_PAR(tid)
       {

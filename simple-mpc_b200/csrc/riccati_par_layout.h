@@ -15,7 +15,7 @@ namespace smpc
 
   struct ParSmem
   {
-    int oPi, oPit, oLam, oY, oX, oRh, oW, oSg, oG, ov, ophi, opsi, oinvd, oflag, size;
+    int oPi, oPit, oLam, oY, oX, oRh, oW, oSg, oG, ov, ophi, opsi, oinvd, osPt, osA, osB, osK, oflag, size;
   };
   inline ParSmem make_par_smem(int ndx, int nu, int ncmax)
   {
@@ -34,6 +34,12 @@ namespace smpc
     R.ophi = o, o += ndx;
     R.opsi = o, o += ndx;
     R.oinvd = o, o += nu + ncmax; // inverse pivots of R^ and of Sigma
+    o += o & 1;
+    // the stage's operands from HBM / L2 (P~, A, B, K), staged once per stage: every product then reads shared memory only
+    R.osPt = o, o += ndx * ndx;
+    R.osA = o, o += ndx * ndx;
+    R.osB = o, o += ndx * nu;
+    R.osK = o, o += nu * ndx;
     R.oflag = o, o += 2;
     R.size = o;
     return R;
