@@ -1,0 +1,1258 @@
+// id_qp.cuh — one CTA solves one whole-body inverse-dynamics QP (the reference's KinodynamicsID::solve /
+// CentroidalID, src/inverse-dynamics/kinodynamics-id.cpp:188-232; TSID acceleration/force formulation + dense QP).
+//
+// Everything lives in shared memory (sized at context creation from the robot and the settings, IdDims):
+//   phase group 1  world-frame kinematics by tree level, body inertias, composite inertias (CRBA), bias forces (RNEA with
+//                  a = 0): joint-space inertia M and nonlinear effects h
+//   phase group 2  the tasks of the formulation, one <= 6-row block at a time (frame Jacobian in the LOCAL or the
+//                  world-oriented frame, desired acceleration, drift): H += w J^T J, g -= w J^T b; contact blocks also
+//                  write their columns of Jc^T T, their cone rows and (when motion is a hard constraint) equality rows
+//   phase group 3  proximal method of multipliers with a semismooth-Newton inner loop on
+//                    min 1/2 x'Hx + g'x  s.t.  A x = b,  l <= C x <= u        x = [a; f]
+//                  (dense Newton matrix K = H + rho I + (A'A + C_act'C_act)/mu factorised by a one-barrier-per-column
+//                  left-looking Cholesky), tau = M_a a + h_a - (Jc^T T)_a f
+// Written in the SMPC_PAR phase discipline of par.cuh, so tests/host_emul compiles it for the CPU.
+// Algorithm, constants and task definitions follow oracle/orc_id.hpp (which cites TSID); the comparison with the oracle is
+// at solution level (both solve the same strictly convex QP to a relative KKT residual of 1e-9).
+#pragma once
+#include "dev_math.cuh"
+#include "dev_types.h"
+#include "../../include/smpc_id.h"
+
+namespace smpc
+{
+
+  constexpr double ID_HESSIAN_REG = 1e-8;
+  constexpr double ID_BIG = 1e10;
+  constexpr double ID_DDQ_MAX = 1e10;
+  constexpr double ID_QP_EPS = 1e-9;
+  constexpr double ID_QP_RHO = 1e-10;
+  constexpr double ID_QP_MU0 = 1e-2;
+  constexpr double ID_QP_MU_MIN = 1e-4;
+  constexpr double ID_QP_GRAD_REL = 1e-13;
+  constexpr int ID_QP_MAX_OUTER = 30;
+  constexpr int ID_QP_MAX_INNER = 30;
+  constexpr int ID_QP_MAX_NEWTON = 200;
+
+  // per-instance target (what setTarget stores in the TSID tasks)
+  struct IdTargetDev
+  {
+    double q_post[SMPC_MAX_NV], v_post[SMPC_MAX_NV], a_post[SMPC_MAX_NV];
+    double base_R[9], base_p[3];
+    double base_vel[6], base_acc[6];
+    double f_ref[SMPC_MAX_FEET][6];
+    double com_ref[3], com_vel[3];
+    double foot_R[SMPC_MAX_FEET][9], foot_p[SMPC_MAX_FEET][3], foot_vel[SMPC_MAX_FEET][6];
+    int active[SMPC_MAX_FEET];
+    int tracked[SMPC_MAX_FEET];
+  };
+
+  // shared-memory plan (offsets in doubles)
+  struct IdDims
+  {
+    int nj, nq, nv, na, nfeet;
+    int nfmax, nx, ldn, me, mi;
+    int o_q, o_v, o_M, o_h, o_JcT, o_H, o_g, o_A, o_b, o_C, o_l, o_u, o_Jt, o_bt, o_fr;
+    int o_x, o_xk, o_grad, o_dx, o_xt, o_hx, o_y, o_re, o_re2, o_z, o_si, o_si2, o_sc, o_act;
+    int o_K;                                 // Newton matrix; the kinematics scratch below aliases it
+    int o_oMi, o_Jw, o_ov, o_oa, o_Y, o_fs, o_Fc;
+    int total;
+  };
+
+  inline IdDims id_make_dims(const smpc_model_desc & m, const smpc_id_desc & D)
+  {
+    IdDims L;
+    L.nj = m.njoints, L.nq = m.nq, L.nv = m.nv, L.na = m.nv - 6, L.nfeet = m.nfeet;
+    int nf = 0, ncone = 0, nmot = 0;
+    for (int f = 0; f < m.nfeet; f++)
+    {
+      const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
+      nf += quad ? 12 : 3;
+      ncone += quad ? 17 : 5;
+      nmot += quad ? 6 : 3;
+    }
+    L.nfmax = nf;
+    L.nx = m.nv + nf;
+    L.ldn = L.nx | 1;
+    L.me = 6 + (D.settings.contact_motion_equality ? nmot : 0);
+    L.mi = ncone + 2 * L.na;
+    int o = 0;
+    auto take = [&](int n) {
+      const int at = o;
+      o += (n + 1) & ~1;
+      return at;
+    };
+    L.o_q = take(L.nq), L.o_v = take(L.nv);
+    L.o_M = take(L.nv * L.nv), L.o_h = take(L.nv), L.o_JcT = take(L.nv * (nf > 0 ? nf : 1));
+    L.o_H = take(L.nx * L.ldn), L.o_g = take(L.nx);
+    L.o_A = take(L.me * L.ldn), L.o_b = take(L.me);
+    L.o_C = take(L.mi * L.ldn), L.o_l = take(L.mi), L.o_u = take(L.mi);
+    L.o_Jt = take(6 * L.nv), L.o_bt = take(8), L.o_fr = take(48);
+    L.o_x = take(L.nx), L.o_xk = take(L.nx), L.o_grad = take(L.nx), L.o_dx = take(L.nx), L.o_xt = take(L.nx), L.o_hx = take(L.nx);
+    L.o_y = take(L.me), L.o_re = take(L.me), L.o_re2 = take(L.me);
+    L.o_z = take(L.mi), L.o_si = take(L.mi), L.o_si2 = take(L.mi);
+    L.o_sc = take(16);
+    L.o_act = take((L.mi + 2) / 2 + 1); // int list of the active inequality rows
+    L.o_K = o;
+    L.o_oMi = take(12 * L.nj), L.o_Jw = take(6 * L.nv), L.o_ov = take(6 * L.nj), L.o_oa = take(6 * L.nj);
+    L.o_Y = take(36 * L.nj), L.o_fs = take(6 * L.nj), L.o_Fc = take(6 * L.nv);
+    const int endK = L.o_K + ((L.nx * L.ldn + 1) & ~1);
+    L.total = o > endK ? o : endK;
+    return L;
+  }
+
+  // scalar slots in sm[o_sc + ...]
+  enum
+  {
+    SC_VAL = 0,
+    SC_VT,
+    SC_GN,
+    SC_GS,
+    SC_SLOPE,
+    SC_SAME,
+    SC_PRES,
+    SC_DRES,
+    SC_OK,
+    SC_BAD
+  };
+
+  // TaskJointPosVelAccBounds::computeAccLimits (position, velocity, viability; no acceleration bound) — oracle id_acc_bounds
+  SMPC_DEV void id_acc_bounds(double q, double dq, double qmin, double qmax, double dqmax, double dt, double & lb, double & ub)
+  {
+    const double two_dt_sq = 2.0 / (dt * dt);
+    const double max_q3 = two_dt_sq * (qmax - q - dt * dq);
+    const double min_q3 = two_dt_sq * (qmin - q - dt * dq);
+    const double mdq_dt = -dq / dt;
+    double lbp, ubp;
+    if (dq <= 0.0)
+    {
+      ubp = max_q3;
+      if (min_q3 < mdq_dt)
+        lbp = min_q3;
+      else if (q != qmin)
+        lbp = fmax(dq * dq / (2.0 * (q - qmin)), mdq_dt);
+      else
+        lbp = ID_BIG;
+    }
+    else
+    {
+      lbp = min_q3;
+      if (max_q3 > mdq_dt)
+        ubp = max_q3;
+      else if (q != qmax)
+        ubp = fmin(-dq * dq / (2.0 * (qmax - q)), mdq_dt);
+      else
+        ubp = -ID_BIG;
+    }
+    const double lbv = (-dqmax - dq) / dt, ubv = (dqmax - dq) / dt;
+    const double dt2 = dt * dt, two_a = 2.0 * dt2, qn = q + dt * dq;
+    const double b1 = 2.0 * dt * dq + ID_DDQ_MAX * dt2;
+    const double c1 = dq * dq - 2.0 * ID_DDQ_MAX * (qmax - qn);
+    const double d1 = b1 * b1 - 2.0 * two_a * c1;
+    double ddq1 = mdq_dt;
+    if (d1 >= 0.0)
+      ddq1 = (b1 >= 0.0) ? (-2.0 * c1) / (b1 + sqrt(d1)) : (-b1 + sqrt(d1)) / two_a;
+    const double b2 = 2.0 * dt * dq - ID_DDQ_MAX * dt2;
+    const double c2 = 2.0 * ID_DDQ_MAX * (qn - qmin) - dq * dq;
+    const double d2 = b2 * b2 - 2.0 * two_a * c2;
+    double ddq2 = mdq_dt;
+    if (d2 >= 0.0)
+      ddq2 = (b2 <= 0.0) ? (2.0 * c2) / (-b2 + sqrt(d2)) : (-b2 - sqrt(d2)) / two_a;
+    const double ubvia = fmax(ddq1, mdq_dt), lbvia = fmin(ddq2, mdq_dt);
+    lb = fmax(fmax(lbp, lbv), fmax(lbvia, -ID_BIG));
+    ub = fmin(fmin(ubp, ubv), fmin(ubvia, ID_BIG));
+    if (ub < lb)
+    {
+      const double mid = (dq <= 0.0) ? lb : ub;
+      lb = ub = mid;
+    }
+  }
+
+  // y = Y6 x for a dense row-major 6x6
+  SMPC_DEV void id_m6v(const double * Y, const double * x, double * y)
+  {
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+    {
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < 6; c++)
+        s += Y[6 * r + c] * x[c];
+      y[r] = s;
+    }
+  }
+
+  // ---- phase group 1: M and h ------------------------------------------------------------------------------------
+  SMPC_DEV void id_dynamics(const DevModel & Mo, const IdDims & L, double * sm)
+  {
+    const smpc_model_desc & d = Mo.d;
+    const int nj = L.nj, nv = L.nv;
+    double * qs = sm + L.o_q;
+    double * vs = sm + L.o_v;
+    double * oMi = sm + L.o_oMi;
+    double * Jw = sm + L.o_Jw; // 6 x nv, row-major
+    double * ov = sm + L.o_ov;
+    double * oa = sm + L.o_oa;
+    double * Y = sm + L.o_Y;
+    double * fs = sm + L.o_fs;
+    double * Fc = sm + L.o_Fc;
+    double * Mm = sm + L.o_M;
+    double * h = sm + L.o_h;
+    for (int l = 0; l < Mo.nlevels; l++)
+    {
+      SMPC_PAR(tid)
+      for (int k = Mo.level_start[l] + tid; k < Mo.level_start[l + 1]; k += SMPC_NT)
+      {
+        const int i = Mo.level_joints[k];
+        const int p = d.parent[i];
+        const int iv = d.idx_v[i];
+        double Rj[9], pj[3] = {0, 0, 0};
+        const bool ff = d.jtype[i] == SMPC_JOINT_FREEFLYER;
+        if (ff)
+        {
+          const double * qq = qs + d.idx_q[i];
+          quat_to_R(qq + 3, Rj);
+          pj[0] = qq[0], pj[1] = qq[1], pj[2] = qq[2];
+        }
+        else
+        {
+          const double ang = qs[d.idx_q[i]];
+          const double s = sin(ang), c = cos(ang);
+          double W[9], W2[9];
+          skew(d.axis[i], W);
+          m3m(W, W, W2);
+#pragma unroll
+          for (int e = 0; e < 9; e++)
+            Rj[e] = ((e % 4 == 0) ? 1.0 : 0.0) + s * W[e] + (1 - c) * W2[e];
+        }
+        // liMi = placement * joint motion ; oMi = oMp * liMi
+        double Rl[9], pl[3], t3[3];
+        m3m(d.place_R[i], Rj, Rl);
+        m3v(d.place_R[i], pj, t3);
+        for (int e = 0; e < 3; e++)
+          pl[e] = d.place_p[i][e] + t3[e];
+        double * Ri = oMi + 12 * i;
+        double * pi = Ri + 9;
+        if (p < 0)
+        {
+          for (int e = 0; e < 9; e++)
+            Ri[e] = Rl[e];
+          for (int e = 0; e < 3; e++)
+            pi[e] = pl[e];
+        }
+        else
+        {
+          const double * Rp = oMi + 12 * p;
+          double Rn[9];
+          m3m(Rp, Rl, Rn);
+          m3v(Rp, pl, t3);
+          for (int e = 0; e < 9; e++)
+            Ri[e] = Rn[e];
+          for (int e = 0; e < 3; e++)
+            pi[e] = Rp[9 + e] + t3[e];
+        }
+        // world-frame Jacobian columns, joint velocity, body velocity / drift acceleration
+        double vJ[6] = {0, 0, 0, 0, 0, 0};
+        const int ndof = ff ? 6 : 1;
+        for (int c = 0; c < ndof; c++)
+        {
+          double S[6] = {0, 0, 0, 0, 0, 0};
+          if (ff)
+            S[c] = 1;
+          else
+            S[3] = d.axis[i][0], S[4] = d.axis[i][1], S[5] = d.axis[i][2];
+          double Rv[3], Rw[3], pxw[3];
+          m3v(Ri, S, Rv);
+          m3v(Ri, S + 3, Rw);
+          v3cross(pi, Rw, pxw);
+          for (int e = 0; e < 3; e++)
+          {
+            const double lin = Rv[e] + pxw[e];
+            Jw[e * nv + iv + c] = lin;
+            Jw[(3 + e) * nv + iv + c] = Rw[e];
+            vJ[e] += lin * vs[iv + c];
+            vJ[3 + e] += Rw[e] * vs[iv + c];
+          }
+        }
+        double vi[6], ai[6], x6[6];
+        for (int e = 0; e < 6; e++)
+          vi[e] = (p >= 0 ? ov[6 * p + e] : 0.0) + vJ[e];
+        mxm(vi, vJ, x6);
+        for (int e = 0; e < 6; e++)
+        {
+          ai[e] = (p >= 0 ? oa[6 * p + e] : 0.0) + x6[e];
+          ov[6 * i + e] = vi[e];
+          oa[6 * i + e] = ai[e];
+        }
+        // world-frame body inertia [[m I, -m[c]x], [m[c]x, Ic - m[c]x[c]x]], bias force I a + v x* (I v)
+        double cw[3], Icw[9], T[9], Cx[9], CC[9];
+        m3v(Ri, d.lever[i], cw);
+        for (int e = 0; e < 3; e++)
+          cw[e] += pi[e];
+        m3m(Ri, d.inertia[i], T);
+        m3mt(T, Ri, Icw);
+        skew(cw, Cx);
+        m3m(Cx, Cx, CC);
+        double * I6 = Y + 36 * i;
+        const double ms = d.mass[i];
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++)
+          {
+            I6[6 * r + c] = (r == c) ? ms : 0.0;
+            I6[6 * r + 3 + c] = -ms * Cx[3 * r + c];
+            I6[6 * (3 + r) + c] = ms * Cx[3 * r + c];
+            I6[6 * (3 + r) + 3 + c] = Icw[3 * r + c] - ms * CC[3 * r + c];
+          }
+        double hi[6], Ia[6], vxh[6];
+        id_m6v(I6, vi, hi);
+        id_m6v(I6, ai, Ia);
+        mxf(vi, hi, vxh);
+        for (int e = 0; e < 6; e++)
+          fs[6 * i + e] = Ia[e] + vxh[e];
+      }
+      SMPC_END
+    }
+    // composite inertias and subtree bias forces, deepest level first; each (parent, entry) sums its children in index order
+    for (int l = Mo.nlevels - 2; l >= 0; l--)
+    {
+      SMPC_PAR(tid)
+      const int n0 = Mo.level_start[l], cnt = Mo.level_start[l + 1] - n0;
+      for (int idx = tid; idx < cnt * 42; idx += SMPC_NT)
+      {
+        const int p = Mo.level_joints[n0 + idx / 42], e = idx % 42;
+        double * dst = (e < 36) ? &Y[36 * p + e] : &fs[6 * p + e - 36];
+        double s = *dst;
+        for (int c = p + 1; c < nj; c++)
+          if (d.parent[c] == p)
+            s += (e < 36) ? Y[36 * c + e] : fs[6 * c + e - 36];
+        *dst = s;
+      }
+      SMPC_END
+    }
+    SMPC_PAR(tid)
+    for (int idx = tid; idx < 6 * nv; idx += SMPC_NT)
+    {
+      const int r = idx / nv, c = idx % nv;
+      const double * Yi = Y + 36 * Mo.joint_of_dof[c] + 6 * r;
+      double s = 0;
+#pragma unroll
+      for (int e = 0; e < 6; e++)
+        s += Yi[e] * Jw[e * nv + c];
+      Fc[r * nv + c] = s;
+    }
+    SMPC_END
+    SMPC_PAR(tid)
+    for (int idx = tid; idx < nv * nv + nv; idx += SMPC_NT)
+    {
+      if (idx < nv * nv)
+      {
+        const int j = idx / nv, c = idx % nv;
+        if (j > c)
+          continue;
+        double s = 0;
+        if ((Mo.anc_mask[Mo.joint_of_dof[c]] >> Mo.joint_of_dof[j]) & 1u)
+        {
+#pragma unroll
+          for (int e = 0; e < 6; e++)
+            s += Jw[e * nv + j] * Fc[e * nv + c];
+        }
+        Mm[j * nv + c] = s;
+        Mm[c * nv + j] = s;
+      }
+      else
+      {
+        const int c = idx - nv * nv;
+        const int i = Mo.joint_of_dof[c];
+        const double g6[6] = {0, 0, -9.81, 0, 0, 0};
+        double Yg[6];
+        id_m6v(Y + 36 * i, g6, Yg);
+        double s = 0;
+#pragma unroll
+        for (int e = 0; e < 6; e++)
+          s += Jw[e * nv + c] * (fs[6 * i + e] - Yg[e]);
+        h[c] = s;
+      }
+    }
+    SMPC_END
+  }
+
+  // LOCAL-frame Jacobian (into Jt, 6 x nv), velocity and classical drift of the frame (Rl, pl) carried by joint jf.
+  // fr[0..8] = R, fr[9..11] = p (world placement), fr[12..17] = v_local, fr[18..23] = drift_local
+  SMPC_DEV void id_frame(const DevModel & Mo, const IdDims & L, double * sm, int jf, const double * Rl, const double * pl)
+  {
+    const int nv = L.nv;
+    double * fr = sm + L.o_fr;
+    const double * oMi = sm + L.o_oMi + 12 * jf;
+    SMPC_PAR(tid)
+    if (tid == 0)
+    {
+      double R[9], t[3], p[3];
+      m3m(oMi, Rl, R);
+      m3v(oMi, pl, t);
+      for (int e = 0; e < 3; e++)
+        p[e] = oMi[9 + e] + t[e];
+      for (int e = 0; e < 9; e++)
+        fr[e] = R[e];
+      for (int e = 0; e < 3; e++)
+        fr[9 + e] = p[e];
+      const double * v = sm + L.o_ov + 6 * jf;
+      const double * a = sm + L.o_oa + 6 * jf;
+      double pd[3], pdd[3], t1[3], t2[3];
+      v3cross(v + 3, p, t);
+      for (int e = 0; e < 3; e++)
+        pd[e] = v[e] + t[e];
+      v3cross(a + 3, p, t1);
+      v3cross(v + 3, pd, t2);
+      for (int e = 0; e < 3; e++)
+        pdd[e] = a[e] + t1[e] + t2[e];
+      m3tv(R, pd, fr + 12);
+      m3tv(R, v + 3, fr + 15);
+      m3tv(R, pdd, fr + 18);
+      m3tv(R, a + 3, fr + 21);
+    }
+    SMPC_END
+    SMPC_PAR(tid)
+    const double * Jw = sm + L.o_Jw;
+    double * Jt = sm + L.o_Jt;
+    for (int c = tid; c < nv; c += SMPC_NT)
+    {
+      double a3[3] = {0, 0, 0}, b3[3] = {0, 0, 0};
+      if ((Mo.anc_mask[jf] >> Mo.joint_of_dof[c]) & 1u)
+      {
+        const double lin0[3] = {Jw[c], Jw[nv + c], Jw[2 * nv + c]};
+        const double ang[3] = {Jw[3 * nv + c], Jw[4 * nv + c], Jw[5 * nv + c]};
+        double t[3], lin[3];
+        v3cross(ang, fr + 9, t);
+        for (int e = 0; e < 3; e++)
+          lin[e] = lin0[e] + t[e];
+        m3tv(fr, lin, a3);
+        m3tv(fr, ang, b3);
+      }
+      for (int e = 0; e < 3; e++)
+      {
+        Jt[e * nv + c] = a3[e];
+        Jt[(3 + e) * nv + c] = b3[e];
+      }
+    }
+    SMPC_END
+  }
+
+  // H += w Jt(rows)^T Jt(rows) on the acceleration block, g -= w Jt(rows)^T bt(rows)
+  SMPC_DEV void id_add_motion_task(const IdDims & L, double * sm, double w, int r0, int r1)
+  {
+    const int nv = L.nv, ld = L.ldn;
+    SMPC_PAR(tid)
+    const double * Jt = sm + L.o_Jt;
+    const double * bt = sm + L.o_bt;
+    double * H = sm + L.o_H;
+    double * g = sm + L.o_g;
+    for (int idx = tid; idx < nv * nv + nv; idx += SMPC_NT)
+    {
+      if (idx < nv * nv)
+      {
+        const int i = idx / nv, j = idx % nv;
+        double s = H[i * ld + j];
+        for (int r = r0; r < r1; r++)
+          s += (w * Jt[r * nv + i]) * Jt[r * nv + j];
+        H[i * ld + j] = s;
+      }
+      else
+      {
+        const int i = idx - nv * nv;
+        double s = g[i];
+        for (int r = r0; r < r1; r++)
+          s -= (w * Jt[r * nv + i]) * bt[r];
+        g[i] = s;
+      }
+    }
+    SMPC_END
+  }
+
+  // ---- phase group 2: the QP data -----------------------------------------------------------------------------------
+  // returns the layout through sm[o_sc + 10..12] = n, me, mi (as doubles) — written by thread 0
+  SMPC_DEV void id_build_qp(const DevModel & Mo, const smpc_id_desc & D, const IdTargetDev & T, const IdDims & L, double * sm, int & n_out, int & me_out, int & mi_out)
+  {
+    const smpc_model_desc & d = Mo.d;
+    const smpc_id_settings & S = D.settings;
+    const int nv = L.nv, na = L.na, nfeet = L.nfeet, ld = L.ldn;
+    double * H = sm + L.o_H;
+    double * g = sm + L.o_g;
+    double * A = sm + L.o_A;
+    double * bq = sm + L.o_b;
+    double * Cm = sm + L.o_C;
+    double * lo = sm + L.o_l;
+    double * up = sm + L.o_u;
+    double * Jt = sm + L.o_Jt;
+    double * bt = sm + L.o_bt;
+    double * fr = sm + L.o_fr;
+    double * JcT = sm + L.o_JcT;
+    const double * Mm = sm + L.o_M;
+    const double * h = sm + L.o_h;
+    const double * qs = sm + L.o_q;
+    const double * vs = sm + L.o_v;
+    // variable layout (uniform over the CTA: computed redundantly by every thread)
+    int foff[SMPC_MAX_FEET], fdim[SMPC_MAX_FEET], nf = 0, ncone = 0, nmot = 0;
+    for (int f = 0; f < nfeet; f++)
+    {
+      foff[f] = nv + nf;
+      fdim[f] = 0;
+      if (!T.active[f])
+        continue;
+      const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
+      fdim[f] = quad ? 12 : 3;
+      nf += fdim[f];
+      ncone += quad ? 17 : 5;
+      nmot += quad ? 6 : 3;
+    }
+    const int n = nv + nf;
+    const int me = 6 + (S.contact_motion_equality ? nmot : 0);
+    const int mi = ncone + 2 * na;
+    const int ldf = nf > 0 ? nf : 1;
+    n_out = n, me_out = me, mi_out = mi;
+    const double weight = Mo.total_mass * 9.81;
+    const double fmaxn = S.contact_weight_ratio_max * weight, fminn = S.contact_weight_ratio_min * weight;
+
+    SMPC_PAR(tid)
+    for (int idx = tid; idx < n * ld; idx += SMPC_NT)
+      H[idx] = (idx / ld == idx % ld) ? ID_HESSIAN_REG : 0.0;
+    for (int idx = tid; idx < n; idx += SMPC_NT)
+      g[idx] = 0.0;
+    for (int idx = tid; idx < me * ld; idx += SMPC_NT)
+      A[idx] = 0.0;
+    for (int idx = tid; idx < mi * ld; idx += SMPC_NT)
+      Cm[idx] = 0.0;
+    SMPC_END
+
+    // posture task: diagonal
+    if (S.w_posture > 0.)
+    {
+      SMPC_PAR(tid)
+      const double kp = S.kp_posture, kd = 2.0 * sqrt(kp);
+      for (int j = tid; j < na; j += SMPC_NT)
+      {
+        const double ades = -kp * (qs[7 + j] - T.q_post[j]) - kd * (vs[6 + j] - T.v_post[j]) + T.a_post[j];
+        H[(6 + j) * ld + 6 + j] += S.w_posture;
+        g[6 + j] -= S.w_posture * ades;
+      }
+      SMPC_END
+    }
+    // base task (LOCAL frame; velocity reference = acceleration target, reference quirk)
+    if (S.w_base > 0.)
+    {
+      id_frame(Mo, L, sm, d.base_joint, d.base_R, d.base_p);
+      SMPC_PAR(tid)
+      if (tid == 0)
+      {
+        const double kp = S.kp_base, kd = 2.0 * sqrt(kp);
+        double Rr[9], dp[3], pr[3], e6[6];
+        m3tm(fr, T.base_R, Rr);
+        for (int e = 0; e < 3; e++)
+          dp[e] = T.base_p[e] - fr[9 + e];
+        m3tv(fr, dp, pr);
+        log6(Rr, pr, e6);
+        for (int r = 0; r < 6; r++)
+          bt[r] = kp * e6[r] + kd * (T.base_acc[r] - fr[12 + r]) - fr[18 + r];
+      }
+      SMPC_END
+      id_add_motion_task(L, sm, S.w_base, S.centroidal ? 3 : 0, 6);
+    }
+    // centre-of-mass task
+    if (S.centroidal && S.w_com > 0.)
+    {
+      SMPC_PAR(tid)
+      const double * Y = sm + L.o_Y;
+      const double * Jw = sm + L.o_Jw;
+      const double Mtot = Y[0];
+      for (int c = tid; c < nv; c += SMPC_NT)
+      {
+        const int i = Mo.joint_of_dof[c];
+        const double * Yi = Y + 36 * i;
+        const double msub = Yi[0];
+        const double cs[3] = {Yi[6 * 5 + 1] / msub, Yi[6 * 3 + 2] / msub, Yi[6 * 4 + 0] / msub};
+        const double ang[3] = {Jw[3 * nv + c], Jw[4 * nv + c], Jw[5 * nv + c]};
+        double t[3];
+        v3cross(ang, cs, t);
+        for (int e = 0; e < 3; e++)
+          Jt[e * nv + c] = (msub / Mtot) * (Jw[e * nv + c] + t[e]);
+      }
+      if (tid == 0)
+      { // com / drift from the composite inertia and the subtree bias force of the root; -kd * vcom is added below
+        const double kp = S.kp_com, kd = 2.0 * sqrt(kp);
+        const double * fs0 = sm + L.o_fs;
+        for (int r = 0; r < 3; r++)
+        {
+          const double com = Y[(r == 0) ? 6 * 5 + 1 : (r == 1) ? 6 * 3 + 2 : 6 * 4 + 0] / Mtot;
+          bt[r] = -kp * (com - T.com_ref[r]) + kd * T.com_vel[r] - fs0[r] / Mtot;
+        }
+        bt[6] = kd;
+      }
+      SMPC_END
+      SMPC_PAR(tid)
+      if (tid < 3)
+      { // vcom_r = Jcom(r, :) v
+        double s = 0;
+        for (int c = 0; c < nv; c++)
+          s += Jt[tid * nv + c] * vs[c];
+        bt[tid] -= bt[6] * s;
+      }
+      SMPC_END
+      id_add_motion_task(L, sm, S.w_com, 0, 3);
+    }
+    // swing-foot tracking tasks (LOCAL frame)
+    if (S.centroidal && S.w_feet_tracking > 0.)
+      for (int f = 0; f < nfeet; f++)
+      {
+        if (!T.tracked[f])
+          continue;
+        id_frame(Mo, L, sm, d.foot_joint[f], d.foot_R[f], d.foot_p[f]);
+        SMPC_PAR(tid)
+        if (tid == 0)
+        {
+          const double kp = S.kp_feet_tracking, kd = 2.0 * sqrt(kp);
+          double Rr[9], dp[3], pr[3], e6[6], vr[6];
+          m3tm(fr, T.foot_R[f], Rr);
+          for (int e = 0; e < 3; e++)
+            dp[e] = T.foot_p[f][e] - fr[9 + e];
+          m3tv(fr, dp, pr);
+          log6(Rr, pr, e6);
+          m3tv(fr, T.foot_vel[f], vr);
+          m3tv(fr, T.foot_vel[f] + 3, vr + 3);
+          for (int r = 0; r < 6; r++)
+            bt[r] = kp * e6[r] + kd * (vr[r] - fr[12 + r]) - fr[18 + r];
+        }
+        SMPC_END
+        id_add_motion_task(L, sm, S.w_feet_tracking, 0, D.foot_type[f] == SMPC_ID_QUAD ? 6 : 3);
+      }
+    // contacts
+    int ie = 6, ii = 0;
+    for (int f = 0; f < nfeet; f++)
+    {
+      if (!T.active[f])
+        continue;
+      const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
+      const int c0 = foff[f], nfv = fdim[f], rows = quad ? 6 : 3;
+      id_frame(Mo, L, sm, d.foot_joint[f], d.foot_R[f], d.foot_p[f]);
+      // motion rows: LOCAL for quad feet, world-oriented linear rows for point feet (rotate Jt, v, drift by R)
+      SMPC_PAR(tid)
+      const double kd = 2.0 * sqrt(S.kp_contact);
+      if (!quad)
+        for (int c = tid; c < nv; c += SMPC_NT)
+        {
+          const double jl[3] = {Jt[c], Jt[nv + c], Jt[2 * nv + c]};
+          double jw[3];
+          m3v(fr, jl, jw);
+          Jt[c] = jw[0], Jt[nv + c] = jw[1], Jt[2 * nv + c] = jw[2];
+        }
+      if (tid == 0)
+      {
+        if (quad)
+          for (int r = 0; r < 6; r++)
+            bt[r] = -kd * fr[12 + r] - fr[18 + r];
+        else
+        {
+          double vw[3], dw[3];
+          m3v(fr, fr + 12, vw);
+          m3v(fr, fr + 18, dw);
+          for (int r = 0; r < 3; r++)
+            bt[r] = -kd * vw[r] - dw[r];
+        }
+      }
+      SMPC_END
+      SMPC_PAR(tid)
+      // generalised force of each force variable: Jm^T T(:, j)
+      for (int idx = tid; idx < nv * nfv; idx += SMPC_NT)
+      {
+        const int c = idx / nfv, j = idx % nfv;
+        double Tc[6] = {0, 0, 0, 0, 0, 0};
+        if (quad)
+        {
+          const int pt = j / 3, ax = j % 3;
+          double e3[3] = {0, 0, 0}, mo[3];
+          e3[ax] = 1;
+          v3cross(D.quad_points[f][pt], e3, mo);
+          Tc[ax] = 1;
+          Tc[3] = mo[0], Tc[4] = mo[1], Tc[5] = mo[2];
+        }
+        else
+          Tc[j] = 1;
+        double s = 0;
+        for (int r = 0; r < rows; r++)
+          s += Jt[r * nv + c] * Tc[r];
+        JcT[c * ldf + (c0 - nv) + j] = s;
+      }
+      if (S.contact_motion_equality)
+        for (int idx = tid; idx < rows * nv + rows; idx += SMPC_NT)
+        {
+          if (idx < rows * nv)
+            A[(ie + idx / nv) * ld + idx % nv] = Jt[idx];
+          else
+            bq[ie + idx - rows * nv] = bt[idx - rows * nv];
+        }
+      // force regularisation |W T f - W f_ref|^2 and the cone rows (thread 0: a few dozen entries)
+      if (tid == 0)
+      {
+        if (S.w_contact_force > 0.)
+        {
+          const double wreg[6] = {1, 1, 1e-3, 2, 2, 2};
+          for (int r = 0; r < rows; r++)
+          {
+            double row[SMPC_ID_MAX_FVAR];
+            for (int j = 0; j < nfv; j++)
+            {
+              double t = 0;
+              if (quad)
+              {
+                const int pt = j / 3, ax = j % 3;
+                if (r < 3)
+                  t = (r == ax) ? 1.0 : 0.0;
+                else
+                {
+                  double e3[3] = {0, 0, 0}, mo[3];
+                  e3[ax] = 1;
+                  v3cross(D.quad_points[f][pt], e3, mo);
+                  t = mo[r - 3];
+                }
+              }
+              else
+                t = (r == j) ? 1.0 : 0.0;
+              row[j] = wreg[r] * t;
+            }
+            const double br = wreg[r] * T.f_ref[f][r];
+            for (int i = 0; i < nfv; i++)
+            {
+              if (row[i] == 0.0)
+                continue;
+              for (int j = 0; j < nfv; j++)
+                H[(c0 + i) * ld + c0 + j] += S.w_contact_force * row[i] * row[j];
+              g[c0 + i] -= S.w_contact_force * row[i] * br;
+            }
+          }
+        }
+        const double mu = S.friction_coefficient;
+        const double pyr[4][3] = {{-1, 0, -mu}, {1, 0, -mu}, {0, -1, -mu}, {0, 1, -mu}};
+        const int npts = quad ? 4 : 1;
+        int row = ii;
+        for (int pt = 0; pt < npts; pt++)
+          for (int r = 0; r < 4; r++, row++)
+          {
+            for (int ax = 0; ax < 3; ax++)
+              Cm[row * ld + c0 + 3 * pt + ax] = pyr[r][ax];
+            lo[row] = -ID_BIG;
+            up[row] = 0.0;
+          }
+        for (int pt = 0; pt < npts; pt++)
+          Cm[row * ld + c0 + 3 * pt + 2] = 1.0;
+        lo[row] = fminn;
+        up[row] = fmaxn;
+      }
+      SMPC_END
+      if (!S.contact_motion_equality && S.w_contact_motion > 0.)
+        id_add_motion_task(L, sm, S.w_contact_motion, 0, rows);
+      ie += S.contact_motion_equality ? rows : 0;
+      ii += quad ? 17 : 5;
+    }
+    // floating-base rows, joint acceleration bounds, actuation bounds
+    SMPC_PAR(tid)
+    for (int idx = tid; idx < 6 * n + 6; idx += SMPC_NT)
+    {
+      if (idx < 6 * n)
+      {
+        const int r = idx / n, c = idx % n;
+        A[r * ld + c] = (c < nv) ? Mm[r * nv + c] : -JcT[r * ldf + c - nv];
+      }
+      else
+        bq[idx - 6 * n] = -h[idx - 6 * n];
+    }
+    for (int j = tid; j < na; j += SMPC_NT)
+    {
+      double lb, ub;
+      id_acc_bounds(qs[7 + j], vs[6 + j], D.qmin[j], D.qmax[j], D.vmax[j], D.control_dt, lb, ub);
+      Cm[(ii + j) * ld + 6 + j] = 1.0;
+      lo[ii + j] = lb;
+      up[ii + j] = ub;
+      lo[ii + na + j] = -D.effort[j] - h[6 + j];
+      up[ii + na + j] = D.effort[j] - h[6 + j];
+    }
+    for (int idx = tid; idx < na * n; idx += SMPC_NT)
+    {
+      const int j = idx / n, c = idx % n;
+      Cm[(ii + na + j) * ld + c] = (c < nv) ? Mm[(6 + j) * nv + c] : -JcT[(6 + j) * ldf + c - nv];
+    }
+    SMPC_END
+    // row equilibration (the solver's own preconditioning: unit inf-norm constraint rows; x is unchanged)
+    SMPC_PAR(tid)
+    for (int idx = tid; idx < me + mi; idx += SMPC_NT)
+    {
+      double * row = (idx < me) ? A + idx * ld : Cm + (idx - me) * ld;
+      double nr = 0;
+      for (int c = 0; c < n; c++)
+        nr = fmax(nr, fabs(row[c]));
+      if (nr > 0)
+      {
+        const double sc = 1.0 / nr;
+        for (int c = 0; c < n; c++)
+          row[c] *= sc;
+        if (idx < me)
+          bq[idx] *= sc;
+        else
+        {
+          lo[idx - me] *= sc;
+          up[idx - me] *= sc;
+        }
+      }
+    }
+    SMPC_END
+  }
+
+  // ---- phase group 3: the QP solve -----------------------------------------------------------------------------------
+  // value of the subproblem at xv: fills hx = H xv, re_out, si_out and sm[sc + slot]
+  SMPC_DEV void id_al_value(const IdDims & L, double * sm, int n, int me, int mi, double mu, const double * xv, double * re_out, double * si_out, int slot)
+  {
+    const int ld = L.ldn;
+    SMPC_PAR(tid)
+    const double * H = sm + L.o_H;
+    const double * A = sm + L.o_A;
+    const double * Cm = sm + L.o_C;
+    const double * y = sm + L.o_y;
+    const double * z = sm + L.o_z;
+    double * hx = sm + L.o_hx;
+    for (int idx = tid; idx < n + me + mi; idx += SMPC_NT)
+    {
+      const double * row = (idx < n) ? H + idx * ld : (idx < n + me) ? A + (idx - n) * ld : Cm + (idx - n - me) * ld;
+      double s0 = 0, s1 = 0;
+      int j = 0;
+      for (; j + 1 < n; j += 2)
+      {
+        s0 += row[j] * xv[j];
+        s1 += row[j + 1] * xv[j + 1];
+      }
+      if (j < n)
+        s0 += row[j] * xv[j];
+      const double s = s0 + s1;
+      if (idx < n)
+        hx[idx] = s;
+      else if (idx < n + me)
+      {
+        const int r = idx - n;
+        re_out[r] = s - sm[L.o_b + r] + mu * y[r];
+      }
+      else
+      {
+        const int r = idx - n - me;
+        const double t = s + mu * z[r];
+        double vi = 0;
+        if (t > sm[L.o_u + r])
+          vi = t - sm[L.o_u + r];
+        else if (t < sm[L.o_l + r])
+          vi = t - sm[L.o_l + r];
+        si_out[r] = vi;
+      }
+    }
+    SMPC_END
+    SMPC_PAR(tid)
+    if (tid == 0)
+    {
+      const double * g = sm + L.o_g;
+      const double * xk = sm + L.o_xk;
+      const double * hx = sm + L.o_hx;
+      double val = 0;
+      for (int i = 0; i < n; i++)
+        val += xv[i] * (0.5 * hx[i] + g[i]) + 0.5 * ID_QP_RHO * (xv[i] - xk[i]) * (xv[i] - xk[i]);
+      double pen = 0;
+      for (int r = 0; r < me; r++)
+        pen += re_out[r] * re_out[r];
+      for (int r = 0; r < mi; r++)
+        pen += si_out[r] * si_out[r];
+      sm[L.o_sc + slot] = val + 0.5 / mu * pen;
+    }
+    SMPC_END
+  }
+
+  // left-looking Cholesky of the leading n x n block of K (lower part), one barrier per column; sm[sc + SC_BAD] = 1 on a
+  // non-positive pivot
+  SMPC_DEV void id_chol(const IdDims & L, double * sm, int n)
+  {
+    const int ld = L.ldn;
+    double * K = sm + L.o_K;
+    for (int k = 0; k < n; k++)
+    {
+      SMPC_PAR(tid)
+      for (int i = k + tid; i < n; i += SMPC_NT)
+      {
+        const double * rk = K + k * ld;
+        const double * ri = K + i * ld;
+        double dk0 = rk[k], dk1 = 0, s0 = ri[k], s1 = 0;
+        int j = 0;
+        for (; j + 1 < k; j += 2)
+        {
+          dk0 -= rk[j] * rk[j];
+          dk1 -= rk[j + 1] * rk[j + 1];
+          s0 -= ri[j] * rk[j];
+          s1 -= ri[j + 1] * rk[j + 1];
+        }
+        if (j < k)
+        {
+          dk0 -= rk[j] * rk[j];
+          s0 -= ri[j] * rk[j];
+        }
+        const double dk = dk0 + dk1;
+        if (!(dk > 0))
+        {
+          sm[L.o_sc + SC_BAD] = 1.0;
+          continue;
+        }
+        const double piv = sqrt(dk);
+        // row k (and K(k,k)) is read by every thread of this phase: the pivot goes to a side array (xt is free during
+        // the factorisation) instead of overwriting the diagonal
+        if (i == k)
+          sm[L.o_xt + k] = piv;
+        else
+          K[i * ld + k] = (s0 + s1) / piv;
+      }
+      SMPC_END
+    }
+  }
+
+  // dx = -(L L^T)^-1 grad with L from id_chol (diagonal in xt); column-oriented substitutions, one barrier per column
+  SMPC_DEV void id_chol_solve(const IdDims & L, double * sm, int n)
+  {
+    const int ld = L.ldn;
+    const double * K = sm + L.o_K;
+    const double * dg = sm + L.o_xt;
+    double * dx = sm + L.o_dx;
+    SMPC_PAR(tid)
+    for (int i = tid; i < n; i += SMPC_NT)
+      dx[i] = -sm[L.o_grad + i];
+    SMPC_END
+    for (int k = 0; k < n; k++)
+    {
+      SMPC_PAR(tid)
+      const double xk = dx[k] / dg[k];
+      for (int i = k + 1 + tid; i < n; i += SMPC_NT)
+        dx[i] -= K[i * ld + k] * xk;
+      SMPC_END
+    }
+    // dx[k] now holds dg[k] * w_k of the forward solve; backward: x_k = (w_k - sum_{i>k} L(i,k) x_i) / dg[k]
+    SMPC_PAR(tid)
+    for (int i = tid; i < n; i += SMPC_NT)
+      dx[i] = dx[i] / dg[i];
+    SMPC_END
+    for (int k = n - 1; k >= 0; k--)
+    {
+      SMPC_PAR(tid)
+      // row-oriented back substitution: thread i < k subtracts L(k,i) x_k from its entry after x_k is final
+      const double xk = dx[k] / dg[k];
+      for (int i = tid; i < k; i += SMPC_NT)
+        dx[i] -= K[k * ld + i] * xk;
+      SMPC_END
+      SMPC_PAR(tid)
+      if (tid == 0)
+        dx[k] = dx[k] / dg[k];
+      SMPC_END
+    }
+  }
+
+  SMPC_DEV void id_solve_qp(const IdDims & L, double * sm, int n, int me, int mi, smpc_id_info * info)
+  {
+    const int ld = L.ldn;
+    double * x = sm + L.o_x;
+    double * xk = sm + L.o_xk;
+    double * xt = sm + L.o_xt;
+    double * dx = sm + L.o_dx;
+    double * grad = sm + L.o_grad;
+    double * y = sm + L.o_y;
+    double * z = sm + L.o_z;
+    double * re = sm + L.o_re;
+    double * re2 = sm + L.o_re2;
+    double * si = sm + L.o_si;
+    double * si2 = sm + L.o_si2;
+    double * sc = sm + L.o_sc;
+    int * act = reinterpret_cast<int *>(sm + L.o_act);
+    SMPC_PAR(tid)
+    for (int i = tid; i < n; i += SMPC_NT)
+      x[i] = 0.0;
+    for (int i = tid; i < me; i += SMPC_NT)
+      y[i] = 0.0;
+    for (int i = tid; i < mi; i += SMPC_NT)
+      z[i] = 0.0;
+    if (tid == 0)
+      sc[SC_BAD] = 0.0;
+    SMPC_END
+    double mu = ID_QP_MU0;
+    int newton = 0, outer = 0, status = 1;
+    double pres = 0, dres = 0;
+    for (outer = 0; outer < ID_QP_MAX_OUTER; outer++)
+    {
+      SMPC_PAR(tid)
+      for (int i = tid; i < n; i += SMPC_NT)
+        xk[i] = x[i];
+      SMPC_END
+      id_al_value(L, sm, n, me, mi, mu, x, re, si, SC_VAL);
+      for (int it = 0; it < ID_QP_MAX_INNER && newton < ID_QP_MAX_NEWTON; it++)
+      {
+        // gradient (hx = H x is current), its norm and the magnitude of its largest term
+        SMPC_PAR(tid)
+        const double * A = sm + L.o_A;
+        const double * Cm = sm + L.o_C;
+        const double * H = sm + L.o_H;
+        const double * g = sm + L.o_g;
+        const double * hx = sm + L.o_hx;
+        for (int i = tid; i < n; i += SMPC_NT)
+        {
+          double s = g[i] + ID_QP_RHO * (x[i] - xk[i]) + hx[i];
+          double sa = fabs(g[i]);
+          for (int j = 0; j < n; j++)
+            sa += fabs(H[i * ld + j] * x[j]);
+          for (int r = 0; r < me; r++)
+          {
+            const double t = A[r * ld + i] * re[r] / mu;
+            s += t;
+            sa += fabs(t);
+          }
+          for (int r = 0; r < mi; r++)
+            if (si[r] != 0.0)
+            {
+              const double t = Cm[r * ld + i] * si[r] / mu;
+              s += t;
+              sa += fabs(t);
+            }
+          grad[i] = s;
+          xt[i] = sa; // scratch until the factorisation
+        }
+        SMPC_END
+        SMPC_PAR(tid)
+        if (tid == 0)
+        {
+          double gn = 0, gs = 0;
+          for (int i = 0; i < n; i++)
+          {
+            gn = fmax(gn, fabs(grad[i]));
+            gs = fmax(gs, xt[i]);
+          }
+          sc[SC_GN] = gn;
+          sc[SC_GS] = gs;
+          int na_ = 0;
+          for (int r = 0; r < mi; r++)
+            if (si[r] != 0.0)
+              act[1 + na_++] = r;
+          act[0] = na_;
+        }
+        SMPC_END
+        if (sc[SC_GN] <= ID_QP_GRAD_REL * sc[SC_GS])
+          break;
+        newton++;
+        // Newton matrix, lower triangle
+        SMPC_PAR(tid)
+        const double * A = sm + L.o_A;
+        const double * Cm = sm + L.o_C;
+        const double * H = sm + L.o_H;
+        double * K = sm + L.o_K;
+        const int nact = act[0];
+        const double imu = 1.0 / mu;
+        for (int idx = tid; idx < n * n; idx += SMPC_NT)
+        {
+          const int i = idx / n, j = idx % n;
+          if (j > i)
+            continue;
+          double t0 = 0, t1 = 0;
+          for (int r = 0; r < me; r++)
+            t0 += A[r * ld + i] * A[r * ld + j];
+          for (int a = 0; a < nact; a++)
+          {
+            const double * cr = Cm + act[1 + a] * ld;
+            t1 += cr[i] * cr[j];
+          }
+          K[i * ld + j] = H[i * ld + j] + (i == j ? ID_QP_RHO : 0.0) + (t0 + t1) * imu;
+        }
+        SMPC_END
+        id_chol(L, sm, n);
+        if (sc[SC_BAD] != 0.0)
+          break;
+        id_chol_solve(L, sm, n);
+        SMPC_PAR(tid)
+        if (tid == 0)
+        {
+          double s = 0;
+          for (int i = 0; i < n; i++)
+            s += grad[i] * dx[i];
+          sc[SC_SLOPE] = s;
+        }
+        SMPC_END
+        double alpha = 1.0;
+        const double val = sc[SC_VAL], slope = sc[SC_SLOPE];
+        for (int ls = 0; ls < 30; ls++)
+        {
+          SMPC_PAR(tid)
+          for (int i = tid; i < n; i += SMPC_NT)
+            xt[i] = x[i] + alpha * dx[i];
+          SMPC_END
+          id_al_value(L, sm, n, me, mi, mu, xt, re2, si2, SC_VT);
+          if (sc[SC_VT] <= val + 1e-4 * alpha * slope + 1e-13 * fabs(val))
+            break;
+          alpha *= 0.5;
+        }
+        SMPC_PAR(tid)
+        if (tid == 0)
+        {
+          bool same = (alpha == 1.0);
+          for (int r = 0; r < mi && same; r++)
+            same = ((si[r] > 0) == (si2[r] > 0)) && ((si[r] < 0) == (si2[r] < 0));
+          sc[SC_SAME] = same ? 1.0 : 0.0;
+        }
+        SMPC_END
+        SMPC_PAR(tid)
+        for (int i = tid; i < n; i += SMPC_NT)
+          x[i] = xt[i];
+        for (int r = tid; r < me; r += SMPC_NT)
+          re[r] = re2[r];
+        for (int r = tid; r < mi; r += SMPC_NT)
+          si[r] = si2[r];
+        if (tid == 0)
+          sc[SC_VAL] = sc[SC_VT];
+        SMPC_END
+        if (sc[SC_SAME] != 0.0)
+          break;
+      }
+      if (sc[SC_BAD] != 0.0)
+      {
+        status = 2;
+        break;
+      }
+      // multiplier update; relative KKT residuals (hx = H x from the last value call)
+      SMPC_PAR(tid)
+      for (int r = tid; r < me; r += SMPC_NT)
+        y[r] = re[r] / mu;
+      for (int r = tid; r < mi; r += SMPC_NT)
+        z[r] = si[r] / mu;
+      SMPC_END
+      SMPC_PAR(tid)
+      const double * A = sm + L.o_A;
+      const double * Cm = sm + L.o_C;
+      const double * g = sm + L.o_g;
+      const double * hx = sm + L.o_hx;
+      double * Ks = sm + L.o_K; // free between factorisations: row scales
+      // per-row residuals and scales: dual rows in (xt, grad), primal rows in (re2 | si2, Ks)
+      for (int idx = tid; idx < n + me + mi; idx += SMPC_NT)
+      {
+        if (idx < n)
+        {
+          const int i = idx;
+          double ay = 0, cz = 0;
+          for (int r = 0; r < me; r++)
+            ay += A[r * ld + i] * y[r];
+          for (int r = 0; r < mi; r++)
+            cz += Cm[r * ld + i] * z[r];
+          xt[i] = fabs(g[i] + hx[i] + ay + cz);
+          grad[i] = fmax(fmax(fabs(hx[i]), fabs(g[i])), fmax(fabs(ay), fabs(cz)));
+        }
+        else if (idx < n + me)
+        {
+          const int r = idx - n;
+          double s = 0;
+          for (int j = 0; j < n; j++)
+            s += A[r * ld + j] * x[j];
+          re2[r] = fabs(s - sm[L.o_b + r]);
+          Ks[r] = fmax(fabs(s), fabs(sm[L.o_b + r]));
+        }
+        else
+        {
+          const int r = idx - n - me;
+          double s = 0;
+          for (int j = 0; j < n; j++)
+            s += Cm[r * ld + j] * x[j];
+          si2[r] = fmax(s - sm[L.o_u + r], sm[L.o_l + r] - s);
+          Ks[me + r] = fabs(s);
+        }
+      }
+      SMPC_END
+      SMPC_PAR(tid)
+      if (tid == 0)
+      {
+        const double * Ks = sm + L.o_K;
+        double pr = 0, ps = 1.0, dr = 0, ds = 1.0;
+        for (int r = 0; r < me; r++)
+          pr = fmax(pr, re2[r]);
+        for (int r = 0; r < mi; r++)
+          pr = fmax(pr, si2[r]);
+        for (int r = 0; r < me + mi; r++)
+          ps = fmax(ps, Ks[r]);
+        for (int i = 0; i < n; i++)
+        {
+          dr = fmax(dr, xt[i]);
+          ds = fmax(ds, grad[i]);
+        }
+        sc[SC_PRES] = pr / ps;
+        sc[SC_DRES] = dr / ds;
+      }
+      SMPC_END
+      pres = sc[SC_PRES];
+      dres = sc[SC_DRES];
+      if (pres <= ID_QP_EPS && dres <= ID_QP_EPS)
+      {
+        status = 0;
+        outer++;
+        break;
+      }
+      mu = fmax(0.1 * mu, ID_QP_MU_MIN);
+    }
+    SMPC_PAR(tid)
+    if (tid == 0)
+    {
+      info->status = status;
+      info->outer_iters = outer;
+      info->newton_iters = newton;
+      info->nvar = n;
+      info->neq = me;
+      info->nin = mi;
+      info->prim_res = pres;
+      info->dual_res = dres;
+    }
+    SMPC_END
+  }
+
+  // One instance: q, v (global) -> tau (na), a (nv), f (nfeet x 12), info.
+  SMPC_DEV void id_solve_cta(
+    const DevModel & Mo, const smpc_id_desc & D, const IdTargetDev & T, const IdDims & L, const double * q_g, const double * v_g,
+    double * sm, double * tau_g, double * a_g, double * f_g, smpc_id_info * info)
+  {
+    const int nv = L.nv, na = L.na;
+    SMPC_PAR(tid)
+    for (int i = tid; i < L.nq; i += SMPC_NT)
+      sm[L.o_q + i] = q_g[i];
+    for (int i = tid; i < nv; i += SMPC_NT)
+      sm[L.o_v + i] = v_g[i];
+    SMPC_END
+    id_dynamics(Mo, L, sm);
+    int n, me, mi;
+    id_build_qp(Mo, D, T, L, sm, n, me, mi);
+    id_solve_qp(L, sm, n, me, mi, info);
+    SMPC_PAR(tid)
+    const double * x = sm + L.o_x;
+    const double * Mm = sm + L.o_M;
+    const double * h = sm + L.o_h;
+    const double * JcT = sm + L.o_JcT;
+    const int nf = n - nv, ldf = nf > 0 ? nf : 1;
+    for (int j = tid; j < na; j += SMPC_NT)
+    {
+      double s = h[6 + j];
+      for (int c = 0; c < nv; c++)
+        s += Mm[(6 + j) * nv + c] * x[c];
+      for (int c = 0; c < nf; c++)
+        s -= JcT[(6 + j) * ldf + c] * x[nv + c];
+      tau_g[j] = s;
+    }
+    for (int i = tid; i < nv; i += SMPC_NT)
+      a_g[i] = x[i];
+    for (int i = tid; i < L.nfeet * SMPC_ID_MAX_FVAR; i += SMPC_NT)
+    {
+      const int f = i / SMPC_ID_MAX_FVAR, j = i % SMPC_ID_MAX_FVAR;
+      int off = nv;
+      for (int k = 0; k < f; k++)
+        off += T.active[k] ? (D.foot_type[k] == SMPC_ID_QUAD ? 12 : 3) : 0;
+      const int dim = T.active[f] ? (D.foot_type[f] == SMPC_ID_QUAD ? 12 : 3) : 0;
+      f_g[i] = (j < dim) ? x[off + j] : 0.0;
+    }
+    SMPC_END
+  }
+
+} // namespace smpc

@@ -8,9 +8,12 @@ from oracle_libs import load_oracle
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, "include", "smpc.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(smpc_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for header in ("smpc.h", "smpc_id.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(smpc_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -27,6 +30,19 @@ def test_oracle_mirrors_the_solver_level_entry_points():
               "cycle_ids", "set_warmstart", "shift_warmstart", "solve", "get_results", "get_head", "get_info", "get_duals",
               "get_ncmax", "get_xdot", "default_solver_opts", "problem_dims", "last_error"]:
         assert hasattr(orc, "orc_" + n), n
+
+
+def test_oracle_mirrors_the_inverse_dynamics_entry_points():
+    orc = load_oracle()
+    for n in ["create", "destroy", "default_settings", "set_target", "set_target_centroidal", "solve", "get_accelerations",
+              "get_forces", "get_info", "last_error"]:
+        assert hasattr(orc, "orc_id_" + n), n
+    import smpc_id
+    a, b = smpc_id.IdSettings(), smpc_id.IdSettings()
+    load_cuda().smpc_id_default_settings(C.byref(a))
+    orc.orc_id_default_settings(C.byref(b))
+    assert bytes(a) == bytes(b) == bytes(smpc_id.default_settings())
+    assert C.sizeof(smpc_id.IdInfo) == 6 * 4 + 2 * 8 and C.sizeof(smpc_id.IdSettings) == 8 * 10 + 2 * 4 + 8 * 4
 
 
 def test_struct_sizes_match_the_header():
