@@ -550,13 +550,10 @@ namespace orc
         double gn = 0, gs = 0;
         for (int i = 0; i < n; i++)
         {
-          double s = qp.g[i] + ID_QP_RHO * (x[i] - xk[i]), sa = std::fabs(qp.g[i]);
+          double hx = 0;
           for (int j = 0; j < n; j++)
-          {
-            const double t = qp.H(i, j) * x[j];
-            s += t;
-            sa += std::fabs(t);
-          }
+            hx += qp.H(i, j) * x[j];
+          double s = qp.g[i] + ID_QP_RHO * (x[i] - xk[i]) + hx, sa = std::fabs(qp.g[i]) + std::fabs(hx);
           for (int r = 0; r < me; r++)
           {
             const double t = qp.A(r, i) * re[r] / mu;

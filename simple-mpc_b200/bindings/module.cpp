@@ -178,6 +178,7 @@ PYBIND11_MODULE(simple_mpc, m)
     .def_readwrite("lowerPositionLimit", &Model::lowerPositionLimit)
     .def_readwrite("upperPositionLimit", &Model::upperPositionLimit)
     .def_readwrite("effortLimit", &Model::effortLimit)
+    .def_readwrite("velocityLimit", &Model::velocityLimit)
     .def_readwrite("friction", &Model::friction)
     .def_readwrite("damping", &Model::damping)
     .def_readonly("frames", &Model::frames)
@@ -349,6 +350,76 @@ PYBIND11_MODULE(simple_mpc, m)
     .def_readonly("nu", &FrictionCompensation::nu_)
     .def_readonly("dry_friction", &FrictionCompensation::dry_friction_)
     .def_readonly("viscuous_friction", &FrictionCompensation::viscuous_friction_);
+
+  // KinodynamicsID / CentroidalID (reference bindings/expose-inverse-dynamics.cpp:62-94): settings classes with read-write
+  // fields, setTarget / solve(t, q, v) -> tau / getAccelerations() -> a
+  py::class_<KinodynamicsID::Settings>(m, "KinodynamicsIDSettings")
+    .def(py::init<>())
+    .def_readwrite("friction_coefficient", &KinodynamicsID::Settings::friction_coefficient)
+    .def_readwrite("contact_weight_ratio_max", &KinodynamicsID::Settings::contact_weight_ratio_max)
+    .def_readwrite("contact_weight_ratio_min", &KinodynamicsID::Settings::contact_weight_ratio_min)
+    .def_readwrite("kp_base", &KinodynamicsID::Settings::kp_base)
+    .def_readwrite("kp_posture", &KinodynamicsID::Settings::kp_posture)
+    .def_readwrite("kp_contact", &KinodynamicsID::Settings::kp_contact)
+    .def_readwrite("w_base", &KinodynamicsID::Settings::w_base)
+    .def_readwrite("w_posture", &KinodynamicsID::Settings::w_posture)
+    .def_readwrite("w_contact_motion", &KinodynamicsID::Settings::w_contact_motion)
+    .def_readwrite("w_contact_force", &KinodynamicsID::Settings::w_contact_force)
+    .def_readwrite("contact_motion_equality", &KinodynamicsID::Settings::contact_motion_equality);
+  py::class_<KinodynamicsID>(m, "KinodynamicsID")
+    .def(py::init<const RobotModelHandler &, double, const KinodynamicsID::Settings>(), py::arg("model_handler"), py::arg("control_dt"),
+         py::arg("settings"), py::keep_alive<1, 2>())
+    .def("setTarget", &KinodynamicsID::setTarget)
+    .def("solve",
+         [](KinodynamicsID & self, double t, const VectorXd & q, const VectorXd & v) {
+           VectorXd tau;
+           self.solve(t, q, v, tau);
+           return tau;
+         })
+    .def("getAccelerations",
+         [](KinodynamicsID & self) {
+           VectorXd a;
+           self.getAccelerations(a);
+           return a;
+         })
+    .def("getContactForces", &KinodynamicsID::getContactForces);
+  py::class_<CentroidalID::Settings, KinodynamicsID::Settings>(m, "CentroidalIDSettings")
+    .def(py::init<>())
+    .def_readwrite("kp_com", &CentroidalID::Settings::kp_com)
+    .def_readwrite("kp_feet_tracking", &CentroidalID::Settings::kp_feet_tracking)
+    .def_readwrite("w_com", &CentroidalID::Settings::w_com)
+    .def_readwrite("w_feet_tracking", &CentroidalID::Settings::w_feet_tracking);
+  py::class_<CentroidalID>(m, "CentroidalID")
+    .def(py::init<const RobotModelHandler &, double, const CentroidalID::Settings>(), py::arg("model_handler"), py::arg("control_dt"),
+         py::arg("settings"), py::keep_alive<1, 2>())
+    .def("setTarget",
+         [](CentroidalID & self, const VectorXd & com, const VectorXd & vcom, const std::vector<SE3> & feet_pose,
+            const std::vector<VectorXd> & feet_velocity, const std::vector<bool> & contact, const std::vector<VectorXd> & f_target) {
+           if (com.size() != 3 || vcom.size() != 3)
+             throw std::runtime_error("CentroidalID.setTarget: com_position / com_velocity must have 3 entries");
+           CentroidalID::FeetVelocityVector fv(feet_velocity.size());
+           for (size_t i = 0; i < feet_velocity.size(); i++)
+           {
+             if (feet_velocity[i].size() != 6)
+               throw std::runtime_error("CentroidalID.setTarget: feet_velocity entries are [linear; angular] (6)");
+             for (size_t e = 0; e < 3; e++)
+               fv[i].lin[e] = feet_velocity[i][e], fv[i].ang[e] = feet_velocity[i][3 + e];
+           }
+           self.setTarget({{com[0], com[1], com[2]}}, {{vcom[0], vcom[1], vcom[2]}}, feet_pose, fv, contact, f_target);
+         })
+    .def("solve",
+         [](CentroidalID & self, double t, const VectorXd & q, const VectorXd & v) {
+           VectorXd tau;
+           self.solve(t, q, v, tau);
+           return tau;
+         })
+    .def("getAccelerations",
+         [](CentroidalID & self) {
+           VectorXd a;
+           self.getAccelerations(a);
+           return a;
+         })
+    .def("getContactForces", &CentroidalID::getContactForces);
 
   // Interpolator (reference bindings/expose-interpolate.cpp:20-62): each method (delay, timestep, list) -> value
   py::class_<Interpolator>(m, "Interpolator")

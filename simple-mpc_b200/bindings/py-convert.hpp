@@ -12,6 +12,7 @@
 #include "simple-mpc/mpc.hpp"
 #include "simple-mpc/interpolator.hpp"
 #include "simple-mpc/friction-compensation.hpp"
+#include "simple-mpc/inverse-dynamics/centroidal-id.hpp"
 
 namespace pybind11
 {

@@ -13,8 +13,6 @@ using namespace smpc;
 
 namespace
 {
-  constexpr int ID_THREADS = 128;
-
   __global__ void __launch_bounds__(ID_THREADS) k_id_solve(
     const DevModel * __restrict__ M, const smpc_id_desc * __restrict__ D, const IdTargetDev * __restrict__ T, const IdDims L,
     const double * __restrict__ q, const double * __restrict__ v, double * __restrict__ tau, double * __restrict__ a,

@@ -33,6 +33,7 @@ namespace smpc
   constexpr int ID_QP_MAX_OUTER = 30;
   constexpr int ID_QP_MAX_INNER = 30;
   constexpr int ID_QP_MAX_NEWTON = 200;
+  constexpr int ID_THREADS = 128; // CTA width the reductions are written for (the emulation runs with SMPC_EMUL_NT = 128)
 
   // per-instance target (what setTarget stores in the TSID tasks)
   struct IdTargetDev
@@ -53,7 +54,7 @@ namespace smpc
     int nj, nq, nv, na, nfeet;
     int nfmax, nx, ldn, me, mi;
     int o_q, o_v, o_M, o_h, o_JcT, o_H, o_g, o_A, o_b, o_C, o_l, o_u, o_Jt, o_bt, o_fr;
-    int o_x, o_xk, o_grad, o_dx, o_xt, o_hx, o_y, o_re, o_re2, o_z, o_si, o_si2, o_sc, o_act;
+    int o_x, o_xk, o_grad, o_dx, o_xt, o_hx, o_y, o_re, o_re2, o_z, o_si, o_si2, o_sc, o_act, o_part;
     int o_K;                                 // Newton matrix; the kinematics scratch below aliases it
     int o_oMi, o_Jw, o_ov, o_oa, o_Y, o_fs, o_Fc;
     int total;
@@ -93,6 +94,7 @@ namespace smpc
     L.o_z = take(L.mi), L.o_si = take(L.mi), L.o_si2 = take(L.mi);
     L.o_sc = take(16);
     L.o_act = take((L.mi + 2) / 2 + 1); // int list of the active inequality rows
+    L.o_part = take(4 * ID_THREADS);    // per-thread partials of the CTA-wide reductions
     L.o_K = o;
     L.o_oMi = take(12 * L.nj), L.o_Jw = take(6 * L.nv), L.o_ov = take(6 * L.nj), L.o_oa = take(6 * L.nj);
     L.o_Y = take(36 * L.nj), L.o_fs = take(6 * L.nj), L.o_Fc = take(6 * L.nv);
@@ -113,7 +115,8 @@ namespace smpc
     SC_PRES,
     SC_DRES,
     SC_OK,
-    SC_BAD
+    SC_BAD,
+    SC_K0 // four consecutive slots: primal residual / scale, dual residual / scale
   };
 
   // TaskJointPosVelAccBounds::computeAccLimits (position, velocity, viability; no acceleration bound) — oracle id_acc_bounds
@@ -805,6 +808,46 @@ namespace smpc
   }
 
   // ---- phase group 3: the QP solve -----------------------------------------------------------------------------------
+  // CTA-wide reductions of up to four per-thread partials (part[k * ID_THREADS + tid]): warp k < nq reduces quantity k by
+  // shuffles and its lane 0 writes sc[slot0 + k]; MAXRED selects max instead of sum. The CPU emulation loops.
+  template <bool MAXRED>
+  SMPC_DEV void id_block_reduce(const IdDims & L, double * sm, int nq, int slot0)
+  {
+    SMPC_PAR(tid)
+    const double * part = sm + L.o_part;
+    double * sc = sm + L.o_sc;
+#ifdef __CUDACC__
+    const int w = tid >> 5, lane = tid & 31;
+    if (w < nq)
+    {
+      const double * pk = part + w * ID_THREADS;
+      double s;
+      if (MAXRED)
+        s = fmax(fmax(pk[lane], pk[lane + 32]), fmax(pk[lane + 64], pk[lane + 96]));
+      else
+        s = (pk[lane] + pk[lane + 32]) + (pk[lane + 64] + pk[lane + 96]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1)
+      {
+        const double t = __shfl_xor_sync(0xffffffffu, s, o);
+        s = MAXRED ? fmax(s, t) : s + t;
+      }
+      if (lane == 0)
+        sc[slot0 + w] = s;
+    }
+#else
+    if (tid == 0)
+      for (int k = 0; k < nq; k++)
+      {
+        double s = MAXRED ? -1e300 : 0.0;
+        for (int t = 0; t < ID_THREADS; t++)
+          s = MAXRED ? fmax(s, part[k * ID_THREADS + t]) : s + part[k * ID_THREADS + t];
+        sc[slot0 + k] = s;
+      }
+#endif
+    SMPC_END
+  }
+
   // value of the subproblem at xv: fills hx = H xv, re_out, si_out and sm[sc + slot]
   SMPC_DEV void id_al_value(const IdDims & L, double * sm, int n, int me, int mi, double mu, const double * xv, double * re_out, double * si_out, int slot)
   {
@@ -815,7 +858,11 @@ namespace smpc
     const double * Cm = sm + L.o_C;
     const double * y = sm + L.o_y;
     const double * z = sm + L.o_z;
+    const double * g = sm + L.o_g;
+    const double * xk = sm + L.o_xk;
     double * hx = sm + L.o_hx;
+    const double himu = 0.5 / mu;
+    double acc = 0;
     for (int idx = tid; idx < n + me + mi; idx += SMPC_NT)
     {
       const double * row = (idx < n) ? H + idx * ld : (idx < n + me) ? A + (idx - n) * ld : Cm + (idx - n - me) * ld;
@@ -830,11 +877,17 @@ namespace smpc
         s0 += row[j] * xv[j];
       const double s = s0 + s1;
       if (idx < n)
+      {
         hx[idx] = s;
+        const double dxi = xv[idx] - xk[idx];
+        acc += xv[idx] * (0.5 * s + g[idx]) + 0.5 * ID_QP_RHO * dxi * dxi;
+      }
       else if (idx < n + me)
       {
         const int r = idx - n;
-        re_out[r] = s - sm[L.o_b + r] + mu * y[r];
+        const double t = s - sm[L.o_b + r] + mu * y[r];
+        re_out[r] = t;
+        acc += himu * t * t;
       }
       else
       {
@@ -846,30 +899,17 @@ namespace smpc
         else if (t < sm[L.o_l + r])
           vi = t - sm[L.o_l + r];
         si_out[r] = vi;
+        acc += himu * vi * vi;
       }
     }
+    sm[L.o_part + tid] = acc;
     SMPC_END
-    SMPC_PAR(tid)
-    if (tid == 0)
-    {
-      const double * g = sm + L.o_g;
-      const double * xk = sm + L.o_xk;
-      const double * hx = sm + L.o_hx;
-      double val = 0;
-      for (int i = 0; i < n; i++)
-        val += xv[i] * (0.5 * hx[i] + g[i]) + 0.5 * ID_QP_RHO * (xv[i] - xk[i]) * (xv[i] - xk[i]);
-      double pen = 0;
-      for (int r = 0; r < me; r++)
-        pen += re_out[r] * re_out[r];
-      for (int r = 0; r < mi; r++)
-        pen += si_out[r] * si_out[r];
-      sm[L.o_sc + slot] = val + 0.5 / mu * pen;
-    }
-    SMPC_END
+    id_block_reduce<false>(L, sm, 1, slot);
   }
 
-  // left-looking Cholesky of the leading n x n block of K (lower part), one barrier per column; sm[sc + SC_BAD] = 1 on a
-  // non-positive pivot
+  // left-looking Cholesky of the leading n x n block of K (lower part), one barrier per column. Row k (and K(k,k)) is read
+  // by every thread of column k's phase, so the INVERSE pivot goes to a side array (xt is free during the factorisation)
+  // instead of overwriting the diagonal. sm[sc + SC_BAD] = 1 on a non-positive pivot.
   SMPC_DEV void id_chol(const IdDims & L, double * sm, int n)
   {
     const int ld = L.ldn;
@@ -901,55 +941,56 @@ namespace smpc
           sm[L.o_sc + SC_BAD] = 1.0;
           continue;
         }
-        const double piv = sqrt(dk);
-        // row k (and K(k,k)) is read by every thread of this phase: the pivot goes to a side array (xt is free during
-        // the factorisation) instead of overwriting the diagonal
+#ifdef __CUDACC__
+        const double rp = rsqrt(dk);
+#else
+        const double rp = 1.0 / sqrt(dk);
+#endif
         if (i == k)
-          sm[L.o_xt + k] = piv;
+          sm[L.o_xt + k] = rp;
         else
-          K[i * ld + k] = (s0 + s1) / piv;
+          K[i * ld + k] = (s0 + s1) * rp;
       }
       SMPC_END
     }
   }
 
-  // dx = -(L L^T)^-1 grad with L from id_chol (diagonal in xt); column-oriented substitutions, one barrier per column
+  // dx = -(L L^T)^-1 grad with L from id_chol (inverse pivots in xt): column-oriented substitutions, one barrier per column;
+  // entry k stays unscaled while the others consume it, one scaling pass closes each direction
   SMPC_DEV void id_chol_solve(const IdDims & L, double * sm, int n)
   {
     const int ld = L.ldn;
     const double * K = sm + L.o_K;
-    const double * dg = sm + L.o_xt;
+    const double * ip = sm + L.o_xt;
     double * dx = sm + L.o_dx;
     SMPC_PAR(tid)
     for (int i = tid; i < n; i += SMPC_NT)
       dx[i] = -sm[L.o_grad + i];
     SMPC_END
-    for (int k = 0; k < n; k++)
+    for (int k = 0; k < n - 1; k++)
     {
       SMPC_PAR(tid)
-      const double xk = dx[k] / dg[k];
+      const double wk = dx[k] * ip[k];
       for (int i = k + 1 + tid; i < n; i += SMPC_NT)
-        dx[i] -= K[i * ld + k] * xk;
+        dx[i] -= K[i * ld + k] * wk;
       SMPC_END
     }
-    // dx[k] now holds dg[k] * w_k of the forward solve; backward: x_k = (w_k - sum_{i>k} L(i,k) x_i) / dg[k]
     SMPC_PAR(tid)
     for (int i = tid; i < n; i += SMPC_NT)
-      dx[i] = dx[i] / dg[i];
+      dx[i] = dx[i] * ip[i];
     SMPC_END
-    for (int k = n - 1; k >= 0; k--)
+    for (int k = n - 1; k > 0; k--)
     {
       SMPC_PAR(tid)
-      // row-oriented back substitution: thread i < k subtracts L(k,i) x_k from its entry after x_k is final
-      const double xk = dx[k] / dg[k];
+      const double xk = dx[k] * ip[k];
       for (int i = tid; i < k; i += SMPC_NT)
         dx[i] -= K[k * ld + i] * xk;
       SMPC_END
-      SMPC_PAR(tid)
-      if (tid == 0)
-        dx[k] = dx[k] / dg[k];
-      SMPC_END
     }
+    SMPC_PAR(tid)
+    for (int i = tid; i < n; i += SMPC_NT)
+      dx[i] = dx[i] * ip[i];
+    SMPC_END
   }
 
   SMPC_DEV void id_solve_qp(const IdDims & L, double * sm, int n, int me, int mi, smpc_id_info * info)
@@ -967,6 +1008,7 @@ namespace smpc
     double * si = sm + L.o_si;
     double * si2 = sm + L.o_si2;
     double * sc = sm + L.o_sc;
+    double * part = sm + L.o_part;
     int * act = reinterpret_cast<int *>(sm + L.o_act);
     SMPC_PAR(tid)
     for (int i = tid; i < n; i += SMPC_NT)
@@ -983,6 +1025,7 @@ namespace smpc
     double pres = 0, dres = 0;
     for (outer = 0; outer < ID_QP_MAX_OUTER; outer++)
     {
+      const double imu = 1.0 / mu;
       SMPC_PAR(tid)
       for (int i = tid; i < n; i += SMPC_NT)
         xk[i] = x[i];
@@ -990,54 +1033,65 @@ namespace smpc
       id_al_value(L, sm, n, me, mi, mu, x, re, si, SC_VAL);
       for (int it = 0; it < ID_QP_MAX_INNER && newton < ID_QP_MAX_NEWTON; it++)
       {
-        // gradient (hx = H x is current), its norm and the magnitude of its largest term
+        // gradient (hx = H x is current), its inf-norm and the magnitude of its largest term; warp 3 compacts the list of
+        // active inequality rows meanwhile
         SMPC_PAR(tid)
         const double * A = sm + L.o_A;
         const double * Cm = sm + L.o_C;
-        const double * H = sm + L.o_H;
         const double * g = sm + L.o_g;
         const double * hx = sm + L.o_hx;
+        double gn = 0, gs = 0;
         for (int i = tid; i < n; i += SMPC_NT)
         {
           double s = g[i] + ID_QP_RHO * (x[i] - xk[i]) + hx[i];
-          double sa = fabs(g[i]);
-          for (int j = 0; j < n; j++)
-            sa += fabs(H[i * ld + j] * x[j]);
+          double sa = fabs(g[i]) + fabs(hx[i]);
           for (int r = 0; r < me; r++)
           {
-            const double t = A[r * ld + i] * re[r] / mu;
+            const double t = A[r * ld + i] * re[r] * imu;
             s += t;
             sa += fabs(t);
           }
           for (int r = 0; r < mi; r++)
-            if (si[r] != 0.0)
-            {
-              const double t = Cm[r * ld + i] * si[r] / mu;
-              s += t;
-              sa += fabs(t);
-            }
+          {
+            const double t = Cm[r * ld + i] * si[r] * imu; // si = 0 on inactive rows
+            s += t;
+            sa += fabs(t);
+          }
           grad[i] = s;
-          xt[i] = sa; // scratch until the factorisation
+          gn = fmax(gn, fabs(s));
+          gs = fmax(gs, sa);
         }
-        SMPC_END
-        SMPC_PAR(tid)
+        part[tid] = gn;
+        part[ID_THREADS + tid] = gs;
+#ifdef __CUDACC__
+        if ((tid >> 5) == 3)
+        {
+          const int lane = tid & 31;
+          int base = 0;
+          for (int r0 = 0; r0 < mi; r0 += 32)
+          {
+            const int r = r0 + lane;
+            const bool on = (r < mi) && (si[r] != 0.0);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on)
+              act[1 + base + __popc(m & ((1u << lane) - 1u))] = r;
+            base += __popc(m);
+          }
+          if (lane == 0)
+            act[0] = base;
+        }
+#else
         if (tid == 0)
         {
-          double gn = 0, gs = 0;
-          for (int i = 0; i < n; i++)
-          {
-            gn = fmax(gn, fabs(grad[i]));
-            gs = fmax(gs, xt[i]);
-          }
-          sc[SC_GN] = gn;
-          sc[SC_GS] = gs;
           int na_ = 0;
           for (int r = 0; r < mi; r++)
             if (si[r] != 0.0)
               act[1 + na_++] = r;
           act[0] = na_;
         }
+#endif
         SMPC_END
+        id_block_reduce<true>(L, sm, 2, SC_GN);
         if (sc[SC_GN] <= ID_QP_GRAD_REL * sc[SC_GS])
           break;
         newton++;
@@ -1048,12 +1102,16 @@ namespace smpc
         const double * H = sm + L.o_H;
         double * K = sm + L.o_K;
         const int nact = act[0];
-        const double imu = 1.0 / mu;
-        for (int idx = tid; idx < n * n; idx += SMPC_NT)
+        const int npair = n * (n + 1) / 2;
+        for (int idx = tid; idx < npair; idx += SMPC_NT)
         {
-          const int i = idx / n, j = idx % n;
-          if (j > i)
-            continue;
+          // idx -> (i, j), j <= i : i = floor((sqrt(8 idx + 1) - 1) / 2)
+          int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+          while (i * (i + 1) / 2 > idx)
+            i--;
+          while ((i + 1) * (i + 2) / 2 <= idx)
+            i++;
+          const int j = idx - i * (i + 1) / 2;
           double t0 = 0, t1 = 0;
           for (int r = 0; r < me; r++)
             t0 += A[r * ld + i] * A[r * ld + j];
@@ -1070,14 +1128,12 @@ namespace smpc
           break;
         id_chol_solve(L, sm, n);
         SMPC_PAR(tid)
-        if (tid == 0)
-        {
-          double s = 0;
-          for (int i = 0; i < n; i++)
-            s += grad[i] * dx[i];
-          sc[SC_SLOPE] = s;
-        }
+        double s = 0;
+        for (int i = tid; i < n; i += SMPC_NT)
+          s += grad[i] * dx[i];
+        part[tid] = s;
         SMPC_END
+        id_block_reduce<false>(L, sm, 1, SC_SLOPE);
         double alpha = 1.0;
         const double val = sc[SC_VAL], slope = sc[SC_SLOPE];
         for (int ls = 0; ls < 30; ls++)
@@ -1091,26 +1147,25 @@ namespace smpc
             break;
           alpha *= 0.5;
         }
+        // accept; a full step that keeps the active set lands on the exact minimiser of the piecewise quadratic
         SMPC_PAR(tid)
-        if (tid == 0)
+        double changed = (alpha == 1.0) ? 0.0 : 1.0;
+        for (int r = tid; r < mi; r += SMPC_NT)
         {
-          bool same = (alpha == 1.0);
-          for (int r = 0; r < mi && same; r++)
-            same = ((si[r] > 0) == (si2[r] > 0)) && ((si[r] < 0) == (si2[r] < 0));
-          sc[SC_SAME] = same ? 1.0 : 0.0;
+          if (((si[r] > 0) != (si2[r] > 0)) || ((si[r] < 0) != (si2[r] < 0)))
+            changed = 1.0;
+          si[r] = si2[r];
         }
-        SMPC_END
-        SMPC_PAR(tid)
         for (int i = tid; i < n; i += SMPC_NT)
           x[i] = xt[i];
         for (int r = tid; r < me; r += SMPC_NT)
           re[r] = re2[r];
-        for (int r = tid; r < mi; r += SMPC_NT)
-          si[r] = si2[r];
+        part[tid] = changed;
         if (tid == 0)
           sc[SC_VAL] = sc[SC_VT];
         SMPC_END
-        if (sc[SC_SAME] != 0.0)
+        id_block_reduce<true>(L, sm, 1, SC_SAME);
+        if (sc[SC_SAME] == 0.0)
           break;
       }
       if (sc[SC_BAD] != 0.0)
@@ -1121,17 +1176,16 @@ namespace smpc
       // multiplier update; relative KKT residuals (hx = H x from the last value call)
       SMPC_PAR(tid)
       for (int r = tid; r < me; r += SMPC_NT)
-        y[r] = re[r] / mu;
+        y[r] = re[r] * imu;
       for (int r = tid; r < mi; r += SMPC_NT)
-        z[r] = si[r] / mu;
+        z[r] = si[r] * imu;
       SMPC_END
       SMPC_PAR(tid)
       const double * A = sm + L.o_A;
       const double * Cm = sm + L.o_C;
       const double * g = sm + L.o_g;
       const double * hx = sm + L.o_hx;
-      double * Ks = sm + L.o_K; // free between factorisations: row scales
-      // per-row residuals and scales: dual rows in (xt, grad), primal rows in (re2 | si2, Ks)
+      double pr = 0, ps = 1.0, dr = 0, ds = 1.0;
       for (int idx = tid; idx < n + me + mi; idx += SMPC_NT)
       {
         if (idx < n)
@@ -1142,8 +1196,8 @@ namespace smpc
             ay += A[r * ld + i] * y[r];
           for (int r = 0; r < mi; r++)
             cz += Cm[r * ld + i] * z[r];
-          xt[i] = fabs(g[i] + hx[i] + ay + cz);
-          grad[i] = fmax(fmax(fabs(hx[i]), fabs(g[i])), fmax(fabs(ay), fabs(cz)));
+          dr = fmax(dr, fabs(g[i] + hx[i] + ay + cz));
+          ds = fmax(ds, fmax(fmax(fabs(hx[i]), fabs(g[i])), fmax(fabs(ay), fabs(cz))));
         }
         else if (idx < n + me)
         {
@@ -1151,8 +1205,8 @@ namespace smpc
           double s = 0;
           for (int j = 0; j < n; j++)
             s += A[r * ld + j] * x[j];
-          re2[r] = fabs(s - sm[L.o_b + r]);
-          Ks[r] = fmax(fabs(s), fabs(sm[L.o_b + r]));
+          pr = fmax(pr, fabs(s - sm[L.o_b + r]));
+          ps = fmax(ps, fmax(fabs(s), fabs(sm[L.o_b + r])));
         }
         else
         {
@@ -1160,33 +1214,18 @@ namespace smpc
           double s = 0;
           for (int j = 0; j < n; j++)
             s += Cm[r * ld + j] * x[j];
-          si2[r] = fmax(s - sm[L.o_u + r], sm[L.o_l + r] - s);
-          Ks[me + r] = fabs(s);
+          pr = fmax(pr, fmax(s - sm[L.o_u + r], sm[L.o_l + r] - s));
+          ps = fmax(ps, fabs(s));
         }
       }
+      part[tid] = pr;
+      part[ID_THREADS + tid] = ps;
+      part[2 * ID_THREADS + tid] = dr;
+      part[3 * ID_THREADS + tid] = ds;
       SMPC_END
-      SMPC_PAR(tid)
-      if (tid == 0)
-      {
-        const double * Ks = sm + L.o_K;
-        double pr = 0, ps = 1.0, dr = 0, ds = 1.0;
-        for (int r = 0; r < me; r++)
-          pr = fmax(pr, re2[r]);
-        for (int r = 0; r < mi; r++)
-          pr = fmax(pr, si2[r]);
-        for (int r = 0; r < me + mi; r++)
-          ps = fmax(ps, Ks[r]);
-        for (int i = 0; i < n; i++)
-        {
-          dr = fmax(dr, xt[i]);
-          ds = fmax(ds, grad[i]);
-        }
-        sc[SC_PRES] = pr / ps;
-        sc[SC_DRES] = dr / ds;
-      }
-      SMPC_END
-      pres = sc[SC_PRES];
-      dres = sc[SC_DRES];
+      id_block_reduce<true>(L, sm, 4, SC_K0);
+      pres = sc[SC_K0] / sc[SC_K0 + 1];
+      dres = sc[SC_K0 + 2] / sc[SC_K0 + 3];
       if (pres <= ID_QP_EPS && dres <= ID_QP_EPS)
       {
         status = 0;

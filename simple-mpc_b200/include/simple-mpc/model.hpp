@@ -45,6 +45,7 @@ namespace simple_mpc
     std::vector<Frame> frames;
     std::map<std::string, VectorXd> referenceConfigurations;
     VectorXd lowerPositionLimit, upperPositionLimit, effortLimit;
+    VectorXd velocityLimit; // nv - 6 actuated joints, like the limits above; read by KinodynamicsID / CentroidalID only
     VectorXd friction, damping; // nv entries each (pinocchio's convention) or empty = zero; read by FrictionCompensation only
 
     /// root free-flyer (must be added first); returns joint index 0

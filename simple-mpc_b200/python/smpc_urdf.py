@@ -139,7 +139,8 @@ def describe(urdf_xml, srdf_xml=None, root_joint="root_joint", lock=(), lock_sta
                 out_j.append(dict(name=name, parent=jidx, type="revolute", axis=ax / np.linalg.norm(ax), R=Tj[0], p=Tj[1], body=_Body(),
                                   lower=float(lim.get("lower", "-inf")) if lim is not None else -np.inf,
                                   upper=float(lim.get("upper", "inf")) if lim is not None else np.inf,
-                                  effort=float(lim.get("effort", "inf")) if lim is not None else np.inf))
+                                  effort=float(lim.get("effort", "inf")) if lim is not None else np.inf,
+                                  velocity=float(lim.get("velocity", "inf")) if lim is not None else np.inf))
                 k = len(out_j) - 1
                 frames[name] = (k, np.eye(3), np.zeros(3))
                 visit(child, k, (np.eye(3), np.zeros(3)))
@@ -178,6 +179,7 @@ def to_model(sm, d):
     m.lowerPositionLimit = np.array([jd["lower"] for jd in rev])
     m.upperPositionLimit = np.array([jd["upper"] for jd in rev])
     m.effortLimit = np.array([jd["effort"] for jd in rev])
+    m.velocityLimit = np.array([jd.get("velocity", np.inf) for jd in rev])
     return m
 
 

@@ -313,6 +313,7 @@ namespace simple_mpc
     m.lowerPositionLimit = VectorXd{-1.0472, -1.5708, -2.7227, -1.0472, -1.5708, -2.7227, -1.0472, -1.5708, -2.7227, -1.0472, -1.5708, -2.7227};
     m.upperPositionLimit = VectorXd{1.0472, 3.4907, -0.83776, 1.0472, 3.4907, -0.83776, 1.0472, 3.4907, -0.83776, 1.0472, 3.4907, -0.83776};
     m.effortLimit = VectorXd(12, 23.7);
+    m.velocityLimit = VectorXd(12, 30.1);
     return m;
   }
 
@@ -359,6 +360,7 @@ namespace simple_mpc
     m.lowerPositionLimit = VectorXd(22, -2.5);
     m.upperPositionLimit = VectorXd(22, 2.5);
     m.effortLimit = VectorXd(22, 300.0);
+    m.velocityLimit = VectorXd(22, 10.0);
     return m;
   }
 

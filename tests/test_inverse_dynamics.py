@@ -340,3 +340,78 @@ def test_cuda_rejects_bad_arguments_loudly():
     qref = np.array(m.q_ref[: m.nq])
     with pytest.raises(RuntimeError):
         ig.set_target(qref[None], np.zeros((1, m.nv)), np.zeros((1, m.nv)), np.ones((1, 4), np.int32), np.zeros((1, 4, 6)), first=2)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# host classes / Python module (the reference's bindings/expose-inverse-dynamics.cpp surface)
+# --------------------------------------------------------------------------------------------------------------------
+def test_python_module_exposes_the_reference_settings_classes():
+    import host_api_utils as hu
+    sm = hu.import_simple_mpc()
+    s = sm.KinodynamicsIDSettings()
+    assert (s.friction_coefficient, s.contact_weight_ratio_max, s.contact_weight_ratio_min) == (0.6, 10.0, 0.01)
+    assert s.w_base == s.w_posture == s.w_contact_motion == s.w_contact_force == -1.0 and s.contact_motion_equality is False
+    c = sm.CentroidalIDSettings()
+    assert isinstance(c, sm.KinodynamicsIDSettings) and c.w_com == c.w_feet_tracking == -1.0 and c.kp_com == 0.0
+    for cls in (sm.KinodynamicsID, sm.CentroidalID):
+        assert all(hasattr(cls, n) for n in ("setTarget", "solve", "getAccelerations"))
+
+
+@pytest.mark.gpu
+def test_host_classes_match_the_c_abi_and_run_the_reference_scenarios():
+    """simple_mpc.KinodynamicsID / CentroidalID (C++ host classes over the C ABI) give the torques of the ctypes path on the
+    same robot, and the reference's allTasks / posture scenarios behave as its tests demand"""
+    import host_api_utils as hu
+    sm = hu.import_simple_mpc()
+    mh = hu.go2_handler(sm)
+    s = sm.KinodynamicsIDSettings()
+    s.kp_base, s.kp_posture, s.kp_contact = 10.0, 1.0, 10.0
+    s.w_base, s.w_posture, s.w_contact_force, s.w_contact_motion = 10.0, 0.1, 1.0, 1.0
+    kid = sm.KinodynamicsID(mh, DT, s)
+    xref = np.array(mh.getReferenceState())
+    nq, nv = mh.getModel().nq, mh.getModel().nv
+    q, v = xref[:nq].copy(), np.zeros(nv)
+    for leg in range(4):
+        q[7 + 3 * leg + 1] += 0.1
+        q[7 + 3 * leg + 2] -= 0.2
+    errs = []
+    for i in range(150):
+        tau = np.array(kid.solve(i * DT, q, v))
+        a = np.array(kid.getAccelerations())
+        assert tau.shape == (nv - 6,) and a.shape == (nv,) and np.abs(tau).max() <= 23.7 + 1e-6
+        q = sid.integrate_q(q, (v + a / 2 * DT) * DT)
+        v = v + a * DT
+        errs.append(np.linalg.norm(np.r_[q[:3] - xref[:3], q[7:] - xref[7:nq]]))
+    assert all(e1 <= e0 + 1e-12 for e0, e1 in zip(errs, errs[1:]))
+    # posture only, no contacts (reference KinodynamicsID_postureTask)
+    s2 = sm.KinodynamicsIDSettings()
+    s2.kp_posture, s2.w_posture = 20.0, 1.0
+    kid2 = sm.KinodynamicsID(mh, DT, s2)
+    kid2.setTarget(xref[:nq], np.zeros(nv), np.zeros(nv), [False] * 4, [])
+    tau = np.array(kid2.solve(0.0, q, v))
+    assert np.isfinite(tau).all() and (np.array(kid2.getContactForces()) == 0).all()
+    # CentroidalID: lift one foot
+    c = sm.CentroidalIDSettings()
+    c.kp_feet_tracking, c.kp_posture, c.kp_contact = 5.0, 0.1, 1.0
+    c.w_feet_tracking, c.w_posture, c.w_contact_force, c.contact_motion_equality = 1e3, 1.0, 0.1, True
+    cid = sm.CentroidalID(mh, DT, c)
+    dh = sm.RobotDataHandler(mh)
+    dh.updateInternalData(xref, False)
+    poses = [dh.getFootPose(i) for i in range(4)]
+    target = np.array(poses[0].translation) + np.array([0, 0, 0.03])
+    poses[0] = sm.SE3(np.array(poses[0].rotation), target)
+    w = mh.getMass() * 9.81 / 3
+    m_desc, *_ = robot("go2")
+    cid.setTarget(sc.com_numpy(m_desc, xref[:nq]), np.zeros(3), poses, [np.zeros(6)] * 4, [False, True, True, True],
+                  [np.zeros(3)] + [np.array([0, 0, w])] * 3)
+    q, v = xref[:nq].copy(), np.zeros(nv)
+    e0 = None
+    for i in range(200):
+        cid.solve(i * DT, q, v)
+        a = np.array(cid.getAccelerations())
+        q = sid.integrate_q(q, (v + a / 2 * DT) * DT)
+        v = v + a * DT
+        dh.updateInternalData(np.r_[q, v], False)
+        e = np.linalg.norm(np.array(dh.getFootPose(0).translation) - target)
+        e0 = e if e0 is None else e0
+    assert e < 0.97 * e0
