@@ -56,6 +56,9 @@ CONFIGS = {
     "c3": dict(scenario="Go2FullScenario", batch=2048, what="go2-like (synthetic) full-dynamics MPC tick, friction pyramid + landing constraints"),
     "c4": dict(scenario="TalosFullScenario", batch=256, what="talos-like (synthetic) full-dynamics walking MPC tick, 6-D contacts, wrench cones, torque + joint limits"),
     "c5": dict(scenario="Go2Scenario", batch=4096, what="go2-like (synthetic) kinodynamics MPC tick"),
+    # the low-level controller that runs after MPC::iterate (reference src/inverse-dynamics/*.cpp):
+    # its own metric (QP solves per second), handled by run_id_bench
+    "id": dict(scenario=None, batch=4096, what="go2-like (synthetic) KinodynamicsID whole-body QP (base + posture + contact tasks, 30 variables, 6 equalities, 44 inequalities)"),
 }
 
 
@@ -200,6 +203,138 @@ def cpu_rows(cfg, ticks, warm, per_thread=2):
     }, rb
 
 
+def id_problem(B, seed):
+    """KinodynamicsID on the go2-like robot with the reference test's allTasks settings (tests/inverse-dynamics/
+    kinodynamics-id.cpp:277-290); one perturbed measured state per instance."""
+    import smpc_ctypes as sct
+    import smpc_id as sid
+    m, lim = sct.go2_like_model()
+    kw = dict(kp_base=10.0, kp_posture=1.0, kp_contact=10.0, w_base=10.0, w_posture=0.1, w_contact_motion=1.0, w_contact_force=1.0)
+    d = sid.make_desc(m, lim["qmin"], lim["qmax"], 30.1, 23.7, sid.default_settings(**kw), control_dt=1e-3)
+    rng = np.random.default_rng(seed)
+    q = np.repeat(np.array(m.q_ref[: m.nq])[None], B, 0)
+    q[:, 7:] += 0.03 * rng.standard_normal((B, m.nv - 6))
+    q[:, :2] += 0.01 * rng.standard_normal((B, 2))
+    v = np.zeros((B, m.nv))
+    v[:, 6:] = 0.02 * rng.standard_normal((B, m.nv - 6))
+    return sid, m, d, np.ascontiguousarray(q), np.ascontiguousarray(v)
+
+
+def run_id_bench(args, rank, world, local_rank, W, K):
+    """bench line of the batched inverse-dynamics QP: one step = one KinodynamicsID::solve of every instance."""
+    B = args.batch or CONFIGS["id"]["batch"]
+    metric, unit = "id_qp_solves_per_s", "solves/s"
+    config = {"workload": "%s, %d instances/GPU, cold-started every solve" % (CONFIGS["id"]["what"], B), "config": "id",
+              "instances_total": B * world, "instances_this_rank": B,
+              "l2": "everything lives in shared memory; HBM carries q, v in and tau, a, f out (2.3 KB per instance)",
+              "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world}
+    cores = os.cpu_count() or 1
+
+    def cpu_leg(steps, warm):
+        sid, m, d, q, v = id_problem(8 * cores, 1000)
+        orc = load_oracle_fast()
+        orc.orc_id_last_error.restype = C.c_char_p
+        ib = sid.IdBatch(orc, "orc_id_", m, d, q.shape[0])
+        for _ in range(warm):
+            ib.solve(0.0, q, v)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ib.solve(0.0, q, v)
+        dt = time.perf_counter() - t0
+        return {"value": q.shape[0] * steps / dt, "unit": unit, "cores": cores, "kind": "port",
+                "sample": "%d instances x %d solves, OpenMP over instances; CPU restatement oracle/liborc_fast.so (-O3, AVX2+FMA) of the "
+                          "TSID formulation + the same QP method, not TSID/ProxQP" % (q.shape[0], steps)}, dt / steps * 1e3
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, ms = cpu_leg(K, W)
+        config["instances_total"] = config["instances_this_rank"] = 8 * cores
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": unit, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cu = load_cuda()
+    cu.smpc_id_launch_count.restype = C.c_int64
+    sid, m, d, q, v = id_problem(B, 1000 + rank)
+    ib = sid.IdBatch(cu, "smpc_id_", m, d, B)
+    qd, vd = torch.from_numpy(q).cuda(), torch.from_numpy(v).cuda()
+    taud = torch.empty((B, m.nv - 6), dtype=torch.float64, device="cuda")
+    ms = C.c_float()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # device-resident arm: inputs already in HBM; the context's own CUDA events time every launch on its stream
+    for _ in range(W):
+        assert cu.smpc_id_solve_dev(ib.ctx, C.c_double(0.0), C.c_void_p(qd.data_ptr()), C.c_void_p(vd.data_ptr()), C.c_void_p(taud.data_ptr())) == 0
+    ib.info()
+    barrier()
+    l0 = cu.smpc_id_launch_count(ib.ctx)
+    kernel_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        assert cu.smpc_id_solve_dev(ib.ctx, C.c_double(0.0), C.c_void_p(qd.data_ptr()), C.c_void_p(vd.data_ptr()), C.c_void_p(taud.data_ptr())) == 0
+        cu.smpc_id_last_solve_ms(ib.ctx, C.byref(ms))  # waits for this launch's end event
+        kernel_ms += ms.value
+    barrier()
+    launches = cu.smpc_id_launch_count(ib.ctx) - l0
+    dev_ms = max_over_ranks(kernel_ms / K)
+    # end-to-end arm: host buffers in, torques out, through the C ABI call a user makes
+    for _ in range(W):
+        ib.solve(0.0, q, v)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        tau = ib.solve(0.0, q, v)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / K * 1e3)
+    sampler.stop_flag = True
+    infos = ib.info()
+    assert all(x.status == 0 for x in infos), "unconverged QP in the bench batch"
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6539.9)))
+    bytes_per_inst = 8.0 * (m.nq + m.nv + (m.nv - 6) + m.nv + m.nfeet * 12) + 1256 + 48
+    achieved = bytes_per_inst * B / (dev_ms * 1e-3) / 1e9
+    line = {"metric": metric, "value": B * world / (dev_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(8 * B * (m.nq + m.nv)), "d2h_bytes_per_step": int(8 * B * (m.nv - 6))},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "note": "k_id_solve keeps the whole QP in shared memory (43.5 KB per CTA, 4 CTAs per SM): it is bound by dependent-issue "
+                                 "latency and CTA barriers (ncu: 7 warps stalled at a barrier per issue), not by HBM or the FP64 pipe"},
+            "newton_iters_mean": float(np.mean([x.newton_iters for x in infos])), "outer_iters_mean": float(np.mean([x.outer_iters for x in infos])),
+            "clocks": sampler.summary()}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_leg(3, 1)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,6 +354,8 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     cfg = args.config
+    if cfg == "id":
+        return run_id_bench(args, rank, world, local_rank, W, K)
     strong = args.total is not None
     if strong:
         first, B = smpc_dist.shard_range(args.total, world, rank)

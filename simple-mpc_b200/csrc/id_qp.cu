@@ -13,7 +13,7 @@ using namespace smpc;
 
 namespace
 {
-  __global__ void __launch_bounds__(ID_THREADS) k_id_solve(
+  __global__ void __launch_bounds__(ID_THREADS, 4) k_id_solve(
     const DevModel * __restrict__ M, const smpc_id_desc * __restrict__ D, const IdTargetDev * __restrict__ T, const IdDims L,
     const double * __restrict__ q, const double * __restrict__ v, double * __restrict__ tau, double * __restrict__ a,
     double * __restrict__ f, smpc_id_info * __restrict__ info, int batch)
@@ -139,6 +139,11 @@ static int id_create_impl(smpc_id_ctx * c, const smpc_model_desc * model, const 
   c->batch = batch;
   c->L = id_make_dims(*model, *desc);
   c->smem = sizeof(double) * (size_t)c->L.total;
+  if (c->L.nx > 64) // the back substitution keeps two rows per lane of one warp
+  {
+    smpc::err() = "smpc_id_create: " + std::to_string(c->L.nx) + " QP variables exceed what the one-warp back substitution is laid out for (64)";
+    return SMPC_ERR_UNSUPPORTED;
+  }
   int dev = 0, max_smem = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -54,7 +54,7 @@ namespace smpc
     int nj, nq, nv, na, nfeet;
     int nfmax, nx, ldn, me, mi;
     int o_q, o_v, o_M, o_h, o_JcT, o_H, o_g, o_A, o_b, o_C, o_l, o_u, o_Jt, o_bt, o_fr;
-    int o_x, o_xk, o_grad, o_dx, o_xt, o_hx, o_y, o_re, o_re2, o_z, o_si, o_si2, o_sc, o_act, o_part;
+    int o_x, o_xk, o_grad, o_dx, o_xt, o_hx, o_y, o_re, o_re2, o_z, o_si, o_si2, o_sc, o_act, o_part, o_pairs;
     int o_K;                                 // Newton matrix; the kinematics scratch below aliases it
     int o_oMi, o_Jw, o_ov, o_oa, o_Y, o_fs, o_Fc;
     int total;
@@ -95,10 +95,11 @@ namespace smpc
     L.o_sc = take(16);
     L.o_act = take((L.mi + 2) / 2 + 1); // int list of the active inequality rows
     L.o_part = take(4 * ID_THREADS);    // per-thread partials of the CTA-wide reductions
+    L.o_pairs = take((L.nx * (L.nx + 1) / 2 + L.nx + 1) / 2); // int table of the (i, j) pairs of the factorisation
     L.o_K = o;
     L.o_oMi = take(12 * L.nj), L.o_Jw = take(6 * L.nv), L.o_ov = take(6 * L.nj), L.o_oa = take(6 * L.nj);
     L.o_Y = take(36 * L.nj), L.o_fs = take(6 * L.nj), L.o_Fc = take(6 * L.nv);
-    const int endK = L.o_K + ((L.nx * L.ldn + 1) & ~1);
+    const int endK = L.o_K + (((L.nx + 1) * L.ldn + 1) & ~1); // + the right-hand-side row
     L.total = o > endK ? o : endK;
     return L;
   }
@@ -907,92 +908,6 @@ namespace smpc
     id_block_reduce<false>(L, sm, 1, slot);
   }
 
-  // left-looking Cholesky of the leading n x n block of K (lower part), one barrier per column. Row k (and K(k,k)) is read
-  // by every thread of column k's phase, so the INVERSE pivot goes to a side array (xt is free during the factorisation)
-  // instead of overwriting the diagonal. sm[sc + SC_BAD] = 1 on a non-positive pivot.
-  SMPC_DEV void id_chol(const IdDims & L, double * sm, int n)
-  {
-    const int ld = L.ldn;
-    double * K = sm + L.o_K;
-    for (int k = 0; k < n; k++)
-    {
-      SMPC_PAR(tid)
-      for (int i = k + tid; i < n; i += SMPC_NT)
-      {
-        const double * rk = K + k * ld;
-        const double * ri = K + i * ld;
-        double dk0 = rk[k], dk1 = 0, s0 = ri[k], s1 = 0;
-        int j = 0;
-        for (; j + 1 < k; j += 2)
-        {
-          dk0 -= rk[j] * rk[j];
-          dk1 -= rk[j + 1] * rk[j + 1];
-          s0 -= ri[j] * rk[j];
-          s1 -= ri[j + 1] * rk[j + 1];
-        }
-        if (j < k)
-        {
-          dk0 -= rk[j] * rk[j];
-          s0 -= ri[j] * rk[j];
-        }
-        const double dk = dk0 + dk1;
-        if (!(dk > 0))
-        {
-          sm[L.o_sc + SC_BAD] = 1.0;
-          continue;
-        }
-#ifdef __CUDACC__
-        const double rp = rsqrt(dk);
-#else
-        const double rp = 1.0 / sqrt(dk);
-#endif
-        if (i == k)
-          sm[L.o_xt + k] = rp;
-        else
-          K[i * ld + k] = (s0 + s1) * rp;
-      }
-      SMPC_END
-    }
-  }
-
-  // dx = -(L L^T)^-1 grad with L from id_chol (inverse pivots in xt): column-oriented substitutions, one barrier per column;
-  // entry k stays unscaled while the others consume it, one scaling pass closes each direction
-  SMPC_DEV void id_chol_solve(const IdDims & L, double * sm, int n)
-  {
-    const int ld = L.ldn;
-    const double * K = sm + L.o_K;
-    const double * ip = sm + L.o_xt;
-    double * dx = sm + L.o_dx;
-    SMPC_PAR(tid)
-    for (int i = tid; i < n; i += SMPC_NT)
-      dx[i] = -sm[L.o_grad + i];
-    SMPC_END
-    for (int k = 0; k < n - 1; k++)
-    {
-      SMPC_PAR(tid)
-      const double wk = dx[k] * ip[k];
-      for (int i = k + 1 + tid; i < n; i += SMPC_NT)
-        dx[i] -= K[i * ld + k] * wk;
-      SMPC_END
-    }
-    SMPC_PAR(tid)
-    for (int i = tid; i < n; i += SMPC_NT)
-      dx[i] = dx[i] * ip[i];
-    SMPC_END
-    for (int k = n - 1; k > 0; k--)
-    {
-      SMPC_PAR(tid)
-      const double xk = dx[k] * ip[k];
-      for (int i = tid; i < k; i += SMPC_NT)
-        dx[i] -= K[k * ld + i] * xk;
-      SMPC_END
-    }
-    SMPC_PAR(tid)
-    for (int i = tid; i < n; i += SMPC_NT)
-      dx[i] = dx[i] * ip[i];
-    SMPC_END
-  }
-
   SMPC_DEV void id_solve_qp(const IdDims & L, double * sm, int n, int me, int mi, smpc_id_info * info)
   {
     const int ld = L.ldn;
@@ -1019,6 +934,25 @@ namespace smpc
       z[i] = 0.0;
     if (tid == 0)
       sc[SC_BAD] = 0.0;
+    SMPC_END
+    // the pairs (i, j <= i) of the lower triangle plus the right-hand-side row (n, j), listed column by column
+    // (column j: rows j..n, starting at cs(j) = j (n + 1) - j (j - 1) / 2) once per solve: pairs[idx] = (i << 8) | j.
+    // Step k of the factorisation touches the contiguous tail idx >= cs(k + 1), dealt round-robin over the threads.
+    const int ntri = n * (n + 1) / 2, npair = ntri + n;
+    int * pairs = reinterpret_cast<int *>(sm + L.o_pairs);
+    SMPC_PAR(tid)
+    for (int idx = tid; idx < npair; idx += SMPC_NT)
+    {
+      const double hb = n + 1.5;
+      int j = (int)(hb - sqrt(hb * hb - 2.0 * idx));
+      j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
+      while (j > 0 && j * (n + 1) - j * (j - 1) / 2 > idx)
+        j--;
+      while (j < n - 1 && (j + 1) * (n + 1) - (j + 1) * j / 2 <= idx)
+        j++;
+      const int i = j + idx - (j * (n + 1) - j * (j - 1) / 2);
+      pairs[idx] = (i << 8) | j;
+    }
     SMPC_END
     double mu = ID_QP_MU0;
     int newton = 0, outer = 0, status = 1;
@@ -1095,23 +1029,21 @@ namespace smpc
         if (sc[SC_GN] <= ID_QP_GRAD_REL * sc[SC_GS])
           break;
         newton++;
-        // Newton matrix, lower triangle
+        // Newton matrix (lower triangle) with the right-hand side -grad as an extra row n, on the pairs this thread owns
         SMPC_PAR(tid)
         const double * A = sm + L.o_A;
         const double * Cm = sm + L.o_C;
         const double * H = sm + L.o_H;
         double * K = sm + L.o_K;
         const int nact = act[0];
-        const int npair = n * (n + 1) / 2;
         for (int idx = tid; idx < npair; idx += SMPC_NT)
         {
-          // idx -> (i, j), j <= i : i = floor((sqrt(8 idx + 1) - 1) / 2)
-          int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-          while (i * (i + 1) / 2 > idx)
-            i--;
-          while ((i + 1) * (i + 2) / 2 <= idx)
-            i++;
-          const int j = idx - i * (i + 1) / 2;
+          const int i = pairs[idx] >> 8, j = pairs[idx] & 255;
+          if (i == n)
+          {
+            K[n * ld + j] = -grad[j];
+            continue;
+          }
           double t0 = 0, t1 = 0;
           for (int r = 0; r < me; r++)
             t0 += A[r * ld + i] * A[r * ld + j];
@@ -1123,10 +1055,65 @@ namespace smpc
           K[i * ld + j] = H[i * ld + j] + (i == j ? ID_QP_RHO : 0.0) + (t0 + t1) * imu;
         }
         SMPC_END
-        id_chol(L, sm, n);
+        // right-looking LDL^T, one barrier per column, every thread updating its own pairs of the trailing block:
+        //   K(i,j) -= K(i,k) K(j,k) / K(k,k)   (j > k; nobody writes column k during step k)
+        // the extra row carries the forward substitution along: K(n,j) ends as z_j of U z = -grad (U unit lower, K = U D U^T)
+        for (int k = 0; k < n; k++)
+        {
+          SMPC_PAR(tid)
+          double * K = sm + L.o_K;
+          const double dk = K[k * ld + k];
+          const double inv = 1.0 / dk;
+          if (tid == 0)
+          {
+            xt[k] = inv; // xt is free during the factorisation
+            if (!(dk > 0))
+              sc[SC_BAD] = 1.0;
+          }
+          for (int idx = (k + 1) * (n + 1) - (k + 1) * k / 2 + tid; idx < npair; idx += SMPC_NT)
+          {
+            const int i = pairs[idx] >> 8, j = pairs[idx] & 255;
+            K[i * ld + j] -= K[i * ld + k] * (K[j * ld + k] * inv);
+          }
+          SMPC_END
+        }
         if (sc[SC_BAD] != 0.0)
           break;
-        id_chol_solve(L, sm, n);
+        // dx = U^-T D^-1 z : column-oriented back substitution. On the device one warp keeps y in registers (lane l owns rows
+        // l and l + 32) and broadcasts x_k by shuffle, so the n dependent steps need no barrier.
+        SMPC_PAR(tid)
+        const double * K = sm + L.o_K;
+#ifdef __CUDACC__
+        if (tid < 32)
+        {
+          const int i0 = tid, i1 = tid + 32;
+          const double d0 = (i0 < n) ? xt[i0] : 0.0, d1 = (i1 < n) ? xt[i1] : 0.0;
+          double y0 = (i0 < n) ? K[n * ld + i0] * d0 : 0.0, y1 = (i1 < n) ? K[n * ld + i1] * d1 : 0.0;
+          for (int k = n - 1; k > 0; k--)
+          {
+            const double xa = __shfl_sync(0xffffffffu, y0, k & 31), xb = __shfl_sync(0xffffffffu, y1, k & 31);
+            const double xk_ = (k < 32) ? xa : xb;
+            if (i0 < k)
+              y0 -= K[k * ld + i0] * d0 * xk_;
+            if (i1 < k)
+              y1 -= K[k * ld + i1] * d1 * xk_;
+          }
+          if (i0 < n)
+            dx[i0] = y0;
+          if (i1 < n)
+            dx[i1] = y1;
+        }
+#else
+        if (tid == 0)
+        {
+          for (int i = 0; i < n; i++)
+            dx[i] = K[n * ld + i] * xt[i];
+          for (int k = n - 1; k > 0; k--)
+            for (int i = 0; i < k; i++)
+              dx[i] -= K[k * ld + i] * xt[i] * dx[k];
+        }
+#endif
+        SMPC_END
         SMPC_PAR(tid)
         double s = 0;
         for (int i = tid; i < n; i += SMPC_NT)

@@ -35,10 +35,12 @@ def main():
                      int(r[iwfi] or 0) if iwfi is not None else 0))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = max([os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")], key=os.path.getsize)
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cub], stdout=subprocess.PIPE, text=True).stdout.splitlines()
     # mangled name fragment from the demangled kernel name
     base = re.search(r"(k_\w+)", kname).group(1)
+    # the library holds one cubin per translation unit: take the one whose symbol table has the kernel
+    cubs = sorted([os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")], key=os.path.getsize, reverse=True)
+    cub = next((c for c in cubs if base.encode() in open(c, "rb").read()), cubs[0])
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cub], stdout=subprocess.PIPE, text=True).stdout.splitlines()
     # template arguments in order, as they appear in the mangled name (Li36ELi24E..., Lb1E)
     targs = re.compile(".*".join(("Li%sE" % a) if k == "int" else ("Lb%sE" % a) for k, a in re.findall(r"\((int|bool)\)(\d+)", kname)))
     sect, cur, lines = None, None, []
