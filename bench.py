@@ -216,34 +216,53 @@ def id_problem(B, seed):
     q[:, 7:] += 0.03 * rng.standard_normal((B, m.nv - 6))
     q[:, :2] += 0.01 * rng.standard_normal((B, 2))
     v = np.zeros((B, m.nv))
-    v[:, 6:] = 0.02 * rng.standard_normal((B, m.nv - 6))
     return sid, m, d, np.ascontiguousarray(q), np.ascontiguousarray(v)
 
 
+def id_trajectory(ib, sid, q, v, steps, dt=1e-3):
+    """closed loop of every instance under its own controller (the integration of the reference's tests,
+    tests/inverse-dynamics/kinodynamics-id.cpp:46-60): the measured states one control period apart that the timed region replays"""
+    qs, vs = [q.copy()], [v.copy()]
+    for t in range(steps - 1):
+        ib.solve(t * dt, q, v)
+        a = ib.accelerations()
+        q = sid.integrate_q_batch(q, (v + a / 2 * dt) * dt)
+        v = v + a * dt
+        qs.append(q.copy())
+        vs.append(v.copy())
+    return np.ascontiguousarray(np.stack(qs)), np.ascontiguousarray(np.stack(vs))
+
+
 def run_id_bench(args, rank, world, local_rank, W, K):
-    """bench line of the batched inverse-dynamics QP: one step = one KinodynamicsID::solve of every instance."""
+    """bench line of the batched inverse-dynamics QP: one step = one KinodynamicsID::solve of every instance at the next
+    measured state of its 1 kHz closed loop (warm-started from the previous solve, as the controller object is in the
+    reference's loop)."""
     B = args.batch or CONFIGS["id"]["batch"]
     metric, unit = "id_qp_solves_per_s", "solves/s"
-    config = {"workload": "%s, %d instances/GPU, cold-started every solve" % (CONFIGS["id"]["what"], B), "config": "id",
-              "instances_total": B * world, "instances_this_rank": B,
-              "l2": "everything lives in shared memory; HBM carries q, v in and tau, a, f out (2.3 KB per instance)",
+    config = {"workload": "%s, %d instances/GPU, closed loop at 1 kHz, each solve warm-started from the previous one" % (CONFIGS["id"]["what"], B),
+              "config": "id", "instances_total": B * world, "instances_this_rank": B,
+              "l2": "everything lives in shared memory; HBM carries q, v in and tau, a, f out plus the 0.7 KB warm-start record (3 KB per instance)",
               "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world}
     cores = os.cpu_count() or 1
+    T = W + K
 
     def cpu_leg(steps, warm):
         sid, m, d, q, v = id_problem(8 * cores, 1000)
         orc = load_oracle_fast()
         orc.orc_id_last_error.restype = C.c_char_p
         ib = sid.IdBatch(orc, "orc_id_", m, d, q.shape[0])
-        for _ in range(warm):
-            ib.solve(0.0, q, v)
+        qs, vs = id_trajectory(ib, sid, q, v, warm + steps)
+        ib.set_warm_start(False)
+        ib.set_warm_start(True)
+        for t in range(warm):
+            ib.solve(0.0, qs[t], vs[t])
         t0 = time.perf_counter()
-        for _ in range(steps):
-            ib.solve(0.0, q, v)
+        for t in range(warm, warm + steps):
+            ib.solve(0.0, qs[t], vs[t])
         dt = time.perf_counter() - t0
         return {"value": q.shape[0] * steps / dt, "unit": unit, "cores": cores, "kind": "port",
-                "sample": "%d instances x %d solves, OpenMP over instances; CPU restatement oracle/liborc_fast.so (-O3, AVX2+FMA) of the "
-                          "TSID formulation + the same QP method, not TSID/ProxQP" % (q.shape[0], steps)}, dt / steps * 1e3
+                "sample": "%d instances x %d consecutive solves of their closed loops (warm-started), OpenMP over instances; CPU restatement "
+                          "oracle/liborc_fast.so (-O3, AVX2+FMA) of the TSID formulation + the same QP method, not TSID/ProxQP" % (q.shape[0], steps)}, dt / steps * 1e3
 
     if args.impl == "reference":
         if rank != 0:
@@ -265,7 +284,8 @@ def run_id_bench(args, rank, world, local_rank, W, K):
     cu.smpc_id_launch_count.restype = C.c_int64
     sid, m, d, q, v = id_problem(B, 1000 + rank)
     ib = sid.IdBatch(cu, "smpc_id_", m, d, B)
-    qd, vd = torch.from_numpy(q).cuda(), torch.from_numpy(v).cuda()
+    qs, vs = id_trajectory(ib, sid, q, v, T)
+    qd, vd = torch.from_numpy(qs).cuda(), torch.from_numpy(vs).cuda()
     taud = torch.empty((B, m.nv - 6), dtype=torch.float64, device="cuda")
     ms = C.c_float()
 
@@ -281,34 +301,51 @@ def run_id_bench(args, rank, world, local_rank, W, K):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def solve_dev(t):
+        rc = cu.smpc_id_solve_dev(ib.ctx, C.c_double(0.0), C.c_void_p(qd[t].data_ptr()), C.c_void_p(vd[t].data_ptr()), C.c_void_p(taud.data_ptr()))
+        assert rc == 0, cu.smpc_last_error()
+
+    def forget():
+        ib.set_warm_start(False)
+        ib.set_warm_start(True)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # device-resident arm: inputs already in HBM; the context's own CUDA events time every launch on its stream
-    for _ in range(W):
-        assert cu.smpc_id_solve_dev(ib.ctx, C.c_double(0.0), C.c_void_p(qd.data_ptr()), C.c_void_p(vd.data_ptr()), C.c_void_p(taud.data_ptr())) == 0
+    # device-resident arm: the measured states already in HBM; the context's own CUDA events time every launch on its stream
+    forget()
+    for t in range(W):
+        solve_dev(t)
     ib.info()
     barrier()
     l0 = cu.smpc_id_launch_count(ib.ctx)
     kernel_ms = 0.0
-    t0 = time.perf_counter()
-    for _ in range(K):
-        assert cu.smpc_id_solve_dev(ib.ctx, C.c_double(0.0), C.c_void_p(qd.data_ptr()), C.c_void_p(vd.data_ptr()), C.c_void_p(taud.data_ptr())) == 0
+    for t in range(W, T):
+        solve_dev(t)
         cu.smpc_id_last_solve_ms(ib.ctx, C.byref(ms))  # waits for this launch's end event
         kernel_ms += ms.value
     barrier()
     launches = cu.smpc_id_launch_count(ib.ctx) - l0
     dev_ms = max_over_ranks(kernel_ms / K)
+    infos = ib.info()
     # end-to-end arm: host buffers in, torques out, through the C ABI call a user makes
-    for _ in range(W):
-        ib.solve(0.0, q, v)
+    forget()
+    for t in range(W):
+        ib.solve(0.0, qs[t], vs[t])
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        tau = ib.solve(0.0, q, v)
+    for t in range(W, T):
+        tau = ib.solve(0.0, qs[t], vs[t])
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) / K * 1e3)
+    # cold-started solves of the last state, for the record
+    ib.set_warm_start(False)
+    cold_ms = 0.0
+    for _ in range(3):
+        solve_dev(T - 1)
+        cu.smpc_id_last_solve_ms(ib.ctx, C.byref(ms))
+        cold_ms += ms.value / 3
+    cold_newton = float(np.mean([x.newton_iters for x in ib.info()]))
     sampler.stop_flag = True
-    infos = ib.info()
     assert all(x.status == 0 for x in infos), "unconverged QP in the bench batch"
     if rank != 0:
         return
@@ -318,20 +355,25 @@ def run_id_bench(args, rank, world, local_rank, W, K):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6539.9)))
-    bytes_per_inst = 8.0 * (m.nq + m.nv + (m.nv - 6) + m.nv + m.nfeet * 12) + 1256 + 48
+    ws_bytes = 8.0 * 2 * (2 + 30 + 6 + 44)  # warm-start record read + written
+    bytes_per_inst = 8.0 * (m.nq + m.nv + (m.nv - 6) + m.nv + m.nfeet * 12) + 1256 + 48 + ws_bytes
     achieved = bytes_per_inst * B / (dev_ms * 1e-3) / 1e9
+    newton = [x.newton_iters for x in infos]
     line = {"metric": metric, "value": B * world / (dev_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(8 * B * (m.nq + m.nv)), "d2h_bytes_per_step": int(8 * B * (m.nv - 6))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "note": "k_id_solve keeps the whole QP in shared memory (43.5 KB per CTA, 4 CTAs per SM): it is bound by dependent-issue "
-                                 "latency and CTA barriers (ncu: 7 warps stalled at a barrier per issue), not by HBM or the FP64 pipe"},
-            "newton_iters_mean": float(np.mean([x.newton_iters for x in infos])), "outer_iters_mean": float(np.mean([x.outer_iters for x in infos])),
+                         "note": "k_id_solve keeps the whole QP in shared memory (44.5 KB per CTA, 4 CTAs per SM): it is bound by dependent-issue "
+                                 "latency and CTA barriers (ncu, profiles/r02an_*), not by HBM or the FP64 pipe"},
+            "newton_iters": {"mean": float(np.mean(newton)), "max": int(np.max(newton))},
+            "outer_iters_mean": float(np.mean([x.outer_iters for x in infos])),
+            "cold_start": {"ms_per_step": cold_ms, "solves_per_s": B * world / (cold_ms * 1e-3), "newton_iters_mean": cold_newton},
+            "control_rate_hz_at_this_batch": 1e3 / e2e_ms,
             "clocks": sampler.summary()}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_leg(3, 1)
+        line["cpu_baseline"], _ = cpu_leg(10, 3)
     print(json.dumps(line))
 
 

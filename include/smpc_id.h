@@ -102,6 +102,10 @@ int smpc_id_get_info(smpc_id_ctx *, int first, int n_inst, smpc_id_info * info);
 
 /* Device-resident variant for callers whose measurements already live in HBM (bench `value` arm): device pointers. */
 int smpc_id_solve_dev(smpc_id_ctx *, double t, const double * q_meas_dev, const double * v_meas_dev, double * tau_res_dev);
+/* Warm start (default on): a solve whose contact layout equals that of the instance's previous converged solve starts from
+ * its primal / dual solution, like the ProxQP object TSID keeps between calls (tsid/solvers/solver-proxqp [UPSTREAM]).
+ * The QP is strictly convex, so only the iteration count depends on it. 0 = every solve starts from zero. */
+int smpc_id_set_warm_start(smpc_id_ctx *, int on);
 int smpc_id_last_solve_ms(smpc_id_ctx *, float * ms);
 int64_t smpc_id_launch_count(smpc_id_ctx *);
 

@@ -16,6 +16,7 @@ namespace
     orc::Model model;
     smpc_id_desc desc;
     int batch;
+    bool warm = true;
     std::vector<orc::IdTarget> tgt;
     std::vector<orc::IdSolution> sol;
     IdCtx(const smpc_model_desc & m, const smpc_id_desc & d, int B) : model(m), desc(d), batch(B), tgt(B), sol(B) {}
@@ -167,7 +168,7 @@ int orc_id_solve(IdCtx * c, double, const double * q_meas, const double * v_meas
   {
     try
     {
-      orc::id_solve(m, c->desc, c->tgt[b], q_meas + (size_t)b * m.nq, v_meas + (size_t)b * m.nv, c->sol[b]);
+      orc::id_solve(m, c->desc, c->tgt[b], q_meas + (size_t)b * m.nq, v_meas + (size_t)b * m.nv, c->sol[b], c->warm);
       memcpy(tau_res + (size_t)b * na, c->sol[b].tau.data(), na * sizeof(double));
     }
     catch (const std::exception & e)
@@ -180,6 +181,17 @@ int orc_id_solve(IdCtx * c, double, const double * q_meas, const double * v_meas
     }
   }
   return bad ? SMPC_ERR_INVALID : 0;
+}
+
+int orc_id_set_warm_start(IdCtx * c, int on)
+{
+  if (!c)
+    return fail("orc_id_set_warm_start: null context");
+  c->warm = on != 0;
+  if (!on)
+    for (auto & s : c->sol)
+      s.sig = -1.0;
+  return 0;
 }
 
 int orc_id_get_accelerations(IdCtx * c, int first, int n_inst, double * a)

@@ -13,8 +13,8 @@
 //   TaskJointPosVelAccBounds (Del Prete, "Joint position and velocity bounds in discrete-time acceleration/torque control
 //   of robot manipulators", RA-L 2018), TaskActuationBounds, contacts::ContactPoint / Contact6d.
 // The QP itself is strictly convex, so its solution does not depend on the solver: instead of restating ProxQP's iterates
-// (proxsuite 0.7.2, un-vendored) it is solved here by a proximal augmented-Lagrangian / semismooth-Newton method to a KKT
-// residual of 1e-9, far below the 1e-5 ProxQP stops at in TSID's wrapper; the CUDA path is compared at solution level.
+// (proxsuite 0.7.2, un-vendored) it is solved here by a proximal augmented-Lagrangian / semismooth-Newton method to a relative KKT
+// residual of 1e-10, far below the 1e-5 ProxQP stops at in TSID's wrapper; the CUDA path is compared at solution level.
 // Reference quirks kept: the base task's velocity reference receives the ACCELERATION target and its acceleration
 // reference stays zero (kinodynamics-id.cpp:224-225 calls setDerivative twice); contact references are reset to the
 // measured foot pose at every solve (:199-216), so the proportional term of the contact tasks is identically zero.
@@ -30,10 +30,11 @@ namespace orc
   constexpr double ID_HESSIAN_REG = 1e-8; // tsid DEFAULT_HESSIAN_REGULARIZATION [UPSTREAM]
   constexpr double ID_BIG = 1e10;         // tsid's "no bound" value [UPSTREAM]
   constexpr double ID_DDQ_MAX = 1e10;     // TaskJointPosVelAccBounds acceleration bound left at its default (kinodynamics-id.cpp:88-89)
-  constexpr double ID_QP_EPS = 1e-9;
+  constexpr double ID_QP_EPS = 1e-10;
   constexpr double ID_QP_RHO = 1e-10; // primal proximal weight (below the Hessian regularisation, so the weakest directions still move)
   constexpr double ID_QP_MU0 = 1e-2;  // initial penalty parameter (1/mu multiplies the constraint violations)
   constexpr double ID_QP_MU_MIN = 1e-4;
+  constexpr double ID_QP_MU_WARM = 1e-3; // first penalty parameter of a warm-started solve
   constexpr double ID_QP_GRAD_REL = 1e-13; // inner stop: gradient at the rounding floor of its largest term
   constexpr int ID_QP_MAX_OUTER = 30;
   constexpr int ID_QP_MAX_INNER = 30;
@@ -64,6 +65,7 @@ namespace orc
     Vec x, y, z, tau, a;
     double f[SMPC_MAX_FEET][SMPC_ID_MAX_FVAR];
     smpc_id_info info;
+    double sig = -1.0; // layout signature of the stored (x, y, z): a matching solve starts from them (warm start)
   };
 
   // Joint-space inertia and nonlinear effects (gravity included) from the drift pass (same construction as full_dynamics).
@@ -532,11 +534,18 @@ namespace orc
     return val;
   }
 
-  inline void id_solve_qp(const IdQP & qp, IdSolution & sol)
+  inline void id_solve_qp(const IdQP & qp, IdSolution & sol, double sig = -2.0, bool warm_enabled = false)
   {
     const int n = qp.n, me = qp.me, mi = qp.mi;
     Vec x(n, 0.0), y(me, 0.0), z(mi, 0.0), xk(n), re(me), si(mi), grad(n), dx(n), xt(n), re2(me), si2(mi);
-    double mu = ID_QP_MU0;
+    const bool warm = warm_enabled && sol.sig == sig && (int)sol.x.size() == n && (int)sol.y.size() == me && (int)sol.z.size() == mi;
+    if (warm)
+    {
+      x = sol.x;
+      y = sol.y;
+      z = sol.z;
+    }
+    double mu = warm ? ID_QP_MU_WARM : ID_QP_MU0;
     int newton = 0, outer = 0, status = 1;
     double pres = 0, dres = 0;
     Mat K(n, n);
@@ -668,6 +677,7 @@ namespace orc
     sol.x = x;
     sol.y = y;
     sol.z = z;
+    sol.sig = (status == 0) ? sig : -1.0;
     sol.info.status = status;
     sol.info.outer_iters = outer;
     sol.info.newton_iters = newton;
@@ -679,12 +689,16 @@ namespace orc
   }
 
   // KinodynamicsID::solve for one instance.
-  inline void id_solve(const Model & m, const smpc_id_desc & D, const IdTarget & T, const double * q, const double * v, IdSolution & sol)
+  inline void id_solve(
+    const Model & m, const smpc_id_desc & D, const IdTarget & T, const double * q, const double * v, IdSolution & sol, bool warm_start = false)
   {
     IdQP qp;
     IdWork W;
     id_build_qp(m, D, T, q, v, qp, W);
-    id_solve_qp(qp, sol);
+    int mask = 0;
+    for (int f = 0; f < m.nfeet; f++)
+      mask |= (T.active[f] ? 1 : 0) << f;
+    id_solve_qp(qp, sol, (double)(qp.n | (qp.me << 8) | (qp.mi << 16) | (mask << 24)), warm_start);
     const int nv = m.nv, na = nv - 6;
     sol.a.assign(sol.x.begin(), sol.x.begin() + nv);
     sol.tau.assign(na, 0);

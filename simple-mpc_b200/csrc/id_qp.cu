@@ -16,7 +16,7 @@ namespace
   __global__ void __launch_bounds__(ID_THREADS, 4) k_id_solve(
     const DevModel * __restrict__ M, const smpc_id_desc * __restrict__ D, const IdTargetDev * __restrict__ T, const IdDims L,
     const double * __restrict__ q, const double * __restrict__ v, double * __restrict__ tau, double * __restrict__ a,
-    double * __restrict__ f, smpc_id_info * __restrict__ info, int batch)
+    double * __restrict__ f, smpc_id_info * __restrict__ info, double * __restrict__ ws, int batch)
   {
     extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.x;
@@ -24,7 +24,7 @@ namespace
       return;
     id_solve_cta(
       *M, *D, T[b], L, q + (size_t)b * L.nq, v + (size_t)b * L.nv, sm, tau + (size_t)b * L.na, a + (size_t)b * L.nv,
-      f + (size_t)b * L.nfeet * SMPC_ID_MAX_FVAR, info + b);
+      f + (size_t)b * L.nfeet * SMPC_ID_MAX_FVAR, info + b, ws ? ws + (size_t)b * L.ws_stride : nullptr);
   }
 } // namespace
 
@@ -42,6 +42,8 @@ struct smpc_id_ctx
   bool tgt_dirty = true;
   double *d_q = nullptr, *d_v = nullptr, *d_tau = nullptr, *d_a = nullptr, *d_f = nullptr;
   smpc_id_info * d_info = nullptr;
+  double * d_ws = nullptr; // previous solution of every instance (warm start)
+  bool warm_start = true;
   double *h_q = nullptr, *h_v = nullptr, *h_tau = nullptr; // pinned staging
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -80,7 +82,7 @@ namespace
       return rc;
     CU(cudaEventRecord(c->e0, c->stream));
     k_id_solve<<<c->batch, ID_THREADS, c->smem, c->stream>>>(
-      c->d_model, c->d_desc, c->d_tgt, c->L, q_dev, v_dev, tau_dev, c->d_a, c->d_f, c->d_info, c->batch);
+      c->d_model, c->d_desc, c->d_tgt, c->L, q_dev, v_dev, tau_dev, c->d_a, c->d_f, c->d_info, c->warm_start ? c->d_ws : nullptr, c->batch);
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->e1, c->stream));
     c->launches++;
@@ -106,6 +108,7 @@ void smpc_id_destroy(smpc_id_ctx * c)
   if (!c)
     return;
   cudaFree(c->d_model), cudaFree(c->d_desc), cudaFree(c->d_tgt);
+  cudaFree(c->d_ws);
   cudaFree(c->d_q), cudaFree(c->d_v), cudaFree(c->d_tau), cudaFree(c->d_a), cudaFree(c->d_f), cudaFree(c->d_info);
   cudaFreeHost(c->h_q), cudaFreeHost(c->h_v), cudaFreeHost(c->h_tau);
   if (c->e0)
@@ -166,6 +169,8 @@ static int id_create_impl(smpc_id_ctx * c, const smpc_model_desc * model, const 
   CU(cudaMalloc(&c->d_a, sizeof(double) * B * model->nv));
   CU(cudaMalloc(&c->d_f, sizeof(double) * B * model->nfeet * SMPC_ID_MAX_FVAR));
   CU(cudaMalloc(&c->d_info, sizeof(smpc_id_info) * B));
+  CU(cudaMalloc(&c->d_ws, sizeof(double) * B * c->L.ws_stride));
+  CU(cudaMemset(c->d_ws, 0xff, sizeof(double) * B * c->L.ws_stride)); // NaN signatures: no previous solution
   CU(cudaMallocHost(&c->h_q, sizeof(double) * B * model->nq));
   CU(cudaMallocHost(&c->h_v, sizeof(double) * B * model->nv));
   CU(cudaMallocHost(&c->h_tau, sizeof(double) * B * (model->nv - 6)));
@@ -312,5 +317,15 @@ int smpc_id_last_solve_ms(smpc_id_ctx * c, float * ms)
 }
 
 int64_t smpc_id_launch_count(smpc_id_ctx * c) { return c ? c->launches : 0; }
+
+int smpc_id_set_warm_start(smpc_id_ctx * c, int on)
+{
+  if (!c)
+    return bad("smpc_id_set_warm_start: null context");
+  c->warm_start = on != 0;
+  if (!on) // forget the stored solutions, so that switching it back on starts cold once
+    CU(cudaMemsetAsync(c->d_ws, 0xff, sizeof(double) * (size_t)c->batch * c->L.ws_stride, c->stream));
+  return 0;
+}
 
 } // extern "C"

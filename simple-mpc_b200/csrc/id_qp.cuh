@@ -13,7 +13,7 @@
 //                  left-looking Cholesky), tau = M_a a + h_a - (Jc^T T)_a f
 // Written in the SMPC_PAR phase discipline of par.cuh, so tests/host_emul compiles it for the CPU.
 // Algorithm, constants and task definitions follow oracle/orc_id.hpp (which cites TSID); the comparison with the oracle is
-// at solution level (both solve the same strictly convex QP to a relative KKT residual of 1e-9).
+// at solution level (both solve the same strictly convex QP to a relative KKT residual of 1e-10).
 #pragma once
 #include "dev_math.cuh"
 #include "dev_types.h"
@@ -25,10 +25,11 @@ namespace smpc
   constexpr double ID_HESSIAN_REG = 1e-8;
   constexpr double ID_BIG = 1e10;
   constexpr double ID_DDQ_MAX = 1e10;
-  constexpr double ID_QP_EPS = 1e-9;
+  constexpr double ID_QP_EPS = 1e-10;
   constexpr double ID_QP_RHO = 1e-10;
   constexpr double ID_QP_MU0 = 1e-2;
   constexpr double ID_QP_MU_MIN = 1e-4;
+  constexpr double ID_QP_MU_WARM = 1e-3; // first penalty parameter of a warm-started solve
   constexpr double ID_QP_GRAD_REL = 1e-13;
   constexpr int ID_QP_MAX_OUTER = 30;
   constexpr int ID_QP_MAX_INNER = 30;
@@ -55,6 +56,7 @@ namespace smpc
     int nfmax, nx, ldn, me, mi;
     int o_q, o_v, o_M, o_h, o_JcT, o_H, o_g, o_A, o_b, o_C, o_l, o_u, o_Jt, o_bt, o_fr;
     int o_x, o_xk, o_grad, o_dx, o_xt, o_hx, o_y, o_re, o_re2, o_z, o_si, o_si2, o_sc, o_act, o_part, o_pairs;
+    int ws_stride;                           // doubles per instance of the warm-start record in global memory
     int o_K;                                 // Newton matrix; the kinematics scratch below aliases it
     int o_oMi, o_Jw, o_ov, o_oa, o_Y, o_fs, o_Fc;
     int total;
@@ -77,6 +79,7 @@ namespace smpc
     L.ldn = L.nx | 1;
     L.me = 6 + (D.settings.contact_motion_equality ? nmot : 0);
     L.mi = ncone + 2 * L.na;
+    L.ws_stride = 2 + L.nx + L.me + L.mi;
     int o = 0;
     auto take = [&](int n) {
       const int at = o;
@@ -908,7 +911,10 @@ namespace smpc
     id_block_reduce<false>(L, sm, 1, slot);
   }
 
-  SMPC_DEV void id_solve_qp(const IdDims & L, double * sm, int n, int me, int mi, smpc_id_info * info)
+  // ws (optional, global memory): the instance's previous solution [signature, x (nx), y (me), z (mi)] with the dims' maxima
+  // as strides; a solve whose layout signature matches starts from it (the QP is strictly convex: the solution does not
+  // depend on the starting point, the iteration count does) and every converged solve stores its own.
+  SMPC_DEV void id_solve_qp(const IdDims & L, double * sm, int n, int me, int mi, smpc_id_info * info, double * ws, double sig)
   {
     const int ld = L.ldn;
     double * x = sm + L.o_x;
@@ -925,13 +931,14 @@ namespace smpc
     double * sc = sm + L.o_sc;
     double * part = sm + L.o_part;
     int * act = reinterpret_cast<int *>(sm + L.o_act);
+    const bool warm = (ws != nullptr) && (ws[0] == sig);
     SMPC_PAR(tid)
     for (int i = tid; i < n; i += SMPC_NT)
-      x[i] = 0.0;
+      x[i] = warm ? ws[1 + i] : 0.0;
     for (int i = tid; i < me; i += SMPC_NT)
-      y[i] = 0.0;
+      y[i] = warm ? ws[1 + L.nx + i] : 0.0;
     for (int i = tid; i < mi; i += SMPC_NT)
-      z[i] = 0.0;
+      z[i] = warm ? ws[1 + L.nx + L.me + i] : 0.0;
     if (tid == 0)
       sc[SC_BAD] = 0.0;
     SMPC_END
@@ -954,7 +961,7 @@ namespace smpc
       pairs[idx] = (i << 8) | j;
     }
     SMPC_END
-    double mu = ID_QP_MU0;
+    double mu = warm ? ID_QP_MU_WARM : ID_QP_MU0;
     int newton = 0, outer = 0, status = 1;
     double pres = 0, dres = 0;
     for (outer = 0; outer < ID_QP_MAX_OUTER; outer++)
@@ -1233,13 +1240,24 @@ namespace smpc
       info->prim_res = pres;
       info->dual_res = dres;
     }
+    if (ws != nullptr)
+    { // ws[0] was read by every thread before the first barrier of this routine
+      if (tid == 0)
+        ws[0] = (status == 0) ? sig : -1.0;
+      for (int i = tid; i < n; i += SMPC_NT)
+        ws[1 + i] = x[i];
+      for (int i = tid; i < me; i += SMPC_NT)
+        ws[1 + L.nx + i] = y[i];
+      for (int i = tid; i < mi; i += SMPC_NT)
+        ws[1 + L.nx + L.me + i] = z[i];
+    }
     SMPC_END
   }
 
   // One instance: q, v (global) -> tau (na), a (nv), f (nfeet x 12), info.
   SMPC_DEV void id_solve_cta(
     const DevModel & Mo, const smpc_id_desc & D, const IdTargetDev & T, const IdDims & L, const double * q_g, const double * v_g,
-    double * sm, double * tau_g, double * a_g, double * f_g, smpc_id_info * info)
+    double * sm, double * tau_g, double * a_g, double * f_g, smpc_id_info * info, double * ws = nullptr)
   {
     const int nv = L.nv, na = L.na;
     SMPC_PAR(tid)
@@ -1251,7 +1269,10 @@ namespace smpc
     id_dynamics(Mo, L, sm);
     int n, me, mi;
     id_build_qp(Mo, D, T, L, sm, n, me, mi);
-    id_solve_qp(L, sm, n, me, mi, info);
+    int mask = 0;
+    for (int f = 0; f < L.nfeet; f++)
+      mask |= (T.active[f] ? 1 : 0) << f;
+    id_solve_qp(L, sm, n, me, mi, info, ws, (double)(n | (me << 8) | (mi << 16) | (mask << 24)));
     SMPC_PAR(tid)
     const double * x = sm + L.o_x;
     const double * Mm = sm + L.o_M;

@@ -127,6 +127,9 @@ class IdBatch:
         self._check(self._f("solve")(self.ctx, C.c_double(t), _p(q), _p(v), _p(tau)))
         return tau
 
+    def set_warm_start(self, on):
+        self._check(self._f("set_warm_start")(self.ctx, C.c_int(1 if on else 0)))
+
     def accelerations(self):
         a = np.zeros((self.B, self.nv))
         self._check(self._f("get_accelerations")(self.ctx, C.c_int(0), C.c_int(self.B), _p(a)))
@@ -166,4 +169,31 @@ def integrate_q(q, dv):
                 s * s2 - x * x2 - y * y2 - z * z2]
     out[3:7] /= np.linalg.norm(out[3:7])
     out[7:] = q[7:] + dv[6:]
+    return out
+
+
+def integrate_q_batch(q, dv):
+    """integrate_q for a batch (B x nq, B x nv), vectorised."""
+    q = np.asarray(q, float)
+    out = q.copy()
+    v, w = dv[:, :3], dv[:, 3:6]
+    th = np.linalg.norm(w, axis=1)
+    small = th < 1e-8
+    ths = np.where(small, 1.0, th)
+    cb = np.where(small, 0.5, (1 - np.cos(ths)) / ths**2)
+    cc = np.where(small, 1.0 / 6.0, (ths - np.sin(ths)) / ths**3)
+    wxv = np.cross(w, v)
+    Vv = v + cb[:, None] * wxv + cc[:, None] * np.cross(w, wxv)
+    x, y, z, s = q[:, 3], q[:, 4], q[:, 5], q[:, 6]
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * s), 2 * (x * z + y * s),
+                  2 * (x * y + z * s), 1 - 2 * (x * x + z * z), 2 * (y * z - x * s),
+                  2 * (x * z - y * s), 2 * (y * z + x * s), 1 - 2 * (x * x + y * y)], axis=1).reshape(-1, 3, 3)
+    out[:, :3] = q[:, :3] + np.einsum("bij,bj->bi", R, Vv)
+    sh = np.where(small, 0.5, np.sin(ths / 2) / ths)
+    x2, y2, z2 = sh * w[:, 0], sh * w[:, 1], sh * w[:, 2]
+    s2 = np.where(small, 1.0, np.cos(ths / 2))
+    quat = np.stack([s * x2 + x * s2 + y * z2 - z * y2, s * y2 - x * z2 + y * s2 + z * x2, s * z2 + x * y2 - y * x2 + z * s2,
+                     s * s2 - x * x2 - y * y2 - z * z2], axis=1)
+    out[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    out[:, 7:] = q[:, 7:] + dv[:, 6:]
     return out

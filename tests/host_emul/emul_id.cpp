@@ -14,7 +14,7 @@ int emul_id_solve(
   const smpc_model_desc * model, const smpc_id_desc * desc, const double * q_target, const double * v_target, const double * a_target,
   const double * com, const double * vcom, const double * feet_pose, const double * feet_vel, const int32_t * contact,
   const double * f_target, int use_default_target, const double * q, const double * v, double * tau, double * a, double * f,
-  smpc_id_info * info)
+  smpc_id_info * info, double * ws /* warm-start record of emul_id_ws_doubles() entries, or NULL */)
 {
   try
   {
@@ -31,7 +31,7 @@ int emul_id_solve(
         id_host_set_target(*model, T, q_target, v_target, a_target, contact, f_target);
     }
     std::vector<double> sm(L.total, 0.0);
-    id_solve_cta(Mo, *desc, T, L, q, v, sm.data(), tau, a, f, info);
+    id_solve_cta(Mo, *desc, T, L, q, v, sm.data(), tau, a, f, info, ws);
     return 0;
   }
   catch (const std::exception &)
@@ -40,6 +40,7 @@ int emul_id_solve(
   }
 }
 
+int emul_id_ws_doubles(const smpc_model_desc * model, const smpc_id_desc * desc) { return id_make_dims(*model, *desc).ws_stride; }
 int emul_id_smem_bytes(const smpc_model_desc * model, const smpc_id_desc * desc) { return id_make_dims(*model, *desc).total * 8; }
 
 } // extern "C"

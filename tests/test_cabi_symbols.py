@@ -35,7 +35,7 @@ def test_oracle_mirrors_the_solver_level_entry_points():
 def test_oracle_mirrors_the_inverse_dynamics_entry_points():
     orc = load_oracle()
     for n in ["create", "destroy", "default_settings", "set_target", "set_target_centroidal", "solve", "get_accelerations",
-              "get_forces", "get_info", "last_error"]:
+              "get_forces", "get_info", "set_warm_start", "last_error"]:
         assert hasattr(orc, "orc_id_" + n), n
     import smpc_id
     a, b = smpc_id.IdSettings(), smpc_id.IdSettings()

@@ -6,8 +6,10 @@ with point feet and the biped with quad feet, joint / velocity / effort limits c
 the CPU emulation of the CUDA routine (tests/host_emul) against the oracle.
 GPU part (`-m gpu`): the CUDA path through the C ABI (include/smpc_id.h) against the oracle on identical measurements along
 closed-loop trajectories of a batch, plus the reference's behavioural checks on the CUDA path itself.
-Tolerances: both sides solve the same strictly convex QP to a relative KKT residual of 1e-9 with the same algorithm; torques and
-accelerations agree to 1e-8 (normwise, with an absolute floor of 1e-8 of the torque / acceleration scale)."""
+Tolerances: both sides solve the same strictly convex QP to a relative KKT residual of 1e-10 with the same algorithm from the
+same starting point (cold, or the previous solution of the same closed loop); torques and
+contact forces agree to 1e-8 (normwise, with an absolute floor at the scale 1), accelerations to 1e-7: a solve that stops one
+Newton step earlier on one side (residual just under / over the threshold) moves them by that much."""
 import ctypes as C
 import numpy as np
 import pytest
@@ -18,7 +20,8 @@ from smpc_ctypes import _p
 from oracle_libs import load_emul, load_oracle
 
 DT = 1e-3
-TOL = 1e-8
+TOL = 1e-8    # torques (the control output) and contact forces
+TOL_A = 1e-7  # accelerations: a by-product, more sensitive along weakly regularised directions of the QP (see the docstring)
 
 
 def robot(name):
@@ -251,19 +254,21 @@ def test_emulated_cta_routine_matches_oracle(name, kw):
     na = m.nv - 6
     worst = {"tau": 0.0, "a": 0.0}
 
+    ws = np.full(em.emul_id_ws_doubles(C.byref(m), C.byref(d)), np.nan)  # the instance's warm-start record, as in HBM
+
     def on_step(i, q, v, qn, vn, tau, a):
-        if i % 5:
-            return
         te, ae, fe, info = np.zeros(na), np.zeros(m.nv), np.zeros((m.nfeet, 12)), sid.IdInfo()
         rc = em.emul_id_solve(C.byref(m), C.byref(d), None, None, None, None, None, None, None, None, None, 1, _p(q[0].copy()),
-                              _p(v[0].copy()), _p(te), _p(ae), _p(fe), C.byref(info))
+                              _p(v[0].copy()), _p(te), _p(ae), _p(fe), C.byref(info), _p(ws))
         assert rc == 0 and info.status == 0
         worst["tau"] = max(worst["tau"], relerr(te, tau[0], max(np.abs(tau[0]).max(), 1.0)))
         worst["a"] = max(worst["a"], relerr(ae, a[0], max(np.abs(a[0]).max(), 1.0)))
 
     q0 = crouched_start(m) if name == "go2" else np.array(m.q_ref[: m.nq])
-    closed_loop(ib, m, lim, vmax, eff, q0, 40 if name == "go2" else 15, on_step=on_step)
-    assert worst["tau"] <= TOL and worst["a"] <= TOL, worst
+    ib.set_warm_start(False)  # the constructor's dry run is not emulated: both sides start their first solve cold
+    ib.set_warm_start(True)
+    closed_loop(ib, m, lim, vmax, eff, q0, 30 if name == "go2" else 10, on_step=on_step)
+    assert worst["tau"] <= TOL and worst["a"] <= TOL_A, worst
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -303,7 +308,7 @@ def test_cuda_matches_oracle_along_closed_loop(name, kw):
             worst["w"] = max(worst["w"], relerr(fg, fo))
         q, v = step_state(q, v, ag)
         check_limits(m, lim, vmax, eff, q, v, tg)
-    assert worst["tau"] <= TOL and worst["a"] <= TOL and worst["w"] <= 1e-7, worst
+    assert worst["tau"] <= TOL and worst["a"] <= TOL_A and worst["w"] <= 1e-7, worst
     assert ig.lib.smpc_id_launch_count(ig.ctx) == steps + 1  # one kernel launch per solve (+ the constructor's dry run)
 
 
@@ -415,3 +420,24 @@ def test_host_classes_match_the_c_abi_and_run_the_reference_scenarios():
         e = np.linalg.norm(np.array(dh.getFootPose(0).translation) - target)
         e0 = e if e0 is None else e0
     assert e < 0.97 * e0
+
+
+def test_warm_start_changes_the_iteration_count_not_the_solution():
+    """smpc_id_set_warm_start: a solve that starts from the previous primal / dual solution needs 1-2 Newton steps instead of
+    6-8 along a closed loop and returns the torques of the cold-started solve (strictly convex QP)"""
+    orc = load_oracle()
+    kw = SCENARIOS[0][1]
+    warm, m, lim, vmax, eff = make(orc, "orc_id_", "go2", 1, **kw)
+    cold, *_ = make(orc, "orc_id_", "go2", 1, **kw)
+    cold.set_warm_start(False)
+    q, v = crouched_start(m)[None], np.zeros((1, m.nv))
+    nw = nc = 0
+    for i in range(60):
+        tw, tc = warm.solve(i * DT, q, v), cold.solve(i * DT, q, v)
+        # two different iteration paths to the same minimiser, each stopped at a relative KKT residual of 1e-10: the torques
+        # (the control) agree to 1e-8, the accelerations - more sensitive along weakly regularised directions - to 1e-6
+        assert relerr(tw, tc, max(np.abs(tc).max(), 1.0)) <= TOL
+        assert relerr(warm.accelerations(), cold.accelerations(), max(np.abs(cold.accelerations()).max(), 1.0)) <= 1e-6
+        nw, nc = nw + warm.info()[0].newton_iters, nc + cold.info()[0].newton_iters
+        q, v = step_state(q, v, cold.accelerations())
+    assert nw < 0.5 * nc, (nw, nc)

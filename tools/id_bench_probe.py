@@ -16,6 +16,7 @@ for name, B in (("go2", 148), ("go2", 4096), ("talos", 148), ("talos", 2048)):
         kw = dict(kp_base=1.0, kp_posture=1.0, kp_contact=10.0, w_base=1.0, w_posture=0.05, w_contact_motion=10.0, w_contact_force=1.0)
     d = sid.make_desc(m, lim["qmin"], lim["qmax"], vmax, eff, sid.default_settings(**kw))
     ib = sid.IdBatch(cuda, "smpc_id_", m, d, B)
+    ib.set_warm_start(False)
     rng = np.random.default_rng(0)
     q = np.repeat(np.array(m.q_ref[: m.nq])[None], B, 0); q[:, 7:] += 0.03 * rng.standard_normal((B, m.nv - 6))
     v = np.zeros((B, m.nv))

@@ -9,6 +9,7 @@ m, lim = sc.go2_like_model()
 kw = dict(kp_base=10.0, kp_posture=1.0, kp_contact=10.0, w_base=10.0, w_posture=0.1, w_contact_motion=1.0, w_contact_force=1.0)
 d = sid.make_desc(m, lim["qmin"], lim["qmax"], 30.0, 23.7, sid.default_settings(**kw))
 ib = sid.IdBatch(sc.load_cuda(), "smpc_id_", m, d, B)
+ib.set_warm_start(False)  # the profiled launch runs the whole algorithm (6-7 Newton steps), not a one-step warm solve
 rng = np.random.default_rng(0)
 q = np.repeat(np.array(m.q_ref[: m.nq])[None], B, 0); q[:, 7:] += 0.03 * rng.standard_normal((B, m.nv - 6))
 for i in range(3):
