@@ -605,159 +605,289 @@ namespace smpc
       SMPC_END
       id_add_motion_task(L, sm, S.w_com, 0, 3);
     }
-    // swing-foot tracking tasks (LOCAL frame)
-    if (S.centroidal && S.w_feet_tracking > 0.)
+    // ---- feet: swing-foot tracking tasks (LOCAL frame) and contacts, all feet at once -----------------------------------
+    // scratch (aliases the reduction partials / pair table, unused until the solve): per foot a frame record
+    // [R 9, p 3, v_local 6, drift_local 6], a 6 x nv Jacobian and the right-hand side of its motion rows
+    double * frs = sm + L.o_part;
+    double * Jts = frs + 24 * nfeet;
+    double * bts = Jts + 6 * nv * nfeet;
+    const bool track = S.centroidal && S.w_feet_tracking > 0.;
+    int eoff[SMPC_MAX_FEET], ioff[SMPC_MAX_FEET]; // first equality / inequality row of each active contact
+    {
+      int ie_ = 6, ii_ = 0;
       for (int f = 0; f < nfeet; f++)
       {
-        if (!T.tracked[f])
+        eoff[f] = ie_, ioff[f] = ii_;
+        if (!T.active[f])
           continue;
-        id_frame(Mo, L, sm, d.foot_joint[f], d.foot_R[f], d.foot_p[f]);
-        SMPC_PAR(tid)
-        if (tid == 0)
+        const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
+        ie_ += S.contact_motion_equality ? (quad ? 6 : 3) : 0;
+        ii_ += quad ? 17 : 5;
+      }
+    }
+    const int ii = ncone;
+    // phase A: frame placement, local velocity and classical drift of every foot in use (one thread per foot)
+    SMPC_PAR(tid)
+    for (int f = tid; f < nfeet; f += SMPC_NT)
+    {
+      if (!T.active[f] && !(track && T.tracked[f]))
+        continue;
+      const int jf = d.foot_joint[f];
+      const double * oMi = sm + L.o_oMi + 12 * jf;
+      double * frf = frs + 24 * f;
+      double R[9], t[3], p[3];
+      m3m(oMi, d.foot_R[f], R);
+      m3v(oMi, d.foot_p[f], t);
+      for (int e = 0; e < 3; e++)
+        p[e] = oMi[9 + e] + t[e];
+      for (int e = 0; e < 9; e++)
+        frf[e] = R[e];
+      for (int e = 0; e < 3; e++)
+        frf[9 + e] = p[e];
+      const double * vj = sm + L.o_ov + 6 * jf;
+      const double * aj = sm + L.o_oa + 6 * jf;
+      double pd[3], pdd[3], t1[3], t2[3];
+      v3cross(vj + 3, p, t);
+      for (int e = 0; e < 3; e++)
+        pd[e] = vj[e] + t[e];
+      v3cross(aj + 3, p, t1);
+      v3cross(vj + 3, pd, t2);
+      for (int e = 0; e < 3; e++)
+        pdd[e] = aj[e] + t1[e] + t2[e];
+      m3tv(R, pd, frf + 12);
+      m3tv(R, vj + 3, frf + 15);
+      m3tv(R, pdd, frf + 18);
+      m3tv(R, aj + 3, frf + 21);
+    }
+    SMPC_END
+    // phase B: Jacobians (LOCAL; the linear rows of an active point contact in world axes) and motion right-hand sides
+    SMPC_PAR(tid)
+    const double * Jw = sm + L.o_Jw;
+    for (int idx = tid; idx < nfeet * nv + nfeet; idx += SMPC_NT)
+    {
+      if (idx < nfeet * nv)
+      {
+        const int f = idx / nv, c = idx % nv;
+        if (!T.active[f] && !(track && T.tracked[f]))
+          continue;
+        const double * frf = frs + 24 * f;
+        double a3[3] = {0, 0, 0}, b3[3] = {0, 0, 0};
+        if ((Mo.anc_mask[d.foot_joint[f]] >> Mo.joint_of_dof[c]) & 1u)
+        {
+          const double lin0[3] = {Jw[c], Jw[nv + c], Jw[2 * nv + c]};
+          const double ang[3] = {Jw[3 * nv + c], Jw[4 * nv + c], Jw[5 * nv + c]};
+          double t[3], lin[3];
+          v3cross(ang, frf + 9, t);
+          for (int e = 0; e < 3; e++)
+            lin[e] = lin0[e] + t[e];
+          m3tv(frf, lin, a3);
+          m3tv(frf, ang, b3);
+          if (T.active[f] && D.foot_type[f] != SMPC_ID_QUAD)
+          { // ContactPoint with useLocalFrame(false): rotate the local linear rows back to world axes, as the oracle does
+            double w3[3];
+            m3v(frf, a3, w3);
+            a3[0] = w3[0], a3[1] = w3[1], a3[2] = w3[2];
+          }
+        }
+        double * Jf = Jts + 6 * nv * f;
+        for (int e = 0; e < 3; e++)
+        {
+          Jf[e * nv + c] = a3[e];
+          Jf[(3 + e) * nv + c] = b3[e];
+        }
+      }
+      else
+      {
+        const int f = idx - nfeet * nv;
+        const double * frf = frs + 24 * f;
+        double * bf = bts + 6 * f;
+        if (T.active[f])
+        {
+          const double kd = 2.0 * sqrt(S.kp_contact);
+          if (D.foot_type[f] == SMPC_ID_QUAD)
+            for (int r = 0; r < 6; r++)
+              bf[r] = -kd * frf[12 + r] - frf[18 + r];
+          else
+          {
+            double vw[3], dw[3];
+            m3v(frf, frf + 12, vw);
+            m3v(frf, frf + 18, dw);
+            for (int r = 0; r < 3; r++)
+              bf[r] = -kd * vw[r] - dw[r];
+          }
+        }
+        else if (track && T.tracked[f])
         {
           const double kp = S.kp_feet_tracking, kd = 2.0 * sqrt(kp);
           double Rr[9], dp[3], pr[3], e6[6], vr[6];
-          m3tm(fr, T.foot_R[f], Rr);
+          m3tm(frf, T.foot_R[f], Rr);
           for (int e = 0; e < 3; e++)
-            dp[e] = T.foot_p[f][e] - fr[9 + e];
-          m3tv(fr, dp, pr);
+            dp[e] = T.foot_p[f][e] - frf[9 + e];
+          m3tv(frf, dp, pr);
           log6(Rr, pr, e6);
-          m3tv(fr, T.foot_vel[f], vr);
-          m3tv(fr, T.foot_vel[f] + 3, vr + 3);
+          m3tv(frf, T.foot_vel[f], vr);
+          m3tv(frf, T.foot_vel[f] + 3, vr + 3);
           for (int r = 0; r < 6; r++)
-            bt[r] = kp * e6[r] + kd * (vr[r] - fr[12 + r]) - fr[18 + r];
+            bf[r] = kp * e6[r] + kd * (vr[r] - frf[12 + r]) - frf[18 + r];
         }
-        SMPC_END
-        id_add_motion_task(L, sm, S.w_feet_tracking, 0, D.foot_type[f] == SMPC_ID_QUAD ? 6 : 3);
       }
-    // contacts
-    int ie = 6, ii = 0;
-    for (int f = 0; f < nfeet; f++)
+    }
+    SMPC_END
+    // phase C: everything the feet contribute — motion tasks into the acceleration block of (H, g) (tracking feet first, then
+    // contacts, each in foot order: the oracle's order of accumulation), columns of Jc^T T, equality rows, force regularisation
+    // blocks, cone rows
+    SMPC_PAR(tid)
+    const double wmot = (!S.contact_motion_equality && S.w_contact_motion > 0.) ? S.w_contact_motion : 0.0;
+    for (int idx = tid; idx < nv * nv + nv; idx += SMPC_NT)
     {
+      const bool isH = idx < nv * nv;
+      const int i = isH ? idx / nv : idx - nv * nv, j = isH ? idx % nv : 0;
+      double acc = isH ? H[i * ld + j] : g[i];
+      for (int pass = 0; pass < 2; pass++)
+        for (int f = 0; f < nfeet; f++)
+        {
+          const bool use = pass == 0 ? (track && T.tracked[f] && !T.active[f]) : (T.active[f] != 0);
+          const double w = pass == 0 ? S.w_feet_tracking : wmot;
+          if (!use || w == 0.0)
+            continue;
+          const int rows = (D.foot_type[f] == SMPC_ID_QUAD) ? 6 : 3;
+          const double * Jf = Jts + 6 * nv * f;
+          if (isH)
+            for (int r = 0; r < rows; r++)
+              acc += (w * Jf[r * nv + i]) * Jf[r * nv + j];
+          else
+            for (int r = 0; r < rows; r++)
+              acc -= (w * Jf[r * nv + i]) * bts[6 * f + r];
+        }
+      if (isH)
+        H[i * ld + j] = acc;
+      else
+        g[i] = acc;
+    }
+    // generalised force of each force variable: Jm^T T(:, j)
+    for (int idx = tid; idx < nv * nf; idx += SMPC_NT)
+    {
+      const int c = idx / nf, jg = idx % nf;
+      int f = 0;
+      while (f + 1 < nfeet && (fdim[f] == 0 || jg >= foff[f] - nv + fdim[f]))
+        f++;
+      const int j = jg - (foff[f] - nv);
+      const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
+      const int rows = quad ? 6 : 3;
+      double Tc[6] = {0, 0, 0, 0, 0, 0};
+      if (quad)
+      {
+        const int pt = j / 3, ax = j % 3;
+        double e3[3] = {0, 0, 0}, mo[3];
+        e3[ax] = 1;
+        v3cross(D.quad_points[f][pt], e3, mo);
+        Tc[ax] = 1;
+        Tc[3] = mo[0], Tc[4] = mo[1], Tc[5] = mo[2];
+      }
+      else
+        Tc[j] = 1;
+      const double * Jf = Jts + 6 * nv * f;
+      double s_ = 0;
+      for (int r = 0; r < rows; r++)
+        s_ += Jf[r * nv + c] * Tc[r];
+      JcT[c * ldf + jg] = s_;
+    }
+    if (S.contact_motion_equality)
+      for (int idx = tid; idx < nfeet * 6 * (nv + 1); idx += SMPC_NT)
+      {
+        const int f = idx / (6 * (nv + 1)), rem = idx % (6 * (nv + 1)), r = rem / (nv + 1), c = rem % (nv + 1);
+        if (!T.active[f] || r >= ((D.foot_type[f] == SMPC_ID_QUAD) ? 6 : 3))
+          continue;
+        if (c < nv)
+          A[(eoff[f] + r) * ld + c] = Jts[6 * nv * f + r * nv + c];
+        else
+          bq[eoff[f] + r] = bts[6 * f + r];
+      }
+    // force regularisation |W T f - W f_ref|^2: one thread per entry of each contact's block of H (+ one per entry of g)
+    if (S.w_contact_force > 0.)
+      for (int idx = tid; idx < nfeet * SMPC_ID_MAX_FVAR * (SMPC_ID_MAX_FVAR + 1); idx += SMPC_NT)
+      {
+        const int f = idx / (SMPC_ID_MAX_FVAR * (SMPC_ID_MAX_FVAR + 1)), rem = idx % (SMPC_ID_MAX_FVAR * (SMPC_ID_MAX_FVAR + 1));
+        const int i = rem / (SMPC_ID_MAX_FVAR + 1), j = rem % (SMPC_ID_MAX_FVAR + 1);
+        const int nfv = fdim[f];
+        if (!T.active[f] || i >= nfv || (j >= nfv && j != SMPC_ID_MAX_FVAR))
+          continue;
+        const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
+        const int rows = quad ? 6 : 3, c0 = foff[f];
+        const double wreg[6] = {1, 1, 1e-3, 2, 2, 2};
+        double acc = (j == SMPC_ID_MAX_FVAR) ? g[c0 + i] : H[(c0 + i) * ld + c0 + j];
+        for (int r = 0; r < rows; r++)
+        {
+          double ti = 0, tj = 0;
+          if (quad)
+          {
+            for (int side = 0; side < 2; side++)
+            {
+              const int k = side == 0 ? i : j;
+              if (k >= nfv)
+                continue;
+              const int pt = k / 3, ax = k % 3;
+              double t = 0;
+              if (r < 3)
+                t = (r == ax) ? 1.0 : 0.0;
+              else
+              {
+                double e3[3] = {0, 0, 0}, mo[3];
+                e3[ax] = 1;
+                v3cross(D.quad_points[f][pt], e3, mo);
+                t = mo[r - 3];
+              }
+              (side == 0 ? ti : tj) = t;
+            }
+          }
+          else
+          {
+            ti = (r == i) ? 1.0 : 0.0;
+            tj = (r == j) ? 1.0 : 0.0;
+          }
+          const double ri = wreg[r] * ti;
+          if (ri == 0.0)
+            continue;
+          if (j == SMPC_ID_MAX_FVAR)
+            acc -= S.w_contact_force * ri * (wreg[r] * T.f_ref[f][r]);
+          else
+            acc += S.w_contact_force * ri * (wreg[r] * tj);
+        }
+        if (j == SMPC_ID_MAX_FVAR)
+          g[c0 + i] = acc;
+        else
+          H[(c0 + i) * ld + c0 + j] = acc;
+      }
+    // force inequalities: friction pyramid per contact point, bounds on the (total) normal force: one thread per row
+    for (int idx = tid; idx < nfeet * 17; idx += SMPC_NT)
+    {
+      const int f = idx / 17, r = idx % 17;
       if (!T.active[f])
         continue;
       const bool quad = D.foot_type[f] == SMPC_ID_QUAD;
-      const int c0 = foff[f], nfv = fdim[f], rows = quad ? 6 : 3;
-      id_frame(Mo, L, sm, d.foot_joint[f], d.foot_R[f], d.foot_p[f]);
-      // motion rows: LOCAL for quad feet, world-oriented linear rows for point feet (rotate Jt, v, drift by R)
-      SMPC_PAR(tid)
-      const double kd = 2.0 * sqrt(S.kp_contact);
-      if (!quad)
-        for (int c = tid; c < nv; c += SMPC_NT)
-        {
-          const double jl[3] = {Jt[c], Jt[nv + c], Jt[2 * nv + c]};
-          double jw[3];
-          m3v(fr, jl, jw);
-          Jt[c] = jw[0], Jt[nv + c] = jw[1], Jt[2 * nv + c] = jw[2];
-        }
-      if (tid == 0)
+      const int npts = quad ? 4 : 1, c0 = foff[f];
+      if (r > 4 * npts)
+        continue;
+      const int row = ioff[f] + r;
+      if (r < 4 * npts)
       {
-        if (quad)
-          for (int r = 0; r < 6; r++)
-            bt[r] = -kd * fr[12 + r] - fr[18 + r];
-        else
-        {
-          double vw[3], dw[3];
-          m3v(fr, fr + 12, vw);
-          m3v(fr, fr + 18, dw);
-          for (int r = 0; r < 3; r++)
-            bt[r] = -kd * vw[r] - dw[r];
-        }
+        const double mu_ = S.friction_coefficient;
+        const double pyr[4][3] = {{-1, 0, -mu_}, {1, 0, -mu_}, {0, -1, -mu_}, {0, 1, -mu_}};
+        const int pt = r / 4;
+        for (int ax = 0; ax < 3; ax++)
+          Cm[row * ld + c0 + 3 * pt + ax] = pyr[r % 4][ax];
+        lo[row] = -ID_BIG;
+        up[row] = 0.0;
       }
-      SMPC_END
-      SMPC_PAR(tid)
-      // generalised force of each force variable: Jm^T T(:, j)
-      for (int idx = tid; idx < nv * nfv; idx += SMPC_NT)
+      else
       {
-        const int c = idx / nfv, j = idx % nfv;
-        double Tc[6] = {0, 0, 0, 0, 0, 0};
-        if (quad)
-        {
-          const int pt = j / 3, ax = j % 3;
-          double e3[3] = {0, 0, 0}, mo[3];
-          e3[ax] = 1;
-          v3cross(D.quad_points[f][pt], e3, mo);
-          Tc[ax] = 1;
-          Tc[3] = mo[0], Tc[4] = mo[1], Tc[5] = mo[2];
-        }
-        else
-          Tc[j] = 1;
-        double s = 0;
-        for (int r = 0; r < rows; r++)
-          s += Jt[r * nv + c] * Tc[r];
-        JcT[c * ldf + (c0 - nv) + j] = s;
-      }
-      if (S.contact_motion_equality)
-        for (int idx = tid; idx < rows * nv + rows; idx += SMPC_NT)
-        {
-          if (idx < rows * nv)
-            A[(ie + idx / nv) * ld + idx % nv] = Jt[idx];
-          else
-            bq[ie + idx - rows * nv] = bt[idx - rows * nv];
-        }
-      // force regularisation |W T f - W f_ref|^2 and the cone rows (thread 0: a few dozen entries)
-      if (tid == 0)
-      {
-        if (S.w_contact_force > 0.)
-        {
-          const double wreg[6] = {1, 1, 1e-3, 2, 2, 2};
-          for (int r = 0; r < rows; r++)
-          {
-            double row[SMPC_ID_MAX_FVAR];
-            for (int j = 0; j < nfv; j++)
-            {
-              double t = 0;
-              if (quad)
-              {
-                const int pt = j / 3, ax = j % 3;
-                if (r < 3)
-                  t = (r == ax) ? 1.0 : 0.0;
-                else
-                {
-                  double e3[3] = {0, 0, 0}, mo[3];
-                  e3[ax] = 1;
-                  v3cross(D.quad_points[f][pt], e3, mo);
-                  t = mo[r - 3];
-                }
-              }
-              else
-                t = (r == j) ? 1.0 : 0.0;
-              row[j] = wreg[r] * t;
-            }
-            const double br = wreg[r] * T.f_ref[f][r];
-            for (int i = 0; i < nfv; i++)
-            {
-              if (row[i] == 0.0)
-                continue;
-              for (int j = 0; j < nfv; j++)
-                H[(c0 + i) * ld + c0 + j] += S.w_contact_force * row[i] * row[j];
-              g[c0 + i] -= S.w_contact_force * row[i] * br;
-            }
-          }
-        }
-        const double mu = S.friction_coefficient;
-        const double pyr[4][3] = {{-1, 0, -mu}, {1, 0, -mu}, {0, -1, -mu}, {0, 1, -mu}};
-        const int npts = quad ? 4 : 1;
-        int row = ii;
-        for (int pt = 0; pt < npts; pt++)
-          for (int r = 0; r < 4; r++, row++)
-          {
-            for (int ax = 0; ax < 3; ax++)
-              Cm[row * ld + c0 + 3 * pt + ax] = pyr[r][ax];
-            lo[row] = -ID_BIG;
-            up[row] = 0.0;
-          }
         for (int pt = 0; pt < npts; pt++)
           Cm[row * ld + c0 + 3 * pt + 2] = 1.0;
         lo[row] = fminn;
         up[row] = fmaxn;
       }
-      SMPC_END
-      if (!S.contact_motion_equality && S.w_contact_motion > 0.)
-        id_add_motion_task(L, sm, S.w_contact_motion, 0, rows);
-      ie += S.contact_motion_equality ? rows : 0;
-      ii += quad ? 17 : 5;
     }
+    SMPC_END
     // floating-base rows, joint acceleration bounds, actuation bounds
     SMPC_PAR(tid)
     for (int idx = tid; idx < 6 * n + 6; idx += SMPC_NT)
