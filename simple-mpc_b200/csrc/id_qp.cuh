@@ -291,7 +291,22 @@ namespace smpc
           ov[6 * i + e] = vi[e];
           oa[6 * i + e] = ai[e];
         }
-        // world-frame body inertia [[m I, -m[c]x], [m[c]x, Ic - m[c]x[c]x]], bias force I a + v x* (I v)
+      }
+      SMPC_END
+    }
+    // world-frame body inertia [[m I, -m[c]x], [m[c]x, Ic - m[c]x[c]x]] and bias force I a + v x* (I v): every joint at once
+    {
+      SMPC_PAR(tid)
+      for (int i = tid; i < nj; i += SMPC_NT)
+      {
+        const double * Ri = oMi + 12 * i;
+        const double * pi = Ri + 9;
+        double vi[6], ai[6];
+        for (int e = 0; e < 6; e++)
+        {
+          vi[e] = ov[6 * i + e];
+          ai[e] = oa[6 * i + e];
+        }
         double cw[3], Icw[9], T[9], Cx[9], CC[9];
         m3v(Ri, d.lever[i], cw);
         for (int e = 0; e < 3; e++)
