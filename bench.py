@@ -274,6 +274,10 @@ def run_id_bench(args, rank, world, local_rank, W, K):
                           "config": config, "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+    # stdout carries exactly one JSON line (see main(): NCCL's version banner is kept off it)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     torch.cuda.set_device(local_rank)
     dist = None
