@@ -108,9 +108,31 @@ namespace smpc
     const double * f_target)
   {
     const int na = d.nv - 6;
-    std::vector<double> oMi;
-    idh::fk(d, q, oMi);
-    idh::frame_pose(oMi, d.base_joint, d.base_R, d.base_p, T.base_R, T.base_p);
+    if (d.base_joint == 0)
+    { // the usual case (base frame on the free-flyer): no tree walk, no allocation - this runs per instance at 1 kHz
+      const double * qq = q + d.idx_q[0];
+      double x = qq[3], y = qq[4], z = qq[5], w = qq[6];
+      const double n = 1.0 / std::sqrt(x * x + y * y + z * z + w * w);
+      x *= n, y *= n, z *= n, w *= n;
+      const double Rj[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                            2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                            2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+      double R0[9], p0[3], t[3];
+      idh::mul3(d.place_R[0], Rj, R0);
+      idh::mv3(d.place_R[0], qq, t);
+      for (int e = 0; e < 3; e++)
+        p0[e] = d.place_p[0][e] + t[e];
+      idh::mul3(R0, d.base_R, T.base_R);
+      idh::mv3(R0, d.base_p, t);
+      for (int e = 0; e < 3; e++)
+        T.base_p[e] = p0[e] + t[e];
+    }
+    else
+    {
+      std::vector<double> oMi;
+      idh::fk(d, q, oMi);
+      idh::frame_pose(oMi, d.base_joint, d.base_R, d.base_p, T.base_R, T.base_p);
+    }
     for (int j = 0; j < na; j++)
     {
       T.q_post[j] = q[7 + j];

@@ -471,3 +471,33 @@ def test_emulated_cta_routine_matches_oracle_with_a_swing_foot():
 
     closed_loop(ib, m, lim, vmax, eff, np.array(m.q_ref[: m.nq]), 25, on_step=on_step)
     assert worst["tau"] <= TOL and worst["a"] <= TOL_A, worst
+
+
+@pytest.mark.gpu
+def test_control_stack_mpc_tick_plus_ten_id_periods():
+    """the loop of the reference's examples/go2_kinodynamics.py:196-305 on the CUDA path, batched (smpc_stack.run): MPC tick at
+    100 Hz, plan interpolation + KinodynamicsID at 1 kHz, ideal plant. Half a second of walking: every QP solved, robots upright,
+    torques within the limits, and the first control periods equal to the same loop on the oracle"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import smpc_stack
+    cuda, orc = sc.load_cuda(), load_oracle()
+    B = 4
+    _, lim = sc.go2_like_model()
+    out = {}
+    for name, lib, pre, idpre, ticks in (("cuda", cuda, "smpc", "smpc_id_", 50), ("orc", orc, "orc", "orc_id_", 3)):
+        scen = bench.make_scenario("c5", B, seed=1000)
+        b = bench.setup_backend(lib, pre, scen, B, 0)
+        hist = []
+
+        def on_tick(tick, q, v, tau, kid):
+            assert all(x.status == 0 for x in kid.info())
+            assert np.isfinite(q).all() and (q[:, 2] > 0.25).all() and (np.abs(tau) <= 23.7 + 1e-6).all()
+            hist.append((q.copy(), tau.copy()))
+
+        smpc_stack.run(lib, pre, lib, idpre, b, scen, lim, ticks, on_tick=on_tick)
+        out[name] = hist
+    for (qc, tc), (qo, to) in zip(out["cuda"][:3], out["orc"]):
+        assert relerr(qc, qo) <= 1e-7 and relerr(tc, to, max(np.abs(to).max(), 1.0)) <= 1e-6
