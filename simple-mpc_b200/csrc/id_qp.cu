@@ -13,7 +13,7 @@ using namespace smpc;
 
 namespace
 {
-  __global__ void __launch_bounds__(ID_THREADS, 4) k_id_solve(
+  __global__ void __launch_bounds__(ID_THREADS, 5) k_id_solve(
     const DevModel * __restrict__ M, const smpc_id_desc * __restrict__ D, const IdTargetDev * __restrict__ T, const IdDims L,
     const double * __restrict__ q, const double * __restrict__ v, double * __restrict__ tau, double * __restrict__ a,
     double * __restrict__ f, smpc_id_info * __restrict__ info, double * __restrict__ ws, int batch)

@@ -97,8 +97,15 @@ namespace smpc
     L.o_z = take(L.mi), L.o_si = take(L.mi), L.o_si2 = take(L.mi);
     L.o_sc = take(16);
     L.o_act = take((L.mi + 2) / 2 + 1); // int list of the active inequality rows
-    L.o_part = take(4 * ID_THREADS);    // per-thread partials of the CTA-wide reductions
+    L.o_part = take(2 * ID_THREADS);    // per-thread partials of the CTA-wide reductions (two quantities at a time)
     L.o_pairs = take((L.nx * (L.nx + 1) / 2 + L.nx + 1) / 2); // int table of the (i, j) pairs of the factorisation
+    // the per-foot assembly scratch (frame records, Jacobians, right-hand sides) aliases everything from o_x up to here: the
+    // solver's vectors, the reduction partials and the pair table are first written when the solve starts
+    {
+      const int need = L.nfeet * (24 + 6 * L.nv + 6);
+      if (o - L.o_x < need)
+        take(need - (o - L.o_x));
+    }
     L.o_K = o;
     L.o_oMi = take(12 * L.nj), L.o_Jw = take(6 * L.nv), L.o_ov = take(6 * L.nj), L.o_oa = take(6 * L.nj);
     L.o_Y = take(36 * L.nj), L.o_fs = take(6 * L.nj), L.o_Fc = take(6 * L.nv);
@@ -621,9 +628,9 @@ namespace smpc
       id_add_motion_task(L, sm, S.w_com, 0, 3);
     }
     // ---- feet: swing-foot tracking tasks (LOCAL frame) and contacts, all feet at once -----------------------------------
-    // scratch (aliases the reduction partials / pair table, unused until the solve): per foot a frame record
+    // scratch (aliases the solver's vectors / reduction partials / pair table, unused until the solve): per foot a frame record
     // [R 9, p 3, v_local 6, drift_local 6], a 6 x nv Jacobian and the right-hand side of its motion rows
-    double * frs = sm + L.o_part;
+    double * frs = sm + L.o_x;
     double * Jts = frs + 24 * nfeet;
     double * bts = Jts + 6 * nv * nfeet;
     const bool track = S.centroidal && S.w_feet_tracking > 0.;
@@ -1322,47 +1329,49 @@ namespace smpc
       SMPC_PAR(tid)
       const double * A = sm + L.o_A;
       const double * Cm = sm + L.o_C;
-      const double * g = sm + L.o_g;
-      const double * hx = sm + L.o_hx;
-      double pr = 0, ps = 1.0, dr = 0, ds = 1.0;
-      for (int idx = tid; idx < n + me + mi; idx += SMPC_NT)
+      double pr = 0, ps = 1.0;
+      for (int idx = tid; idx < me + mi; idx += SMPC_NT)
       {
-        if (idx < n)
+        const double * row = (idx < me) ? A + idx * ld : Cm + (idx - me) * ld;
+        double s = 0;
+        for (int j = 0; j < n; j++)
+          s += row[j] * x[j];
+        if (idx < me)
         {
-          const int i = idx;
-          double ay = 0, cz = 0;
-          for (int r = 0; r < me; r++)
-            ay += A[r * ld + i] * y[r];
-          for (int r = 0; r < mi; r++)
-            cz += Cm[r * ld + i] * z[r];
-          dr = fmax(dr, fabs(g[i] + hx[i] + ay + cz));
-          ds = fmax(ds, fmax(fmax(fabs(hx[i]), fabs(g[i])), fmax(fabs(ay), fabs(cz))));
-        }
-        else if (idx < n + me)
-        {
-          const int r = idx - n;
-          double s = 0;
-          for (int j = 0; j < n; j++)
-            s += A[r * ld + j] * x[j];
-          pr = fmax(pr, fabs(s - sm[L.o_b + r]));
-          ps = fmax(ps, fmax(fabs(s), fabs(sm[L.o_b + r])));
+          pr = fmax(pr, fabs(s - sm[L.o_b + idx]));
+          ps = fmax(ps, fmax(fabs(s), fabs(sm[L.o_b + idx])));
         }
         else
         {
-          const int r = idx - n - me;
-          double s = 0;
-          for (int j = 0; j < n; j++)
-            s += Cm[r * ld + j] * x[j];
+          const int r = idx - me;
           pr = fmax(pr, fmax(s - sm[L.o_u + r], sm[L.o_l + r] - s));
           ps = fmax(ps, fabs(s));
         }
       }
       part[tid] = pr;
       part[ID_THREADS + tid] = ps;
-      part[2 * ID_THREADS + tid] = dr;
-      part[3 * ID_THREADS + tid] = ds;
       SMPC_END
-      id_block_reduce<true>(L, sm, 4, SC_K0);
+      id_block_reduce<true>(L, sm, 2, SC_K0);
+      SMPC_PAR(tid)
+      const double * A = sm + L.o_A;
+      const double * Cm = sm + L.o_C;
+      const double * g = sm + L.o_g;
+      const double * hx = sm + L.o_hx;
+      double dr = 0, ds = 1.0;
+      for (int i = tid; i < n; i += SMPC_NT)
+      {
+        double ay = 0, cz = 0;
+        for (int r = 0; r < me; r++)
+          ay += A[r * ld + i] * y[r];
+        for (int r = 0; r < mi; r++)
+          cz += Cm[r * ld + i] * z[r];
+        dr = fmax(dr, fabs(g[i] + hx[i] + ay + cz));
+        ds = fmax(ds, fmax(fmax(fabs(hx[i]), fabs(g[i])), fmax(fabs(ay), fabs(cz))));
+      }
+      part[tid] = dr;
+      part[ID_THREADS + tid] = ds;
+      SMPC_END
+      id_block_reduce<true>(L, sm, 2, SC_K0 + 2);
       pres = sc[SC_K0] / sc[SC_K0 + 1];
       dres = sc[SC_K0 + 2] / sc[SC_K0 + 3];
       if (pres <= ID_QP_EPS && dres <= ID_QP_EPS)
