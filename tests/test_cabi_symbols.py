@@ -75,3 +75,22 @@ def test_no_device_means_loud_failure_not_cpu_fallback():
     rc = lib.smpc_create(C.byref(ctx), 0, 1, C.byref(sc.model), C.byref(sc.ocpb.desc), C.byref(o))
     assert rc == -3, rc  # SMPC_ERR_CUDA
     assert b"no CPU fallback" in lib.smpc_last_error() or b"cuda" in lib.smpc_last_error().lower()
+
+
+def test_inverse_dynamics_context_also_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        return
+    import smpc_id
+    from smpc_ctypes import go2_like_model
+    lib = load_cuda()
+    m, lim = go2_like_model()
+    d = smpc_id.make_desc(m, lim["qmin"], lim["qmax"], 30.0, 23.7, smpc_id.default_settings(w_posture=1.0))
+    ctx = C.c_void_p()
+    rc = lib.smpc_id_create(C.byref(ctx), C.byref(m), C.byref(d), C.c_int(1))
+    assert rc == -3 and not ctx.value, rc  # SMPC_ERR_CUDA, no context handed out
+    assert b"cuda" in lib.smpc_last_error().lower()
+    # bad arguments are rejected before any CUDA call
+    assert lib.smpc_id_create(C.byref(ctx), C.byref(m), C.byref(d), C.c_int(0)) == -1
+    d.control_dt = 0.0
+    assert lib.smpc_id_create(C.byref(ctx), C.byref(m), C.byref(d), C.c_int(1)) == -1
