@@ -34,6 +34,7 @@ namespace smpc
   constexpr int ID_QP_MAX_OUTER = 30;
   constexpr int ID_QP_MAX_INNER = 30;
   constexpr int ID_QP_MAX_NEWTON = 200;
+  constexpr int ID_RED_SLOTS = 10; // reduction slots (id_red_put / id_red_get)
   constexpr int ID_THREADS = 128; // CTA width the reductions are written for (the emulation runs with SMPC_EMUL_NT = 128)
 
   // per-instance target (what setTarget stores in the TSID tasks)
@@ -97,7 +98,11 @@ namespace smpc
     L.o_z = take(L.mi), L.o_si = take(L.mi), L.o_si2 = take(L.mi);
     L.o_sc = take(16);
     L.o_act = take((L.mi + 2) / 2 + 1); // int list of the active inequality rows
-    L.o_part = take(2 * ID_THREADS);    // per-thread partials of the CTA-wide reductions (two quantities at a time)
+#ifdef __CUDACC__
+    L.o_part = take(4 * ID_RED_SLOTS);  // one value per warp and reduction slot
+#else
+    L.o_part = take(ID_THREADS * ID_RED_SLOTS); // the emulation keeps one value per thread
+#endif
     L.o_pairs = take((L.nx * (L.nx + 1) / 2 + L.nx + 1) / 2); // int table of the (i, j) pairs of the factorisation
     // the per-foot assembly scratch (frame records, Jacobians, right-hand sides) aliases everything from o_x up to here: the
     // solver's vectors, the reduction partials and the pair table are first written when the solve starts
@@ -964,48 +969,55 @@ namespace smpc
   }
 
   // ---- phase group 3: the QP solve -----------------------------------------------------------------------------------
-  // CTA-wide reductions of up to four per-thread partials (part[k * ID_THREADS + tid]): warp k < nq reduces quantity k by
-  // shuffles and its lane 0 writes sc[slot0 + k]; MAXRED selects max instead of sum. The CPU emulation loops.
-  template <bool MAXRED>
-  SMPC_DEV void id_block_reduce(const IdDims & L, double * sm, int nq, int slot0)
+  // CTA-wide reductions with ONE barrier: at the end of the producing phase every thread hands its partial to id_red_put
+  // (device: shuffle reduction inside the warp, lane 0 stores the warp's value in part[4 k + warp]); after the phase's barrier
+  // every thread combines the four warp values with id_red_get. Consecutive reductions use different slots k, so a fast warp
+  // can never overwrite a slot another warp has not read yet. The CPU emulation keeps one value per thread and loops.
+  enum
   {
-    SMPC_PAR(tid)
-    const double * part = sm + L.o_part;
-    double * sc = sm + L.o_sc;
+    RK_VAL0 = 0, // subproblem value (two slots, alternating between consecutive evaluations)
+    RK_VAL1,
+    RK_GN,
+    RK_GS,
+    RK_SLOPE,
+    RK_CHANGED,
+    RK_PR,
+    RK_PS,
+    RK_DR,
+    RK_DS
+  };
+  template <bool MAXRED>
+  SMPC_DEV void id_red_put(double * part, int k, int tid, double v)
+  {
 #ifdef __CUDACC__
-    const int w = tid >> 5, lane = tid & 31;
-    if (w < nq)
-    {
-      const double * pk = part + w * ID_THREADS;
-      double s;
-      if (MAXRED)
-        s = fmax(fmax(pk[lane], pk[lane + 32]), fmax(pk[lane + 64], pk[lane + 96]));
-      else
-        s = (pk[lane] + pk[lane + 32]) + (pk[lane + 64] + pk[lane + 96]);
 #pragma unroll
-      for (int o = 16; o; o >>= 1)
-      {
-        const double t = __shfl_xor_sync(0xffffffffu, s, o);
-        s = MAXRED ? fmax(s, t) : s + t;
-      }
-      if (lane == 0)
-        sc[slot0 + w] = s;
+    for (int o = 16; o; o >>= 1)
+    {
+      const double t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = MAXRED ? fmax(v, t) : v + t;
     }
+    if ((tid & 31) == 0)
+      part[4 * k + (tid >> 5)] = v;
 #else
-    if (tid == 0)
-      for (int k = 0; k < nq; k++)
-      {
-        double s = MAXRED ? -1e300 : 0.0;
-        for (int t = 0; t < ID_THREADS; t++)
-          s = MAXRED ? fmax(s, part[k * ID_THREADS + t]) : s + part[k * ID_THREADS + t];
-        sc[slot0 + k] = s;
-      }
+    part[k * ID_THREADS + tid] = v;
 #endif
-    SMPC_END
+  }
+  template <bool MAXRED>
+  SMPC_DEV double id_red_get(const double * part, int k)
+  {
+#ifdef __CUDACC__
+    const double * p = part + 4 * k;
+    return MAXRED ? fmax(fmax(p[0], p[1]), fmax(p[2], p[3])) : (p[0] + p[1]) + (p[2] + p[3]);
+#else
+    double s = MAXRED ? -1e300 : 0.0;
+    for (int t = 0; t < ID_THREADS; t++)
+      s = MAXRED ? fmax(s, part[k * ID_THREADS + t]) : s + part[k * ID_THREADS + t];
+    return s;
+#endif
   }
 
-  // value of the subproblem at xv: fills hx = H xv, re_out, si_out and sm[sc + slot]
-  SMPC_DEV void id_al_value(const IdDims & L, double * sm, int n, int me, int mi, double mu, const double * xv, double * re_out, double * si_out, int slot)
+  // value of the subproblem at xv (returned to every thread); fills hx = H xv, re_out, si_out. rk: reduction slot
+  SMPC_DEV double id_al_value(const IdDims & L, double * sm, int n, int me, int mi, double mu, const double * xv, double * re_out, double * si_out, int rk)
   {
     const int ld = L.ldn;
     SMPC_PAR(tid)
@@ -1058,9 +1070,9 @@ namespace smpc
         acc += himu * vi * vi;
       }
     }
-    sm[L.o_part + tid] = acc;
+    id_red_put<false>(sm + L.o_part, rk, tid, acc);
     SMPC_END
-    id_block_reduce<false>(L, sm, 1, slot);
+    return id_red_get<false>(sm + L.o_part, rk);
   }
 
   // ws (optional, global memory): the instance's previous solution [signature, x (nx), y (me), z (mi)] with the dims' maxima
@@ -1123,7 +1135,7 @@ namespace smpc
       for (int i = tid; i < n; i += SMPC_NT)
         xk[i] = x[i];
       SMPC_END
-      id_al_value(L, sm, n, me, mi, mu, x, re, si, SC_VAL);
+      double val = id_al_value(L, sm, n, me, mi, mu, x, re, si, RK_VAL0);
       for (int it = 0; it < ID_QP_MAX_INNER && newton < ID_QP_MAX_NEWTON; it++)
       {
         // gradient (hx = H x is current), its inf-norm and the magnitude of its largest term; warp 3 compacts the list of
@@ -1154,8 +1166,8 @@ namespace smpc
           gn = fmax(gn, fabs(s));
           gs = fmax(gs, sa);
         }
-        part[tid] = gn;
-        part[ID_THREADS + tid] = gs;
+        id_red_put<true>(part, RK_GN, tid, gn);
+        id_red_put<true>(part, RK_GS, tid, gs);
 #ifdef __CUDACC__
         if ((tid >> 5) == 3)
         {
@@ -1184,8 +1196,7 @@ namespace smpc
         }
 #endif
         SMPC_END
-        id_block_reduce<true>(L, sm, 2, SC_GN);
-        if (sc[SC_GN] <= ID_QP_GRAD_REL * sc[SC_GS])
+        if (id_red_get<true>(part, RK_GN) <= ID_QP_GRAD_REL * id_red_get<true>(part, RK_GS))
           break;
         newton++;
         // Newton matrix (lower triangle) with the right-hand side -grad as an extra row n, on the pairs this thread owns
@@ -1277,19 +1288,18 @@ namespace smpc
         double s = 0;
         for (int i = tid; i < n; i += SMPC_NT)
           s += grad[i] * dx[i];
-        part[tid] = s;
+        id_red_put<false>(part, RK_SLOPE, tid, s);
         SMPC_END
-        id_block_reduce<false>(L, sm, 1, SC_SLOPE);
-        double alpha = 1.0;
-        const double val = sc[SC_VAL], slope = sc[SC_SLOPE];
+        double alpha = 1.0, vt = val;
+        const double slope = id_red_get<false>(part, RK_SLOPE);
         for (int ls = 0; ls < 30; ls++)
         {
           SMPC_PAR(tid)
           for (int i = tid; i < n; i += SMPC_NT)
             xt[i] = x[i] + alpha * dx[i];
           SMPC_END
-          id_al_value(L, sm, n, me, mi, mu, xt, re2, si2, SC_VT);
-          if (sc[SC_VT] <= val + 1e-4 * alpha * slope + 1e-13 * fabs(val))
+          vt = id_al_value(L, sm, n, me, mi, mu, xt, re2, si2, (ls & 1) ? RK_VAL0 : RK_VAL1);
+          if (vt <= val + 1e-4 * alpha * slope + 1e-13 * fabs(val))
             break;
           alpha *= 0.5;
         }
@@ -1306,12 +1316,10 @@ namespace smpc
           x[i] = xt[i];
         for (int r = tid; r < me; r += SMPC_NT)
           re[r] = re2[r];
-        part[tid] = changed;
-        if (tid == 0)
-          sc[SC_VAL] = sc[SC_VT];
+        id_red_put<true>(part, RK_CHANGED, tid, changed);
         SMPC_END
-        id_block_reduce<true>(L, sm, 1, SC_SAME);
-        if (sc[SC_SAME] == 0.0)
+        val = vt;
+        if (id_red_get<true>(part, RK_CHANGED) == 0.0)
           break;
       }
       if (sc[SC_BAD] != 0.0)
@@ -1348,10 +1356,9 @@ namespace smpc
           ps = fmax(ps, fabs(s));
         }
       }
-      part[tid] = pr;
-      part[ID_THREADS + tid] = ps;
+      id_red_put<true>(part, RK_PR, tid, pr);
+      id_red_put<true>(part, RK_PS, tid, ps);
       SMPC_END
-      id_block_reduce<true>(L, sm, 2, SC_K0);
       SMPC_PAR(tid)
       const double * A = sm + L.o_A;
       const double * Cm = sm + L.o_C;
@@ -1368,12 +1375,11 @@ namespace smpc
         dr = fmax(dr, fabs(g[i] + hx[i] + ay + cz));
         ds = fmax(ds, fmax(fmax(fabs(hx[i]), fabs(g[i])), fmax(fabs(ay), fabs(cz))));
       }
-      part[tid] = dr;
-      part[ID_THREADS + tid] = ds;
+      id_red_put<true>(part, RK_DR, tid, dr);
+      id_red_put<true>(part, RK_DS, tid, ds);
       SMPC_END
-      id_block_reduce<true>(L, sm, 2, SC_K0 + 2);
-      pres = sc[SC_K0] / sc[SC_K0 + 1];
-      dres = sc[SC_K0 + 2] / sc[SC_K0 + 3];
+      pres = id_red_get<true>(part, RK_PR) / id_red_get<true>(part, RK_PS);
+      dres = id_red_get<true>(part, RK_DR) / id_red_get<true>(part, RK_DS);
       if (pres <= ID_QP_EPS && dres <= ID_QP_EPS)
       {
         status = 0;
