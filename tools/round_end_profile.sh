@@ -17,3 +17,13 @@ done
 # 8 x B200 (gpurun --gpus 8): weak scaling and the north-star case
 # python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline
 # python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --total 4096 --steps 20 --warmup 5 --no-cpu-baseline
+# the inverse-dynamics controllers (profiles/r02ar_*): bench lines, cold-solve probe, ncu capture + summary, the chained control stack
+python bench.py --config id > gpurun_out/${R}_bench_id.json 2> gpurun_out/${R}_id.err
+python bench.py --config id --impl reference > gpurun_out/${R}_bench_id_reference.json 2>> gpurun_out/${R}_id.err
+python bench.py --config id --batch 512 --no-cpu-baseline > gpurun_out/${R}_bench_id_b512.json 2>> gpurun_out/${R}_id.err
+python tools/id_bench_probe.py > gpurun_out/${R}_id_probe_cold.txt 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_id_solve -s 2 -c 1 -f -o gpurun_out/${R}_ncu_id_b1024 python tools/id_ncu_probe.py 1024 > gpurun_out/${R}_ncu_id.log 2>&1
+# (here, after the report came back: python tools/id_ncu_summary.py gpurun_out/${R}_ncu_id_b1024.ncu-rep > profiles/${R}_ncu_id_summary.txt)
+for n in 1 256 512; do python tools/control_stack.py $n 100 > gpurun_out/${R}_control_stack_$n.json 2>> gpurun_out/${R}_id.err; done
+# python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --config id --no-cpu-baseline
+
