@@ -506,3 +506,25 @@ def test_control_stack_mpc_tick_plus_ten_id_periods():
         out[name] = hist
     for (qc, tc), (qo, to) in zip(out["cuda"][:3], out["orc"]):
         assert relerr(qc, qo) <= 1e-7 and relerr(tc, to, max(np.abs(to).max(), 1.0)) <= 1e-6
+
+
+def test_infeasible_qp_is_reported_not_hidden():
+    """the biped in single support with the stance contact as a HARD constraint: no acceleration / force pair satisfies the
+    floating-base dynamics, the contact rows and the stance foot's cone together. The oracle and the emulated CUDA routine both stop
+    with status 1 and a primal residual far above the tolerance (the reference asserts HQP_STATUS_OPTIMAL, kinodynamics-id.cpp:230;
+    the host class throws)"""
+    orc, em = load_oracle(), load_emul()
+    kw = dict(centroidal=1, kp_feet_tracking=5.0, kp_posture=0.1, kp_contact=1.0, w_feet_tracking=1e3, w_posture=1.0, w_contact_force=0.1,
+              contact_motion_equality=1, kp_com=1.0, w_com=1.0, kp_base=1.0, w_base=1.0)
+    ib, m, lim, vmax, eff = make(orc, "orc_id_", "talos", 1, **kw)
+    d = sid.make_desc(m, lim["qmin"], lim["qmax"], vmax, eff, sid.default_settings(**kw), control_dt=DT)
+    com, vcom, pose, fvel, cs, ft = centroidal_targets(m, 1, lift=1)
+    ib.set_target_centroidal(com, vcom, pose, fvel, cs, ft)
+    q, v = np.array(m.q_ref[: m.nq]), np.zeros(m.nv)
+    ib.solve(0.0, q[None], v[None])
+    io = ib.info()[0]
+    assert io.status == 1 and io.prim_res > 1e-7
+    te, ae, fe, ie = np.zeros(m.nv - 6), np.zeros(m.nv), np.zeros((m.nfeet, 12)), sid.IdInfo()
+    rc = em.emul_id_solve(C.byref(m), C.byref(d), None, None, None, _p(com), _p(vcom), _p(pose), _p(fvel),
+                          cs.ctypes.data_as(C.POINTER(C.c_int32)), _p(ft), 0, _p(q), _p(v), _p(te), _p(ae), _p(fe), C.byref(ie), None)
+    assert rc == 0 and ie.status == 1 and ie.prim_res > 1e-7
