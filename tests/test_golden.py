@@ -17,7 +17,8 @@ import numpy as np
 import pytest
 import host_api_utils as hu
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("id_"))  # id_*: the inverse-dynamics fixtures at the end of this file
 # what the north star asks of the real reference; the oracle's own fixtures must reproduce to rounding of libm differences
 TOL = {"simple-mpc": dict(xs=1e-8, us=1e-8, K=1e-8), "oracle": dict(xs=1e-10, us=1e-10, K=1e-9), "cuda": dict(xs=1e-7, us=1e-7, K=1e-6)}
 
@@ -111,3 +112,50 @@ def test_cuda_reproduces_the_golden_vectors(path):
     # against the real reference the north-star tolerance; against the repository's own fixtures the GPU-parity tolerances
     tol = TOL["simple-mpc"] if meta["source"] == "simple-mpc" else dict(xs=1e-6, us=1e-6, K=1e-5)
     assert w["xs"] <= tol["xs"] and w["us"] <= tol["us"] and w["K"] <= tol["K"], (meta["source"], w)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# inverse-dynamics controllers (scripts/dump_golden_id.py)
+# ----------------------------------------------------------------------------------------------------------------------
+ID_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "id_*.npz")))
+# the real reference solves its QP to ProxQP's absolute accuracy of 1e-5; the repo's own fixtures replay along the same warm-started path
+ID_TOL = {"simple-mpc": 1e-4, "cuda": 1e-9}
+
+
+def test_id_goldens_present_or_explained():
+    if not any("_simple-mpc" in os.path.basename(p) for p in ID_GOLDEN):
+        pytest.skip("no inverse-dynamics golden vector from the real simple-mpc: run `pixi run python scripts/dump_golden_id.py "
+                    "--backend reference` in the reference's environment and drop tests/golden/id_*_simple-mpc.npz here (parity unpinned)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ID_GOLDEN, ids=[os.path.basename(p) for p in ID_GOLDEN])
+def test_cuda_reproduces_the_id_golden_vectors(path):
+    """replays the measured states of a golden closed loop through simple_mpc.KinodynamicsID / CentroidalID on the CUDA path"""
+    sm = hu.import_simple_mpc()
+    z = np.load(path, allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    model = rebuild_model(sm, z)
+    model.referenceConfigurations = {meta["reference_configuration"]: np.array(z["q_ref"])}
+    model.lowerPositionLimit, model.upperPositionLimit = z["limit_lower"], z["limit_upper"]
+    model.velocityLimit, model.effortLimit = z["limit_velocity"], z["limit_effort"]
+    mh = sm.RobotModelHandler(model, meta["reference_configuration"], meta["base"])
+    for n in meta["feet"]:
+        if len(meta["feet"]) == 4:
+            mh.addPointFoot(n, meta["base"])
+        else:
+            mh.addQuadFoot(n, meta["base"], np.array([[0.1, 0.075, 0], [-0.1, 0.075, 0], [-0.1, -0.075, 0], [0.1, -0.075, 0]]))
+    settings = sm.CentroidalIDSettings() if meta["kind"] == "centroidal" else sm.KinodynamicsIDSettings()
+    for k, v in meta["settings"].items():
+        setattr(settings, k, v)
+    ctrl = (sm.CentroidalID if meta["kind"] == "centroidal" else sm.KinodynamicsID)(mh, meta["control_dt"], settings)
+    if meta["kind"] == "centroidal":
+        poses = [sm.SE3(z["target_poses_R"][i], z["target_poses_p"][i]) for i in range(len(meta["feet"]))]
+        ctrl.setTarget(z["target_com"], np.zeros(3), poses, [np.zeros(6)] * len(poses), [bool(c) for c in z["target_contact"]],
+                       [np.array(f) for f in z["target_forces"]])
+    tol = ID_TOL[meta["source"]]
+    worst = 0.0
+    for i in range(z["q"].shape[0]):
+        tau = np.array(ctrl.solve(i * meta["control_dt"], np.array(z["q"][i]), np.array(z["v"][i])))
+        worst = max(worst, float(np.abs(tau - z["tau"][i]).max() / max(np.abs(z["tau"][i]).max(), 1.0)))
+    assert worst <= tol, (meta["scenario"], meta["source"], worst)
